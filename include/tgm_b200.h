@@ -1,0 +1,167 @@
+/*
+ * tgm_b200.h -- C ABI of the B200-native temporal neighbor-sampling engine.
+ *
+ * The reference (tgm-team/tgm @ 5183dc9) is pure Python and has no FFI of its own; its plug-in
+ * points for this path are Python protocols.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference tree).  The Python face that TGM
+ * calls (DGStorageBase subclass, DGHook object) lives in tgm_b200/ and binds this library with
+ * ctypes; INTEGRATION.md shows the stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns TGM_OK (0) or a negative TGM_ERR_* code; tgm_last_error() returns a
+ *     thread-local message for the last failure on the calling thread.
+ *   - plain pointers and sizes only.  Unless a parameter says "host", array arguments are DEVICE
+ *     pointers owned by the caller and must stay valid until the stream operation completes.
+ *   - all work is stream-ordered on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream); no call synchronises the device except *_create / *_destroy / *_host.
+ *   - handles are not thread-safe; one handle = one device.
+ *   - node ids are int32, timestamps int64, edge features float32 (tgm/data/dg_data.py:129-161).
+ *   - TGM_PADDED_NODE_ID (-1) marks padded neighbour slots (tgm/constants.py:3); padded
+ *     timestamps are 0 and padded features 0.0f (tgm/hooks/neighbors/recency.py:317-319).
+ */
+#ifndef TGM_B200_H
+#define TGM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGM_OK 0
+#define TGM_ERR_INVALID (-1)   /* bad argument */
+#define TGM_ERR_CUDA (-2)      /* CUDA runtime error (message has the cudaError string) */
+#define TGM_ERR_NO_DEVICE (-3) /* handle was created without a device (metadata-only store) */
+#define TGM_ERR_OOM (-4)
+
+#define TGM_PADDED_NODE_ID (-1)
+
+#define TGM_MEM_DEVICE 0 /* array arguments are device pointers, adopted as zero-copy views */
+#define TGM_MEM_HOST 1   /* array arguments are host pointers, the library uploads and owns copies */
+
+typedef struct tgm_store tgm_store;     /* device-resident time-sorted COO edge store */
+typedef struct tgm_recency tgm_recency; /* per-node ring buffers (stateful sampler) */
+typedef struct tgm_csr tgm_csr;         /* per-node chronological adjacency (stateless sampler) */
+typedef void *tgm_stream;               /* cudaStream_t */
+
+const char *tgm_last_error(void);
+int tgm_version(void);
+/* number of visible CUDA devices (0 on a CPU-only host; never an error). */
+int tgm_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Edge store.  Replaces DGStorageArrayBackend's edge arrays and its slice lookup:
+ *   tgm/core/_storage/backends/array_backend.py:15-21   (__init__ holding DGData)
+ *   tgm/core/_storage/backends/array_backend.py:301-321 (_binary_search)
+ *   tgm/core/_storage/backends/array_backend.py:57-68, 259-268 (get_edges / get_edge_x)
+ * The reference rebuilds O(E) boolean masks per batch; here a slice is two binary searches on a
+ * host mirror of the timestamps and a pointer offset into the device slabs.
+ *
+ * src,dst: int32[E]; t: int64[E] non-decreasing; edge_x: float32[E*D] row-major or NULL (D=0).
+ * mem = TGM_MEM_HOST: pointers are host memory, uploaded on `device`.
+ * mem = TGM_MEM_DEVICE: pointers are device memory on `device`, adopted without a copy; t_host
+ *       may pass a host copy of t (else it is read back once).
+ * device = -1 (TGM_MEM_HOST only): metadata-only store; bounds work, slabs/kernels do not.
+ */
+int tgm_store_create(tgm_store **out, const int32_t *src, const int32_t *dst, const int64_t *t,
+                     const float *edge_x, int64_t E, int32_t D, int32_t num_nodes, int device,
+                     int mem, const int64_t *t_host);
+void tgm_store_destroy(tgm_store *);
+int tgm_store_info(const tgm_store *, int64_t *E, int32_t *D, int32_t *num_nodes, int *device);
+/* [lb, ub) edge-index bounds of a slice; == _binary_search (array_backend.py:301-321):
+ * lb = first index with t >= t_lo (has_lo=0: 0), ub = first index with t > t_hi (has_hi=0: E),
+ * both clamped into [idx_lo, idx_hi] (idx_lo < 0: 0, idx_hi < 0: E). */
+int tgm_store_bounds(const tgm_store *, int64_t t_lo, int has_lo, int64_t t_hi, int has_hi,
+                     int64_t idx_lo, int64_t idx_hi, int64_t *lb, int64_t *ub);
+/* zero-copy device views of edges [lb, ub); *x is NULL when the store has no features. */
+int tgm_store_slab(const tgm_store *, int64_t lb, int64_t ub, const int32_t **src,
+                   const int32_t **dst, const int64_t **t, const float **x);
+
+/* ------------------------------------------------------------------------------------------
+ * Stateful recency sampler: per-node ring buffers.  Replaces RecencyNeighborHook's state and
+ * its two per-batch operations (tgm/hooks/neighbors/recency.py):
+ *   :93-97,:410-416  state  ids int32[N,B], times int64[N,B], feats f32[N,B,D], write_pos int32[N]
+ *   :111-117         reset_state            -> tgm_recency_reset
+ *   :239-321         _get_recency_neighbors -> tgm_recency_query
+ *   :323-399         _update                -> tgm_recency_update
+ * B = max(num_nbrs) (:73).
+ */
+int tgm_recency_create(tgm_recency **out, int32_t num_nodes, int32_t B, int32_t D, int device);
+void tgm_recency_destroy(tgm_recency *);
+int tgm_recency_reset(tgm_recency *, tgm_stream stream);
+/* For each seed (v, tq): among the ring of v in chronological order find the right-most entry
+ * with id != -1 and time < tq, and return the k entries ending there, right-aligned and
+ * left-padded with (-1, 0, 0.0f).  seeds int32[S] (negative ids wrap like torch indexing, so the
+ * padded id -1 reads row N-1), tq int64[S]; out_nid int32[S*k], out_t int64[S*k],
+ * out_x float32[S*k*D] (may be NULL when D == 0).  1 <= k <= B. */
+int tgm_recency_query(const tgm_recency *, const int32_t *seeds, const int64_t *tq, int64_t S,
+                      int32_t k, int32_t *out_nid, int64_t *out_t, float *out_x,
+                      tgm_stream stream);
+/* Push one batch of edges: entries (src->dst) then, unless directed, (dst->src); per node ordered
+ * by (time, position in that concatenation); the last B per node are written at
+ * (write_pos + j) % B and write_pos advances by the number written.  x float32[Eb*D] or NULL
+ * (zeros, recency.py:325-329). */
+int tgm_recency_update(tgm_recency *, const int32_t *src, const int32_t *dst, const int64_t *t,
+                       const float *x, int64_t Eb, int directed, tgm_stream stream);
+/* device pointers to the live state (for checkpointing / inspection); any may be NULL. */
+int tgm_recency_state(const tgm_recency *, int32_t **ids, int64_t **times, float **feats,
+                      int32_t **write_pos);
+
+/* ------------------------------------------------------------------------------------------
+ * Stateless recency sampler over a per-node chronological adjacency ("CSR").  Same answers as
+ * the ring sampler driven batch by batch (recency.py:119-171), but one launch serves the seeds
+ * of thousands of loader batches: the history a batch may see is encoded by an edge-index cut.
+ *
+ * Built for one loader geometry: batches are [e_start + i*batch_size, e_start + (i+1)*batch_size)
+ * (tgm/data/loader.py:136-148,158-160).  Entries of a node are ordered (batch, time, side, edge)
+ * with side 0 = node is the edge source -- the order in which the reference's stable sort
+ * (recency.py:347-349) appends them to the ring.
+ * colocate_x != 0 additionally stores the feature rows in adjacency order so a seed's window is
+ * one contiguous read (costs 2*E*D*4 bytes of HBM when undirected).
+ */
+int tgm_csr_build(tgm_csr **out, const tgm_store *, int64_t e_start, int64_t batch_size,
+                  int directed, int colocate_x, tgm_stream stream);
+void tgm_csr_destroy(tgm_csr *);
+int tgm_csr_info(const tgm_csr *, int64_t *num_entries, int64_t *e_start, int64_t *batch_size,
+                 int *directed, int *colocate_x);
+/* General seeds.  Seed i may only see entries whose edge index is < cut[i / cut_group]
+ * (cut = first edge of the loader batch the seed belongs to; hop h>0 seeds inherit the cut of
+ * their root, hence cut_group = k of the previous hops multiplied).  Among those the window is
+ * the last B; the rest is tgm_recency_query's rule.  seeds may contain -1 (all-padding row). */
+int tgm_csr_sample(const tgm_csr *, const int32_t *seeds, const int64_t *tq, const int64_t *cut,
+                   int64_t cut_group, int64_t S, int32_t B, int32_t k, int32_t *out_nid,
+                   int64_t *out_t, float *out_x, tgm_stream stream);
+/* Fast path for hop-0 seeds that are the endpoints of the stream edges [e_lo, e_hi) themselves
+ * (seed_nodes_keys = ['edge_src','edge_dst'], seed_times_keys = ['edge_time','edge_time']):
+ * no seed arrays are read and the history cut comes from a prebuilt per-edge anchor table.
+ * e_lo must sit on a batch boundary.  Rows are laid out as the concatenation of the per-batch
+ * hook outputs: batch j (nb edges) owns rows [2*(lb_j - e_lo), 2*(lb_j - e_lo) + 2*nb), src seeds
+ * first, then dst seeds (recency.py:181-233 with the keys above). */
+int tgm_csr_sample_edges(const tgm_csr *, int64_t e_lo, int64_t e_hi, int32_t B, int32_t k,
+                         int32_t *out_nid, int64_t *out_t, float *out_x, tgm_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Frontier compaction (hop h+1 seeds = flatten(hop h), recency.py:141-143; the non-padded
+ * subset is also what DeduplicationHook keeps, tgm/hooks/dedup.py:44-48).
+ * Writes the indices i with nid[i] != -1 in increasing order to out_idx (capacity n) and their
+ * number to *out_count (device int64). */
+int tgm_frontier_compact(const int32_t *nid, int64_t n, int64_t *out_idx, int64_t *out_count,
+                         tgm_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Aggregation over sampled neighbours.
+ * masked mean (examples/linkproppred/graphmixer.py:131-135):
+ *   out[s,:] = sum_c z[s,c,:]*[nid[s,c] != -1] / max(1, #valid), accumulated left to right in
+ *   fp32.  z float32[S*k*D], nid int32[S*k], out float32[S*D]. */
+int tgm_masked_mean(const float *z, const int32_t *nid, int64_t S, int32_t k, int32_t D,
+                    float *out, tgm_stream stream);
+/* Time2Vec (tgm/nn/modules/time_encoding.py:22-24): out[i,j] = cosf(float(dt[i]) * w[j] + b[j])
+ * with one rounding for the product and one for the sum (no FMA contraction), full-range cosf.
+ * dt int64[n], w,b float32[d], out float32[n*d]. */
+int tgm_time2vec(const int64_t *dt, int64_t n, const float *w, const float *b, int32_t d,
+                 float *out, tgm_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGM_B200_H */

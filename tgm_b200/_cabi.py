@@ -1,0 +1,120 @@
+"""ctypes binding of the C ABI declared in include/tgm_b200.h.
+
+The product path has no CPU fallback: if the shared library is missing this module raises at
+import, and every device entry point raises `TGMNativeError` when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libtgm_b200.so')
+
+TGM_MEM_DEVICE, TGM_MEM_HOST = 0, 1
+
+
+class TGMNativeError(RuntimeError):
+    """A C-ABI call returned a negative status."""
+
+    def __init__(self, code: int, message: str) -> None:
+        super().__init__(f'[tgm_b200 rc={code}] {message}')
+        self.code = code
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f'{LIB_PATH} is missing. Build it with `python -m tgm_b200.build` (needs nvcc); '
+        'tgm_b200 has no CPU fallback.'
+    )
+
+lib = ctypes.CDLL(LIB_PATH)
+
+# every symbol include/tgm_b200.h declares, with its signature (checked by tests/test_cabi.py)
+SIGNATURES = {
+    'tgm_last_error': (c_char_p, []),
+    'tgm_version': (c_int, []),
+    'tgm_device_count': (c_int, []),
+    'tgm_store_create': (c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int64, c_int32, c_int32, c_int, c_int, c_void_p]),
+    'tgm_store_destroy': (None, [c_void_p]),
+    'tgm_store_info': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int32), POINTER(c_int32),
+                               POINTER(c_int)]),
+    'tgm_store_bounds': (c_int, [c_void_p, c_int64, c_int, c_int64, c_int, c_int64, c_int64,
+                                 POINTER(c_int64), POINTER(c_int64)]),
+    'tgm_store_slab': (c_int, [c_void_p, c_int64, c_int64, POINTER(c_void_p), POINTER(c_void_p),
+                               POINTER(c_void_p), POINTER(c_void_p)]),
+    'tgm_recency_create': (c_int, [POINTER(c_void_p), c_int32, c_int32, c_int32, c_int]),
+    'tgm_recency_destroy': (None, [c_void_p]),
+    'tgm_recency_reset': (c_int, [c_void_p, c_void_p]),
+    'tgm_recency_query': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
+    'tgm_recency_update': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                   c_int, c_void_p]),
+    'tgm_recency_state': (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p),
+                                  POINTER(c_void_p), POINTER(c_void_p)]),
+    'tgm_csr_build': (c_int, [POINTER(c_void_p), c_void_p, c_int64, c_int64, c_int, c_int,
+                              c_void_p]),
+    'tgm_csr_destroy': (None, [c_void_p]),
+    'tgm_csr_info': (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64),
+                             POINTER(c_int), POINTER(c_int)]),
+    'tgm_csr_sample': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+                               c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'tgm_csr_sample_edges': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p,
+                                     c_void_p, c_void_p, c_void_p]),
+    'tgm_frontier_compact': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    'tgm_masked_mean': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p,
+                                c_void_p]),
+    'tgm_time2vec': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p,
+                             c_void_p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error() -> str:
+    msg = lib.tgm_last_error()
+    return msg.decode('utf-8', 'replace') if msg else ''
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise TGMNativeError(rc, last_error())
+
+
+def device_count() -> int:
+    return int(lib.tgm_device_count())
+
+
+def require_device() -> None:
+    if device_count() < 1:
+        raise TGMNativeError(-3, 'no CUDA device visible: tgm_b200 has no CPU fallback')
+
+
+def ptr(t) -> int | None:
+    """data_ptr of a torch tensor (or None)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream(device) -> int:
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _DevicePointer:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can alias it."""
+
+    def __init__(self, ptr_value: int, shape, typestr: str) -> None:
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr,
+                                         'data': (int(ptr_value), False), 'version': 2}
+
+
+def device_view(ptr_value: int, shape, dtype, device):
+    """Zero-copy torch view of library-owned device memory (valid while the handle lives)."""
+    import torch
+    typestr = {torch.int32: '<i4', torch.int64: '<i8', torch.float32: '<f4'}[dtype]
+    return torch.as_tensor(_DevicePointer(ptr_value, shape, typestr), device=device)

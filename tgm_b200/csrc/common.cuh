@@ -1,0 +1,91 @@
+// Shared helpers for the tgm_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+
+#include "../../include/tgm_b200.h"
+
+namespace tgm {
+
+constexpr int kWarp = 32;
+constexpr int kSmCount = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+// RAII device guard: every entry point runs on the handle's device and restores the caller's.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    target = dev;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != target) cudaSetDevice(prev);
+  }
+  int target = -1;
+};
+
+inline cudaStream_t as_stream(tgm_stream s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Grid size for a grid-stride kernel: enough CTAs for `work_items`, capped at a whole number of
+// waves over the 148 SMs.
+inline int grid_for(int64_t work_items, int items_per_cta, int ctas_per_sm) {
+  int64_t need = (work_items + items_per_cta - 1) / items_per_cta;
+  int64_t cap = int64_t(kSmCount) * ctas_per_sm;
+  if (need < 1) need = 1;
+  return int(need < cap ? need : cap);
+}
+
+}  // namespace tgm
+
+#define TGM_CUDA(expr)                                                        \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess) return tgm::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define TGM_REQUIRE(cond, msg)                                  \
+  do {                                                          \
+    if (!(cond)) return tgm::fail(TGM_ERR_INVALID, (msg));      \
+  } while (0)
+
+#define TGM_LAUNCH_CHECK() TGM_CUDA(cudaGetLastError())
+
+// ---- device helpers ------------------------------------------------------------------------
+namespace tgm {
+
+// One adjacency / ring entry as it travels through the sampler: 16 bytes, one 128-bit load.
+struct __align__(16) Entry {
+  int32_t nbr;  // neighbour node id
+  int32_t eid;  // edge index in the store (feature row)
+  int64_t t;    // edge timestamp
+};
+static_assert(sizeof(Entry) == 16, "Entry must be one 16-byte vector");
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// streaming 128-bit load that does not allocate in L1 (data is touched once)
+__device__ __forceinline__ float4 ldg_stream_f4(const float4 *p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream_f4(float4 *p, const float4 &v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+}  // namespace tgm

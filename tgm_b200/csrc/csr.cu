@@ -1,0 +1,492 @@
+// Stateless recency sampler over a per-node chronological adjacency.
+//
+// Same answers as RecencyNeighborHook driven batch by batch (reference tgm-team/tgm @ 5183dc9,
+// tgm/hooks/neighbors/recency.py:119-171, :239-321, :323-399), restated without mutable state
+// (SURVEY.md Appendix A.2): the ring of node v at the time batch b queries it holds the last B
+// entries of v's history restricted to batches < b, and that history, ordered the way the
+// reference's stable sort appends it -- (batch, time, side, edge) -- is immutable.  So it is
+// built once per loader geometry, and one launch then serves the seeds of thousands of loader
+// batches: per seed an edge-index cut selects the visible prefix, the window is its last B
+// entries, the time test and the right-aligned k-gather follow.
+//
+// HBM layout (E edges, n = 2E entries when undirected):
+//   entries  Entry[n]      16 B each {nbr, eid, t}, grouped by node, chronological per node
+//   rowptr   int64[N+1]
+//   anchors  uint2[2][E]   per stream edge and endpoint: {first entry of the endpoint's list that
+//                          belongs to the edge's own batch or later, #entries before it}
+//                          -> hop-0 seeds that are edge endpoints need no search at all
+//   xrows    float[n, D]   optional: feature rows in adjacency order (window = contiguous read)
+#include <cub/cub.cuh>
+
+#include <new>
+
+#include "store.cuh"
+
+using namespace tgm;
+
+struct tgm_csr {
+  int device = -1;
+  const tgm_store *store = nullptr;  // borrowed: must outlive the csr
+  int64_t e_start = 0, Ew = 0, bs = 1, n = 0;
+  int32_t N = 0, D = 0;
+  int directed = 0, colocate = 0;
+  Entry *entries = nullptr;
+  int64_t *rowptr = nullptr;
+  uint2 *anchors = nullptr;  // [2][Ew]
+  float *xrows = nullptr;    // [n, D] when colocate
+  ~tgm_csr() {
+    if (device >= 0) {
+      DeviceGuard g(device);
+      cudaFree(entries);
+      cudaFree(rowptr);
+      cudaFree(anchors);
+      cudaFree(xrows);
+    }
+  }
+};
+
+namespace {
+
+constexpr uint32_t kNoRow = 0xFFFFFFFFu;
+
+// ---- build -----------------------------------------------------------------------------------
+// Position of every entry in the global (batch, time, side, edge) order.  Inside one batch the
+// edges sharing a timestamp form a run [rs, re); its side-0 entries precede its side-1 entries.
+__global__ void csr_keys_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                                const int64_t *__restrict__ t, int64_t Ew, int64_t bs, int directed,
+                                uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  for (int64_t l = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; l < Ew;
+       l += int64_t(gridDim.x) * blockDim.x) {
+    if (directed) {
+      keys[l] = uint32_t(src[l]);
+      vals[l] = uint32_t(l) << 1;
+      continue;
+    }
+    const int64_t bl = (l / bs) * bs;
+    const int64_t bh = bl + bs < Ew ? bl + bs : Ew;
+    const int64_t te = t[l];
+    int64_t lo = bl, hi = l;  // first index in [bl, l] with t == te
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (t[mid] < te) lo = mid + 1; else hi = mid;
+    }
+    const int64_t rs = lo;
+    lo = l + 1, hi = bh;  // first index in (l, bh] with t > te
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (t[mid] <= te) lo = mid + 1; else hi = mid;
+    }
+    const int64_t re = lo;
+    const int64_t p0 = 2 * rs + (l - rs);
+    const int64_t p1 = 2 * rs + (re - rs) + (l - rs);
+    keys[p0] = uint32_t(src[l]);
+    vals[p0] = uint32_t(l) << 1;
+    keys[p1] = uint32_t(dst[l]);
+    vals[p1] = (uint32_t(l) << 1) | 1u;
+  }
+}
+
+__global__ void csr_rowptr_kernel(const uint32_t *__restrict__ keys, int64_t n, int32_t N,
+                                  int64_t *__restrict__ rowptr) {
+  for (int64_t v = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; v <= N;
+       v += int64_t(gridDim.x) * blockDim.x) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (keys[mid] < uint32_t(v)) lo = mid + 1; else hi = mid;
+    }
+    rowptr[v] = lo;
+  }
+}
+
+__global__ void csr_entries_kernel(const uint32_t *__restrict__ vals, int64_t n,
+                                   const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                                   const int64_t *__restrict__ t, int64_t e_start,
+                                   Entry *__restrict__ entries) {
+  for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n;
+       j += int64_t(gridDim.x) * blockDim.x) {
+    const uint32_t val = vals[j];
+    const int64_t l = val >> 1;
+    Entry en;
+    en.nbr = (val & 1u) ? src[l] : dst[l];
+    en.eid = int32_t(e_start + l);
+    en.t = t[l];
+    entries[j] = en;
+  }
+}
+
+// first index in [lo, hi) whose entry belongs to an edge >= cut (monotone: batch-major order)
+__device__ __forceinline__ int64_t lower_bound_eid(const Entry *__restrict__ entries, int64_t lo,
+                                                   int64_t hi, int64_t cut) {
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (int64_t(entries[mid].eid) < cut) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void csr_anchor_kernel(const Entry *__restrict__ entries,
+                                  const int64_t *__restrict__ rowptr,
+                                  const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                                  int64_t Ew, int64_t bs, int64_t e_start, int32_t N,
+                                  uint2 *__restrict__ anchors) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < 2 * Ew;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int side = i >= Ew;
+    const int64_t l = side ? i - Ew : i;
+    const int32_t v = side ? dst[l] : src[l];
+    uint2 a = make_uint2(0u, 0u);
+    if (v >= 0 && v < N) {
+      const int64_t lo = rowptr[v], hi = rowptr[v + 1];
+      const int64_t cut = e_start + (l / bs) * bs;
+      const int64_t pos = lower_bound_eid(entries, lo, hi, cut);
+      a = make_uint2(uint32_t(pos), uint32_t(pos - lo));
+    }
+    anchors[i] = a;
+  }
+}
+
+template <bool VEC4>
+__global__ void csr_gather_x_kernel(const Entry *__restrict__ entries, int64_t n,
+                                    const float *__restrict__ x, int D, float *__restrict__ xrows) {
+  if (VEC4) {
+    const int D4 = D >> 2;
+    const int64_t total = n * D4;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x);
+    float4 *o4 = reinterpret_cast<float4 *>(xrows);
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += int64_t(gridDim.x) * blockDim.x) {
+      const int64_t j = i / D4;
+      const int d = int(i - j * D4);
+      o4[i] = __ldg(x4 + int64_t(entries[j].eid) * D4 + d);
+    }
+  } else {
+    const int64_t total = n * D;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += int64_t(gridDim.x) * blockDim.x) {
+      const int64_t j = i / D;
+      const int d = int(i - j * D);
+      xrows[i] = __ldg(x + int64_t(entries[j].eid) * D + d);
+    }
+  }
+}
+
+// ---- sample ----------------------------------------------------------------------------------
+constexpr int kSampleThreads = 256;
+
+// The part shared by both entry points: given the visible window [wstart, wstart + nwin) of a
+// seed's adjacency, apply the time test and emit the right-aligned k-gather (recency.py:267-319).
+template <bool VEC4, bool COLOC>
+__device__ __forceinline__ void emit_window(const Entry *__restrict__ entries,
+                                            const float *__restrict__ xsrc, int D, int64_t wstart,
+                                            int nwin, int64_t q, int k, int64_t s,
+                                            int32_t *__restrict__ out_nid,
+                                            int64_t *__restrict__ out_t, float *__restrict__ out_x,
+                                            uint32_t *my, int lane) {
+  int last = -1;  // right-most window position with time < tq
+  for (int base = 0; base < nwin; base += 32) {
+    const int j = base + lane;
+    const bool ok = (j < nwin) && (entries[wstart + j].t < q);
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (m) last = base + 31 - __clz(m);
+  }
+  for (int c = lane; c < k; c += 32) {
+    const int p = last - (k - 1 - c);
+    int32_t id = TGM_PADDED_NODE_ID;
+    int64_t tt = 0;
+    uint32_t row = kNoRow;
+    if (p >= 0) {
+      const Entry en = entries[wstart + p];
+      id = en.nbr;
+      tt = en.t;
+      row = COLOC ? uint32_t(wstart + p) : uint32_t(en.eid);
+    }
+    my[c] = row;
+    out_nid[s * k + c] = id;
+    out_t[s * k + c] = tt;
+  }
+  __syncwarp();
+  if (D > 0) {
+    if (VEC4) {
+      const int D4 = D >> 2;
+      const float4 *x4 = reinterpret_cast<const float4 *>(xsrc);
+      float4 *o4 = reinterpret_cast<float4 *>(out_x) + s * int64_t(k) * D4;
+      const int total = k * D4;
+      for (int i = lane; i < total; i += 32) {
+        const int c = i / D4, d = i - c * D4;
+        const uint32_t row = my[c];
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row != kNoRow) val = ldg_stream_f4(x4 + int64_t(row) * D4 + d);
+        stg_stream_f4(o4 + i, val);
+      }
+    } else {
+      float *o = out_x + s * int64_t(k) * D;
+      const int total = k * D;
+      for (int i = lane; i < total; i += 32) {
+        const int c = i / D, d = i - c * D;
+        const uint32_t row = my[c];
+        o[i] = row != kNoRow ? __ldg(xsrc + int64_t(row) * D + d) : 0.f;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <bool VEC4, bool COLOC>
+__global__ void __launch_bounds__(kSampleThreads)
+csr_sample_kernel(const Entry *__restrict__ entries, const int64_t *__restrict__ rowptr,
+                  const float *__restrict__ xsrc, int32_t N, int D,
+                  const int32_t *__restrict__ seeds, const int64_t *__restrict__ tq,
+                  const int64_t *__restrict__ cut, int64_t cut_group, int64_t S, int B, int k,
+                  int32_t *__restrict__ out_nid, int64_t *__restrict__ out_t,
+                  float *__restrict__ out_x) {
+  extern __shared__ uint32_t s_rows[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  uint32_t *my = s_rows + warp * k;
+  for (int64_t s = int64_t(blockIdx.x) * wpb + warp; s < S; s += int64_t(gridDim.x) * wpb) {
+    const int32_t v = seeds[s];
+    int64_t wstart = 0;
+    int nwin = 0;
+    if (v >= 0 && v < N) {  // a padded seed (-1) always yields an all-padding row
+      const int64_t lo = rowptr[v], hi = rowptr[v + 1];
+      const int64_t pos = lower_bound_eid(entries, lo, hi, cut[s / cut_group]);
+      wstart = pos - B > lo ? pos - B : lo;
+      nwin = int(pos - wstart);
+    }
+    emit_window<VEC4, COLOC>(entries, xsrc, D, wstart, nwin, tq[s], k, s, out_nid, out_t, out_x,
+                             my, lane);
+  }
+}
+
+template <bool VEC4, bool COLOC>
+__global__ void __launch_bounds__(kSampleThreads)
+csr_sample_edges_kernel(const Entry *__restrict__ entries, const uint2 *__restrict__ anchors,
+                        const float *__restrict__ xsrc, const int64_t *__restrict__ t, int D,
+                        int64_t Ew, int64_t bs, int64_t l_lo, int64_t l_hi, int B, int k,
+                        int32_t *__restrict__ out_nid, int64_t *__restrict__ out_t,
+                        float *__restrict__ out_x) {
+  extern __shared__ uint32_t s_rows[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  uint32_t *my = s_rows + warp * k;
+  const int64_t S = 2 * (l_hi - l_lo);
+  for (int64_t s = int64_t(blockIdx.x) * wpb + warp; s < S; s += int64_t(gridDim.x) * wpb) {
+    // row s -> (edge, endpoint): batch jb owns rows [2*bs*jb, ...), src seeds then dst seeds
+    const int64_t jb = s / (2 * bs);
+    const int64_t bstart = l_lo + jb * bs;
+    const int64_t nb = l_hi - bstart < bs ? l_hi - bstart : bs;
+    const int64_t rr = s - jb * 2 * bs;
+    const int side = rr >= nb;
+    const int64_t l = bstart + (side ? rr - nb : rr);
+    const uint2 a = anchors[side ? Ew + l : l];
+    const int nwin = a.y < uint32_t(B) ? int(a.y) : B;
+    const int64_t wstart = int64_t(a.x) - nwin;
+    emit_window<VEC4, COLOC>(entries, xsrc, D, wstart, nwin, t[l], k, s, out_nid, out_t, out_x, my,
+                             lane);
+  }
+}
+
+int bits_for(uint32_t max_value) {
+  int b = 1;
+  while (b < 32 && (max_value >> b) != 0) ++b;
+  return b;
+}
+
+}  // namespace
+
+extern "C" int tgm_csr_build(tgm_csr **out, const tgm_store *store, int64_t e_start,
+                             int64_t batch_size, int directed, int colocate_x, tgm_stream stream) {
+  TGM_REQUIRE(out != nullptr, "tgm_csr_build: out is NULL");
+  *out = nullptr;
+  TGM_REQUIRE(store != nullptr, "tgm_csr_build: store is NULL");
+  if (store->device < 0) return fail(TGM_ERR_NO_DEVICE, "tgm_csr_build: metadata-only store");
+  TGM_REQUIRE(batch_size > 0, "tgm_csr_build: batch_size must be > 0");
+  TGM_REQUIRE(e_start >= 0 && e_start <= store->E, "tgm_csr_build: e_start outside [0, E]");
+  TGM_REQUIRE(store->num_nodes > 0, "tgm_csr_build: store has no nodes");
+  DeviceGuard g(store->device);
+  if (!g.ok) return fail(TGM_ERR_CUDA, "tgm_csr_build: cannot select device");
+  cudaStream_t st = as_stream(stream);
+
+  tgm_csr *c = new (std::nothrow) tgm_csr();
+  if (!c) return fail(TGM_ERR_OOM, "tgm_csr_build: host allocation failed");
+  c->device = store->device;
+  c->store = store;
+  c->e_start = e_start;
+  c->Ew = store->E - e_start;
+  c->bs = batch_size;
+  c->directed = directed ? 1 : 0;
+  c->N = store->num_nodes;
+  c->D = store->D;
+  c->n = directed ? c->Ew : 2 * c->Ew;
+  c->colocate = (colocate_x && c->D > 0) ? 1 : 0;
+  const int64_t n = c->n, Ew = c->Ew;
+
+  uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr;
+  void *cub_tmp = nullptr;
+  auto cleanup_tmp = [&]() {
+    cudaFree(keys_a);
+    cudaFree(keys_b);
+    cudaFree(vals_a);
+    cudaFree(vals_b);
+    cudaFree(cub_tmp);
+  };
+  auto bail = [&](int code) {
+    cleanup_tmp();
+    delete c;
+    return code;
+  };
+#define CSR_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) return bail(cuda_fail(_e, #expr, __FILE__, __LINE__));   \
+  } while (0)
+
+  CSR_CUDA(cudaMalloc(&c->rowptr, size_t(c->N + 1) * 8));
+  if (n == 0) {
+    CSR_CUDA(cudaMemsetAsync(c->rowptr, 0, size_t(c->N + 1) * 8, st));
+    CSR_CUDA(cudaStreamSynchronize(st));
+    *out = c;
+    return TGM_OK;
+  }
+  const size_t nn = size_t(n);
+  CSR_CUDA(cudaMalloc(&c->entries, nn * sizeof(Entry)));
+  CSR_CUDA(cudaMalloc(&c->anchors, size_t(2 * Ew) * sizeof(uint2)));
+  if (c->colocate) CSR_CUDA(cudaMalloc(&c->xrows, nn * size_t(c->D) * 4));
+  CSR_CUDA(cudaMalloc(&keys_a, nn * 4));
+  CSR_CUDA(cudaMalloc(&keys_b, nn * 4));
+  CSR_CUDA(cudaMalloc(&vals_a, nn * 4));
+  CSR_CUDA(cudaMalloc(&vals_b, nn * 4));
+
+  const int32_t *src = store->src + e_start, *dst = store->dst + e_start;
+  const int64_t *t = store->t + e_start;
+  const int threads = 256;
+  csr_keys_kernel<<<grid_for(Ew, threads, 8), threads, 0, st>>>(src, dst, t, Ew, batch_size,
+                                                                c->directed, keys_a, vals_a);
+  CSR_CUDA(cudaGetLastError());
+
+  // stable LSD radix sort by node id; the input order already is the chronological order
+  const int end_bit = bits_for(uint32_t(c->N - 1));
+  size_t tmp_bytes = 0;
+  CSR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, vals_a, vals_b, n, 0,
+                                           end_bit, st));
+  CSR_CUDA(cudaMalloc(&cub_tmp, tmp_bytes ? tmp_bytes : 1));
+  CSR_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp_bytes, keys_a, keys_b, vals_a, vals_b, n, 0,
+                                           end_bit, st));
+
+  csr_rowptr_kernel<<<grid_for(int64_t(c->N) + 1, threads, 8), threads, 0, st>>>(keys_b, n, c->N,
+                                                                                 c->rowptr);
+  CSR_CUDA(cudaGetLastError());
+  csr_entries_kernel<<<grid_for(n, threads, 8), threads, 0, st>>>(vals_b, n, src, dst, t, e_start,
+                                                                  c->entries);
+  CSR_CUDA(cudaGetLastError());
+  csr_anchor_kernel<<<grid_for(2 * Ew, threads, 8), threads, 0, st>>>(
+      c->entries, c->rowptr, src, dst, Ew, batch_size, e_start, c->N, c->anchors);
+  CSR_CUDA(cudaGetLastError());
+  if (c->colocate) {
+    const bool vec4 = (c->D % 4 == 0) && aligned16(store->x) && aligned16(c->xrows);
+    if (vec4)
+      csr_gather_x_kernel<true><<<grid_for(n * (c->D / 4), threads, 16), threads, 0, st>>>(
+          c->entries, n, store->x, c->D, c->xrows);
+    else
+      csr_gather_x_kernel<false><<<grid_for(n * c->D, threads, 16), threads, 0, st>>>(
+          c->entries, n, store->x, c->D, c->xrows);
+    CSR_CUDA(cudaGetLastError());
+  }
+  CSR_CUDA(cudaStreamSynchronize(st));
+#undef CSR_CUDA
+  cleanup_tmp();
+  *out = c;
+  return TGM_OK;
+}
+
+extern "C" void tgm_csr_destroy(tgm_csr *c) { delete c; }
+
+extern "C" int tgm_csr_info(const tgm_csr *c, int64_t *num_entries, int64_t *e_start,
+                            int64_t *batch_size, int *directed, int *colocate_x) {
+  TGM_REQUIRE(c != nullptr, "tgm_csr_info: csr is NULL");
+  if (num_entries) *num_entries = c->n;
+  if (e_start) *e_start = c->e_start;
+  if (batch_size) *batch_size = c->bs;
+  if (directed) *directed = c->directed;
+  if (colocate_x) *colocate_x = c->colocate;
+  return TGM_OK;
+}
+
+namespace {
+struct SampleCfg {
+  bool vec4, coloc;
+  const float *xsrc;
+  int grid;
+  size_t smem;
+};
+int sample_cfg(const tgm_csr *c, const char *who, int64_t S, int32_t B, int32_t k, float *out_x,
+               SampleCfg *cfg) {
+  if (!(B >= 1)) return fail(TGM_ERR_INVALID, std::string(who) + ": B must be >= 1");
+  if (!(k >= 1 && k <= B)) return fail(TGM_ERR_INVALID, std::string(who) + ": k must be in [1, B]");
+  if (c->D > 0 && out_x == nullptr)
+    return fail(TGM_ERR_INVALID, std::string(who) + ": out_x is NULL but D > 0");
+  cfg->coloc = c->colocate != 0;
+  cfg->xsrc = cfg->coloc ? c->xrows : c->store->x;
+  cfg->vec4 = c->D > 0 && (c->D % 4 == 0) && aligned16(cfg->xsrc) && aligned16(out_x) &&
+              ((int64_t(k) * c->D * 4) % 16 == 0);
+  const int wpb = kSampleThreads / 32;
+  cfg->smem = size_t(wpb) * size_t(k) * sizeof(uint32_t);
+  if (cfg->smem > 48 * 1024) return fail(TGM_ERR_INVALID, std::string(who) + ": k too large");
+  cfg->grid = grid_for(S, wpb, 8);
+  return TGM_OK;
+}
+}  // namespace
+
+#define DISPATCH_SAMPLE(KERNEL, ...)                                                           \
+  do {                                                                                         \
+    if (cfg.vec4 && cfg.coloc)                                                                 \
+      KERNEL<true, true><<<cfg.grid, kSampleThreads, cfg.smem, st>>>(__VA_ARGS__);             \
+    else if (cfg.vec4)                                                                         \
+      KERNEL<true, false><<<cfg.grid, kSampleThreads, cfg.smem, st>>>(__VA_ARGS__);            \
+    else if (cfg.coloc)                                                                        \
+      KERNEL<false, true><<<cfg.grid, kSampleThreads, cfg.smem, st>>>(__VA_ARGS__);            \
+    else                                                                                       \
+      KERNEL<false, false><<<cfg.grid, kSampleThreads, cfg.smem, st>>>(__VA_ARGS__);           \
+  } while (0)
+
+extern "C" int tgm_csr_sample(const tgm_csr *c, const int32_t *seeds, const int64_t *tq,
+                              const int64_t *cut, int64_t cut_group, int64_t S, int32_t B,
+                              int32_t k, int32_t *out_nid, int64_t *out_t, float *out_x,
+                              tgm_stream stream) {
+  TGM_REQUIRE(c != nullptr, "tgm_csr_sample: csr is NULL");
+  TGM_REQUIRE(S >= 0, "tgm_csr_sample: S must be >= 0");
+  TGM_REQUIRE(cut_group >= 1, "tgm_csr_sample: cut_group must be >= 1");
+  if (S == 0) return TGM_OK;
+  TGM_REQUIRE(seeds && tq && cut && out_nid && out_t, "tgm_csr_sample: NULL array argument");
+  SampleCfg cfg;
+  int rc = sample_cfg(c, "tgm_csr_sample", S, B, k, out_x, &cfg);
+  if (rc != TGM_OK) return rc;
+  DeviceGuard g(c->device);
+  cudaStream_t st = as_stream(stream);
+  DISPATCH_SAMPLE(csr_sample_kernel, c->entries, c->rowptr, cfg.xsrc, c->N, c->D, seeds, tq, cut,
+                  cut_group, S, B, k, out_nid, out_t, out_x);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+
+extern "C" int tgm_csr_sample_edges(const tgm_csr *c, int64_t e_lo, int64_t e_hi, int32_t B,
+                                    int32_t k, int32_t *out_nid, int64_t *out_t, float *out_x,
+                                    tgm_stream stream) {
+  TGM_REQUIRE(c != nullptr, "tgm_csr_sample_edges: csr is NULL");
+  const int64_t l_lo = e_lo - c->e_start, l_hi = e_hi - c->e_start;
+  TGM_REQUIRE(l_lo >= 0 && l_lo <= l_hi && l_hi <= c->Ew,
+              "tgm_csr_sample_edges: [e_lo, e_hi) outside the indexed stream");
+  TGM_REQUIRE(l_lo % c->bs == 0, "tgm_csr_sample_edges: e_lo must sit on a batch boundary");
+  const int64_t S = 2 * (l_hi - l_lo);
+  if (S == 0) return TGM_OK;
+  TGM_REQUIRE(out_nid && out_t, "tgm_csr_sample_edges: NULL array argument");
+  SampleCfg cfg;
+  int rc = sample_cfg(c, "tgm_csr_sample_edges", S, B, k, out_x, &cfg);
+  if (rc != TGM_OK) return rc;
+  DeviceGuard g(c->device);
+  cudaStream_t st = as_stream(stream);
+  DISPATCH_SAMPLE(csr_sample_edges_kernel, c->entries, c->anchors, cfg.xsrc,
+                  c->store->t + c->e_start, c->D, c->Ew, c->bs, l_lo, l_hi, B, k, out_nid, out_t,
+                  out_x);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}

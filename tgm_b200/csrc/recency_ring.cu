@@ -1,0 +1,351 @@
+// Stateful recency sampler: per-node ring buffers on the device.
+// Replaces RecencyNeighborHook's state machine (reference tgm-team/tgm @ 5183dc9,
+// tgm/hooks/neighbors/recency.py): state :93-97/:410-416, reset_state :111-117,
+// _get_recency_neighbors :239-321 (~25 eager ops + an O(N*B) min() scan per call), _update
+// :323-399 (argsort + 15 eager ops).  Here a query is one launch (a warp per seed, only the k
+// needed feature rows are read) and an update is two launches.
+#include "common.cuh"
+
+#include <new>
+
+using namespace tgm;
+
+struct tgm_recency {
+  int32_t N = 0, B = 0, D = 0;
+  int device = -1;
+  int32_t *ids = nullptr;    // [N, B]
+  int64_t *times = nullptr;  // [N, B]
+  float *feats = nullptr;    // [N, B, D]
+  int32_t *wpos = nullptr;   // [N]
+  // update scratch (grown on demand)
+  int64_t *dest = nullptr;  // [cap] ring row (node*B+slot) an entry lands in, -1 = dropped
+  int32_t *inc = nullptr;   // [cap] write_pos increment carried by the last entry of each node
+  int64_t cap = 0;
+  ~tgm_recency() {
+    if (device >= 0) {
+      DeviceGuard g(device);
+      cudaFree(ids);
+      cudaFree(times);
+      cudaFree(feats);
+      cudaFree(wpos);
+      cudaFree(dest);
+      cudaFree(inc);
+    }
+  }
+};
+
+namespace {
+
+constexpr int kQueryThreads = 256;
+
+// ---- query (recency.py:239-321) --------------------------------------------------------------
+// One warp per seed.  Unrolled ring position j (oldest .. newest) lives in slot (wp + j) % B.
+template <bool VEC4>
+__global__ void __launch_bounds__(kQueryThreads)
+ring_query_kernel(const int32_t *__restrict__ ids, const int64_t *__restrict__ times,
+                  const float *__restrict__ feats, const int32_t *__restrict__ wpos, int N, int B,
+                  int D, const int32_t *__restrict__ seeds, const int64_t *__restrict__ tq,
+                  int64_t S, int k, int32_t *__restrict__ out_nid, int64_t *__restrict__ out_t,
+                  float *__restrict__ out_x) {
+  extern __shared__ int32_t s_slot[];  // [warps][k]: ring slot feeding each output column, -1 = pad
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  int32_t *my = s_slot + warp * k;
+  for (int64_t s = int64_t(blockIdx.x) * wpb + warp; s < S; s += int64_t(gridDim.x) * wpb) {
+    int v = seeds[s];
+    if (v < 0) v += N;  // torch negative indexing: the padded id -1 reads row N-1 (recency.py:256)
+    const bool in_range = (v >= 0 && v < N);
+    const int64_t q = tq[s];
+    const int64_t row = int64_t(in_range ? v : 0) * B;
+    const int wp = in_range ? int(uint32_t(wpos[v]) % uint32_t(B)) : 0;
+    int last = -1;  // right-most unrolled position with id != -1 && time < tq (:267-281)
+    if (in_range) {
+      for (int base = 0; base < B; base += 32) {
+        const int j = base + lane;
+        bool ok = false;
+        if (j < B) {
+          int slot = wp + j;
+          if (slot >= B) slot -= B;
+          ok = (ids[row + slot] != TGM_PADDED_NODE_ID) && (times[row + slot] < q);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (m) last = base + 31 - __clz(m);
+      }
+    }
+    // k-window ending at `last`, right-aligned (:287-319)
+    for (int c = lane; c < k; c += 32) {
+      const int p = last - (k - 1 - c);
+      int slot = -1;
+      int32_t id = TGM_PADDED_NODE_ID;
+      int64_t tt = 0;
+      if (p >= 0) {
+        slot = wp + p;
+        if (slot >= B) slot -= B;
+        id = ids[row + slot];
+        tt = times[row + slot];
+      }
+      my[c] = slot;
+      out_nid[s * k + c] = id;
+      out_t[s * k + c] = tt;
+    }
+    __syncwarp();
+    if (D > 0) {
+      if (VEC4) {
+        const int D4 = D >> 2;
+        const float4 *f4 = reinterpret_cast<const float4 *>(feats);
+        float4 *o4 = reinterpret_cast<float4 *>(out_x) + s * int64_t(k) * D4;
+        const int total = k * D4;
+        for (int i = lane; i < total; i += 32) {
+          const int c = i / D4, d = i - c * D4;
+          const int slot = my[c];
+          float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (slot >= 0) val = __ldg(f4 + (row + slot) * D4 + d);
+          o4[i] = val;
+        }
+      } else {
+        float *o = out_x + s * int64_t(k) * D;
+        const int total = k * D;
+        for (int i = lane; i < total; i += 32) {
+          const int c = i / D, d = i - c * D;
+          const int slot = my[c];
+          o[i] = slot >= 0 ? __ldg(feats + (row + slot) * D + d) : 0.f;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- update (recency.py:323-399) -------------------------------------------------------------
+// Entry i of the concatenation [src->dst entries | dst->src entries] (:339-342).
+struct UpdEntry {
+  int32_t node, nbr;
+  int64_t t;
+  int64_t e;
+};
+__device__ __forceinline__ UpdEntry load_entry(const int32_t *src, const int32_t *dst,
+                                               const int64_t *t, int64_t Eb, int64_t i) {
+  UpdEntry u;
+  if (i < Eb) {
+    u.e = i;
+    u.node = src[i];
+    u.nbr = dst[i];
+  } else {
+    u.e = i - Eb;
+    u.node = dst[u.e];
+    u.nbr = src[u.e];
+  }
+  u.t = t[u.e];
+  return u;
+}
+
+constexpr int kRankThreads = 256;
+
+// Phase A: every entry finds its rank among the entries of the same node in the order of the
+// reference's stable sort -- (time, position in the concatenation) (:347-349) -- and the node's
+// entry count.  The last B are written to (write_pos + j) % B (:373,:389-393).  O(n^2 / tile)
+// over a batch of a few hundred edges; the tiles of (node, time) are staged in shared memory.
+__global__ void __launch_bounds__(kRankThreads)
+ring_update_rank_kernel(int32_t *__restrict__ ids, int64_t *__restrict__ times,
+                        const int32_t *__restrict__ wpos, int N, int B,
+                        const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                        const int64_t *__restrict__ t, int64_t Eb, int64_t n,
+                        int64_t *__restrict__ dest, int32_t *__restrict__ inc) {
+  __shared__ int32_t s_node[kRankThreads];
+  __shared__ int64_t s_t[kRankThreads];
+  const int64_t i = int64_t(blockIdx.x) * kRankThreads + threadIdx.x;
+  UpdEntry me{};
+  me.node = -2;
+  if (i < n) me = load_entry(src, dst, t, Eb, i);
+  int rank = 0, cnt = 0;
+  for (int64_t base = 0; base < n; base += kRankThreads) {
+    const int64_t j = base + threadIdx.x;
+    if (j < n) {
+      const UpdEntry o = load_entry(src, dst, t, Eb, j);
+      s_node[threadIdx.x] = o.node;
+      s_t[threadIdx.x] = o.t;
+    } else {
+      s_node[threadIdx.x] = -3;
+    }
+    __syncthreads();
+    const int lim = int(n - base < kRankThreads ? n - base : kRankThreads);
+    for (int u = 0; u < lim; ++u) {
+      if (s_node[u] == me.node) {
+        ++cnt;
+        const int64_t ot = s_t[u];
+        rank += (ot < me.t) || (ot == me.t && base + u < i);
+      }
+    }
+    __syncthreads();
+  }
+  if (i >= n) return;
+  int64_t d = -1;
+  int32_t add = 0;
+  if (me.node >= 0 && me.node < N) {
+    const int first_kept = cnt > B ? cnt - B : 0;
+    if (rank >= first_kept) {
+      const int wp = int(uint32_t(wpos[me.node]) % uint32_t(B));
+      const int slot = (wp + (rank - first_kept)) % B;
+      d = int64_t(me.node) * B + slot;
+      ids[d] = me.nbr;
+      times[d] = me.t;
+    }
+    if (rank == cnt - 1) add = cnt < B ? cnt : B;  // :397-399 counts the kept entries only
+  }
+  dest[i] = d;
+  inc[i] = add;
+}
+
+// Phase B: copy the kept feature rows (a warp per entry, coalesced) and advance write_pos.
+__global__ void __launch_bounds__(256)
+ring_update_commit_kernel(float *__restrict__ feats, int32_t *__restrict__ wpos, int D,
+                          const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                          const float *__restrict__ x, int64_t Eb, int64_t n,
+                          const int64_t *__restrict__ dest, const int32_t *__restrict__ inc) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int64_t i = int64_t(blockIdx.x) * wpb + (threadIdx.x >> 5); i < n;
+       i += int64_t(gridDim.x) * wpb) {
+    const int64_t d = dest[i];
+    const int64_t e = i < Eb ? i : i - Eb;
+    if (d >= 0 && D > 0) {
+      float *o = feats + d * D;
+      if (x) {
+        const float *r = x + e * D;
+        for (int c = lane; c < D; c += 32) o[c] = __ldg(r + c);
+      } else {
+        for (int c = lane; c < D; c += 32) o[c] = 0.f;  // missing edge_x pushes zeros (:325-329)
+      }
+    }
+    if (lane == 0) {
+      const int32_t a = inc[i];
+      if (a > 0) {
+        const int32_t node = i < Eb ? src[e] : dst[e];
+        wpos[node] += a;  // exactly one entry per node carries a non-zero increment
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int tgm_recency_create(tgm_recency **out, int32_t num_nodes, int32_t B, int32_t D,
+                                  int device) {
+  TGM_REQUIRE(out != nullptr, "tgm_recency_create: out is NULL");
+  *out = nullptr;
+  TGM_REQUIRE(num_nodes > 0, "tgm_recency_create: num_nodes must be > 0");
+  TGM_REQUIRE(B > 0, "tgm_recency_create: B must be > 0");
+  TGM_REQUIRE(D >= 0, "tgm_recency_create: D must be >= 0");
+  TGM_REQUIRE(device >= 0, "tgm_recency_create: a CUDA device is required (no CPU fallback)");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(TGM_ERR_CUDA, "tgm_recency_create: cannot select device");
+  tgm_recency *h = new (std::nothrow) tgm_recency();
+  if (!h) return fail(TGM_ERR_OOM, "tgm_recency_create: host allocation failed");
+  h->N = num_nodes;
+  h->B = B;
+  h->D = D;
+  h->device = device;
+  const size_t nb = size_t(num_nodes) * size_t(B);
+  cudaError_t e = cudaMalloc(&h->ids, nb * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&h->times, nb * 8);
+  if (e == cudaSuccess && D > 0) e = cudaMalloc(&h->feats, nb * size_t(D) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&h->wpos, size_t(num_nodes) * 4);
+  if (e != cudaSuccess) {
+    delete h;
+    return cuda_fail(e, "ring allocation", __FILE__, __LINE__);
+  }
+  int rc = tgm_recency_reset(h, nullptr);
+  if (rc == TGM_OK) {
+    e = cudaStreamSynchronize(nullptr);
+    if (e != cudaSuccess) rc = cuda_fail(e, "ring reset", __FILE__, __LINE__);
+  }
+  if (rc != TGM_OK) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return TGM_OK;
+}
+
+extern "C" void tgm_recency_destroy(tgm_recency *h) { delete h; }
+
+extern "C" int tgm_recency_reset(tgm_recency *h, tgm_stream stream) {
+  TGM_REQUIRE(h != nullptr, "tgm_recency_reset: handle is NULL");
+  DeviceGuard g(h->device);
+  cudaStream_t st = as_stream(stream);
+  const size_t nb = size_t(h->N) * size_t(h->B);
+  TGM_CUDA(cudaMemsetAsync(h->ids, 0xFF, nb * 4, st));  // int32 -1 == PADDED_NODE_ID
+  TGM_CUDA(cudaMemsetAsync(h->times, 0, nb * 8, st));
+  if (h->D > 0) TGM_CUDA(cudaMemsetAsync(h->feats, 0, nb * size_t(h->D) * 4, st));
+  TGM_CUDA(cudaMemsetAsync(h->wpos, 0, size_t(h->N) * 4, st));
+  return TGM_OK;
+}
+
+extern "C" int tgm_recency_query(const tgm_recency *h, const int32_t *seeds, const int64_t *tq,
+                                 int64_t S, int32_t k, int32_t *out_nid, int64_t *out_t,
+                                 float *out_x, tgm_stream stream) {
+  TGM_REQUIRE(h != nullptr, "tgm_recency_query: handle is NULL");
+  TGM_REQUIRE(S >= 0, "tgm_recency_query: S must be >= 0");
+  TGM_REQUIRE(k >= 1 && k <= h->B, "tgm_recency_query: k must be in [1, B]");
+  if (S == 0) return TGM_OK;
+  TGM_REQUIRE(seeds && tq && out_nid && out_t, "tgm_recency_query: NULL array argument");
+  TGM_REQUIRE(h->D == 0 || out_x != nullptr, "tgm_recency_query: out_x is NULL but D > 0");
+  DeviceGuard g(h->device);
+  const int wpb = kQueryThreads / 32;
+  const size_t smem = size_t(wpb) * size_t(k) * sizeof(int32_t);
+  TGM_REQUIRE(smem <= 48 * 1024, "tgm_recency_query: k too large");
+  const int grid = grid_for(S, wpb, 8);
+  const bool vec4 = h->D > 0 && (h->D % 4 == 0) && aligned16(h->feats) && aligned16(out_x);
+  if (vec4)
+    ring_query_kernel<true><<<grid, kQueryThreads, smem, as_stream(stream)>>>(
+        h->ids, h->times, h->feats, h->wpos, h->N, h->B, h->D, seeds, tq, S, k, out_nid, out_t,
+        out_x);
+  else
+    ring_query_kernel<false><<<grid, kQueryThreads, smem, as_stream(stream)>>>(
+        h->ids, h->times, h->feats, h->wpos, h->N, h->B, h->D, seeds, tq, S, k, out_nid, out_t,
+        out_x);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+
+extern "C" int tgm_recency_update(tgm_recency *h, const int32_t *src, const int32_t *dst,
+                                  const int64_t *t, const float *x, int64_t Eb, int directed,
+                                  tgm_stream stream) {
+  TGM_REQUIRE(h != nullptr, "tgm_recency_update: handle is NULL");
+  TGM_REQUIRE(Eb >= 0, "tgm_recency_update: Eb must be >= 0");
+  if (Eb == 0) return TGM_OK;
+  TGM_REQUIRE(src && dst && t, "tgm_recency_update: NULL array argument");
+  DeviceGuard g(h->device);
+  cudaStream_t st = as_stream(stream);
+  const int64_t n = directed ? Eb : 2 * Eb;
+  if (n > h->cap) {
+    // growing the scratch is the only synchronising path; steady state never reallocates
+    TGM_CUDA(cudaStreamSynchronize(st));
+    cudaFree(h->dest);
+    cudaFree(h->inc);
+    h->dest = nullptr;
+    h->inc = nullptr;
+    h->cap = 0;
+    const int64_t cap = n < 1024 ? 1024 : n + n / 2;
+    TGM_CUDA(cudaMalloc(&h->dest, size_t(cap) * 8));
+    TGM_CUDA(cudaMalloc(&h->inc, size_t(cap) * 4));
+    h->cap = cap;
+  }
+  const int gridA = int((n + kRankThreads - 1) / kRankThreads);
+  ring_update_rank_kernel<<<gridA, kRankThreads, 0, st>>>(h->ids, h->times, h->wpos, h->N, h->B,
+                                                          src, dst, t, Eb, n, h->dest, h->inc);
+  TGM_LAUNCH_CHECK();
+  const int gridB = grid_for(n, 8, 8);
+  ring_update_commit_kernel<<<gridB, 256, 0, st>>>(h->feats, h->wpos, h->D, src, dst, x, Eb, n,
+                                                   h->dest, h->inc);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+
+extern "C" int tgm_recency_state(const tgm_recency *h, int32_t **ids, int64_t **times,
+                                 float **feats, int32_t **write_pos) {
+  TGM_REQUIRE(h != nullptr, "tgm_recency_state: handle is NULL");
+  if (ids) *ids = h->ids;
+  if (times) *times = h->times;
+  if (feats) *feats = h->feats;
+  if (write_pos) *write_pos = h->wpos;
+  return TGM_OK;
+}

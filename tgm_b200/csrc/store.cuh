@@ -1,0 +1,22 @@
+// Internal definition of the edge-store handle (shared by store.cu and csr.cu).
+#pragma once
+
+#include <vector>
+
+#include "common.cuh"
+
+struct tgm_store {
+  int64_t E = 0;
+  int32_t D = 0;
+  int32_t num_nodes = 0;
+  int device = -1;
+  bool owns_device = false;
+  // device slabs, time-sorted (structure of arrays: a slice is a pointer offset)
+  const int32_t *src = nullptr;
+  const int32_t *dst = nullptr;
+  const int64_t *t = nullptr;
+  const float *x = nullptr;  // [E, D] row-major, NULL when D == 0
+  // host mirror of t for O(log E) slice bounds without touching the device
+  std::vector<int64_t> t_host;
+  ~tgm_store();
+};

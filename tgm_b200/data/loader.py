@@ -1,0 +1,92 @@
+"""DGDataLoader: sequential batches over a DGraph, hooks applied per batch.
+
+Same constructor arguments, batching rules and empty-batch policy as tgm/data/loader.py:64-184
+(event-ordered 'r' batches are [i, i+bs) event indices :136-148,:158-160; time-unit batches are
+[t, t+bs) windows; `drop_last`; on_empty in {'skip','raise',None} :20-61).  It is a plain
+Python iterator rather than a torch DataLoader subclass: there are no workers to manage (state
+lives on the GPU) and the torch DataLoader machinery costs more per step than the kernels do.
+"""
+from __future__ import annotations
+
+from typing import Any, Iterator, Optional
+
+from tgm_b200.core.batch import DGBatch
+from tgm_b200.core.graph import DGraph
+from tgm_b200.core.timedelta import TimeDeltaDG
+from tgm_b200.exceptions import (EmptyBatchError, EventOrderedConversionError,
+                                 InvalidDiscretizationError)
+
+_ON_EMPTY = ('skip', 'raise', None)
+
+
+class DGDataLoader:
+    def __init__(self, dg: DGraph, batch_size: int = 1, batch_unit: str = 'r',
+                 on_empty: Optional[str] = 'skip', hook_manager=None, **kwargs: Any) -> None:
+        if batch_size <= 0:
+            raise ValueError(f'batch_size must be > 0 but got {batch_size}')
+        if on_empty not in _ON_EMPTY:
+            raise ValueError(f'Invalid on_empty={on_empty}, expected one of: {list(_ON_EMPTY)}')
+        unit = TimeDeltaDG(batch_unit)
+        if dg.time_delta.is_event_ordered and unit.is_time_ordered:
+            raise EventOrderedConversionError(
+                'Cannot iterate event-ordered dg using time-ordered batch_unit')
+        if dg.time_delta.is_time_ordered and unit.is_time_ordered:
+            unit = TimeDeltaDG(batch_unit, value=batch_size)
+            if dg.time_delta.is_coarser_than(unit):
+                raise InvalidDiscretizationError(
+                    f'Tried to construct a data loader on a DGraph with time delta: '
+                    f'{dg.time_delta} which is strictly coarser than the batch_unit: '
+                    f'{batch_unit}, batch_size: {batch_size}.')
+            batch_size = int(unit.convert(dg.time_delta))
+        if dg.start_time is None or dg.end_time is None:
+            raise ValueError('cannot iterate an empty DGraph')
+        self._dg = dg
+        self._batch_size = batch_size
+        self._hook_manager = hook_manager
+        self._on_empty = on_empty
+        self._by_events = unit.is_event_ordered
+        if self._by_events:
+            self._slice_op = dg.slice_events
+            start, stop = 0, dg.num_events  # loader.py:137-139
+        else:
+            self._slice_op = dg.slice_time
+            start, stop = dg.start_time, dg.end_time + 1
+        if kwargs.get('drop_last', False):
+            self._starts = range(start, stop - batch_size, batch_size)
+        else:
+            self._starts = range(start, stop, batch_size)
+
+    @property
+    def dgraph(self) -> DGraph:
+        return self._dg
+
+    def __len__(self) -> int:
+        return len(self._starts)
+
+    def _load(self, start: int) -> DGBatch:
+        dg = self._slice_op(start, start + self._batch_size)
+        batch = dg.materialize()
+        if self._hook_manager is not None:
+            batch = self._hook_manager.execute_active_hooks(dg, batch)
+        return batch
+
+    # kept for API parity with the reference, whose loader is its own collate_fn (:158)
+    def __call__(self, slice_start) -> DGBatch:
+        return self._load(slice_start[0])
+
+    @staticmethod
+    def _is_batch_empty(batch: DGBatch) -> bool:
+        n = batch.edge_src.numel()
+        n += batch.node_x_nids.numel() if batch.node_x_nids is not None else 0
+        n += batch.node_y_nids.numel() if batch.node_y_nids is not None else 0
+        return n == 0
+
+    def __iter__(self) -> Iterator[DGBatch]:
+        for start in self._starts:
+            batch = self._load(start)
+            if self._is_batch_empty(batch):
+                if self._on_empty == 'raise':
+                    raise EmptyBatchError('Empty batch encountered')
+                if self._on_empty == 'skip':
+                    continue
+            yield batch

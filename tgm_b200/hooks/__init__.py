@@ -1,0 +1,5 @@
+from .base import BaseDGHook, DGHook, SeedableHook, StatefulHook, StatelessHook
+from .hook_manager import HookManager
+from .recency import RecencyNeighborHook
+from .negatives import RandomNegativeEdgeSamplerHook
+from .dedup import DeduplicationHook

@@ -1,0 +1,251 @@
+"""RecencyNeighborHook: drop-in for tgm/hooks/neighbors/recency.py:18-416 on the B200.
+
+Same constructor, ValueErrors, requires/produces, batch attributes, dtypes, padding and
+query-before-update order; the per-node ring buffers live in HBM behind a `tgm_recency` handle
+(include/tgm_b200.h) and each hop is ONE kernel launch (`tgm_recency_query`) instead of ~25
+eager ops plus an O(N*B) `.min()` scan + host sync (recency.py:242); the push is two launches
+(`tgm_recency_update`) instead of an argsort and ~15 eager ops (recency.py:323-399).
+
+Deliberate difference: the reference's update sort key overflows int32 when
+num_nodes * (t_max + 1) >= 2**31 (recency.py:347-348) and its output is then undefined; this
+implementation always follows the ideal semantics (what the reference computes inside the
+parity domain, and what it would compute with `node_ids.long()`).
+"""
+from __future__ import annotations
+
+import ctypes
+import warnings
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from tgm_b200 import _cabi
+from tgm_b200.constants import PADDED_NODE_ID
+from tgm_b200.hooks.base import SeedableHook, StatefulHook
+from tgm_b200.hooks.hook_manager import register_hook_class
+
+# seed attributes that are views of the validated store slabs (ids in [0, N), times >= 0 by
+# DGData construction): checking them again would cost a host sync per batch
+_TRUSTED_NODE_KEYS = ('edge_src', 'edge_dst')
+_TRUSTED_TIME_KEYS = ('edge_time',)
+
+
+def _is_store_view(store, tensor: Tensor) -> bool:
+    """True when `tensor` aliases one of the store's validated device slabs."""
+    if not tensor.is_cuda:
+        return False
+    base = tensor.untyped_storage().data_ptr()
+    for name in ('_src', '_dst', '_t'):
+        slab = getattr(store, name, None)
+        if slab is not None and slab.untyped_storage().data_ptr() == base:
+            return True
+    return False
+
+
+@register_hook_class
+class RecencyNeighborHook(StatefulHook, SeedableHook):
+    """Load the most recent neighbors of each seed node; every node keeps a fixed number of
+    recent neighbors (recency sampling, k-hop, historical)."""
+
+    _cls_requires = {'edge_src', 'edge_dst', 'edge_time'}
+    _cls_produces = {'seed_nids', 'seed_times', 'nbr_nids', 'nbr_edge_time', 'nbr_edge_x',
+                     'seed_node_nbr_mask'}
+
+    def __init__(self, num_nodes: int, num_nbrs: List[int], seed_nodes_keys: List[str],
+                 seed_times_keys: List[str], directed: bool = False,
+                 id: Optional[str] = None) -> None:
+        if not len(num_nbrs):
+            raise ValueError('num_nbrs must be non-empty')
+        if not all(isinstance(x, int) and x > 0 for x in num_nbrs):
+            raise ValueError('Each value in num_nbrs must be a positive integer')
+        if len(seed_nodes_keys) != len(seed_times_keys):
+            raise ValueError(
+                f'len(seed_nodes_keys) ({len(seed_nodes_keys)}) != len(seed_times_keys) '
+                f'({len(seed_times_keys)})\nseed_nodes_keys={seed_nodes_keys}, '
+                f'seed_times_keys={seed_times_keys}')
+        self._num_nodes = num_nodes
+        self._num_nbrs = num_nbrs
+        self._max_nbrs = max(num_nbrs)
+        self._directed = directed
+        self._seed_nodes_keys = seed_nodes_keys
+        self._seed_times_keys = seed_times_keys
+        self._warned_seed_None = False
+        self._handle = ctypes.c_void_p()   # tgm_recency*, created on first call
+        self._device: Optional[torch.device] = None
+        self._edge_x_dim: Optional[int] = None
+        self._init_hook(id=id, seed_keys=seed_nodes_keys)
+
+    def __del__(self, _destroy=_cabi.lib.tgm_recency_destroy) -> None:
+        h = getattr(self, '_handle', None)
+        if h is not None and h.value:
+            _destroy(h)
+            h.value = None
+
+    @property
+    def num_nbrs(self) -> List[int]:
+        return self._num_nbrs
+
+    def reset_state(self) -> None:
+        if self._handle.value:
+            _cabi.check(_cabi.lib.tgm_recency_reset(self._handle, _cabi.current_stream(self._device)))
+
+    # -- state ------------------------------------------------------------------------------
+    def _ensure_state(self, dg) -> None:
+        """First call fixes D = dg.edge_x_dim or 0 and the device (recency.py:401-416)."""
+        if self._handle.value:
+            return
+        device = dg.device
+        if device.type != 'cuda':
+            raise _cabi.TGMNativeError(
+                -3, f'RecencyNeighborHook needs a CUDA DGraph, got device={device} '
+                    '(tgm_b200 has no CPU fallback)')
+        if device.index is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self._device = device
+        self._edge_x_dim = dg.edge_x_dim or 0
+        _cabi.check(_cabi.lib.tgm_recency_create(ctypes.byref(self._handle), self._num_nodes,
+                                                 self._max_nbrs, self._edge_x_dim, device.index))
+
+    def state_tensors(self) -> Dict[str, Tensor]:
+        """Copies of the ring state (ids, times, feats, write_pos) for inspection/checkpoints."""
+        if not self._handle.value:
+            raise RuntimeError('hook state is created on the first call')
+        N, B, D = self._num_nodes, self._max_nbrs, self._edge_x_dim
+        p = [ctypes.c_void_p() for _ in range(4)]
+        _cabi.check(_cabi.lib.tgm_recency_state(self._handle, *[ctypes.byref(q) for q in p]))
+        shapes = [((N, B), torch.int32), ((N, B), torch.int64), ((N, B, D), torch.float32),
+                  ((N,), torch.int32)]
+        out = {}
+        for name, q, (shape, dtype) in zip(('ids', 'times', 'feats', 'write_pos'), p, shapes):
+            if q.value and all(shape):
+                out[name] = _cabi.device_view(q.value, shape, dtype, self._device).clone()
+            else:
+                out[name] = torch.zeros(shape, dtype=dtype, device=self._device)
+        return out
+
+    # -- the hook ---------------------------------------------------------------------------
+    def __call__(self, dg, batch):
+        self._ensure_state(dg)
+        seed_nodes, seed_times, seed_mask = self._get_seed_tensors(dg, batch)
+        seeds_out: List[Tensor] = []
+        times_out: List[Tensor] = []
+        nids: List[Tensor] = []
+        nts: List[Tensor] = []
+        nxs: List[Tensor] = []
+        if not seed_nodes.numel():
+            for _ in self._num_nbrs:  # recency.py:127-137: empty CPU tensors, exact dtypes
+                seeds_out.append(torch.empty(0, dtype=torch.int32))
+                times_out.append(torch.empty(0, dtype=torch.int64))
+                nids.append(torch.empty(0, dtype=torch.int32))
+                nts.append(torch.empty(0, dtype=torch.int64))
+                nxs.append(torch.empty(0, dg.edge_x_dim).float())
+        else:
+            stream = _cabi.current_stream(self._device)
+            for hop, k in enumerate(self._num_nbrs):
+                if hop > 0:
+                    seed_nodes = nids[hop - 1].flatten()
+                    seed_times = nts[hop - 1].flatten()
+                nid, nt, nx = self._query(seed_nodes, seed_times, k, stream)
+                seeds_out.append(seed_nodes)
+                times_out.append(seed_times)
+                nids.append(nid)
+                nts.append(nt)
+                nxs.append(nx)
+            if batch.edge_src.numel():
+                self._update(batch, stream)
+        self.add_batch_attribute(batch, 'seed_nids', seeds_out)
+        self.add_batch_attribute(batch, 'seed_times', times_out)
+        self.add_batch_attribute(batch, 'nbr_nids', nids)
+        self.add_batch_attribute(batch, 'nbr_edge_time', nts)
+        self.add_batch_attribute(batch, 'nbr_edge_x', nxs)
+        self.add_batch_attribute(batch, 'seed_node_nbr_mask', seed_mask)
+        return batch
+
+    def _query(self, seeds: Tensor, tq: Tensor, k: int, stream: int
+               ) -> Tuple[Tensor, Tensor, Tensor]:
+        S, D, dev = seeds.numel(), self._edge_x_dim, self._device
+        seeds = seeds.to(device=dev, dtype=torch.int32).contiguous()
+        tq = tq.to(device=dev, dtype=torch.int64).contiguous()
+        nid = torch.empty((S, k), dtype=torch.int32, device=dev)
+        nt = torch.empty((S, k), dtype=torch.int64, device=dev)
+        nx = torch.empty((S, k, D), dtype=torch.float32, device=dev)
+        _cabi.check(_cabi.lib.tgm_recency_query(
+            self._handle, seeds.data_ptr(), tq.data_ptr(), S, k, nid.data_ptr(), nt.data_ptr(),
+            nx.data_ptr() if D else None, stream))
+        return nid, nt, nx
+
+    def _update(self, batch, stream: int) -> None:
+        dev = self._device
+        src = batch.edge_src.to(device=dev, dtype=torch.int32).contiguous()
+        dst = batch.edge_dst.to(device=dev, dtype=torch.int32).contiguous()
+        t = batch.edge_time.to(device=dev, dtype=torch.int64).contiguous()
+        x = batch.edge_x
+        if x is not None and self._edge_x_dim:
+            x = x.to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            x = None  # zeros are pushed (recency.py:325-329)
+        _cabi.check(_cabi.lib.tgm_recency_update(
+            self._handle, src.data_ptr(), dst.data_ptr(), t.data_ptr(), _cabi.ptr(x),
+            src.numel(), int(self._directed), stream))
+
+    def _get_seed_tensors(self, dg, batch) -> Tuple[Tensor, Tensor, Dict[str, Tensor]]:
+        """Seed assembly and validation (recency.py:173-237)."""
+        device = batch.edge_src.device
+        seeds: List[Tensor] = []
+        times: List[Tensor] = []
+        mask: Dict[str, Tensor] = {}
+        to_check: List[Tuple[str, Tensor, bool]] = []
+        store = getattr(dg, '_storage', None)
+        n_global = getattr(store, 'num_nodes_global', None)
+        ids_fit = n_global is not None and n_global <= self._num_nodes
+        offset = 0
+        for node_attr, time_attr in zip(self._seed_nodes_keys, self._seed_times_keys):
+            missing = [a for a in (node_attr, time_attr) if not hasattr(batch, a)]
+            if missing:
+                raise ValueError(f'Missing seed attributes {missing} on batch')
+            pair = [(node_attr, getattr(batch, node_attr)), (time_attr, getattr(batch, time_attr))]
+            for name, tensor in pair:
+                if tensor is None:  # e.g. a batch without this kind of event: skip the key
+                    if not self._warned_seed_None:
+                        warnings.warn(
+                            f'Seed attribute {name} is None on this batch, skipping this batch. '
+                            'Future occurrences will also be skipped but the warning will be '
+                            'suppressed', UserWarning)
+                        self._warned_seed_None = True
+                    break
+                if not isinstance(tensor, Tensor):
+                    raise ValueError(f'{name} must be a Tensor, got {type(tensor)}')
+                if tensor.ndim != 1:
+                    raise ValueError(f'{name} must be 1-D, got shape {tensor.shape}')
+                if name == node_attr:
+                    if not (ids_fit and name in _TRUSTED_NODE_KEYS and
+                            _is_store_view(store, tensor)):
+                        to_check.append((name, tensor, True))
+                    seeds.append(tensor.to(device))
+                    n = tensor.shape[0]
+                    mask[name] = torch.arange(offset, offset + n, device=device)
+                    offset += n
+                else:
+                    if not (name in _TRUSTED_TIME_KEYS and _is_store_view(store, tensor)):
+                        to_check.append((name, tensor, False))
+                    times.append(tensor.to(device))
+        self._validate(to_check)
+        if seeds and times:
+            return torch.cat(seeds), torch.cat(times), mask
+        return (torch.empty(0, dtype=torch.int32, device=device),
+                torch.empty(0, dtype=torch.int64, device=device), mask)
+
+    def _validate(self, items: List[Tuple[str, Tensor, bool]]) -> None:
+        """Bounds checks of recency.py:208-229 with ONE host sync for all keys."""
+        items = [(n, t, is_node) for n, t, is_node in items if t.numel()]
+        if not items:
+            return
+        stats = torch.stack([torch.stack([t.min(), t.max()]).to(torch.int64) for _, t, _ in items])
+        stats = stats.cpu().tolist()
+        for (name, _, is_node), (lo, hi) in zip(items, stats):
+            if is_node and (lo < 0 or hi >= self._num_nodes):
+                raise ValueError(f'Seed nodes in {name} must satisfy 0 <= x < {self._num_nodes}, '
+                                 f'got values in range [{lo}, {hi}]')
+            if not is_node and lo < 0:
+                raise ValueError(f'Seed times in {name} must be >= 0, got min value: {lo}')

@@ -1,0 +1,160 @@
+"""Stateless windowed recency sampler: the throughput form of the hot path.
+
+`RecencyCSR` wraps `tgm_csr_*` (include/tgm_b200.h).  It answers exactly what
+RecencyNeighborHook answers batch by batch (tgm/hooks/neighbors/recency.py:119-171 of the
+reference), but one launch per hop serves every loader batch of a window of the event stream;
+the batch a seed belongs to is encoded as an edge-index cut.  This is the path that is sharded
+across GPUs by time range (tgm_b200/parallel.py) and that bench.py measures.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from tgm_b200 import _cabi
+
+
+@dataclass
+class HopSample:
+    """One hop of sampled neighbourhoods (rows follow the reference's per-batch seed order)."""
+    seed_nids: Tensor      # int32 (S,)
+    seed_times: Tensor     # int64 (S,)
+    nbr_nids: Tensor       # int32 (S, k)
+    nbr_edge_time: Tensor  # int64 (S, k)
+    nbr_edge_x: Tensor     # float32 (S, k, D)
+
+
+class RecencyCSR:
+    """Per-node chronological adjacency of a device store for one loader geometry.
+
+    Args:
+        storage: a `DeviceCOOStorage` on a CUDA device.
+        batch_size: loader batch size in events (batch_unit='r'); batches start at `e_start`.
+        directed: only src->dst entries are pushed (RecencyNeighborHook(directed=True)).
+        colocate_x: keep a copy of the feature rows in adjacency order so a seed's window is a
+            contiguous read (2*E*D*4 bytes of HBM when undirected).
+    """
+
+    def __init__(self, storage, batch_size: int, directed: bool = False,
+                 colocate_x: bool = True, e_start: int = 0) -> None:
+        if storage.device is None:
+            raise _cabi.TGMNativeError(-3, 'RecencyCSR needs a device-resident store')
+        self._storage = storage  # keeps the store (and its slabs) alive
+        self.device = storage.device
+        self.batch_size = int(batch_size)
+        self.directed = bool(directed)
+        self.e_start = int(e_start)
+        self.D = storage.get_edge_x_dim() or 0
+        self._handle = ctypes.c_void_p()
+        _cabi.check(_cabi.lib.tgm_csr_build(
+            ctypes.byref(self._handle), storage.handle, self.e_start, self.batch_size,
+            int(self.directed), int(colocate_x), _cabi.current_stream(self.device)))
+
+    def __del__(self, _destroy=_cabi.lib.tgm_csr_destroy) -> None:
+        h = getattr(self, '_handle', None)
+        if h is not None and h.value:
+            _destroy(h)
+            h.value = None
+
+    @property
+    def handle(self) -> ctypes.c_void_p:
+        return self._handle
+
+    def _alloc(self, S: int, k: int):
+        dev = self.device
+        return (torch.empty((S, k), dtype=torch.int32, device=dev),
+                torch.empty((S, k), dtype=torch.int64, device=dev),
+                torch.empty((S, k, self.D), dtype=torch.float32, device=dev))
+
+    def sample(self, seeds: Tensor, tq: Tensor, cut: Tensor, k: int, B: int,
+               cut_group: int = 1, out=None):
+        """General seeds: seed i sees entries of edges < cut[i // cut_group]."""
+        S = seeds.numel()
+        nid, nt, nx = out if out is not None else self._alloc(S, k)
+        _cabi.check(_cabi.lib.tgm_csr_sample(
+            self._handle, seeds.data_ptr(), tq.data_ptr(), cut.data_ptr(), int(cut_group), S,
+            int(B), int(k), nid.data_ptr(), nt.data_ptr(), nx.data_ptr() if self.D else None,
+            _cabi.current_stream(self.device)))
+        return nid, nt, nx
+
+    def sample_edges(self, e_lo: int, e_hi: int, k: int, B: int, out=None):
+        """Hop 0 for seeds = endpoints of stream edges [e_lo, e_hi) (src rows then dst rows per
+        batch): no seed arrays, no search -- the prebuilt anchor table gives the window."""
+        S = 2 * (e_hi - e_lo)
+        nid, nt, nx = out if out is not None else self._alloc(S, k)
+        _cabi.check(_cabi.lib.tgm_csr_sample_edges(
+            self._handle, int(e_lo), int(e_hi), int(B), int(k), nid.data_ptr(), nt.data_ptr(),
+            nx.data_ptr() if self.D else None, _cabi.current_stream(self.device)))
+        return nid, nt, nx
+
+    # -- whole windows ----------------------------------------------------------------------
+    def window_seed_tensors(self, e_lo: int, e_hi: int, neg: Optional[Tensor] = None):
+        """hop-0 seeds/times/cuts of the window laid out batch by batch in the reference's
+        seed order [src | dst (| neg)] (recency.py:181-233)."""
+        st, bs = self._storage, self.batch_size
+        src, dst, t = st._src[e_lo:e_hi], st._dst[e_lo:e_hi], st._t[e_lo:e_hi]
+        n = e_hi - e_lo
+        parts = [src, dst] + ([neg] if neg is not None else [])
+        P = len(parts)
+        nfull, rem = divmod(n, bs)
+
+        def lay(cols: Sequence[Tensor]) -> Tensor:
+            full = torch.stack([c[:nfull * bs].view(nfull, bs) for c in cols], 1).reshape(-1)
+            if rem:
+                return torch.cat([full] + [c[nfull * bs:] for c in cols])
+            return full
+
+        seeds = lay(parts)
+        times = lay([t] * P)
+        starts = e_lo + torch.arange(0, n, bs, device=self.device, dtype=torch.int64)
+        counts = torch.full((len(starts),), bs * P, device=self.device, dtype=torch.int64)
+        if rem:
+            counts[-1] = rem * P
+        cut = torch.repeat_interleave(starts, counts)
+        return seeds.contiguous(), times.contiguous(), cut
+
+    def sample_window(self, e_lo: int, e_hi: int, num_nbrs: Sequence[int],
+                      neg: Optional[Tensor] = None) -> List[HopSample]:
+        """All hops for the loader batches covering stream edges [e_lo, e_hi).
+
+        Rows are the concatenation over batches of what RecencyNeighborHook puts on each batch;
+        `split_window` cuts them back into per-batch views."""
+        B = max(num_nbrs)
+        hops: List[HopSample] = []
+        seeds, times, cut = self.window_seed_tensors(e_lo, e_hi, neg)
+        group = 1
+        for h, k in enumerate(num_nbrs):
+            if h == 0 and neg is None:
+                nid, nt, nx = self.sample_edges(e_lo, e_hi, k, B)
+            else:
+                nid, nt, nx = self.sample(seeds, times, cut, k, B, cut_group=group)
+            hops.append(HopSample(seeds, times, nid, nt, nx))
+            seeds, times = nid.reshape(-1), nt.reshape(-1)
+            group *= k
+        return hops
+
+    def split_window(self, hops: List[HopSample], e_lo: int, e_hi: int, seeds_per_edge: int = 2):
+        """Yield (batch_lo, batch_hi, [HopSample views]) per loader batch of the window."""
+        bs = self.batch_size
+        row = 0
+        for lo in range(e_lo, e_hi, bs):
+            hi = min(lo + bs, e_hi)
+            n = (hi - lo) * seeds_per_edge
+            views, a, b = [], row, row + n
+            for hop in hops:
+                k = hop.nbr_nids.shape[1]
+                views.append(HopSample(hop.seed_nids[a:b], hop.seed_times[a:b], hop.nbr_nids[a:b],
+                                       hop.nbr_edge_time[a:b], hop.nbr_edge_x[a:b]))
+                a, b = a * k, b * k
+            yield lo, hi, views
+            row += n
+
+
+def full_history_neighbors(storage, seed_nodes: Tensor, num_nbrs: int, slice, directed: bool):
+    raise NotImplementedError(
+        'DeviceCOOStorage.get_nbrs (uniform full-history sampling, array_backend.py:108-171) is '
+        'scheduled after the recency path (SURVEY.md section 8f)')
