@@ -140,6 +140,22 @@ int tgm_csr_sample(const tgm_csr *, const int32_t *seeds, const int64_t *tq, con
 int tgm_csr_sample_edges(const tgm_csr *, int64_t e_lo, int64_t e_hi, int32_t B, int32_t k,
                          int32_t *out_nid, int64_t *out_t, float *out_x, tgm_stream stream);
 
+/* Host-buffer form of tgm_csr_sample_edges: what a CPU-resident caller binds (the reference
+ * keeps its arrays on the CPU and moves every batch property with .to(device),
+ * tgm/core/graph.py:232-263, and its CPU hook returns CPU tensors).  Stream-ordered on `stream`:
+ *   1. H2D of the caller's slab of stream edges [e_lo, e_hi) (h_src/h_dst int32[n], h_t int64[n],
+ *      h_x float32[n*D]; any may be NULL = already resident) into the store,
+ *   2. the sampling kernel into a device staging block (`slot` in [0, TGM_HOST_SLOTS) selects
+ *      it, so calls on different streams with different slots overlap),
+ *   3. D2H of out_nid int32[2n*k], out_t int64[2n*k], out_x float32[2n*k*D] to host memory.
+ * The host outputs are valid once `stream` is synchronised; pinned host memory keeps the copies
+ * asynchronous.  The slab written in step 1 must equal what the adjacency was built from. */
+#define TGM_HOST_SLOTS 4
+int tgm_csr_sample_edges_host(tgm_csr *, int64_t e_lo, int64_t e_hi, int32_t B, int32_t k,
+                              const int32_t *h_src, const int32_t *h_dst, const int64_t *h_t,
+                              const float *h_x, int32_t *h_out_nid, int64_t *h_out_t,
+                              float *h_out_x, int slot, tgm_stream stream);
+
 /* ------------------------------------------------------------------------------------------
  * Frontier compaction (hop h+1 seeds = flatten(hop h), recency.py:141-143; the non-padded
  * subset is also what DeduplicationHook keeps, tgm/hooks/dedup.py:44-48).

@@ -1,0 +1,399 @@
+"""GPU parity tests proper: every CUDA path, called through the C ABI (include/tgm_b200.h), must
+reproduce the reference bit-for-bit -- against the committed reference-generated fixtures
+(tests/golden/*.npz) and against the CPU oracle on seeded inputs."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from oracle.c_oracle import CRing
+from oracle.recency_oracle import RingOracle, masked_mean
+from tests._golden import Golden, assert_hop_equal, golden_files, golden_ids
+
+pytestmark = pytest.mark.gpu
+
+from tgm_b200 import (DGData, DGDataLoader, DGraph, HookManager, RecencyCSR,  # noqa: E402
+                      RecencyNeighborHook, _cabi)
+
+DEV = 'cuda:0'
+
+
+def dev(a, dtype):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).to(DEV)
+
+
+def stream():
+    return torch.cuda.current_stream(DEV).cuda_stream
+
+
+class Ring:
+    """tgm_recency_* through ctypes, nothing else."""
+
+    def __init__(self, N, B, D):
+        self.N, self.B, self.D = N, B, D
+        self.h = ctypes.c_void_p()
+        _cabi.check(_cabi.lib.tgm_recency_create(ctypes.byref(self.h), N, B, D, 0))
+
+    def __del__(self):
+        if self.h.value:
+            _cabi.lib.tgm_recency_destroy(self.h)
+            self.h.value = None
+
+    def reset(self):
+        _cabi.check(_cabi.lib.tgm_recency_reset(self.h, stream()))
+
+    def query(self, seeds, tq, k):
+        S = seeds.numel()
+        nid = torch.empty((S, k), dtype=torch.int32, device=DEV)
+        nt = torch.empty((S, k), dtype=torch.int64, device=DEV)
+        nx = torch.empty((S, k, self.D), dtype=torch.float32, device=DEV)
+        _cabi.check(_cabi.lib.tgm_recency_query(self.h, seeds.data_ptr(), tq.data_ptr(), S, k,
+                                                nid.data_ptr(), nt.data_ptr(),
+                                                nx.data_ptr() if self.D else None, stream()))
+        return nid, nt, nx
+
+    def update(self, src, dst, t, x, directed):
+        _cabi.check(_cabi.lib.tgm_recency_update(self.h, src.data_ptr(), dst.data_ptr(),
+                                                 t.data_ptr(), None if x is None else x.data_ptr(),
+                                                 src.numel(), int(directed), stream()))
+
+    def state(self):
+        p = [ctypes.c_void_p() for _ in range(4)]
+        _cabi.check(_cabi.lib.tgm_recency_state(self.h, *[ctypes.byref(q) for q in p]))
+        N, B, D = self.N, self.B, self.D
+        ids = _cabi.device_view(p[0].value, (N, B), torch.int32, DEV).cpu().numpy()
+        times = _cabi.device_view(p[1].value, (N, B), torch.int64, DEV).cpu().numpy()
+        feats = (_cabi.device_view(p[2].value, (N, B, D), torch.float32, DEV).cpu().numpy()
+                 if D else np.zeros((N, B, 0), np.float32))
+        wpos = _cabi.device_view(p[3].value, (N,), torch.int32, DEV).cpu().numpy()
+        return ids, times, feats, wpos
+
+
+def ring_hook_call(ring, num_nbrs, seeds, tq, src, dst, t, x, directed):
+    out = []
+    s, q = seeds, tq
+    for hop, k in enumerate(num_nbrs):
+        if hop:
+            s, q = out[-1][2].reshape(-1), out[-1][3].reshape(-1)
+        nid, nt, nx = ring.query(s, q, k)
+        out.append((s, q, nid, nt, nx))
+    if src.numel():
+        ring.update(src, dst, t, x, directed)
+    return out
+
+
+def to_np(hop):
+    return tuple(v.cpu().numpy() for v in hop)
+
+
+# ---- stateful ring kernels vs reference fixtures ---------------------------------------------
+@pytest.mark.parametrize('path', golden_files(), ids=golden_ids())
+def test_ring_kernels_match_reference_fixture(path):
+    g = Golden(path)
+    ring = Ring(g.N, max(g.num_nbrs), g.D)
+    src, dst, t = dev(g.src, torch.int32), dev(g.dst, torch.int32), dev(g.t, torch.int64)
+    x = None if g.x is None else dev(g.x, torch.float32)
+    for ep in range(g.epochs):
+        if ep:
+            ring.reset()
+        for b, lo, hi in g.batches():
+            s, q = g.seeds(lo, hi)
+            hops = ring_hook_call(ring, g.num_nbrs, dev(s, torch.int32), dev(q, torch.int64),
+                                  src[lo:hi], dst[lo:hi], t[lo:hi],
+                                  None if x is None else x[lo:hi], g.directed)
+            for h, got in enumerate(hops):
+                assert_hop_equal(to_np(got), g.expect(ep, b, h), f'ep{ep} batch{b} hop{h}')
+    ids, times, feats, wpos = ring.state()
+    assert np.array_equal(ids, g.z['final_ids'])
+    assert np.array_equal(times, g.z['final_times'])
+    assert np.array_equal(feats, g.z['final_feats'])
+    assert np.array_equal(wpos, g.z['final_write_pos'])
+
+
+# ---- the drop-in Python face vs reference fixtures --------------------------------------------
+class _InjectNegatives:
+    has_state = False
+    requires = {'edge_src', 'edge_dst', 'edge_time'}
+    produces = {'neg', 'neg_time'}
+
+    def __init__(self, neg):
+        self.neg, self.i = neg, 0
+
+    def __call__(self, dg, batch):
+        n = batch.edge_src.numel()
+        batch.neg = self.neg[self.i:self.i + n].clone()
+        batch.neg_time = batch.edge_time.clone()
+        self.i += n
+        return batch
+
+    def reset_state(self):
+        self.i = 0
+
+
+@pytest.mark.parametrize('path', golden_files(), ids=golden_ids())
+def test_loader_hook_api_matches_reference_fixture(path):
+    """DGData -> DGraph(cuda) -> DGDataLoader -> HookManager -> RecencyNeighborHook: the exact
+    call sequence of tests/golden/make_golden.py, on the B200 path."""
+    g = Golden(path)
+    ei = torch.from_numpy(np.stack([g.src, g.dst], 1).astype(np.int32))
+    data = DGData.from_raw(torch.from_numpy(g.t), ei,
+                           None if g.x is None else torch.from_numpy(g.x))
+    dg = DGraph(data, device=DEV)
+    keys_n, keys_t = ['edge_src', 'edge_dst'], ['edge_time', 'edge_time']
+    hm = HookManager(keys=['g'])
+    if g.neg is not None:
+        hm.register('g', _InjectNegatives(dev(g.neg, torch.int32)))
+        keys_n, keys_t = keys_n + ['neg'], keys_t + ['neg_time']
+    hook = RecencyNeighborHook(num_nodes=g.N, num_nbrs=g.num_nbrs, seed_nodes_keys=keys_n,
+                               seed_times_keys=keys_t, directed=g.directed)
+    hm.register('g', hook)
+    with hm.activate('g'):
+        for ep in range(g.epochs):
+            nb = 0
+            for b, batch in enumerate(DGDataLoader(dg, batch_size=g.bs, hook_manager=hm)):
+                nb += 1
+                for h in range(len(g.num_nbrs)):
+                    got = (batch.seed_nids[h], batch.seed_times[h], batch.nbr_nids[h],
+                           batch.nbr_edge_time[h], batch.nbr_edge_x[h])
+                    assert all(v.is_cuda for v in got)
+                    assert_hop_equal(to_np(got), g.expect(ep, b, h), f'ep{ep} batch{b} hop{h}')
+            assert nb == sum(1 for _ in g.batches())
+            if ep + 1 < g.epochs:
+                hm.reset_state()
+    st = hook.state_tensors()
+    assert np.array_equal(st['ids'].cpu().numpy(), g.z['final_ids'])
+    assert np.array_equal(st['write_pos'].cpu().numpy(), g.z['final_write_pos'])
+
+
+# ---- stateless CSR sampler vs reference fixtures -----------------------------------------------
+def _store_and_csr(g_src, g_dst, g_t, g_x, bs, directed, colocate):
+    ei = torch.from_numpy(np.stack([g_src, g_dst], 1).astype(np.int32))
+    data = DGData.from_raw(torch.from_numpy(np.asarray(g_t, np.int64)), ei,
+                           None if g_x is None else torch.from_numpy(g_x))
+    dg = DGraph(data, device=DEV)
+    return dg, RecencyCSR(dg._storage, bs, directed=directed, colocate_x=colocate)
+
+
+@pytest.mark.parametrize('colocate', [False, True], ids=['eid_rows', 'colocated'])
+@pytest.mark.parametrize('path', golden_files(), ids=golden_ids())
+def test_csr_window_matches_reference_fixture(path, colocate):
+    """One launch per hop for ALL loader batches == the reference driven batch by batch."""
+    g = Golden(path)
+    dg, csr = _store_and_csr(g.src, g.dst, g.t, g.x, g.bs, g.directed, colocate)
+    neg = None if g.neg is None else dev(g.neg, torch.int32)
+    hops = csr.sample_window(0, g.E, g.num_nbrs, neg=neg)
+    per_edge = 2 if neg is None else 3
+    for b, (lo, hi, views) in enumerate(csr.split_window(hops, 0, g.E, per_edge)):
+        for h, v in enumerate(views):
+            got = (v.seed_nids, v.seed_times, v.nbr_nids, v.nbr_edge_time, v.nbr_edge_x)
+            assert_hop_equal(to_np(got), g.expect(0, b, h), f'batch{b} hop{h}')
+
+
+def _random_stream(seed, N, E, T, D, hot=0.0):
+    rng = np.random.default_rng(seed)
+    src, dst = rng.integers(0, N, E), rng.integers(0, N, E)
+    if hot:
+        src = np.where(rng.random(E) < hot, 1, src)
+    t = np.sort(rng.integers(0, T, E))
+    x = rng.standard_normal((E, D)).astype(np.float32) if D else None
+    return src.astype(np.int32), dst.astype(np.int32), t.astype(np.int64), x
+
+
+@pytest.mark.parametrize('cfg', [
+    # N, E, T, D, bs, num_nbrs, directed, hot
+    (2000, 60000, 900, 16, 200, [20], False, 0.0),
+    (300, 40000, 200, 4, 200, [20, 20], False, 0.05),   # > B pushes per node per batch
+    (5000, 50000, 5000, 0, 128, [10, 5], True, 0.0),
+    (64, 30000, 100, 3, 333, [7], False, 0.3),          # D not a multiple of 4 (scalar path)
+    (1000, 30000, 3000, 172, 200, [10], False, 0.0),    # wiki-sized feature rows
+], ids=['k20', 'twohop_hot', 'directed_nofeat', 'odd_D', 'D172'])
+def test_all_three_paths_agree_with_oracle(cfg):
+    """ring kernels == CSR kernels == C oracle == numpy oracle on seeded random streams."""
+    N, E, T, D, bs, nn, directed, hot = cfg
+    src, dst, t, x = _random_stream(7, N, E, T, D, hot)
+    oracle = CRing(N, nn, D, directed)
+    ring = Ring(N, max(nn), D)
+    dsrc, ddst, dt = dev(src, torch.int32), dev(dst, torch.int32), dev(t, torch.int64)
+    dx = None if x is None else dev(x, torch.float32)
+    dg, csr = _store_and_csr(src, dst, t, x, bs, directed, True)
+    hops = csr.sample_window(0, E, nn)
+    check_numpy = RingOracle(N, nn, D, directed) if E <= 40000 else None
+    for b, (lo, hi, views) in enumerate(csr.split_window(hops, 0, E)):
+        s = np.concatenate([src[lo:hi], dst[lo:hi]])
+        q = np.concatenate([t[lo:hi], t[lo:hi]])
+        want = oracle.hook_call(s, q, src[lo:hi], dst[lo:hi], t[lo:hi],
+                                None if x is None else x[lo:hi])
+        got_ring = ring_hook_call(ring, nn, dev(s, torch.int32), dev(q, torch.int64), dsrc[lo:hi],
+                                  ddst[lo:hi], dt[lo:hi], None if dx is None else dx[lo:hi],
+                                  directed)
+        if b % 7 == 0 or hi == E:  # D2H of every batch would dominate the test time
+            for h, w in enumerate(want):
+                v = views[h]
+                assert_hop_equal(to_np((v.seed_nids, v.seed_times, v.nbr_nids, v.nbr_edge_time,
+                                        v.nbr_edge_x)), w, f'csr batch{b} hop{h}')
+                assert_hop_equal(to_np(got_ring[h]), w, f'ring batch{b} hop{h}')
+        if check_numpy is not None:
+            w2 = check_numpy.hook_call(s, q, src[lo:hi], dst[lo:hi], t[lo:hi],
+                                       None if x is None else x[lo:hi])
+            if b % 7 == 0:
+                for h in range(len(nn)):
+                    assert_hop_equal(w2[h], want[h], f'numpy-vs-c batch{b} hop{h}')
+    ids, times, feats, wpos = ring.state()
+    assert np.array_equal(ids, oracle.ids) and np.array_equal(times, oracle.times)
+    assert np.array_equal(feats, oracle.feats) and np.array_equal(wpos, oracle.write_pos)
+
+
+def torch_checksum(v: torch.Tensor, base: int = 0) -> int:
+    """Same position-sensitive checksum as oracle/recency_ring.c, on the device."""
+    flat = v.reshape(-1)
+    if flat.dtype == torch.float32:
+        flat = flat.view(torch.int32)
+    gold = c_oracle.GOLD - (1 << 64)  # as a signed int64
+    total = 0
+    step = 1 << 26
+    for a in range(0, flat.numel(), step):
+        part = flat[a:a + step].to(torch.int64)
+        w = torch.arange(base + a, base + a + part.numel(), dtype=torch.int64, device=v.device)
+        total += int((part * (w * gold + 1)).sum().item())
+    return total % (1 << 64)
+
+
+def test_full_stream_checksums_match_c_oracle():
+    """2M-edge / 1M-node stream (BASELINE configs[1] geometry: bs=200, k=20, D=16), sampled in
+    windows of 1000 loader batches per launch; the checksum of every output element equals the
+    C oracle's, which replays the reference state machine batch by batch."""
+    N, E, T, D, bs, k = 1_000_000, 2_000_000, 2000, 16, 200, 20
+    src, dst, t, x = _random_stream(1, N, E, T, D)
+    slots, want, _ = CRing(N, [k], D).run_stream(src, dst, t, x, 0, E, bs)
+    dg, csr = _store_and_csr(src, dst, t, x, bs, False, True)
+    got = [0, 0, 0]
+    W = 1000 * bs
+    for lo in range(0, E, W):
+        hi = min(lo + W, E)
+        nid, nt, nx = csr.sample_edges(lo, hi, k, k)
+        base = 2 * lo * k
+        got[0] += torch_checksum(nid, base)
+        got[1] += torch_checksum(nt, base)
+        got[2] += torch_checksum(nx, base * D)
+    assert slots == 2 * E * k
+    assert [v % (1 << 64) for v in got] == [int(v) for v in want[0]]
+
+
+# ---- size-independent properties at scale ------------------------------------------------------
+def test_properties_at_scale():
+    """10M-edge stream: (i) every non-padded slot is a true earlier event of the seed with
+    time < tq; (ii) slots are right-aligned and chronologically non-decreasing; (iii) features
+    equal the store row of the (unique) matching edge; (iv) k=20 output's last 10 columns equal
+    a k=10 query with the same window B (prefix property of the right-aligned window)."""
+    N, E, T, D, bs, k = 1_000_000, 10_000_000, 2000, 4, 200, 20
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    src = torch.randint(0, N, (E,), generator=gen, device=DEV, dtype=torch.int32)
+    dst = torch.randint(0, N, (E,), generator=gen, device=DEV, dtype=torch.int32)
+    t = torch.sort(torch.randint(0, T, (E,), generator=gen, device=DEV, dtype=torch.int64))[0]
+    x = torch.randn(E, D, generator=gen, device=DEV)
+    data = DGData.from_raw(t.cpu(), torch.stack([src, dst], 1).cpu(), x.cpu())
+    dg = DGraph(data, device=DEV)
+    csr = RecencyCSR(dg._storage, bs, colocate_x=True)
+    lo, hi = E - 1000 * bs, E
+    nid, nt, nx = csr.sample_edges(lo, hi, k, k)
+    nid10, nt10, nx10 = csr.sample_edges(lo, hi, 10, k)
+    assert torch.equal(nid[:, 10:], nid10) and torch.equal(nt[:, 10:], nt10)
+    assert torch.equal(nx[:, 10:], nx10)
+    valid = nid != -1
+    # right-aligned: once valid, valid to the end
+    assert bool((valid[:, 1:] >= valid[:, :-1]).all())
+    # chronological
+    ok = (nt[:, 1:] >= nt[:, :-1]) | ~valid[:, :-1]
+    assert bool(ok.all())
+    seeds, tq, _ = csr.window_seed_tensors(lo, hi)
+    assert bool(((nt < tq[:, None]) | ~valid).all())
+    assert bool((nt[~valid] == 0).all()) and bool((nx[~valid] == 0).all())
+    assert float(valid.float().mean()) > 0.9  # average degree 20 by then: mostly full rows
+    # every sampled (seed, nbr, time) is an edge of the store: look the pair up by a hash join
+    key = lambda a, b, c: (a.to(torch.int64) * N + b.to(torch.int64)) * T + c
+    edge_keys = torch.cat([key(src, dst, t), key(dst, src, t)])
+    edge_keys = torch.sort(edge_keys)[0]
+    probe = key(seeds[:, None].expand_as(nid)[valid], nid[valid], nt[valid])
+    pos = torch.searchsorted(edge_keys, probe).clamp_(max=edge_keys.numel() - 1)
+    assert bool((edge_keys[pos] == probe).all())
+
+
+# ---- frontier compaction / aggregation --------------------------------------------------------
+@pytest.mark.parametrize('n', [0, 1, 31, 4096, 4097, 1_000_003])
+def test_frontier_compact(n):
+    rng = np.random.default_rng(n)
+    nid = np.where(rng.random(n) < 0.37, -1, rng.integers(0, 1000, n)).astype(np.int32)
+    d = dev(nid, torch.int32)
+    idx = torch.empty(max(n, 1), dtype=torch.int64, device=DEV)
+    cnt = torch.full((1,), -7, dtype=torch.int64, device=DEV)
+    _cabi.check(_cabi.lib.tgm_frontier_compact(d.data_ptr() if n else None, n, idx.data_ptr(),
+                                               cnt.data_ptr(), stream()))
+    want = np.flatnonzero(nid != -1)
+    assert int(cnt.item()) == len(want)
+    assert np.array_equal(idx[:len(want)].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize('S,k,D', [(1, 1, 1), (257, 20, 16), (100, 7, 5), (64, 20, 172)])
+def test_masked_mean_bit_exact(S, k, D):
+    rng = np.random.default_rng(S)
+    z = rng.standard_normal((S, k, D)).astype(np.float32)
+    nid = np.where(rng.random((S, k)) < 0.4, -1, rng.integers(0, 50, (S, k))).astype(np.int32)
+    nid[0] = -1
+    out = torch.empty((S, D), dtype=torch.float32, device=DEV)
+    _cabi.check(_cabi.lib.tgm_masked_mean(dev(z, torch.float32).data_ptr(),
+                                          dev(nid, torch.int32).data_ptr(), S, k, D,
+                                          out.data_ptr(), stream()))
+    want = masked_mean(z, nid)
+    assert np.array_equal(out.cpu().numpy(), want)  # same fp32 operation order: bit-exact
+    assert np.array_equal(c_oracle.masked_mean(z, nid), want)
+
+
+def test_time2vec_within_1e5():
+    """tgm/nn/modules/time_encoding.py:12-24: cos(Linear(1,d)(float(dt))), shipped init
+    w = 1/10^linspace(0,9,d), b = 0, and a trained-like b != 0.  Tolerance 1e-5 (north star)."""
+    d = 100
+    w = (1.0 / 10 ** np.linspace(0, 9, d)).astype(np.float32)
+    rng = np.random.default_rng(0)
+    dt = np.concatenate([rng.integers(0, 2_700_000, 5000), [0, 1, 2_678_373]]).astype(np.int64)
+    for b in (np.zeros(d, np.float32), rng.standard_normal(d).astype(np.float32)):
+        out = torch.empty((len(dt), d), dtype=torch.float32, device=DEV)
+        _cabi.check(_cabi.lib.tgm_time2vec(dev(dt, torch.int64).data_ptr(), len(dt),
+                                           dev(w, torch.float32).data_ptr(),
+                                           dev(b, torch.float32).data_ptr(), d, out.data_ptr(),
+                                           stream()))
+        lin = torch.nn.Linear(1, d)
+        with torch.no_grad():
+            lin.weight.copy_(torch.from_numpy(w).reshape(d, 1))
+            lin.bias.copy_(torch.from_numpy(b))
+            want = torch.cos(lin(torch.from_numpy(dt).float().unsqueeze(-1)))
+        assert float((out.cpu() - want).abs().max()) <= 1e-5
+
+
+# ---- error behaviour of the C ABI on a live device --------------------------------------------
+def test_query_argument_errors():
+    ring = Ring(8, 4, 0)
+    s = torch.zeros(2, dtype=torch.int32, device=DEV)
+    q = torch.zeros(2, dtype=torch.int64, device=DEV)
+    with pytest.raises(_cabi.TGMNativeError, match='k must be in'):
+        ring.query(s, q, 5)
+    rc = _cabi.lib.tgm_recency_query(ring.h, None, None, 2, 2, None, None, None, None)
+    assert rc == -1 and 'NULL' in _cabi.last_error()
+
+
+def test_hook_validates_seeds_like_the_reference():
+    """recency.py:208-229: ids outside [0, N) and negative times raise ValueError."""
+    ei = torch.tensor([[0, 1], [1, 2]], dtype=torch.int32)
+    dg = DGraph(DGData.from_raw(torch.tensor([1, 2]), ei), device=DEV)
+    hook = RecencyNeighborHook(num_nodes=2, num_nbrs=[1], seed_nodes_keys=['edge_dst'],
+                               seed_times_keys=['edge_time'])
+    with pytest.raises(ValueError, match='must satisfy'):
+        hook(dg, dg.materialize())
+    hook = RecencyNeighborHook(num_nodes=3, num_nbrs=[1], seed_nodes_keys=['foo'],
+                               seed_times_keys=['bar'])
+    batch = dg.materialize()
+    batch.foo = torch.tensor([0], dtype=torch.int32, device=DEV)
+    batch.bar = torch.tensor([-1], dtype=torch.int64, device=DEV)
+    with pytest.raises(ValueError, match='must be >= 0'):
+        hook(dg, batch)

@@ -3,14 +3,17 @@ fixtures (tests/golden/make_golden.py).  CPU only."""
 import numpy as np
 import pytest
 
+from oracle import c_oracle
+from oracle.c_oracle import CRing
 from oracle.recency_oracle import PADDED_NODE_ID, RingOracle, masked_mean, stateless_sample
 from tests._golden import Golden, assert_hop_equal, golden_files, golden_ids
 
 
+@pytest.mark.parametrize('impl', [RingOracle, CRing], ids=['numpy', 'c'])
 @pytest.mark.parametrize('path', golden_files(), ids=golden_ids())
-def test_ring_oracle_matches_reference_fixture(path):
+def test_ring_oracle_matches_reference_fixture(path, impl):
     g = Golden(path)
-    ring = RingOracle(g.N, g.num_nbrs, g.D, g.directed)
+    ring = impl(g.N, g.num_nbrs, g.D, g.directed)
     for ep in range(g.epochs):
         if ep:
             ring.reset_state()
@@ -105,3 +108,54 @@ def test_masked_mean_kat():
     ids = np.array([[-1, 4, 5], [-1, -1, -1]], np.int32)
     out = masked_mean(z, ids)
     assert np.allclose(out[0], (z[0, 1] + z[0, 2]) / 2) and (out[1] == 0).all()
+
+
+@pytest.mark.parametrize('path', golden_files(), ids=golden_ids())
+def test_c_run_stream_checksums_match_fixture(path):
+    """ring_run_stream (the full-size checker) reproduces the fixture's outputs and its running
+    checksums equal checksum_np over the concatenated per-batch expectations."""
+    g = Golden(path)
+    if g.neg is not None:
+        pytest.skip('run_stream drives the [src | dst] seed layout only')
+    ring = CRing(g.N, g.num_nbrs, g.D, g.directed)
+    slots, csum, outs = ring.run_stream(g.src, g.dst, g.t, g.x, 0, g.E, g.bs, keep_hop0=True)
+    nb = sum(1 for _ in g.batches())
+    want_slots = 0
+    for h in range(len(g.num_nbrs)):
+        cat = [np.concatenate([g.expect(0, b, h)[i] for b in range(nb)]) for i in (2, 3, 4)]
+        want_slots += cat[0].size
+        assert int(csum[h, 0]) == c_oracle.checksum_np(cat[0])
+        assert int(csum[h, 1]) == c_oracle.checksum_np(cat[1])
+        if g.D:
+            assert int(csum[h, 2]) == c_oracle.checksum_np(cat[2])
+        if h == 0:
+            for got, want in zip(outs, cat):
+                assert np.array_equal(got, want)
+    assert slots == want_slots
+
+
+def test_c_masked_mean_equals_numpy_oracle():
+    rng = np.random.default_rng(3)
+    z = rng.standard_normal((50, 7, 12)).astype(np.float32)
+    ids = np.where(rng.random((50, 7)) < 0.4, -1, rng.integers(0, 9, (50, 7))).astype(np.int32)
+    ids[0] = -1
+    assert np.array_equal(c_oracle.masked_mean(z, ids), masked_mean(z, ids))
+
+
+def test_c_oracle_equals_numpy_oracle_on_a_larger_stream():
+    rng = np.random.default_rng(11)
+    N, E, T, D, bs, nn = 500, 20000, 400, 4, 200, [20, 5]
+    src, dst = rng.integers(0, N, E), rng.integers(0, N, E)
+    src = np.where(rng.random(E) < 0.2, 3, src)  # hot node: > B pushes per batch
+    t = np.sort(rng.integers(0, T, E))
+    x = rng.standard_normal((E, D)).astype(np.float32)
+    a, b = RingOracle(N, nn, D), CRing(N, nn, D)
+    for lo in range(0, E, bs):
+        hi = lo + bs
+        s = np.concatenate([src[lo:hi], dst[lo:hi]]).astype(np.int32)
+        q = np.concatenate([t[lo:hi], t[lo:hi]]).astype(np.int64)
+        ha = a.hook_call(s, q, src[lo:hi], dst[lo:hi], t[lo:hi], x[lo:hi])
+        hb = b.hook_call(s, q, src[lo:hi], dst[lo:hi], t[lo:hi], x[lo:hi])
+        for h, (u, v) in enumerate(zip(ha, hb)):
+            assert_hop_equal(v, u, f'edge {lo} hop{h}')
+    assert np.array_equal(a.ids, b.ids) and np.array_equal(a.write_pos, b.write_pos)

@@ -63,6 +63,9 @@ SIGNATURES = {
                                c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     'tgm_csr_sample_edges': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
+    'tgm_csr_sample_edges_host': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_int, c_void_p]),
     'tgm_frontier_compact': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'tgm_masked_mean': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p,
                                 c_void_p]),

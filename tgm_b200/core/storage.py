@@ -129,6 +129,38 @@ class DeviceCOOStorage(DGStorageBase):
             self._t.data_ptr(), _cabi.ptr(self._x), self._E, self._D, self._num_nodes, dev.index,
             _cabi.TGM_MEM_DEVICE, self._edge_time_host.data_ptr()))
 
+    @classmethod
+    def from_device_tensors(cls, src: Tensor, dst: Tensor, t: Tensor, x: Optional[Tensor],
+                            num_nodes: int) -> 'DeviceCOOStorage':
+        """Adopt an edge stream that already lives in HBM (src/dst int32[E], t int64[E] sorted,
+        x float32[E,D] or None) without a host DGData mirror.  Serves the samplers and the edge
+        getters; getters that need host-side node events / labels are not available."""
+        if not (src.is_cuda and dst.is_cuda and t.is_cuda and (x is None or x.is_cuda)):
+            raise _cabi.TGMNativeError(-1, 'from_device_tensors needs CUDA tensors')
+        if src.dtype != torch.int32 or dst.dtype != torch.int32 or t.dtype != torch.int64:
+            raise TypeError('src/dst must be int32 and t int64')
+        if x is not None and (x.dtype != torch.float32 or x.ndim != 2 or x.shape[0] != src.numel()):
+            raise TypeError('x must be float32 [E, D]')
+        self = cls.__new__(cls)
+        self._data = None
+        self._device = src.device
+        self._E, self._D = int(src.numel()), 0 if x is None else int(x.shape[1])
+        self._num_nodes = int(num_nodes)
+        self._edge_only = True
+        self._edge_time_host = t.cpu()
+        self._time_np = self._edge_time_host.numpy()
+        self._edge_pos_np = None
+        self._node_cache = {}
+        self._src, self._dst, self._t = src.contiguous(), dst.contiguous(), t.contiguous()
+        self._x = None if x is None else x.contiguous()
+        self._edge_type = None
+        self._handle = ctypes.c_void_p()
+        _cabi.check(_cabi.lib.tgm_store_create(
+            ctypes.byref(self._handle), self._src.data_ptr(), self._dst.data_ptr(),
+            self._t.data_ptr(), _cabi.ptr(self._x), self._E, self._D, self._num_nodes,
+            self._device.index, _cabi.TGM_MEM_DEVICE, self._edge_time_host.data_ptr()))
+        return self
+
     def __del__(self, _destroy=_cabi.lib.tgm_store_destroy) -> None:
         h = getattr(self, '_handle', None)
         if h is not None and h.value:
@@ -151,6 +183,10 @@ class DeviceCOOStorage(DGStorageBase):
     @property
     def num_nodes_global(self) -> int:
         return self._num_nodes
+
+    @property
+    def _has_edge_x(self) -> bool:
+        return self._x is not None if self._data is None else self._data.edge_x is not None
 
     def _require_device(self) -> None:
         if self._device is None:
@@ -223,14 +259,14 @@ class DeviceCOOStorage(DGStorageBase):
         return self._src[lo:hi], self._dst[lo:hi], self._t[lo:hi]
 
     def get_edge_x(self, slice: DGSliceTracker) -> Optional[Tensor]:
-        if self._data.edge_x is None:
+        if not self._has_edge_x:
             return None
         self._require_device()
         lo, hi = self.edge_range(slice)
         return None if hi <= lo else self._x[lo:hi]  # None on an empty slice (:264-266)
 
     def get_edge_type(self, slice: DGSliceTracker) -> Optional[Tensor]:
-        if self._data.edge_type is None:
+        if self._edge_type is None and (self._data is None or self._data.edge_type is None):
             return None
         self._require_device()
         lo, hi = self.edge_range(slice)
@@ -295,7 +331,7 @@ class DeviceCOOStorage(DGStorageBase):
         return None if self._data.node_y is None else int(self._data.node_y.shape[1])
 
     def get_edge_x_dim(self) -> Optional[int]:
-        return None if self._data.edge_x is None else self._D
+        return self._D if self._has_edge_x else None
 
     def get_static_node_x_dim(self) -> Optional[int]:
         sx = self._data.static_node_x

@@ -34,6 +34,13 @@ struct tgm_csr {
   int64_t *rowptr = nullptr;
   uint2 *anchors = nullptr;  // [2][Ew]
   float *xrows = nullptr;    // [n, D] when colocate
+  // device staging of the host-buffer entry point: one output block per slot, grown on demand
+  struct Stage {
+    int32_t *nid = nullptr;
+    int64_t *t = nullptr;
+    float *x = nullptr;
+    int64_t cells = 0;  // capacity in (seed, slot) cells
+  } stage[TGM_HOST_SLOTS];
   ~tgm_csr() {
     if (device >= 0) {
       DeviceGuard g(device);
@@ -41,6 +48,11 @@ struct tgm_csr {
       cudaFree(rowptr);
       cudaFree(anchors);
       cudaFree(xrows);
+      for (auto &st : stage) {
+        cudaFree(st.nid);
+        cudaFree(st.t);
+        cudaFree(st.x);
+      }
     }
   }
 };
@@ -488,5 +500,53 @@ extern "C" int tgm_csr_sample_edges(const tgm_csr *c, int64_t e_lo, int64_t e_hi
                   c->store->t + c->e_start, c->D, c->Ew, c->bs, l_lo, l_hi, B, k, out_nid, out_t,
                   out_x);
   TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+
+
+// Host-buffer form: H2D of the slab, the same kernel, D2H of the outputs, all on `stream`.
+extern "C" int tgm_csr_sample_edges_host(tgm_csr *c, int64_t e_lo, int64_t e_hi, int32_t B,
+                                         int32_t k, const int32_t *h_src, const int32_t *h_dst,
+                                         const int64_t *h_t, const float *h_x, int32_t *h_out_nid,
+                                         int64_t *h_out_t, float *h_out_x, int slot,
+                                         tgm_stream stream) {
+  TGM_REQUIRE(c != nullptr, "tgm_csr_sample_edges_host: csr is NULL");
+  TGM_REQUIRE(slot >= 0 && slot < TGM_HOST_SLOTS, "tgm_csr_sample_edges_host: bad slot");
+  const int64_t l_lo = e_lo - c->e_start, l_hi = e_hi - c->e_start;
+  TGM_REQUIRE(l_lo >= 0 && l_lo <= l_hi && l_hi <= c->Ew,
+              "tgm_csr_sample_edges_host: [e_lo, e_hi) outside the indexed stream");
+  const int64_t nE = e_hi - e_lo, cells = 2 * nE * k;
+  if (nE == 0) return TGM_OK;
+  TGM_REQUIRE(h_out_nid && h_out_t, "tgm_csr_sample_edges_host: NULL output argument");
+  TGM_REQUIRE(c->D == 0 || h_out_x, "tgm_csr_sample_edges_host: h_out_x is NULL but D > 0");
+  DeviceGuard g(c->device);
+  cudaStream_t st = as_stream(stream);
+  const tgm_store *s = c->store;
+  const size_t D = size_t(c->D);
+  // the slab of the window as the caller holds it on the host (the reference keeps its arrays on
+  // the CPU and copies each batch's properties to the device, tgm/core/graph.py:232-263)
+  if (h_src) TGM_CUDA(cudaMemcpyAsync(const_cast<int32_t *>(s->src) + e_lo, h_src, size_t(nE) * 4,
+                                      cudaMemcpyHostToDevice, st));
+  if (h_dst) TGM_CUDA(cudaMemcpyAsync(const_cast<int32_t *>(s->dst) + e_lo, h_dst, size_t(nE) * 4,
+                                      cudaMemcpyHostToDevice, st));
+  if (h_t) TGM_CUDA(cudaMemcpyAsync(const_cast<int64_t *>(s->t) + e_lo, h_t, size_t(nE) * 8,
+                                    cudaMemcpyHostToDevice, st));
+  if (h_x && D) TGM_CUDA(cudaMemcpyAsync(const_cast<float *>(s->x) + size_t(e_lo) * D, h_x,
+                                         size_t(nE) * D * 4, cudaMemcpyHostToDevice, st));
+  tgm_csr::Stage &sg = c->stage[slot];
+  if (cells > sg.cells) {  // growing is the only synchronising path
+    TGM_CUDA(cudaStreamSynchronize(st));
+    cudaFree(sg.nid), cudaFree(sg.t), cudaFree(sg.x);
+    sg = tgm_csr::Stage();
+    TGM_CUDA(cudaMalloc(&sg.nid, size_t(cells) * 4));
+    TGM_CUDA(cudaMalloc(&sg.t, size_t(cells) * 8));
+    if (D) TGM_CUDA(cudaMalloc(&sg.x, size_t(cells) * D * 4));
+    sg.cells = cells;
+  }
+  int rc = tgm_csr_sample_edges(c, e_lo, e_hi, B, k, sg.nid, sg.t, sg.x, stream);
+  if (rc != TGM_OK) return rc;
+  TGM_CUDA(cudaMemcpyAsync(h_out_nid, sg.nid, size_t(cells) * 4, cudaMemcpyDeviceToHost, st));
+  TGM_CUDA(cudaMemcpyAsync(h_out_t, sg.t, size_t(cells) * 8, cudaMemcpyDeviceToHost, st));
+  if (D) TGM_CUDA(cudaMemcpyAsync(h_out_x, sg.x, size_t(cells) * D * 4, cudaMemcpyDeviceToHost, st));
   return TGM_OK;
 }

@@ -91,6 +91,20 @@ class RecencyCSR:
             nx.data_ptr() if self.D else None, _cabi.current_stream(self.device)))
         return nid, nt, nx
 
+    def sample_edges_host(self, e_lo: int, e_hi: int, k: int, B: int, host_in, host_out,
+                          slot: int = 0, stream: Optional[int] = None) -> None:
+        """Host-buffer form (tgm_csr_sample_edges_host): `host_in` = (src, dst, t, x) CPU tensors
+        of the slab [e_lo, e_hi) (entries may be None), `host_out` = (nid, t, x) CPU tensors
+        receiving the result; pinned tensors keep the copies asynchronous.  Stream-ordered: the
+        outputs are valid after the stream is synchronised."""
+        src, dst, t, x = host_in
+        nid, nt, nx = host_out
+        _cabi.check(_cabi.lib.tgm_csr_sample_edges_host(
+            self._handle, int(e_lo), int(e_hi), int(B), int(k), _cabi.ptr(src), _cabi.ptr(dst),
+            _cabi.ptr(t), _cabi.ptr(x), nid.data_ptr(), nt.data_ptr(),
+            nx.data_ptr() if self.D else None, int(slot),
+            _cabi.current_stream(self.device) if stream is None else stream))
+
     # -- whole windows ----------------------------------------------------------------------
     def window_seed_tensors(self, e_lo: int, e_hi: int, neg: Optional[Tensor] = None):
         """hop-0 seeds/times/cuts of the window laid out batch by batch in the reference's
