@@ -226,9 +226,10 @@ def run_b200(a):
     torch.cuda.synchronize(dev)
     t_build = time.perf_counter() - t_build
 
-    # this rank's time-range shard of the batch stream
-    nbatch = (E + bs - 1) // bs
-    b_lo, b_hi = nbatch * rank // world, nbatch * (rank + 1) // world
+    # this rank's time-range shard of the batch stream (tgm_b200/parallel.py)
+    from tgm_b200.parallel import shard_batches
+    shard = shard_batches(E, bs, rank, world)
+    b_lo, b_hi = shard.batch_lo, shard.batch_hi
     W = min(a.window_batches, b_hi - b_lo)
     nwin = max(1, (b_hi - b_lo) // W)
 

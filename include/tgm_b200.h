@@ -171,8 +171,9 @@ int tgm_frontier_compact(const int32_t *nid, int64_t n, int64_t *out_idx, int64_
  *   fp32.  z float32[S*k*D], nid int32[S*k], out float32[S*D]. */
 int tgm_masked_mean(const float *z, const int32_t *nid, int64_t S, int32_t k, int32_t D,
                     float *out, tgm_stream stream);
-/* Time2Vec (tgm/nn/modules/time_encoding.py:22-24): out[i,j] = cosf(float(dt[i]) * w[j] + b[j])
- * with one rounding for the product and one for the sum (no FMA contraction), full-range cosf.
+/* Time2Vec (tgm/nn/modules/time_encoding.py:22-24): out[i,j] = cosf(fma(float(dt[i]), w[j], b[j]))
+ * -- a single rounding of the argument, as the reference's batched nn.Linear(1,d) GEMM does --
+ * and full-range cosf.
  * dt int64[n], w,b float32[d], out float32[n*d]. */
 int tgm_time2vec(const int64_t *dt, int64_t n, const float *w, const float *b, int32_t d,
                  float *out, tgm_stream stream);

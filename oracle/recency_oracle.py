@@ -201,3 +201,17 @@ def masked_mean(z: np.ndarray, nbr_nids: np.ndarray) -> np.ndarray:
         acc = acc + z[:, c, :] * mask[:, c, None].astype(np.float32)
     cnt = np.clip(mask.sum(1, keepdims=True), 1, None).astype(np.float32)
     return (acc / cnt).astype(np.float32)
+
+
+def time2vec(dt: np.ndarray, w: np.ndarray, b: np.ndarray, fused: bool = True) -> np.ndarray:
+    """tgm/nn/modules/time_encoding.py:22-24: cos(Linear(1,d)(float32(dt))).  Returned in float64:
+    the exact cosine of the float32 argument.  `fused` selects how Linear rounds x*w+b: once
+    (FMA; torch's batched CPU GEMM in the build container) or twice (product, then sum; torch's
+    single-row GEMV path).  The two coincide when b == 0 (the shipped init, :20)."""
+    x = np.asarray(dt).astype(np.float32)[:, None]
+    w32, b32 = np.asarray(w, np.float32)[None, :], np.asarray(b, np.float32)[None, :]
+    if fused:  # the float64 product of two float32 is exact; one rounding to float32 at the end
+        arg = (x.astype(np.float64) * w32.astype(np.float64) + b32.astype(np.float64)).astype(np.float32)
+    else:
+        arg = (x * w32).astype(np.float32) + b32
+    return np.cos(arg.astype(np.float64))

@@ -342,8 +342,8 @@ def test_masked_mean_bit_exact(S, k, D):
     nid = np.where(rng.random((S, k)) < 0.4, -1, rng.integers(0, 50, (S, k))).astype(np.int32)
     nid[0] = -1
     out = torch.empty((S, D), dtype=torch.float32, device=DEV)
-    _cabi.check(_cabi.lib.tgm_masked_mean(dev(z, torch.float32).data_ptr(),
-                                          dev(nid, torch.int32).data_ptr(), S, k, D,
+    dz, dnid = dev(z, torch.float32), dev(nid, torch.int32)  # keep the inputs alive over the call
+    _cabi.check(_cabi.lib.tgm_masked_mean(dz.data_ptr(), dnid.data_ptr(), S, k, D,
                                           out.data_ptr(), stream()))
     want = masked_mean(z, nid)
     assert np.array_equal(out.cpu().numpy(), want)  # same fp32 operation order: bit-exact
@@ -351,24 +351,27 @@ def test_masked_mean_bit_exact(S, k, D):
 
 
 def test_time2vec_within_1e5():
-    """tgm/nn/modules/time_encoding.py:12-24: cos(Linear(1,d)(float(dt))), shipped init
-    w = 1/10^linspace(0,9,d), b = 0, and a trained-like b != 0.  Tolerance 1e-5 (north star)."""
+    """tgm/nn/modules/time_encoding.py:12-24: cos(Linear(1,d)(float(dt))) with the shipped init
+    w = 1/10^linspace(0,9,d), b = 0 -- and a trained-like b != 0.  Tolerance 1e-5 (north star).
+
+    The argument reaches 2.7e6 (ulp 0.25), so whether Linear rounds x*w+b once (fused) or twice
+    decides the result; torch itself differs between BLAS paths/CPUs (tests/test_oracle_golden.py
+    ::test_time2vec_oracle_pins_torch_linear).  With b = 0 both forms coincide and the bar is
+    1e-5 against the float64 cosine of the float32 argument.  With b != 0 the kernel implements
+    the fused form (what torch's batched CPU GEMM does in the build container) and is held to
+    1e-5 against exactly that."""
+    from oracle.recency_oracle import time2vec
     d = 100
     w = (1.0 / 10 ** np.linspace(0, 9, d)).astype(np.float32)
     rng = np.random.default_rng(0)
     dt = np.concatenate([rng.integers(0, 2_700_000, 5000), [0, 1, 2_678_373]]).astype(np.int64)
     for b in (np.zeros(d, np.float32), rng.standard_normal(d).astype(np.float32)):
         out = torch.empty((len(dt), d), dtype=torch.float32, device=DEV)
-        _cabi.check(_cabi.lib.tgm_time2vec(dev(dt, torch.int64).data_ptr(), len(dt),
-                                           dev(w, torch.float32).data_ptr(),
-                                           dev(b, torch.float32).data_ptr(), d, out.data_ptr(),
-                                           stream()))
-        lin = torch.nn.Linear(1, d)
-        with torch.no_grad():
-            lin.weight.copy_(torch.from_numpy(w).reshape(d, 1))
-            lin.bias.copy_(torch.from_numpy(b))
-            want = torch.cos(lin(torch.from_numpy(dt).float().unsqueeze(-1)))
-        assert float((out.cpu() - want).abs().max()) <= 1e-5
+        ddt, dw, db = dev(dt, torch.int64), dev(w, torch.float32), dev(b, torch.float32)
+        _cabi.check(_cabi.lib.tgm_time2vec(ddt.data_ptr(), len(dt), dw.data_ptr(), db.data_ptr(),
+                                           d, out.data_ptr(), stream()))
+        want = time2vec(dt, w, b, fused=True)
+        assert float(np.abs(out.cpu().numpy().astype(np.float64) - want).max()) <= 1e-5
 
 
 # ---- error behaviour of the C ABI on a live device --------------------------------------------

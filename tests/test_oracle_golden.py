@@ -159,3 +159,31 @@ def test_c_oracle_equals_numpy_oracle_on_a_larger_stream():
         for h, (u, v) in enumerate(zip(ha, hb)):
             assert_hop_equal(v, u, f'edge {lo} hop{h}')
     assert np.array_equal(a.ids, b.ids) and np.array_equal(a.write_pos, b.write_pos)
+
+
+def test_time2vec_oracle_pins_torch_linear():
+    """The Time2Vec oracle against the live torch module arithmetic (time_encoding.py:12-24).
+    b = 0 (shipped init): torch's argument equals the oracle's bit for bit and the cosine agrees
+    to 1e-6.  b != 0: every torch argument equals the fused or the two-rounding form (which one
+    depends on the BLAS path), so only that pair is a well-posed target."""
+    import torch
+    from oracle.recency_oracle import time2vec
+    d = 100
+    w = (1.0 / 10 ** np.linspace(0, 9, d)).astype(np.float32)
+    rng = np.random.default_rng(0)
+    dt = rng.integers(0, 2_700_000, 2000).astype(np.int64)
+    lin = torch.nn.Linear(1, d)
+    for b in (np.zeros(d, np.float32), rng.standard_normal(d).astype(np.float32)):
+        with torch.no_grad():
+            lin.weight.copy_(torch.from_numpy(w).reshape(d, 1))
+            lin.bias.copy_(torch.from_numpy(b))
+            arg = lin(torch.from_numpy(dt).float().unsqueeze(-1))
+            out = torch.cos(arg).numpy()
+        arg = arg.numpy()
+        x = dt.astype(np.float32)[:, None]
+        fused = (x.astype(np.float64) * w.astype(np.float64) + b.astype(np.float64)).astype(np.float32)
+        twice = (x * w).astype(np.float32) + b
+        assert ((arg == fused) | (arg == twice)).all()
+        if not b.any():
+            assert (arg == fused).all() and (fused == twice).all()
+            assert np.abs(out - time2vec(dt, w, b)).max() <= 1e-6

@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libtgm_b200.so')
+LIB_PATH = os.environ.get('TGM_B200_LIB') or os.path.join(_HERE, 'csrc', 'libtgm_b200.so')
 
 TGM_MEM_DEVICE, TGM_MEM_HOST = 0, 1
 

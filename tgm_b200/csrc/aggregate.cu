@@ -55,8 +55,11 @@ masked_mean_kernel(const float *__restrict__ z, const int32_t *__restrict__ nid,
   }
 }
 
-// out[i,j] = cosf(fl(float(dt[i]) * w[j]) + b[j]): int64 -> fp32 cast (time_encoding.py:23), one
-// rounding for the product, one for the sum (nn.Linear(1,d) on CPU), full-range cosf.
+// out[i,j] = cosf(fma(float(dt[i]), w[j], b[j])): int64 -> fp32 cast (time_encoding.py:23), then
+// nn.Linear(1,d), whose batched CPU GEMM (and cuBLAS on the reference's CUDA path) fuses the
+// multiply-add into ONE rounding -- verified against torch CPU: 100% of arguments equal the fused
+// form, 80% the two-rounding form; with arguments up to 2.7e6 (ulp 0.25) the choice decides the
+// result.  Full-range cosf (no fast-math).
 __global__ void __launch_bounds__(256)
 time2vec_kernel(const int64_t *__restrict__ dt, int64_t n, const float *__restrict__ w,
                 const float *__restrict__ b, int d, float *__restrict__ out) {
@@ -66,7 +69,7 @@ time2vec_kernel(const int64_t *__restrict__ dt, int64_t n, const float *__restri
     const int64_t r = i / d;
     const int j = int(i - r * d);
     const float x = float(dt[r]);
-    out[i] = cosf(__fadd_rn(__fmul_rn(x, __ldg(w + j)), __ldg(b + j)));
+    out[i] = cosf(__fmaf_rn(x, __ldg(w + j), __ldg(b + j)));
   }
 }
 

@@ -82,6 +82,26 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4 *p) {
                : "l"(p));
   return r;
 }
+// one adjacency entry as a single streaming 128-bit load
+__device__ __forceinline__ Entry ldg_stream_entry(const Entry *p) {
+  int32_t a, b;
+  int64_t c;
+  asm volatile("{\n\t.reg .b64 lo;\n\t"
+               "ld.global.nc.L1::no_allocate.v2.b64 {lo, %2}, [%3];\n\t"
+               "mov.b64 {%0, %1}, lo;\n\t}"
+               : "=r"(a), "=r"(b), "=l"(c)
+               : "l"(p));
+  Entry e;
+  e.nbr = a;
+  e.eid = b;
+  e.t = c;
+  return e;
+}
+__device__ __forceinline__ int64_t shfl_i64(int64_t v, int src_lane) {
+  int lo = __shfl_sync(0xffffffffu, int(uint64_t(v) & 0xffffffffull), src_lane);
+  int hi = __shfl_sync(0xffffffffu, int(uint64_t(v) >> 32), src_lane);
+  return int64_t((uint64_t(uint32_t(hi)) << 32) | uint64_t(uint32_t(lo)));
+}
 __device__ __forceinline__ void stg_stream_f4(float4 *p, const float4 &v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
                "f"(v.y), "f"(v.z), "f"(v.w)

@@ -297,6 +297,162 @@ csr_sample_edges_kernel(const Entry *__restrict__ entries, const uint2 *__restri
   }
 }
 
+// ---- fast path: B <= 32, features colocated (or absent) ---------------------------------------
+// A warp owns 32 consecutive seeds.  Prologue, lane-parallel: lane i resolves seed i's window
+// (one coalesced anchor/time load, or a private binary search for general seeds).  Then the warp
+// walks its 32 seeds: lane j holds window entry j (ONE 128-bit load per lane, issued one seed
+// ahead), a ballot finds the right-most entry with t < tq, shuffles route entries to their
+// output columns, and because the features are colocated the k-gather is a single contiguous
+// copy of nvalid*D floats -- no per-row indexing, no shared memory.
+constexpr int kFastThreads = 256;
+#ifndef TGM_FAST_MIN_BLOCKS
+#define TGM_FAST_MIN_BLOCKS 6
+#endif
+
+struct SeedWin {
+  int64_t wstart;  // first visible-window entry
+  int nwin;        // window length (<= B <= 32)
+  int64_t q;       // query time
+};
+
+__device__ __forceinline__ Entry load_window_entry(const Entry *__restrict__ entries,
+                                                   int64_t wstart, int nwin, int lane) {
+  Entry e;
+  e.nbr = TGM_PADDED_NODE_ID;
+  e.eid = 0;
+  e.t = 0;
+  if (lane < nwin) e = ldg_stream_entry(entries + wstart + lane);
+  return e;
+}
+
+__device__ __forceinline__ void emit_fast(const float4 *__restrict__ x4, int D4, int64_t wstart,
+                                          int nwin, int64_t q, int k, int64_t s, const Entry &cur,
+                                          int32_t *__restrict__ out_nid,
+                                          int64_t *__restrict__ out_t, float4 *__restrict__ out_x4,
+                                          int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, lane < nwin && cur.t < q);
+  const int last = m ? 31 - __clz(m) : -1;  // recency.py:267-281
+  const int nvalid = last + 1 < k ? last + 1 : k;
+  const int first = last + 1 - nvalid, pad = k - nvalid;
+  const int srcl = (first + lane - pad) & 31;
+  const int32_t nbr = __shfl_sync(0xffffffffu, cur.nbr, srcl);
+  const int64_t tt = shfl_i64(cur.t, srcl);
+  if (lane < k) {  // right-aligned, left-padded with (-1, 0) (:287-319)
+    const bool v = lane >= pad;
+    out_nid[s * k + lane] = v ? nbr : TGM_PADDED_NODE_ID;
+    out_t[s * k + lane] = v ? tt : 0;
+  }
+  if (D4 > 0) {
+    float4 *o4 = out_x4 + s * int64_t(k) * D4;
+    const int npad4 = pad * D4;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = lane; i < npad4; i += 32) stg_stream_f4(o4 + i, zero);
+    o4 += npad4;
+    const float4 *src = x4 + (wstart + first) * D4;
+    const int n4 = nvalid * D4;
+    int i = lane;
+    for (; i + 96 < n4; i += 128) {
+      const float4 a = ldg_stream_f4(src + i), b = ldg_stream_f4(src + i + 32),
+                   c = ldg_stream_f4(src + i + 64), d = ldg_stream_f4(src + i + 96);
+      stg_stream_f4(o4 + i, a);
+      stg_stream_f4(o4 + i + 32, b);
+      stg_stream_f4(o4 + i + 64, c);
+      stg_stream_f4(o4 + i + 96, d);
+    }
+    if (i + 32 < n4) {
+      const float4 a = ldg_stream_f4(src + i), b = ldg_stream_f4(src + i + 32);
+      stg_stream_f4(o4 + i, a);
+      stg_stream_f4(o4 + i + 32, b);
+      i += 64;
+    }
+    for (; i < n4; i += 32) stg_stream_f4(o4 + i, ldg_stream_f4(src + i));
+  }
+}
+
+// walk the (up to) 32 seeds whose windows the lanes resolved
+__device__ __forceinline__ void walk_chunk(const Entry *__restrict__ entries,
+                                           const float4 *__restrict__ x4, int D4,
+                                           const SeedWin &mine, int64_t s_base, int nseeds, int k,
+                                           int32_t *__restrict__ out_nid,
+                                           int64_t *__restrict__ out_t,
+                                           float4 *__restrict__ out_x4, int lane) {
+  int64_t wstart = shfl_i64(mine.wstart, 0);
+  int nwin = __shfl_sync(0xffffffffu, mine.nwin, 0);
+  Entry cur = load_window_entry(entries, wstart, nwin, lane);
+  for (int i = 0; i < nseeds; ++i) {
+    const int64_t q = shfl_i64(mine.q, i);
+    const int nxt = i + 1 < nseeds ? i + 1 : i;
+    const int64_t wstart_n = shfl_i64(mine.wstart, nxt);
+    const int nwin_n = __shfl_sync(0xffffffffu, mine.nwin, nxt);
+    const Entry ahead = load_window_entry(entries, wstart_n, nwin_n, lane);  // one seed ahead
+    emit_fast(x4, D4, wstart, nwin, q, k, s_base + i, cur, out_nid, out_t, out_x4, lane);
+    cur = ahead;
+    wstart = wstart_n;
+    nwin = nwin_n;
+  }
+}
+
+__global__ void __launch_bounds__(kFastThreads, TGM_FAST_MIN_BLOCKS)
+csr_sample_edges_fast_kernel(const Entry *__restrict__ entries, const uint2 *__restrict__ anchors,
+                             const float4 *__restrict__ x4, const int64_t *__restrict__ t, int D4,
+                             int64_t Ew, uint32_t bs, int64_t l_lo, int64_t l_hi, int B, int k,
+                             int32_t *__restrict__ out_nid, int64_t *__restrict__ out_t,
+                             float4 *__restrict__ out_x4) {
+  const int lane = threadIdx.x & 31;
+  const int64_t S = 2 * (l_hi - l_lo);
+  const int64_t nchunks = (S + 31) >> 5;
+  const int64_t wstride = int64_t(gridDim.x) * (kFastThreads >> 5);
+  for (int64_t ch = int64_t(blockIdx.x) * (kFastThreads >> 5) + (threadIdx.x >> 5); ch < nchunks;
+       ch += wstride) {
+    const int64_t s_base = ch << 5, s = s_base + lane;
+    SeedWin mine{0, 0, 0};
+    if (s < S) {
+      // row s -> (edge, endpoint): batch jb owns rows [2*bs*jb, ...), src seeds then dst seeds
+      const int64_t jb = s / (2 * int64_t(bs));
+      const int64_t bstart = l_lo + jb * bs;
+      const int64_t nb = l_hi - bstart < int64_t(bs) ? l_hi - bstart : int64_t(bs);
+      const int64_t rr = s - jb * 2 * int64_t(bs);
+      const bool side = rr >= nb;
+      const int64_t l = bstart + (side ? rr - nb : rr);
+      const uint2 a = __ldg(anchors + (side ? Ew + l : l));
+      mine.nwin = a.y < uint32_t(B) ? int(a.y) : B;
+      mine.wstart = int64_t(a.x) - mine.nwin;
+      mine.q = __ldg(t + l);
+    }
+    const int nseeds = S - s_base < 32 ? int(S - s_base) : 32;
+    walk_chunk(entries, x4, D4, mine, s_base, nseeds, k, out_nid, out_t, out_x4, lane);
+  }
+}
+
+__global__ void __launch_bounds__(kFastThreads, TGM_FAST_MIN_BLOCKS)
+csr_sample_fast_kernel(const Entry *__restrict__ entries, const int64_t *__restrict__ rowptr,
+                       const float4 *__restrict__ x4, int32_t N, int D4,
+                       const int32_t *__restrict__ seeds, const int64_t *__restrict__ tq,
+                       const int64_t *__restrict__ cut, int64_t cut_group, int64_t S, int B, int k,
+                       int32_t *__restrict__ out_nid, int64_t *__restrict__ out_t,
+                       float4 *__restrict__ out_x4) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nchunks = (S + 31) >> 5;
+  const int64_t wstride = int64_t(gridDim.x) * (kFastThreads >> 5);
+  for (int64_t ch = int64_t(blockIdx.x) * (kFastThreads >> 5) + (threadIdx.x >> 5); ch < nchunks;
+       ch += wstride) {
+    const int64_t s_base = ch << 5, s = s_base + lane;
+    SeedWin mine{0, 0, 0};
+    if (s < S) {
+      const int32_t v = __ldg(seeds + s);
+      mine.q = __ldg(tq + s);
+      if (v >= 0 && v < N) {  // a padded seed (-1) always yields an all-padding row
+        const int64_t lo = __ldg(rowptr + v), hi = __ldg(rowptr + v + 1);
+        const int64_t pos = lower_bound_eid(entries, lo, hi, __ldg(cut + s / cut_group));
+        mine.wstart = pos - B > lo ? pos - B : lo;
+        mine.nwin = int(pos - mine.wstart);
+      }
+    }
+    const int nseeds = S - s_base < 32 ? int(S - s_base) : 32;
+    walk_chunk(entries, x4, D4, mine, s_base, nseeds, k, out_nid, out_t, out_x4, lane);
+  }
+}
+
 int bits_for(uint32_t max_value) {
   int b = 1;
   while (b < 32 && (max_value >> b) != 0) ++b;
@@ -425,7 +581,8 @@ extern "C" int tgm_csr_info(const tgm_csr *c, int64_t *num_entries, int64_t *e_s
 
 namespace {
 struct SampleCfg {
-  bool vec4, coloc;
+  bool vec4, coloc, fast;
+  int fast_grid;
   const float *xsrc;
   int grid;
   size_t smem;
@@ -444,6 +601,9 @@ int sample_cfg(const tgm_csr *c, const char *who, int64_t S, int32_t B, int32_t 
   cfg->smem = size_t(wpb) * size_t(k) * sizeof(uint32_t);
   if (cfg->smem > 48 * 1024) return fail(TGM_ERR_INVALID, std::string(who) + ": k too large");
   cfg->grid = grid_for(S, wpb, 8);
+  // warp-per-32-seeds kernels: ring width fits a warp and feature rows (if any) are colocated
+  cfg->fast = B <= 32 && (c->D == 0 || (cfg->vec4 && cfg->coloc));
+  cfg->fast_grid = grid_for((S + 31) / 32, kFastThreads / 32, TGM_FAST_MIN_BLOCKS);
   return TGM_OK;
 }
 }  // namespace
@@ -474,8 +634,13 @@ extern "C" int tgm_csr_sample(const tgm_csr *c, const int32_t *seeds, const int6
   if (rc != TGM_OK) return rc;
   DeviceGuard g(c->device);
   cudaStream_t st = as_stream(stream);
-  DISPATCH_SAMPLE(csr_sample_kernel, c->entries, c->rowptr, cfg.xsrc, c->N, c->D, seeds, tq, cut,
-                  cut_group, S, B, k, out_nid, out_t, out_x);
+  if (cfg.fast)
+    csr_sample_fast_kernel<<<cfg.fast_grid, kFastThreads, 0, st>>>(
+        c->entries, c->rowptr, reinterpret_cast<const float4 *>(cfg.xsrc), c->N, c->D / 4, seeds,
+        tq, cut, cut_group, S, B, k, out_nid, out_t, reinterpret_cast<float4 *>(out_x));
+  else
+    DISPATCH_SAMPLE(csr_sample_kernel, c->entries, c->rowptr, cfg.xsrc, c->N, c->D, seeds, tq,
+                    cut, cut_group, S, B, k, out_nid, out_t, out_x);
   TGM_LAUNCH_CHECK();
   return TGM_OK;
 }
@@ -496,9 +661,15 @@ extern "C" int tgm_csr_sample_edges(const tgm_csr *c, int64_t e_lo, int64_t e_hi
   if (rc != TGM_OK) return rc;
   DeviceGuard g(c->device);
   cudaStream_t st = as_stream(stream);
-  DISPATCH_SAMPLE(csr_sample_edges_kernel, c->entries, c->anchors, cfg.xsrc,
-                  c->store->t + c->e_start, c->D, c->Ew, c->bs, l_lo, l_hi, B, k, out_nid, out_t,
-                  out_x);
+  if (cfg.fast && c->bs < (int64_t(1) << 31))
+    csr_sample_edges_fast_kernel<<<cfg.fast_grid, kFastThreads, 0, st>>>(
+        c->entries, c->anchors, reinterpret_cast<const float4 *>(cfg.xsrc),
+        c->store->t + c->e_start, c->D / 4, c->Ew, uint32_t(c->bs), l_lo, l_hi, B, k, out_nid,
+        out_t, reinterpret_cast<float4 *>(out_x));
+  else
+    DISPATCH_SAMPLE(csr_sample_edges_kernel, c->entries, c->anchors, cfg.xsrc,
+                    c->store->t + c->e_start, c->D, c->Ew, c->bs, l_lo, l_hi, B, k, out_nid, out_t,
+                    out_x);
   TGM_LAUNCH_CHECK();
   return TGM_OK;
 }
