@@ -301,7 +301,7 @@ def run_b200(a):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     achieved = algo_bytes / launch_s / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'csr_sample_edges_kernel', 'achieved': achieved,
+    roofline = {'bound': 'hbm', 'kernel': 'csr_sample_edges_fast_kernel', 'achieved': achieved,
                 'peak': peak, 'peak_source': 'measured' if 'hbm_gbs' in peaks else 'fallback',
                 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                 'algorithmic_bytes_per_launch': algo_bytes,
