@@ -178,6 +178,53 @@ int tgm_masked_mean(const float *z, const int32_t *nid, int64_t S, int32_t k, in
 int tgm_time2vec(const int64_t *dt, int64_t n, const float *w, const float *b, int32_t d,
                  float *out, tgm_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Time-encoded attention aggregation (TGAT).  Replaces TemporalAttention.forward together with
+ * the Time2Vec calls that feed it, and MergeLayer:
+ *   tgm/nn/modules/attention.py:28-56   parameters: W_Q [out,out] (no bias), W_KV [2*out,key]
+ *                                       (no bias), W_O [out,out] + bias, LayerNorm(out);
+ *                                       out = node_dim + time_dim padded up to a multiple of
+ *                                       n_heads, key = node_dim + edge_dim + time_dim
+ *   tgm/nn/modules/attention.py:58-128  forward (eval mode: dropout is the identity)
+ *   tgm/nn/modules/time_encoding.py:12-24  Time2Vec weight [time_dim] / bias [time_dim]
+ *   tgm/nn/encoder/tgat.py:136-147      call site; tgat.py:11-38 MergeLayer
+ * All parameter pointers are float32 in torch's row-major [out_features, in_features] layout, host
+ * or device (copied at creation).  fp32 throughout; results are within 1e-5 of the reference.
+ */
+typedef struct tgm_attn tgm_attn;
+typedef struct tgm_mlp2 tgm_mlp2;
+int tgm_attn_create(tgm_attn **out, int32_t n_heads, int32_t node_dim, int32_t edge_dim,
+                    int32_t time_dim, const float *W_Q, const float *W_KV, const float *W_O,
+                    const float *b_O, const float *ln_w, const float *ln_b, float ln_eps,
+                    const float *t2v_w, const float *t2v_b, int device);
+void tgm_attn_destroy(tgm_attn *);
+int tgm_attn_out_dim(const tgm_attn *);
+/* node_x float32[S,node_dim]; nbr_node_feat float32[S,k,node_dim]; edge_feat float32[S,k,edge_dim];
+ * seed_t int64[S]; nbr_t int64[S,k]; nbr_id int32[S,k] (-1 = masked slot); out float32[S,out].
+ * The time features are computed inside: Time2Vec(0) for the seed, Time2Vec(seed_t - nbr_t) per
+ * slot.  Masked slots take part exactly as in the reference (logit -1e10, attention.py:110-113),
+ * so the caller passes the rows the reference would gather for them. */
+int tgm_attn_forward(tgm_attn *, const float *node_x, const float *nbr_node_feat,
+                     const float *edge_feat, const int64_t *seed_t, const int64_t *nbr_t,
+                     const int32_t *nbr_id, int64_t S, int32_t k, float *out, tgm_stream stream);
+/* The plain signature of attention.py:58-66 -- time features supplied by the caller: time_feat
+ * float32[S,time_dim], nbr_time_feat float32[S,k,time_dim] (argument order as in the reference). */
+int tgm_attn_forward_feats(tgm_attn *, const float *node_x, const float *time_feat,
+                           const float *edge_feat, const float *nbr_node_feat,
+                           const float *nbr_time_feat, const int32_t *nbr_id, int64_t S, int32_t k,
+                           float *out, tgm_stream stream);
+/* MergeLayer (tgat.py:11-38): out = fc2(relu(fc1(cat[x1, x2]))); W1 [hidden, in1+in2], W2
+ * [out, hidden].  x1 float32[S,in1], x2 float32[S,in2], out float32[S,out]. */
+int tgm_mlp2_create(tgm_mlp2 **out, int32_t in1, int32_t in2, int32_t hidden, int32_t out_dim,
+                    const float *W1, const float *b1, const float *W2, const float *b2, int device);
+void tgm_mlp2_destroy(tgm_mlp2 *);
+int tgm_mlp2_forward(tgm_mlp2 *, const float *x1, const float *x2, int64_t S, float *out,
+                     tgm_stream stream);
+/* out[i,:] = table[ids[i]] with torch's negative indexing (id -1 reads the last row, as
+ * node_x[nbr_nids] does in tgat.py:131-134).  table float32[num_rows,dim], ids int32[n]. */
+int tgm_gather_rows(const float *table, int64_t num_rows, int32_t dim, const int32_t *ids,
+                    int64_t n, float *out, tgm_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

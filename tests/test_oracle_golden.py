@@ -187,3 +187,42 @@ def test_time2vec_oracle_pins_torch_linear():
         if not b.any():
             assert (arg == fused).all() and (fused == twice).all()
             assert np.abs(out - time2vec(dt, w, b)).max() <= 1e-6
+
+
+# ---- aggregation modules: numpy oracle vs fixtures from the live reference modules ---------------
+import glob  # noqa: E402
+import os  # noqa: E402
+
+from oracle import nn_oracle  # noqa: E402
+from tests._golden import GOLDEN_DIR  # noqa: E402
+
+
+def _params(z):
+    return {k[2:]: z[k] for k in z.files if k.startswith('p.')}
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'nn_attn_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[8:-4])
+def test_attention_oracle_matches_reference_module(path):
+    z = np.load(path)
+    p = _params(z)
+    S = z['node_x'].shape[0]
+    tf0 = nn_oracle._t2v(p, 'time_encoder.', np.zeros(S, np.int64))
+    tfn = nn_oracle._t2v(p, 'time_encoder.', z['seed_t'][:, None] - z['nbr_t'])
+    out = nn_oracle.temporal_attention(p, '', int(z['n_heads']), z['node_x'], tf0, z['edge_feat'],
+                                       z['nbr_feat'], tfn, z['nbr_id'] != -1)
+    assert out.dtype == np.float32 and out.shape == z['out'].shape
+    assert np.abs(out - z['out']).max() <= 5e-6
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'nn_tgat_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[8:-4])
+def test_tgat_oracle_matches_reference_module(path):
+    z = np.load(path)
+    L = int(z['num_layers'])
+    out = nn_oracle.tgat_forward(
+        _params(z), L, int(z['n_heads']), z['node_x'],
+        [z[f'seed_nids{h}'] for h in range(L)], [z[f'seed_times{h}'] for h in range(L)],
+        [z[f'nbr_nids{h}'] for h in range(L)], [z[f'nbr_edge_x{h}'] for h in range(L)],
+        [z[f'nbr_edge_time{h}'] for h in range(L)])
+    assert np.abs(out - z['out']).max() <= 5e-6

@@ -9,6 +9,8 @@ import ctypes
 import os
 from ctypes import POINTER, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
+import torch  # noqa: F401  loaded first so its bundled CUDA libraries (cuBLAS) are the ones resolved
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TGM_B200_LIB') or os.path.join(_HERE, 'csrc', 'libtgm_b200.so')
 
@@ -71,6 +73,21 @@ SIGNATURES = {
                                 c_void_p]),
     'tgm_time2vec': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p,
                              c_void_p]),
+    'tgm_attn_create': (c_int, [POINTER(c_void_p), c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                c_void_p, c_void_p, c_int]),
+    'tgm_attn_destroy': (None, [c_void_p]),
+    'tgm_attn_out_dim': (c_int, [c_void_p]),
+    'tgm_attn_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    'tgm_attn_forward_feats': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    'tgm_mlp2_create': (c_int, [POINTER(c_void_p), c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_int]),
+    'tgm_mlp2_destroy': (None, [c_void_p]),
+    'tgm_mlp2_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'tgm_gather_rows': (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p,
+                                c_void_p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -8,7 +8,8 @@ import subprocess
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc')
 LIB_PATH = os.path.join(CSRC, 'libtgm_b200.so')
-SOURCES = ['store.cu', 'recency_ring.cu', 'csr.cu', 'frontier.cu', 'aggregate.cu']
+SOURCES = ['store.cu', 'recency_ring.cu', 'csr.cu', 'frontier.cu', 'aggregate.cu', 'attention.cu']
+LINK_FLAGS = ['-lcublas', '-Xlinker', '-rpath=/usr/local/cuda/lib64']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 
@@ -33,7 +34,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     """nvcc all sources into one shared object; returns its path."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, '-o', LIB_PATH, *SOURCES]
+    cmd = [_nvcc(), *NVCC_FLAGS, '-o', LIB_PATH, *SOURCES, *LINK_FLAGS]
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)

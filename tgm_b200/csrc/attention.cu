@@ -1,0 +1,485 @@
+// Time-encoded single-query multi-head attention over sampled neighbours (TGAT aggregation).
+//
+// Replaces TemporalAttention.forward + the two Time2Vec calls feeding it (reference
+// tgm-team/tgm @ 5183dc9: tgm/nn/modules/attention.py:58-128, tgm/nn/modules/time_encoding.py:
+// 22-24, call site tgm/nn/encoder/tgat.py:136-147) and MergeLayer (tgat.py:11-38).
+//
+// The reference materialises Z = cat[nbr_node_feat, edge_feat, Time2Vec(dt)] (S,k,key_dim) and
+// pushes all S*k rows through W_KV (key_dim -> 2*out).  Because there is ONE query per seed the
+// contraction reassociates exactly (W_KV has no bias, attention.py:52):
+//     Q_h . K_n   = Q_h . (W_K,h z_n)        = (W_K,h^T Q_h) . z_n          =: qk_h . z_n
+//     sum_n a_hn V_n = sum_n a_hn W_V,h z_n  = W_V,h (sum_n a_hn z_n)       =: W_V,h u_h
+// so the per-neighbour GEMM disappears: per seed two skinny GEMMs (out x key_dim) and a fused
+// HBM-streaming kernel that gathers the neighbour rows, evaluates Time2Vec in registers, takes
+// the masked softmax and accumulates u_h -- Z, K and V never exist in memory.  k-fold fewer
+// flops than the reference; fp32 FMA throughout (TF32/BF16 would break the 1e-5 bar).
+//
+// Dense plain GEMMs (S rows) go through cuBLAS SGEMM (default math: true fp32).
+#include <cublas_v2.h>
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+#include "common.cuh"
+
+using namespace tgm;
+
+struct tgm_attn {
+  int device = -1;
+  int H = 0, node_dim = 0, edge_dim = 0, time_dim = 0, pad_dim = 0, out_dim = 0, hd = 0, key = 0;
+  float eps = 1e-5f;
+  // parameters (device copies)
+  float *Wq = nullptr, *Wkv = nullptr, *Wo = nullptr, *bo = nullptr, *lnw = nullptr, *lnb = nullptr;
+  float *tw = nullptr, *tb = nullptr;  // Time2Vec weight [time_dim], bias [time_dim]
+  float *t0 = nullptr;                 // Time2Vec(0) = cos(b)   [time_dim]
+  cublasHandle_t blas = nullptr;
+  // workspace, grown on demand (rows = seeds)
+  int64_t cap = 0;
+  float *R = nullptr, *Q = nullptr, *QK = nullptr, *U = nullptr, *O = nullptr, *Y = nullptr;
+  ~tgm_attn() {
+    if (device >= 0) {
+      DeviceGuard g(device);
+      for (float *p : {Wq, Wkv, Wo, bo, lnw, lnb, tw, tb, t0, R, Q, QK, U, O, Y}) cudaFree(p);
+      if (blas) cublasDestroy(blas);
+    }
+  }
+};
+
+struct tgm_mlp2 {
+  int device = -1;
+  int in1 = 0, in2 = 0, hidden = 0, out = 0;
+  float *W1 = nullptr, *b1 = nullptr, *W2 = nullptr, *b2 = nullptr;
+  cublasHandle_t blas = nullptr;
+  int64_t cap = 0;
+  float *cat = nullptr, *h = nullptr;
+  ~tgm_mlp2() {
+    if (device >= 0) {
+      DeviceGuard g(device);
+      for (float *p : {W1, b1, W2, b2, cat, h}) cudaFree(p);
+      if (blas) cublasDestroy(blas);
+    }
+  }
+};
+
+namespace {
+
+int blas_fail(cublasStatus_t s, const char *what) {
+  return fail(TGM_ERR_CUDA, std::string("cuBLAS error ") + std::to_string(int(s)) + " in " + what);
+}
+#define TGM_BLAS(expr)                                          \
+  do {                                                          \
+    cublasStatus_t _s = (expr);                                 \
+    if (_s != CUBLAS_STATUS_SUCCESS) return blas_fail(_s, #expr); \
+  } while (0)
+
+// C[S,N] = A[S,K] . W[N,K]^T   (all row-major)
+cublasStatus_t gemm_nt(cublasHandle_t h, int64_t S, int N, int K, const float *A, int lda,
+                       const float *W, float *C, int ldc) {
+  const float one = 1.f, zero = 0.f;
+  return cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, N, int(S), K, &one, W, K, A, lda, &zero, C, ldc);
+}
+
+// R[s] = [X[s] | 0 (pad) | Time2Vec(0)]   (attention.py:93-95, tgat.py:141)
+__global__ void attn_residual_kernel(const float *__restrict__ X, const float *__restrict__ t0,
+                                     const float *__restrict__ seed_tf, int64_t S, int node_dim,
+                                     int pad_dim, int time_dim, float *__restrict__ R) {
+  const int out = node_dim + pad_dim + time_dim;
+  const int64_t total = S * out;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t s = i / out;
+    const int c = int(i - s * out);
+    float v = 0.f;
+    if (c < node_dim) v = X[s * node_dim + c];
+    else if (c >= node_dim + pad_dim) {
+      const int j = c - node_dim - pad_dim;
+      v = seed_tf ? seed_tf[s * time_dim + j] : __ldg(t0 + j);
+    }
+    R[i] = v;
+  }
+}
+
+__global__ void cos_kernel(const float *__restrict__ b, int n, float *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = cosf(b[i]);
+}
+
+// ---- the fused neighbour pass ------------------------------------------------------------------
+// One CTA per seed.  z_n = [nbr_feat[s,n,:] | edge_feat[s,n,:] | cos(fma(float(tq - t_n), w, b))]
+// is built once in shared memory (k x key_dim floats), logits_hn = (qk_h . z_n) * hd^-0.5 with
+// masked slots set to -1e10 (attention.py:110-113), softmax over n, u_h = sum_n a_hn z_n.
+// Padded slots are real inputs of the reference computation (their value rows are averaged when a
+// seed has no valid neighbour at all), so they are assembled like any other slot; the caller
+// passes the same rows the reference would gather (node row N-1 for id -1, zero edge features,
+// time 0).
+constexpr int kAttnThreads = 128;
+
+__global__ void __launch_bounds__(kAttnThreads)
+attn_neighbor_kernel(const float *__restrict__ nbr_feat, const float *__restrict__ edge_feat,
+                     const int64_t *__restrict__ seed_t, const int64_t *__restrict__ nbr_t,
+                     const int32_t *__restrict__ nbr_id, const float *__restrict__ tw,
+                     const float *__restrict__ tb, const float *__restrict__ nbr_tf,
+                     const float *__restrict__ QK, int64_t S, int k, int node_dim, int edge_dim,
+                     int time_dim, int H, float scale, float *__restrict__ U) {
+  extern __shared__ float smem[];
+  const int key = node_dim + edge_dim + time_dim;
+  float *z = smem;                 // [k][key]
+  float *qk = z + k * key;         // [H][key]
+  float *a = qk + H * key;         // [H][k] logits -> probabilities
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kAttnThreads >> 5;
+  for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
+    const int64_t tq = nbr_tf ? 0 : seed_t[s];
+    const float *nf = nbr_feat + s * int64_t(k) * node_dim;
+    const float *ef = edge_feat + s * int64_t(k) * edge_dim;
+    for (int i = tid; i < k * node_dim; i += kAttnThreads) {
+      const int n = i / node_dim, c = i - n * node_dim;
+      z[n * key + c] = __ldg(nf + i);
+    }
+    for (int i = tid; i < k * edge_dim; i += kAttnThreads) {
+      const int n = i / edge_dim, c = i - n * edge_dim;
+      z[n * key + node_dim + c] = __ldg(ef + i);
+    }
+    if (nbr_tf) {  // caller-provided time features (the plain attention.py:58 signature)
+      const float *tf = nbr_tf + s * int64_t(k) * time_dim;
+      for (int i = tid; i < k * time_dim; i += kAttnThreads) {
+        const int n = i / time_dim, c = i - n * time_dim;
+        z[n * key + node_dim + edge_dim + c] = __ldg(tf + i);
+      }
+    } else {
+      for (int i = tid; i < k * time_dim; i += kAttnThreads) {
+        const int n = i / time_dim, c = i - n * time_dim;
+        const float dt = float(tq - nbr_t[s * k + n]);  // int64 difference, then .float() (:23)
+        z[n * key + node_dim + edge_dim + c] = cosf(__fmaf_rn(dt, __ldg(tw + c), __ldg(tb + c)));
+      }
+    }
+    for (int i = tid; i < H * key; i += kAttnThreads) qk[i] = QK[s * int64_t(H) * key + i];
+    __syncthreads();
+    // logits: one warp per (h, n) pair
+    for (int p = warp; p < H * k; p += nwarp) {
+      const int h = p / k, n = p - h * k;
+      const float *zz = z + n * key, *qq = qk + h * key;
+      float acc = 0.f;
+      for (int j = lane; j < key; j += 32) acc = fmaf(qq[j], zz[j], acc);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0)
+        a[p] = nbr_id[s * k + n] != TGM_PADDED_NODE_ID ? acc * scale : -1e10f;
+    }
+    __syncthreads();
+    // softmax over the k slots of each head: one warp per head
+    for (int h = warp; h < H; h += nwarp) {
+      float m = -INFINITY;
+      for (int n = lane; n < k; n += 32) m = fmaxf(m, a[h * k + n]);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float sum = 0.f;
+      for (int n = lane; n < k; n += 32) {
+        const float e = expf(a[h * k + n] - m);
+        a[h * k + n] = e;
+        sum += e;
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = 1.f / sum;
+      for (int n = lane; n < k; n += 32) a[h * k + n] *= inv;
+    }
+    __syncthreads();
+    // u_h[j] = sum_n a_hn z_n[j]
+    float *u = U + s * int64_t(H) * key;
+    for (int i = tid; i < H * key; i += kAttnThreads) {
+      const int h = i / key, j = i - h * key;
+      float acc = 0.f;
+      for (int n = 0; n < k; ++n) acc = fmaf(a[h * k + n], z[n * key + j], acc);
+      u[i] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// out = LayerNorm(Y + b_O + R) (attention.py:124-127); one warp per row, two-pass variance
+__global__ void __launch_bounds__(256)
+attn_epilogue_kernel(const float *__restrict__ Y, const float *__restrict__ bo,
+                     const float *__restrict__ R, const float *__restrict__ lnw,
+                     const float *__restrict__ lnb, int64_t S, int out, float eps,
+                     float *__restrict__ dst) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int64_t s = int64_t(blockIdx.x) * wpb + (threadIdx.x >> 5); s < S;
+       s += int64_t(gridDim.x) * wpb) {
+    const float *y = Y + s * out, *r = R + s * out;
+    float sum = 0.f;
+    for (int c = lane; c < out; c += 32) sum += y[c] + __ldg(bo + c) + r[c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / float(out);
+    float var = 0.f;
+    for (int c = lane; c < out; c += 32) {
+      const float d = y[c] + __ldg(bo + c) + r[c] - mean;
+      var = fmaf(d, d, var);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / float(out) + eps);
+    for (int c = lane; c < out; c += 32) {
+      const float v = y[c] + __ldg(bo + c) + r[c];
+      dst[s * out + c] = (v - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
+    }
+  }
+}
+
+// ---- MergeLayer pieces (tgat.py:34-38) ----------------------------------------------------------
+__global__ void concat2_kernel(const float *__restrict__ a, const float *__restrict__ b, int64_t S,
+                               int da, int db, float *__restrict__ out) {
+  const int d = da + db;
+  const int64_t total = S * d;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t s = i / d;
+    const int c = int(i - s * d);
+    out[i] = c < da ? a[s * da + c] : b[s * db + (c - da)];
+  }
+}
+__global__ void bias_act_kernel(float *__restrict__ x, const float *__restrict__ b, int64_t S,
+                                int d, int relu) {
+  const int64_t total = S * d;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    float v = x[i] + __ldg(b + int(i % d));
+    x[i] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+
+// Row gather with torch negative-index semantics: out[i,:] = table[ids[i] < 0 ? ids[i]+N : ids[i]]
+__global__ void gather_rows_kernel(const float *__restrict__ table, int64_t N, int dim,
+                                   const int32_t *__restrict__ ids, int64_t n,
+                                   float *__restrict__ out) {
+  const int64_t total = n * dim;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / dim;
+    const int c = int(i - r * dim);
+    int64_t v = ids[r];
+    if (v < 0) v += N;
+    out[i] = (v >= 0 && v < N) ? __ldg(table + v * dim + c) : 0.f;
+  }
+}
+
+int dev_copy(float **dst, const float *src, size_t n) {
+  TGM_CUDA(cudaMalloc(dst, (n ? n : 1) * sizeof(float)));
+  if (n) TGM_CUDA(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyDefault));
+  return TGM_OK;
+}
+
+}  // namespace
+
+extern "C" int tgm_attn_create(tgm_attn **out, int32_t n_heads, int32_t node_dim, int32_t edge_dim,
+                               int32_t time_dim, const float *W_Q, const float *W_KV,
+                               const float *W_O, const float *b_O, const float *ln_w,
+                               const float *ln_b, float ln_eps, const float *t2v_w,
+                               const float *t2v_b, int device) {
+  TGM_REQUIRE(out != nullptr, "tgm_attn_create: out is NULL");
+  *out = nullptr;
+  TGM_REQUIRE(n_heads > 0 && node_dim > 0 && edge_dim > 0 && time_dim > 0,
+              "tgm_attn_create: n_heads,node_dim,edge_dim,time_dim must be > 0");  // attention.py:38-39
+  TGM_REQUIRE(W_Q && W_KV && W_O && b_O && ln_w && ln_b && t2v_w && t2v_b,
+              "tgm_attn_create: NULL parameter");
+  TGM_REQUIRE(device >= 0, "tgm_attn_create: a CUDA device is required (no CPU fallback)");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(TGM_ERR_CUDA, "tgm_attn_create: cannot select device");
+  tgm_attn *a = new (std::nothrow) tgm_attn();
+  if (!a) return fail(TGM_ERR_OOM, "tgm_attn_create: host allocation failed");
+  a->device = device;
+  a->H = n_heads, a->node_dim = node_dim, a->edge_dim = edge_dim, a->time_dim = time_dim;
+  int od = node_dim + time_dim;  // attention.py:41-45
+  if (od % n_heads) a->pad_dim = n_heads - od % n_heads;
+  od += a->pad_dim;
+  a->out_dim = od, a->hd = od / n_heads, a->key = node_dim + edge_dim + time_dim;
+  a->eps = ln_eps;
+  const size_t o = size_t(od), kd = size_t(a->key), td = size_t(time_dim);
+  int rc = dev_copy(&a->Wq, W_Q, o * o);
+  if (!rc) rc = dev_copy(&a->Wkv, W_KV, 2 * o * kd);
+  if (!rc) rc = dev_copy(&a->Wo, W_O, o * o);
+  if (!rc) rc = dev_copy(&a->bo, b_O, o);
+  if (!rc) rc = dev_copy(&a->lnw, ln_w, o);
+  if (!rc) rc = dev_copy(&a->lnb, ln_b, o);
+  if (!rc) rc = dev_copy(&a->tw, t2v_w, td);
+  if (!rc) rc = dev_copy(&a->tb, t2v_b, td);
+  if (!rc) rc = dev_copy(&a->t0, t2v_b, td);
+  if (!rc) {
+    cos_kernel<<<(time_dim + 127) / 128, 128>>>(a->tb, time_dim, a->t0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = cuda_fail(e, "Time2Vec(0)", __FILE__, __LINE__);
+  }
+  if (!rc) {
+    cublasStatus_t s = cublasCreate(&a->blas);
+    if (s != CUBLAS_STATUS_SUCCESS) rc = blas_fail(s, "cublasCreate");
+    else cublasSetMathMode(a->blas, CUBLAS_PEDANTIC_MATH);  // true fp32, no TF32 down-conversion
+  }
+  if (rc) {
+    delete a;
+    return rc;
+  }
+  *out = a;
+  return TGM_OK;
+}
+
+extern "C" void tgm_attn_destroy(tgm_attn *a) { delete a; }
+
+extern "C" int tgm_attn_out_dim(const tgm_attn *a) { return a ? a->out_dim : TGM_ERR_INVALID; }
+
+static int attn_forward_impl(tgm_attn *a, const float *node_x, const float *nbr_node_feat,
+                             const float *edge_feat, const int64_t *seed_t, const int64_t *nbr_t,
+                             const float *seed_tf, const float *nbr_tf, const int32_t *nbr_id,
+                             int64_t S, int32_t k, float *out, tgm_stream stream) {
+  TGM_REQUIRE(a != nullptr, "tgm_attn_forward: handle is NULL");
+  TGM_REQUIRE(S >= 0 && k >= 1, "tgm_attn_forward: bad sizes");
+  if (S == 0) return TGM_OK;
+  TGM_REQUIRE(node_x && nbr_node_feat && edge_feat && nbr_id && out,
+              "tgm_attn_forward: NULL array argument");
+  TGM_REQUIRE((seed_t && nbr_t) || (seed_tf && nbr_tf),
+              "tgm_attn_forward: need either timestamps or time features");
+  TGM_REQUIRE(S < (int64_t(1) << 31), "tgm_attn_forward: S must be < 2^31");
+  DeviceGuard g(a->device);
+  cudaStream_t st = as_stream(stream);
+  const int od = a->out_dim, key = a->key, H = a->H, hd = a->hd;
+  if (S > a->cap) {
+    TGM_CUDA(cudaStreamSynchronize(st));
+    for (float **p : {&a->R, &a->Q, &a->QK, &a->U, &a->O, &a->Y}) {
+      cudaFree(*p);
+      *p = nullptr;
+    }
+    a->cap = 0;
+    const size_t rows = size_t(S + S / 4);
+    TGM_CUDA(cudaMalloc(&a->R, rows * od * 4));
+    TGM_CUDA(cudaMalloc(&a->Q, rows * od * 4));
+    TGM_CUDA(cudaMalloc(&a->QK, rows * H * key * 4));
+    TGM_CUDA(cudaMalloc(&a->U, rows * H * key * 4));
+    TGM_CUDA(cudaMalloc(&a->O, rows * od * 4));
+    TGM_CUDA(cudaMalloc(&a->Y, rows * od * 4));
+    a->cap = int64_t(rows);
+  }
+  TGM_BLAS(cublasSetStream(a->blas, st));
+  const float one = 1.f, zero = 0.f;
+  // R = [X | pad | Time2Vec(0)],  Q = R W_Q^T
+  attn_residual_kernel<<<grid_for(S * od, 256, 8), 256, 0, st>>>(
+      node_x, a->t0, seed_tf, S, a->node_dim, a->pad_dim, a->time_dim, a->R);
+  TGM_LAUNCH_CHECK();
+  TGM_BLAS(gemm_nt(a->blas, S, od, od, a->R, od, a->Wq, a->Q, od));
+  // qk[s,h,:] = W_K,h^T Q[s,h,:]   (W_K = rows [0,out) of W_KV)
+  TGM_BLAS(cublasSgemmStridedBatched(a->blas, CUBLAS_OP_N, CUBLAS_OP_N, key, int(S), hd, &one,
+                                     a->Wkv, key, int64_t(hd) * key, a->Q, od, hd, &zero, a->QK,
+                                     H * key, key, H));
+  // fused gather + Time2Vec + masked softmax + weighted sum
+  const size_t smem = (size_t(k) * key + size_t(H) * key + size_t(H) * k) * sizeof(float);
+  TGM_REQUIRE(smem <= 200 * 1024, "tgm_attn_forward: k * key_dim too large for shared memory");
+  if (smem > 48 * 1024)
+    TGM_CUDA(cudaFuncSetAttribute(attn_neighbor_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const int ctas_per_sm = int(std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 1024))));
+  attn_neighbor_kernel<<<grid_for(S, 1, ctas_per_sm), kAttnThreads, smem, st>>>(
+      nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, a->tw, a->tb, nbr_tf, a->QK, S, k,
+      a->node_dim, a->edge_dim, a->time_dim, H, 1.0f / sqrtf(float(hd)), a->U);
+  TGM_LAUNCH_CHECK();
+  // O[s,h,:] = W_V,h u[s,h,:]   (W_V = rows [out, 2 out) of W_KV)
+  TGM_BLAS(cublasSgemmStridedBatched(a->blas, CUBLAS_OP_T, CUBLAS_OP_N, hd, int(S), key, &one,
+                                     a->Wkv + size_t(od) * key, key, int64_t(hd) * key, a->U,
+                                     H * key, key, &zero, a->O, od, hd, H));
+  // Y = O W_O^T ; out = LayerNorm(Y + b_O + R)
+  TGM_BLAS(gemm_nt(a->blas, S, od, od, a->O, od, a->Wo, a->Y, od));
+  attn_epilogue_kernel<<<grid_for(S, 8, 8), 256, 0, st>>>(a->Y, a->bo, a->R, a->lnw, a->lnb, S, od,
+                                                          a->eps, out);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+
+extern "C" int tgm_attn_forward(tgm_attn *a, const float *node_x, const float *nbr_node_feat,
+                                const float *edge_feat, const int64_t *seed_t, const int64_t *nbr_t,
+                                const int32_t *nbr_id, int64_t S, int32_t k, float *out,
+                                tgm_stream stream) {
+  TGM_REQUIRE(seed_t && nbr_t, "tgm_attn_forward: NULL array argument");
+  return attn_forward_impl(a, node_x, nbr_node_feat, edge_feat, seed_t, nbr_t, nullptr, nullptr,
+                           nbr_id, S, k, out, stream);
+}
+
+extern "C" int tgm_attn_forward_feats(tgm_attn *a, const float *node_x, const float *time_feat,
+                                      const float *edge_feat, const float *nbr_node_feat,
+                                      const float *nbr_time_feat, const int32_t *nbr_id, int64_t S,
+                                      int32_t k, float *out, tgm_stream stream) {
+  TGM_REQUIRE(time_feat && nbr_time_feat, "tgm_attn_forward_feats: NULL array argument");
+  return attn_forward_impl(a, node_x, nbr_node_feat, edge_feat, nullptr, nullptr, time_feat,
+                           nbr_time_feat, nbr_id, S, k, out, stream);
+}
+
+extern "C" int tgm_mlp2_create(tgm_mlp2 **out, int32_t in1, int32_t in2, int32_t hidden,
+                               int32_t out_dim, const float *W1, const float *b1, const float *W2,
+                               const float *b2, int device) {
+  TGM_REQUIRE(out != nullptr, "tgm_mlp2_create: out is NULL");
+  *out = nullptr;
+  TGM_REQUIRE(in1 > 0 && in2 >= 0 && hidden > 0 && out_dim > 0, "tgm_mlp2_create: bad sizes");
+  TGM_REQUIRE(W1 && b1 && W2 && b2, "tgm_mlp2_create: NULL parameter");
+  TGM_REQUIRE(device >= 0, "tgm_mlp2_create: a CUDA device is required (no CPU fallback)");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(TGM_ERR_CUDA, "tgm_mlp2_create: cannot select device");
+  tgm_mlp2 *m = new (std::nothrow) tgm_mlp2();
+  if (!m) return fail(TGM_ERR_OOM, "tgm_mlp2_create: host allocation failed");
+  m->device = device, m->in1 = in1, m->in2 = in2, m->hidden = hidden, m->out = out_dim;
+  int rc = dev_copy(&m->W1, W1, size_t(hidden) * (in1 + in2));
+  if (!rc) rc = dev_copy(&m->b1, b1, hidden);
+  if (!rc) rc = dev_copy(&m->W2, W2, size_t(out_dim) * hidden);
+  if (!rc) rc = dev_copy(&m->b2, b2, out_dim);
+  if (!rc) {
+    cublasStatus_t s = cublasCreate(&m->blas);
+    if (s != CUBLAS_STATUS_SUCCESS) rc = blas_fail(s, "cublasCreate");
+    else cublasSetMathMode(m->blas, CUBLAS_PEDANTIC_MATH);
+  }
+  if (rc) {
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return TGM_OK;
+}
+
+extern "C" void tgm_mlp2_destroy(tgm_mlp2 *m) { delete m; }
+
+extern "C" int tgm_mlp2_forward(tgm_mlp2 *m, const float *x1, const float *x2, int64_t S,
+                                float *out, tgm_stream stream) {
+  TGM_REQUIRE(m != nullptr, "tgm_mlp2_forward: handle is NULL");
+  TGM_REQUIRE(S >= 0, "tgm_mlp2_forward: S must be >= 0");
+  if (S == 0) return TGM_OK;
+  TGM_REQUIRE(x1 && (x2 || m->in2 == 0) && out, "tgm_mlp2_forward: NULL array argument");
+  DeviceGuard g(m->device);
+  cudaStream_t st = as_stream(stream);
+  const int in = m->in1 + m->in2;
+  if (S > m->cap) {
+    TGM_CUDA(cudaStreamSynchronize(st));
+    cudaFree(m->cat), cudaFree(m->h);
+    m->cat = m->h = nullptr;
+    m->cap = 0;
+    const size_t rows = size_t(S + S / 4);
+    TGM_CUDA(cudaMalloc(&m->cat, rows * in * 4));
+    TGM_CUDA(cudaMalloc(&m->h, rows * m->hidden * 4));
+    m->cap = int64_t(rows);
+  }
+  TGM_BLAS(cublasSetStream(m->blas, st));
+  concat2_kernel<<<grid_for(S * in, 256, 8), 256, 0, st>>>(x1, x2, S, m->in1, m->in2, m->cat);
+  TGM_LAUNCH_CHECK();
+  TGM_BLAS(gemm_nt(m->blas, S, m->hidden, in, m->cat, in, m->W1, m->h, m->hidden));
+  bias_act_kernel<<<grid_for(S * m->hidden, 256, 8), 256, 0, st>>>(m->h, m->b1, S, m->hidden, 1);
+  TGM_LAUNCH_CHECK();
+  TGM_BLAS(gemm_nt(m->blas, S, m->out, m->hidden, m->h, m->hidden, m->W2, out, m->out));
+  bias_act_kernel<<<grid_for(S * m->out, 256, 8), 256, 0, st>>>(out, m->b2, S, m->out, 0);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+
+extern "C" int tgm_gather_rows(const float *table, int64_t num_rows, int32_t dim,
+                               const int32_t *ids, int64_t n, float *out, tgm_stream stream) {
+  TGM_REQUIRE(num_rows >= 0 && dim >= 1 && n >= 0, "tgm_gather_rows: bad sizes");
+  if (n == 0) return TGM_OK;
+  TGM_REQUIRE(table && ids && out, "tgm_gather_rows: NULL array argument");
+  gather_rows_kernel<<<grid_for(n * dim, 256, 8), 256, 0, as_stream(stream)>>>(table, num_rows, dim,
+                                                                               ids, n, out);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}

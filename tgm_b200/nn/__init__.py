@@ -1,0 +1,7 @@
+"""Aggregation modules of the hot path (tgm/nn of the reference, the parts SURVEY.md section 8
+puts on the path): forward-only `torch.nn.Module`s with the reference's parameter names and
+shapes, so `state_dict`s interchange, executing on the CUDA library (include/tgm_b200.h)."""
+from .attention import MergeLayer, TemporalAttention, Time2Vec, masked_mean
+from .tgat import TGAT
+
+__all__ = ['TemporalAttention', 'Time2Vec', 'MergeLayer', 'TGAT', 'masked_mean']

@@ -1,0 +1,226 @@
+"""Time2Vec, TemporalAttention and MergeLayer on the B200 library.
+
+Same constructors, parameter names/shapes and forward signatures as the reference
+(tgm/nn/modules/time_encoding.py:6-24, tgm/nn/modules/attention.py:5-128,
+tgm/nn/encoder/tgat.py:11-38).  Forward only (inference / evaluation: dropout is the identity);
+the computation runs in `tgm_attn_forward` / `tgm_mlp2_forward` / `tgm_time2vec`.  There is no
+CPU path: parameters must live on a CUDA device when forward is called.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from tgm_b200 import _cabi
+
+
+def _need_cuda(t: Tensor, what: str) -> torch.device:
+    if not t.is_cuda:
+        raise _cabi.TGMNativeError(-3, f'{what} needs CUDA tensors (tgm_b200 has no CPU fallback)')
+    return t.device
+
+
+def _f32(t: Tensor) -> Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+class _NativeHandle:
+    """Owns a C handle created from the module's current parameters; rebuilt when they change."""
+
+    def __init__(self, destroy) -> None:
+        self.h = ctypes.c_void_p()
+        self._destroy = destroy
+        self.version = None
+
+    def free(self) -> None:
+        if self.h.value:
+            self._destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self) -> None:
+        try:
+            self.free()
+        except Exception:  # noqa: BLE001  interpreter shutdown
+            pass
+
+
+def _version(params) -> tuple:
+    return tuple((p.data_ptr(), p._version, str(p.device)) for p in params)
+
+
+class Time2Vec(nn.Module):
+    """cos(Linear(1, time_dim)(t)), w initialised to 1/10^linspace(0,9,d), b = 0."""
+
+    def __init__(self, time_dim: int) -> None:
+        super().__init__()
+        self.time_dim = time_dim
+        self.w = nn.Linear(1, time_dim)
+        w = (1 / 10 ** np.linspace(0, 9, time_dim)).reshape(time_dim, 1)
+        self.w.weight = nn.Parameter(torch.from_numpy(w).float())
+        self.w.bias = nn.Parameter(torch.zeros(time_dim))
+
+    @torch.no_grad()
+    def forward(self, x: Tensor) -> Tensor:
+        dev = _need_cuda(self.w.weight, 'Time2Vec')
+        dt = x.to(device=dev)
+        if dt.dtype != torch.int64:
+            # the reference casts to float32 first; integer-valued inputs (time deltas) are the
+            # hot-path case and are passed exactly
+            if not torch.equal(dt, dt.round()):
+                raise ValueError('Time2Vec on the B200 path takes integer time deltas')
+            dt = dt.to(torch.int64)
+        dt = dt.contiguous()
+        out = torch.empty((*dt.shape, self.time_dim), dtype=torch.float32, device=dev)
+        w = _f32(self.w.weight).reshape(-1)
+        b = _f32(self.w.bias)
+        _cabi.check(_cabi.lib.tgm_time2vec(dt.data_ptr(), dt.numel(), w.data_ptr(), b.data_ptr(),
+                                           self.time_dim, out.data_ptr(),
+                                           _cabi.current_stream(dev)))
+        return out
+
+
+class TemporalAttention(nn.Module):
+    """Multi-head temporal attention over a seed's sampled neighbours (one query per seed)."""
+
+    def __init__(self, n_heads: int, node_dim: int, edge_dim: int, time_dim: int,
+                 dropout: float = 0.1) -> None:
+        super().__init__()
+        if any(x <= 0 for x in [n_heads, node_dim, edge_dim, time_dim]):
+            raise ValueError('n_heads,node_dim,edge_dim,time_dim,out_dim must be > 0')
+        out_dim = node_dim + time_dim
+        self.pad_dim = 0
+        if out_dim % n_heads != 0:
+            self.pad_dim = n_heads - out_dim % n_heads
+            out_dim += self.pad_dim
+        self.n_heads, self.head_dim, self.out_dim = n_heads, out_dim // n_heads, out_dim
+        self.node_dim, self.edge_dim, self.time_dim = node_dim, edge_dim, time_dim
+        key_dim = node_dim + edge_dim + time_dim
+        self.W_Q = nn.Linear(out_dim, out_dim, bias=False)
+        self.W_KV = nn.Linear(key_dim, out_dim * 2, bias=False)
+        self.W_O = nn.Linear(out_dim, out_dim)
+        self.dropout = nn.Dropout(dropout)
+        self.layer_norm = nn.LayerNorm(out_dim)
+        self._native = _NativeHandle(_cabi.lib.tgm_attn_destroy)
+
+    def _handle(self, time_encoder: Time2Vec, dev: torch.device) -> ctypes.c_void_p:
+        params = [self.W_Q.weight, self.W_KV.weight, self.W_O.weight, self.W_O.bias,
+                  self.layer_norm.weight, self.layer_norm.bias, time_encoder.w.weight,
+                  time_encoder.w.bias]
+        ver = _version(params)
+        if self._native.version != ver:
+            self._native.free()
+            for p in params:
+                _need_cuda(p, 'TemporalAttention parameters')
+            t = [_f32(p) for p in params]
+            _cabi.check(_cabi.lib.tgm_attn_create(
+                ctypes.byref(self._native.h), self.n_heads, self.node_dim, self.edge_dim,
+                self.time_dim, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(),
+                t[4].data_ptr(), t[5].data_ptr(), float(self.layer_norm.eps),
+                t[6].reshape(-1).data_ptr(), t[7].data_ptr(), dev.index))
+            self._native.version = ver
+        return self._native.h
+
+    @torch.no_grad()
+    def forward(self, node_x: Tensor, time_feat: Tensor, edge_feat: Tensor, nbr_node_feat: Tensor,
+                nbr_time_feat: Tensor, valid_nbr_mask: Tensor,
+                time_encoder: Optional[Time2Vec] = None) -> Tensor:
+        """The reference signature (attention.py:58-66): time features supplied by the caller."""
+        if self.training and self.dropout.p > 0:
+            raise RuntimeError('TemporalAttention on the B200 path is forward/eval only')
+        dev = _need_cuda(node_x, 'TemporalAttention')
+        S, k = valid_nbr_mask.shape
+        te = time_encoder if time_encoder is not None else self._dummy_encoder(dev)
+        nid = torch.where(valid_nbr_mask, 0, -1).to(torch.int32).contiguous()
+        out = torch.empty((S, self.out_dim), dtype=torch.float32, device=dev)
+        args = [_f32(node_x), _f32(time_feat), _f32(edge_feat), _f32(nbr_node_feat),
+                _f32(nbr_time_feat), nid]
+        _cabi.check(_cabi.lib.tgm_attn_forward_feats(
+            self._handle(te, dev), *[a.data_ptr() for a in args], S, k, out.data_ptr(),
+            _cabi.current_stream(dev)))
+        return out
+
+    def _dummy_encoder(self, dev: torch.device) -> Time2Vec:
+        if getattr(self, '_te', None) is None:
+            object.__setattr__(self, '_te', Time2Vec(self.time_dim).to(dev))
+        return self._te
+
+    @torch.no_grad()
+    def forward_fused(self, time_encoder: Time2Vec, node_x: Tensor, nbr_node_feat: Tensor,
+                      edge_feat: Tensor, seed_times: Tensor, nbr_times: Tensor,
+                      nbr_nids: Tensor) -> Tensor:
+        """attention.py:58-128 with the Time2Vec calls of tgat.py:141-146 folded in: the time
+        features are computed inside the kernel from (seed_times, nbr_times)."""
+        if self.training and self.dropout.p > 0:
+            raise RuntimeError('TemporalAttention on the B200 path is forward/eval only')
+        dev = _need_cuda(node_x, 'TemporalAttention')
+        S, k = nbr_nids.shape
+        out = torch.empty((S, self.out_dim), dtype=torch.float32, device=dev)
+        args = [_f32(node_x), _f32(nbr_node_feat), _f32(edge_feat),
+                seed_times.to(torch.int64).contiguous(), nbr_times.to(torch.int64).contiguous(),
+                nbr_nids.to(torch.int32).contiguous()]
+        _cabi.check(_cabi.lib.tgm_attn_forward(
+            self._handle(time_encoder, dev), *[a.data_ptr() for a in args], S, k, out.data_ptr(),
+            _cabi.current_stream(dev)))
+        return out
+
+
+class MergeLayer(nn.Module):
+    """fc2(relu(fc1(cat[x1, x2])))."""
+
+    def __init__(self, in_dim1: int, in_dim2: int, hidden_dim: int, output_dim: int) -> None:
+        super().__init__()
+        self.in_dim1, self.in_dim2 = in_dim1, in_dim2
+        self.fc1 = nn.Linear(in_dim1 + in_dim2, hidden_dim)
+        self.fc2 = nn.Linear(hidden_dim, output_dim)
+        self._native = _NativeHandle(_cabi.lib.tgm_mlp2_destroy)
+
+    @torch.no_grad()
+    def forward(self, x1: Tensor, x2: Tensor) -> Tensor:
+        dev = _need_cuda(x1, 'MergeLayer')
+        params = [self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias]
+        ver = _version(params)
+        if self._native.version != ver:
+            self._native.free()
+            t = [_f32(p) for p in params]
+            for p in t:
+                _need_cuda(p, 'MergeLayer parameters')
+            _cabi.check(_cabi.lib.tgm_mlp2_create(
+                ctypes.byref(self._native.h), self.in_dim1, self.in_dim2, self.fc1.out_features,
+                self.fc2.out_features, *[p.data_ptr() for p in t], dev.index))
+            self._native.version = ver
+        S = x1.shape[0]
+        out = torch.empty((S, self.fc2.out_features), dtype=torch.float32, device=dev)
+        a, b = _f32(x1), _f32(x2)
+        _cabi.check(_cabi.lib.tgm_mlp2_forward(self._native.h, a.data_ptr(), b.data_ptr(), S,
+                                               out.data_ptr(), _cabi.current_stream(dev)))
+        return out
+
+
+def gather_rows(table: Tensor, ids: Tensor) -> Tensor:
+    """table[ids] with torch's negative indexing (tgat.py:131-134), via tgm_gather_rows."""
+    dev = _need_cuda(table, 'gather_rows')
+    table = _f32(table)
+    ids = ids.to(device=dev, dtype=torch.int32).contiguous()
+    out = torch.empty((ids.numel(), table.shape[1]), dtype=torch.float32, device=dev)
+    _cabi.check(_cabi.lib.tgm_gather_rows(table.data_ptr(), table.shape[0], table.shape[1],
+                                          ids.data_ptr(), ids.numel(), out.data_ptr(),
+                                          _cabi.current_stream(dev)))
+    return out
+
+
+def masked_mean(z: Tensor, nbr_nids: Tensor) -> Tensor:
+    """sum_k(z * mask) / clamp(sum mask, 1) over the sampled neighbours
+    (examples/linkproppred/graphmixer.py:131-135), via tgm_masked_mean."""
+    dev = _need_cuda(z, 'masked_mean')
+    S, k, D = z.shape
+    z = _f32(z)
+    nid = nbr_nids.to(device=dev, dtype=torch.int32).contiguous()
+    out = torch.zeros((S, D), dtype=torch.float32, device=dev)
+    _cabi.check(_cabi.lib.tgm_masked_mean(z.data_ptr(), nid.data_ptr(), S, k, D, out.data_ptr(),
+                                          _cabi.current_stream(dev)))
+    return out
