@@ -140,6 +140,19 @@ int tgm_csr_sample(const tgm_csr *, const int32_t *seeds, const int64_t *tq, con
 int tgm_csr_sample_edges(const tgm_csr *, int64_t e_lo, int64_t e_hi, int32_t B, int32_t k,
                          int32_t *out_nid, int64_t *out_t, float *out_x, tgm_stream stream);
 
+/* Uniform full-history sampling == DGStorageArrayBackend.get_nbrs
+ * (tgm/core/_storage/backends/array_backend.py:108-171, called by NeighborSamplerHook,
+ * tgm/hooks/neighbors/uniform.py:122-127).  The adjacency must have been built with batch_size 1
+ * and e_start 0 (entries of a node ordered by (edge, side), the reference's candidate order).
+ * For every seed: its candidates are the entries with e_lo <= edge < e_hi; at most k are returned
+ * LEFT-aligned, right-padded with (-1, 0, 0.0f).  With <= k candidates the output equals the
+ * reference bit for bit; with more, the reference draws with CPython's random.sample and this
+ * call draws a uniform k-subset from a counter-based generator keyed by (rng_seed, node id).
+ * seeds int32[S] (ids outside [0, N) give padding rows). */
+int tgm_csr_sample_uniform(const tgm_csr *, const int32_t *seeds, int64_t S, int64_t e_lo,
+                           int64_t e_hi, int32_t k, uint64_t rng_seed, int32_t *out_nid,
+                           int64_t *out_t, float *out_x, tgm_stream stream);
+
 /* Host-buffer form of tgm_csr_sample_edges: what a CPU-resident caller binds (the reference
  * keeps its arrays on the CPU and moves every batch property with .to(device),
  * tgm/core/graph.py:232-263, and its CPU hook returns CPU tensors).  Stream-ordered on `stream`:

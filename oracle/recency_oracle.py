@@ -215,3 +215,45 @@ def time2vec(dt: np.ndarray, w: np.ndarray, b: np.ndarray, fused: bool = True) -
     else:
         arg = (x * w32).astype(np.float32) + b32
     return np.cos(arg.astype(np.float64))
+
+
+def uniform_candidates(src: np.ndarray, dst: np.ndarray, e_lo: int, e_hi: int, seeds,
+                       directed: bool = False):
+    """Candidate lists of DGStorageArrayBackend.get_nbrs (array_backend.py:125-137): for every
+    seed the (edge, neighbour) pairs of the edges [e_lo, e_hi) it touches, in edge order, the
+    src-side entry before the dst-side entry of the same edge."""
+    want = set(int(v) for v in np.asarray(seeds).reshape(-1))
+    cand = {v: [] for v in want}
+    for e in range(e_lo, e_hi):
+        s, d = int(src[e]), int(dst[e])
+        if s in cand:
+            cand[s].append((e, d))
+        if not directed and d in cand:
+            cand[d].append((e, s))
+    return cand
+
+
+def uniform_sample_deterministic(src, dst, t, x, e_lo: int, e_hi: int, seeds, k: int,
+                                 directed: bool = False):
+    """get_nbrs (array_backend.py:108-171) for the seeds whose candidate count is <= k (no random
+    sub-sampling involved): left-aligned, right-padded (-1, 0, 0.0).  Returns (nid, nt, nx,
+    exact) where exact[i] is False for seeds with more than k candidates (rows left as padding;
+    the caller checks those for set-validity instead)."""
+    seeds = np.asarray(seeds).reshape(-1)
+    D = 0 if x is None else x.shape[1]
+    cand = uniform_candidates(src, dst, e_lo, e_hi, seeds, directed)
+    S = len(seeds)
+    nid = np.full((S, k), PADDED_NODE_ID, np.int32)
+    nt = np.zeros((S, k), np.int64)
+    nx = np.zeros((S, k, D), np.float32)
+    exact = np.ones(S, bool)
+    for i, v in enumerate(seeds.tolist()):
+        c = cand[int(v)]
+        if len(c) > k:
+            exact[i] = False
+            continue
+        for j, (e, nb) in enumerate(c):
+            nid[i, j], nt[i, j] = nb, t[e]
+            if D:
+                nx[i, j] = x[e]
+    return nid, nt, nx, exact

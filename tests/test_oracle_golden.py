@@ -226,3 +226,32 @@ def test_tgat_oracle_matches_reference_module(path):
         [z[f'nbr_nids{h}'] for h in range(L)], [z[f'nbr_edge_x{h}'] for h in range(L)],
         [z[f'nbr_edge_time{h}'] for h in range(L)])
     assert np.abs(out - z['out']).max() <= 5e-6
+
+
+# ---- uniform sampler oracle vs reference fixtures ------------------------------------------------
+from oracle.recency_oracle import uniform_sample_deterministic  # noqa: E402
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'uniform_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[8:-4])
+def test_uniform_oracle_matches_reference_fixture(path):
+    """NeighborSamplerHook (uniform.py:87-142): every hop samples the history strictly before the
+    batch's earliest time; fixtures have k >= every degree, so the reference is deterministic."""
+    z = np.load(path)
+    src, dst, t = z['src'], z['dst'], z['t']
+    x = z['x'] if int(z['has_x']) else None
+    bs, nn, directed = int(z['bs']), [int(v) for v in z['num_nbrs']], bool(int(z['directed']))
+    for b, lo in enumerate(range(0, len(src), bs)):
+        hi = min(lo + bs, len(src))
+        e_hi = int(np.searchsorted(t, t[lo:hi].min() - 1, 'right'))  # end_time = min t - 1
+        seeds = np.concatenate([src[lo:hi], dst[lo:hi]])
+        for h, k in enumerate(nn):
+            if h:
+                seeds = nid.reshape(-1)
+            nid, nt, nx, exact = uniform_sample_deterministic(src, dst, t, x, 0, e_hi, seeds, k,
+                                                              directed)
+            assert exact.all()
+            assert np.array_equal(nid, z[f'b{b}_h{h}_nid'])
+            assert np.array_equal(nt, z[f'b{b}_h{h}_nt'])
+            assert np.array_equal(nx, z[f'b{b}_h{h}_nx'])
+            assert np.array_equal(seeds.astype(np.int32), z[f'b{b}_h{h}_seed'])

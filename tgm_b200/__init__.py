@@ -10,11 +10,11 @@ from . import _cabi  # noqa: F401  (fails loudly when the CUDA library is missin
 from .constants import PADDED_NODE_ID
 from .core import DGBatch, DGraph, TimeDeltaDG
 from .data import DGData, DGDataLoader
-from .hooks import (DeduplicationHook, HookManager, RandomNegativeEdgeSamplerHook,
-                    RecencyNeighborHook)
+from .hooks import (DeduplicationHook, HookManager, NeighborSamplerHook,
+                    RandomNegativeEdgeSamplerHook, RecencyNeighborHook)
 from .sampler import RecencyCSR
 
 __version__ = '0.1.0'
 __all__ = ['DGraph', 'DGBatch', 'DGData', 'DGDataLoader', 'TimeDeltaDG', 'HookManager',
-           'RecencyNeighborHook', 'RandomNegativeEdgeSamplerHook', 'DeduplicationHook',
+           'RecencyNeighborHook', 'NeighborSamplerHook', 'RandomNegativeEdgeSamplerHook', 'DeduplicationHook',
            'RecencyCSR', 'PADDED_NODE_ID']

@@ -7,7 +7,8 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import (POINTER, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64,
+                    c_void_p)
 
 import torch  # noqa: F401  loaded first so its bundled CUDA libraries (cuBLAS) are the ones resolved
 
@@ -65,6 +66,8 @@ SIGNATURES = {
                                c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     'tgm_csr_sample_edges': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
+    'tgm_csr_sample_uniform': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32,
+                                       c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
     'tgm_csr_sample_edges_host': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_int, c_void_p]),

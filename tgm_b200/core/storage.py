@@ -340,9 +340,10 @@ class DeviceCOOStorage(DGStorageBase):
     def get_nbrs(self, seed_nodes: Tensor, num_nbrs: int, slice: DGSliceTracker,
                  directed: bool) -> Tuple[Tensor, ...]:
         """Neighbours among all edges of the slice (array_backend.py:108-171), right-padded.
-        Served from the full-history adjacency: when a seed has more than `num_nbrs` candidates
-        the most recent ones are returned (the reference draws them with CPython's `random`,
-        which no device path can reproduce; index parity holds for seeds with <= k candidates)."""
+        Served from the (edge, side)-ordered adjacency by `tgm_csr_sample_uniform`: seeds with
+        <= `num_nbrs` candidates get exactly the reference's rows; with more, a uniform subset is
+        drawn on the device (the reference uses CPython's `random.sample`, :152-153, which no
+        device path can reproduce bit for bit)."""
         self._require_device()
         from tgm_b200.sampler import full_history_neighbors
         return full_history_neighbors(self, seed_nodes, num_nbrs, slice, directed)

@@ -453,6 +453,85 @@ csr_sample_fast_kernel(const Entry *__restrict__ entries, const int64_t *__restr
   }
 }
 
+// ---- uniform full-history sampler (array_backend.py:108-171 via uniform.py:87-142) -------------
+// Needs the adjacency built with batch_size 1: per node the entries are then ordered (edge, side),
+// which is the order the reference appends candidates in (:132-137).  Candidates of a seed are its
+// entries with e_lo <= edge < e_hi; up to k of them are returned left-aligned / right-padded
+// (:155-169).  When there are more than k the reference draws k with CPython's random.sample
+// (:152-153), which no device path can reproduce: here a k-subset is drawn uniformly with Floyd's
+// algorithm from a counter-based generator keyed by (rng_seed, node id) -- like the reference, all
+// occurrences of a node in one call share the same draw (:119,:166).
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+constexpr int kUniformThreads = 256;
+
+__global__ void __launch_bounds__(kUniformThreads)
+csr_uniform_kernel(const Entry *__restrict__ entries, const int64_t *__restrict__ rowptr,
+                   const float *__restrict__ x, int32_t N, int D, const int32_t *__restrict__ seeds,
+                   int64_t S, int64_t e_lo, int64_t e_hi, int k, uint64_t rng_seed,
+                   int32_t *__restrict__ out_nid, int64_t *__restrict__ out_t,
+                   float *__restrict__ out_x) {
+  extern __shared__ int64_t s_pick[];  // [warps][k] chosen entry index, -1 = padding
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  int64_t *pick = s_pick + warp * k;
+  for (int64_t s = int64_t(blockIdx.x) * wpb + warp; s < S; s += int64_t(gridDim.x) * wpb) {
+    const int32_t v = seeds[s];
+    int64_t lo = 0, cnt = 0;
+    if (v >= 0 && v < N) {
+      const int64_t r0 = rowptr[v], r1 = rowptr[v + 1];
+      lo = lower_bound_eid(entries, r0, r1, e_lo);
+      cnt = lower_bound_eid(entries, lo, r1, e_hi) - lo;
+    }
+    if (cnt <= k) {
+      for (int c = lane; c < k; c += 32) pick[c] = c < cnt ? lo + c : -1;
+    } else if (lane == 0) {
+      // Floyd: for j = cnt-k .. cnt-1 pick t ~ U[0, j]; if t was already chosen take j instead
+      uint64_t state = splitmix64(rng_seed ^ (uint64_t(uint32_t(v)) * 0xD1B54A32D192ED03ull));
+      for (int i = 0; i < k; ++i) {
+        const int64_t j = cnt - k + i;
+        state = splitmix64(state);
+        int64_t t = int64_t(state % uint64_t(j + 1));
+        for (int u = 0; u < i; ++u)
+          if (pick[u] == lo + t) {
+            t = j;
+            break;
+          }
+        pick[i] = lo + t;
+      }
+    }
+    __syncwarp();
+    for (int c = lane; c < k; c += 32) {
+      const int64_t p = pick[c];
+      int32_t id = TGM_PADDED_NODE_ID;
+      int64_t tt = 0;
+      if (p >= 0) {
+        const Entry en = entries[p];
+        id = en.nbr;
+        tt = en.t;
+        pick[c] = en.eid;  // feature row
+      }
+      out_nid[s * k + c] = id;
+      out_t[s * k + c] = tt;
+    }
+    __syncwarp();
+    if (D > 0) {
+      float *o = out_x + s * int64_t(k) * D;
+      const int total = k * D;
+      for (int i = lane; i < total; i += 32) {
+        const int c = i / D, d = i - c * D;
+        const int64_t row = pick[c];
+        o[i] = row >= 0 ? __ldg(x + row * D + d) : 0.f;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 int bits_for(uint32_t max_value) {
   int b = 1;
   while (b < 32 && (max_value >> b) != 0) ++b;
@@ -719,5 +798,30 @@ extern "C" int tgm_csr_sample_edges_host(tgm_csr *c, int64_t e_lo, int64_t e_hi,
   TGM_CUDA(cudaMemcpyAsync(h_out_nid, sg.nid, size_t(cells) * 4, cudaMemcpyDeviceToHost, st));
   TGM_CUDA(cudaMemcpyAsync(h_out_t, sg.t, size_t(cells) * 8, cudaMemcpyDeviceToHost, st));
   if (D) TGM_CUDA(cudaMemcpyAsync(h_out_x, sg.x, size_t(cells) * D * 4, cudaMemcpyDeviceToHost, st));
+  return TGM_OK;
+}
+
+
+extern "C" int tgm_csr_sample_uniform(const tgm_csr *c, const int32_t *seeds, int64_t S,
+                                      int64_t e_lo, int64_t e_hi, int32_t k, uint64_t rng_seed,
+                                      int32_t *out_nid, int64_t *out_t, float *out_x,
+                                      tgm_stream stream) {
+  TGM_REQUIRE(c != nullptr, "tgm_csr_sample_uniform: csr is NULL");
+  TGM_REQUIRE(c->bs == 1 && c->e_start == 0,
+              "tgm_csr_sample_uniform: the adjacency must be built with batch_size 1, e_start 0");
+  TGM_REQUIRE(S >= 0 && k >= 1, "tgm_csr_sample_uniform: bad sizes");
+  TGM_REQUIRE(0 <= e_lo && e_lo <= e_hi && e_hi <= c->Ew,
+              "tgm_csr_sample_uniform: [e_lo, e_hi) outside the store");
+  if (S == 0) return TGM_OK;
+  TGM_REQUIRE(seeds && out_nid && out_t, "tgm_csr_sample_uniform: NULL array argument");
+  TGM_REQUIRE(c->D == 0 || out_x != nullptr, "tgm_csr_sample_uniform: out_x is NULL but D > 0");
+  const int wpb = kUniformThreads / 32;
+  const size_t smem = size_t(wpb) * size_t(k) * sizeof(int64_t);
+  TGM_REQUIRE(smem <= 48 * 1024, "tgm_csr_sample_uniform: k too large");
+  DeviceGuard g(c->device);
+  csr_uniform_kernel<<<grid_for(S, wpb, 8), kUniformThreads, smem, as_stream(stream)>>>(
+      c->entries, c->rowptr, c->store->x, c->N, c->D, seeds, S, e_lo, e_hi, k, rng_seed, out_nid,
+      out_t, out_x);
+  TGM_LAUNCH_CHECK();
   return TGM_OK;
 }

@@ -3,3 +3,4 @@ from .hook_manager import HookManager
 from .recency import RecencyNeighborHook
 from .negatives import RandomNegativeEdgeSamplerHook
 from .dedup import DeduplicationHook
+from .uniform import NeighborSamplerHook

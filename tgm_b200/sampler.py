@@ -168,7 +168,26 @@ class RecencyCSR:
             row += n
 
 
-def full_history_neighbors(storage, seed_nodes: Tensor, num_nbrs: int, slice, directed: bool):
-    raise NotImplementedError(
-        'DeviceCOOStorage.get_nbrs (uniform full-history sampling, array_backend.py:108-171) is '
-        'scheduled after the recency path (SURVEY.md section 8f)')
+def full_history_neighbors(storage, seed_nodes: Tensor, num_nbrs: int, slice, directed: bool,
+                           rng_seed: Optional[int] = None):
+    """DGStorageArrayBackend.get_nbrs (array_backend.py:108-171) on the device: neighbours among
+    all edges of `slice`, left-aligned / right-padded.  The (edge, side)-ordered adjacency is
+    built once per `directed` flag and cached on the storage."""
+    cache = storage._node_cache
+    key = ('uniform_csr', bool(directed))
+    if key not in cache:
+        cache[key] = RecencyCSR(storage, 1, directed=directed, colocate_x=False)
+    csr = cache[key]
+    if rng_seed is None:  # a fresh draw per call, reproducible under torch.manual_seed
+        rng_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    lo, hi = storage.edge_range(slice)
+    dev = storage.device
+    seeds = seed_nodes.to(device=dev, dtype=torch.int32).contiguous()
+    S, D = seeds.numel(), csr.D
+    nid = torch.empty((S, num_nbrs), dtype=torch.int32, device=dev)
+    nt = torch.empty((S, num_nbrs), dtype=torch.int64, device=dev)
+    nx = torch.empty((S, num_nbrs, D), dtype=torch.float32, device=dev)
+    _cabi.check(_cabi.lib.tgm_csr_sample_uniform(
+        csr.handle, seeds.data_ptr(), S, lo, hi, int(num_nbrs), int(rng_seed), nid.data_ptr(),
+        nt.data_ptr(), nx.data_ptr() if D else None, _cabi.current_stream(dev)))
+    return nid, nt, nx
