@@ -59,7 +59,9 @@ def test_get_nbrs_subsampling_is_valid_and_uniform():
     candidate is picked about equally often."""
     rng = np.random.default_rng(5)
     N, E, D, k = 50, 4000, 3, 5
-    src, dst = rng.integers(0, N, E).astype(np.int32), rng.integers(0, N, E).astype(np.int32)
+    src = rng.integers(0, N, E).astype(np.int32)
+    dst = ((src + 1 + rng.integers(0, N - 1, E)) % N).astype(np.int32)  # no self-loops: a
+    # self-loop contributes two identical candidate rows, which the bookkeeping below would merge
     t = np.sort(rng.integers(0, 500, E)).astype(np.int64)
     x = rng.standard_normal((E, D)).astype(np.float32)
     dg = _graph(src, dst, t, x)
