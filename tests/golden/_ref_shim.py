@@ -48,8 +48,15 @@ def _stub_torch_geometric() -> None:
     mods = {n: types.ModuleType(n) for n in names}
     for cls in ['GCNConv', 'Linear', 'AntiSymmetricConv', 'TransformerConv', 'ChebConv']:
         setattr(mods['torch_geometric.nn'], cls, type(cls, (_Dummy,), {}))
-    for fn in ['ones', 'zeros', 'glorot']:
+    def _zeros(value):
+        # torch_geometric.nn.inits.zeros: in-place fill with 0 (TGNMemory.reset_state relies on it,
+        # tgm/nn/encoder/tgn.py:149-152)
+        if isinstance(value, torch.Tensor):
+            value.data.fill_(0)
+
+    for fn in ['ones', 'glorot']:
         setattr(mods['torch_geometric.nn.inits'], fn, _noop)
+    mods['torch_geometric.nn.inits'].zeros = _zeros
     mods['torch_geometric.nn.models.tgn'].TimeEncoder = type('TimeEncoder', (_Dummy,), {})
     mods['torch_geometric.utils'].scatter = _scatter
     mods['torch_geometric'].nn = mods['torch_geometric.nn']

@@ -255,3 +255,32 @@ def test_uniform_oracle_matches_reference_fixture(path):
             assert np.array_equal(nt, z[f'b{b}_h{h}_nt'])
             assert np.array_equal(nx, z[f'b{b}_h{h}_nx'])
             assert np.array_equal(seeds.astype(np.int32), z[f'b{b}_h{h}_seed'])
+
+
+# ---- TGN node memory oracle vs fixtures from the live reference TGNMemory ------------------------
+from oracle.tgn_oracle import TGNMemoryOracle  # noqa: E402
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'tgn_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[4:-4])
+def test_tgn_memory_oracle_matches_reference(path):
+    z = np.load(path)
+    p = _params(z)
+    N, bs, eval_from = int(z['N']), int(z['bs']), int(z['eval_from'])
+    D = z['x'].shape[1]
+    M = p['memory_updater.weight_hh'].shape[1]
+    TD = p['time_enc.w.bias'].shape[0]
+    mem = TGNMemoryOracle(N, D, M, TD, p)
+    E = len(z['src'])
+    for b, lo in enumerate(range(0, E, bs)):
+        hi = min(lo + bs, E)
+        if b == eval_from:
+            mem.train(False)
+            assert np.abs(mem.memory - z['flush_memory']).max() <= 5e-6
+            assert np.array_equal(mem.last_update, z['flush_last_update'])
+        zz, lu = mem.forward(z[f'b{b}_nid'])
+        assert np.abs(zz - z[f'b{b}_z']).max() <= 5e-6, b
+        assert np.array_equal(lu, z[f'b{b}_lu']), b
+        mem.update_state(z['src'][lo:hi], z['dst'][lo:hi], z['t'][lo:hi], z['x'][lo:hi])
+    assert np.abs(mem.memory - z['final_memory']).max() <= 5e-6
+    assert np.array_equal(mem.last_update, z['final_last_update'])
