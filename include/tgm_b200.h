@@ -238,6 +238,38 @@ int tgm_mlp2_forward(tgm_mlp2 *, const float *x1, const float *x2, int64_t S, fl
 int tgm_gather_rows(const float *table, int64_t num_rows, int32_t dim, const int32_t *ids,
                     int64_t n, float *out, tgm_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * TGN node memory with IdentityMessage + LastAggregator.  Replaces TGNMemory's state machine
+ * (tgm/nn/encoder/tgn.py):
+ *   :128-133 state (memory f32[N,M], last_update int64[N], per-node message stores)
+ *   :149-152 reset_state -> tgm_tgn_reset        :157-163 forward      -> tgm_tgn_forward
+ *   :165-178 update_state -> tgm_tgn_update_state :245-251 train(False) -> tgm_tgn_flush
+ * memory_updater = GRUCell(raw_msg_dim + 2*memory_dim + time_dim, memory_dim): gru_w_ih
+ * [3M, in], gru_w_hh [3M, M], gru_b_ih [3M], gru_b_hh [3M] in torch's (r, z, n) gate order;
+ * time_enc = Time2Vec(time_dim).  Parameter pointers may be host or device (copied).
+ */
+typedef struct tgm_tgn tgm_tgn;
+int tgm_tgn_create(tgm_tgn **out, int32_t num_nodes, int32_t raw_msg_dim, int32_t memory_dim,
+                   int32_t time_dim, const float *gru_w_ih, const float *gru_w_hh,
+                   const float *gru_b_ih, const float *gru_b_hh, const float *t2v_w,
+                   const float *t2v_b, int device);
+void tgm_tgn_destroy(tgm_tgn *);
+int tgm_tgn_reset(tgm_tgn *, tgm_stream stream);
+/* device pointers to the live memory [N,M] / last_update [N] (checkpointing, all-gather). */
+int tgm_tgn_state(const tgm_tgn *, float **memory, int64_t **last_update);
+/* n_id int64[n] -> out_memory f32[n,M], out_last_update int64[n].  training != 0: the memory the
+ * nodes would have after consuming their stored messages, WITHOUT writing it (tgn.py:158-159);
+ * training == 0: the stored rows (tgn.py:160-161). */
+int tgm_tgn_forward(tgm_tgn *, const int64_t *n_id, int64_t n, int training, float *out_memory,
+                    int64_t *out_last_update, tgm_stream stream);
+/* One batch of events: src,dst int32[Eb], t int64[Eb], raw_msg f32[Eb,raw_msg_dim].
+ * training != 0: update the memory of the batch's nodes from their stored messages, then store
+ * this batch's messages; training == 0: store first, then update (tgn.py:170-177). */
+int tgm_tgn_update_state(tgm_tgn *, const int32_t *src, const int32_t *dst, const int64_t *t,
+                         const float *raw_msg, int64_t Eb, int training, tgm_stream stream);
+/* train() -> eval() transition: consume every stored message into memory, clear the stores. */
+int tgm_tgn_flush(tgm_tgn *, tgm_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

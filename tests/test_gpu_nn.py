@@ -117,3 +117,70 @@ def test_attention_requires_cuda_and_eval():
                           torch.zeros(2, 1, dtype=torch.int32))
     with pytest.raises(ValueError):
         TemporalAttention(0, 1, 1, 1)
+
+
+# ---- TGN node memory ---------------------------------------------------
+from oracle.tgn_oracle import TGNMemoryOracle  # noqa: E402
+from tgm_b200.nn import TGNMemory  # noqa: E402
+
+
+def _tgn_from_fixture(z):
+    p = _params(z)
+    N, D = int(z['N']), z['x'].shape[1]
+    M = p['memory_updater.weight_hh'].shape[1]
+    TD = p['time_enc.w.bias'].shape[0]
+    mem = TGNMemory(N, D, M, TD)
+    mem.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+    return mem.to(DEV), p, (N, D, M, TD)
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'tgn_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[4:-4])
+def test_tgn_memory_matches_reference_fixture(path):
+    """Same call sequence as tests/golden/make_golden_tgn.py (the driving loop of
+    examples/linkproppred/tgn.py): forward(n_id) then update_state per batch, train -> eval
+    flush in the middle; memory within 1e-5, last_update exact."""
+    z = np.load(path)
+    mem, _, _ = _tgn_from_fixture(z)
+    mem.train()
+    mem.reset_state()
+    bs, eval_from, E = int(z['bs']), int(z['eval_from']), len(z['src'])
+    for b, lo in enumerate(range(0, E, bs)):
+        hi = min(lo + bs, E)
+        if b == eval_from:
+            mem.eval()
+            assert np.abs(mem.memory.cpu().numpy() - z['flush_memory']).max() <= TOL
+            assert np.array_equal(mem.last_update.cpu().numpy(), z['flush_last_update'])
+        zz, lu = mem(T(z[f'b{b}_nid']))
+        assert np.abs(zz.cpu().numpy() - z[f'b{b}_z']).max() <= TOL, b
+        assert np.array_equal(lu.cpu().numpy(), z[f'b{b}_lu']), b
+        mem.update_state(T(z['src'][lo:hi]), T(z['dst'][lo:hi]), T(z['t'][lo:hi]), T(z['x'][lo:hi]))
+    assert np.abs(mem.memory.cpu().numpy() - z['final_memory']).max() <= TOL
+    assert np.array_equal(mem.last_update.cpu().numpy(), z['final_last_update'])
+
+
+def test_tgn_memory_vs_oracle_longer_stream():
+    """3000 events, 500 nodes, bs 200, unique timestamps (parity domain), C4 dims D=16, M=100."""
+    rng = np.random.default_rng(12)
+    N, E, D, M, TD, bs = 500, 3000, 16, 100, 100, 200
+    src, dst = rng.integers(0, N, E), rng.integers(0, N, E)
+    t = np.sort(rng.choice(2_000_000, E, replace=False))
+    x = rng.standard_normal((E, D)).astype(np.float32)
+    torch.manual_seed(1)
+    mem = TGNMemory(N, D, M, TD).to(DEV)
+    p = {k: v.detach().cpu().numpy() for k, v in mem.state_dict().items()}
+    oracle = TGNMemoryOracle(N, D, M, TD, p)
+    mem.train()
+    mem.reset_state()
+    for b, lo in enumerate(range(0, E, bs)):
+        hi = lo + bs
+        n_id = np.unique(np.concatenate([src[lo:hi], dst[lo:hi], rng.integers(0, N, 50)]))
+        zz, lu = mem(T(n_id))
+        wz, wlu = oracle.forward(n_id)
+        assert np.abs(zz.cpu().numpy() - wz).max() <= TOL and np.array_equal(lu.cpu().numpy(), wlu)
+        mem.update_state(T(src[lo:hi]), T(dst[lo:hi]), T(t[lo:hi]), T(x[lo:hi]))
+        oracle.update_state(src[lo:hi], dst[lo:hi], t[lo:hi], x[lo:hi])
+    mem.eval()
+    oracle.train(False)
+    assert np.abs(mem.memory.cpu().numpy() - oracle.memory).max() <= TOL
+    assert np.array_equal(mem.last_update.cpu().numpy(), oracle.last_update)

@@ -89,6 +89,16 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_int]),
     'tgm_mlp2_destroy': (None, [c_void_p]),
     'tgm_mlp2_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'tgm_tgn_create': (c_int, [POINTER(c_void_p), c_int32, c_int32, c_int32, c_int32, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    'tgm_tgn_destroy': (None, [c_void_p]),
+    'tgm_tgn_reset': (c_int, [c_void_p, c_void_p]),
+    'tgm_tgn_state': (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
+    'tgm_tgn_forward': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p,
+                                c_void_p]),
+    'tgm_tgn_update_state': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                     c_int, c_void_p]),
+    'tgm_tgn_flush': (c_int, [c_void_p, c_void_p]),
     'tgm_gather_rows': (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p,
                                 c_void_p]),
 }

@@ -1,0 +1,135 @@
+"""TGNMemory on the B200 library: same constructor, parameter/buffer names and methods as
+tgm/nn/encoder/tgn.py:80-251 (`forward`, `update_state`, `reset_state`, `detach`, `train`), with
+IdentityMessage + LastAggregator.  The per-node Python dict message store and its per-node Python
+loops (tgn.py:183-184, :226-229, :234) are a fixed-size device state behind `tgm_tgn_*`
+(include/tgm_b200.h).  Forward / state updates only (no autograd through the memory updater)."""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from tgm_b200 import _cabi
+from tgm_b200.nn.attention import Time2Vec, _NativeHandle, _f32, _version
+
+
+class IdentityMessage(nn.Module):
+    def __init__(self, raw_msg_dim: int, memory_dim: int, time_dim: int) -> None:
+        super().__init__()
+        self.out_channels = raw_msg_dim + 2 * memory_dim + time_dim
+
+    def forward(self, z_src: Tensor, z_dst: Tensor, raw_msg: Tensor, t_enc: Tensor) -> Tensor:
+        return torch.cat([z_src, z_dst, raw_msg, t_enc], dim=-1)
+
+
+class LastAggregator(nn.Module):
+    """Marker module: the device state machine implements exactly this aggregator (tgn.py:43-56)."""
+
+
+class TGNMemory(nn.Module):
+    def __init__(self, num_nodes: int, raw_msg_dim: int, memory_dim: int, time_dim: int,
+                 message_module: Optional[Callable] = None,
+                 aggregator_module: Optional[Callable] = None) -> None:
+        super().__init__()
+        message_module = message_module or IdentityMessage(raw_msg_dim, memory_dim, time_dim)
+        aggregator_module = aggregator_module or LastAggregator()
+        if not isinstance(message_module, IdentityMessage) or \
+                not isinstance(aggregator_module, LastAggregator):
+            raise NotImplementedError('the B200 TGN memory implements IdentityMessage + '
+                                      'LastAggregator (examples/linkproppred/tgn.py)')
+        self.num_nodes, self.raw_msg_dim = num_nodes, raw_msg_dim
+        self.memory_dim, self.time_dim = memory_dim, time_dim
+        self.msg_s_module, self.msg_d_module = message_module, message_module
+        self.aggr_module = aggregator_module
+        self.time_enc = Time2Vec(time_dim=time_dim)
+        self.memory_updater = nn.GRUCell(message_module.out_channels, memory_dim)
+        self._native = _NativeHandle(_cabi.lib.tgm_tgn_destroy)
+
+    @property
+    def device(self) -> torch.device:
+        return self.time_enc.w.weight.device
+
+    def _handle(self) -> ctypes.c_void_p:
+        params = [self.memory_updater.weight_ih, self.memory_updater.weight_hh,
+                  self.memory_updater.bias_ih, self.memory_updater.bias_hh,
+                  self.time_enc.w.weight, self.time_enc.w.bias]
+        ver = _version(params)
+        if self._native.version != ver:
+            dev = self.device
+            if dev.type != 'cuda':
+                raise _cabi.TGMNativeError(-3, 'TGNMemory needs CUDA parameters (no CPU fallback)')
+            old = self._snapshot() if self._native.h.value else None
+            self._native.free()
+            t = [_f32(p) for p in params]
+            _cabi.check(_cabi.lib.tgm_tgn_create(
+                ctypes.byref(self._native.h), self.num_nodes, self.raw_msg_dim, self.memory_dim,
+                self.time_dim, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(),
+                t[4].reshape(-1).data_ptr(), t[5].data_ptr(),
+                dev.index if dev.index is not None else torch.cuda.current_device()))
+            self._native.version = ver
+            if old is not None:  # parameters changed (optimizer step): the state carries over
+                self.memory.copy_(old[0])
+                self.last_update.copy_(old[1])
+        return self._native.h
+
+    def _views(self) -> Tuple[Tensor, Tensor]:
+        pm, pl = ctypes.c_void_p(), ctypes.c_void_p()
+        _cabi.check(_cabi.lib.tgm_tgn_state(self._handle(), ctypes.byref(pm), ctypes.byref(pl)))
+        dev = self.device
+        return (_cabi.device_view(pm.value, (self.num_nodes, self.memory_dim), torch.float32, dev),
+                _cabi.device_view(pl.value, (self.num_nodes,), torch.int64, dev))
+
+    def _snapshot(self):
+        pm, pl = ctypes.c_void_p(), ctypes.c_void_p()
+        _cabi.check(_cabi.lib.tgm_tgn_state(self._native.h, ctypes.byref(pm), ctypes.byref(pl)))
+        dev = self.device
+        return (_cabi.device_view(pm.value, (self.num_nodes, self.memory_dim), torch.float32,
+                                  dev).clone(),
+                _cabi.device_view(pl.value, (self.num_nodes,), torch.int64, dev).clone())
+
+    @property
+    def memory(self) -> Tensor:
+        """Live view of the device memory [num_nodes, memory_dim]."""
+        return self._views()[0]
+
+    @property
+    def last_update(self) -> Tensor:
+        return self._views()[1]
+
+    def reset_state(self) -> None:
+        _cabi.check(_cabi.lib.tgm_tgn_reset(self._handle(), _cabi.current_stream(self.device)))
+
+    def detach(self) -> None:  # no autograd state is kept on the device path
+        return None
+
+    @torch.no_grad()
+    def forward(self, n_id: Tensor) -> Tuple[Tensor, Tensor]:
+        dev = self.device
+        n_id = n_id.to(device=dev, dtype=torch.int64).contiguous()
+        n = n_id.numel()
+        mem = torch.empty((n, self.memory_dim), dtype=torch.float32, device=dev)
+        lu = torch.empty((n,), dtype=torch.int64, device=dev)
+        _cabi.check(_cabi.lib.tgm_tgn_forward(self._handle(), n_id.data_ptr(), n,
+                                              int(self.training), mem.data_ptr(), lu.data_ptr(),
+                                              _cabi.current_stream(dev)))
+        return mem, lu
+
+    @torch.no_grad()
+    def update_state(self, src: Tensor, dst: Tensor, t: Tensor, raw_msg: Tensor) -> None:
+        dev = self.device
+        src = src.to(device=dev, dtype=torch.int32).contiguous()
+        dst = dst.to(device=dev, dtype=torch.int32).contiguous()
+        t = t.to(device=dev, dtype=torch.int64).contiguous()
+        raw = _f32(raw_msg.to(dev))
+        _cabi.check(_cabi.lib.tgm_tgn_update_state(
+            self._handle(), src.data_ptr(), dst.data_ptr(), t.data_ptr(), raw.data_ptr(),
+            src.numel(), int(self.training), _cabi.current_stream(dev)))
+
+    def train(self, mode: bool = True) -> 'TGNMemory':
+        if self.training and not mode and self._native.h.value:
+            # flush the message store into memory when entering eval mode (tgn.py:245-251)
+            _cabi.check(_cabi.lib.tgm_tgn_flush(self._handle(), _cabi.current_stream(self.device)))
+        return super().train(mode)
