@@ -106,7 +106,7 @@ def test_get_nbrs_deterministic_cases_vs_oracle():
     """Mixed degrees: rows of seeds with <= k candidates equal the oracle exactly (incl. a slice
     with a start bound and directed mode); the others are checked for validity."""
     rng = np.random.default_rng(8)
-    N, E, D, k = 400, 3000, 4, 12
+    N, E, D, k = 400, 3000, 4, 8
     src, dst = rng.integers(0, N, E).astype(np.int32), rng.integers(0, N, E).astype(np.int32)
     t = np.sort(rng.integers(0, 900, E)).astype(np.int64)
     x = rng.standard_normal((E, D)).astype(np.float32)
@@ -120,7 +120,7 @@ def test_get_nbrs_deterministic_cases_vs_oracle():
             nid, nt, nx = dg._storage.get_nbrs(torch.from_numpy(seeds), k, sl, directed)
             w_nid, w_nt, w_nx, exact = uniform_sample_deterministic(src, dst, t, x, e_lo, e_hi,
                                                                     seeds, k, directed)
-            assert exact.sum() > 100 and (~exact).sum() > 10
+            assert exact.sum() > 100 and (~exact).sum() > (3 if directed else 50)
             assert np.array_equal(nid.cpu().numpy()[exact], w_nid[exact])
             assert np.array_equal(nt.cpu().numpy()[exact], w_nt[exact])
             assert np.array_equal(nx.cpu().numpy()[exact], w_nx[exact])
