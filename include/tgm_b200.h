@@ -270,6 +270,41 @@ int tgm_tgn_update_state(tgm_tgn *, const int32_t *src, const int32_t *dst, cons
 /* train() -> eval() transition: consume every stored message into memory, clear the stores. */
 int tgm_tgn_flush(tgm_tgn *, tgm_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * DyGFormer forward (eval mode).  Replaces DyGFormer.forward with its co-occurrence encoder,
+ * patching and transformer layers (tgm/nn/encoder/dygformer.py:13-77, 80-143, 243-444).
+ * Parameters use torch's layouts ([out_features, in_features] row-major; MultiheadAttention
+ * in_proj_weight [3E, E]); E = 4 * channel_dim; pointers may be host or device (copied).
+ */
+typedef struct {
+  const float *in_proj_w, *in_proj_b;   /* transformers.i.multi_head_attention.in_proj_{weight,bias} */
+  const float *out_proj_w, *out_proj_b; /* ....multi_head_attention.out_proj.{weight,bias} */
+  const float *ffn1_w, *ffn1_b;         /* ....linear_layers.0  [4E, E] */
+  const float *ffn2_w, *ffn2_b;         /* ....linear_layers.1  [E, 4E] */
+  const float *ln0_w, *ln0_b, *ln1_w, *ln1_b; /* ....norm_layers.{0,1} */
+} tgm_dyg_layer;
+typedef struct {
+  int32_t node_dim, edge_dim, time_dim, channel_dim, out_dim, patch_size, num_layers, num_heads;
+  int32_t seq_len; /* max_input_sequence_length = 1 + sampled neighbours per node */
+  float ln_eps;
+  const float *t2v_w, *t2v_b;                     /* time_encoder.w.{weight,bias} */
+  const float *cooc_w1, *cooc_b1, *cooc_w2, *cooc_b2; /* co-occurrence MLP: Linear(1,C), Linear(C,C) */
+  const float *proj_w[4], *proj_b[4];             /* projection_layer.{node,edge,time,neighbor_co_occurrence} */
+  const tgm_dyg_layer *layers;                    /* [num_layers] */
+  const float *out_w, *out_b;                     /* output_layer */
+} tgm_dyg_params;
+typedef struct tgm_dyg tgm_dyg;
+int tgm_dyg_create(tgm_dyg **out, const tgm_dyg_params *params, int device);
+void tgm_dyg_destroy(tgm_dyg *);
+/* node_x f32[num_nodes,node_dim]; src,dst int32[B] (edge_index rows); edge_time int64[B];
+ * nbrs int32[2B,k], nbr_t int64[2B,k], nbr_x f32[2B,k,edge_dim] with k = seq_len - 1: rows [0,B)
+ * are the neighbours of the sources, [B,2B) of the destinations (dygformer.py:262-270);
+ * out_src,out_dst f32[B,out_dim]. */
+int tgm_dyg_forward(tgm_dyg *, const float *node_x, int64_t num_nodes, const int32_t *src,
+                    const int32_t *dst, const int64_t *edge_time, const int32_t *nbrs,
+                    const int64_t *nbr_t, const float *nbr_x, int64_t B, float *out_src,
+                    float *out_dst, tgm_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,3 +97,96 @@ def tgat_forward(p: Dict[str, np.ndarray], num_layers: int, n_heads: int, node_x
                 nbr_time_feat=_t2v(p, 'time_encoder.', seed_times[i][:, None] - nbr_edge_time[i]))
             z[j][i] = merge_layer(p, f'merge_layers.{j - 1}.', out, z[0][i])  # :148
     return z[num_layers][0]
+
+
+# ---- DyGFormer (tgm/nn/encoder/dygformer.py) ------------------------------------------------------
+def _gelu(x: np.ndarray) -> np.ndarray:
+    from math import erf
+    v = np.vectorize(erf, otypes=[np.float64])(x.astype(np.float64) / np.sqrt(2.0))
+    return (x * (0.5 * (1.0 + v))).astype(f32)
+
+
+def cooccurrence_freq(src_nbrs: np.ndarray, dst_nbrs: np.ndarray):
+    """NeighborCooccurrenceEncoder._count_nodes_freq (dygformer.py:33-51): per position the
+    number of occurrences of that id in its own sequence and in the other one; 0 for padding."""
+    B, L = src_nbrs.shape
+    src_freq = np.zeros((B, L, 2), f32)
+    dst_freq = np.zeros((B, L, 2), f32)
+    for b in range(B):
+        s, d = src_nbrs[b], dst_nbrs[b]
+        for j in range(L):
+            src_freq[b, j] = ((s == s[j]).sum(), (d == s[j]).sum())
+            dst_freq[b, j] = ((d == d[j]).sum(), (s == d[j]).sum())
+    src_freq[src_nbrs == PADDED_NODE_ID] = 0
+    dst_freq[dst_nbrs == PADDED_NODE_ID] = 0
+    return src_freq, dst_freq
+
+
+def _cooc_encode(p, freq):
+    pre = 'co_occurrence_encoder.neighbor_co_occurrence_encoder.'
+    h = np.maximum(_linear(freq[..., None], p[pre + '0.weight'], p[pre + '0.bias']), 0)  # :68-70
+    return _linear(h, p[pre + '2.weight'], p[pre + '2.bias']).sum(2).astype(f32)
+
+
+def _mha(p, pre, x, num_heads):
+    """nn.MultiheadAttention(batch_first=False) self-attention on x [B, T, E] (eval mode)."""
+    B, T, E = x.shape
+    hd = E // num_heads
+    qkv = _linear(x, p[pre + 'in_proj_weight'], p[pre + 'in_proj_bias'])
+    q, k, v = (qkv[..., i * E:(i + 1) * E].reshape(B, T, num_heads, hd).transpose(0, 2, 1, 3)
+               for i in range(3))
+    a = np.einsum('bhqd,bhkd->bhqk', q * f32(hd ** -0.5), k).astype(f32)
+    a = np.exp(a - a.max(-1, keepdims=True), dtype=f32)
+    a = a / a.sum(-1, keepdims=True, dtype=f32)
+    o = np.einsum('bhqk,bhkd->bhqd', a, v).astype(f32).transpose(0, 2, 1, 3).reshape(B, T, E)
+    return _linear(o, p[pre + 'out_proj.weight'], p[pre + 'out_proj.bias'])
+
+
+def _transformer_layer(p, pre, x, num_heads):
+    """TransformerEncoder.forward (dygformer.py:117-143), pre-LN, eval mode."""
+    h = layer_norm(x, p[pre + 'norm_layers.0.weight'], p[pre + 'norm_layers.0.bias'])
+    out = x + _mha(p, pre + 'multi_head_attention.', h, num_heads)
+    h = layer_norm(out, p[pre + 'norm_layers.1.weight'], p[pre + 'norm_layers.1.bias'])
+    h = _gelu(_linear(h, p[pre + 'linear_layers.0.weight'], p[pre + 'linear_layers.0.bias']))
+    return out + _linear(h, p[pre + 'linear_layers.1.weight'], p[pre + 'linear_layers.1.bias'])
+
+
+def dygformer_forward(p: Dict[str, np.ndarray], patch_size: int, num_layers: int, num_heads: int,
+                      node_x, edge_index, edge_time, neighbours, neighbours_time,
+                      neighbours_edge_feat):
+    """DyGFormer.forward (dygformer.py:243-431); `p` is the module's state_dict as numpy."""
+    src, dst = edge_index[0], edge_index[1]
+    B = len(src)
+    seqs = []
+    for ids, sl in ((src, slice(0, B)), (dst, slice(B, 2 * B))):
+        nb = np.concatenate([ids[:, None], neighbours[sl]], 1)  # :274-275
+        nt = np.concatenate([edge_time[:, None], neighbours_time[sl]], 1)
+        ef = np.concatenate([np.zeros((B, 1, neighbours_edge_feat.shape[2]), f32),
+                             neighbours_edge_feat[sl]], 1)
+        nf = node_x[nb].astype(f32)
+        nf[nb == PADDED_NODE_ID] = 0  # :298-299
+        tf = _t2v(p, 'time_encoder.', edge_time[:, None] - nt)
+        tf[nb == PADDED_NODE_ID] = 0  # :308-310
+        seqs.append((nb, nf, ef, tf))
+    cs, cd = cooccurrence_freq(seqs[0][0], seqs[1][0])
+    cooc = (_cooc_encode(p, cs), _cooc_encode(p, cd))
+    L = seqs[0][0].shape[1]
+    NP = L // patch_size
+    tokens = []
+    for side in range(2):
+        _, nf, ef, tf = seqs[side]
+        chans = []
+        for name, feat in (('node', nf), ('edge', ef), ('time', tf),
+                           ('neighbor_co_occurrence', cooc[side])):
+            patches = feat.reshape(B, NP, patch_size * feat.shape[2])  # _get_patches :433-444
+            chans.append(_linear(patches, p[f'projection_layer.{name}.weight'],
+                                 p[f'projection_layer.{name}.bias']))
+        tokens.append(np.stack(chans, 2).reshape(B, NP, -1))  # :401-413
+    x = np.concatenate(tokens, 1).astype(f32)
+    for i in range(num_layers):
+        x = _transformer_layer(p, f'transformers.{i}.', x, num_heads)
+    outs = []
+    for side in range(2):
+        pooled = x[:, side * NP:(side + 1) * NP].mean(1, dtype=f32)  # :424-425
+        outs.append(_linear(pooled, p['output_layer.weight'], p['output_layer.bias']))
+    return outs[0], outs[1]

@@ -184,3 +184,55 @@ def test_tgn_memory_vs_oracle_longer_stream():
     oracle.train(False)
     assert np.abs(mem.memory.cpu().numpy() - oracle.memory).max() <= TOL
     assert np.array_equal(mem.last_update.cpu().numpy(), oracle.last_update)
+
+
+# ---- DyGFormer ---------------------------------------------------------
+from tgm_b200.nn import DyGFormer  # noqa: E402
+
+
+def _dyg_from_params(p, patch_size, num_layers, num_heads, L):
+    dN = p['projection_layer.node.weight'].shape[1] // patch_size
+    dE = p['projection_layer.edge.weight'].shape[1] // patch_size
+    dT = p['time_encoder.w.bias'].shape[0]
+    C = p['projection_layer.node.weight'].shape[0]
+    out = p['output_layer.bias'].shape[0]
+    m = DyGFormer(dN, dE, dT, C, output_dim=out, patch_size=patch_size, num_layers=num_layers,
+                  num_heads=num_heads, max_input_sequence_length=L)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+    return m.to(DEV).eval()
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'nn_dygformer_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[13:-4])
+def test_dygformer_matches_reference_fixture(path):
+    z = np.load(path)
+    L = z['nbrs'].shape[1] + 1
+    m = _dyg_from_params(_params(z), int(z['patch_size']), int(z['num_layers']),
+                         int(z['num_heads']), L)
+    zs, zd = m(T(z['node_x']), T(np.stack([z['src'], z['dst']])), T(z['t']), T(z['nbrs']),
+               T(z['nt']), T(z['ef']))
+    assert np.abs(zs.cpu().numpy() - z['z_src']).max() <= TOL
+    assert np.abs(zd.cpu().numpy() - z['z_dst']).max() <= TOL
+
+
+def test_dygformer_vs_oracle_at_config5_dims():
+    """BASELINE configs[4] shapes: sequence 32 (self + 31 sampled), patch 1, 4 x 50 channels,
+    2 layers, 2 heads, edge dim 16; 24 edge pairs, seeded weights, left-padded sequences."""
+    torch.manual_seed(3)
+    rng = np.random.default_rng(3)
+    N, B, L, dN, dE, dT, C, out = 500, 24, 32, 8, 16, 100, 50, 172
+    m = DyGFormer(dN, dE, dT, C, output_dim=out, patch_size=1, num_layers=2, num_heads=2,
+                  max_input_sequence_length=L).to(DEV).eval()
+    k = L - 1
+    node_x = rng.standard_normal((N, dN)).astype(np.float32)
+    src, dst = rng.integers(0, N, B), rng.integers(0, N, B)
+    t = rng.integers(10_000, 2_000_000, B)
+    nbrs = rng.integers(0, 40, (2 * B, k)).astype(np.int32)
+    nt = np.sort(np.clip(np.tile(t, 2)[:, None] - rng.integers(1, 9000, (2 * B, k)), 0, None), 1)
+    ef = rng.standard_normal((2 * B, k, dE)).astype(np.float32)
+    pad = np.arange(k)[None, :] < rng.integers(0, k + 1, 2 * B)[:, None]
+    nbrs[pad], nt[pad], ef[pad] = -1, 0, 0.0
+    zs, zd = m(T(node_x), T(np.stack([src, dst])), T(t), T(nbrs), T(nt), T(ef))
+    p = {k_: v.detach().cpu().numpy() for k_, v in m.state_dict().items()}
+    ws, wd = nn_oracle.dygformer_forward(p, 1, 2, 2, node_x, np.stack([src, dst]), t, nbrs, nt, ef)
+    assert np.abs(zs.cpu().numpy() - ws).max() <= TOL and np.abs(zd.cpu().numpy() - wd).max() <= TOL

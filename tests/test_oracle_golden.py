@@ -284,3 +284,13 @@ def test_tgn_memory_oracle_matches_reference(path):
         mem.update_state(z['src'][lo:hi], z['dst'][lo:hi], z['t'][lo:hi], z['x'][lo:hi])
     assert np.abs(mem.memory - z['final_memory']).max() <= 5e-6
     assert np.array_equal(mem.last_update, z['final_last_update'])
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'nn_dygformer_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[13:-4])
+def test_dygformer_oracle_matches_reference_module(path):
+    z = np.load(path)
+    zs, zd = nn_oracle.dygformer_forward(
+        _params(z), int(z['patch_size']), int(z['num_layers']), int(z['num_heads']), z['node_x'],
+        np.stack([z['src'], z['dst']]), z['t'], z['nbrs'], z['nt'], z['ef'])
+    assert np.abs(zs - z['z_src']).max() <= 5e-6 and np.abs(zd - z['z_dst']).max() <= 5e-6

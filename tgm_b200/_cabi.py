@@ -99,6 +99,11 @@ SIGNATURES = {
     'tgm_tgn_update_state': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                      c_int, c_void_p]),
     'tgm_tgn_flush': (c_int, [c_void_p, c_void_p]),
+    'tgm_dyg_create': (c_int, [POINTER(c_void_p), c_void_p, c_int]),
+    'tgm_dyg_destroy': (None, [c_void_p]),
+    'tgm_dyg_forward': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                c_void_p]),
     'tgm_gather_rows': (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p,
                                 c_void_p]),
 }
@@ -107,6 +112,25 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+class DygLayer(ctypes.Structure):
+    """tgm_dyg_layer (include/tgm_b200.h)."""
+    _fields_ = [(n, c_void_p) for n in ('in_proj_w', 'in_proj_b', 'out_proj_w', 'out_proj_b',
+                                        'ffn1_w', 'ffn1_b', 'ffn2_w', 'ffn2_b', 'ln0_w', 'ln0_b',
+                                        'ln1_w', 'ln1_b')]
+
+
+class DygParams(ctypes.Structure):
+    """tgm_dyg_params (include/tgm_b200.h)."""
+    _fields_ = ([(n, c_int32) for n in ('node_dim', 'edge_dim', 'time_dim', 'channel_dim',
+                                        'out_dim', 'patch_size', 'num_layers', 'num_heads',
+                                        'seq_len')] +
+                [('ln_eps', c_float)] +
+                [(n, c_void_p) for n in ('t2v_w', 't2v_b', 'cooc_w1', 'cooc_b1', 'cooc_w2',
+                                         'cooc_b2')] +
+                [('proj_w', c_void_p * 4), ('proj_b', c_void_p * 4),
+                 ('layers', POINTER(DygLayer)), ('out_w', c_void_p), ('out_b', c_void_p)])
 
 
 def last_error() -> str:

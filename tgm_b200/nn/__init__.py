@@ -2,8 +2,9 @@
 puts on the path): forward-only `torch.nn.Module`s with the reference's parameter names and
 shapes, so `state_dict`s interchange, executing on the CUDA library (include/tgm_b200.h)."""
 from .attention import MergeLayer, TemporalAttention, Time2Vec, masked_mean
+from .dygformer import DyGFormer
 from .tgat import TGAT
 from .tgn import IdentityMessage, LastAggregator, TGNMemory
 
-__all__ = ['TemporalAttention', 'Time2Vec', 'MergeLayer', 'TGAT', 'masked_mean',
+__all__ = ['TemporalAttention', 'Time2Vec', 'MergeLayer', 'TGAT', 'DyGFormer', 'masked_mean',
            'TGNMemory', 'IdentityMessage', 'LastAggregator']
