@@ -211,6 +211,9 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO; keep stdout to the
+        # one JSON line the driver parses
+        os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
 
     E, N, D, k, bs = a.edges, a.nodes, a.dim, a.k, a.batch_size
