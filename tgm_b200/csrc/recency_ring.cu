@@ -316,6 +316,10 @@ extern "C" int tgm_recency_update(tgm_recency *h, const int32_t *src, const int3
   DeviceGuard g(h->device);
   cudaStream_t st = as_stream(stream);
   const int64_t n = directed ? Eb : 2 * Eb;
+  // the in-batch ranking is O(n^2 / tile): right for loader batches, not for bulk loads
+  TGM_REQUIRE(n <= (int64_t(1) << 17),
+              "tgm_recency_update: batch too large for the stateful ring (max 65536 edges); "
+              "bulk streams go through tgm_csr_build / tgm_csr_sample");
   if (n > h->cap) {
     // growing the scratch is the only synchronising path; steady state never reallocates
     TGM_CUDA(cudaStreamSynchronize(st));

@@ -443,6 +443,8 @@ extern "C" int tgm_tgn_update_state(tgm_tgn *h, const int32_t *src, const int32_
   if (Eb == 0) return TGM_OK;
   TGM_REQUIRE(src && dst && t && (raw_msg || h->D == 0),
               "tgm_tgn_update_state: NULL array argument");
+  TGM_REQUIRE(Eb <= (int64_t(1) << 16),
+              "tgm_tgn_update_state: batch too large (max 65536 events per update)");
   DeviceGuard g(h->device);
   cudaStream_t st = as_stream(stream);
   int rc = ensure_rows(h, 2 * Eb, st);
