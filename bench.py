@@ -56,6 +56,8 @@ def parse_args():
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--no-e2e', action='store_true')
     p.add_argument('--no-colocate', action='store_true')
+    p.add_argument('--feature-copy', default='tma', choices=['tma', 'lsu'],
+                   help='how the sampler moves feature rows: TMA bulk copies or warp loads/stores')
     p.add_argument('--seed', type=int, default=0)
     return p.parse_args()
 
@@ -200,8 +202,9 @@ def run_b200(a):
     import torch
     import torch.distributed as dist
 
-    from tgm_b200 import RecencyCSR
+    from tgm_b200 import RecencyCSR, _cabi
     from tgm_b200.core.storage import DeviceCOOStorage
+    _cabi.check(_cabi.lib.tgm_set_option(b'csr_feature_copy', int(a.feature_copy == 'tma')))
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -304,7 +307,8 @@ def run_b200(a):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     achieved = algo_bytes / launch_s / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'csr_sample_edges_fast_kernel', 'achieved': achieved,
+    roofline = {'bound': 'hbm', 'kernel': 'csr_sample_edges_tma_kernel' if a.feature_copy == 'tma' else
+                'csr_sample_edges_fast_kernel', 'achieved': achieved,
                 'peak': peak, 'peak_source': 'measured' if 'hbm_gbs' in peaks else 'fallback',
                 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                 'algorithmic_bytes_per_launch': algo_bytes,

@@ -49,6 +49,11 @@ int tgm_version(void);
 /* number of visible CUDA devices (0 on a CPU-only host; never an error). */
 int tgm_device_count(void);
 
+/* Tuning switches (process-wide).  "csr_feature_copy": 1 (default) = the hop-0 window sampler moves
+ * feature rows with the TMA unit (cp.async.bulk through shared-memory stages), 0 = with the warp's
+ * own loads/stores.  Results are identical. */
+int tgm_set_option(const char *name, int value);
+
 /* ------------------------------------------------------------------------------------------
  * Edge store.  Replaces DGStorageArrayBackend's edge arrays and its slice lookup:
  *   tgm/core/_storage/backends/array_backend.py:15-21   (__init__ holding DGData)

@@ -101,8 +101,13 @@ def tgat_forward(p: Dict[str, np.ndarray], num_layers: int, n_heads: int, node_x
 
 # ---- DyGFormer (tgm/nn/encoder/dygformer.py) ------------------------------------------------------
 def _gelu(x: np.ndarray) -> np.ndarray:
-    from math import erf
-    v = np.vectorize(erf, otypes=[np.float64])(x.astype(np.float64) / np.sqrt(2.0))
+    """F.gelu (exact, erf form) in float64, rounded once."""
+    try:
+        from scipy.special import erf as _erf
+        v = _erf(x.astype(np.float64) / np.sqrt(2.0))
+    except ImportError:
+        from math import erf
+        v = np.vectorize(erf, otypes=[np.float64])(x.astype(np.float64) / np.sqrt(2.0))
     return (x * (0.5 * (1.0 + v))).astype(f32)
 
 

@@ -39,6 +39,7 @@ SIGNATURES = {
     'tgm_last_error': (c_char_p, []),
     'tgm_version': (c_int, []),
     'tgm_device_count': (c_int, []),
+    'tgm_set_option': (c_int, [c_char_p, c_int]),
     'tgm_store_create': (c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int64, c_int32, c_int32, c_int, c_int, c_void_p]),
     'tgm_store_destroy': (None, [c_void_p]),

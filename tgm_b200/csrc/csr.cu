@@ -18,6 +18,8 @@
 //   xrows    float[n, D]   optional: feature rows in adjacency order (window = contiguous read)
 #include <cub/cub.cuh>
 
+#include <algorithm>
+#include <cstring>
 #include <new>
 
 #include "store.cuh"
@@ -56,6 +58,9 @@ struct tgm_csr {
     }
   }
 };
+
+// 0: feature rows copied by the warp (LSU), 1: by the TMA unit (cp.async.bulk staging)
+static int g_csr_feature_copy = 1;
 
 namespace {
 
@@ -532,6 +537,168 @@ csr_uniform_kernel(const Entry *__restrict__ entries, const int64_t *__restrict_
   }
 }
 
+// ---- TMA variant of the fast hop-0 kernel -------------------------------------------------------
+// Same per-seed logic, but the feature rows never pass through registers: lane 0 of each warp
+// drives a ring of shared-memory stages with 1-D bulk async copies (cp.async.bulk, the TMA unit):
+//   global xrows --(bulk load, mbarrier complete_tx)--> smem stage --(bulk store)--> global out_x
+// Loads run kTmaLag seeds ahead of the stores, so every warp keeps several 1-KB row blocks in
+// flight without spending registers or issue slots on them; the left padding of a row is a bulk
+// store from a zeroed smem block.  Used when a seed's feature block (k*D*4 bytes) fits a stage.
+constexpr int kTmaStages = 4, kTmaLag = 2, kTmaMaxStageBytes = 4096;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return uint32_t(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+struct TmaMeta {  // what the retiring step needs to know about an in-flight seed
+  float *dst;        // first float of the seed's out_x row block
+  uint32_t nbytes;   // valid feature bytes (bulk-loaded)
+  uint32_t padbytes; // zero bytes in front of them
+};
+
+__global__ void __launch_bounds__(kFastThreads)
+csr_sample_edges_tma_kernel(const Entry *__restrict__ entries, const uint2 *__restrict__ anchors,
+                            const float *__restrict__ xrows, const int64_t *__restrict__ t, int D,
+                            int64_t Ew, uint32_t bs, int64_t l_lo, int64_t l_hi, int B, int k,
+                            int32_t *__restrict__ out_nid, int64_t *__restrict__ out_t,
+                            float *__restrict__ out_x, int stage_bytes) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int W = kFastThreads >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // layout: zero block | W * kTmaStages stages | W * kTmaStages mbarriers | W * kTmaStages metas
+  unsigned char *zero = smem_raw;
+  unsigned char *stages = zero + stage_bytes + size_t(warp) * kTmaStages * stage_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + stage_bytes +
+                                                size_t(W) * kTmaStages * stage_bytes) +
+                   warp * kTmaStages;
+  TmaMeta *meta = reinterpret_cast<TmaMeta *>(smem_raw + stage_bytes +
+                                              size_t(W) * kTmaStages * (stage_bytes + 8)) +
+                  warp * kTmaStages;
+  for (int i = threadIdx.x * 4; i < stage_bytes; i += kFastThreads * 4)
+    *reinterpret_cast<uint32_t *>(zero + i) = 0u;
+  if (lane == 0)
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(smem_u32(bars + s), 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const uint32_t zero_s = smem_u32(zero), stage_s = smem_u32(stages), bar_s = smem_u32(bars);
+
+  auto retire = [&](uint32_t q) {  // lane 0 only: seed number q of this warp has landed -> store it
+    const int st = int(q % kTmaStages);
+    const TmaMeta m = meta[st];
+    if (m.nbytes) {
+      mbar_wait(bar_s + st * 8, (q / kTmaStages) & 1u);
+      bulk_s2g(reinterpret_cast<unsigned char *>(m.dst) + m.padbytes, stage_s + st * stage_bytes,
+               m.nbytes);
+    }
+    if (m.padbytes) bulk_s2g(m.dst, zero_s, m.padbytes);
+    bulk_commit();
+  };
+
+  const int64_t S = 2 * (l_hi - l_lo);
+  const int64_t nchunks = (S + 31) >> 5;
+  const int64_t wstride = int64_t(gridDim.x) * W;
+  uint32_t g = 0;  // seeds this warp has started
+  for (int64_t ch = int64_t(blockIdx.x) * W + warp; ch < nchunks; ch += wstride) {
+    const int64_t s_base = ch << 5, s = s_base + lane;
+    SeedWin mine{0, 0, 0};
+    if (s < S) {
+      const int64_t jb = s / (2 * int64_t(bs));
+      const int64_t bstart = l_lo + jb * bs;
+      const int64_t nb = l_hi - bstart < int64_t(bs) ? l_hi - bstart : int64_t(bs);
+      const int64_t rr = s - jb * 2 * int64_t(bs);
+      const bool side = rr >= nb;
+      const int64_t l = bstart + (side ? rr - nb : rr);
+      const uint2 a = __ldg(anchors + (side ? Ew + l : l));
+      mine.nwin = a.y < uint32_t(B) ? int(a.y) : B;
+      mine.wstart = int64_t(a.x) - mine.nwin;
+      mine.q = __ldg(t + l);
+    }
+    const int nseeds = S - s_base < 32 ? int(S - s_base) : 32;
+    int64_t wstart = shfl_i64(mine.wstart, 0);
+    int nwin = __shfl_sync(0xffffffffu, mine.nwin, 0);
+    Entry cur = load_window_entry(entries, wstart, nwin, lane);
+    for (int i = 0; i < nseeds; ++i, ++g) {
+      const int64_t q = shfl_i64(mine.q, i);
+      const int nxt = i + 1 < nseeds ? i + 1 : i;
+      const int64_t wstart_n = shfl_i64(mine.wstart, nxt);
+      const int nwin_n = __shfl_sync(0xffffffffu, mine.nwin, nxt);
+      const Entry ahead = load_window_entry(entries, wstart_n, nwin_n, lane);
+      const unsigned m = __ballot_sync(0xffffffffu, lane < nwin && cur.t < q);
+      const int last = m ? 31 - __clz(m) : -1;
+      const int nvalid = last + 1 < k ? last + 1 : k;
+      const int first = last + 1 - nvalid, pad = k - nvalid;
+      const int srcl = (first + lane - pad) & 31;
+      const int32_t nbr = __shfl_sync(0xffffffffu, cur.nbr, srcl);
+      const int64_t tt = shfl_i64(cur.t, srcl);
+      const int64_t sg = s_base + i;
+      if (lane < k) {
+        const bool v = lane >= pad;
+        out_nid[sg * k + lane] = v ? nbr : TGM_PADDED_NODE_ID;
+        out_t[sg * k + lane] = v ? tt : 0;
+      }
+      if (lane == 0) {
+        const int st = int(g % kTmaStages);
+        bulk_wait_read<kTmaStages - kTmaLag - 1>();  // the store that last read this stage is done
+        TmaMeta mt;
+        mt.dst = out_x + sg * int64_t(k) * D;
+        mt.nbytes = uint32_t(nvalid) * uint32_t(D) * 4u;
+        mt.padbytes = uint32_t(pad) * uint32_t(D) * 4u;
+        meta[st] = mt;
+        if (mt.nbytes) {
+          mbar_expect_tx(bar_s + st * 8, mt.nbytes);
+          bulk_g2s(stage_s + st * stage_bytes, xrows + (wstart + first) * int64_t(D), mt.nbytes,
+                   bar_s + st * 8);
+        }
+        if (g >= uint32_t(kTmaLag)) retire(g - kTmaLag);
+      }
+      cur = ahead;
+      wstart = wstart_n;
+      nwin = nwin_n;
+    }
+  }
+  if (lane == 0) {  // drain
+    for (uint32_t q = g >= uint32_t(kTmaLag) ? g - kTmaLag : 0; q < g; ++q) retire(q);
+    bulk_wait_read<0>();
+  }
+}
+
 int bits_for(uint32_t max_value) {
   int b = 1;
   while (b < 32 && (max_value >> b) != 0) ++b;
@@ -740,7 +907,20 @@ extern "C" int tgm_csr_sample_edges(const tgm_csr *c, int64_t e_lo, int64_t e_hi
   if (rc != TGM_OK) return rc;
   DeviceGuard g(c->device);
   cudaStream_t st = as_stream(stream);
-  if (cfg.fast && c->bs < (int64_t(1) << 31))
+  const int stage_bytes = k * c->D * 4;
+  if (cfg.fast && c->bs < (int64_t(1) << 31) && c->D > 0 && g_csr_feature_copy == 1 &&
+      stage_bytes <= kTmaMaxStageBytes) {
+    const size_t smem = size_t(stage_bytes) +
+                        size_t(kFastThreads / 32) * kTmaStages * (size_t(stage_bytes) + 8 + 16);
+    if (smem > 48 * 1024)
+      TGM_CUDA(cudaFuncSetAttribute(csr_sample_edges_tma_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const int per_sm = int(std::max<size_t>(1, std::min<size_t>(TGM_FAST_MIN_BLOCKS, (220 * 1024) / (smem + 1024))));
+    const int grid = grid_for((S + 31) / 32, kFastThreads / 32, per_sm);
+    csr_sample_edges_tma_kernel<<<grid, kFastThreads, smem, st>>>(
+        c->entries, c->anchors, cfg.xsrc, c->store->t + c->e_start, c->D, c->Ew, uint32_t(c->bs),
+        l_lo, l_hi, B, k, out_nid, out_t, out_x, stage_bytes);
+  } else if (cfg.fast && c->bs < (int64_t(1) << 31))
     csr_sample_edges_fast_kernel<<<cfg.fast_grid, kFastThreads, 0, st>>>(
         c->entries, c->anchors, reinterpret_cast<const float4 *>(cfg.xsrc),
         c->store->t + c->e_start, c->D / 4, c->Ew, uint32_t(c->bs), l_lo, l_hi, B, k, out_nid,
@@ -824,4 +1004,15 @@ extern "C" int tgm_csr_sample_uniform(const tgm_csr *c, const int32_t *seeds, in
       out_t, out_x);
   TGM_LAUNCH_CHECK();
   return TGM_OK;
+}
+
+
+extern "C" int tgm_set_option(const char *name, int value) {
+  TGM_REQUIRE(name != nullptr, "tgm_set_option: name is NULL");
+  if (std::strcmp(name, "csr_feature_copy") == 0) {
+    TGM_REQUIRE(value == 0 || value == 1, "tgm_set_option: csr_feature_copy must be 0 (LSU) or 1 (TMA)");
+    g_csr_feature_copy = value;
+    return TGM_OK;
+  }
+  return fail(TGM_ERR_INVALID, std::string("tgm_set_option: unknown option ") + name);
 }

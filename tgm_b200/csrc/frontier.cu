@@ -3,9 +3,22 @@
 // non-padded subset is what DeduplicationHook keeps (tgm/hooks/dedup.py:44-48).  Three launches:
 // per-tile popcount of warp ballots, a single-CTA scan of the tile counts, and a stable scatter
 // that re-derives each slot's rank from its warp ballot + tile prefix.
+#include <mutex>
+
 #include "common.cuh"
 
 using namespace tgm;
+
+// per-device scratch for the tile counts, grown on demand and kept (cudaMallocAsync's pool is
+// trimmed at every synchronisation, which made each call pay a fresh allocation)
+namespace {
+struct Scratch {
+  int64_t *p = nullptr;
+  size_t cap = 0;
+};
+Scratch g_scratch[64];
+std::mutex g_scratch_mu;
+}  // namespace
 
 namespace {
 
@@ -109,8 +122,23 @@ extern "C" int tgm_frontier_compact(const int32_t *nid, int64_t n, int64_t *out_
   }
   TGM_REQUIRE(nid && out_idx, "tgm_frontier_compact: NULL array argument");
   const int64_t tiles = (n + kTile - 1) / kTile;
+  int dev = 0;
+  TGM_CUDA(cudaGetDevice(&dev));
+  TGM_REQUIRE(dev >= 0 && dev < 64, "tgm_frontier_compact: unsupported device ordinal");
   int64_t *tile_cnt = nullptr;
-  TGM_CUDA(cudaMallocAsync(&tile_cnt, size_t(tiles) * sizeof(int64_t), st));
+  {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    Scratch &sc = g_scratch[dev];
+    if (size_t(tiles) > sc.cap) {
+      TGM_CUDA(cudaStreamSynchronize(st));
+      cudaFree(sc.p);
+      sc.p = nullptr, sc.cap = 0;
+      const size_t cap = size_t(tiles) * 2 + 1024;
+      TGM_CUDA(cudaMalloc(&sc.p, cap * sizeof(int64_t)));
+      sc.cap = cap;
+    }
+    tile_cnt = sc.p;
+  }
   frontier_count_kernel<<<int(tiles), kTileThreads, 0, st>>>(nid, n, tile_cnt);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) {
@@ -121,7 +149,6 @@ extern "C" int tgm_frontier_compact(const int32_t *nid, int64_t n, int64_t *out_
     frontier_scatter_kernel<<<int(tiles), kTileThreads, 0, st>>>(nid, n, tile_cnt, out_idx);
     e = cudaGetLastError();
   }
-  cudaFreeAsync(tile_cnt, st);
   if (e != cudaSuccess) return cuda_fail(e, "frontier launch", __FILE__, __LINE__);
   return TGM_OK;
 }
