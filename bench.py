@@ -58,6 +58,7 @@ def parse_args():
     p.add_argument('--no-colocate', action='store_true')
     p.add_argument('--feature-copy', default='tma', choices=['tma', 'lsu'],
                    help='how the sampler moves feature rows: TMA bulk copies or warp loads/stores')
+    p.add_argument('--tma-ctas-per-sm', type=int, default=0)
     p.add_argument('--seed', type=int, default=0)
     return p.parse_args()
 
@@ -205,6 +206,7 @@ def run_b200(a):
     from tgm_b200 import RecencyCSR, _cabi
     from tgm_b200.core.storage import DeviceCOOStorage
     _cabi.check(_cabi.lib.tgm_set_option(b'csr_feature_copy', int(a.feature_copy == 'tma')))
+    _cabi.check(_cabi.lib.tgm_set_option(b'csr_tma_ctas_per_sm', a.tma_ctas_per_sm))
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

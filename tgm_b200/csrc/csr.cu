@@ -36,6 +36,11 @@ struct tgm_csr {
   int64_t *rowptr = nullptr;
   uint2 *anchors = nullptr;  // [2][Ew]
   float *xrows = nullptr;    // [n, D] when colocate
+  // dynamic chunk counters of the TMA kernel: launch i uses ticket[i % kTickets], so launches of
+  // one handle that overlap on different streams never share a counter
+  static constexpr int kTickets = 64;
+  unsigned long long *ticket = nullptr;
+  mutable unsigned launches = 0;
   // device staging of the host-buffer entry point: one output block per slot, grown on demand
   struct Stage {
     int32_t *nid = nullptr;
@@ -50,6 +55,7 @@ struct tgm_csr {
       cudaFree(rowptr);
       cudaFree(anchors);
       cudaFree(xrows);
+      cudaFree(ticket);
       for (auto &st : stage) {
         cudaFree(st.nid);
         cudaFree(st.t);
@@ -61,6 +67,7 @@ struct tgm_csr {
 
 // 0: feature rows copied by the warp (LSU), 1: by the TMA unit (cp.async.bulk staging)
 static int g_csr_feature_copy = 1;
+static int g_csr_tma_ctas_per_sm = 0;  // 0 = as many as shared memory allows (<= TGM_FAST_MIN_BLOCKS)
 
 namespace {
 
@@ -544,7 +551,11 @@ csr_uniform_kernel(const Entry *__restrict__ entries, const int64_t *__restrict_
 // Loads run kTmaLag seeds ahead of the stores, so every warp keeps several 1-KB row blocks in
 // flight without spending registers or issue slots on them; the left padding of a row is a bulk
 // store from a zeroed smem block.  Used when a seed's feature block (k*D*4 bytes) fits a stage.
-constexpr int kTmaStages = 4, kTmaLag = 2, kTmaMaxStageBytes = 4096;
+#ifndef TGM_TMA_STAGES
+#define TGM_TMA_STAGES 4
+#define TGM_TMA_LAG 2
+#endif
+constexpr int kTmaStages = TGM_TMA_STAGES, kTmaLag = TGM_TMA_LAG, kTmaMaxStageBytes = 4096;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return uint32_t(__cvta_generic_to_shared(p));
@@ -588,8 +599,8 @@ __device__ __forceinline__ void bulk_wait_read() {
 
 struct TmaMeta {  // what the retiring step needs to know about an in-flight seed
   float *dst;        // first float of the seed's out_x row block
-  uint32_t nbytes;   // valid feature bytes (bulk-loaded)
-  uint32_t padbytes; // zero bytes in front of them
+  uint32_t nbytes;   // valid feature bytes (bulk-loaded); 0 = nothing was loaded
+  uint32_t padbytes; // zero bytes in front of them; bit 31 carries the mbarrier phase parity
 };
 
 __global__ void __launch_bounds__(kFastThreads)
@@ -597,7 +608,8 @@ csr_sample_edges_tma_kernel(const Entry *__restrict__ entries, const uint2 *__re
                             const float *__restrict__ xrows, const int64_t *__restrict__ t, int D,
                             int64_t Ew, uint32_t bs, int64_t l_lo, int64_t l_hi, int B, int k,
                             int32_t *__restrict__ out_nid, int64_t *__restrict__ out_t,
-                            float *__restrict__ out_x, int stage_bytes) {
+                            float *__restrict__ out_x, int stage_bytes,
+                            unsigned long long *__restrict__ ticket) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int W = kFastThreads >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -622,20 +634,25 @@ csr_sample_edges_tma_kernel(const Entry *__restrict__ entries, const uint2 *__re
   auto retire = [&](uint32_t q) {  // lane 0 only: seed number q of this warp has landed -> store it
     const int st = int(q % kTmaStages);
     const TmaMeta m = meta[st];
+    const uint32_t padbytes = m.padbytes & 0x7fffffffu;
     if (m.nbytes) {
-      mbar_wait(bar_s + st * 8, (q / kTmaStages) & 1u);
-      bulk_s2g(reinterpret_cast<unsigned char *>(m.dst) + m.padbytes, stage_s + st * stage_bytes,
+      mbar_wait(bar_s + st * 8, m.padbytes >> 31);
+      bulk_s2g(reinterpret_cast<unsigned char *>(m.dst) + padbytes, stage_s + st * stage_bytes,
                m.nbytes);
     }
-    if (m.padbytes) bulk_s2g(m.dst, zero_s, m.padbytes);
+    if (padbytes) bulk_s2g(m.dst, zero_s, padbytes);
     bulk_commit();
   };
 
   const int64_t S = 2 * (l_hi - l_lo);
   const int64_t nchunks = (S + 31) >> 5;
   const int64_t wstride = int64_t(gridDim.x) * W;
-  uint32_t g = 0;  // seeds this warp has started
-  for (int64_t ch = int64_t(blockIdx.x) * W + warp; ch < nchunks; ch += wstride) {
+  uint32_t g = 0;       // seeds this warp has started
+  uint32_t phases = 0;  // lane 0: bit st = parity of the next phase of stage st's mbarrier (a
+                        // stage's barrier only advances when a load is actually issued on it)
+  // chunks of 32 seeds are handed out dynamically (first one by warp id, the rest from a ticket
+  // counter): windows differ in length, and a static split leaves a ~1/iterations tail
+  for (int64_t ch = int64_t(blockIdx.x) * W + warp; ch < nchunks;) {
     const int64_t s_base = ch << 5, s = s_base + lane;
     SeedWin mine{0, 0, 0};
     if (s < S) {
@@ -680,6 +697,10 @@ csr_sample_edges_tma_kernel(const Entry *__restrict__ entries, const uint2 *__re
         mt.dst = out_x + sg * int64_t(k) * D;
         mt.nbytes = uint32_t(nvalid) * uint32_t(D) * 4u;
         mt.padbytes = uint32_t(pad) * uint32_t(D) * 4u;
+        if (mt.nbytes) {
+          mt.padbytes |= ((phases >> st) & 1u) << 31;
+          phases ^= 1u << st;
+        }
         meta[st] = mt;
         if (mt.nbytes) {
           mbar_expect_tx(bar_s + st * 8, mt.nbytes);
@@ -692,6 +713,10 @@ csr_sample_edges_tma_kernel(const Entry *__restrict__ entries, const uint2 *__re
       wstart = wstart_n;
       nwin = nwin_n;
     }
+    unsigned long long nx = 0;
+    if (lane == 0) nx = atomicAdd(ticket, 1ull);
+    ch = wstride + int64_t(__shfl_sync(0xffffffffu, (unsigned int)(nx & 0xffffffffu), 0)) +
+         (int64_t(__shfl_sync(0xffffffffu, (unsigned int)(nx >> 32), 0)) << 32);
   }
   if (lane == 0) {  // drain
     for (uint32_t q = g >= uint32_t(kTmaLag) ? g - kTmaLag : 0; q < g; ++q) retire(q);
@@ -755,6 +780,7 @@ extern "C" int tgm_csr_build(tgm_csr **out, const tgm_store *store, int64_t e_st
   } while (0)
 
   CSR_CUDA(cudaMalloc(&c->rowptr, size_t(c->N + 1) * 8));
+  CSR_CUDA(cudaMalloc(&c->ticket, tgm_csr::kTickets * sizeof(unsigned long long)));
   if (n == 0) {
     CSR_CUDA(cudaMemsetAsync(c->rowptr, 0, size_t(c->N + 1) * 8, st));
     CSR_CUDA(cudaStreamSynchronize(st));
@@ -915,11 +941,14 @@ extern "C" int tgm_csr_sample_edges(const tgm_csr *c, int64_t e_lo, int64_t e_hi
     if (smem > 48 * 1024)
       TGM_CUDA(cudaFuncSetAttribute(csr_sample_edges_tma_kernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    const int per_sm = int(std::max<size_t>(1, std::min<size_t>(TGM_FAST_MIN_BLOCKS, (220 * 1024) / (smem + 1024))));
+    int per_sm = int(std::max<size_t>(1, std::min<size_t>(TGM_FAST_MIN_BLOCKS, (220 * 1024) / (smem + 1024))));
+    if (g_csr_tma_ctas_per_sm > 0 && g_csr_tma_ctas_per_sm < per_sm) per_sm = g_csr_tma_ctas_per_sm;
     const int grid = grid_for((S + 31) / 32, kFastThreads / 32, per_sm);
+    unsigned long long *ticket = c->ticket + (c->launches++ % tgm_csr::kTickets);
+    TGM_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
     csr_sample_edges_tma_kernel<<<grid, kFastThreads, smem, st>>>(
         c->entries, c->anchors, cfg.xsrc, c->store->t + c->e_start, c->D, c->Ew, uint32_t(c->bs),
-        l_lo, l_hi, B, k, out_nid, out_t, out_x, stage_bytes);
+        l_lo, l_hi, B, k, out_nid, out_t, out_x, stage_bytes, ticket);
   } else if (cfg.fast && c->bs < (int64_t(1) << 31))
     csr_sample_edges_fast_kernel<<<cfg.fast_grid, kFastThreads, 0, st>>>(
         c->entries, c->anchors, reinterpret_cast<const float4 *>(cfg.xsrc),
@@ -1012,6 +1041,11 @@ extern "C" int tgm_set_option(const char *name, int value) {
   if (std::strcmp(name, "csr_feature_copy") == 0) {
     TGM_REQUIRE(value == 0 || value == 1, "tgm_set_option: csr_feature_copy must be 0 (LSU) or 1 (TMA)");
     g_csr_feature_copy = value;
+    return TGM_OK;
+  }
+  if (std::strcmp(name, "csr_tma_ctas_per_sm") == 0) {
+    TGM_REQUIRE(value >= 0 && value <= 32, "tgm_set_option: csr_tma_ctas_per_sm must be in [0, 32]");
+    g_csr_tma_ctas_per_sm = value;
     return TGM_OK;
   }
   return fail(TGM_ERR_INVALID, std::string("tgm_set_option: unknown option ") + name);
