@@ -309,10 +309,19 @@ def run_b200(a):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     achieved = algo_bytes / launch_s / 1e9
+    traffic = None  # DRAM bytes per launch from the committed ncu capture of this kernel
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+        if a.feature_copy == 'tma' and D == 16 and k == 20:
+            traffic = tr['dram_bytes_per_sampled_edge'] * slots_per_launch
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {'bound': 'hbm', 'kernel': 'csr_sample_edges_tma_kernel' if a.feature_copy == 'tma' else
                 'csr_sample_edges_fast_kernel', 'achieved': achieved,
                 'peak': peak, 'peak_source': 'measured' if 'hbm_gbs' in peaks else 'fallback',
-                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                'traffic_source': 'profiles/traffic.json (ncu dram__bytes_read+write per sampled edge '
+                                  'x sampled edges per launch)' if traffic else None,
                 'algorithmic_bytes_per_launch': algo_bytes,
                 'bytes_per_sampled_edge': bytes_per_slot, 'launch_ms': launch_s * 1e3}
 
