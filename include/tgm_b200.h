@@ -112,6 +112,8 @@ int tgm_recency_update(tgm_recency *, const int32_t *src, const int32_t *dst, co
 int tgm_recency_state(const tgm_recency *, int32_t **ids, int64_t **times, float **feats,
                       int32_t **write_pos);
 
+int tgm_recency_dims(const tgm_recency *, int32_t *num_nodes, int32_t *B, int32_t *D);
+
 /* ------------------------------------------------------------------------------------------
  * Stateless recency sampler over a per-node chronological adjacency ("CSR").  Same answers as
  * the ring sampler driven batch by batch (recency.py:119-171), but one launch serves the seeds
@@ -144,6 +146,13 @@ int tgm_csr_sample(const tgm_csr *, const int32_t *seeds, const int64_t *tq, con
  * first, then dst seeds (recency.py:181-233 with the keys above). */
 int tgm_csr_sample_edges(const tgm_csr *, int64_t e_lo, int64_t e_hi, int32_t B, int32_t k,
                          int32_t *out_nid, int64_t *out_t, float *out_x, tgm_stream stream);
+
+/* Materialise, into a stateful sampler, the ring state RecencyNeighborHook would hold after the
+ * stream edges [e_start, e_cut) were pushed batch by batch (equivalent for every later query; the
+ * physical slot rotation follows one-by-one pushes).  Lets a windowed (pre-sampled) run hand over
+ * to tgm_recency_query/_update, e.g. train stream -> validation stream with shared hook state
+ * (examples/linkproppred/tgat.py:168).  e_cut must sit on a batch boundary of the adjacency. */
+int tgm_csr_export_ring(const tgm_csr *, int64_t e_cut, tgm_recency *ring, tgm_stream stream);
 
 /* Uniform full-history sampling == DGStorageArrayBackend.get_nbrs
  * (tgm/core/_storage/backends/array_backend.py:108-171, called by NeighborSamplerHook,

@@ -400,3 +400,91 @@ def test_hook_validates_seeds_like_the_reference():
     batch.bar = torch.tensor([-1], dtype=torch.int64, device=DEV)
     with pytest.raises(ValueError, match='must be >= 0'):
         hook(dg, batch)
+
+
+# ---- windowed (pre-sampled) mode of the drop-in hook ------------------------------------------
+@pytest.mark.parametrize('window', [1, 3, 1000])
+@pytest.mark.parametrize('path', golden_files(), ids=golden_ids())
+def test_windowed_hook_matches_reference_fixture(path, window):
+    """RecencyNeighborHook(window_batches=W): batches are served as views of a pre-sampled
+    window; what lands on every batch is what the reference put there."""
+    g = Golden(path)
+    ei = torch.from_numpy(np.stack([g.src, g.dst], 1).astype(np.int32))
+    dg = DGraph(DGData.from_raw(torch.from_numpy(g.t), ei,
+                                None if g.x is None else torch.from_numpy(g.x)), device=DEV)
+    keys_n, keys_t = ['edge_src', 'edge_dst'], ['edge_time', 'edge_time']
+    hm = HookManager(keys=['g'])
+    if g.neg is not None:
+        hm.register('g', _InjectNegatives(dev(g.neg, torch.int32)))
+        keys_n, keys_t = keys_n + ['neg'], keys_t + ['neg_time']
+    hook = RecencyNeighborHook(num_nodes=g.N, num_nbrs=g.num_nbrs, seed_nodes_keys=keys_n,
+                               seed_times_keys=keys_t, directed=g.directed, window_batches=window)
+    hm.register('g', hook)
+    with hm.activate('g'):
+        for ep in range(g.epochs):
+            for b, batch in enumerate(DGDataLoader(dg, batch_size=g.bs, hook_manager=hm)):
+                assert isinstance(hook._win, dict), 'left the windowed mode unexpectedly'
+                for h in range(len(g.num_nbrs)):
+                    got = (batch.seed_nids[h], batch.seed_times[h], batch.nbr_nids[h],
+                           batch.nbr_edge_time[h], batch.nbr_edge_x[h])
+                    assert_hop_equal(to_np(got), g.expect(ep, b, h), f'ep{ep} batch{b} hop{h}')
+                mask = batch.seed_node_nbr_mask
+                n = batch.edge_src.numel()
+                assert mask['edge_src'].tolist() == list(range(n))
+                assert mask['edge_dst'].tolist() == list(range(n, 2 * n))
+            if ep + 1 < g.epochs:
+                hm.reset_state()
+
+
+def test_windowed_hook_hands_over_to_the_ring():
+    """Shared hook state across streams (examples/linkproppred/tgat.py:168): a windowed train
+    stream, then a second store (validation) and, after a reset, a skipped batch -- both leave the
+    window and must continue exactly where the batch-by-batch reference state machine would be."""
+    N, D, bs, nn = 300, 4, 50, [6, 3]
+    s1, d1, t1, x1 = _random_stream(21, N, 2000, 500, D, hot=0.1)
+    s2, d2, t2, x2 = _random_stream(22, N, 600, 300, D)
+    t2 = t2 + 500  # the validation stream continues in time
+    mk = lambda s, d, t, x: DGraph(DGData.from_raw(
+        torch.from_numpy(t), torch.from_numpy(np.stack([s, d], 1)), torch.from_numpy(x)), device=DEV)
+    dg1, dg2 = mk(s1, d1, t1, x1), mk(s2, d2, t2, x2)
+    hook = RecencyNeighborHook(num_nodes=N, num_nbrs=nn, seed_nodes_keys=['edge_src', 'edge_dst'],
+                               seed_times_keys=['edge_time', 'edge_time'], window_batches=7)
+    hm = HookManager(keys=['g'])
+    hm.register('g', hook)
+    oracle = CRing(N, nn, D)
+
+    def check(batch, s, d, t, x, lo, hi, tag):
+        seeds = np.concatenate([s[lo:hi], d[lo:hi]])
+        tq = np.concatenate([t[lo:hi], t[lo:hi]])
+        want = oracle.hook_call(seeds, tq, s[lo:hi], d[lo:hi], t[lo:hi], x[lo:hi])
+        for h, w in enumerate(want):
+            got = (batch.seed_nids[h], batch.seed_times[h], batch.nbr_nids[h],
+                   batch.nbr_edge_time[h], batch.nbr_edge_x[h])
+            assert_hop_equal(to_np(got), w, f'{tag} edge{lo} hop{h}')
+
+    with hm.activate('g'):
+        for b, batch in enumerate(DGDataLoader(dg1, batch_size=bs, hook_manager=hm)):
+            check(batch, s1, d1, t1, x1, b * bs, (b + 1) * bs, 'train')
+        assert isinstance(hook._win, dict)
+        for b, batch in enumerate(DGDataLoader(dg2, batch_size=bs, hook_manager=hm)):
+            check(batch, s2, d2, t2, x2, b * bs, (b + 1) * bs, 'val')
+        assert hook._win is False  # handed over to the ring kernels
+        st = hook.state_tensors()
+        # same ring contents in chronological order (the slot rotation may differ)
+        B = max(nn)
+        for ids, times, wp, name in ((st['ids'].cpu().numpy(), st['times'].cpu().numpy(),
+                                      st['write_pos'].cpu().numpy(), 'gpu'),):
+            rot = (wp[:, None] + np.arange(B)[None, :]) % B
+            o_rot = (oracle.write_pos[:, None].astype(np.int64) + np.arange(B)[None, :]) % B
+            assert np.array_equal(np.take_along_axis(ids, rot, 1),
+                                  np.take_along_axis(oracle.ids, o_rot, 1))
+            assert np.array_equal(np.take_along_axis(times, rot, 1),
+                                  np.take_along_axis(oracle.times, o_rot, 1))
+        # new epoch: windowed again, then a skipped batch forces the hand-over mid-stream
+        hm.reset_state()
+        oracle.reset_state()
+        loader = DGDataLoader(dg1, batch_size=bs, hook_manager=hm)
+        for b in list(range(0, 9)) + list(range(10, 16)):  # batch 9 never happens
+            batch = loader([b * bs])
+            check(batch, s1, d1, t1, x1, b * bs, (b + 1) * bs, 'skip')
+            assert (hook._win is False) == (b >= 10)

@@ -67,6 +67,8 @@ SIGNATURES = {
                                c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     'tgm_csr_sample_edges': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
+    'tgm_recency_dims': (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
+    'tgm_csr_export_ring': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     'tgm_csr_sample_uniform': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32,
                                        c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
     'tgm_csr_sample_edges_host': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p,

@@ -465,6 +465,45 @@ csr_sample_fast_kernel(const Entry *__restrict__ entries, const int64_t *__restr
   }
 }
 
+// ---- ring export: the stateful sampler's state after the edges [e_start, e_cut) were pushed ------
+// One warp per node: the last min(count, B) visible entries land in the slots sequential pushes
+// would have used (write_pos = number of pushes), so a stateful RecencyNeighborHook can take over
+// from a windowed run (train epoch pre-sampled, validation stream driven batch by batch).
+__global__ void __launch_bounds__(256)
+csr_export_ring_kernel(const Entry *__restrict__ entries, const int64_t *__restrict__ rowptr,
+                       const float *__restrict__ x, int32_t N, int D, int64_t e_cut, int B,
+                       int32_t *__restrict__ ids, int64_t *__restrict__ times,
+                       float *__restrict__ feats, int32_t *__restrict__ wpos) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int64_t v = int64_t(blockIdx.x) * wpb + (threadIdx.x >> 5); v < N;
+       v += int64_t(gridDim.x) * wpb) {
+    const int64_t lo = rowptr[v], hi = rowptr[v + 1];
+    const int64_t pos = lower_bound_eid(entries, lo, hi, e_cut);
+    const int64_t cnt = pos - lo;
+    const int nkeep = cnt < B ? int(cnt) : B;
+    for (int j = lane; j < B; j += 32) {  // unrolled position j (oldest .. newest) of the ring
+      const int64_t slot = (cnt + j) % B;  // == (write_pos - B + j) mod B with write_pos = cnt
+      const int64_t src = pos - B + j;     // entry feeding it
+      const bool has = j >= B - nkeep;
+      Entry en;
+      if (has) en = entries[src];
+      ids[v * B + slot] = has ? en.nbr : TGM_PADDED_NODE_ID;
+      times[v * B + slot] = has ? en.t : 0;
+    }
+    if (D > 0) {
+      for (int i = lane; i < B * D; i += 32) {
+        const int j = i / D, d = i - j * D;
+        const int64_t slot = (cnt + j) % B;
+        const bool has = j >= B - nkeep;
+        float val = 0.f;
+        if (has) val = __ldg(x + int64_t(entries[pos - B + j].eid) * D + d);
+        feats[(v * B + slot) * D + d] = val;
+      }
+    }
+    if (lane == 0) wpos[v] = int32_t(cnt);
+  }
+}
+
 // ---- uniform full-history sampler (array_backend.py:108-171 via uniform.py:87-142) -------------
 // Needs the adjacency built with batch_size 1: per node the entries are then ordered (edge, side),
 // which is the order the reference appends candidates in (:132-137).  Candidates of a seed are its
@@ -1049,4 +1088,31 @@ extern "C" int tgm_set_option(const char *name, int value) {
     return TGM_OK;
   }
   return fail(TGM_ERR_INVALID, std::string("tgm_set_option: unknown option ") + name);
+}
+
+
+extern "C" int tgm_csr_export_ring(const tgm_csr *c, int64_t e_cut, tgm_recency *ring,
+                                   tgm_stream stream) {
+  TGM_REQUIRE(c != nullptr && ring != nullptr, "tgm_csr_export_ring: NULL handle");
+  TGM_REQUIRE(e_cut >= c->e_start && e_cut <= c->e_start + c->Ew,
+              "tgm_csr_export_ring: e_cut outside the indexed stream");
+  int32_t *ids = nullptr, *wpos = nullptr;
+  int64_t *times = nullptr;
+  float *feats = nullptr;
+  int32_t N = 0, B = 0, D = 0;
+  int rc = tgm_recency_dims(ring, &N, &B, &D);
+  if (rc != TGM_OK) return rc;
+  rc = tgm_recency_state(ring, &ids, &times, &feats, &wpos);
+  if (rc != TGM_OK) return rc;
+  TGM_REQUIRE(D == c->D, "tgm_csr_export_ring: feature width of ring and store differ");
+  TGM_REQUIRE(N >= c->N, "tgm_csr_export_ring: ring has fewer nodes than the store");
+  DeviceGuard g(c->device);
+  cudaStream_t st = as_stream(stream);
+  rc = tgm_recency_reset(ring, stream);  // nodes beyond the store's id range stay empty
+  if (rc != TGM_OK) return rc;
+  if (c->n == 0) return TGM_OK;
+  csr_export_ring_kernel<<<grid_for(c->N, 8, 8), 256, 0, st>>>(
+      c->entries, c->rowptr, c->store->x, c->N, c->D, e_cut, B, ids, times, feats, wpos);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
 }

@@ -353,3 +353,12 @@ extern "C" int tgm_recency_state(const tgm_recency *h, int32_t **ids, int64_t **
   if (write_pos) *write_pos = h->wpos;
   return TGM_OK;
 }
+
+
+extern "C" int tgm_recency_dims(const tgm_recency *h, int32_t *num_nodes, int32_t *B, int32_t *D) {
+  TGM_REQUIRE(h != nullptr, "tgm_recency_dims: handle is NULL");
+  if (num_nodes) *num_nodes = h->N;
+  if (B) *B = h->B;
+  if (D) *D = h->D;
+  return TGM_OK;
+}

@@ -54,7 +54,12 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
 
     def __init__(self, num_nodes: int, num_nbrs: List[int], seed_nodes_keys: List[str],
                  seed_times_keys: List[str], directed: bool = False,
-                 id: Optional[str] = None) -> None:
+                 id: Optional[str] = None, window_batches: int = 0) -> None:
+        """`window_batches` > 0 turns on pre-sampling (an addition to the reference signature):
+        while the loader walks one store front to back in equal event batches, the neighbourhoods
+        of `window_batches` upcoming batches are sampled by ONE launch per hop over the stateless
+        adjacency (tgm_csr_*) and each call only slices views.  Outputs are identical; any other
+        call pattern (another store, a skipped batch) hands the state over to the ring kernels."""
         if not len(num_nbrs):
             raise ValueError('num_nbrs must be non-empty')
         if not all(isinstance(x, int) and x > 0 for x in num_nbrs):
@@ -71,6 +76,10 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         self._seed_nodes_keys = seed_nodes_keys
         self._seed_times_keys = seed_times_keys
         self._warned_seed_None = False
+        if not isinstance(window_batches, int) or window_batches < 0:
+            raise ValueError('window_batches must be a non-negative integer')
+        self._window_batches = window_batches
+        self._win = None  # windowed-mode cursor, see _windowed_call
         self._handle = ctypes.c_void_p()   # tgm_recency*, created on first call
         self._device: Optional[torch.device] = None
         self._edge_x_dim: Optional[int] = None
@@ -87,6 +96,7 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         return self._num_nbrs
 
     def reset_state(self) -> None:
+        self._win = None  # the next call may start a fresh windowed run
         if self._handle.value:
             _cabi.check(_cabi.lib.tgm_recency_reset(self._handle, _cabi.current_stream(self._device)))
 
@@ -125,8 +135,126 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         return out
 
     # -- the hook ---------------------------------------------------------------------------
+    # -- windowed (pre-sampled) mode ----------------------------------------------------------
+    def _batch_range(self, dg, batch):
+        """[lo, hi) of the batch in the store's edge index space, or None if it is not a plain
+        contiguous slab of a device store."""
+        store = getattr(dg, '_storage', None)
+        if store is None or not hasattr(store, 'edge_range') or getattr(store, 'device', None) is None:
+            return None
+        src = batch.edge_src
+        if not (isinstance(src, Tensor) and _is_store_view(store, src)):
+            return None
+        lo = (src.data_ptr() - store._src.data_ptr()) // 4
+        return store, lo, lo + src.numel()
+
+    def _windowed_call(self, dg, batch):
+        """Returns the decorated batch, or None when this call cannot be served from a window (the
+        caller then continues on the ring kernels, after `_leave_window` moved the state over)."""
+        keys = list(zip(self._seed_nodes_keys, self._seed_times_keys))
+        if keys[:2] != [('edge_src', 'edge_time'), ('edge_dst', 'edge_time')]:
+            return None
+        rng = self._batch_range(dg, batch)
+        if rng is None or rng[2] == rng[1]:
+            return None
+        store, lo, hi = rng
+        w = self._win
+        if w is None:
+            if self._win is False:  # already handed over to the ring since the last reset
+                return None
+            from tgm_b200.sampler import RecencyCSR
+            bs = hi - lo
+            cache = store._node_cache
+            key = ('recency_csr', lo, bs, self._directed)
+            if key not in cache:
+                cache[key] = RecencyCSR(store, bs, directed=self._directed, colocate_x=True,
+                                        e_start=lo)
+            w = self._win = {'store': store, 'csr': cache[key], 'bs': bs, 'next': lo,
+                             'w_lo': lo, 'w_hi': lo, 'hops': None, 'start': lo}
+        elif w['store'] is not store or lo != w['next'] or \
+                (hi - lo != w['bs'] and hi != store.num_edges):
+            return None
+        csr, bs = w['csr'], w['bs']
+        if hi > w['w_hi']:  # pre-sample the next window, one launch per hop
+            w['w_lo'], w['w_hi'] = lo, min(lo + self._window_batches * bs, store.num_edges)
+            w['hops'] = csr.sample_window(w['w_lo'], w['w_hi'], self._num_nbrs)
+        # rows of this batch inside the window block, hop by hop
+        a, b = 2 * (lo - w['w_lo']), 2 * (hi - w['w_lo'])
+        parts = []
+        for hop in w['hops']:
+            k = hop.nbr_nids.shape[1]
+            parts.append((hop.seed_nids[a:b], hop.seed_times[a:b], hop.nbr_nids[a:b],
+                          hop.nbr_edge_time[a:b], hop.nbr_edge_x[a:b]))
+            a, b = a * k, b * k
+        n = hi - lo
+        dev = self._device
+        mask = {'edge_src': torch.arange(0, n, device=dev),
+                'edge_dst': torch.arange(n, 2 * n, device=dev)}
+        extra = keys[2:]
+        if extra:  # seeds the window cannot know in advance (negatives): one launch per hop
+            xs, xt, offset = [], [], 2 * n
+            to_check = []
+            for node_attr, time_attr in extra:
+                for name in (node_attr, time_attr):
+                    if not hasattr(batch, name):
+                        raise ValueError(f'Missing seed attributes {[name]} on batch')
+                sn, stt = getattr(batch, node_attr), getattr(batch, time_attr)
+                if sn is None or stt is None:
+                    if not self._warned_seed_None:
+                        warnings.warn(
+                            f'Seed attribute {node_attr if sn is None else time_attr} is None on '
+                            'this batch, skipping this batch. Future occurrences will also be '
+                            'skipped but the warning will be suppressed', UserWarning)
+                        self._warned_seed_None = True
+                    continue
+                for name, tensor in ((node_attr, sn), (time_attr, stt)):
+                    if not isinstance(tensor, Tensor):
+                        raise ValueError(f'{name} must be a Tensor, got {type(tensor)}')
+                    if tensor.ndim != 1:
+                        raise ValueError(f'{name} must be 1-D, got shape {tensor.shape}')
+                to_check += [(node_attr, sn, True), (time_attr, stt, False)]
+                xs.append(sn.to(device=dev, dtype=torch.int32))
+                xt.append(stt.to(device=dev, dtype=torch.int64))
+                mask[node_attr] = torch.arange(offset, offset + sn.shape[0], device=dev)
+                offset += sn.shape[0]
+            self._validate(to_check)
+            if xs:
+                seeds, times = torch.cat(xs).contiguous(), torch.cat(xt).contiguous()
+                cut = torch.full((1,), lo, dtype=torch.int64, device=dev)
+                group = seeds.numel()
+                merged = []
+                for h, k in enumerate(self._num_nbrs):
+                    nid, nt, nx = csr.sample(seeds, times, cut, k, self._max_nbrs, cut_group=group)
+                    p = parts[h]
+                    merged.append((torch.cat([p[0], seeds]), torch.cat([p[1], times]),
+                                   torch.cat([p[2], nid]), torch.cat([p[3], nt]),
+                                   torch.cat([p[4], nx])))
+                    seeds, times = nid.reshape(-1), nt.reshape(-1)
+                    group *= k
+                parts = merged
+        w['next'] = hi
+        for i, name in enumerate(('seed_nids', 'seed_times', 'nbr_nids', 'nbr_edge_time',
+                                  'nbr_edge_x')):
+            self.add_batch_attribute(batch, name, [p[i] for p in parts])
+        self.add_batch_attribute(batch, 'seed_node_nbr_mask', mask)
+        return batch
+
+    def _leave_window(self) -> None:
+        """Hand the state of a windowed run over to the ring: after this the ring holds what the
+        batch-by-batch hook would hold once every edge before `next` was pushed."""
+        w = self._win
+        if isinstance(w, dict):
+            _cabi.check(_cabi.lib.tgm_csr_export_ring(w['csr'].handle, w['next'], self._handle,
+                                                      _cabi.current_stream(self._device)))
+        self._win = False
+
     def __call__(self, dg, batch):
         self._ensure_state(dg)
+        if self._window_batches and self._win is not False:
+            out = self._windowed_call(dg, batch)
+            if out is not None:
+                return out
+            self._leave_window()
         seed_nodes, seed_times, seed_mask = self._get_seed_tensors(dg, batch)
         seeds_out: List[Tensor] = []
         times_out: List[Tensor] = []
