@@ -188,8 +188,7 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
             a, b = a * k, b * k
         n = hi - lo
         dev = self._device
-        mask = {'edge_src': torch.arange(0, n, device=dev),
-                'edge_dst': torch.arange(n, 2 * n, device=dev)}
+        mask = {'edge_src': self._arange(0, n), 'edge_dst': self._arange(n, 2 * n)}
         extra = keys[2:]
         if extra:  # seeds the window cannot know in advance (negatives): one launch per hop
             xs, xt, offset = [], [], 2 * n
@@ -215,7 +214,7 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
                 to_check += [(node_attr, sn, True), (time_attr, stt, False)]
                 xs.append(sn.to(device=dev, dtype=torch.int32))
                 xt.append(stt.to(device=dev, dtype=torch.int64))
-                mask[node_attr] = torch.arange(offset, offset + sn.shape[0], device=dev)
+                mask[node_attr] = self._arange(offset, offset + sn.shape[0])
                 offset += sn.shape[0]
             self._validate(to_check)
             if xs:
@@ -238,6 +237,15 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
             self.add_batch_attribute(batch, name, [p[i] for p in parts])
         self.add_batch_attribute(batch, 'seed_node_nbr_mask', mask)
         return batch
+
+    def _arange(self, a: int, b: int) -> Tensor:
+        """View [a, b) of a cached device arange (seed_node_nbr_mask rows, recency.py:221-224);
+        read-only by convention, like every other view the hook hands out."""
+        cache = getattr(self, '_arange_cache', None)
+        if cache is None or cache.numel() < b:
+            cache = torch.arange(0, max(b, 4096), device=self._device)
+            self._arange_cache = cache
+        return cache[a:b]
 
     def _leave_window(self) -> None:
         """Hand the state of a windowed run over to the ring: after this the ring holds what the
@@ -352,7 +360,8 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
                         to_check.append((name, tensor, True))
                     seeds.append(tensor.to(device))
                     n = tensor.shape[0]
-                    mask[name] = torch.arange(offset, offset + n, device=device)
+                    mask[name] = (self._arange(offset, offset + n) if device == self._device
+                                  else torch.arange(offset, offset + n, device=device))
                     offset += n
                 else:
                     if not (name in _TRUSTED_TIME_KEYS and _is_store_view(store, tensor)):
