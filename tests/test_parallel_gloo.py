@@ -69,3 +69,44 @@ def test_world_size_2_gloo(tmp_path):
     assert summ[:, 0].sum() == E == total_edges
     assert summ[:, 2].sum() == E * (E - 1) / 2  # every stream position owned exactly once
     assert slowest == 2.0
+
+
+def _merge_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    from tgm_b200.parallel import merge_node_memory
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        N, M = 50, 4
+        g = torch.Generator().manual_seed(0)
+        base_mem = torch.randn(N, M, generator=g)           # common snapshot
+        base_lu = torch.randint(0, 100, (N,), generator=g)
+        # rank r touches nodes with (i % 3 == r) or (i % 7 == 0); its rows get a rank signature
+        idx = torch.arange(N)
+        touched = (idx % 3 == rank) | (idx % 7 == 0)
+        mem, lu = base_mem.clone(), base_lu.clone()
+        mem[touched] = 1000.0 * (rank + 1) + idx[touched, None].float()
+        lu[touched] = 1000 * (rank + 1) + idx[touched]
+        merge_node_memory(mem, lu, touched)
+        if rank == 0:
+            torch.save({'mem': mem, 'lu': lu, 'base_mem': base_mem, 'base_lu': base_lu},
+                       os.path.join(out_dir, 'merged.pt'))
+        # every rank must hold the same merged state
+        ref = [torch.empty_like(mem) for _ in range(world)]
+        dist.all_gather(ref, mem)
+        assert all(torch.equal(r, mem) for r in ref)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_merge_node_memory_world_size_2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_merge_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    z = torch.load(tmp_path / 'merged.pt')
+    idx = torch.arange(50)
+    for i in idx.tolist():
+        owners = [r for r in range(world) if (i % 3 == r) or (i % 7 == 0)]
+        if owners:
+            r = max(owners)  # the later shard wins
+            assert z['mem'][i, 0] == 1000.0 * (r + 1) + i and z['lu'][i] == 1000 * (r + 1) + i
+        else:
+            assert torch.equal(z['mem'][i], z['base_mem'][i]) and z['lu'][i] == z['base_lu'][i]

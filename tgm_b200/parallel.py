@@ -89,3 +89,36 @@ def sum_over_ranks(value: float, device='cpu') -> float:
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def merge_node_memory(memory: torch.Tensor, last_update: torch.Tensor,
+                      touched: torch.Tensor) -> None:
+    """Reconcile TGN-style node memory at a shard join (BASELINE config 4), in place.
+
+    Every rank advanced ITS time-range shard of the event stream starting from the same memory
+    snapshot and touched a subset of the nodes (`touched` bool[N]: endpoints of its shard's
+    events).  Shards are ordered in time by rank, so for each node the row written by the highest
+    rank that touched it is the most recent one; nodes nobody touched keep the common value.
+
+    This is the one collective of the hot path: a rank-id MAX all-reduce over int32[N] elects the
+    owner of every row, then one SUM all-reduce over the owner-masked memory [N, M] (and one MAX
+    over last_update) delivers the rows -- the all-gather of the touched rows, expressed as
+    reductions so NVSwitch can combine in-network (NVLS).  Time-sharded training of a memory model
+    is an approximation of the sequential reference (tgm/nn/encoder/tgn.py processes the stream
+    strictly in order): inside a shard a node sees only its own shard's updates until the join.
+    Works on NCCL (device tensors) and gloo (CPU tests) alike.
+    """
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    rank = dist.get_rank()
+    owner = torch.where(touched, rank + 1, 0).to(torch.int32)
+    dist.all_reduce(owner, op=dist.ReduceOp.MAX)
+    mine = owner == rank + 1
+    nobody = owner == 0
+    keep = mine | (nobody if rank == 0 else torch.zeros_like(nobody))  # rank 0 speaks for untouched rows
+    contrib = torch.where(keep[:, None], memory, torch.zeros((), dtype=memory.dtype, device=memory.device))
+    dist.all_reduce(contrib, op=dist.ReduceOp.SUM)
+    lu = torch.where(keep, last_update, torch.zeros((), dtype=last_update.dtype, device=last_update.device))
+    dist.all_reduce(lu, op=dist.ReduceOp.MAX)
+    memory.copy_(contrib)
+    last_update.copy_(lu)
