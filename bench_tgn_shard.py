@@ -79,6 +79,8 @@ def main():
         torch.cuda.synchronize(dev)
 
     run_shard()  # warm-up (allocations, cuBLAS heuristics)
+    for _ in range(2):  # warm-up of the collective (communicator setup, NVLS buffers)
+        merge_node_memory(mem.memory.clone(), mem.last_update.clone(), touched)
     mem.reset_state()
     touched.zero_()
     barrier()
