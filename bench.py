@@ -52,7 +52,7 @@ def parse_args():
     p.add_argument('--window-batches', type=int, default=5000)
     p.add_argument('--e2e-window-batches', type=int, default=1000)
     p.add_argument('--e2e-steps', type=int, default=0, help='0 = same as --steps')
-    p.add_argument('--cpu-sample-edges', type=int, default=1_500_000)
+    p.add_argument('--cpu-sample-edges', type=int, default=9_000_000)
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--no-e2e', action='store_true')
     p.add_argument('--no-colocate', action='store_true')
