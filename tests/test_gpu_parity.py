@@ -488,3 +488,87 @@ def test_windowed_hook_hands_over_to_the_ring():
             batch = loader([b * bs])
             check(batch, s1, d1, t1, x1, b * bs, (b + 1) * bs, 'skip')
             assert (hook._win is False) == (b >= 10)
+
+
+# ---- edge cases the reference's own unit tests pin (test_recency_nbr_hook.py:250-326, 898-1004) --
+def _tiny_dg(with_node_events=False, feat=True):
+    ei = torch.tensor([[1, 2], [2, 3], [3, 4]], dtype=torch.int32)
+    t = torch.tensor([1, 2, 3])
+    x = torch.tensor([[1.], [2.], [3.]]) if feat else None
+    kw = {}
+    if with_node_events:
+        kw = dict(node_x=torch.rand(2, 5), node_x_time=torch.tensor([4, 5]),
+                  node_x_nids=torch.tensor([5, 6], dtype=torch.int32))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        return DGraph(DGData.from_raw(t, ei, x, **kw), device=DEV)
+
+
+def _hooked_loader(dg, window, **kw):
+    hook = RecencyNeighborHook(num_nbrs=[1], num_nodes=dg.num_nodes,
+                               seed_nodes_keys=['edge_src', 'edge_dst'],
+                               seed_times_keys=['edge_time', 'edge_time'], directed=True,
+                               window_batches=window)
+    hm = HookManager(keys=['unit'])
+    hm.register('unit', hook)
+    hm.set_active_hooks('unit')
+    return DGDataLoader(dg, batch_size=3, hook_manager=hm, **kw)
+
+
+@pytest.mark.parametrize('window', [0, 4])
+def test_no_edge_features_give_zero_width_feature_tensors(window):
+    batch = next(iter(_hooked_loader(_tiny_dg(feat=False), window)))
+    assert batch.seed_nids[0].shape == (6,) and batch.nbr_nids[0].shape == (6, 1)
+    assert batch.nbr_edge_time[0].shape == (6, 1)
+    assert batch.nbr_edge_x[0].shape == (6, 1, 0) and batch.nbr_edge_x[0].dtype == torch.float32
+
+
+@pytest.mark.parametrize('window', [0, 4])
+def test_node_only_batch_yields_empty_hops_with_exact_dtypes(window):
+    """A batch with node events but no edges: empty CPU tensors int32 / int64 / float32 (0, D),
+    and the sampler state is left alone (recency.py:127-137, :161-163)."""
+    it = iter(_hooked_loader(_tiny_dg(with_node_events=True), window))
+    b1 = next(it)
+    assert b1.nbr_nids[0].shape == (6, 1) and b1.nbr_edge_x[0].shape == (6, 1, 1)
+    b2 = next(it)
+    assert b2.edge_src.numel() == 0 and b2.node_x_nids.tolist() == [5, 6]
+    assert b2.seed_nids[0].dtype == torch.int32 and b2.seed_nids[0].shape == (0,)
+    assert b2.nbr_nids[0].dtype == torch.int32 and b2.nbr_nids[0].shape == (0,)
+    assert b2.nbr_edge_time[0].dtype == torch.int64 and b2.nbr_edge_time[0].shape == (0,)
+    assert b2.nbr_edge_x[0].dtype == torch.float32 and b2.nbr_edge_x[0].shape == (0, 1)
+
+
+def test_seed_attribute_errors_and_none_warning():
+    dg = _tiny_dg()
+    mk = lambda: RecencyNeighborHook(num_nbrs=[1], num_nodes=5, seed_nodes_keys=['foo'],
+                                     seed_times_keys=['bar'])
+    with pytest.raises(ValueError, match='Missing seed attributes'):
+        mk()(dg, dg.materialize())
+    batch = dg.materialize()
+    batch.foo, batch.bar = None, None
+    with pytest.warns(UserWarning, match='is None on this batch'):
+        out = mk()(dg, batch)
+    assert out.nbr_nids[0].numel() == 0  # the key contributed no seeds
+    for bad in ('should_be_1d_tensor', torch.rand(2, 3, device=DEV)):
+        batch = dg.materialize()
+        batch.foo = batch.bar = bad
+        with pytest.raises(ValueError):
+            mk()(dg, batch)
+    for ids in ([-1], [5]):  # negative / >= num_nodes
+        batch = dg.materialize()
+        batch.foo = torch.tensor(ids, dtype=torch.int32, device=DEV)
+        batch.bar = torch.tensor([1], dtype=torch.int64, device=DEV)
+        with pytest.raises(ValueError, match='must satisfy'):
+            mk()(dg, batch)
+
+
+def test_constructor_errors_match_the_reference():
+    """recency.py:56-90."""
+    for bad in ([], [0], [-1], [1.5]):
+        with pytest.raises(ValueError):
+            RecencyNeighborHook(num_nodes=3, num_nbrs=bad, seed_nodes_keys=['edge_src'],
+                                seed_times_keys=['edge_time'])
+    with pytest.raises(ValueError, match='seed_nodes_keys'):
+        RecencyNeighborHook(num_nodes=3, num_nbrs=[1], seed_nodes_keys=['edge_src', 'edge_dst'],
+                            seed_times_keys=['edge_time'])
