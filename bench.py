@@ -316,7 +316,7 @@ def run_b200(a):
             traffic = tr['dram_bytes_per_sampled_edge'] * slots_per_launch
     except Exception:  # noqa: BLE001
         pass
-    roofline = {'bound': 'hbm', 'kernel': 'csr_sample_edges_tma_kernel' if a.feature_copy == 'tma' else
+    roofline = {'bound': 'hbm', 'kernel': 'csr_sample_tma_kernel<true>' if a.feature_copy == 'tma' else
                 'csr_sample_edges_fast_kernel', 'achieved': achieved,
                 'peak': peak, 'peak_source': 'measured' if 'hbm_gbs' in peaks else 'fallback',
                 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,

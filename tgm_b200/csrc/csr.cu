@@ -642,13 +642,28 @@ struct TmaMeta {  // what the retiring step needs to know about an in-flight see
   uint32_t padbytes; // zero bytes in front of them; bit 31 carries the mbarrier phase parity
 };
 
+// EDGE_SEEDS: hop-0 seeds are the endpoints of stream edges [l_lo, l_hi) (anchor table, no seed
+// arrays); otherwise arbitrary seeds (seeds/tq/cut arrays, private binary search per lane).
+struct TmaSeedArgs {
+  // EDGE_SEEDS
+  const uint2 *anchors;
+  const int64_t *t;
+  int64_t Ew, l_lo, l_hi;
+  uint32_t bs;
+  // general seeds
+  const int64_t *rowptr;
+  const int32_t *seeds;
+  const int64_t *tq, *cut;
+  int64_t cut_group, S;
+  int32_t N;
+};
+
+template <bool EDGE_SEEDS>
 __global__ void __launch_bounds__(kFastThreads)
-csr_sample_edges_tma_kernel(const Entry *__restrict__ entries, const uint2 *__restrict__ anchors,
-                            const float *__restrict__ xrows, const int64_t *__restrict__ t, int D,
-                            int64_t Ew, uint32_t bs, int64_t l_lo, int64_t l_hi, int B, int k,
-                            int32_t *__restrict__ out_nid, int64_t *__restrict__ out_t,
-                            float *__restrict__ out_x, int stage_bytes,
-                            unsigned long long *__restrict__ ticket) {
+csr_sample_tma_kernel(const Entry *__restrict__ entries, const float *__restrict__ xrows,
+                      const TmaSeedArgs a, int D, int B, int k, int32_t *__restrict__ out_nid,
+                      int64_t *__restrict__ out_t, float *__restrict__ out_x, int stage_bytes,
+                      unsigned long long *__restrict__ ticket) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int W = kFastThreads >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -683,7 +698,7 @@ csr_sample_edges_tma_kernel(const Entry *__restrict__ entries, const uint2 *__re
     bulk_commit();
   };
 
-  const int64_t S = 2 * (l_hi - l_lo);
+  const int64_t S = EDGE_SEEDS ? 2 * (a.l_hi - a.l_lo) : a.S;
   const int64_t nchunks = (S + 31) >> 5;
   const int64_t wstride = int64_t(gridDim.x) * W;
   uint32_t g = 0;       // seeds this warp has started
@@ -695,16 +710,29 @@ csr_sample_edges_tma_kernel(const Entry *__restrict__ entries, const uint2 *__re
     const int64_t s_base = ch << 5, s = s_base + lane;
     SeedWin mine{0, 0, 0};
     if (s < S) {
-      const int64_t jb = s / (2 * int64_t(bs));
-      const int64_t bstart = l_lo + jb * bs;
-      const int64_t nb = l_hi - bstart < int64_t(bs) ? l_hi - bstart : int64_t(bs);
-      const int64_t rr = s - jb * 2 * int64_t(bs);
-      const bool side = rr >= nb;
-      const int64_t l = bstart + (side ? rr - nb : rr);
-      const uint2 a = __ldg(anchors + (side ? Ew + l : l));
-      mine.nwin = a.y < uint32_t(B) ? int(a.y) : B;
-      mine.wstart = int64_t(a.x) - mine.nwin;
-      mine.q = __ldg(t + l);
+      if (EDGE_SEEDS) {
+        // row s -> (edge, endpoint): batch jb owns rows [2*bs*jb, ...), src seeds then dst seeds
+        const int64_t bs = a.bs;
+        const int64_t jb = s / (2 * bs);
+        const int64_t bstart = a.l_lo + jb * bs;
+        const int64_t nb = a.l_hi - bstart < bs ? a.l_hi - bstart : bs;
+        const int64_t rr = s - jb * 2 * bs;
+        const bool side = rr >= nb;
+        const int64_t l = bstart + (side ? rr - nb : rr);
+        const uint2 an = __ldg(a.anchors + (side ? a.Ew + l : l));
+        mine.nwin = an.y < uint32_t(B) ? int(an.y) : B;
+        mine.wstart = int64_t(an.x) - mine.nwin;
+        mine.q = __ldg(a.t + l);
+      } else {
+        const int32_t v = __ldg(a.seeds + s);
+        mine.q = __ldg(a.tq + s);
+        if (v >= 0 && v < a.N) {  // a padded seed (-1) always yields an all-padding row
+          const int64_t lo = __ldg(a.rowptr + v), hi = __ldg(a.rowptr + v + 1);
+          const int64_t pos = lower_bound_eid(entries, lo, hi, __ldg(a.cut + s / a.cut_group));
+          mine.wstart = pos - B > lo ? pos - B : lo;
+          mine.nwin = int(pos - mine.wstart);
+        }
+      }
     }
     const int nseeds = S - s_base < 32 ? int(S - s_base) : 32;
     int64_t wstart = shfl_i64(mine.wstart, 0);
@@ -919,6 +947,31 @@ int sample_cfg(const tgm_csr *c, const char *who, int64_t S, int32_t B, int32_t 
 }
 }  // namespace
 
+namespace {
+bool tma_applies(const tgm_csr *c, int k) {
+  return c->D > 0 && g_csr_feature_copy == 1 && k * c->D * 4 <= kTmaMaxStageBytes;
+}
+template <bool EDGE_SEEDS>
+int launch_tma(const tgm_csr *c, const TmaSeedArgs &a, int64_t S, int B, int k, const float *xrows,
+               int32_t *out_nid, int64_t *out_t, float *out_x, cudaStream_t st) {
+  const int stage_bytes = k * c->D * 4;
+  const size_t smem = size_t(stage_bytes) +
+                      size_t(kFastThreads / 32) * kTmaStages * (size_t(stage_bytes) + 8 + 16);
+  if (smem > 48 * 1024)
+    TGM_CUDA(cudaFuncSetAttribute(csr_sample_tma_kernel<EDGE_SEEDS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int per_sm = int(std::max<size_t>(1, std::min<size_t>(TGM_FAST_MIN_BLOCKS, (220 * 1024) / (smem + 1024))));
+  if (g_csr_tma_ctas_per_sm > 0 && g_csr_tma_ctas_per_sm < per_sm) per_sm = g_csr_tma_ctas_per_sm;
+  const int grid = grid_for((S + 31) / 32, kFastThreads / 32, per_sm);
+  unsigned long long *ticket = c->ticket + (c->launches++ % tgm_csr::kTickets);
+  TGM_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
+  csr_sample_tma_kernel<EDGE_SEEDS><<<grid, kFastThreads, smem, st>>>(
+      c->entries, xrows, a, c->D, B, k, out_nid, out_t, out_x, stage_bytes, ticket);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+}  // namespace
+
 #define DISPATCH_SAMPLE(KERNEL, ...)                                                           \
   do {                                                                                         \
     if (cfg.vec4 && cfg.coloc)                                                                 \
@@ -945,7 +998,13 @@ extern "C" int tgm_csr_sample(const tgm_csr *c, const int32_t *seeds, const int6
   if (rc != TGM_OK) return rc;
   DeviceGuard g(c->device);
   cudaStream_t st = as_stream(stream);
-  if (cfg.fast)
+  if (cfg.fast && tma_applies(c, k)) {
+    TmaSeedArgs a{};
+    a.rowptr = c->rowptr, a.seeds = seeds, a.tq = tq, a.cut = cut, a.cut_group = cut_group, a.S = S;
+    a.N = c->N;
+    rc = launch_tma<false>(c, a, S, B, k, cfg.xsrc, out_nid, out_t, out_x, st);
+    if (rc != TGM_OK) return rc;
+  } else if (cfg.fast)
     csr_sample_fast_kernel<<<cfg.fast_grid, kFastThreads, 0, st>>>(
         c->entries, c->rowptr, reinterpret_cast<const float4 *>(cfg.xsrc), c->N, c->D / 4, seeds,
         tq, cut, cut_group, S, B, k, out_nid, out_t, reinterpret_cast<float4 *>(out_x));
@@ -972,22 +1031,12 @@ extern "C" int tgm_csr_sample_edges(const tgm_csr *c, int64_t e_lo, int64_t e_hi
   if (rc != TGM_OK) return rc;
   DeviceGuard g(c->device);
   cudaStream_t st = as_stream(stream);
-  const int stage_bytes = k * c->D * 4;
-  if (cfg.fast && c->bs < (int64_t(1) << 31) && c->D > 0 && g_csr_feature_copy == 1 &&
-      stage_bytes <= kTmaMaxStageBytes) {
-    const size_t smem = size_t(stage_bytes) +
-                        size_t(kFastThreads / 32) * kTmaStages * (size_t(stage_bytes) + 8 + 16);
-    if (smem > 48 * 1024)
-      TGM_CUDA(cudaFuncSetAttribute(csr_sample_edges_tma_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    int per_sm = int(std::max<size_t>(1, std::min<size_t>(TGM_FAST_MIN_BLOCKS, (220 * 1024) / (smem + 1024))));
-    if (g_csr_tma_ctas_per_sm > 0 && g_csr_tma_ctas_per_sm < per_sm) per_sm = g_csr_tma_ctas_per_sm;
-    const int grid = grid_for((S + 31) / 32, kFastThreads / 32, per_sm);
-    unsigned long long *ticket = c->ticket + (c->launches++ % tgm_csr::kTickets);
-    TGM_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
-    csr_sample_edges_tma_kernel<<<grid, kFastThreads, smem, st>>>(
-        c->entries, c->anchors, cfg.xsrc, c->store->t + c->e_start, c->D, c->Ew, uint32_t(c->bs),
-        l_lo, l_hi, B, k, out_nid, out_t, out_x, stage_bytes, ticket);
+  if (cfg.fast && c->bs < (int64_t(1) << 31) && tma_applies(c, k)) {
+    TmaSeedArgs a{};
+    a.anchors = c->anchors, a.t = c->store->t + c->e_start, a.Ew = c->Ew, a.l_lo = l_lo, a.l_hi = l_hi;
+    a.bs = uint32_t(c->bs);
+    rc = launch_tma<true>(c, a, S, B, k, cfg.xsrc, out_nid, out_t, out_x, st);
+    if (rc != TGM_OK) return rc;
   } else if (cfg.fast && c->bs < (int64_t(1) << 31))
     csr_sample_edges_fast_kernel<<<cfg.fast_grid, kFastThreads, 0, st>>>(
         c->entries, c->anchors, reinterpret_cast<const float4 *>(cfg.xsrc),
