@@ -55,6 +55,8 @@ def parse_args():
     p.add_argument('--cpu-sample-edges', type=int, default=9_000_000)
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--no-e2e', action='store_true')
+    p.add_argument('--loader-batches', type=int, default=20000,
+                   help='loader batches iterated for the public-API (DGDataLoader + hook) number; 0 = skip')
     p.add_argument('--no-colocate', action='store_true')
     p.add_argument('--feature-copy', default='tma', choices=['tma', 'lsu'],
                    help='how the sampler moves feature rows: TMA bulk copies or warp loads/stores')
@@ -384,6 +386,38 @@ def run_b200(a):
                       '2 streams)'}
         del host_out, host_in
 
+    # ---- the call a TGM user makes: for batch in DGDataLoader(dg, 200, hook_manager=hm) ---------
+    loader_api = None
+    if a.loader_batches and not a.no_e2e:
+        from tgm_b200 import DGDataLoader, DGraph, HookManager, RecencyNeighborHook
+        from tgm_b200.core.storage import DGSliceTracker
+        from tgm_b200.core.timedelta import TimeDeltaDG
+        nbl = min(a.loader_batches, b_hi - b_lo)
+        # every rank walks the head of the stream (loader.py:137-139 iterates absolute event indices
+        # from 0, so an index-sliced view cannot start mid-stream); this key measures the Python API
+        sl = DGSliceTracker(end_idx=min(nbl * bs, E))
+        dg = DGraph._from_storage(store, TimeDeltaDG('r'), dev, sl)
+        hm = HookManager(keys=['bench'])
+        hm.register('bench', RecencyNeighborHook(
+            num_nodes=N, num_nbrs=[k], seed_nodes_keys=['edge_src', 'edge_dst'],
+            seed_times_keys=['edge_time', 'edge_time'], window_batches=min(5000, nbl)))
+        with hm.activate('bench'):
+            for pass_ in range(2):  # first pass warms the adjacency cache and the allocator
+                hm.reset_state()
+                barrier()
+                t0 = time.perf_counter()
+                got = 0
+                for batch in DGDataLoader(dg, batch_size=bs, hook_manager=hm):
+                    got += batch.nbr_nids[0].numel()
+                barrier()
+                dt = time.perf_counter() - t0
+        dt_max = reduce_max(dt)
+        loader_api = {'value': reduce_sum(float(got)) / dt_max, 'unit': UNIT, 'batches': nbl,
+                      'us_per_batch': dt_max / nbl * 1e6,
+                      'api': 'DGDataLoader(batch_size=200) + HookManager + RecencyNeighborHook('
+                             'window_batches=5000): outputs stay on the device, one DGBatch per '
+                             'iteration (Python-bound)'}
+
     # ---- CPU baseline on this host (rank 0, N=1 only) ---------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -404,7 +438,8 @@ def run_b200(a):
             'dtype': 'int32/int64 ids+times, f32 feature copy', 'data': 'synthetic',
             'config': workload_config(a, world), 'gpu_launches': a.steps,
             'stream_edges_per_s': value / (2 * k),
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'clocks': clocks.result(),
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'loader_api': loader_api,
+            'clocks': clocks.result(),
             'build_s': t_build,
         }
         print(json.dumps(line))
