@@ -246,6 +246,9 @@ class DeviceCOOStorage(DGStorageBase):
 
     def get_nodes(self, slice: DGSliceTracker) -> Set[int]:
         lo, hi = self.edge_range(slice)
+        if self._data is None:  # adopted device stream: no host mirror of the ids
+            both = torch.cat([self._src[lo:hi], self._dst[lo:hi]])
+            return set(torch.unique(both).cpu().tolist())
         nodes = set(np.unique(self._data.edge_index[lo:hi].numpy()).tolist())
         a, b = self._sub_range(self._data.node_x_mask, slice)
         if b > a:
@@ -273,13 +276,13 @@ class DeviceCOOStorage(DGStorageBase):
         return None if hi <= lo else self._edge_type[lo:hi]
 
     def get_node_events(self, slice: DGSliceTracker) -> Tuple[Tensor, Tensor]:
-        if self._data.node_x_mask is None:
+        if self._data is None or self._data.node_x_mask is None:
             return torch.empty(0, dtype=torch.int32), torch.empty(0, dtype=torch.int64)
         a, b = self._sub_range(self._data.node_x_mask, slice)
         return self._data.node_x_nids[a:b], self._data.time[self._data.node_x_mask[a:b]]
 
     def get_node_labels(self, slice: DGSliceTracker) -> Tuple[Tensor, Tensor]:
-        if self._data.node_y_mask is None:
+        if self._data is None or self._data.node_y_mask is None:
             return torch.empty(0, dtype=torch.int32), torch.empty(0, dtype=torch.int64)
         a, b = self._sub_range(self._data.node_y_mask, slice)
         return self._data.node_y_nids[a:b], self._data.time[self._data.node_y_mask[a:b]]
@@ -310,31 +313,37 @@ class DeviceCOOStorage(DGStorageBase):
 
     def get_node_x(self, slice: DGSliceTracker) -> Optional[Tensor]:
         d = self._data
+        if d is None:
+            return None
         return self._sparse_node_tensor(slice, d.node_x_mask, d.node_x_nids, d.node_x,
                                         self.get_node_x_dim())
 
     def get_node_y(self, slice: DGSliceTracker) -> Optional[Tensor]:
         d = self._data
+        if d is None:
+            return None
         return self._sparse_node_tensor(slice, d.node_y_mask, d.node_y_nids, d.node_y,
                                         self.get_node_y_dim())
 
     def get_static_node_x(self) -> Optional[Tensor]:
-        return self._data.static_node_x
+        return None if self._data is None else self._data.static_node_x
 
     def get_node_type(self) -> Optional[Tensor]:
-        return self._data.node_type
+        return None if self._data is None else self._data.node_type
 
     def get_node_x_dim(self) -> Optional[int]:
-        return None if self._data.node_x is None else int(self._data.node_x.shape[1])
+        d = self._data
+        return None if d is None or d.node_x is None else int(d.node_x.shape[1])
 
     def get_node_y_dim(self) -> Optional[int]:
-        return None if self._data.node_y is None else int(self._data.node_y.shape[1])
+        d = self._data
+        return None if d is None or d.node_y is None else int(d.node_y.shape[1])
 
     def get_edge_x_dim(self) -> Optional[int]:
         return self._D if self._has_edge_x else None
 
     def get_static_node_x_dim(self) -> Optional[int]:
-        sx = self._data.static_node_x
+        sx = None if self._data is None else self._data.static_node_x
         return None if sx is None else int(sx.shape[1])
 
     def get_nbrs(self, seed_nodes: Tensor, num_nbrs: int, slice: DGSliceTracker,
