@@ -572,3 +572,25 @@ def test_constructor_errors_match_the_reference():
     with pytest.raises(ValueError, match='seed_nodes_keys'):
         RecencyNeighborHook(num_nodes=3, num_nbrs=[1], seed_nodes_keys=['edge_src', 'edge_dst'],
                             seed_times_keys=['edge_time'])
+
+
+@pytest.mark.parametrize('directed', [False, True])
+def test_bulk_ring_update_matches_oracle(directed):
+    """One tgm_recency_update call with 300k edges (the sort-based ranking path) followed by a
+    small one (the in-batch path): state and queries equal the C oracle's."""
+    N, D, B = 5000, 4, 8
+    src, dst, t, x = _random_stream(33, N, 300_000, 4000, D, hot=0.02)
+    ring, oracle = Ring(N, B, D), CRing(N, [B], D, directed)
+    for lo, hi in ((0, 299_000), (299_000, 300_000)):
+        ring.update(dev(src[lo:hi], torch.int32), dev(dst[lo:hi], torch.int32),
+                    dev(t[lo:hi], torch.int64), dev(x[lo:hi], torch.float32), directed)
+        oracle.update(src[lo:hi], dst[lo:hi], t[lo:hi], x[lo:hi])
+    ids, times, feats, wpos = ring.state()
+    assert np.array_equal(ids, oracle.ids) and np.array_equal(times, oracle.times)
+    assert np.array_equal(feats, oracle.feats) and np.array_equal(wpos, oracle.write_pos)
+    seeds = np.arange(N, dtype=np.int32)
+    tq = np.full(N, 3500, np.int64)
+    got = ring.query(dev(seeds, torch.int32), dev(tq, torch.int64), B)
+    want = oracle.query(seeds, tq, B)
+    for g_, w_ in zip(got, want):
+        assert np.array_equal(g_.cpu().numpy(), w_)

@@ -4,9 +4,11 @@
 // _get_recency_neighbors :239-321 (~25 eager ops + an O(N*B) min() scan per call), _update
 // :323-399 (argsort + 15 eager ops).  Here a query is one launch (a warp per seed, only the k
 // needed feature rows are read) and an update is two launches.
-#include "common.cuh"
+#include <cub/cub.cuh>
 
 #include <new>
+
+#include "common.cuh"
 
 using namespace tgm;
 
@@ -195,6 +197,73 @@ ring_update_rank_kernel(int32_t *__restrict__ ids, int64_t *__restrict__ times,
   inc[i] = add;
 }
 
+// Bulk path (n > kRankDirectMax): the same ranking from two stable radix sorts -- by time, then by
+// node -- so entries of a node end up contiguous in (time, position) order.
+constexpr int64_t kRankDirectMax = 8192;
+
+__global__ void bulk_time_keys_kernel(const int64_t *__restrict__ t, int64_t Eb, int64_t n,
+                                      uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    // order-preserving map of int64 to uint64 (times are >= 0 in valid streams, but stay total)
+    keys[i] = uint64_t(t[i < Eb ? i : i - Eb]) ^ 0x8000000000000000ull;
+    vals[i] = uint32_t(i);
+  }
+}
+__global__ void bulk_node_keys_kernel(const int32_t *__restrict__ src,
+                                      const int32_t *__restrict__ dst, int64_t Eb, int64_t n,
+                                      const uint32_t *__restrict__ vals,
+                                      uint32_t *__restrict__ keys) {
+  for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n;
+       j += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t i = vals[j];
+    keys[j] = uint32_t(i < Eb ? src[i] : dst[i - Eb]);
+  }
+}
+// sorted position j -> rank and count inside its node run, then the same placement rule as
+// ring_update_rank_kernel
+__global__ void bulk_place_kernel(int32_t *__restrict__ ids, int64_t *__restrict__ times,
+                                  const int32_t *__restrict__ wpos, int N, int B,
+                                  const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                                  const int64_t *__restrict__ t, int64_t Eb, int64_t n,
+                                  const uint32_t *__restrict__ keys,
+                                  const uint32_t *__restrict__ vals, int64_t *__restrict__ dest,
+                                  int32_t *__restrict__ inc) {
+  for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n;
+       j += int64_t(gridDim.x) * blockDim.x) {
+    const uint32_t node = keys[j];
+    int64_t lo = 0, hi = j;  // first position of the run
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (keys[mid] < node) lo = mid + 1; else hi = mid;
+    }
+    const int64_t start = lo;
+    lo = j + 1, hi = n;  // one past the run
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (keys[mid] <= node) lo = mid + 1; else hi = mid;
+    }
+    const int64_t cnt = lo - start, rank = j - start;
+    const int64_t i = vals[j];
+    const UpdEntry me = load_entry(src, dst, t, Eb, i);
+    int64_t d = -1;
+    int32_t add = 0;
+    if (me.node >= 0 && me.node < N) {
+      const int64_t first_kept = cnt > B ? cnt - B : 0;
+      if (rank >= first_kept) {
+        const int wp = int(uint32_t(wpos[me.node]) % uint32_t(B));
+        const int slot = int((wp + (rank - first_kept)) % B);
+        d = int64_t(me.node) * B + slot;
+        ids[d] = me.nbr;
+        times[d] = me.t;
+      }
+      if (rank == cnt - 1) add = int32_t(cnt < B ? cnt : B);
+    }
+    dest[i] = d;
+    inc[i] = add;
+  }
+}
+
 // Phase B: copy the kept feature rows (a warp per entry, coalesced) and advance write_pos.
 __global__ void __launch_bounds__(256)
 ring_update_commit_kernel(float *__restrict__ feats, int32_t *__restrict__ wpos, int D,
@@ -316,10 +385,7 @@ extern "C" int tgm_recency_update(tgm_recency *h, const int32_t *src, const int3
   DeviceGuard g(h->device);
   cudaStream_t st = as_stream(stream);
   const int64_t n = directed ? Eb : 2 * Eb;
-  // the in-batch ranking is O(n^2 / tile): right for loader batches, not for bulk loads
-  TGM_REQUIRE(n <= (int64_t(1) << 17),
-              "tgm_recency_update: batch too large for the stateful ring (max 65536 edges); "
-              "bulk streams go through tgm_csr_build / tgm_csr_sample");
+  TGM_REQUIRE(n < (int64_t(1) << 31), "tgm_recency_update: batch too large");
   if (n > h->cap) {
     // growing the scratch is the only synchronising path; steady state never reallocates
     TGM_CUDA(cudaStreamSynchronize(st));
@@ -333,10 +399,52 @@ extern "C" int tgm_recency_update(tgm_recency *h, const int32_t *src, const int3
     TGM_CUDA(cudaMalloc(&h->inc, size_t(cap) * 4));
     h->cap = cap;
   }
-  const int gridA = int((n + kRankThreads - 1) / kRankThreads);
-  ring_update_rank_kernel<<<gridA, kRankThreads, 0, st>>>(h->ids, h->times, h->wpos, h->N, h->B,
-                                                          src, dst, t, Eb, n, h->dest, h->inc);
-  TGM_LAUNCH_CHECK();
+  if (n <= kRankDirectMax) {  // loader batches: O(n^2 / tile) ranking over shared-memory tiles
+    const int gridA = int((n + kRankThreads - 1) / kRankThreads);
+    ring_update_rank_kernel<<<gridA, kRankThreads, 0, st>>>(h->ids, h->times, h->wpos, h->N, h->B,
+                                                            src, dst, t, Eb, n, h->dest, h->inc);
+    TGM_LAUNCH_CHECK();
+  } else {  // bulk load: sort-based ranking (scratch is allocated per call; synchronises)
+    uint64_t *kt_a = nullptr, *kt_b = nullptr;
+    uint32_t *v_a = nullptr, *v_b = nullptr, *kn_a = nullptr, *kn_b = nullptr;
+    void *tmp = nullptr;
+    auto done = [&](int rc) {
+      cudaStreamSynchronize(st);
+      cudaFree(kt_a), cudaFree(kt_b), cudaFree(v_a), cudaFree(v_b), cudaFree(kn_a), cudaFree(kn_b);
+      cudaFree(tmp);
+      return rc;
+    };
+#define BULK_CUDA(expr)                                                        \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess) return done(cuda_fail(_e, #expr, __FILE__, __LINE__)); \
+  } while (0)
+    const size_t nn = size_t(n);
+    BULK_CUDA(cudaMalloc(&kt_a, nn * 8));
+    BULK_CUDA(cudaMalloc(&kt_b, nn * 8));
+    BULK_CUDA(cudaMalloc(&v_a, nn * 4));
+    BULK_CUDA(cudaMalloc(&v_b, nn * 4));
+    BULK_CUDA(cudaMalloc(&kn_a, nn * 4));
+    BULK_CUDA(cudaMalloc(&kn_b, nn * 4));
+    size_t b1 = 0, b2 = 0;
+    BULK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b1, kt_a, kt_b, v_a, v_b, n, 0, 64, st));
+    BULK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b2, kn_a, kn_b, v_b, v_a, n, 0, 32, st));
+    size_t tmp_bytes = b1 > b2 ? b1 : b2;
+    BULK_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    bulk_time_keys_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(t, Eb, n, kt_a, v_a);
+    BULK_CUDA(cudaGetLastError());
+    BULK_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kt_a, kt_b, v_a, v_b, n, 0, 64, st));
+    bulk_node_keys_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(src, dst, Eb, n, v_b, kn_a);
+    BULK_CUDA(cudaGetLastError());
+    BULK_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kn_a, kn_b, v_b, v_a, n, 0, 32, st));
+    bulk_place_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(h->ids, h->times, h->wpos, h->N, h->B,
+                                                           src, dst, t, Eb, n, kn_b, v_a, h->dest,
+                                                           h->inc);
+    BULK_CUDA(cudaGetLastError());
+#undef BULK_CUDA
+    int rc = done(TGM_OK);
+    if (rc != TGM_OK) return rc;
+  }
   const int gridB = grid_for(n, 8, 8);
   ring_update_commit_kernel<<<gridB, 256, 0, st>>>(h->feats, h->wpos, h->D, src, dst, x, Eb, n,
                                                    h->dest, h->inc);
