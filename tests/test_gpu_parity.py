@@ -594,3 +594,57 @@ def test_bulk_ring_update_matches_oracle(directed):
     want = oracle.query(seeds, tq, B)
     for g_, w_ in zip(got, want):
         assert np.array_equal(g_.cpu().numpy(), w_)
+
+
+# ---- section 8f rows N2 / N3: dedup and negative hooks around the sampler ----------------------
+from tgm_b200 import DeduplicationHook, RandomNegativeEdgeSamplerHook  # noqa: E402
+
+
+@pytest.mark.parametrize('name', ['twohop_neg', 'rand_b', 'rand_d'])
+def test_dedup_hook_after_the_sampler(name):
+    """The hook chain of examples/linkproppred/tgn.py:190-210: negatives -> recency sampler ->
+    DeduplicationHook(['neg', 'nbr_nids']).  unique_nids must be the sorted unique of
+    [src, dst, neg, non-padded neighbours of every hop] (tgm/hooks/dedup.py:35-57) -- computed here
+    from what the REFERENCE put on the batch (the fixture) -- and global_to_local its inverse."""
+    import os
+    g = Golden(os.path.join(os.path.dirname(golden_files()[0]), f'recency_{name}.npz'))
+    ei = torch.from_numpy(np.stack([g.src, g.dst], 1).astype(np.int32))
+    dg = DGraph(DGData.from_raw(torch.from_numpy(g.t), ei, torch.from_numpy(g.x)), device=DEV)
+    hm = HookManager(keys=['g'])
+    hm.register('g', _InjectNegatives(dev(g.neg, torch.int32)))
+    hm.register('g', RecencyNeighborHook(num_nodes=g.N, num_nbrs=g.num_nbrs,
+                                         seed_nodes_keys=['edge_src', 'edge_dst', 'neg'],
+                                         seed_times_keys=['edge_time', 'edge_time', 'neg_time'],
+                                         directed=g.directed))
+    hm.register('g', DeduplicationHook(seed_nodes_keys=['neg', 'nbr_nids']))
+    with hm.activate('g'):
+        for b, batch in enumerate(DGDataLoader(dg, batch_size=g.bs, hook_manager=hm)):
+            lo, hi = b * g.bs, min((b + 1) * g.bs, g.E)
+            parts = [g.src[lo:hi], g.dst[lo:hi], g.neg[lo:hi]]
+            for h in range(len(g.num_nbrs)):
+                nid = g.expect(0, b, h)[2].reshape(-1)
+                parts.append(nid[nid != -1])
+            want = np.unique(np.concatenate(parts))
+            got = batch.unique_nids.cpu().numpy()
+            assert got.dtype == np.int32 and np.array_equal(got, want)
+            probe = torch.from_numpy(want[::-1].copy()).to(DEV)
+            local = batch.global_to_local(probe)
+            assert local.dtype == torch.int32
+            assert local.cpu().tolist() == list(range(len(want) - 1, -1, -1))
+
+
+def test_random_negative_sampler_contract():
+    """tgm/hooks/negatives/sampler.py:14-65: int32 ids in [low, high) on the graph's device,
+    round(neg_ratio * E_b) of them, neg_time a copy of edge_time; constructor errors."""
+    dg = _tiny_dg()
+    batch = dg.materialize()
+    torch.manual_seed(0)
+    out = RandomNegativeEdgeSamplerHook(low=10, high=20)(dg, batch)
+    assert out.neg.dtype == torch.int32 and out.neg.is_cuda and out.neg.shape == (3,)
+    assert bool(((out.neg >= 10) & (out.neg < 20)).all())
+    assert torch.equal(out.neg_time, batch.edge_time) and out.neg_time is not batch.edge_time
+    half = RandomNegativeEdgeSamplerHook(low=0, high=5, neg_ratio=0.1)(dg, dg.materialize())
+    assert half.neg.shape == (0,) and half.neg_time.dtype == torch.int64
+    for kw in (dict(low=3, high=3), dict(low=0, high=5, neg_ratio=0.0), dict(low=0, high=5, neg_ratio=1.5)):
+        with pytest.raises(ValueError):
+            RandomNegativeEdgeSamplerHook(**kw)
