@@ -381,6 +381,16 @@ __device__ __forceinline__ void emit_fast(const float4 *__restrict__ x4, int D4,
   }
 }
 
+// Chunks of 32 seeds are handed out dynamically: the first by warp id, the rest from a ticket
+// counter (windows differ in length; a static split leaves a ~1/iterations tail).
+__device__ __forceinline__ int64_t next_chunk(unsigned long long *ticket, int64_t wstride,
+                                              int lane) {
+  unsigned long long nx = 0;
+  if (lane == 0) nx = atomicAdd(ticket, 1ull);
+  return wstride + int64_t(__shfl_sync(0xffffffffu, (unsigned int)(nx & 0xffffffffu), 0)) +
+         (int64_t(__shfl_sync(0xffffffffu, (unsigned int)(nx >> 32), 0)) << 32);
+}
+
 // walk the (up to) 32 seeds whose windows the lanes resolved
 __device__ __forceinline__ void walk_chunk(const Entry *__restrict__ entries,
                                            const float4 *__restrict__ x4, int D4,
@@ -409,13 +419,13 @@ csr_sample_edges_fast_kernel(const Entry *__restrict__ entries, const uint2 *__r
                              const float4 *__restrict__ x4, const int64_t *__restrict__ t, int D4,
                              int64_t Ew, uint32_t bs, int64_t l_lo, int64_t l_hi, int B, int k,
                              int32_t *__restrict__ out_nid, int64_t *__restrict__ out_t,
-                             float4 *__restrict__ out_x4) {
+                             float4 *__restrict__ out_x4, unsigned long long *__restrict__ ticket) {
   const int lane = threadIdx.x & 31;
   const int64_t S = 2 * (l_hi - l_lo);
   const int64_t nchunks = (S + 31) >> 5;
   const int64_t wstride = int64_t(gridDim.x) * (kFastThreads >> 5);
   for (int64_t ch = int64_t(blockIdx.x) * (kFastThreads >> 5) + (threadIdx.x >> 5); ch < nchunks;
-       ch += wstride) {
+       ch = next_chunk(ticket, wstride, lane)) {
     const int64_t s_base = ch << 5, s = s_base + lane;
     SeedWin mine{0, 0, 0};
     if (s < S) {
@@ -442,12 +452,12 @@ csr_sample_fast_kernel(const Entry *__restrict__ entries, const int64_t *__restr
                        const int32_t *__restrict__ seeds, const int64_t *__restrict__ tq,
                        const int64_t *__restrict__ cut, int64_t cut_group, int64_t S, int B, int k,
                        int32_t *__restrict__ out_nid, int64_t *__restrict__ out_t,
-                       float4 *__restrict__ out_x4) {
+                       float4 *__restrict__ out_x4, unsigned long long *__restrict__ ticket) {
   const int lane = threadIdx.x & 31;
   const int64_t nchunks = (S + 31) >> 5;
   const int64_t wstride = int64_t(gridDim.x) * (kFastThreads >> 5);
   for (int64_t ch = int64_t(blockIdx.x) * (kFastThreads >> 5) + (threadIdx.x >> 5); ch < nchunks;
-       ch += wstride) {
+       ch = next_chunk(ticket, wstride, lane)) {
     const int64_t s_base = ch << 5, s = s_base + lane;
     SeedWin mine{0, 0, 0};
     if (s < S) {
@@ -780,10 +790,7 @@ csr_sample_tma_kernel(const Entry *__restrict__ entries, const float *__restrict
       wstart = wstart_n;
       nwin = nwin_n;
     }
-    unsigned long long nx = 0;
-    if (lane == 0) nx = atomicAdd(ticket, 1ull);
-    ch = wstride + int64_t(__shfl_sync(0xffffffffu, (unsigned int)(nx & 0xffffffffu), 0)) +
-         (int64_t(__shfl_sync(0xffffffffu, (unsigned int)(nx >> 32), 0)) << 32);
+    ch = next_chunk(ticket, wstride, lane);
   }
   if (lane == 0) {  // drain
     for (uint32_t q = g >= uint32_t(kTmaLag) ? g - kTmaLag : 0; q < g; ++q) retire(q);
@@ -948,6 +955,12 @@ int sample_cfg(const tgm_csr *c, const char *who, int64_t S, int32_t B, int32_t 
 }  // namespace
 
 namespace {
+// a zeroed chunk counter for one launch (launches of a handle rotate through kTickets counters)
+int new_ticket(const tgm_csr *c, cudaStream_t st, unsigned long long **out) {
+  *out = c->ticket + (c->launches++ % tgm_csr::kTickets);
+  TGM_CUDA(cudaMemsetAsync(*out, 0, sizeof(unsigned long long), st));
+  return TGM_OK;
+}
 bool tma_applies(const tgm_csr *c, int k) {
   return c->D > 0 && g_csr_feature_copy == 1 && k * c->D * 4 <= kTmaMaxStageBytes;
 }
@@ -963,8 +976,9 @@ int launch_tma(const tgm_csr *c, const TmaSeedArgs &a, int64_t S, int B, int k, 
   int per_sm = int(std::max<size_t>(1, std::min<size_t>(TGM_FAST_MIN_BLOCKS, (220 * 1024) / (smem + 1024))));
   if (g_csr_tma_ctas_per_sm > 0 && g_csr_tma_ctas_per_sm < per_sm) per_sm = g_csr_tma_ctas_per_sm;
   const int grid = grid_for((S + 31) / 32, kFastThreads / 32, per_sm);
-  unsigned long long *ticket = c->ticket + (c->launches++ % tgm_csr::kTickets);
-  TGM_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st));
+  unsigned long long *ticket = nullptr;
+  int trc = new_ticket(c, st, &ticket);
+  if (trc != TGM_OK) return trc;
   csr_sample_tma_kernel<EDGE_SEEDS><<<grid, kFastThreads, smem, st>>>(
       c->entries, xrows, a, c->D, B, k, out_nid, out_t, out_x, stage_bytes, ticket);
   TGM_LAUNCH_CHECK();
@@ -1004,13 +1018,17 @@ extern "C" int tgm_csr_sample(const tgm_csr *c, const int32_t *seeds, const int6
     a.N = c->N;
     rc = launch_tma<false>(c, a, S, B, k, cfg.xsrc, out_nid, out_t, out_x, st);
     if (rc != TGM_OK) return rc;
-  } else if (cfg.fast)
+  } else if (cfg.fast) {
+    unsigned long long *ticket = nullptr;
+    rc = new_ticket(c, st, &ticket);
+    if (rc != TGM_OK) return rc;
     csr_sample_fast_kernel<<<cfg.fast_grid, kFastThreads, 0, st>>>(
         c->entries, c->rowptr, reinterpret_cast<const float4 *>(cfg.xsrc), c->N, c->D / 4, seeds,
-        tq, cut, cut_group, S, B, k, out_nid, out_t, reinterpret_cast<float4 *>(out_x));
-  else
+        tq, cut, cut_group, S, B, k, out_nid, out_t, reinterpret_cast<float4 *>(out_x), ticket);
+  } else {
     DISPATCH_SAMPLE(csr_sample_kernel, c->entries, c->rowptr, cfg.xsrc, c->N, c->D, seeds, tq,
                     cut, cut_group, S, B, k, out_nid, out_t, out_x);
+  }
   TGM_LAUNCH_CHECK();
   return TGM_OK;
 }
@@ -1037,15 +1055,19 @@ extern "C" int tgm_csr_sample_edges(const tgm_csr *c, int64_t e_lo, int64_t e_hi
     a.bs = uint32_t(c->bs);
     rc = launch_tma<true>(c, a, S, B, k, cfg.xsrc, out_nid, out_t, out_x, st);
     if (rc != TGM_OK) return rc;
-  } else if (cfg.fast && c->bs < (int64_t(1) << 31))
+  } else if (cfg.fast && c->bs < (int64_t(1) << 31)) {
+    unsigned long long *ticket = nullptr;
+    rc = new_ticket(c, st, &ticket);
+    if (rc != TGM_OK) return rc;
     csr_sample_edges_fast_kernel<<<cfg.fast_grid, kFastThreads, 0, st>>>(
         c->entries, c->anchors, reinterpret_cast<const float4 *>(cfg.xsrc),
         c->store->t + c->e_start, c->D / 4, c->Ew, uint32_t(c->bs), l_lo, l_hi, B, k, out_nid,
-        out_t, reinterpret_cast<float4 *>(out_x));
-  else
+        out_t, reinterpret_cast<float4 *>(out_x), ticket);
+  } else {
     DISPATCH_SAMPLE(csr_sample_edges_kernel, c->entries, c->anchors, cfg.xsrc,
                     c->store->t + c->e_start, c->D, c->Ew, c->bs, l_lo, l_hi, B, k, out_nid, out_t,
                     out_x);
+  }
   TGM_LAUNCH_CHECK();
   return TGM_OK;
 }
