@@ -132,25 +132,20 @@ attn_neighbor_kernel(const float *__restrict__ nbr_feat, const float *__restrict
     const int64_t tq = nbr_tf ? 0 : seed_t[s];
     const float *nf = nbr_feat + s * int64_t(k) * node_dim;
     const float *ef = edge_feat + s * int64_t(k) * edge_dim;
-    for (int i = tid; i < k * node_dim; i += kAttnThreads) {
-      const int n = i / node_dim, c = i - n * node_dim;
-      z[n * key + c] = __ldg(nf + i);
-    }
-    for (int i = tid; i < k * edge_dim; i += kAttnThreads) {
-      const int n = i / edge_dim, c = i - n * edge_dim;
-      z[n * key + node_dim + c] = __ldg(ef + i);
-    }
-    if (nbr_tf) {  // caller-provided time features (the plain attention.py:58 signature)
-      const float *tf = nbr_tf + s * int64_t(k) * time_dim;
-      for (int i = tid; i < k * time_dim; i += kAttnThreads) {
-        const int n = i / time_dim, c = i - n * time_dim;
-        z[n * key + node_dim + edge_dim + c] = __ldg(tf + i);
-      }
-    } else {
-      for (int i = tid; i < k * time_dim; i += kAttnThreads) {
-        const int n = i / time_dim, c = i - n * time_dim;
+    // one warp per neighbour row, lanes along the feature dimension (coalesced, no divisions)
+    for (int n = warp; n < k; n += nwarp) {
+      float *zn = z + n * key;
+      const float *nfr = nf + n * node_dim, *efr = ef + n * edge_dim;
+      for (int c = lane; c < node_dim; c += 32) zn[c] = __ldg(nfr + c);
+      for (int c = lane; c < edge_dim; c += 32) zn[node_dim + c] = __ldg(efr + c);
+      float *zt = zn + node_dim + edge_dim;
+      if (nbr_tf) {  // caller-provided time features (the plain attention.py:58 signature)
+        const float *tf = nbr_tf + (s * int64_t(k) + n) * time_dim;
+        for (int c = lane; c < time_dim; c += 32) zt[c] = __ldg(tf + c);
+      } else {
         const float dt = float(tq - nbr_t[s * k + n]);  // int64 difference, then .float() (:23)
-        z[n * key + node_dim + edge_dim + c] = cosf(__fmaf_rn(dt, __ldg(tw + c), __ldg(tb + c)));
+        for (int c = lane; c < time_dim; c += 32)
+          zt[c] = cosf(__fmaf_rn(dt, __ldg(tw + c), __ldg(tb + c)));
       }
     }
     for (int i = tid; i < H * key; i += kAttnThreads) qk[i] = QK[s * int64_t(H) * key + i];
