@@ -1,0 +1,181 @@
+#!/usr/bin/env python
+"""End-to-end pipelines for BASELINE.json configs[2] and configs[4] (configs[3], TGN memory with
+the shard join, is bench_tgn_shard.py; configs[1]/headline is bench.py).
+
+    python bench_configs.py --config 3                      # TGAT, tgbl-wiki-shaped, 1 GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29544 bench_configs.py --config 5      # DyGFormer, time-sharded
+
+config 3  per loader batch of 200 edges: random negatives -> 2-hop recent-neighbour sampling
+          k=[20,20] over [src|dst|neg] (windowed hook through DGDataLoader/HookManager, the
+          drop-in API) -> TGAT forward (2 layers, 2 heads, time 100, embed 172) -> 600 embeddings.
+config 5  per rank a time-range shard of a synthetic stream: one pre-sampled window (k=31 so the
+          DyGFormer sequence is 32), then per batch of 200 edges a DyGFormer forward (patch 1,
+          4x50 channels, 2 layers, 2 heads) -> 2x200 embeddings.  No collective on the data path.
+
+Forward/evaluation pipelines (the library has no backward).  One JSON line on rank 0; CUDA-event
+times, max over ranks; the CPU oracle is timed beside it on a few batches (config 3 only: the
+numpy DyGFormer oracle is timed in bench_rows.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tgm_b200 import (DGData, DGDataLoader, DGraph, HookManager,  # noqa: E402
+                      RandomNegativeEdgeSamplerHook, RecencyCSR, RecencyNeighborHook)
+from tgm_b200.core.storage import DeviceCOOStorage  # noqa: E402
+from tgm_b200.nn import TGAT, DyGFormer  # noqa: E402
+from tgm_b200.parallel import max_over_ranks, shard_batches, sum_over_ranks  # noqa: E402
+
+
+def config3(a, dev):
+    from bench_rows import wiki_stream
+    src, dst, t, x, N = wiki_stream()
+    ei = torch.from_numpy(np.stack([src, dst], 1))
+    dg = DGraph(DGData.from_raw(torch.from_numpy(t), ei, torch.from_numpy(x)), device=dev)
+    bs, nn = 200, [20, 20]
+    torch.manual_seed(1337)
+    model = TGAT(node_dim=1, edge_dim=x.shape[1], time_dim=100, embed_dim=172, num_layers=2,
+                 n_heads=2).to(dev).eval()
+    node_x = torch.randn(N, 1, device=dev)
+    hm = HookManager(keys=['train'])
+    hm.register('train', RandomNegativeEdgeSamplerHook(low=8227, high=N))
+    hm.register('train', RecencyNeighborHook(
+        num_nodes=N, num_nbrs=nn, seed_nodes_keys=['edge_src', 'edge_dst', 'neg'],
+        seed_times_keys=['edge_time', 'edge_time', 'neg_time'], window_batches=a.window_batches))
+    nb = a.batches
+
+    def epoch():
+        hm.reset_state()
+        done = 0
+        with hm.activate('train'):
+            for batch in DGDataLoader(dg, batch_size=bs, hook_manager=hm):
+                z = model(node_x, batch.seed_nids, batch.seed_times, batch.nbr_nids,
+                          batch.nbr_edge_x, batch.nbr_edge_time)
+                done += 1
+                if done == nb:
+                    break
+        return z
+
+    epoch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    z = epoch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    # CPU: C ring sampler + numpy TGAT oracle on a few batches (same shapes, same weights)
+    from oracle import nn_oracle
+    from oracle.c_oracle import CRing
+    p = {k_: v.detach().cpu().numpy() for k_, v in model.state_dict().items()}
+    ring = CRing(N, nn, x.shape[1])
+    npx = node_x.cpu().numpy()
+    rng = np.random.default_rng(0)
+    nbc = 3
+    c0 = time.perf_counter()
+    for b in range(nbc):
+        lo, hi = b * bs, (b + 1) * bs
+        neg = rng.integers(8227, N, hi - lo).astype(np.int32)
+        seeds = np.concatenate([src[lo:hi], dst[lo:hi], neg])
+        tq = np.concatenate([t[lo:hi]] * 3)
+        hops = ring.hook_call(seeds, tq, src[lo:hi], dst[lo:hi], t[lo:hi], x[lo:hi])
+        nn_oracle.tgat_forward(p, 2, 2, npx, [h[0] for h in hops], [h[1] for h in hops],
+                               [h[2] for h in hops], [h[4] for h in hops], [h[3] for h in hops])
+    cpu_ms = (time.perf_counter() - c0) / nbc * 1e3
+    return {'row': 'config 3: TGAT on tgbl-wiki-shaped stream, 2-hop k=[20,20], bs=200 (+200 negatives)',
+            'batches': nb, 'ms_per_batch': ms / nb, 'events_per_s': nb * bs / (ms * 1e-3),
+            'embeddings_per_batch': int(z.shape[0]),
+            'sampled_edges_per_s': nb * (600 * 20 + 12000 * 20) / (ms * 1e-3),
+            'cpu_baseline': {'value': cpu_ms, 'unit': 'ms/batch', 'kind': 'port',
+                             'cores': os.cpu_count(),
+                             'sample': f'{nbc} batches: C ring sampler + numpy TGAT oracle'},
+            'note': 'DGDataLoader + HookManager + windowed RecencyNeighborHook + TGAT.forward; '
+                    'forward only'}
+
+
+def config5(a, dev, rank, world):
+    E, N, D, bs, k = a.edges, a.nodes, 16, 200, 31
+    g = torch.Generator(device=dev).manual_seed(0)
+    src = torch.randint(0, N, (E,), generator=g, device=dev, dtype=torch.int32)
+    dst = torch.randint(0, N, (E,), generator=g, device=dev, dtype=torch.int32)
+    t = torch.sort(torch.randint(0, 2000, (E,), generator=g, device=dev))[0]
+    x = torch.randn(E, D, generator=g, device=dev)
+    store = DeviceCOOStorage.from_device_tensors(src, dst, t, x, N)
+    csr = RecencyCSR(store, bs, colocate_x=True)
+    torch.manual_seed(0)
+    model = DyGFormer(node_feat_dim=128, edge_x_dim=D, time_feat_dim=100, channel_embedding_dim=50,
+                      output_dim=172, patch_size=1, num_layers=2, num_heads=2,
+                      max_input_sequence_length=k + 1).to(dev).eval()
+    node_x = torch.randn(N, 128, generator=g, device=dev)
+    shard = shard_batches(E, bs, rank, world)
+    lo = shard.edge_lo + (shard.num_edges // 2 // bs) * bs  # mid-shard: populated histories
+    hi = min(lo + a.batches * bs, shard.edge_hi)
+
+    def run():
+        hop = csr.sample_window(lo, hi, [k])[0]
+        for b_lo in range(lo, hi, bs):
+            b_hi = min(b_lo + bs, hi)
+            r0, r1 = 2 * (b_lo - lo), 2 * (b_hi - lo)
+            ei = torch.stack([src[b_lo:b_hi], dst[b_lo:b_hi]])
+            zs, zd = model(node_x, ei, t[b_lo:b_hi], hop.nbr_nids[r0:r1], hop.nbr_edge_time[r0:r1],
+                           hop.nbr_edge_x[r0:r1])
+        return zs
+
+    run()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    events = sum_over_ranks(float(hi - lo), dev)
+    nb = (hi - lo) // bs
+    return {'row': 'config 5: DyGFormer on a time-sharded synthetic stream, sequence 32 (k=31), patch 1',
+            'n_gpus': world, 'edges': E, 'batches_per_rank': nb, 'ms_per_batch': ms / nb,
+            'events_per_s': events / (ms * 1e-3), 'sequences_per_s': 2 * events / (ms * 1e-3),
+            'note': 'one pre-sampled window per rank + DyGFormer.forward per 200-edge batch; '
+                    'store/adjacency replicated, no collective on the data path; forward only'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--config', type=int, required=True, choices=[3, 5])
+    ap.add_argument('--batches', type=int, default=200)
+    ap.add_argument('--window-batches', type=int, default=25)
+    ap.add_argument('--edges', type=int, default=100_000_000)
+    ap.add_argument('--nodes', type=int, default=1_000_000)
+    a = ap.parse_args()
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ['NCCL_DEBUG'] = 'WARN'
+        dist.init_process_group('nccl', device_id=dev)
+    out = config3(a, dev) if a.config == 3 else config5(a, dev, rank, world)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
