@@ -648,3 +648,71 @@ def test_random_negative_sampler_contract():
     for kw in (dict(low=3, high=3), dict(low=0, high=5, neg_ratio=0.0), dict(low=0, high=5, neg_ratio=1.5)):
         with pytest.raises(ValueError):
             RandomNegativeEdgeSamplerHook(**kw)
+
+
+def test_host_buffer_entry_point_matches_device_path():
+    """tgm_csr_sample_edges_host (H2D of the slab, kernel, D2H of the result, stream-ordered) gives
+    the device path's answer, for pinned and pageable host memory, with NULL slab pointers
+    (already resident) and on two slots/streams at once."""
+    N, E, D, bs, k = 4000, 40_000, 8, 100, 12
+    src, dst, t, x = _random_stream(3, N, E, 1500, D)
+    dg, csr = _store_and_csr(src, dst, t, x, bs, False, True)
+    lo, hi = 20_000, 26_000
+    want = [v.cpu() for v in csr.sample_edges(lo, hi, k, k)]
+    n = 2 * (hi - lo)
+    host_in = tuple(torch.from_numpy(np.ascontiguousarray(a[lo:hi])) for a in (src, dst, t, x))
+    for pinned in (False, True):
+        for slab in (host_in, (None, None, None, None)):
+            out = (torch.full((n, k), -7, dtype=torch.int32), torch.full((n, k), -7, dtype=torch.int64),
+                   torch.full((n, k, D), -7.0))
+            if pinned:
+                out = tuple(o.pin_memory() for o in out)
+                slab = tuple(None if s is None else s.pin_memory() for s in slab)
+            csr.sample_edges_host(lo, hi, k, k, slab, out)
+            torch.cuda.synchronize()
+            for g_, w_ in zip(out, want):
+                assert torch.equal(g_, w_)
+    s1, s2 = torch.cuda.Stream(DEV), torch.cuda.Stream(DEV)
+    outs = [tuple(o.pin_memory() for o in (torch.empty((n, k), dtype=torch.int32),
+                                           torch.empty((n, k), dtype=torch.int64),
+                                           torch.empty((n, k, D)))) for _ in range(2)]
+    for _ in range(3):
+        csr.sample_edges_host(lo, hi, k, k, host_in, outs[0], slot=0, stream=s1.cuda_stream)
+        csr.sample_edges_host(lo, hi, k, k, host_in, outs[1], slot=1, stream=s2.cuda_stream)
+    s1.synchronize(), s2.synchronize()
+    for o in outs:
+        for g_, w_ in zip(o, want):
+            assert torch.equal(g_, w_)
+    with pytest.raises(_cabi.TGMNativeError, match='bad slot'):
+        csr.sample_edges_host(lo, hi, k, k, host_in, outs[0], slot=99)
+
+
+def test_time_unit_batches_run_through_the_hook():
+    """batch_unit='s' (tgm/data/loader.py:101-156): batches are time windows of unequal size, so a
+    windowed hook leaves its window on the first irregular batch and continues on the ring
+    kernels; outputs equal the oracle driven with the same batches."""
+    N, D, nn = 200, 3, [5]
+    src, dst, t, x = _random_stream(9, N, 3000, 600, D)
+    ei = torch.from_numpy(np.stack([src, dst], 1))
+    dg = DGraph(DGData.from_raw(torch.from_numpy(t), ei, torch.from_numpy(x), time_delta='s'),
+                device=DEV)
+    for window in (0, 50):
+        hook = RecencyNeighborHook(num_nodes=N, num_nbrs=nn, seed_nodes_keys=['edge_src', 'edge_dst'],
+                                   seed_times_keys=['edge_time', 'edge_time'], window_batches=window)
+        hm = HookManager(keys=['g'])
+        hm.register('g', hook)
+        oracle = CRing(N, nn, D)
+        seen = 0
+        with hm.activate('g'):
+            for batch in DGDataLoader(dg, batch_size=7, batch_unit='s', hook_manager=hm):
+                n = batch.edge_src.numel()
+                lo, hi = seen, seen + n
+                assert batch.edge_time.cpu().tolist() == t[lo:hi].tolist()
+                seeds = np.concatenate([src[lo:hi], dst[lo:hi]])
+                tq = np.concatenate([t[lo:hi], t[lo:hi]])
+                want = oracle.hook_call(seeds, tq, src[lo:hi], dst[lo:hi], t[lo:hi], x[lo:hi])
+                got = (batch.seed_nids[0], batch.seed_times[0], batch.nbr_nids[0],
+                       batch.nbr_edge_time[0], batch.nbr_edge_x[0])
+                assert_hop_equal(to_np(got), want[0], f'window{window} edge{lo}')
+                seen = hi
+        assert seen == len(src)
