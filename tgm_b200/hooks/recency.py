@@ -176,7 +176,8 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
             return None
         csr, bs = w['csr'], w['bs']
         if hi > w['w_hi']:  # pre-sample the next window, one launch per hop
-            w['w_lo'], w['w_hi'] = lo, min(lo + self._window_batches * bs, store.num_edges)
+            nwin = min(self._window_batches, self._window_budget_batches(bs))
+            w['w_lo'], w['w_hi'] = lo, min(lo + nwin * bs, store.num_edges)
             w['hops'] = csr.sample_window(w['w_lo'], w['w_hi'], self._num_nbrs)
         # rows of this batch inside the window block, hop by hop
         a, b = 2 * (lo - w['w_lo']), 2 * (hi - w['w_lo'])
@@ -237,6 +238,17 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
             self.add_batch_attribute(batch, name, [p[i] for p in parts])
         self.add_batch_attribute(batch, 'seed_node_nbr_mask', mask)
         return batch
+
+    def _window_budget_batches(self, bs: int) -> int:
+        """How many batches fit the pre-sampling budget (a quarter of the free HBM, at most 16 GB):
+        multi-hop outputs grow as prod(k) -- 165 MB per batch for k=[20,20] at D=172."""
+        per_batch, seeds = 0, 2 * bs
+        for k in self._num_nbrs:
+            per_batch += seeds * k * (12 + 4 * self._edge_x_dim)
+            seeds *= k
+        free, _ = torch.cuda.mem_get_info(self._device)
+        budget = min(free // 4, 16 << 30)
+        return max(1, int(budget // max(per_batch, 1)))
 
     def _arange(self, a: int, b: int) -> Tensor:
         """View [a, b) of a cached device arange (seed_node_nbr_mask rows, recency.py:221-224);
