@@ -28,6 +28,8 @@ import sys
 import threading
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -429,7 +431,22 @@ def run_b200(a):
         warm = n_cpu // 3
         stream = tuple(None if v is None else v[:n_cpu].cpu().numpy() for v in (src, dst, t, x))
         v, s, dt = time_cpu_port(a, stream, n_cpu, warm)
+        # the numpy restatement follows the reference's eager tensor-op structure (gathers, masks,
+        # argsort) more closely than the C port does: reported beside it, on fewer batches
+        from oracle.recency_oracle import RingOracle
+        nb_np = 300
+        ring_np = RingOracle(N, [k], D)
+        lo_np = warm
+        t0 = time.perf_counter()
+        for b in range(nb_np):
+            lo_b, hi_b = lo_np + b * bs, lo_np + (b + 1) * bs
+            sd = np.concatenate([stream[0][lo_b:hi_b], stream[1][lo_b:hi_b]])
+            tq_ = np.concatenate([stream[2][lo_b:hi_b]] * 2)
+            ring_np.hook_call(sd, tq_, stream[0][lo_b:hi_b], stream[1][lo_b:hi_b],
+                              stream[2][lo_b:hi_b], None if D == 0 else stream[3][lo_b:hi_b])
+        np_rate = nb_np * 2 * bs * k / (time.perf_counter() - t0)
         cpu = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'host_cores': os.cpu_count(),
+               'numpy_port_value': np_rate,
                'sample': f'edges [{warm}, {n_cpu}) of the same stream ({s} sampled edges, '
                          f'{dt:.1f} s) after pushing the first {warm}; C port of the '
                          f'reference ring sampler (oracle/recency_ring.c), batch by batch'}
