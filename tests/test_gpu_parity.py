@@ -716,3 +716,17 @@ def test_time_unit_batches_run_through_the_hook():
                 assert_hop_equal(to_np(got), want[0], f'window{window} edge{lo}')
                 seen = hi
         assert seen == len(src)
+
+
+def test_dgraph_to_cuda_uploads_a_host_side_graph():
+    """DGraph(data) defaults to the CPU like the reference (graph.py:58); there it is a
+    metadata-only view here (no CPU compute path), and .to('cuda') makes it usable."""
+    ei = torch.tensor([[0, 1], [1, 2], [2, 0]], dtype=torch.int32)
+    host = DGraph(DGData.from_raw(torch.tensor([1, 2, 3]), ei, torch.ones(3, 2)))
+    assert host.num_events == 3 and host.device.type == 'cpu'
+    with pytest.raises(_cabi.TGMNativeError):
+        host.edge_src
+    dg = host.slice_events(1, 3).to(DEV)
+    assert dg.device.type == 'cuda' and dg.edge_src.is_cuda
+    assert dg.edge_src.cpu().tolist() == [1, 2] and dg.edge_time.cpu().tolist() == [2, 3]
+    assert dg.edge_x.shape == (2, 2)

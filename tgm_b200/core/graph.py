@@ -76,8 +76,15 @@ class DGraph:
         return DGraph._from_storage(self._storage, self._time_delta, self._device, s)
 
     def to(self, device: 'str | torch.device') -> 'DGraph':
-        return DGraph._from_storage(self._storage, self._time_delta, torch.device(device),
-                                    replace(self._slice))
+        """View on another device (graph.py:169-181).  Moving a host-side (metadata-only) graph to
+        a CUDA device uploads the store once; the new view keeps the slice."""
+        device = torch.device(device)
+        storage = self._storage
+        if device.type == 'cuda' and getattr(storage, 'device', 'n/a') is None and \
+                getattr(storage, '_data', None) is not None:
+            storage = type(storage)(storage._data, device=device)
+            device = storage.device
+        return DGraph._from_storage(storage, self._time_delta, device, replace(self._slice))
 
     def materialize(self, materialize_features: bool = True) -> DGBatch:
         src, dst, time = self._edges
