@@ -730,3 +730,71 @@ def test_dgraph_to_cuda_uploads_a_host_side_graph():
     assert dg.device.type == 'cuda' and dg.edge_src.is_cuda
     assert dg.edge_src.cpu().tolist() == [1, 2] and dg.edge_time.cpu().tolist() == [2, 3]
     assert dg.edge_x.shape == (2, 2)
+
+
+def test_config1_wiki_shaped_epoch_is_index_exact():
+    """BASELINE configs[0]: tgbl-wiki-shaped stream (9,227 nodes, 157,474 edges, D=172,
+    t in [0, 2.68e6]), DGDataLoader batch_size=200, recent-neighbour hook k=10.  Every id, time
+    and feature of the whole epoch, from both the stateful and the windowed hook, is compared with
+    the C oracle through position-sensitive checksums (plus exact tensors on sampled batches)."""
+    rng = np.random.default_rng(0)
+    E, N, D, bs, k = 157_474, 9227, 172, 200, 10
+    src = rng.integers(0, 8227, E).astype(np.int32)
+    dst = rng.integers(8227, N, E).astype(np.int32)
+    t = np.sort(rng.integers(0, 2_678_374, E)).astype(np.int64)
+    x = rng.standard_normal((E, D)).astype(np.float32)
+    assert N * (int(t.max()) + 1) >= 2 ** 31  # outside the reference's int32-key domain (H1):
+    # the oracle computes the ideal semantics, i.e. the reference with node_ids.long()
+    oracle = CRing(N, [k], D)
+    slots, want, hop0 = oracle.run_stream(src, dst, t, x, 0, E, bs, keep_hop0=True)
+    dg = DGraph(DGData.from_raw(torch.from_numpy(t), torch.from_numpy(np.stack([src, dst], 1)),
+                                torch.from_numpy(x)), device=DEV)
+    for window in (0, 100):
+        hook = RecencyNeighborHook(num_nodes=N, num_nbrs=[k], seed_nodes_keys=['edge_src', 'edge_dst'],
+                                   seed_times_keys=['edge_time', 'edge_time'], window_batches=window)
+        hm = HookManager(keys=['g'])
+        hm.register('g', hook)
+        got, rows = [0, 0, 0], 0
+        with hm.activate('g'):
+            for b, batch in enumerate(DGDataLoader(dg, batch_size=bs, hook_manager=hm)):
+                nid, nt, nx = batch.nbr_nids[0], batch.nbr_edge_time[0], batch.nbr_edge_x[0]
+                base = rows * k
+                got[0] += torch_checksum(nid, base)
+                got[1] += torch_checksum(nt, base)
+                got[2] += torch_checksum(nx, base * D)
+                if b % 97 == 0:
+                    a, e = rows, rows + nid.shape[0]
+                    assert np.array_equal(nid.cpu().numpy(), hop0[0][a:e])
+                    assert np.array_equal(nt.cpu().numpy(), hop0[1][a:e])
+                    assert np.array_equal(nx.cpu().numpy(), hop0[2][a:e])
+                rows += nid.shape[0]
+        assert rows * k == slots == 2 * E * k
+        assert [v % (1 << 64) for v in got] == [int(v) for v in want[0]], f'window={window}'
+
+
+def test_realistic_timestamps_r_domain():
+    """SURVEY section 8d R-domain: ~unique timestamps up to 2^31 - 2 (unix-epoch scale).  The
+    reference's int32 sort key overflows there; the CUDA paths must follow the ideal semantics
+    (the C oracle / the reference with node_ids.long())."""
+    rng = np.random.default_rng(4)
+    N, E, D, bs, nn = 20_000, 120_000, 4, 200, [20, 4]
+    src, dst = rng.integers(0, N, E).astype(np.int32), rng.integers(0, N, E).astype(np.int32)
+    t = np.sort(rng.integers(0, 2 ** 31 - 2, E)).astype(np.int64)
+    x = rng.standard_normal((E, D)).astype(np.float32)
+    oracle, ring = CRing(N, nn, D), Ring(N, max(nn), D)
+    dg, csr = _store_and_csr(src, dst, t, x, bs, False, True)
+    hops = csr.sample_window(0, E, nn)
+    dsrc, ddst, dt, dx = (dev(src, torch.int32), dev(dst, torch.int32), dev(t, torch.int64),
+                          dev(x, torch.float32))
+    for b, (lo, hi, views) in enumerate(csr.split_window(hops, 0, E)):
+        s = np.concatenate([src[lo:hi], dst[lo:hi]])
+        q = np.concatenate([t[lo:hi], t[lo:hi]])
+        want = oracle.hook_call(s, q, src[lo:hi], dst[lo:hi], t[lo:hi], x[lo:hi])
+        got_ring = ring_hook_call(ring, nn, dev(s, torch.int32), dev(q, torch.int64), dsrc[lo:hi],
+                                  ddst[lo:hi], dt[lo:hi], dx[lo:hi], False)
+        if b % 41 == 0 or hi == E:
+            for h, w in enumerate(want):
+                v = views[h]
+                assert_hop_equal(to_np((v.seed_nids, v.seed_times, v.nbr_nids, v.nbr_edge_time,
+                                        v.nbr_edge_x)), w, f'csr batch{b} hop{h}')
+                assert_hop_equal(to_np(got_ring[h]), w, f'ring batch{b} hop{h}')
