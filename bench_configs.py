@@ -155,6 +155,7 @@ def config5(a, dev, rank, world):
 
 
 def main():
+    torch.set_grad_enabled(False)  # forward pipelines
     ap = argparse.ArgumentParser()
     ap.add_argument('--config', type=int, required=True, choices=[3, 5])
     ap.add_argument('--batches', type=int, default=200)

@@ -279,6 +279,7 @@ def row_tgat():
         hop[h] = (seeds, stt, nid, nt, ex)
     dv = lambda i: [torch.from_numpy(np.ascontiguousarray(hop[h][i])).to(DEV) for h in range(2)]
     args = (node_x, dv(0), dv(1), dv(2), dv(4), dv(3))
+    torch.set_grad_enabled(False)  # inference rows: keep autograd out of the timings
     ms = cuda_ms(lambda: model(*args), iters=10)
     att = model.attn[0]
     a1 = (model.time_encoder, torch.randn(sizes[1], 1, device=DEV), torch.randn(sizes[1], k, 1, device=DEV),

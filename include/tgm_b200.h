@@ -224,6 +224,10 @@ int tgm_attn_create(tgm_attn **out, int32_t n_heads, int32_t node_dim, int32_t e
                     int32_t time_dim, const float *W_Q, const float *W_KV, const float *W_O,
                     const float *b_O, const float *ln_w, const float *ln_b, float ln_eps,
                     const float *t2v_w, const float *t2v_b, int device);
+/* Refresh the parameter copies in place (after an optimizer step), stream-ordered. */
+int tgm_attn_set_params(tgm_attn *, const float *W_Q, const float *W_KV, const float *W_O,
+                        const float *b_O, const float *ln_w, const float *ln_b,
+                        const float *t2v_w, const float *t2v_b, tgm_stream stream);
 void tgm_attn_destroy(tgm_attn *);
 int tgm_attn_out_dim(const tgm_attn *);
 /* node_x float32[S,node_dim]; nbr_node_feat float32[S,k,node_dim]; edge_feat float32[S,k,edge_dim];
@@ -240,6 +244,20 @@ int tgm_attn_forward_feats(tgm_attn *, const float *node_x, const float *time_fe
                            const float *edge_feat, const float *nbr_node_feat,
                            const float *nbr_time_feat, const int32_t *nbr_id, int64_t S, int32_t k,
                            float *out, tgm_stream stream);
+/* Backward of tgm_attn_forward (what autograd computes through attention.py:58-128 and the two
+ * Time2Vec calls of tgat.py:141-146).  d_out float32[S,out] is the gradient of the output.  Input
+ * gradients are WRITTEN: d_node_x float32[S,node_dim], d_nbr_node_feat float32[S,k,node_dim]
+ * (nullable), d_edge_feat float32[S,k,edge_dim] (nullable).  Parameter gradients are ACCUMULATED
+ * (+=) into dW_Q [out,out], dW_KV [2*out,key], dW_O [out,out], db_O, dln_w, dln_b [out], dt2v_w,
+ * dt2v_b [time_dim] (device pointers, torch layouts), so they can alias .grad buffers.  The
+ * forward intermediates are recomputed internally; the handle must hold the same parameters the
+ * forward used.  Masked slots carry no logit gradient (their logit is the constant -1e10). */
+int tgm_attn_backward(tgm_attn *, const float *node_x, const float *nbr_node_feat,
+                      const float *edge_feat, const int64_t *seed_t, const int64_t *nbr_t,
+                      const int32_t *nbr_id, int64_t S, int32_t k, const float *d_out,
+                      float *d_node_x, float *d_nbr_node_feat, float *d_edge_feat, float *dW_Q,
+                      float *dW_KV, float *dW_O, float *db_O, float *dln_w, float *dln_b,
+                      float *dt2v_w, float *dt2v_b, tgm_stream stream);
 /* MergeLayer (tgat.py:11-38): out = fc2(relu(fc1(cat[x1, x2]))); W1 [hidden, in1+in2], W2
  * [out, hidden].  x1 float32[S,in1], x2 float32[S,in2], out float32[S,out]. */
 int tgm_mlp2_create(tgm_mlp2 **out, int32_t in1, int32_t in2, int32_t hidden, int32_t out_dim,

@@ -236,3 +236,67 @@ def test_dygformer_vs_oracle_at_config5_dims():
     p = {k_: v.detach().cpu().numpy() for k_, v in m.state_dict().items()}
     ws, wd = nn_oracle.dygformer_forward(p, 1, 2, 2, node_x, np.stack([src, dst]), t, nbrs, nt, ef)
     assert np.abs(zs.cpu().numpy() - ws).max() <= TOL and np.abs(zd.cpu().numpy() - wd).max() <= TOL
+
+
+# ---- gradients: tgm_attn_backward vs the reference's autograd ------------------------------------
+def _close(got, want, what, rtol=2e-4):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else got
+    scale = max(1.0, float(np.abs(want).max()))
+    err = float(np.abs(got - want).max())
+    assert got.shape == want.shape and err <= rtol * scale, f'{what}: max err {err} (scale {scale})'
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'nn_attngrad_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[12:-4])
+def test_attention_gradients_match_reference_autograd(path):
+    """loss = sum(out * G): gradients of every parameter (incl. Time2Vec weight and bias, which
+    get contributions from both time encodings) and of the seed / neighbour / edge features."""
+    z = np.load(path)
+    att, te = _attn_from_fixture(z)
+    att.train()
+    att.dropout.p = 0.0
+    node_x = T(z['node_x']).requires_grad_(True)
+    nbr = T(z['nbr_feat']).requires_grad_(True)
+    edge = T(z['edge_feat']).requires_grad_(True)
+    out = att.forward_fused(te, node_x, nbr, edge, T(z['seed_t']), T(z['nbr_t']), T(z['nbr_id']))
+    _close(out, z['out'], 'forward', 1e-5)
+    (out * T(z['G'])).sum().backward()
+    _close(node_x.grad, z['d_node_x'], 'd node_x')
+    _close(nbr.grad, z['d_nbr_feat'], 'd nbr_feat')
+    _close(edge.grad, z['d_edge_feat'], 'd edge_feat')
+    for name, prm in att.named_parameters():
+        _close(prm.grad, z['g.' + name], name)
+    for name, prm in te.named_parameters():
+        _close(prm.grad, z['g.time_encoder.' + name], 'time_encoder.' + name)
+    # a second backward after an in-place parameter update uses the refreshed weights
+    with torch.no_grad():
+        att.W_O.bias.add_(1.0)
+    out2 = att.forward_fused(te, node_x, nbr, edge, T(z['seed_t']), T(z['nbr_t']), T(z['nbr_id']))
+    assert float((out2 - out).abs().max()) > 1e-3
+
+
+def test_tgat_gradients_match_reference_autograd():
+    z = np.load(os.path.join(GOLDEN_DIR, 'nn_tgatgrad_two_layer.npz'))
+    p = _params(z)
+    L, H = int(z['num_layers']), int(z['n_heads'])
+    model = TGAT(z['node_x'].shape[1], z['nbr_edge_x0'].shape[2], p['time_encoder.w.bias'].shape[0],
+                 p['merge_layers.0.fc2.bias'].shape[0], L, H, dropout=0.0)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+    model = model.to(DEV).train()
+    hop = lambda name: [T(z[f'{name}{h}']) for h in range(L)]
+    out = model(T(z['node_x']), hop('seed_nids'), hop('seed_times'), hop('nbr_nids'),
+                hop('nbr_edge_x'), hop('nbr_edge_time'))
+    _close(out, z['out'], 'forward', 1e-5)
+    (out * T(z['G'])).sum().backward()
+    for name, prm in model.named_parameters():
+        _close(prm.grad, z['g.' + name], name)
+
+
+def test_training_mode_with_dropout_is_refused():
+    att = TemporalAttention(2, 3, 4, 6).to(DEV).train()
+    te = Time2Vec(6).to(DEV)
+    with pytest.raises(RuntimeError, match='dropout=0'):
+        att.forward_fused(te, torch.zeros(2, 3, device=DEV), torch.zeros(2, 1, 3, device=DEV),
+                          torch.zeros(2, 1, 4, device=DEV), torch.zeros(2, dtype=torch.int64, device=DEV),
+                          torch.zeros(2, 1, dtype=torch.int64, device=DEV),
+                          torch.zeros(2, 1, dtype=torch.int32, device=DEV))

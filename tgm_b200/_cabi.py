@@ -82,12 +82,15 @@ SIGNATURES = {
     'tgm_attn_create': (c_int, [POINTER(c_void_p), c_int32, c_int32, c_int32, c_int32, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                 c_void_p, c_void_p, c_int]),
+    'tgm_attn_set_params': (c_int, [c_void_p] * 10),
     'tgm_attn_destroy': (None, [c_void_p]),
     'tgm_attn_out_dim': (c_int, [c_void_p]),
     'tgm_attn_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     'tgm_attn_forward_feats': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    'tgm_attn_backward': (c_int, [c_void_p] + [c_void_p] * 6 + [c_int64, c_int32] + [c_void_p] * 12 +
+                          [c_void_p]),
     'tgm_mlp2_create': (c_int, [POINTER(c_void_p), c_int32, c_int32, c_int32, c_int32, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_int]),
     'tgm_mlp2_destroy': (None, [c_void_p]),

@@ -25,26 +25,7 @@
 
 using namespace tgm;
 
-struct tgm_attn {
-  int device = -1;
-  int H = 0, node_dim = 0, edge_dim = 0, time_dim = 0, pad_dim = 0, out_dim = 0, hd = 0, key = 0;
-  float eps = 1e-5f;
-  // parameters (device copies)
-  float *Wq = nullptr, *Wkv = nullptr, *Wo = nullptr, *bo = nullptr, *lnw = nullptr, *lnb = nullptr;
-  float *tw = nullptr, *tb = nullptr;  // Time2Vec weight [time_dim], bias [time_dim]
-  float *t0 = nullptr;                 // Time2Vec(0) = cos(b)   [time_dim]
-  cublasHandle_t blas = nullptr;
-  // workspace, grown on demand (rows = seeds)
-  int64_t cap = 0;
-  float *R = nullptr, *Q = nullptr, *QK = nullptr, *U = nullptr, *O = nullptr, *Y = nullptr;
-  ~tgm_attn() {
-    if (device >= 0) {
-      DeviceGuard g(device);
-      for (float *p : {Wq, Wkv, Wo, bo, lnw, lnb, tw, tb, t0, R, Q, QK, U, O, Y}) cudaFree(p);
-      if (blas) cublasDestroy(blas);
-    }
-  }
-};
+#include "attention.cuh"
 
 struct tgm_mlp2 {
   int device = -1;
@@ -318,11 +299,34 @@ extern "C" int tgm_attn_create(tgm_attn **out, int32_t n_heads, int32_t node_dim
   return TGM_OK;
 }
 
+extern "C" int tgm_attn_set_params(tgm_attn *a, const float *W_Q, const float *W_KV,
+                                   const float *W_O, const float *b_O, const float *ln_w,
+                                   const float *ln_b, const float *t2v_w, const float *t2v_b,
+                                   tgm_stream stream) {
+  TGM_REQUIRE(a != nullptr, "tgm_attn_set_params: handle is NULL");
+  TGM_REQUIRE(W_Q && W_KV && W_O && b_O && ln_w && ln_b && t2v_w && t2v_b,
+              "tgm_attn_set_params: NULL parameter");
+  DeviceGuard g(a->device);
+  cudaStream_t st = as_stream(stream);
+  const size_t o = size_t(a->out_dim), kd = size_t(a->key), td = size_t(a->time_dim);
+  TGM_CUDA(cudaMemcpyAsync(a->Wq, W_Q, o * o * 4, cudaMemcpyDefault, st));
+  TGM_CUDA(cudaMemcpyAsync(a->Wkv, W_KV, 2 * o * kd * 4, cudaMemcpyDefault, st));
+  TGM_CUDA(cudaMemcpyAsync(a->Wo, W_O, o * o * 4, cudaMemcpyDefault, st));
+  TGM_CUDA(cudaMemcpyAsync(a->bo, b_O, o * 4, cudaMemcpyDefault, st));
+  TGM_CUDA(cudaMemcpyAsync(a->lnw, ln_w, o * 4, cudaMemcpyDefault, st));
+  TGM_CUDA(cudaMemcpyAsync(a->lnb, ln_b, o * 4, cudaMemcpyDefault, st));
+  TGM_CUDA(cudaMemcpyAsync(a->tw, t2v_w, td * 4, cudaMemcpyDefault, st));
+  TGM_CUDA(cudaMemcpyAsync(a->tb, t2v_b, td * 4, cudaMemcpyDefault, st));
+  cos_kernel<<<(a->time_dim + 127) / 128, 128, 0, st>>>(a->tb, a->time_dim, a->t0);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+
 extern "C" void tgm_attn_destroy(tgm_attn *a) { delete a; }
 
 extern "C" int tgm_attn_out_dim(const tgm_attn *a) { return a ? a->out_dim : TGM_ERR_INVALID; }
 
-static int attn_forward_impl(tgm_attn *a, const float *node_x, const float *nbr_node_feat,
+int attn_forward_impl(tgm_attn *a, const float *node_x, const float *nbr_node_feat,
                              const float *edge_feat, const int64_t *seed_t, const int64_t *nbr_t,
                              const float *seed_tf, const float *nbr_tf, const int32_t *nbr_id,
                              int64_t S, int32_t k, float *out, tgm_stream stream) {

@@ -2,9 +2,11 @@
 
 Same constructors, parameter names/shapes and forward signatures as the reference
 (tgm/nn/modules/time_encoding.py:6-24, tgm/nn/modules/attention.py:5-128,
-tgm/nn/encoder/tgat.py:11-38).  Forward only (inference / evaluation: dropout is the identity);
-the computation runs in `tgm_attn_forward` / `tgm_mlp2_forward` / `tgm_time2vec`.  There is no
-CPU path: parameters must live on a CUDA device when forward is called.
+tgm/nn/encoder/tgat.py:11-38).  The computation runs in `tgm_attn_forward` / `tgm_mlp2_forward` /
+`tgm_time2vec`; `TemporalAttention.forward_fused` is differentiable (`tgm_attn_backward` behind a
+torch.autograd.Function) for every parameter, the seed features and the neighbour features, with
+dropout 0 (a dropout mask cannot match the reference's RNG stream anyway).  There is no CPU path:
+parameters must live on a CUDA device when forward is called.
 """
 from __future__ import annotations
 
@@ -51,6 +53,47 @@ class _NativeHandle:
 
 def _version(params) -> tuple:
     return tuple((p.data_ptr(), p._version, str(p.device)) for p in params)
+
+
+class _FusedAttention(torch.autograd.Function):
+    """tgm_attn_forward / tgm_attn_backward as one differentiable op.  The parameters are passed
+    explicitly so autograd routes their gradients; the C handle recomputes the forward
+    intermediates in backward, so nothing but the inputs is saved."""
+
+    @staticmethod
+    def forward(ctx, module, te, seed_times, nbr_times, nbr_nids, node_x, nbr_node_feat, edge_feat,
+                *params):
+        dev = node_x.device
+        S, k = nbr_nids.shape
+        args = [_f32(node_x), _f32(nbr_node_feat), _f32(edge_feat),
+                seed_times.to(torch.int64).contiguous(), nbr_times.to(torch.int64).contiguous(),
+                nbr_nids.to(torch.int32).contiguous()]
+        out = torch.empty((S, module.out_dim), dtype=torch.float32, device=dev)
+        _cabi.check(_cabi.lib.tgm_attn_forward(
+            module._handle(te, dev), *[a.data_ptr() for a in args], S, k, out.data_ptr(),
+            _cabi.current_stream(dev)))
+        ctx.module, ctx.te, ctx.args = module, te, args
+        ctx.need = (node_x.requires_grad, nbr_node_feat.requires_grad, edge_feat.requires_grad)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        module, te, args = ctx.module, ctx.te, ctx.args
+        dev = d_out.device
+        S, k = args[5].shape
+        d_out = _f32(d_out)
+        od, key, td = module.out_dim, module.node_dim + module.edge_dim + module.time_dim, module.time_dim
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+        d_x = z(S, module.node_dim)
+        d_nbr = z(S, k, module.node_dim) if ctx.need[1] else None
+        d_edge = z(S, k, module.edge_dim) if ctx.need[2] else None
+        gp = [z(od, od), z(2 * od, key), z(od, od), z(od), z(od), z(od), z(td), z(td)]
+        _cabi.check(_cabi.lib.tgm_attn_backward(
+            module._handle(te, dev), *[a.data_ptr() for a in args], S, k, d_out.data_ptr(),
+            d_x.data_ptr(), _cabi.ptr(d_nbr), _cabi.ptr(d_edge), *[g.data_ptr() for g in gp],
+            _cabi.current_stream(dev)))
+        gp[6] = gp[6].reshape(td, 1)  # Time2Vec weight is Linear(1, d).weight
+        return (None, None, None, None, None, d_x if ctx.need[0] else None, d_nbr, d_edge, *gp)
 
 
 class Time2Vec(nn.Module):
@@ -112,11 +155,21 @@ class TemporalAttention(nn.Module):
                   self.layer_norm.weight, self.layer_norm.bias, time_encoder.w.weight,
                   time_encoder.w.bias]
         ver = _version(params)
-        if self._native.version != ver:
+        if self._native.version != ver and self._native.h.value and \
+                getattr(self, '_native_dev', None) == dev:
+            # same shapes, new values (optimizer step): refresh the copies in place
+            t = [_f32(p) for p in params]
+            _cabi.check(_cabi.lib.tgm_attn_set_params(
+                self._native.h, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(),
+                t[4].data_ptr(), t[5].data_ptr(), t[6].reshape(-1).data_ptr(), t[7].data_ptr(),
+                _cabi.current_stream(dev)))
+            self._native.version = ver
+        elif self._native.version != ver:
             self._native.free()
             for p in params:
                 _need_cuda(p, 'TemporalAttention parameters')
             t = [_f32(p) for p in params]
+            self._native_dev = dev
             _cabi.check(_cabi.lib.tgm_attn_create(
                 ctypes.byref(self._native.h), self.n_heads, self.node_dim, self.edge_dim,
                 self.time_dim, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(),
@@ -149,15 +202,29 @@ class TemporalAttention(nn.Module):
             object.__setattr__(self, '_te', Time2Vec(self.time_dim).to(dev))
         return self._te
 
-    @torch.no_grad()
     def forward_fused(self, time_encoder: Time2Vec, node_x: Tensor, nbr_node_feat: Tensor,
                       edge_feat: Tensor, seed_times: Tensor, nbr_times: Tensor,
                       nbr_nids: Tensor) -> Tensor:
         """attention.py:58-128 with the Time2Vec calls of tgat.py:141-146 folded in: the time
-        features are computed inside the kernel from (seed_times, nbr_times)."""
+        features are computed inside the kernel from (seed_times, nbr_times).  Differentiable
+        when autograd is recording (dropout must be 0 in training mode)."""
         if self.training and self.dropout.p > 0:
-            raise RuntimeError('TemporalAttention on the B200 path is forward/eval only')
+            raise RuntimeError('TemporalAttention on the B200 path trains with dropout=0 only '
+                               '(use eval() for inference)')
         dev = _need_cuda(node_x, 'TemporalAttention')
+        params = [self.W_Q.weight, self.W_KV.weight, self.W_O.weight, self.W_O.bias,
+                  self.layer_norm.weight, self.layer_norm.bias, time_encoder.w.weight,
+                  time_encoder.w.bias]
+        if torch.is_grad_enabled() and any(
+                t.requires_grad for t in (*params, node_x, nbr_node_feat, edge_feat)):
+            return _FusedAttention.apply(self, time_encoder, seed_times, nbr_times, nbr_nids,
+                                         node_x, nbr_node_feat, edge_feat, *params)
+        with torch.no_grad():
+            return self._forward_fused_nograd(time_encoder, node_x, nbr_node_feat, edge_feat,
+                                              seed_times, nbr_times, nbr_nids, dev)
+
+    def _forward_fused_nograd(self, time_encoder, node_x, nbr_node_feat, edge_feat, seed_times,
+                              nbr_times, nbr_nids, dev) -> Tensor:
         S, k = nbr_nids.shape
         out = torch.empty((S, self.out_dim), dtype=torch.float32, device=dev)
         args = [_f32(node_x), _f32(nbr_node_feat), _f32(edge_feat),
@@ -179,10 +246,17 @@ class MergeLayer(nn.Module):
         self.fc2 = nn.Linear(hidden_dim, output_dim)
         self._native = _NativeHandle(_cabi.lib.tgm_mlp2_destroy)
 
-    @torch.no_grad()
     def forward(self, x1: Tensor, x2: Tensor) -> Tensor:
         dev = _need_cuda(x1, 'MergeLayer')
         params = [self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias]
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (*params, x1, x2)):
+            # two plain Linear layers: when autograd is recording they run as cuBLAS GEMMs
+            # through torch (plain library GEMMs either way), which supplies their backward
+            return self.fc2(self.fc1(torch.cat([x1, x2], dim=1)).relu())
+        with torch.no_grad():
+            return self._forward_nograd(x1, x2, dev, params)
+
+    def _forward_nograd(self, x1: Tensor, x2: Tensor, dev, params) -> Tensor:
         ver = _version(params)
         if self._native.version != ver:
             self._native.free()
@@ -204,6 +278,8 @@ class MergeLayer(nn.Module):
 def gather_rows(table: Tensor, ids: Tensor) -> Tensor:
     """table[ids] with torch's negative indexing (tgat.py:131-134), via tgm_gather_rows."""
     dev = _need_cuda(table, 'gather_rows')
+    if torch.is_grad_enabled() and table.requires_grad:  # learnable node features: let autograd
+        return table[ids.to(device=dev, dtype=torch.int64)]  # scatter the gradient rows
     table = _f32(table)
     ids = ids.to(device=dev, dtype=torch.int32).contiguous()
     out = torch.empty((ids.numel(), table.shape[1]), dtype=torch.float32, device=dev)

@@ -12,7 +12,8 @@ from tgm_b200.nn.attention import MergeLayer, TemporalAttention, Time2Vec, gathe
 
 
 class TGAT(nn.Module):
-    """Temporal Graph Attention Network (forward / evaluation only)."""
+    """Temporal Graph Attention Network.  Differentiable end to end (attention layers through
+    tgm_attn_backward, merge layers through torch's Linear) with dropout 0."""
 
     def __init__(self, node_dim: int, edge_dim: int, time_dim: int, embed_dim: int,
                  num_layers: int, n_heads: int = 2, dropout: float = 0.1) -> None:
@@ -28,7 +29,6 @@ class TGAT(nn.Module):
                 in_dim1=self.attn[-1].out_dim, in_dim2=node_dim, hidden_dim=embed_dim,
                 output_dim=embed_dim))
 
-    @torch.no_grad()
     def forward(self, node_x: Tensor, seed_nids: List[Tensor], seed_times: List[Tensor],
                 nbr_nids: List[Tensor], nbr_edge_x: List[Tensor],
                 nbr_edge_time: List[Tensor]) -> Tensor:
