@@ -52,14 +52,14 @@ def test_attention_matches_reference_fixture(path):
     out = att.forward_fused(te, T(z['node_x']), T(z['nbr_feat']), T(z['edge_feat']), T(z['seed_t']),
                             T(z['nbr_t']), T(z['nbr_id']))
     assert out.shape == z['out'].shape and out.dtype == torch.float32
-    assert np.abs(out.cpu().numpy() - z['out']).max() <= TOL
+    assert np.abs(out.detach().cpu().numpy() - z['out']).max() <= TOL
     # the reference signature with caller-supplied time features gives the same answer
     S = z['node_x'].shape[0]
     tf0 = te(torch.zeros(S, dtype=torch.int64, device=DEV))
     tfn = te(T(z['seed_t'])[:, None] - T(z['nbr_t']))
     out2 = att(T(z['node_x']), tf0, T(z['edge_feat']), T(z['nbr_feat']), tfn, T(z['nbr_id']) != -1,
                time_encoder=te)
-    assert np.abs(out2.cpu().numpy() - z['out']).max() <= TOL
+    assert np.abs(out2.detach().cpu().numpy() - z['out']).max() <= TOL
 
 
 @pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'nn_tgat_*.npz'))),
@@ -76,7 +76,7 @@ def test_tgat_matches_reference_fixture(path):
     hop = lambda name: [T(z[f'{name}{h}']) for h in range(L)]
     out = model(T(z['node_x']), hop('seed_nids'), hop('seed_times'), hop('nbr_nids'),
                 hop('nbr_edge_x'), hop('nbr_edge_time'))
-    assert np.abs(out.cpu().numpy() - z['out']).max() <= TOL
+    assert np.abs(out.detach().cpu().numpy() - z['out']).max() <= TOL
 
 
 def test_attention_vs_oracle_on_a_wiki_sized_batch():
@@ -104,7 +104,7 @@ def test_attention_vs_oracle_on_a_wiki_sized_batch():
     want = nn_oracle.temporal_attention(
         p, '', H, node_x, nn_oracle._t2v(p, 'time_encoder.', np.zeros(S, np.int64)), edge_feat,
         nbr_feat, nn_oracle._t2v(p, 'time_encoder.', seed_t[:, None] - nbr_t), nbr_id != -1)
-    assert np.abs(out.cpu().numpy() - want).max() <= TOL
+    assert np.abs(out.detach().cpu().numpy() - want).max() <= TOL
 
 
 def test_attention_requires_cuda_and_eval():
@@ -149,14 +149,14 @@ def test_tgn_memory_matches_reference_fixture(path):
         hi = min(lo + bs, E)
         if b == eval_from:
             mem.eval()
-            assert np.abs(mem.memory.cpu().numpy() - z['flush_memory']).max() <= TOL
-            assert np.array_equal(mem.last_update.cpu().numpy(), z['flush_last_update'])
+            assert np.abs(mem.memory.detach().cpu().numpy() - z['flush_memory']).max() <= TOL
+            assert np.array_equal(mem.last_update.detach().cpu().numpy(), z['flush_last_update'])
         zz, lu = mem(T(z[f'b{b}_nid']))
-        assert np.abs(zz.cpu().numpy() - z[f'b{b}_z']).max() <= TOL, b
-        assert np.array_equal(lu.cpu().numpy(), z[f'b{b}_lu']), b
+        assert np.abs(zz.detach().cpu().numpy() - z[f'b{b}_z']).max() <= TOL, b
+        assert np.array_equal(lu.detach().cpu().numpy(), z[f'b{b}_lu']), b
         mem.update_state(T(z['src'][lo:hi]), T(z['dst'][lo:hi]), T(z['t'][lo:hi]), T(z['x'][lo:hi]))
-    assert np.abs(mem.memory.cpu().numpy() - z['final_memory']).max() <= TOL
-    assert np.array_equal(mem.last_update.cpu().numpy(), z['final_last_update'])
+    assert np.abs(mem.memory.detach().cpu().numpy() - z['final_memory']).max() <= TOL
+    assert np.array_equal(mem.last_update.detach().cpu().numpy(), z['final_last_update'])
 
 
 def test_tgn_memory_vs_oracle_longer_stream():
@@ -177,13 +177,13 @@ def test_tgn_memory_vs_oracle_longer_stream():
         n_id = np.unique(np.concatenate([src[lo:hi], dst[lo:hi], rng.integers(0, N, 50)]))
         zz, lu = mem(T(n_id))
         wz, wlu = oracle.forward(n_id)
-        assert np.abs(zz.cpu().numpy() - wz).max() <= TOL and np.array_equal(lu.cpu().numpy(), wlu)
+        assert np.abs(zz.detach().cpu().numpy() - wz).max() <= TOL and np.array_equal(lu.detach().cpu().numpy(), wlu)
         mem.update_state(T(src[lo:hi]), T(dst[lo:hi]), T(t[lo:hi]), T(x[lo:hi]))
         oracle.update_state(src[lo:hi], dst[lo:hi], t[lo:hi], x[lo:hi])
     mem.eval()
     oracle.train(False)
-    assert np.abs(mem.memory.cpu().numpy() - oracle.memory).max() <= TOL
-    assert np.array_equal(mem.last_update.cpu().numpy(), oracle.last_update)
+    assert np.abs(mem.memory.detach().cpu().numpy() - oracle.memory).max() <= TOL
+    assert np.array_equal(mem.last_update.detach().cpu().numpy(), oracle.last_update)
 
 
 # ---- DyGFormer ---------------------------------------------------------
@@ -211,8 +211,8 @@ def test_dygformer_matches_reference_fixture(path):
                          int(z['num_heads']), L)
     zs, zd = m(T(z['node_x']), T(np.stack([z['src'], z['dst']])), T(z['t']), T(z['nbrs']),
                T(z['nt']), T(z['ef']))
-    assert np.abs(zs.cpu().numpy() - z['z_src']).max() <= TOL
-    assert np.abs(zd.cpu().numpy() - z['z_dst']).max() <= TOL
+    assert np.abs(zs.detach().cpu().numpy() - z['z_src']).max() <= TOL
+    assert np.abs(zd.detach().cpu().numpy() - z['z_dst']).max() <= TOL
 
 
 def test_dygformer_vs_oracle_at_config5_dims():
@@ -235,7 +235,7 @@ def test_dygformer_vs_oracle_at_config5_dims():
     zs, zd = m(T(node_x), T(np.stack([src, dst])), T(t), T(nbrs), T(nt), T(ef))
     p = {k_: v.detach().cpu().numpy() for k_, v in m.state_dict().items()}
     ws, wd = nn_oracle.dygformer_forward(p, 1, 2, 2, node_x, np.stack([src, dst]), t, nbrs, nt, ef)
-    assert np.abs(zs.cpu().numpy() - ws).max() <= TOL and np.abs(zd.cpu().numpy() - wd).max() <= TOL
+    assert np.abs(zs.detach().cpu().numpy() - ws).max() <= TOL and np.abs(zd.detach().cpu().numpy() - wd).max() <= TOL
 
 
 # ---- gradients: tgm_attn_backward vs the reference's autograd ------------------------------------
