@@ -337,6 +337,31 @@ int tgm_dyg_forward(tgm_dyg *, const float *node_x, int64_t num_nodes, const int
                     const int64_t *nbr_t, const float *nbr_x, int64_t B, float *out_src,
                     float *out_dst, tgm_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * TGN embedding.  Replaces GraphAttentionEmbedding (tgm/nn/encoder/tgn.py:14-40) as called from
+ * examples/linkproppred/tgn.py:74-98: rel_t = last_update[edge_src] - t, edge_attr =
+ * [Time2Vec(rel_t) | msg], then torch_geometric's TransformerConv(in_channels, out_channels/heads,
+ * heads, edge_dim = msg_dim + time_dim) -- third-party arithmetic (torch-geometric 2.6.1, not
+ * vendored, reference tests shape-only): restated from the published algorithm, PARITY UNPINNED.
+ * Eval-mode forward (attention dropout = identity).  Weights in torch layout [out, in]; out_channels
+ * is the full output width (heads * per-head channels); W_edge [out_channels, time_dim + msg_dim]
+ * with the time-encoding columns first (tgn.py:39); pointers may be host or device (copied).
+ */
+typedef struct tgm_gae tgm_gae;
+int tgm_gae_create(tgm_gae **out, int32_t in_channels, int32_t out_channels, int32_t heads,
+                   int32_t msg_dim, int32_t time_dim, const float *W_query, const float *b_query,
+                   const float *W_key, const float *b_key, const float *W_value,
+                   const float *b_value, const float *W_edge, const float *W_skip,
+                   const float *b_skip, const float *t2v_w, const float *t2v_b, int device);
+void tgm_gae_destroy(tgm_gae *);
+/* x f32[n,in_channels], last_update int64[n] (TGNMemory.forward's outputs for the batch's unique
+ * nodes); edge_src,edge_dst int64[m] = edge_index rows (LOCAL indices in [0,n): messages flow
+ * edge_src -> edge_dst and are normalised per edge_dst), t int64[m], msg f32[m,msg_dim];
+ * out f32[n,out_channels].  Nodes without incoming edges get the skip projection only. */
+int tgm_gae_forward(tgm_gae *, const float *x, const int64_t *last_update, int64_t n,
+                    const int64_t *edge_src, const int64_t *edge_dst, const int64_t *t,
+                    const float *msg, int64_t m, float *out, tgm_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -269,10 +269,11 @@ def test_attention_gradients_match_reference_autograd(path):
     for name, prm in te.named_parameters():
         _close(prm.grad, z['g.time_encoder.' + name], 'time_encoder.' + name)
     # a second backward after an in-place parameter update uses the refreshed weights
+    # (a uniform bias shift would be removed by the LayerNorm, so scale W_O instead)
     with torch.no_grad():
-        att.W_O.bias.add_(1.0)
+        att.W_O.weight.mul_(1.5)
     out2 = att.forward_fused(te, node_x, nbr, edge, T(z['seed_t']), T(z['nbr_t']), T(z['nbr_id']))
-    assert float((out2 - out).abs().max()) > 1e-3
+    assert float((out2 - out).detach().abs().max()) > 1e-3
 
 
 def test_tgat_gradients_match_reference_autograd():
@@ -300,3 +301,63 @@ def test_training_mode_with_dropout_is_refused():
                           torch.zeros(2, 1, 4, device=DEV), torch.zeros(2, dtype=torch.int64, device=DEV),
                           torch.zeros(2, 1, dtype=torch.int64, device=DEV),
                           torch.zeros(2, 1, dtype=torch.int32, device=DEV))
+
+
+# ---- TGN embedding (parity UNPINNED: torch_geometric is third-party) -----
+from oracle.tgn_oracle import graph_attention_embedding  # noqa: E402
+from tgm_b200.nn import GraphAttentionEmbedding  # noqa: E402
+
+
+def _gae_case(rng, n, m, M, Z, D, TD, hub=True):
+    torch.manual_seed(3)
+    te = Time2Vec(TD)
+    enc = GraphAttentionEmbedding(in_channels=M, out_channels=Z, msg_dim=D, time_enc=te).to(DEV).eval()
+    p = {k: v.detach().cpu().numpy() for k, v in enc.state_dict().items()}
+    x = rng.standard_normal((n, M)).astype(np.float32)
+    lu = rng.integers(0, 2_000_000, n)
+    src = rng.integers(0, n, m)
+    dst = rng.integers(0, max(1, n // 2), m)  # the upper half of the nodes has no incoming edge
+    if hub and m > 10:
+        dst[: m // 4] = 3  # one node with a quarter of all edges
+    t = rng.integers(0, 2_000_000, m)
+    msg = rng.standard_normal((m, D)).astype(np.float32)
+    return enc, p, x, lu, np.stack([src, dst]), t, msg
+
+
+@pytest.mark.parametrize('dims', [(700, 6000, 100, 100, 172, 100), (40, 300, 5, 100, 7, 2),
+                                  (33, 65, 8, 6, 0, 3)],
+                         ids=['tgn_example_wiki', 'reference_test_dims', 'no_msg_feats'])
+def test_graph_attention_embedding_vs_oracle(dims):
+    """examples/linkproppred/tgn.py:74-98 shapes: ~600 seeds x k=10 edges over the batch's unique
+    nodes, memory 100 -> embedding 100, msg 172, time 100, heads 2."""
+    n, m, M, Z, D, TD = dims
+    rng = np.random.default_rng(n)
+    enc, p, x, lu, ei, t, msg = _gae_case(rng, n, m, M, Z, D, TD)
+    out = enc(T(x), T(lu), T(ei), T(t), T(msg))
+    assert out.shape == (n, Z) and out.dtype == torch.float32
+    want = graph_attention_embedding(p, 2, x, lu, ei, t, msg)
+    assert np.abs(out.cpu().numpy() - want).max() <= TOL
+    # deterministic: same bits on a second call (edge-ordered accumulation, no atomics)
+    assert torch.equal(out, enc(T(x), T(lu), T(ei), T(t), T(msg)))
+
+
+def test_graph_attention_embedding_without_edges_is_the_skip_projection():
+    rng = np.random.default_rng(0)
+    enc, p, x, lu, ei, t, msg = _gae_case(rng, 50, 0, 16, 8, 4, 4)
+    out = enc(T(x), T(lu), T(ei), T(t), T(msg)).cpu().numpy()
+    want = x @ p['conv.lin_skip.weight'].T + p['conv.lin_skip.bias']
+    assert np.abs(out - want).max() <= TOL
+
+
+def test_graph_attention_embedding_state_dict_has_the_pyg_names_and_refuses_training():
+    enc = GraphAttentionEmbedding(100, 100, 172, Time2Vec(100))
+    assert set(enc.state_dict()) == {
+        'time_enc.w.weight', 'time_enc.w.bias', 'conv.lin_key.weight', 'conv.lin_key.bias',
+        'conv.lin_query.weight', 'conv.lin_query.bias', 'conv.lin_value.weight',
+        'conv.lin_value.bias', 'conv.lin_edge.weight', 'conv.lin_skip.weight', 'conv.lin_skip.bias'}
+    assert enc.conv.lin_edge.weight.shape == (100, 272)
+    enc = enc.to(DEV).train()
+    with pytest.raises(RuntimeError):
+        enc(torch.zeros(2, 100, device=DEV), torch.zeros(2, dtype=torch.int64, device=DEV),
+            torch.zeros(2, 0, dtype=torch.int64, device=DEV), torch.zeros(0, dtype=torch.int64, device=DEV),
+            torch.zeros(0, 172, device=DEV))

@@ -294,3 +294,59 @@ def test_dygformer_oracle_matches_reference_module(path):
         _params(z), int(z['patch_size']), int(z['num_layers']), int(z['num_heads']), z['node_x'],
         np.stack([z['src'], z['dst']]), z['t'], z['nbrs'], z['nt'], z['ef'])
     assert np.abs(zs - z['z_src']).max() <= 5e-6 and np.abs(zd - z['z_dst']).max() <= 5e-6
+
+
+# ---- GraphAttentionEmbedding / TransformerConv (parity UNPINNED: third-party arithmetic) -----------
+def _torch_transformer_conv(p, heads, x, ei, ea):
+    """Independent restatement in torch ops (scatter_reduce/index_add), written from
+    torch_geometric 2.6.1's TransformerConv.forward/message and utils.softmax; two restatements
+    agreeing is a consistency check of the oracle, not a pin against the real package."""
+    import math
+
+    import torch
+    x, ea = torch.from_numpy(x), torch.from_numpy(ea)
+    j, i = torch.from_numpy(ei[0]), torch.from_numpy(ei[1])
+    W = lambda n: torch.from_numpy(p[f'conv.{n}'])
+    n, HC = x.shape[0], p['conv.lin_query.weight'].shape[0]
+    C = HC // heads
+    q = torch.nn.functional.linear(x, W('lin_query.weight'), W('lin_query.bias')).view(n, heads, C)
+    k = torch.nn.functional.linear(x, W('lin_key.weight'), W('lin_key.bias')).view(n, heads, C)
+    v = torch.nn.functional.linear(x, W('lin_value.weight'), W('lin_value.bias')).view(n, heads, C)
+    e = torch.nn.functional.linear(ea, W('lin_edge.weight')).view(-1, heads, C)
+    alpha = (q[i] * (k[j] + e)).sum(-1) / math.sqrt(C)
+    mx = torch.full((n, heads), float('-inf')).scatter_reduce(0, i[:, None].expand(-1, heads), alpha,
+                                                             'amax', include_self=True)
+    ex = (alpha - mx[i]).exp()
+    den = torch.zeros(n, heads).index_add_(0, i, ex) + 1e-16
+    a = ex / den[i]
+    out = torch.zeros(n, heads, C).index_add_(0, i, (v[j] + e) * a[:, :, None])
+    return (out.view(n, HC) + torch.nn.functional.linear(x, W('lin_skip.weight'), W('lin_skip.bias'))).numpy()
+
+
+def test_transformer_conv_oracle_agrees_with_an_independent_torch_restatement():
+    from oracle.tgn_oracle import graph_attention_embedding, transformer_conv
+    rng = np.random.default_rng(5)
+    n, m, IN, HC, H, D, TD = 60, 400, 12, 16, 2, 5, 6
+    p = {f'conv.{nm}.weight': rng.standard_normal((HC, IN)).astype(np.float32) * 0.3
+         for nm in ('lin_query', 'lin_key', 'lin_value', 'lin_skip')}
+    p.update({f'conv.{nm}.bias': rng.standard_normal(HC).astype(np.float32) * 0.1
+              for nm in ('lin_query', 'lin_key', 'lin_value', 'lin_skip')})
+    p['conv.lin_edge.weight'] = rng.standard_normal((HC, TD + D)).astype(np.float32) * 0.3
+    p['time_enc.w.weight'] = (1 / 10 ** np.linspace(0, 4, TD)).astype(np.float32).reshape(TD, 1)
+    p['time_enc.w.bias'] = np.zeros(TD, np.float32)
+    x = rng.standard_normal((n, IN)).astype(np.float32)
+    ei = np.stack([rng.integers(0, n, m), rng.integers(0, n // 2, m)])  # half the nodes: no in-edges
+    ea = rng.standard_normal((m, TD + D)).astype(np.float32)
+    got = transformer_conv(p, 'conv.', H, x, ei, ea)
+    want = _torch_transformer_conv(p, H, x, ei, ea)
+    assert got.shape == (n, HC) and np.abs(got - want).max() <= 2e-6
+    # nodes without incoming edges reduce to the skip projection
+    skip = x @ p['conv.lin_skip.weight'].T + p['conv.lin_skip.bias']
+    assert np.abs(got[n // 2:] - skip[n // 2:]).max() <= 1e-6
+    # the embedding wrapper builds edge_attr = [Time2Vec(last_update[src] - t) | msg]
+    lu, t = rng.integers(0, 1000, n), rng.integers(0, 1000, m)
+    msg = rng.standard_normal((m, D)).astype(np.float32)
+    z = graph_attention_embedding(p, H, x, lu, ei, t, msg)
+    enc = np.cos(((lu[ei[0]] - t).astype(np.float32)[:, None] * p['time_enc.w.weight'].reshape(1, -1)))
+    want = _torch_transformer_conv(p, H, x, ei, np.concatenate([enc.astype(np.float32), msg], 1))
+    assert np.abs(z - want).max() <= 1e-5

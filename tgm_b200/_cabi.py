@@ -110,6 +110,10 @@ SIGNATURES = {
     'tgm_dyg_forward': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                 c_void_p]),
+    'tgm_gae_create': (c_int, [POINTER(c_void_p)] + [c_int32] * 5 + [c_void_p] * 11 + [c_int]),
+    'tgm_gae_destroy': (None, [c_void_p]),
+    'tgm_gae_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     'tgm_gather_rows': (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p,
                                 c_void_p]),
 }

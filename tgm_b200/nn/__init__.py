@@ -4,7 +4,9 @@ shapes, so `state_dict`s interchange, executing on the CUDA library (include/tgm
 from .attention import MergeLayer, TemporalAttention, Time2Vec, masked_mean
 from .dygformer import DyGFormer
 from .tgat import TGAT
-from .tgn import IdentityMessage, LastAggregator, TGNMemory
+from .tgn import (GraphAttentionEmbedding, IdentityMessage, LastAggregator, TGNMemory,
+                  TransformerConv)
 
 __all__ = ['TemporalAttention', 'Time2Vec', 'MergeLayer', 'TGAT', 'DyGFormer', 'masked_mean',
-           'TGNMemory', 'IdentityMessage', 'LastAggregator']
+           'TGNMemory', 'IdentityMessage', 'LastAggregator', 'GraphAttentionEmbedding',
+           'TransformerConv']

@@ -133,3 +133,80 @@ class TGNMemory(nn.Module):
             # flush the message store into memory when entering eval mode (tgn.py:245-251)
             _cabi.check(_cabi.lib.tgm_tgn_flush(self._handle(), _cabi.current_stream(self.device)))
         return super().train(mode)
+
+
+class TransformerConv(nn.Module):
+    """Parameter container with torch_geometric.nn.TransformerConv's names and shapes (lin_key,
+    lin_query, lin_value, lin_skip: Linear(in, heads*out) with bias; lin_edge: Linear(edge_dim,
+    heads*out) without), so a PyG state_dict loads into it.  The arithmetic runs in
+    `tgm_gae_forward` (GraphAttentionEmbedding below)."""
+
+    def __init__(self, in_channels: int, out_channels: int, heads: int = 1, dropout: float = 0.0,
+                 edge_dim: Optional[int] = None) -> None:
+        super().__init__()
+        if edge_dim is None:
+            raise NotImplementedError('the B200 TransformerConv is the edge-attributed form '
+                                      'GraphAttentionEmbedding uses (tgn.py:25-27)')
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.dropout, self.edge_dim = dropout, edge_dim
+        self.lin_key = nn.Linear(in_channels, heads * out_channels)
+        self.lin_query = nn.Linear(in_channels, heads * out_channels)
+        self.lin_value = nn.Linear(in_channels, heads * out_channels)
+        self.lin_edge = nn.Linear(edge_dim, heads * out_channels, bias=False)
+        self.lin_skip = nn.Linear(in_channels, heads * out_channels)
+
+
+class GraphAttentionEmbedding(nn.Module):
+    """tgm/nn/encoder/tgn.py:14-40 on the B200 library: same constructor, `time_enc` shared with
+    the memory module, `conv` carrying the TransformerConv parameters.  Forward only (eval-mode
+    arithmetic: the convolution's attention dropout cannot follow the reference's RNG stream).
+    Parity with torch_geometric is unpinned: see include/tgm_b200.h (tgm_gae_*)."""
+
+    def __init__(self, in_channels: int, out_channels: int, msg_dim: int, time_enc: nn.Module) -> None:
+        super().__init__()
+        self.time_enc = time_enc
+        edge_dim = msg_dim + time_enc.time_dim
+        self.msg_dim = msg_dim
+        self.conv = TransformerConv(in_channels, out_channels // 2, heads=2, dropout=0.1,
+                                    edge_dim=edge_dim)
+        self._native = _NativeHandle(_cabi.lib.tgm_gae_destroy)
+
+    def _handle(self, dev: torch.device) -> ctypes.c_void_p:
+        c = self.conv
+        params = [c.lin_query.weight, c.lin_query.bias, c.lin_key.weight, c.lin_key.bias,
+                  c.lin_value.weight, c.lin_value.bias, c.lin_edge.weight, c.lin_skip.weight,
+                  c.lin_skip.bias, self.time_enc.w.weight, self.time_enc.w.bias]
+        ver = _version(params)
+        if self._native.version != ver:
+            self._native.free()
+            if dev.type != 'cuda':
+                raise _cabi.TGMNativeError(-3, 'GraphAttentionEmbedding needs CUDA parameters '
+                                               '(no CPU fallback)')
+            t = [_f32(p) for p in params]
+            t[9] = t[9].reshape(-1)
+            _cabi.check(_cabi.lib.tgm_gae_create(
+                ctypes.byref(self._native.h), c.in_channels, c.heads * c.out_channels, c.heads,
+                self.msg_dim, self.time_enc.time_dim, *[p.data_ptr() for p in t],
+                dev.index if dev.index is not None else torch.cuda.current_device()))
+            self._native.version = ver
+        return self._native.h
+
+    @torch.no_grad()
+    def forward(self, x: Tensor, last_update: Tensor, edge_index: Tensor, t: Tensor,
+                msg: Tensor) -> Tensor:
+        dev = self.conv.lin_key.weight.device
+        if self.training and self.conv.dropout > 0:
+            raise RuntimeError('GraphAttentionEmbedding on the B200 path is forward/eval only')
+        x = _f32(x.to(dev))
+        n = x.shape[0]
+        lu = last_update.to(device=dev, dtype=torch.int64).contiguous()
+        ei = edge_index.to(device=dev, dtype=torch.int64).contiguous()
+        m = ei.shape[1]
+        tt = t.to(device=dev, dtype=torch.int64).contiguous()
+        mm = _f32(msg.to(dev)).reshape(m, self.msg_dim)
+        out = torch.empty((n, self.conv.heads * self.conv.out_channels), dtype=torch.float32,
+                          device=dev)
+        _cabi.check(_cabi.lib.tgm_gae_forward(
+            self._handle(dev), x.data_ptr(), lu.data_ptr(), n, ei[0].data_ptr(), ei[1].data_ptr(),
+            tt.data_ptr(), mm.data_ptr(), m, out.data_ptr(), _cabi.current_stream(dev)))
+        return out
