@@ -346,6 +346,70 @@ def row_tgn():
                        'sample': 'numpy oracle, 20 batches, N=2e4 nodes'})
 
 
+# ---- N4 full TGN inference step through the drop-in API (examples/linkproppred/tgn.py loop) --------
+def row_tgn_step():
+    from oracle.tgn_oracle import TGNMemoryOracle, graph_attention_embedding
+    from tgm_b200 import DeduplicationHook, RandomNegativeEdgeSamplerHook
+    from tgm_b200.nn import GraphAttentionEmbedding
+    src, dst, t, x, N = wiki_stream()
+    nb, bs, k, D, M, TD = 300, 200, 10, 172, 100, 100
+    E = nb * bs
+    t = np.arange(len(t), dtype=np.int64) * 17  # unique times: the TGN-memory parity domain
+    dg = graph(src[:E], dst[:E], t[:E], x[:E])
+    torch.manual_seed(0)
+    mem = TGNMemory(N, D, M, TD).to(DEV).eval()
+    enc = GraphAttentionEmbedding(M, 100, D, mem.time_enc).to(DEV).eval()
+    hm = HookManager(keys=['k'])
+    hm.register('k', RandomNegativeEdgeSamplerHook(low=8227, high=N))
+    hm.register('k', RecencyNeighborHook(num_nodes=N, num_nbrs=[k],
+                                         seed_nodes_keys=['edge_src', 'edge_dst', 'neg'],
+                                         seed_times_keys=['edge_time', 'edge_time', 'neg_time']))
+    hm.register('k', DeduplicationHook(seed_nodes_keys=['neg', 'nbr_nids']))
+    keep = {}
+
+    def step(batch):
+        nbr = batch.nbr_nids[0].flatten()
+        mask = nbr != -1
+        seeds = torch.cat([batch.edge_src, batch.edge_dst, batch.neg]).repeat_interleave(k)
+        ei = torch.stack([batch.global_to_local(seeds[mask]), batch.global_to_local(nbr[mask])]).long()
+        et = batch.nbr_edge_time[0].flatten()[mask]
+        ex = batch.nbr_edge_x[0].flatten(0, -2)[mask]
+        z, lu = mem(batch.unique_nids)
+        emb = enc(z, lu, ei, et, ex)
+        mem.update_state(batch.edge_src, batch.edge_dst, batch.edge_time, batch.edge_x)
+        return z, lu, ei, et, ex, emb
+
+    def epoch():
+        hm.reset_state()
+        mem.reset_state()
+        with hm.activate('k'):
+            for i, batch in enumerate(DGDataLoader(dg, batch_size=bs, hook_manager=hm)):
+                out = step(batch)
+                if i == nb - 1:
+                    keep['last'] = out
+    torch.set_grad_enabled(False)
+    epoch()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    epoch()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / nb * 1e3
+    z, lu, ei, et, ex, emb = [v.cpu().numpy() for v in keep['last']]
+    p = {k_: v.detach().cpu().numpy() for k_, v in enc.state_dict().items()}
+    t_cpu = cpu_s(lambda: graph_attention_embedding(p, 2, z, lu, ei, et, ex))
+    want = graph_attention_embedding(p, 2, z, lu, ei, et, ex)
+    ms_enc = cuda_ms(lambda: enc(*keep['last'][:5]), iters=20)
+    emit('N4 full TGN inference step per batch through DGDataLoader + hooks (wiki-shaped, bs=200 + 200 '
+         'negatives, k=10, memory 100, embed 100)', value=ms, unit='ms/batch', higher_is_better=False,
+         events_per_s=bs / (ms * 1e-3), embedding_ms=ms_enc, embedding_edges=int(ei.shape[1]),
+         embedding_nodes=int(z.shape[0]), embedding_max_abs_err_vs_oracle=float(np.abs(emb - want).max()),
+         note='negatives -> recency sampler (ring) -> dedup -> TGNMemory.forward -> '
+              'GraphAttentionEmbedding (2 SGEMM + sort + 3 kernels) -> update_state; wall clock, '
+              'launch/Python-bound at bs=200; TransformerConv parity is unpinned (third party)',
+         cpu_baseline={'value': t_cpu * 1e3, 'unit': 'ms/batch (embedding only)', 'kind': 'port',
+                       'cores': os.cpu_count(), 'sample': 'numpy oracle of the last batch'})
+
+
 # ---- A5 DyGFormer (config 5) ------------------------------------------------------------------------
 def row_dygformer():
     from oracle import nn_oracle
@@ -377,7 +441,7 @@ def row_dygformer():
                        'sample': 'numpy oracle of the same call'})
 
 
-ROWS = {'store': row_store, 'ring': row_ring, 'twohop': row_twohop, 'uniform': row_uniform,
+ROWS = {'tgn_step': row_tgn_step, 'store': row_store, 'ring': row_ring, 'twohop': row_twohop, 'uniform': row_uniform,
         'stream': row_stream_kernels, 'tgat': row_tgat, 'tgn': row_tgn, 'dygformer': row_dygformer}
 
 

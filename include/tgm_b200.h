@@ -362,6 +362,31 @@ int tgm_gae_forward(tgm_gae *, const float *x, const int64_t *last_update, int64
                     const int64_t *edge_src, const int64_t *edge_dst, const int64_t *t,
                     const float *msg, int64_t m, float *out, tgm_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Batch de-duplication.  Replaces DeduplicationHook.__call__ (tgm/hooks/dedup.py:35-67): masked
+ * gather per hop + torch.cat + torch.unique(sorted=True) + a torch.searchsorted per lookup.
+ * Node ids are dense in [0, num_nodes): the set is a bitmap, unique ids come out ascending
+ * without a sort and global_to_local(v) = #{u in set: u < v} (== searchsorted left, for members
+ * and non-members alike) is an O(1) rank lookup.
+ * The caller owns the state of one batch: bitmap uint32[bitmap_words], prefix int32[prefix_len]
+ * and tmp (tmp_bytes) from tgm_dedup_sizes; they must stay alive while tgm_dedup_map is used.
+ */
+int tgm_dedup_sizes(int32_t num_nodes, int64_t *bitmap_words, int64_t *prefix_len,
+                    int64_t *tmp_bytes);
+/* parts/sizes/skip_padded: HOST arrays of n_parts (<= 8) entries: device pointers to int32 ids,
+ * their lengths, and whether -1 entries are padding to drop (nbr_nids, dedup.py:46-48) or
+ * ordinary elements (seed arrays, as torch.unique would keep them).  out_unique int32[capacity >=
+ * min(sum sizes, num_nodes) + 1]; out_count int64[1] on the device: the number of unique ids, or
+ * -1 when an id fell outside [-1, num_nodes). */
+int tgm_dedup_unique(const int32_t *const *parts, const int64_t *sizes, const int32_t *skip_padded,
+                     int32_t n_parts, int32_t num_nodes, uint32_t *bitmap, int32_t *prefix,
+                     void *tmp, int64_t tmp_bytes, int32_t *out_unique, int64_t *out_count,
+                     tgm_stream stream);
+/* out_local[i] = searchsorted(unique, ids[i]) as int32 (dedup.py:57-59), ids int32[n]. */
+int tgm_dedup_map(const uint32_t *bitmap, const int32_t *prefix, const void *tmp,
+                  int32_t num_nodes, const int32_t *ids, int64_t n, int32_t *out_local,
+                  tgm_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

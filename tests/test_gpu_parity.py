@@ -633,6 +633,66 @@ def test_dedup_hook_after_the_sampler(name):
             assert local.cpu().tolist() == list(range(len(want) - 1, -1, -1))
 
 
+
+def _dedup_reference(parts):
+    """tgm/hooks/dedup.py:35-59 restated with torch ops on the host."""
+    keep = [t[t != -1] if skip else t for t, skip in parts]
+    unique = torch.unique(torch.cat(keep), sorted=True)
+    return unique, lambda x: torch.searchsorted(unique, x).int()
+
+
+@pytest.mark.parametrize('N,sizes', [(1, [1, 1]), (33, [5, 0, 40]), (10_000, [200, 200, 200, 6000]),
+                                     (1_000_000, [200, 200, 200, 6000, 120_000]),
+                                     (5000, [50] * 11)],
+                         ids=['one_node', 'tiny', 'wiki_like', 'million_nodes_two_hop', 'eleven_arrays'])
+def test_dedup_kernels_match_unique_and_searchsorted(N, sizes):
+    """tgm_dedup_unique / tgm_dedup_map vs torch.unique(sorted) / searchsorted on the host: padded
+    neighbour slots dropped, ids ascending, the map equal to searchsorted for members AND
+    non-members (incl. -1 and ids beyond the largest member)."""
+    from tgm_b200.hooks.dedup import _BatchIdSet
+    rng = np.random.default_rng(N + len(sizes))
+    parts = []
+    for i, n in enumerate(sizes):
+        a = rng.integers(0, N, n).astype(np.int32)
+        skip = i >= 3
+        if skip:
+            a[rng.random(n) < 0.4] = -1
+        parts.append((torch.from_numpy(a), skip))
+    want, want_map = _dedup_reference(parts)
+    ids = _BatchIdSet(N, torch.device(DEV))
+    dparts = [(t.to(DEV), s) for t, s in parts if t.numel()]
+    if len(dparts) > 8:
+        dparts = dparts[:3] + [(torch.cat([t for t, _ in dparts[3:]]), True)]
+    got = ids.unique(dparts)
+    assert got.dtype == torch.int32 and torch.equal(got.cpu(), want)
+    probe = torch.from_numpy(np.concatenate([rng.integers(0, N, 3000), [-1, 0, N - 1]]).astype(np.int32))
+    assert torch.equal(ids.local(probe.to(DEV)).cpu(), want_map(probe))
+    # a second set does not disturb the first one's map
+    other = _BatchIdSet(N, torch.device(DEV))
+    other.unique([(torch.arange(min(N, 7), dtype=torch.int32, device=DEV), False)])
+    assert torch.equal(ids.local(probe.to(DEV)).cpu(), want_map(probe))
+
+
+def test_dedup_hook_edge_cases():
+    """A -1 in a SEED array is an ordinary element (torch.unique keeps it, dedup.py:50-52); int64
+    seeds promote the result dtype like torch.cat; ids beyond the store's node range still work;
+    a missing attribute raises ValueError (dedup.py:43-44)."""
+    dg = _tiny_dg()
+    batch = dg.materialize()
+    hook = DeduplicationHook(seed_nodes_keys=['extra', 'nbr_nids'])
+    with pytest.raises(ValueError):
+        hook(dg, batch)
+    batch.extra = torch.tensor([-1, 2, 50_000, 2], dtype=torch.int64, device=DEV)
+    batch.nbr_nids = [torch.tensor([[-1, 1], [7, -1]], dtype=torch.int32, device=DEV)]
+    out = hook(dg, batch)
+    want, want_map = _dedup_reference([(batch.edge_src.cpu().long(), False), (batch.edge_dst.cpu().long(), False),
+                                       (batch.extra.cpu(), False), (batch.nbr_nids[0].flatten().cpu().long(), True)])
+    assert out.unique_nids.dtype == torch.int64 and torch.equal(out.unique_nids.cpu(), want)
+    assert int(out.unique_nids[0]) == -1
+    probe = torch.tensor([-1, 0, 1, 2, 7, 49_999, 50_000, 60_000], dtype=torch.int64)
+    assert torch.equal(out.global_to_local(probe.to(DEV)).cpu(), want_map(probe))
+
+
 def test_random_negative_sampler_contract():
     """tgm/hooks/negatives/sampler.py:14-65: int32 ids in [low, high) on the graph's device,
     round(neg_ratio * E_b) of them, neg_time a copy of edge_time; constructor errors."""

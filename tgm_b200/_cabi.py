@@ -114,6 +114,12 @@ SIGNATURES = {
     'tgm_gae_destroy': (None, [c_void_p]),
     'tgm_gae_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'tgm_dedup_sizes': (c_int, [c_int32, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
+    'tgm_dedup_unique': (c_int, [POINTER(c_void_p), POINTER(c_int64), POINTER(c_int32), c_int32,
+                                 c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                 c_void_p, c_void_p]),
+    'tgm_dedup_map': (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p,
+                              c_void_p]),
     'tgm_gather_rows': (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p,
                                 c_void_p]),
 }
