@@ -13,7 +13,8 @@ config 5  per rank a time-range shard of a synthetic stream: one pre-sampled win
           DyGFormer sequence is 32), then per batch of 200 edges a DyGFormer forward (patch 1,
           4x50 channels, 2 layers, 2 heads) -> 2x200 embeddings.  No collective on the data path.
 
-Forward/evaluation pipelines (the library has no backward).  One JSON line on rank 0; CUDA-event
+Forward/evaluation pipelines; `--config 3 --train` adds the backward pass (tgm_attn_backward
+through autograd) and an Adam step.  One JSON line on rank 0; CUDA-event
 times, max over ranks; the CPU oracle is timed beside it on a few batches (config 3 only: the
 numpy DyGFormer oracle is timed in bench_rows.py).
 """
@@ -47,7 +48,13 @@ def config3(a, dev):
     bs, nn = 200, [20, 20]
     torch.manual_seed(1337)
     model = TGAT(node_dim=1, edge_dim=x.shape[1], time_dim=100, embed_dim=172, num_layers=2,
-                 n_heads=2).to(dev).eval()
+                 n_heads=2, dropout=0.0).to(dev)
+    model = model.train() if a.train else model.eval()
+    # link decoder of the example (examples/linkproppred/tgat.py: LinkPredictor): plain torch MLP,
+    # not part of the hot path; only used by --train to give the backward pass a loss
+    decoder = torch.nn.Sequential(torch.nn.Linear(2 * 172, 172), torch.nn.ReLU(),
+                                  torch.nn.Linear(172, 1)).to(dev)
+    opt = torch.optim.Adam(list(model.parameters()) + list(decoder.parameters()), lr=1e-4)
     node_x = torch.randn(N, 1, device=dev)
     hm = HookManager(keys=['train'])
     hm.register('train', RandomNegativeEdgeSamplerHook(low=8227, high=N))
@@ -56,13 +63,30 @@ def config3(a, dev):
         seed_times_keys=['edge_time', 'edge_time', 'neg_time'], window_batches=a.window_batches))
     nb = a.batches
 
+    losses = []
+
     def epoch():
         hm.reset_state()
         done = 0
+        losses.clear()
         with hm.activate('train'):
             for batch in DGDataLoader(dg, batch_size=bs, hook_manager=hm):
+                if a.train:
+                    opt.zero_grad(set_to_none=True)
                 z = model(node_x, batch.seed_nids, batch.seed_times, batch.nbr_nids,
                           batch.nbr_edge_x, batch.nbr_edge_time)
+                if a.train:  # the example's loss: BCE on (src,dst) positives vs (src,neg) negatives
+                    n = batch.edge_src.numel()
+                    zs, zd, zn = z[:n], z[n:2 * n], z[2 * n:]
+                    pos = decoder(torch.cat([zs, zd], 1))
+                    neg = decoder(torch.cat([zs, zn], 1))
+                    loss = torch.nn.functional.binary_cross_entropy_with_logits(
+                        pos, torch.ones_like(pos)) + \
+                        torch.nn.functional.binary_cross_entropy_with_logits(
+                            neg, torch.zeros_like(neg))
+                    loss.backward()
+                    opt.step()
+                    losses.append(loss.detach())
                 done += 1
                 if done == nb:
                     break
@@ -101,8 +125,11 @@ def config3(a, dev):
             'cpu_baseline': {'value': cpu_ms, 'unit': 'ms/batch', 'kind': 'port',
                              'cores': os.cpu_count(),
                              'sample': f'{nbc} batches: C ring sampler + numpy TGAT oracle'},
-            'note': 'DGDataLoader + HookManager + windowed RecencyNeighborHook + TGAT.forward; '
-                    'forward only'}
+            'mode': 'train (forward + tgm_attn_backward + Adam step, dropout 0)' if a.train else 'forward',
+            'loss_first_last': [float(losses[0]), float(losses[-1])] if losses else None,
+            'note': 'DGDataLoader + HookManager + windowed RecencyNeighborHook + TGAT.forward' +
+                    (' + BCE loss on a torch MLP decoder + backward + Adam' if a.train else '') +
+                    '; the CPU figure is forward only'}
 
 
 def config5(a, dev, rank, world):
@@ -155,14 +182,15 @@ def config5(a, dev, rank, world):
 
 
 def main():
-    torch.set_grad_enabled(False)  # forward pipelines
     ap = argparse.ArgumentParser()
+    ap.add_argument('--train', action='store_true', help='config 3: forward + backward + Adam')
     ap.add_argument('--config', type=int, required=True, choices=[3, 5])
     ap.add_argument('--batches', type=int, default=200)
     ap.add_argument('--window-batches', type=int, default=25)
     ap.add_argument('--edges', type=int, default=100_000_000)
     ap.add_argument('--nodes', type=int, default=1_000_000)
     a = ap.parse_args()
+    torch.set_grad_enabled(bool(a.train))  # forward pipelines unless --train
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)

@@ -320,6 +320,49 @@ def test_properties_at_scale():
     assert bool((edge_keys[pos] == probe).all())
 
 
+
+def test_headline_size_rows_match_a_brute_force_of_the_reference_rule():
+    """BASELINE's headline workload at full size (1e8 edges, 1e6 nodes, T=2000, D=16, k=B=20,
+    bs=200): rows of the last and of an early window are re-derived from the raw stream by the
+    reference's rule (recency.py:239-321,323-399 -- entries of earlier batches ordered (batch,
+    time, side, edge), ring = last B of them, answer = the ring's prefix with time < tq, right-
+    aligned) and must match bit for bit, features included.  ~50k edges share a timestamp, so
+    ties at tq and ring eviction are exercised on every row."""
+    from tgm_b200.core.storage import DeviceCOOStorage
+    N, E, T, D, bs, k = 1_000_000, 100_000_000, 2000, 16, 200, 20
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    src = torch.randint(0, N, (E,), generator=gen, device=DEV, dtype=torch.int32)
+    dst = torch.randint(0, N, (E,), generator=gen, device=DEV, dtype=torch.int32)
+    t = torch.sort(torch.randint(0, T, (E,), generator=gen, device=DEV, dtype=torch.int64))[0]
+    x = torch.randn(E, D, generator=gen, device=DEV)
+    store = DeviceCOOStorage.from_device_tensors(src, dst, t, x, N)
+    csr = RecencyCSR(store, bs, colocate_x=True)
+    rng = np.random.default_rng(1)
+    for lo in (E - 500 * bs, 40_000 * bs):
+        hi = lo + 500 * bs
+        nid, nt, nx = csr.sample_edges(lo, hi, k, k)
+        for row in rng.integers(0, 2 * (hi - lo), 24):
+            b, r = divmod(int(row), 2 * bs)  # rows are [src rows | dst rows] per batch
+            e = lo + b * bs + (r % bs)
+            v = int((src if r < bs else dst)[e])
+            tq, cut = int(t[e]), lo + b * bs
+            es = torch.nonzero(src[:cut] == v).flatten().cpu().numpy()
+            ed = torch.nonzero(dst[:cut] == v).flatten().cpu().numpy()
+            ent = [(int(i) // bs, int(t[i]), 0, int(i), int(dst[i])) for i in es]
+            ent += [(int(i) // bs, int(t[i]), 1, int(i), int(src[i])) for i in ed]
+            ent.sort()
+            ring = ent[-k:]
+            keep = [q for q in ring if q[1] < tq]
+            assert all(q[1] >= tq for q in ring[len(keep):])  # the kept part is a prefix
+            pad = k - len(keep)
+            assert nid[row].tolist() == [-1] * pad + [q[4] for q in keep], (lo, row)
+            assert nt[row].tolist() == [0] * pad + [q[1] for q in keep], (lo, row)
+            want_x = torch.zeros(k, D, device=DEV)
+            if keep:
+                want_x[pad:] = x[torch.tensor([q[3] for q in keep], device=DEV)]
+            assert torch.equal(nx[row], want_x), (lo, row)
+
+
 # ---- frontier compaction / aggregation --------------------------------------------------------
 @pytest.mark.parametrize('n', [0, 1, 31, 4096, 4097, 1_000_003])
 def test_frontier_compact(n):
