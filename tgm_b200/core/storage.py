@@ -227,6 +227,40 @@ class DeviceCOOStorage(DGStorageBase):
         m = mask.numpy()
         return int(np.searchsorted(m, lb, 'left')), int(np.searchsorted(m, max(lb, ub), 'left'))
 
+    # -- loader fast path -------------------------------------------------------------------
+    _CHUNK_BATCHES = 4096
+
+    @property
+    def edges_only(self) -> bool:
+        """True when the event timeline holds edge events only and there are no edge types: a
+        loader batch is then fully described by its slab [lo, hi) of the edge arrays."""
+        return bool(self._edge_only and self._device is not None and
+                    getattr(self, '_edge_type', None) is None and
+                    (self._data is None or (self._data.node_x_mask is None and
+                                            self._data.node_y_mask is None)))
+
+    def batch_views(self, origin: int, batch_size: int, lo: int, hi: int):
+        """(src, dst, t, x) views of the slab [lo, hi), where lo = origin + j * batch_size: served
+        from per-chunk `Tensor.split` tuples (one C++ call yields the views of 4096 batches)
+        instead of four slicing calls per batch.  Identical tensors to get_edges/get_edge_x."""
+        j = (lo - origin) // batch_size
+        c, r = divmod(j, self._CHUNK_BATCHES)
+        key = ('batch_views', origin, batch_size, c)
+        chunk = self._node_cache.get(key)
+        if chunk is None:
+            for k in [k for k in self._node_cache if isinstance(k, tuple) and k[0] == 'batch_views']:
+                del self._node_cache[k]  # one live chunk: the loader walks forward
+            a = origin + c * self._CHUNK_BATCHES * batch_size
+            b = min(a + self._CHUNK_BATCHES * batch_size, self._E)
+            chunk = tuple(None if v is None else v[a:b].split(batch_size)
+                          for v in (self._src, self._dst, self._t, self._x))
+            self._node_cache[key] = chunk
+        if hi - lo == batch_size or lo + batch_size > self._E:
+            if hi - lo == len(chunk[0][r]):
+                return tuple(None if v is None else v[r] for v in chunk)
+        return (self._src[lo:hi], self._dst[lo:hi], self._t[lo:hi],
+                None if self._x is None else self._x[lo:hi])
+
     # -- getters --------------------------------------------------------------------------
     def get_start_time(self, slice: DGSliceTracker) -> Optional[int]:
         lb, ub = self._event_bounds(slice)

@@ -12,6 +12,7 @@ from typing import Any, Iterator, Optional
 
 from tgm_b200.core.batch import DGBatch
 from tgm_b200.core.graph import DGraph
+from tgm_b200.core.storage import DGSliceTracker
 from tgm_b200.core.timedelta import TimeDeltaDG
 from tgm_b200.exceptions import (EmptyBatchError, EventOrderedConversionError,
                                  InvalidDiscretizationError)
@@ -55,6 +56,13 @@ class DGDataLoader:
             self._starts = range(start, stop - batch_size, batch_size)
         else:
             self._starts = range(start, stop, batch_size)
+        # Fast path: event-ordered batches over an edge-only device store are plain slabs
+        # [max(i, lo0), min(i + bs, hi0)) of the edge arrays -- what slice_events + materialize
+        # compute (graph.py:110-152, 73-108) without the per-batch view objects and bound lookups.
+        self._fast = None
+        store = getattr(dg, '_storage', None)
+        if self._by_events and getattr(store, 'edges_only', False) and dg.device == store.device:
+            self._fast = (store,) + tuple(store.edge_range(dg._slice))
 
     @property
     def dgraph(self) -> DGraph:
@@ -64,10 +72,30 @@ class DGDataLoader:
         return len(self._starts)
 
     def _load(self, start: int) -> DGBatch:
+        if self._fast is not None:
+            return self._load_fast(start)
         dg = self._slice_op(start, start + self._batch_size)
         batch = dg.materialize()
         if self._hook_manager is not None:
             batch = self._hook_manager.execute_active_hooks(dg, batch)
+        return batch
+
+    def _load_fast(self, start: int) -> DGBatch:
+        store, lo0, hi0 = self._fast
+        bs = self._batch_size
+        lo, hi = max(start, lo0), min(start + bs, hi0)
+        if hi < lo:
+            hi = lo
+        src, dst, t, x = store.batch_views(lo0 - lo0 % bs, bs, lo, hi) if lo % bs == 0 else (
+            store._src[lo:hi], store._dst[lo:hi], store._t[lo:hi],
+            None if store._x is None else store._x[lo:hi])
+        batch = DGBatch(src, dst, t, x if hi > lo else None)
+        if self._hook_manager is not None:
+            src_dg = self._dg
+            s = src_dg._slice
+            view = DGraph._from_storage(store, src_dg._time_delta, src_dg._device, DGSliceTracker(
+                s.start_time, s.end_time, lo, hi))
+            batch = self._hook_manager.execute_active_hooks(view, batch)
         return batch
 
     # kept for API parity with the reference, whose loader is its own collate_fn (:158)

@@ -179,17 +179,24 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
             nwin = min(self._window_batches, self._window_budget_batches(bs))
             w['w_lo'], w['w_hi'] = lo, min(lo + nwin * bs, store.num_edges)
             w['hops'] = csr.sample_window(w['w_lo'], w['w_hi'], self._num_nbrs)
+            # per-batch views of the whole window in five C++ calls per hop (Tensor.split) rather
+            # than five slicing calls per hop per batch; only the stream's last batch can be short
+            rows, split = 2 * bs, []
+            for hop in w['hops']:
+                split.append(tuple(v.split(rows) for v in (
+                    hop.seed_nids, hop.seed_times, hop.nbr_nids, hop.nbr_edge_time,
+                    hop.nbr_edge_x)))
+                rows *= hop.nbr_nids.shape[1]
+            w['split'] = split
         # rows of this batch inside the window block, hop by hop
-        a, b = 2 * (lo - w['w_lo']), 2 * (hi - w['w_lo'])
-        parts = []
-        for hop in w['hops']:
-            k = hop.nbr_nids.shape[1]
-            parts.append((hop.seed_nids[a:b], hop.seed_times[a:b], hop.nbr_nids[a:b],
-                          hop.nbr_edge_time[a:b], hop.nbr_edge_x[a:b]))
-            a, b = a * k, b * k
+        j = (lo - w['w_lo']) // bs
+        parts = [tuple(v[j] for v in hop) for hop in w['split']]
         n = hi - lo
         dev = self._device
-        mask = {'edge_src': self._arange(0, n), 'edge_dst': self._arange(n, 2 * n)}
+        mask = w.get('mask')
+        if mask is None or mask[0] != n:
+            mask = w['mask'] = (n, self._arange(0, n), self._arange(n, 2 * n))
+        mask = {'edge_src': mask[1], 'edge_dst': mask[2]}
         extra = keys[2:]
         if extra:  # seeds the window cannot know in advance (negatives): one launch per hop
             xs, xt, offset = [], [], 2 * n
