@@ -298,7 +298,8 @@ def row_tgat():
          layer1_attention_roofline=hbm(sizes[1] * (k * (1 + D) * 4 + k * 12 + 2 * 2 * key1 * 4), ms_att),
          note=f'reassociated single-query attention: the reference W_KV GEMM ({flops_ref / 1e9:.1f} '
               'GFLOP per layer-1 call) is replaced by two S-row skinny GEMMs; the neighbour pass is '
-              'SIMT fp32 (cosf + dot products), issue-bound rather than HBM-bound',
+              'SIMT fp32 (Time2Vec cosines + dot products over cp.async-staged rows), '
+              'issue/latency-bound rather than HBM-bound',
          cpu_baseline={'value': t_cpu * 1e3, 'unit': 'ms/batch', 'kind': 'port', 'cores': os.cpu_count(),
                        'sample': 'numpy oracle of the same batch (BLAS threads = all cores)'})
 

@@ -96,81 +96,276 @@ __global__ void cos_kernel(const float *__restrict__ b, int n, float *__restrict
 // time 0).
 constexpr int kAttnThreads = 128;
 
-__global__ void __launch_bounds__(kAttnThreads)
+// cos(a) for the Time2Vec argument a = fl32(fma(dt, w, b)), |error| <= 1.6e-7 for |a| < 2^22
+// (checked against float64 over 1e7 arguments up to 4e6): q = rint(a / pi) by the magic-number
+// add, a three-term Cody-Waite reduction with FMAs (pi = C1 - D1 - D2), a degree-14 Taylor
+// polynomial on |r| <~ 1.75 and the sign from the parity of q.  15 instructions against ~47 for
+// libdevice cosf's fast path; larger arguments take cosf.
+__device__ __forceinline__ float t2v_cos(float a) {
+  if (!(fabsf(a) < 4194304.f)) return cosf(a);
+  const float kMagic = 12582912.f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float t = __fmaf_rn(a, 0.318309886183790672f, kMagic);
+  const float q = t - kMagic;
+  float r = __fmaf_rn(q, -3.1415927410125732f, a);
+  r = __fmaf_rn(q, 8.742277657347586e-08f, r);
+  r = __fmaf_rn(q, 3.4302490200117637e-15f, r);
+  const float x2 = r * r;
+  float p = -1.1470745597729725e-11f;          // -1/14!
+  p = __fmaf_rn(p, x2, 2.08767569878681e-09f);  //  1/12!
+  p = __fmaf_rn(p, x2, -2.755731922398589e-07f);
+  p = __fmaf_rn(p, x2, 2.48015873015873e-05f);
+  p = __fmaf_rn(p, x2, -1.388888888888889e-03f);
+  p = __fmaf_rn(p, x2, 4.1666666666666664e-02f);
+  p = __fmaf_rn(p, x2, -0.5f);
+  p = __fmaf_rn(p, x2, 1.0f);
+  return __uint_as_float(__float_as_uint(p) ^ ((__float_as_uint(t) & 1u) << 31));
+}
+
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gmem_src) {
+  const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Shared-memory row layout: z row n starts at z + n * zs + pad with pad = (4 - node_dim % 4) % 4 and
+// zs = roundup4(pad + key), so the edge-feature part of every row is 16-byte aligned and is filled
+// with 128-bit loads/stores.
+struct AttnLayout {
+  int pad, zs, a_len;
+  size_t bytes;
+};
+static inline AttnLayout attn_layout(int k, int node_dim, int key, int H, bool qk_in_smem) {
+  AttnLayout L;
+  L.pad = (4 - node_dim % 4) % 4;
+  L.zs = (L.pad + key + 3) & ~3;
+  L.a_len = ((H + 1) / 2) * k * 2;  // probabilities of a head pair interleaved: [pair][n][2]
+  L.bytes = (size_t(k) * L.zs + (qk_in_smem ? size_t(H) * key : 0) + L.a_len) * sizeof(float);
+  return L;
+}
+
+// KT > 0: key <= 32 * KT and each lane keeps its KT columns of qk (two heads) in registers;
+// KT == 0: any key, qk staged in shared memory.
+template <int KT>
+__global__ void __launch_bounds__(kAttnThreads, 8)
 attn_neighbor_kernel(const float *__restrict__ nbr_feat, const float *__restrict__ edge_feat,
                      const int64_t *__restrict__ seed_t, const int64_t *__restrict__ nbr_t,
                      const int32_t *__restrict__ nbr_id, const float *__restrict__ tw,
                      const float *__restrict__ tb, const float *__restrict__ nbr_tf,
                      const float *__restrict__ QK, int64_t S, int k, int node_dim, int edge_dim,
-                     int time_dim, int H, float scale, float *__restrict__ U) {
-  extern __shared__ float smem[];
+                     int time_dim, int H, float scale, int vec_node, int vec_edge,
+                     float *__restrict__ U) {
+  extern __shared__ __align__(16) float smem[];
   const int key = node_dim + edge_dim + time_dim;
-  float *z = smem;                 // [k][key]
-  float *qk = z + k * key;         // [H][key]
-  float *a = qk + H * key;         // [H][k] logits -> probabilities
+  const int pad = (4 - node_dim % 4) % 4, zs = (pad + key + 3) & ~3;
+  float *z = smem + pad;                            // row n: z + n * zs, [key] floats
+  float *qk = smem + k * zs;                        // [H][key]   (KT == 0 only)
+  float *a = qk + (KT == 0 ? H * key : 0);          // [ceil(H/2)][k][2] logits -> probabilities
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kAttnThreads >> 5;
+  const int td_full = time_dim & ~31, td_rem = time_dim - td_full;  // whole warp tiles + leftover
+  const int feat = node_dim + edge_dim;
+  // Time2Vec weights of this lane's columns (first four tiles) live in registers
+  float wr[4], br[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int c = lane + 32 * t;
+    wr[t] = c < td_full ? __ldg(tw + c) : 0.f;
+    br[t] = c < td_full ? __ldg(tb + c) : 0.f;
+  }
   for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
     const int64_t tq = nbr_tf ? 0 : seed_t[s];
     const float *nf = nbr_feat + s * int64_t(k) * node_dim;
     const float *ef = edge_feat + s * int64_t(k) * edge_dim;
-    // one warp per neighbour row, lanes along the feature dimension (coalesced, no divisions)
+    const float *qks = QK + s * int64_t(H) * key;
+    // feature rows go global -> shared with 16-byte asynchronous copies (no register staging, all
+    // of a warp's rows in flight at once); the cosines below overlap their latency.  One warp per
+    // neighbour row, lanes along the feature dimension (coalesced); short runtime-bounded loops
+    // are kept rolled (the unrolled forms cost ~25 instructions per copy in bounds logic).
+    if (!vec_node) {  // narrow / unaligned node features (TGAT layer 1: one column): flat pass
+#pragma unroll 1
+      for (int i = tid; i < k * node_dim; i += kAttnThreads) {
+        const int n = i / node_dim;
+        z[n * zs + (i - n * node_dim)] = __ldg(nf + i);
+      }
+    }
+#pragma unroll 1
     for (int n = warp; n < k; n += nwarp) {
-      float *zn = z + n * key;
-      const float *nfr = nf + n * node_dim, *efr = ef + n * edge_dim;
-      for (int c = lane; c < node_dim; c += 32) zn[c] = __ldg(nfr + c);
-      for (int c = lane; c < edge_dim; c += 32) zn[node_dim + c] = __ldg(efr + c);
-      float *zt = zn + node_dim + edge_dim;
+      float *zn = z + n * zs;
+      if (vec_node) {
+        const float *src = nf + n * node_dim + 4 * lane;
+        float *dst = zn + 4 * lane;
+#pragma unroll 1
+        for (int c = lane; c < (node_dim >> 2); c += 32, src += 128, dst += 128) cp_async16(dst, src);
+      }
+      if (vec_edge) {
+        const float *src = ef + n * edge_dim + 4 * lane;
+        float *dst = zn + node_dim + 4 * lane;
+#pragma unroll 1
+        for (int c = lane; c < (edge_dim >> 2); c += 32, src += 128, dst += 128) cp_async16(dst, src);
+      } else {
+        const float *efr = ef + n * edge_dim;
+#pragma unroll 1
+        for (int c = lane; c < edge_dim; c += 32) zn[node_dim + c] = __ldg(efr + c);
+      }
+    }
+    cp_async_commit();
+    // this lane's qk columns of the first head pair: requested now, used after the barrier
+    float q0[KT > 0 ? KT : 1], q1[KT > 0 ? KT : 1];
+    if (KT > 0) {
+#pragma unroll
+      for (int t = 0; t < KT; ++t) {
+        const int j = lane + 32 * t;
+        q0[t] = j < key ? __ldg(qks + j) : 0.f;
+        q1[t] = (H > 1 && j < key) ? __ldg(qks + key + j) : 0.f;
+      }
+    }
+    if (KT == 0)
+      for (int i = tid; i < H * key; i += kAttnThreads) qk[i] = __ldg(qks + i);
+    // leftover time columns (time_dim % 32) of all k rows as flat (row, column) pairs, so the
+    // per-row pass below runs whole warp tiles only (100 columns: 63 warp-cosines, not 80)
+    if (!nbr_tf && td_rem) {
+      for (int p = tid; p < k * td_rem; p += kAttnThreads) {
+        const int n = p / td_rem, c = td_full + (p - n * td_rem);
+        const float dt = float(tq - nbr_t[s * k + n]);
+        z[n * zs + feat + c] = t2v_cos(__fmaf_rn(dt, __ldg(tw + c), __ldg(tb + c)));
+      }
+    }
+    for (int n = warp; n < k; n += nwarp) {
+      float *zn = z + n * zs;
+      float *zt = zn + feat;
       if (nbr_tf) {  // caller-provided time features (the plain attention.py:58 signature)
         const float *tf = nbr_tf + (s * int64_t(k) + n) * time_dim;
         for (int c = lane; c < time_dim; c += 32) zt[c] = __ldg(tf + c);
       } else {
         const float dt = float(tq - nbr_t[s * k + n]);  // int64 difference, then .float() (:23)
-        for (int c = lane; c < time_dim; c += 32)
-          zt[c] = cosf(__fmaf_rn(dt, __ldg(tw + c), __ldg(tb + c)));
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (32 * t < td_full) zt[lane + 32 * t] = t2v_cos(__fmaf_rn(dt, wr[t], br[t]));
+        for (int c = 128 + lane; c < td_full; c += 32)
+          zt[c] = t2v_cos(__fmaf_rn(dt, __ldg(tw + c), __ldg(tb + c)));
       }
     }
-    for (int i = tid; i < H * key; i += kAttnThreads) qk[i] = QK[s * int64_t(H) * key + i];
+    cp_async_wait_all();
     __syncthreads();
-    // logits: one warp per (h, n) pair
-    for (int p = warp; p < H * k; p += nwarp) {
-      const int h = p / k, n = p - h * k;
-      const float *zz = z + n * key, *qq = qk + h * key;
-      float acc = 0.f;
-      for (int j = lane; j < key; j += 32) acc = fmaf(qq[j], zz[j], acc);
+    // logits: the same warp-per-row split, two heads share each z load
+    for (int h0 = 0; h0 < H; h0 += 2) {
+      const bool two = h0 + 1 < H;
+      float *ap = a + (h0 >> 1) * k * 2;
+      if (KT > 0) {
+        if (h0 > 0) {
 #pragma unroll
-      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0)
-        a[p] = nbr_id[s * k + n] != TGM_PADDED_NODE_ID ? acc * scale : -1e10f;
+          for (int t = 0; t < KT; ++t) {
+            const int j = lane + 32 * t;
+            q0[t] = j < key ? __ldg(qks + h0 * key + j) : 0.f;
+            q1[t] = (two && j < key) ? __ldg(qks + (h0 + 1) * key + j) : 0.f;
+          }
+        }
+        for (int n = warp; n < k; n += nwarp) {
+          const float *zn = z + n * zs;
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+          for (int t = 0; t < KT; ++t) {
+            const int j = lane + 32 * t;
+            const float v = j < key ? zn[j] : 0.f;
+            acc0 = fmaf(q0[t], v, acc0);
+            acc1 = fmaf(q1[t], v, acc1);
+          }
+#pragma unroll
+          for (int o = 16; o; o >>= 1) {
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+            acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+          }
+          if (lane == 0) {
+            const bool valid = nbr_id[s * k + n] != TGM_PADDED_NODE_ID;
+            ap[2 * n] = valid ? acc0 * scale : -1e10f;
+            ap[2 * n + 1] = valid ? acc1 * scale : -1e10f;
+          }
+        }
+      } else {
+        const float *q0 = qk + h0 * key, *q1 = q0 + (two ? key : 0);
+        for (int n = warp; n < k; n += nwarp) {
+          const float *zn = z + n * zs;
+          float acc0 = 0.f, acc1 = 0.f;
+          for (int j = lane; j < key; j += 32) {
+            const float v = zn[j];
+            acc0 = fmaf(q0[j], v, acc0);
+            acc1 = fmaf(q1[j], v, acc1);
+          }
+#pragma unroll
+          for (int o = 16; o; o >>= 1) {
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+            acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+          }
+          if (lane == 0) {
+            const bool valid = nbr_id[s * k + n] != TGM_PADDED_NODE_ID;
+            ap[2 * n] = valid ? acc0 * scale : -1e10f;
+            ap[2 * n + 1] = valid ? acc1 * scale : -1e10f;
+          }
+        }
+      }
     }
     __syncthreads();
     // softmax over the k slots of each head: one warp per head
     for (int h = warp; h < H; h += nwarp) {
+      float *ah = a + (h >> 1) * k * 2 + (h & 1);  // stride 2
       float m = -INFINITY;
-      for (int n = lane; n < k; n += 32) m = fmaxf(m, a[h * k + n]);
+      for (int n = lane; n < k; n += 32) m = fmaxf(m, ah[2 * n]);
 #pragma unroll
       for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
       float sum = 0.f;
       for (int n = lane; n < k; n += 32) {
-        const float e = expf(a[h * k + n] - m);
-        a[h * k + n] = e;
+        const float e = expf(ah[2 * n] - m);
+        ah[2 * n] = e;
         sum += e;
       }
 #pragma unroll
       for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       const float inv = 1.f / sum;
-      for (int n = lane; n < k; n += 32) a[h * k + n] *= inv;
+      for (int n = lane; n < k; n += 32) ah[2 * n] *= inv;
     }
     __syncthreads();
-    // u_h[j] = sum_n a_hn z_n[j]
+    // u_h[j] = sum_n a_hn z_n[j]: one thread per column j, two heads per pass (one 64-bit
+    // broadcast load brings both probabilities)
     float *u = U + s * int64_t(H) * key;
-    for (int i = tid; i < H * key; i += kAttnThreads) {
-      const int h = i / key, j = i - h * key;
-      float acc = 0.f;
-      for (int n = 0; n < k; ++n) acc = fmaf(a[h * k + n], z[n * key + j], acc);
-      u[i] = acc;
+    for (int h0 = 0; h0 < H; h0 += 2) {
+      const bool two = h0 + 1 < H;
+      const float2 *ap = reinterpret_cast<const float2 *>(a + (h0 >> 1) * k * 2);
+      for (int j = tid; j < key; j += kAttnThreads) {
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+        for (int n = 0; n < k; ++n) {
+          const float v = z[n * zs + j];
+          const float2 av = ap[n];
+          acc0 = fmaf(av.x, v, acc0);
+          acc1 = fmaf(av.y, v, acc1);
+        }
+        u[h0 * key + j] = acc0;
+        if (two) u[(h0 + 1) * key + j] = acc1;
+      }
     }
     __syncthreads();
   }
+}
+
+template <int KT>
+int launch_attn_neighbor(const tgm_attn *a, const float *nbr_node_feat, const float *edge_feat,
+                         const int64_t *seed_t, const int64_t *nbr_t, const int32_t *nbr_id,
+                         const float *nbr_tf, int64_t S, int k, cudaStream_t st) {
+  const AttnLayout L = attn_layout(k, a->node_dim, a->key, a->H, KT == 0);
+  TGM_REQUIRE(L.bytes <= 200 * 1024, "tgm_attn_forward: k * key_dim too large for shared memory");
+  if (L.bytes > 48 * 1024)
+    TGM_CUDA(cudaFuncSetAttribute(attn_neighbor_kernel<KT>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, int(L.bytes)));
+  const int ctas_per_sm =
+      int(std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (L.bytes + 1024))));
+  const int vec_node = a->node_dim % 4 == 0 && aligned16(nbr_node_feat);
+  const int vec_edge = a->edge_dim % 4 == 0 && aligned16(edge_feat);
+  attn_neighbor_kernel<KT><<<grid_for(S, 1, ctas_per_sm), kAttnThreads, L.bytes, st>>>(
+      nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, a->tw, a->tb, nbr_tf, a->QK, S, k,
+      a->node_dim, a->edge_dim, a->time_dim, a->H, 1.0f / sqrtf(float(a->hd)), vec_node, vec_edge,
+      a->U);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
 }
 
 // out = LayerNorm(Y + b_O + R) (attention.py:124-127); one warp per row, two-pass variance
@@ -369,16 +564,15 @@ int attn_forward_impl(tgm_attn *a, const float *node_x, const float *nbr_node_fe
                                      a->Wkv, key, int64_t(hd) * key, a->Q, od, hd, &zero, a->QK,
                                      H * key, key, H));
   // fused gather + Time2Vec + masked softmax + weighted sum
-  const size_t smem = (size_t(k) * key + size_t(H) * key + size_t(H) * k) * sizeof(float);
-  TGM_REQUIRE(smem <= 200 * 1024, "tgm_attn_forward: k * key_dim too large for shared memory");
-  if (smem > 48 * 1024)
-    TGM_CUDA(cudaFuncSetAttribute(attn_neighbor_kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  const int ctas_per_sm = int(std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 1024))));
-  attn_neighbor_kernel<<<grid_for(S, 1, ctas_per_sm), kAttnThreads, smem, st>>>(
-      nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, a->tw, a->tb, nbr_tf, a->QK, S, k,
-      a->node_dim, a->edge_dim, a->time_dim, H, 1.0f / sqrtf(float(hd)), a->U);
-  TGM_LAUNCH_CHECK();
+  {
+    const int kt = (key + 31) / 32;
+    int rc;
+    if (kt <= 4) rc = launch_attn_neighbor<4>(a, nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, nbr_tf, S, k, st);
+    else if (kt <= 9) rc = launch_attn_neighbor<9>(a, nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, nbr_tf, S, k, st);
+    else if (kt <= 14) rc = launch_attn_neighbor<14>(a, nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, nbr_tf, S, k, st);
+    else rc = launch_attn_neighbor<0>(a, nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, nbr_tf, S, k, st);
+    if (rc) return rc;
+  }
   // O[s,h,:] = W_V,h u[s,h,:]   (W_V = rows [out, 2 out) of W_KV)
   TGM_BLAS(cublasSgemmStridedBatched(a->blas, CUBLAS_OP_T, CUBLAS_OP_N, hd, int(S), key, &one,
                                      a->Wkv + size_t(od) * key, key, int64_t(hd) * key, a->U,
