@@ -108,6 +108,17 @@ int tgm_recency_query(const tgm_recency *, const int32_t *seeds, const int64_t *
  * (zeros, recency.py:325-329). */
 int tgm_recency_update(tgm_recency *, const int32_t *src, const int32_t *dst, const int64_t *t,
                        const float *x, int64_t Eb, int directed, tgm_stream stream);
+/* One whole hook call for the standard seed configuration -- seed_nodes_keys [edge_src, edge_dst],
+ * seed_times_keys [edge_time, edge_time] (recency.py:119-171): writes the hop-0 seeds/times
+ * ([src|dst], [t|t]; int32[2Eb], int64[2Eb]), queries every hop (hop h+1 seeds = flattened hop-h
+ * neighbours, :141-143), THEN pushes the batch (:161-163).  num_nbrs: HOST int32[num_hops];
+ * out_nid/out_t/out_x: HOST arrays [num_hops] of device pointers sized (S_h,k_h), (S_h,k_h),
+ * (S_h,k_h,D) with S_0 = 2Eb, S_{h+1} = S_h*k_h (out_x entries may be NULL when D == 0). */
+int tgm_recency_step(tgm_recency *, const int32_t *src, const int32_t *dst, const int64_t *t,
+                     const float *x /* nullable */, int64_t Eb, int directed, int32_t num_hops,
+                     const int32_t *num_nbrs, int32_t *seed_nids0, int64_t *seed_times0,
+                     int32_t *const *out_nid, int64_t *const *out_t, float *const *out_x,
+                     tgm_stream stream);
 /* device pointers to the live state (for checkpointing / inspection); any may be NULL. */
 int tgm_recency_state(const tgm_recency *, int32_t **ids, int64_t **times, float **feats,
                       int32_t **write_pos);

@@ -56,6 +56,9 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p]),
     'tgm_recency_update': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                    c_int, c_void_p]),
+    'tgm_recency_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                 c_int32, POINTER(c_int32), c_void_p, c_void_p, POINTER(c_void_p),
+                                 POINTER(c_void_p), POINTER(c_void_p), c_void_p]),
     'tgm_recency_state': (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p),
                                   POINTER(c_void_p), POINTER(c_void_p)]),
     'tgm_csr_build': (c_int, [POINTER(c_void_p), c_void_p, c_int64, c_int64, c_int, c_int,

@@ -294,6 +294,20 @@ ring_update_commit_kernel(float *__restrict__ feats, int32_t *__restrict__ wpos,
   }
 }
 
+// hop-0 seeds of the standard hook configuration: [edge_src | edge_dst], [edge_time | edge_time]
+__global__ void __launch_bounds__(256)
+step_seeds_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                  const int64_t *__restrict__ t, int64_t n, int32_t *__restrict__ seeds,
+                  int64_t *__restrict__ times) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < 2 * n;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const bool second = i >= n;
+    const int64_t e = second ? i - n : i;
+    seeds[i] = second ? dst[e] : src[e];
+    times[i] = t[e];
+  }
+}
+
 }  // namespace
 
 extern "C" int tgm_recency_create(tgm_recency **out, int32_t num_nodes, int32_t B, int32_t D,
@@ -450,6 +464,33 @@ extern "C" int tgm_recency_update(tgm_recency *h, const int32_t *src, const int3
                                                    h->dest, h->inc);
   TGM_LAUNCH_CHECK();
   return TGM_OK;
+}
+
+extern "C" int tgm_recency_step(tgm_recency *h, const int32_t *src, const int32_t *dst,
+                                const int64_t *t, const float *x, int64_t Eb, int directed,
+                                int32_t num_hops, const int32_t *num_nbrs, int32_t *seed_nids0,
+                                int64_t *seed_times0, int32_t *const *out_nid,
+                                int64_t *const *out_t, float *const *out_x, tgm_stream stream) {
+  TGM_REQUIRE(h != nullptr, "tgm_recency_step: handle is NULL");
+  TGM_REQUIRE(Eb > 0 && num_hops >= 1, "tgm_recency_step: needs a non-empty batch and >= 1 hop");
+  TGM_REQUIRE(src && dst && t && num_nbrs && seed_nids0 && seed_times0 && out_nid && out_t && out_x,
+              "tgm_recency_step: NULL argument");
+  DeviceGuard g(h->device);
+  step_seeds_kernel<<<grid_for(2 * Eb, 256, 8), 256, 0, as_stream(stream)>>>(src, dst, t, Eb,
+                                                                           seed_nids0, seed_times0);
+  TGM_LAUNCH_CHECK();
+  const int32_t *seeds = seed_nids0;
+  const int64_t *times = seed_times0;
+  int64_t S = 2 * Eb;
+  for (int32_t hop = 0; hop < num_hops; ++hop) {  // query BEFORE update (recency.py:161-163)
+    const int32_t k = num_nbrs[hop];
+    int rc = tgm_recency_query(h, seeds, times, S, k, out_nid[hop], out_t[hop], out_x[hop], stream);
+    if (rc) return rc;
+    seeds = out_nid[hop];  // hop h+1 seeds = flattened hop-h neighbours (recency.py:141-143)
+    times = out_t[hop];
+    S *= k;
+  }
+  return tgm_recency_update(h, src, dst, t, x, Eb, directed, stream);
 }
 
 extern "C" int tgm_recency_state(const tgm_recency *h, int32_t **ids, int64_t **times,

@@ -80,6 +80,9 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
             raise ValueError('window_batches must be a non-negative integer')
         self._window_batches = window_batches
         self._win = None  # windowed-mode cursor, see _windowed_call
+        self._standard_seeds = (list(seed_nodes_keys) == ['edge_src', 'edge_dst'] and
+                                list(seed_times_keys) == ['edge_time', 'edge_time'])
+        self._num_nbrs_c = (ctypes.c_int32 * len(num_nbrs))(*num_nbrs)
         self._handle = ctypes.c_void_p()   # tgm_recency*, created on first call
         self._device: Optional[torch.device] = None
         self._edge_x_dim: Optional[int] = None
@@ -282,6 +285,8 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
             if out is not None:
                 return out
             self._leave_window()
+        if self._standard_seeds and self._step_call(dg, batch):
+            return batch
         seed_nodes, seed_times, seed_mask = self._get_seed_tensors(dg, batch)
         seeds_out: List[Tensor] = []
         times_out: List[Tensor] = []
@@ -316,6 +321,47 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         self.add_batch_attribute(batch, 'nbr_edge_x', nxs)
         self.add_batch_attribute(batch, 'seed_node_nbr_mask', seed_mask)
         return batch
+
+    def _step_call(self, dg, batch) -> bool:
+        """The whole hook call in ONE library call (tgm_recency_step) for the standard seed keys
+        [edge_src, edge_dst] x [edge_time, edge_time] when the batch tensors are views of the
+        validated device store (no per-key validation, concatenation or dtype moves needed).
+        Returns False when the batch does not qualify; the general path then handles it."""
+        src = batch.edge_src
+        n = src.numel()
+        store = getattr(dg, '_storage', None)
+        if n == 0 or getattr(store, 'num_nodes_global', 1 << 62) > self._num_nodes or \
+                not _is_store_view(store, src) or batch.edge_dst.numel() != n:
+            return False
+        x = batch.edge_x
+        D, dev = self._edge_x_dim, self._device
+        if D and (x is None or x.dtype != torch.float32 or not x.is_contiguous()):
+            return False
+        hops = len(self._num_nbrs)
+        seeds0 = torch.empty(2 * n, dtype=torch.int32, device=dev)
+        times0 = torch.empty(2 * n, dtype=torch.int64, device=dev)
+        nids, nts, nxs, S = [], [], [], 2 * n
+        for k in self._num_nbrs:
+            nids.append(torch.empty((S, k), dtype=torch.int32, device=dev))
+            nts.append(torch.empty((S, k), dtype=torch.int64, device=dev))
+            nxs.append(torch.empty((S, k, D), dtype=torch.float32, device=dev))
+            S *= k
+        P = ctypes.c_void_p * hops
+        _cabi.check(_cabi.lib.tgm_recency_step(
+            self._handle, src.data_ptr(), batch.edge_dst.data_ptr(), batch.edge_time.data_ptr(),
+            x.data_ptr() if D else None, n, int(self._directed), hops, self._num_nbrs_c,
+            seeds0.data_ptr(), times0.data_ptr(), P(*[v.data_ptr() for v in nids]),
+            P(*[v.data_ptr() for v in nts]), P(*[v.data_ptr() if D else None for v in nxs]),
+            _cabi.current_stream(dev)))
+        add = self.add_batch_attribute
+        add(batch, 'seed_nids', [seeds0] + [v.view(-1) for v in nids[:-1]])
+        add(batch, 'seed_times', [times0] + [v.view(-1) for v in nts[:-1]])
+        add(batch, 'nbr_nids', nids)
+        add(batch, 'nbr_edge_time', nts)
+        add(batch, 'nbr_edge_x', nxs)
+        add(batch, 'seed_node_nbr_mask', {'edge_src': self._arange(0, n),
+                                          'edge_dst': self._arange(n, 2 * n)})
+        return True
 
     def _query(self, seeds: Tensor, tq: Tensor, k: int, stream: int
                ) -> Tuple[Tensor, Tensor, Tensor]:
