@@ -246,13 +246,13 @@ def row_stream_kernels():
     ms = cuda_ms(lambda: compact_frontier(flat))
     emit('frontier compaction (4e7 slots)', value=flat.numel() / (ms * 1e-3), unit='slots/s', ms=ms,
          roofline=hbm(flat.numel() * (4 + 4 + 8), ms),
-         note='count + scan + scatter: ids are read twice; includes one .item() sync for the count')
+         note='single pass (tile tickets + decoupled look-back); includes one .item() sync for the count')
     te = Time2Vec(100).to(DEV)
     dt = torch.randint(0, 2_600_000, (400_000,), generator=g, device=DEV)
     ms = cuda_ms(lambda: te(dt))
     emit('A1 time2vec_kernel (4e5 deltas x 100 dims)', value=dt.numel() * 100 / (ms * 1e-3),
          unit='encodings/s', ms=ms, roofline=hbm(dt.numel() * (8 + 400), ms),
-         note='full-range cosf; arguments up to 2.6e6 take the Payne-Hanek path')
+         note='warp per row, 15-instruction cosine (1.6e-7 abs); includes the torch output allocation')
 
 
 # ---- A2/A3 TGAT (config 3) --------------------------------------------------------------------------

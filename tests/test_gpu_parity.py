@@ -393,6 +393,25 @@ def test_masked_mean_bit_exact(S, k, D):
     assert np.array_equal(c_oracle.masked_mean(z, nid), want)
 
 
+
+def test_time2vec_wide_rows_and_huge_arguments():
+    """d > 128 (columns beyond the register-resident tiles) and millisecond-scale deltas whose
+    arguments exceed 2^22, where the kernel's short cosine hands over to libdevice cosf."""
+    from oracle.recency_oracle import time2vec
+    d = 150
+    rng = np.random.default_rng(3)
+    w = np.concatenate([[1.0, 0.5], 1.0 / 10 ** np.linspace(0, 9, d - 2)]).astype(np.float32)
+    b = rng.standard_normal(d).astype(np.float32)
+    dt = np.concatenate([rng.integers(0, 2_000_000_000, 3000), rng.integers(0, 5_000_000, 3000),
+                         [0, 4194303, 4194304, 4194305]]).astype(np.int64)
+    out = torch.empty((len(dt), d), dtype=torch.float32, device=DEV)
+    ddt, dw, db = dev(dt, torch.int64), dev(w, torch.float32), dev(b, torch.float32)
+    _cabi.check(_cabi.lib.tgm_time2vec(ddt.data_ptr(), len(dt), dw.data_ptr(), db.data_ptr(), d,
+                                       out.data_ptr(), stream()))
+    want = time2vec(dt, w, b, fused=True)
+    assert float(np.abs(out.cpu().numpy().astype(np.float64) - want).max()) <= 1e-5
+
+
 def test_time2vec_within_1e5():
     """tgm/nn/modules/time_encoding.py:12-24: cos(Linear(1,d)(float(dt))) with the shipped init
     w = 1/10^linspace(0,9,d), b = 0 -- and a trained-like b != 0.  Tolerance 1e-5 (north star).

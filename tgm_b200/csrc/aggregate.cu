@@ -25,6 +25,7 @@ masked_mean_kernel(const float *__restrict__ z, const int32_t *__restrict__ nid,
       const int d = int(i - s * D4);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       int cnt = 0;
+#pragma unroll 4  // four independent 128-bit loads in flight per thread; the adds stay in order
       for (int c = 0; c < k; ++c) {
         const float m = nid[s * k + c] != TGM_PADDED_NODE_ID ? 1.f : 0.f;
         cnt += m != 0.f;
@@ -55,21 +56,34 @@ masked_mean_kernel(const float *__restrict__ z, const int32_t *__restrict__ nid,
   }
 }
 
-// out[i,j] = cosf(fma(float(dt[i]), w[j], b[j])): int64 -> fp32 cast (time_encoding.py:23), then
+// out[r,j] = cos(fma(float(dt[r]), w[j], b[j])): int64 -> fp32 cast (time_encoding.py:23), then
 // nn.Linear(1,d), whose batched CPU GEMM (and cuBLAS on the reference's CUDA path) fuses the
 // multiply-add into ONE rounding -- verified against torch CPU: 100% of arguments equal the fused
 // form, 80% the two-rounding form; with arguments up to 2.7e6 (ulp 0.25) the choice decides the
-// result.  Full-range cosf (no fast-math).
+// result.  One warp per row, lanes along the d columns (coalesced 4*d-byte row stores, no integer
+// divisions); the weights of the first four column tiles stay in registers; cosine = t2v_cos
+// (common.cuh: 1.6e-7 abs error, 15 instructions).
 __global__ void __launch_bounds__(256)
 time2vec_kernel(const int64_t *__restrict__ dt, int64_t n, const float *__restrict__ w,
                 const float *__restrict__ b, int d, float *__restrict__ out) {
-  const int64_t total = n * d;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t r = i / d;
-    const int j = int(i - r * d);
+  const int lane = threadIdx.x & 31;
+  float wr[4], br[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int c = lane + 32 * t;
+    wr[t] = c < d ? __ldg(w + c) : 0.f;
+    br[t] = c < d ? __ldg(b + c) : 0.f;
+  }
+  const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
     const float x = float(dt[r]);
-    out[i] = cosf(__fmaf_rn(x, __ldg(w + j), __ldg(b + j)));
+    float *o = out + r * d;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int c = lane + 32 * t;
+      if (c < d) o[c] = t2v_cos(__fmaf_rn(x, wr[t], br[t]));
+    }
+    for (int c = 128 + lane; c < d; c += 32) o[c] = t2v_cos(__fmaf_rn(x, __ldg(w + c), __ldg(b + c)));
   }
 }
 
@@ -95,7 +109,7 @@ extern "C" int tgm_time2vec(const int64_t *dt, int64_t n, const float *w, const 
   TGM_REQUIRE(n >= 0 && d >= 1, "tgm_time2vec: bad sizes");
   if (n == 0) return TGM_OK;
   TGM_REQUIRE(dt && w && b && out, "tgm_time2vec: NULL array argument");
-  time2vec_kernel<<<grid_for(n * d, 256, 8), 256, 0, as_stream(stream)>>>(dt, n, w, b, d, out);
+  time2vec_kernel<<<grid_for(n, 8, 8), 256, 0, as_stream(stream)>>>(dt, n, w, b, d, out);
   TGM_LAUNCH_CHECK();
   return TGM_OK;
 }

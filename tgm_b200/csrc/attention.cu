@@ -96,31 +96,6 @@ __global__ void cos_kernel(const float *__restrict__ b, int n, float *__restrict
 // time 0).
 constexpr int kAttnThreads = 128;
 
-// cos(a) for the Time2Vec argument a = fl32(fma(dt, w, b)), |error| <= 1.6e-7 for |a| < 2^22
-// (checked against float64 over 1e7 arguments up to 4e6): q = rint(a / pi) by the magic-number
-// add, a three-term Cody-Waite reduction with FMAs (pi = C1 - D1 - D2), a degree-14 Taylor
-// polynomial on |r| <~ 1.75 and the sign from the parity of q.  15 instructions against ~47 for
-// libdevice cosf's fast path; larger arguments take cosf.
-__device__ __forceinline__ float t2v_cos(float a) {
-  if (!(fabsf(a) < 4194304.f)) return cosf(a);
-  const float kMagic = 12582912.f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
-  const float t = __fmaf_rn(a, 0.318309886183790672f, kMagic);
-  const float q = t - kMagic;
-  float r = __fmaf_rn(q, -3.1415927410125732f, a);
-  r = __fmaf_rn(q, 8.742277657347586e-08f, r);
-  r = __fmaf_rn(q, 3.4302490200117637e-15f, r);
-  const float x2 = r * r;
-  float p = -1.1470745597729725e-11f;          // -1/14!
-  p = __fmaf_rn(p, x2, 2.08767569878681e-09f);  //  1/12!
-  p = __fmaf_rn(p, x2, -2.755731922398589e-07f);
-  p = __fmaf_rn(p, x2, 2.48015873015873e-05f);
-  p = __fmaf_rn(p, x2, -1.388888888888889e-03f);
-  p = __fmaf_rn(p, x2, 4.1666666666666664e-02f);
-  p = __fmaf_rn(p, x2, -0.5f);
-  p = __fmaf_rn(p, x2, 1.0f);
-  return __uint_as_float(__float_as_uint(p) ^ ((__float_as_uint(t) & 1u) << 31));
-}
-
 __device__ __forceinline__ void cp_async16(float *smem_dst, const float *gmem_src) {
   const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");

@@ -296,7 +296,7 @@ def masked_mean(z: Tensor, nbr_nids: Tensor) -> Tensor:
     S, k, D = z.shape
     z = _f32(z)
     nid = nbr_nids.to(device=dev, dtype=torch.int32).contiguous()
-    out = torch.zeros((S, D), dtype=torch.float32, device=dev)
+    out = torch.empty((S, D), dtype=torch.float32, device=dev)  # every element is written
     _cabi.check(_cabi.lib.tgm_masked_mean(z.data_ptr(), nid.data_ptr(), S, k, D, out.data_ptr(),
                                           _cabi.current_stream(dev)))
     return out
