@@ -51,7 +51,9 @@ int tgm_device_count(void);
 
 /* Tuning switches (process-wide).  "csr_feature_copy": 1 (default) = the hop-0 window sampler moves
  * feature rows with the TMA unit (cp.async.bulk through shared-memory stages), 0 = with the warp's
- * own loads/stores.  Results are identical. */
+ * own loads/stores.  Results are identical.  "gemm_fastf32": 1 (default) = token-sized fp32 GEMMs of
+ * the transformer layers run on the tensor cores (tcgen05, fp32-accurate 9xBF16 emulation), 0 = on
+ * cuBLAS's SIMT SGEMM; both hold the 1e-5 parity bar. */
 int tgm_set_option(const char *name, int value);
 
 /* ------------------------------------------------------------------------------------------

@@ -33,6 +33,14 @@ struct DeviceGuard {
   int target = -1;
 };
 
+// gemm_fastf32.cu: fp32-accurate GEMM on the tcgen05 tensor cores (CUTLASS FastF32 collective).
+// out[S,N] = act(A[S,K] W[N,K]^T + bias[N] (+ residual[S,N])), act = exact GELU when `gelu`;
+// residual may alias out.  Returns 1 = computed, 0 = not applicable (caller uses cuBLAS), < 0 = error.
+bool fastf32_available();
+int fastf32_linear(int64_t S, int N, int K, const float *A, const float *W, const float *bias,
+                   const float *residual, int gelu, float *out, cudaStream_t stream);
+extern int g_gemm_fastf32;  // tgm_set_option("gemm_fastf32", 0|1); default 1
+
 inline cudaStream_t as_stream(tgm_stream s) { return reinterpret_cast<cudaStream_t>(s); }
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

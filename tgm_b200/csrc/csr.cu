@@ -1158,6 +1158,11 @@ extern "C" int tgm_set_option(const char *name, int value) {
     g_csr_tma_ctas_per_sm = value;
     return TGM_OK;
   }
+  if (std::strcmp(name, "gemm_fastf32") == 0) {
+    TGM_REQUIRE(value == 0 || value == 1, "tgm_set_option: gemm_fastf32 must be 0 (cuBLAS) or 1 (tensor cores)");
+    tgm::g_gemm_fastf32 = value;
+    return TGM_OK;
+  }
   return fail(TGM_ERR_INVALID, std::string("tgm_set_option: unknown option ") + name);
 }
 

@@ -64,7 +64,7 @@ int blas_fail3(cublasStatus_t s, const char *what) {
     if (_s != CUBLAS_STATUS_SUCCESS) return blas_fail3(_s, #expr); \
   } while (0)
 
-// C[S,N] = A[S,K] . W[N,K]^T (row-major)
+// C[S,N] = A[S,K] . W[N,K]^T (row-major), cuBLAS true-fp32 SGEMM
 cublasStatus_t gemm_nt3(cublasHandle_t h, int64_t S, int N, int K, const float *A, const float *W,
                         float *C) {
   const float one = 1.f, zero = 0.f;
@@ -151,13 +151,13 @@ __global__ void add_bias_kernel(float *__restrict__ x, const float *__restrict__
     x[i] = v;
   }
 }
-// x += y + b   (residual connection with the bias of the preceding Linear)
-__global__ void residual_bias_kernel(float *__restrict__ x, const float *__restrict__ y,
+// out = r + (y + b)   (residual connection with the bias of the preceding Linear; out may alias r)
+__global__ void residual_bias_kernel(float *out, const float *r, const float *__restrict__ y,
                                      const float *__restrict__ b, int64_t rows, int cols) {
   const int64_t total = rows * cols;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += int64_t(gridDim.x) * blockDim.x)
-    x[i] = x[i] + (y[i] + __ldg(b + int(i % cols)));
+    out[i] = r[i] + (y[i] + __ldg(b + int(i % cols)));
 }
 
 __global__ void __launch_bounds__(256)
@@ -231,6 +231,28 @@ int dup(tgm_dyg *m, float **dst, const float *src, size_t n) {
   TGM_CUDA(cudaMalloc(dst, (n ? n : 1) * sizeof(float)));
   m->owned.push_back(*dst);
   if (n) TGM_CUDA(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyDefault));
+  return TGM_OK;
+}
+
+// out[S,N] = act(A[S,K] W[N,K]^T + b (+ residual)); residual may alias out, `tmp` is [S,N] scratch.
+// Token-sized linears run on the tensor cores with the bias / residual / GELU fused into the
+// epilogue (gemm_fastf32.cu: fp32-accurate 9xBF16 emulation on tcgen05, 1.6x cuBLAS's SIMT SGEMM at
+// a quarter of its rounding error); small or unaligned ones use cuBLAS (true fp32) + one
+// elementwise pass.
+int linear(cublasHandle_t blas, int64_t S, int N, int K, const float *A, const float *W,
+           const float *b, const float *residual, int gelu, float *out, float *tmp,
+           cudaStream_t st) {
+  if (g_gemm_fastf32 && S >= 2048) {
+    const int rc = fastf32_linear(S, N, K, A, W, b, residual, gelu, out, st);
+    if (rc != 0) return rc < 0 ? rc : TGM_OK;
+  }
+  float *dst = residual ? tmp : out;
+  DYG_BLAS(gemm_nt3(blas, S, N, K, A, W, dst));
+  if (residual)
+    residual_bias_kernel<<<grid_for(S * N, 256, 8), 256, 0, st>>>(out, residual, tmp, b, S, N);
+  else
+    add_bias_kernel<<<grid_for(S * N, 256, 8), 256, 0, st>>>(out, b, S, N, gelu);
+  TGM_LAUNCH_CHECK();
   return TGM_OK;
 }
 
@@ -378,10 +400,9 @@ extern "C" int tgm_dyg_forward(tgm_dyg *m, const float *node_x, int64_t num_node
     layernorm_kernel<<<grid_for(tokens, 8, 8), 256, 0, st>>>(m->X, ly.ln0_w, ly.ln0_b, tokens, E,
                                                              m->eps, m->Xn);
     TGM_LAUNCH_CHECK();
-    DYG_BLAS(gemm_nt3(m->blas, tokens, 3 * E, E, m->Xn, ly.in_w, m->QKV));
-    add_bias_kernel<<<grid_for(tokens * 3 * E, 256, 8), 256, 0, st>>>(m->QKV, ly.in_b, tokens,
-                                                                      3 * E, 0);
-    TGM_LAUNCH_CHECK();
+    if (int rc = linear(m->blas, tokens, 3 * E, E, m->Xn, ly.in_w, ly.in_b, nullptr, 0, m->QKV,
+                        nullptr, st))
+      return rc;
     for (int h = 0; h < H; ++h)  // S[b,h,q,k] = Q_bh[q,:] . K_bh[k,:]
       DYG_BLAS(cublasSgemmStridedBatched(
           m->blas, CUBLAS_OP_T, CUBLAS_OP_N, T, T, hd, &one, m->QKV + E + h * hd, 3 * E,
@@ -394,21 +415,17 @@ extern "C" int tgm_dyg_forward(tgm_dyg *m, const float *node_x, int64_t num_node
           m->blas, CUBLAS_OP_N, CUBLAS_OP_N, hd, T, T, &one, m->QKV + 2 * E + h * hd, 3 * E,
           int64_t(T) * 3 * E, m->S + size_t(h) * T * T, T, int64_t(H) * T * T, &zero,
           m->O + h * hd, E, int64_t(T) * E, int(B)));
-    DYG_BLAS(gemm_nt3(m->blas, tokens, E, E, m->O, ly.out_w, m->tmp));
-    residual_bias_kernel<<<grid_for(tokens * E, 256, 8), 256, 0, st>>>(m->X, m->tmp, ly.out_b,
-                                                                       tokens, E);
-    TGM_LAUNCH_CHECK();
+    if (int rc = linear(m->blas, tokens, E, E, m->O, ly.out_w, ly.out_b, m->X, 0, m->X, m->tmp, st))
+      return rc;
     layernorm_kernel<<<grid_for(tokens, 8, 8), 256, 0, st>>>(m->X, ly.ln1_w, ly.ln1_b, tokens, E,
                                                              m->eps, m->Xn);
     TGM_LAUNCH_CHECK();
-    DYG_BLAS(gemm_nt3(m->blas, tokens, 4 * E, E, m->Xn, ly.f1_w, m->F1));
-    add_bias_kernel<<<grid_for(tokens * 4 * E, 256, 8), 256, 0, st>>>(m->F1, ly.f1_b, tokens,
-                                                                      4 * E, 1);
-    TGM_LAUNCH_CHECK();
-    DYG_BLAS(gemm_nt3(m->blas, tokens, E, 4 * E, m->F1, ly.f2_w, m->tmp));
-    residual_bias_kernel<<<grid_for(tokens * E, 256, 8), 256, 0, st>>>(m->X, m->tmp, ly.f2_b,
-                                                                       tokens, E);
-    TGM_LAUNCH_CHECK();
+    if (int rc = linear(m->blas, tokens, 4 * E, E, m->Xn, ly.f1_w, ly.f1_b, nullptr, 1, m->F1,
+                        nullptr, st))
+      return rc;
+    if (int rc = linear(m->blas, tokens, E, 4 * E, m->F1, ly.f2_w, ly.f2_b, m->X, 0, m->X, m->tmp,
+                        st))
+      return rc;
   }
   meanpool_kernel<<<grid_for(2 * B * E, 256, 8), 256, 0, st>>>(m->X, B, NP, E, m->pooled);
   TGM_LAUNCH_CHECK();
