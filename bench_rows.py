@@ -437,7 +437,9 @@ def row_dygformer():
     flops = 2 * (2 * tok * E_ * (3 * E_ + E_ + 8 * E_) + 2 * 2 * B * 2 * (2 * L) ** 2 * (E_ // 2))
     emit('A5 DyGFormer forward (200 edges -> 400 sequences of 32, 4x50 channels, 2 layers)', value=ms,
          unit='ms/call', higher_is_better=False, dense_gflop=flops / 1e9,
-         note='frontend kernel (gather, Time2Vec, exact co-occurrence counts) + fp32 cuBLAS transformer',
+         note='frontend kernel (gather, Time2Vec, exact co-occurrence counts) + transformer: token linears on '
+              'the tensor cores (tcgen05, fp32-accurate 9xBF16 emulation, fused bias/residual/GELU), '
+              'per-head attention products on cuBLAS fp32',
          cpu_baseline={'value': t_cpu * 1e3, 'unit': 'ms/call', 'kind': 'port', 'cores': os.cpu_count(),
                        'sample': 'numpy oracle of the same call'})
 
