@@ -578,6 +578,35 @@ def _hooked_loader(dg, window, **kw):
     return DGDataLoader(dg, batch_size=3, hook_manager=hm, **kw)
 
 
+
+@pytest.mark.parametrize('lo,hi,bs', [(None, None, 7), (5, 93, 10), (10, 100, 10), (3, 4, 5),
+                                      (0, 57, 57), (41, None, 16)])
+def test_loader_fast_path_equals_slice_and_materialize(lo, hi, bs):
+    """The loader's slab fast path (edge-only device stores) yields exactly the batches of the
+    general slice_events + materialize path (loader.py:136-170, graph.py:73-152), for index-sliced
+    views whose start is not a multiple of the batch size, short tails and drop_last."""
+    rng = np.random.default_rng(7)
+    E, N = 100, 30
+    ei = torch.from_numpy(rng.integers(0, N, (E, 2)).astype(np.int32))
+    t = torch.from_numpy(np.sort(rng.integers(0, 40, E)).astype(np.int64))
+    x = torch.from_numpy(rng.standard_normal((E, 3)).astype(np.float32))
+    dg = DGraph(DGData.from_raw(t, ei, x), device=DEV).slice_events(lo, hi)
+    for kw in ({}, {'drop_last': True}):
+        fast = DGDataLoader(dg, batch_size=bs, **kw)
+        slow = DGDataLoader(dg, batch_size=bs, **kw)
+        assert fast._fast is not None
+        slow._fast = None
+        a, b = list(fast), list(slow)
+        assert len(a) == len(b) and (len(a) > 0 or kw)
+        for u, v in zip(a, b):
+            for name in ('edge_src', 'edge_dst', 'edge_time', 'edge_x'):
+                p, q = getattr(u, name), getattr(v, name)
+                assert (p is None) == (q is None)
+                if p is not None:
+                    assert p.dtype == q.dtype and torch.equal(p, q) and p.is_cuda
+            assert u.node_x is None and u.edge_type is None
+
+
 @pytest.mark.parametrize('window', [0, 4])
 def test_no_edge_features_give_zero_width_feature_tensors(window):
     batch = next(iter(_hooked_loader(_tiny_dg(feat=False), window)))
