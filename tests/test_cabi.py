@@ -87,3 +87,25 @@ def test_device_entry_points_fail_loudly_without_gpu():
     assert rc < 0 and not h.value
     with pytest.raises(_cabi.TGMNativeError):
         _cabi.require_device()
+
+
+def test_new_entry_points_fail_loudly_without_gpu_or_arguments():
+    """tgm_dedup_*, tgm_gae_*, tgm_recency_step: argument errors and the no-device case are
+    reported through the status code + tgm_last_error, never by falling back to the host."""
+    rc = _cabi.lib.tgm_recency_step(None, None, None, None, None, 1, 0, 1, None, None, None, None,
+                                    None, None, None)
+    assert rc == -1 and 'handle is NULL' in _cabi.last_error()
+    rc = _cabi.lib.tgm_dedup_map(None, None, None, 8, None, 4, None, None)
+    assert rc == -1 and 'NULL' in _cabi.last_error()
+    assert _cabi.lib.tgm_set_option(b'gemm_fastf32', 1) == 0
+    assert _cabi.lib.tgm_set_option(b'gemm_fastf32', 3) == -1
+    assert _cabi.lib.tgm_set_option(b'no_such_option', 1) == -1
+    if _cabi.device_count() > 0:
+        return
+    z = np.zeros(64, np.float32)
+    P = z.ctypes.data_as(ctypes.c_void_p)
+    h = ctypes.c_void_p()
+    rc = _cabi.lib.tgm_gae_create(ctypes.byref(h), 4, 4, 2, 0, 2, *[P] * 11, 0)
+    assert rc == -3 and not h.value and 'no such CUDA device' in _cabi.last_error()
+    w, p, b = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    assert _cabi.lib.tgm_dedup_sizes(1000, ctypes.byref(w), ctypes.byref(p), ctypes.byref(b)) < 0
