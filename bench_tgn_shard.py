@@ -6,8 +6,9 @@ boundary.  Launch with torchrun (one rank per GPU):
         --master-port 29533 bench_tgn_shard.py --batches 500
 
 Every rank owns a contiguous time range of the stream (tgm_b200/parallel.py), samples k=10 recent
-neighbours for its batches from the replicated store (one pre-sampled window), runs
-TGNMemory.forward + update_state per batch, then all ranks reconcile memory with
+neighbours for its batches from the replicated store (one pre-sampled window), runs the model step
+of examples/linkproppred/tgn.py per batch (device dedup -> TGNMemory.forward -> GraphAttentionEmbedding
+-> update_state; `--no-embedding` keeps the memory state machine only), then all ranks reconcile memory with
 `merge_node_memory` (the single collective of the path).  Prints one JSON line on rank 0; times
 are CUDA-event times, max over ranks."""
 from __future__ import annotations
@@ -25,7 +26,8 @@ sys.path.insert(0, ROOT)
 
 from tgm_b200 import RecencyCSR  # noqa: E402
 from tgm_b200.core.storage import DeviceCOOStorage  # noqa: E402
-from tgm_b200.nn import TGNMemory  # noqa: E402
+from tgm_b200.hooks.dedup import _BatchIdSet  # noqa: E402
+from tgm_b200.nn import GraphAttentionEmbedding, TGNMemory  # noqa: E402
 from tgm_b200.parallel import max_over_ranks, merge_node_memory, shard_batches, sum_over_ranks  # noqa: E402
 
 
@@ -37,6 +39,8 @@ def main():
     ap.add_argument('--k', type=int, default=10)
     ap.add_argument('--batch-size', type=int, default=200)
     ap.add_argument('--batches', type=int, default=500, help='loader batches per rank')
+    ap.add_argument('--no-embedding', dest='embedding', action='store_false',
+                    help='memory state machine only (the first measurement of the round)')
     a = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -58,20 +62,36 @@ def main():
     hi = min(shard.edge_hi, lo + a.batches * bs)
     torch.manual_seed(0)
     mem = TGNMemory(N, D, 100, 100).to(dev)
+    enc = GraphAttentionEmbedding(100, 100, D, mem.time_enc).to(dev).eval()
     mem.train()
     mem.reset_state()
     touched = torch.zeros(N, dtype=torch.bool, device=dev)
 
     def run_shard():
-        hops = csr.sample_window(lo, hi, [k])  # neighbourhoods of every batch of the shard
+        """The per-batch model step of examples/linkproppred/tgn.py (without the decoder): sampled
+        neighbourhoods -> unique nodes -> memory.forward -> GraphAttentionEmbedding over the
+        (seed -> neighbour) edge list -> memory.update_state."""
+        hop = csr.sample_window(lo, hi, [k])[0]  # neighbourhoods of every batch of the shard
+        z = None
         for b_lo in range(lo, hi, bs):
             b_hi = min(b_lo + bs, hi)
             s, d = src[b_lo:b_hi], dst[b_lo:b_hi]
-            n_id = torch.cat([s, d]).long()
-            mem(n_id)
+            r0, r1 = 2 * (b_lo - lo), 2 * (b_hi - lo)
+            nbr = hop.nbr_nids[r0:r1].reshape(-1)
+            ids = _BatchIdSet(N, dev)
+            uniq = ids.unique([(s, False), (d, False), (nbr, True)])
+            if a.embedding:
+                keep = nbr != -1
+                seeds = torch.cat([s, d]).repeat_interleave(k)
+                ei = torch.stack([ids.local(seeds[keep]), ids.local(nbr[keep])]).long()
+                zz, lu = mem(uniq)
+                z = enc(zz, lu, ei, hop.nbr_edge_time[r0:r1].reshape(-1)[keep],
+                        hop.nbr_edge_x[r0:r1].reshape(-1, D)[keep])
+            else:
+                mem(torch.cat([s, d]).long())
             mem.update_state(s, d, t[b_lo:b_hi], x[b_lo:b_hi])
-            touched[n_id] = True
-        return hops
+            touched[torch.cat([s, d]).long()] = True  # rows this shard's update_state wrote
+        return z
 
     def barrier():
         if world > 1:
@@ -99,7 +119,9 @@ def main():
     if rank == 0:
         row_bytes = N * (100 * 4 + 8 + 4)
         print(json.dumps({
-            'row': 'config 4: TGN memory, time-sharded, memory join at the shard boundary',
+            'row': 'config 4: TGN ' + ('memory + attention embedding (model step without the decoder)'
+                                       if a.embedding else 'memory') +
+                   ', time-sharded, memory join at the shard boundary',
             'n_gpus': world, 'batches_per_rank': (hi - lo) // bs, 'nodes': N,
             'events_per_s': events / ((shard_ms + merge_ms) * 1e-3),
             'shard_ms': shard_ms, 'merge_ms': merge_ms,
