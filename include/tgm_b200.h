@@ -350,6 +350,29 @@ int tgm_dyg_forward(tgm_dyg *, const float *node_x, int64_t num_nodes, const int
                     const int64_t *nbr_t, const float *nbr_x, int64_t B, float *out_src,
                     float *out_dst, tgm_stream stream);
 
+/* Training support for DyGFormer (dropout 0).  tgm_dyg_set_params refreshes the handle's parameter
+ * copies in place after an optimizer step (same shapes as at creation).  tgm_dyg_backward
+ * recomputes the forward pass, keeping the activations the chain rule needs, and OVERWRITES every
+ * gradient buffer of `grads` (torch layouts, as in tgm_dyg_params) with the gradient of
+ * sum(out_src * d_src) + sum(out_dst * d_dst) -- what loss.backward() leaves in .grad of the
+ * reference module (tgm/nn/encoder/dygformer.py:243-431 under autograd).  Inputs as tgm_dyg_forward;
+ * d_src, d_dst f32[B,out_dim].  Input features receive no gradient. */
+typedef struct {
+  float *in_proj_w, *in_proj_b, *out_proj_w, *out_proj_b, *ffn1_w, *ffn1_b, *ffn2_w, *ffn2_b;
+  float *ln0_w, *ln0_b, *ln1_w, *ln1_b;
+} tgm_dyg_layer_grads;
+typedef struct {
+  float *t2v_w, *t2v_b, *cooc_w1, *cooc_b1, *cooc_w2, *cooc_b2;
+  float *proj_w[4], *proj_b[4];
+  tgm_dyg_layer_grads *layers; /* [num_layers] */
+  float *out_w, *out_b;
+} tgm_dyg_grads;
+int tgm_dyg_set_params(tgm_dyg *, const tgm_dyg_params *params, tgm_stream stream);
+int tgm_dyg_backward(tgm_dyg *, const float *node_x, int64_t num_nodes, const int32_t *src,
+                     const int32_t *dst, const int64_t *edge_time, const int32_t *nbrs,
+                     const int64_t *nbr_t, const float *nbr_x, int64_t B, const float *d_src,
+                     const float *d_dst, const tgm_dyg_grads *grads, tgm_stream stream);
+
 /* ------------------------------------------------------------------------------------------
  * TGN embedding.  Replaces GraphAttentionEmbedding (tgm/nn/encoder/tgn.py:14-40) as called from
  * examples/linkproppred/tgn.py:74-98: rel_t = last_update[edge_src] - t, edge_attr =

@@ -271,6 +271,48 @@ def test_dygformer_tensor_core_gemm_matches_cublas_path_and_oracle():
     assert max(np.abs(a - b).max() for a, b in zip(outs[0], outs[1])) <= TOL
 
 
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'nn_dyggrad_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[11:-4])
+def test_dygformer_gradients_match_reference_autograd(path):
+    """tgm_dyg_backward through autograd: .grad of every parameter after loss.backward() with
+    loss = sum(z_src * G_src) + sum(z_dst * G_dst), against the reference module's autograd
+    (train mode, dropout 0).  Relative tolerance 5e-4 of each gradient's largest entry (fp32 sums
+    over up to a few thousand terms, some through atomics)."""
+    z = np.load(path)
+    p = _params(z)
+    P_, NL, NH = int(z['patch_size']), int(z['num_layers']), int(z['num_heads'])
+    dN = p['projection_layer.node.weight'].shape[1] // P_
+    dE = p['projection_layer.edge.weight'].shape[1] // P_
+    m = DyGFormer(dN, dE, p['time_encoder.w.bias'].shape[0], p['projection_layer.node.weight'].shape[0],
+                  output_dim=p['output_layer.bias'].shape[0], patch_size=P_, num_layers=NL, num_heads=NH,
+                  dropout=0.0, max_input_sequence_length=z['nbrs'].shape[1] + 1)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+    m = m.to(DEV).train()
+    args = (T(z['node_x']), T(np.stack([z['src'], z['dst']])), T(z['t']), T(z['nbrs']), T(z['nt']), T(z['ef']))
+    zs, zd = m(*args)
+    assert np.abs(zs.detach().cpu().numpy() - z['z_src']).max() <= TOL
+    assert np.abs(zd.detach().cpu().numpy() - z['z_dst']).max() <= TOL
+    ((zs * T(z['G_src'])).sum() + (zd * T(z['G_dst'])).sum()).backward()
+    for name, prm in m.named_parameters():
+        want = z['g.' + name]
+        got = prm.grad.detach().cpu().numpy()
+        assert got.shape == want.shape, name
+        assert np.abs(got - want).max() <= 5e-4 * max(1e-2, np.abs(want).max()), name
+    # an optimizer step refreshes the handle's weights in place: the next forward differs
+    with torch.no_grad():
+        m.output_layer.weight.mul_(1.5)
+    zs2, _ = m(*args)
+    assert float((zs2 - zs).detach().abs().max()) > 1e-3
+
+
+def test_dygformer_refuses_training_with_dropout():
+    m = DyGFormer(3, 4, 6, 4, output_dim=5, num_layers=1, max_input_sequence_length=8).to(DEV).train()
+    with pytest.raises(RuntimeError, match='dropout=0'):
+        m(torch.zeros(5, 3, device=DEV), torch.zeros(2, 1, dtype=torch.int64, device=DEV),
+          torch.zeros(1, dtype=torch.int64, device=DEV), torch.zeros(2, 7, dtype=torch.int32, device=DEV),
+          torch.zeros(2, 7, dtype=torch.int64, device=DEV), torch.zeros(2, 7, 4, device=DEV))
+
+
 # ---- gradients: tgm_attn_backward vs the reference's autograd ------------------------------------
 def _close(got, want, what, rtol=2e-4):
     got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else got

@@ -350,3 +350,24 @@ def test_transformer_conv_oracle_agrees_with_an_independent_torch_restatement():
     enc = np.cos(((lu[ei[0]] - t).astype(np.float32)[:, None] * p['time_enc.w.weight'].reshape(1, -1)))
     want = _torch_transformer_conv(p, H, x, ei, np.concatenate([enc.astype(np.float32), msg], 1))
     assert np.abs(z - want).max() <= 1e-5
+
+
+# ---- DyGFormer gradients: the hand-derived backward vs the reference's autograd -----------------------
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'nn_dyggrad_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[11:-4])
+def test_dygformer_backward_oracle_matches_reference_autograd(path):
+    """oracle/nn_oracle.py::dygformer_backward (float64 chain rule) against .grad of every parameter
+    of the unmodified reference module after loss.backward() (tests/golden/make_golden_dygformer.py
+    ::run_grad)."""
+    from oracle import nn_oracle
+    z = np.load(path)
+    p = {k[2:]: z[k] for k in z.files if k.startswith('p.')}
+    g = nn_oracle.dygformer_backward(p, int(z['patch_size']), int(z['num_layers']), int(z['num_heads']),
+                                     z['node_x'], np.stack([z['src'], z['dst']]), z['t'], z['nbrs'],
+                                     z['nt'], z['ef'], z['G_src'], z['G_dst'])
+    names = [k[2:] for k in z.files if k.startswith('g.')]
+    assert set(names) == set(g) and len(names) >= 20
+    for name in names:
+        want = z['g.' + name]
+        assert g[name].shape == want.shape, name
+        assert np.abs(g[name] - want).max() <= 5e-5 * max(1.0, np.abs(want).max()), name

@@ -110,6 +110,9 @@ SIGNATURES = {
     'tgm_tgn_flush': (c_int, [c_void_p, c_void_p]),
     'tgm_dyg_create': (c_int, [POINTER(c_void_p), c_void_p, c_int]),
     'tgm_dyg_destroy': (None, [c_void_p]),
+    'tgm_dyg_set_params': (c_int, [c_void_p, c_void_p, c_void_p]),
+    'tgm_dyg_backward': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     'tgm_dyg_forward': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                 c_void_p]),
@@ -147,6 +150,14 @@ class DygParams(ctypes.Structure):
                                         'seq_len')] +
                 [('ln_eps', c_float)] +
                 [(n, c_void_p) for n in ('t2v_w', 't2v_b', 'cooc_w1', 'cooc_b1', 'cooc_w2',
+                                         'cooc_b2')] +
+                [('proj_w', c_void_p * 4), ('proj_b', c_void_p * 4),
+                 ('layers', POINTER(DygLayer)), ('out_w', c_void_p), ('out_b', c_void_p)])
+
+
+class DygGrads(ctypes.Structure):
+    """tgm_dyg_grads (include/tgm_b200.h); the per-layer table has DygLayer's field order."""
+    _fields_ = ([(n, c_void_p) for n in ('t2v_w', 't2v_b', 'cooc_w1', 'cooc_b1', 'cooc_w2',
                                          'cooc_b2')] +
                 [('proj_w', c_void_p * 4), ('proj_b', c_void_p * 4),
                  ('layers', POINTER(DygLayer)), ('out_w', c_void_p), ('out_b', c_void_p)])

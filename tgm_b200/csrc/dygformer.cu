@@ -42,9 +42,27 @@ struct tgm_dyg {
   float *feat[4] = {};  // [2B, L, d_c]
   float *X = nullptr, *Xn = nullptr, *QKV = nullptr, *S = nullptr, *O = nullptr, *F1 = nullptr,
         *tmp = nullptr, *pooled = nullptr;
+  // backward (tgm_dyg_backward): per-layer saved activations + gradient scratch, grown on demand
+  int64_t bcap = 0;
+  struct Saved {
+    float *Xin = nullptr, *QKV = nullptr, *Pm = nullptr, *O = nullptr, *X1 = nullptr,
+          *F1pre = nullptr;
+  };
+  std::vector<Saved> saved;
+  float *dX = nullptr, *dXn = nullptr, *dQKV = nullptr, *dP = nullptr, *dO = nullptr,
+        *dF1 = nullptr, *G1 = nullptr, *dCh = nullptr, *dFeat = nullptr, *Gst = nullptr,
+        *dPool = nullptr;
+  void free_backward() {
+    for (Saved &sv : saved)
+      for (float **q : {&sv.Xin, &sv.QKV, &sv.Pm, &sv.O, &sv.X1, &sv.F1pre}) cudaFree(*q), *q = nullptr;
+    for (float **q : {&dX, &dXn, &dQKV, &dP, &dO, &dF1, &G1, &dCh, &dFeat, &Gst, &dPool})
+      cudaFree(*q), *q = nullptr;
+    bcap = 0;
+  }
   ~tgm_dyg() {
     if (device >= 0) {
       DeviceGuard g(device);
+      free_backward();
       for (float *p : owned) cudaFree(p);
       for (float *p : {feat[0], feat[1], feat[2], feat[3], X, Xn, QKV, S, O, F1, tmp, pooled})
         cudaFree(p);
@@ -234,6 +252,235 @@ int dup(tgm_dyg *m, float **dst, const float *src, size_t n) {
   return TGM_OK;
 }
 
+// ---- backward pieces (tgm_dyg_backward) -------------------------------------------------------------
+// C[M,N] = A[M,K] B[K,N] and C[Ka,Nb] = A[M,Ka]^T B[M,Nb], row-major with leading dimensions
+cublasStatus_t gemm_nn(cublasHandle_t h, int64_t M, int N, int K, const float *A, int lda,
+                       const float *B, int ldb, float *C, int ldc) {
+  const float one = 1.f, zero = 0.f;
+  return cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, N, int(M), K, &one, B, ldb, A, lda, &zero, C, ldc);
+}
+cublasStatus_t gemm_tn(cublasHandle_t h, int64_t M, int Ka, int Nb, const float *A, int lda,
+                       const float *B, int ldb, float *C, int ldc) {
+  const float one = 1.f, zero = 0.f;
+  return cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, Nb, Ka, int(M), &one, B, ldb, A, lda, &zero, C, ldc);
+}
+
+// out[c] += sum_r a[r, c]   (out zeroed by the caller); 32 columns x 8 row lanes per CTA
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float *__restrict__ a, int64_t rows, int cols, float *__restrict__ out) {
+  __shared__ float s[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (c < cols)
+    for (int64_t r = int64_t(blockIdx.y) * 8 + ty; r < rows; r += int64_t(gridDim.y) * 8)
+      acc += a[r * cols + c];
+  s[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += s[j][tx];
+    atomicAdd(out + c, t);
+  }
+}
+
+__global__ void gelu_fwd_kernel(const float *__restrict__ pre, int64_t n, float *__restrict__ act) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const float v = pre[i];
+    act[i] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  }
+}
+// d_pre = d_act * gelu'(pre), gelu'(x) = Phi(x) + x phi(x); in place on d
+__global__ void gelu_bwd_kernel(const float *__restrict__ pre, int64_t n, float *__restrict__ d) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const float v = pre[i];
+    const float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
+    d[i] *= cdf + v * pdf;
+  }
+}
+// LayerNorm backward, one warp per row: dx_total[r,:] += rstd * (dxh - mean(dxh) - xh * mean(dxh*xh))
+// with xh, rstd recomputed from x; dgamma/dbeta accumulated per CTA in shared memory, then atomics.
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                     const float *__restrict__ dy, int64_t rows, int cols, float eps,
+                     float *__restrict__ dx_total, float *__restrict__ dgamma,
+                     float *__restrict__ dbeta) {
+  extern __shared__ float s_acc[];  // [2][cols]
+  for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) s_acc[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int64_t r = int64_t(blockIdx.x) * wpb + (threadIdx.x >> 5); r < rows;
+       r += int64_t(gridDim.x) * wpb) {
+    const float *xr = x + r * cols, *dr = dy + r * cols;
+    float sum = 0.f;
+    for (int c = lane; c < cols; c += 32) sum += xr[c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / float(cols);
+    float var = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      const float d = xr[c] - mean;
+      var = fmaf(d, d, var);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / float(cols) + eps);
+    float m1 = 0.f, m2 = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      const float xh = (xr[c] - mean) * rstd, dxh = dr[c] * __ldg(w + c);
+      m1 += dxh;
+      m2 = fmaf(dxh, xh, m2);
+      atomicAdd(&s_acc[c], dr[c] * xh);
+      atomicAdd(&s_acc[cols + c], dr[c]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+      m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    }
+    m1 /= float(cols), m2 /= float(cols);
+    for (int c = lane; c < cols; c += 32) {
+      const float xh = (xr[c] - mean) * rstd, dxh = dr[c] * __ldg(w + c);
+      dx_total[r * cols + c] += rstd * (dxh - m1 - xh * m2);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    atomicAdd(dgamma + c, s_acc[c]);
+    atomicAdd(dbeta + c, s_acc[cols + c]);
+  }
+}
+
+// softmax backward in place on dp: ds = scale * p * (dp - sum(dp * p)); one warp per row
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const float *__restrict__ p, float *__restrict__ dp, int64_t rows, int cols,
+                   float scale) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int64_t r = int64_t(blockIdx.x) * wpb + (threadIdx.x >> 5); r < rows;
+       r += int64_t(gridDim.x) * wpb) {
+    const float *pr = p + r * cols;
+    float *dr = dp + r * cols;
+    float dot = 0.f;
+    for (int c = lane; c < cols; c += 32) dot = fmaf(dr[c], pr[c], dot);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    for (int c = lane; c < cols; c += 32) dr[c] = scale * pr[c] * (dr[c] - dot);
+  }
+}
+
+// dX[b, side*NP + p, :] = dpooled[side*B + b, :] / NP
+__global__ void meanpool_bwd_kernel(const float *__restrict__ dpooled, int64_t B, int NP, int E,
+                                    float *__restrict__ dX) {
+  const int64_t total = B * 2 * NP * E;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % E);
+    const int64_t tok = i / E, b = tok / (2 * NP);
+    const int side = int((tok - b * 2 * NP) / NP);
+    dX[i] = dpooled[(int64_t(side) * B + b) * E + c] / float(NP);
+  }
+}
+
+// channel c of the token gradient as a dense [2B*NP, C] matrix in the (side, b, patch) row order of
+// the feature tensors: dCh[(side*B + b)*NP + p, j] = dX[(b*2NP + side*NP + p)*E + c*C + j]
+__global__ void gather_channel_kernel(const float *__restrict__ dX, int64_t B, int NP, int E, int C,
+                                      int c, float *__restrict__ dCh) {
+  const int64_t total = 2 * B * NP * C;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int j = int(i % C);
+    const int64_t row = i / C, sb = row / NP, p = row - sb * NP;
+    const int64_t side = sb / B, b = sb - side * B;
+    dCh[i] = dX[(b * 2 * NP + side * NP + p) * E + int64_t(c) * C + j];
+  }
+}
+
+// Gradients of the Time2Vec weights and of the co-occurrence MLP from the per-position feature
+// gradients; one warp per sequence position (same indexing as dyg_frontend_kernel), accumulation in
+// shared memory per CTA, then global atomics.  d_time may be NULL-free: both are required.
+__global__ void __launch_bounds__(256)
+dyg_frontend_bwd_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                        const int64_t *__restrict__ edge_time, const int32_t *__restrict__ nbrs,
+                        const int64_t *__restrict__ nbr_t, int64_t B, int L, int dT, int C,
+                        const float *__restrict__ tw, const float *__restrict__ tb,
+                        const float *__restrict__ w1, const float *__restrict__ b1,
+                        const float *__restrict__ w2, const float *__restrict__ d_time,
+                        const float *__restrict__ d_cooc, float *__restrict__ g_tw,
+                        float *__restrict__ g_tb, float *__restrict__ g_w1, float *__restrict__ g_b1,
+                        float *__restrict__ g_w2, float *__restrict__ g_b2) {
+  extern __shared__ float sm[];
+  float *a_tw = sm, *a_tb = a_tw + dT, *a_w1 = a_tb + dT, *a_b1 = a_w1 + C, *a_b2 = a_b1 + C,
+        *a_w2 = a_b2 + C, *scratch = a_w2 + C * C;  // scratch: [warps][2C] (hsum, dh)
+  const int nacc = 2 * dT + 3 * C + C * C;
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float *hs = scratch + warp * 2 * C, *dh = hs + C;
+  const int k = L - 1;
+  const int64_t total = 2 * B * L;
+  for (int64_t i = int64_t(blockIdx.x) * wpb + warp; i < total; i += int64_t(gridDim.x) * wpb) {
+    const int64_t r = i / L;
+    const int l = int(i - r * L);
+    const int64_t pair = r < B ? r : r - B, other = r < B ? r + B : r - B;
+    const int32_t id = seq_id(src, dst, nbrs, B, k, r, l);
+    const bool padded = id == TGM_PADDED_NODE_ID;
+    if (!padded) {  // time channel: f = cos(dt w + b)  ->  d/dw = -sin(.) dt, d/db = -sin(.)
+      const int64_t tq = edge_time[pair];
+      const float dt = float(tq - (l == 0 ? tq : nbr_t[r * k + (l - 1)]));
+      for (int c = lane; c < dT; c += 32) {
+        const float d = -sinf(__fmaf_rn(dt, __ldg(tw + c), __ldg(tb + c))) * d_time[i * dT + c];
+        atomicAdd(a_tw + c, d * dt);
+        atomicAdd(a_tb + c, d);
+      }
+    }
+    int own = 0, cross = 0;
+    if (!padded) {
+      for (int base = 0; base < L; base += 32) {
+        const int j = base + lane;
+        const bool in = j < L;
+        const bool a = in && seq_id(src, dst, nbrs, B, k, r, j) == id;
+        const bool b = in && seq_id(src, dst, nbrs, B, k, other, j) == id;
+        own += __popc(__ballot_sync(0xffffffffu, a));
+        cross += __popc(__ballot_sync(0xffffffffu, b));
+      }
+    }
+    const float f0 = float(own), f1 = float(cross);
+    const float *dc = d_cooc + i * C;
+    for (int j = lane; j < C; j += 32) {
+      const float w = __ldg(w1 + j), bb = __ldg(b1 + j);
+      hs[j] = fmaxf(fmaf(w, f0, bb), 0.f) + fmaxf(fmaf(w, f1, bb), 0.f);
+      float acc = 0.f;  // dh[j] = sum_c W2[c, j] dc[c]
+      for (int c = 0; c < C; ++c) acc = fmaf(__ldg(w2 + c * C + j), dc[c], acc);
+      dh[j] = acc;
+      const float m0 = fmaf(w, f0, bb) > 0.f ? 1.f : 0.f, m1 = fmaf(w, f1, bb) > 0.f ? 1.f : 0.f;
+      atomicAdd(a_w1 + j, acc * (m0 * f0 + m1 * f1));
+      atomicAdd(a_b1 + j, acc * (m0 + m1));
+    }
+    __syncwarp();
+    for (int c = lane; c < C; c += 32) atomicAdd(a_b2 + c, 2.f * dc[c]);
+    for (int e = lane; e < C * C; e += 32) {  // dW2[c, j] += dc[c] * hsum[j]
+      const int c = e / C, j = e - c * C;
+      atomicAdd(a_w2 + e, dc[c] * hs[j]);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < dT; i += blockDim.x) {
+    atomicAdd(g_tw + i, a_tw[i]);
+    atomicAdd(g_tb + i, a_tb[i]);
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(g_w1 + i, a_w1[i]);
+    atomicAdd(g_b1 + i, a_b1[i]);
+    atomicAdd(g_b2 + i, a_b2[i]);
+  }
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) atomicAdd(g_w2 + i, a_w2[i]);
+}
+
 // out[S,N] = act(A[S,K] W[N,K]^T + b (+ residual)); residual may alias out, `tmp` is [S,N] scratch.
 // Token-sized linears run on the tensor cores with the bias / residual / GELU fused into the
 // epilogue (gemm_fastf32.cu: fp32-accurate 9xBF16 emulation on tcgen05, 1.6x cuBLAS's SIMT SGEMM at
@@ -253,6 +500,32 @@ int linear(cublasHandle_t blas, int64_t S, int N, int K, const float *A, const f
   else
     add_bias_kernel<<<grid_for(S * N, 256, 8), 256, 0, st>>>(out, b, S, N, gelu);
   TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+
+int reserve_forward(tgm_dyg *m, int64_t B, cudaStream_t st) {
+  const int L = m->L, E = m->E, H = m->H, T = 2 * m->NP;
+  const int dims[4] = {m->dN, m->dE, m->dT, m->C};
+  if (B > m->cap) {
+    TGM_CUDA(cudaStreamSynchronize(st));
+    for (float **p : {&m->feat[0], &m->feat[1], &m->feat[2], &m->feat[3], &m->X, &m->Xn, &m->QKV,
+                      &m->S, &m->O, &m->F1, &m->tmp, &m->pooled}) {
+      cudaFree(*p);
+      *p = nullptr;
+    }
+    m->cap = 0;
+    const size_t cb = size_t(B + B / 4 + 1), ct = cb * T;
+    for (int c = 0; c < 4; ++c) TGM_CUDA(cudaMalloc(&m->feat[c], 2 * cb * L * dims[c] * 4));
+    TGM_CUDA(cudaMalloc(&m->X, ct * E * 4));
+    TGM_CUDA(cudaMalloc(&m->Xn, ct * E * 4));
+    TGM_CUDA(cudaMalloc(&m->QKV, ct * 3 * E * 4));
+    TGM_CUDA(cudaMalloc(&m->S, cb * H * T * T * 4));
+    TGM_CUDA(cudaMalloc(&m->O, ct * E * 4));
+    TGM_CUDA(cudaMalloc(&m->F1, ct * 4 * E * 4));
+    TGM_CUDA(cudaMalloc(&m->tmp, ct * E * 4));
+    TGM_CUDA(cudaMalloc(&m->pooled, 2 * cb * E * 4));
+    m->cap = int64_t(cb);
+  }
   return TGM_OK;
 }
 
@@ -349,26 +622,7 @@ extern "C" int tgm_dyg_forward(tgm_dyg *m, const float *node_x, int64_t num_node
   const int dims[4] = {m->dN, m->dE, m->dT, C};
   const int64_t tokens = B * T;
   TGM_REQUIRE(tokens * 4 * E < (int64_t(1) << 31), "tgm_dyg_forward: batch too large");
-  if (B > m->cap) {
-    TGM_CUDA(cudaStreamSynchronize(st));
-    for (float **p : {&m->feat[0], &m->feat[1], &m->feat[2], &m->feat[3], &m->X, &m->Xn, &m->QKV,
-                      &m->S, &m->O, &m->F1, &m->tmp, &m->pooled}) {
-      cudaFree(*p);
-      *p = nullptr;
-    }
-    m->cap = 0;
-    const size_t cb = size_t(B + B / 4 + 1), ct = cb * T;
-    for (int c = 0; c < 4; ++c) TGM_CUDA(cudaMalloc(&m->feat[c], 2 * cb * L * dims[c] * 4));
-    TGM_CUDA(cudaMalloc(&m->X, ct * E * 4));
-    TGM_CUDA(cudaMalloc(&m->Xn, ct * E * 4));
-    TGM_CUDA(cudaMalloc(&m->QKV, ct * 3 * E * 4));
-    TGM_CUDA(cudaMalloc(&m->S, cb * H * T * T * 4));
-    TGM_CUDA(cudaMalloc(&m->O, ct * E * 4));
-    TGM_CUDA(cudaMalloc(&m->F1, ct * 4 * E * 4));
-    TGM_CUDA(cudaMalloc(&m->tmp, ct * E * 4));
-    TGM_CUDA(cudaMalloc(&m->pooled, 2 * cb * E * 4));
-    m->cap = int64_t(cb);
-  }
+  if (int rc = reserve_forward(m, B, st)) return rc;
   DYG_BLAS(cublasSetStream(m->blas, st));
   const float one = 1.f, zero = 0.f;
 
@@ -434,5 +688,303 @@ extern "C" int tgm_dyg_forward(tgm_dyg *m, const float *node_x, int64_t num_node
   add_bias_kernel<<<grid_for(B * m->out, 256, 8), 256, 0, st>>>(out_src, m->out_b, B, m->out, 0);
   add_bias_kernel<<<grid_for(B * m->out, 256, 8), 256, 0, st>>>(out_dst, m->out_b, B, m->out, 0);
   TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+
+// ---- training support ----------------------------------------------------------------------------
+namespace {
+
+int copy_param(float *dst, const float *src, size_t n, cudaStream_t st) {
+  TGM_REQUIRE(src != nullptr, "tgm_dyg_set_params: NULL parameter");
+  if (n) TGM_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDefault, st));
+  return TGM_OK;
+}
+
+int reserve_backward(tgm_dyg *m, int64_t B, cudaStream_t st) {
+  if (B <= m->bcap && int(m->saved.size()) == m->layers) return TGM_OK;
+  TGM_CUDA(cudaStreamSynchronize(st));
+  m->free_backward();
+  m->saved.assign(m->layers, tgm_dyg::Saved{});
+  const int L = m->L, E = m->E, H = m->H, T = 2 * m->NP, C = m->C;
+  const size_t cb = size_t(B + B / 4 + 1), ct = cb * T;
+  const int dmax = std::max(m->dT, C);
+  for (tgm_dyg::Saved &sv : m->saved) {
+    TGM_CUDA(cudaMalloc(&sv.Xin, ct * E * 4));
+    TGM_CUDA(cudaMalloc(&sv.QKV, ct * 3 * E * 4));
+    TGM_CUDA(cudaMalloc(&sv.Pm, cb * H * T * T * 4));
+    TGM_CUDA(cudaMalloc(&sv.O, ct * E * 4));
+    TGM_CUDA(cudaMalloc(&sv.X1, ct * E * 4));
+    TGM_CUDA(cudaMalloc(&sv.F1pre, ct * 4 * E * 4));
+  }
+  TGM_CUDA(cudaMalloc(&m->dX, ct * E * 4));
+  TGM_CUDA(cudaMalloc(&m->dXn, ct * E * 4));
+  TGM_CUDA(cudaMalloc(&m->dQKV, ct * 3 * E * 4));
+  TGM_CUDA(cudaMalloc(&m->dP, cb * H * T * T * 4));
+  TGM_CUDA(cudaMalloc(&m->dO, ct * E * 4));
+  TGM_CUDA(cudaMalloc(&m->dF1, ct * 4 * E * 4));
+  TGM_CUDA(cudaMalloc(&m->G1, ct * 4 * E * 4));
+  TGM_CUDA(cudaMalloc(&m->dCh, 2 * cb * m->NP * C * 4));
+  TGM_CUDA(cudaMalloc(&m->dFeat, 2 * cb * L * dmax * 4 * 2));  // time | co-occurrence
+  TGM_CUDA(cudaMalloc(&m->Gst, 2 * cb * m->out * 4));
+  TGM_CUDA(cudaMalloc(&m->dPool, 2 * cb * E * 4));
+  m->bcap = int64_t(cb);
+  return TGM_OK;
+}
+
+int colsum(const float *a, int64_t rows, int cols, float *out, cudaStream_t st) {
+  TGM_CUDA(cudaMemsetAsync(out, 0, size_t(cols) * sizeof(float), st));
+  if (rows == 0) return TGM_OK;
+  const dim3 grid((cols + 31) / 32, unsigned(std::min<int64_t>((rows + 63) / 64, 256)));
+  colsum_kernel<<<grid, 256, 0, st>>>(a, rows, cols, out);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+
+}  // namespace
+
+extern "C" int tgm_dyg_set_params(tgm_dyg *m, const tgm_dyg_params *p, tgm_stream stream) {
+  TGM_REQUIRE(m != nullptr && p != nullptr, "tgm_dyg_set_params: NULL argument");
+  TGM_REQUIRE(p->node_dim == m->dN && p->edge_dim == m->dE && p->time_dim == m->dT &&
+                  p->channel_dim == m->C && p->out_dim == m->out && p->patch_size == m->P &&
+                  p->num_layers == m->layers && p->num_heads == m->H && p->seq_len == m->L,
+              "tgm_dyg_set_params: shapes differ from the handle's");
+  TGM_REQUIRE(m->layers == 0 || p->layers != nullptr, "tgm_dyg_set_params: layers is NULL");
+  DeviceGuard g(m->device);
+  cudaStream_t st = as_stream(stream);
+  const size_t C = m->C, E = m->E, P = m->P;
+  const size_t dims[4] = {size_t(m->dN), size_t(m->dE), size_t(m->dT), C};
+  int rc = copy_param(m->tw, p->t2v_w, m->dT, st);
+  if (!rc) rc = copy_param(m->tb, p->t2v_b, m->dT, st);
+  if (!rc) rc = copy_param(m->c_w1, p->cooc_w1, C, st);
+  if (!rc) rc = copy_param(m->c_b1, p->cooc_b1, C, st);
+  if (!rc) rc = copy_param(m->c_w2, p->cooc_w2, C * C, st);
+  if (!rc) rc = copy_param(m->c_b2, p->cooc_b2, C, st);
+  for (int c = 0; c < 4 && !rc; ++c) {
+    rc = copy_param(m->proj_w[c], p->proj_w[c], C * P * dims[c], st);
+    if (!rc) rc = copy_param(m->proj_b + c * C, p->proj_b[c], C, st);
+  }
+  if (!rc) rc = copy_param(m->out_w, p->out_w, size_t(m->out) * E, st);
+  if (!rc) rc = copy_param(m->out_b, p->out_b, m->out, st);
+  for (int l = 0; l < m->layers && !rc; ++l) {
+    const tgm_dyg_layer &s = p->layers[l];
+    DygLayerDev &d = m->lay[l];
+    rc = copy_param(d.in_w, s.in_proj_w, 3 * E * E, st);
+    if (!rc) rc = copy_param(d.in_b, s.in_proj_b, 3 * E, st);
+    if (!rc) rc = copy_param(d.out_w, s.out_proj_w, E * E, st);
+    if (!rc) rc = copy_param(d.out_b, s.out_proj_b, E, st);
+    if (!rc) rc = copy_param(d.f1_w, s.ffn1_w, 4 * E * E, st);
+    if (!rc) rc = copy_param(d.f1_b, s.ffn1_b, 4 * E, st);
+    if (!rc) rc = copy_param(d.f2_w, s.ffn2_w, 4 * E * E, st);
+    if (!rc) rc = copy_param(d.f2_b, s.ffn2_b, E, st);
+    if (!rc) rc = copy_param(d.ln0_w, s.ln0_w, E, st);
+    if (!rc) rc = copy_param(d.ln0_b, s.ln0_b, E, st);
+    if (!rc) rc = copy_param(d.ln1_w, s.ln1_w, E, st);
+    if (!rc) rc = copy_param(d.ln1_b, s.ln1_b, E, st);
+  }
+  return rc;
+}
+
+extern "C" int tgm_dyg_backward(tgm_dyg *m, const float *node_x, int64_t num_nodes,
+                                const int32_t *src, const int32_t *dst, const int64_t *edge_time,
+                                const int32_t *nbrs, const int64_t *nbr_t, const float *nbr_x,
+                                int64_t B, const float *d_src, const float *d_dst,
+                                const tgm_dyg_grads *gr, tgm_stream stream) {
+  TGM_REQUIRE(m != nullptr && gr != nullptr, "tgm_dyg_backward: NULL handle or gradient table");
+  TGM_REQUIRE(B > 0 && num_nodes > 0, "tgm_dyg_backward: bad sizes");
+  TGM_REQUIRE(node_x && src && dst && edge_time && nbrs && nbr_t && nbr_x && d_src && d_dst,
+              "tgm_dyg_backward: NULL array argument");
+  TGM_REQUIRE(m->layers == 0 || gr->layers != nullptr, "tgm_dyg_backward: gradient layers is NULL");
+  DeviceGuard g(m->device);
+  cudaStream_t st = as_stream(stream);
+  const int L = m->L, NP = m->NP, P = m->P, C = m->C, E = m->E, H = m->H, hd = E / H, T = 2 * NP;
+  const int dims[4] = {m->dN, m->dE, m->dT, C};
+  const int64_t tokens = B * T, rowsF = 2 * B * L, rowsP = 2 * B * NP;
+  TGM_REQUIRE(tokens * 4 * E < (int64_t(1) << 31), "tgm_dyg_backward: batch too large");
+  if (int rc = reserve_forward(m, B, st)) return rc;
+  if (int rc = reserve_backward(m, B, st)) return rc;
+  DYG_BLAS(cublasSetStream(m->blas, st));
+  const float one = 1.f, zero = 0.f;
+  const float scale = 1.0f / sqrtf(float(hd));
+  const size_t tokE = size_t(tokens) * E * sizeof(float);
+
+  // ---- forward, keeping what the chain rule needs (layer inputs, QKV, probabilities, O, the
+  //      post-attention stream, the pre-GELU activations); normalised inputs are recomputed ----
+  {
+    const size_t smem = size_t(8) * C * sizeof(float);
+    TGM_REQUIRE(smem <= 48 * 1024, "tgm_dyg_backward: channel_dim too large");
+    dyg_frontend_kernel<<<grid_for(rowsF, 8, 8), 256, smem, st>>>(
+        node_x, num_nodes, src, dst, edge_time, nbrs, nbr_t, nbr_x, B, L, m->dN, m->dE, m->dT, C,
+        m->tw, m->tb, m->c_w1, m->c_b1, m->c_w2, m->c_b2, m->feat[0], m->feat[1], m->feat[2],
+        m->feat[3]);
+    TGM_LAUNCH_CHECK();
+    for (int c = 0; c < 4; ++c) {
+      const int K = P * dims[c];
+      for (int side = 0; side < 2; ++side) {
+        const float *A = m->feat[c] + size_t(side) * B * L * dims[c];
+        float *Cp = m->X + size_t(side) * NP * E + size_t(c) * C;
+        DYG_BLAS(cublasSgemmStridedBatched(m->blas, CUBLAS_OP_T, CUBLAS_OP_N, C, NP, K, &one,
+                                           m->proj_w[c], K, 0, A, K, int64_t(NP) * K, &zero, Cp, E,
+                                           int64_t(T) * E, int(B)));
+      }
+    }
+    add_bias_kernel<<<grid_for(tokens * E, 256, 8), 256, 0, st>>>(m->X, m->proj_b, tokens, E, 0);
+    TGM_LAUNCH_CHECK();
+    for (int l = 0; l < m->layers; ++l) {
+      const DygLayerDev &ly = m->lay[l];
+      tgm_dyg::Saved &sv = m->saved[l];
+      TGM_CUDA(cudaMemcpyAsync(sv.Xin, m->X, tokE, cudaMemcpyDeviceToDevice, st));
+      layernorm_kernel<<<grid_for(tokens, 8, 8), 256, 0, st>>>(m->X, ly.ln0_w, ly.ln0_b, tokens, E,
+                                                               m->eps, m->Xn);
+      TGM_LAUNCH_CHECK();
+      if (int rc = linear(m->blas, tokens, 3 * E, E, m->Xn, ly.in_w, ly.in_b, nullptr, 0, sv.QKV,
+                          nullptr, st))
+        return rc;
+      for (int h = 0; h < H; ++h)
+        DYG_BLAS(cublasSgemmStridedBatched(
+            m->blas, CUBLAS_OP_T, CUBLAS_OP_N, T, T, hd, &one, sv.QKV + E + h * hd, 3 * E,
+            int64_t(T) * 3 * E, sv.QKV + h * hd, 3 * E, int64_t(T) * 3 * E, &zero,
+            sv.Pm + size_t(h) * T * T, T, int64_t(H) * T * T, int(B)));
+      softmax_rows_kernel<<<grid_for(B * H * T, 8, 8), 256, 0, st>>>(sv.Pm, B * H * T, T, scale);
+      TGM_LAUNCH_CHECK();
+      for (int h = 0; h < H; ++h)
+        DYG_BLAS(cublasSgemmStridedBatched(
+            m->blas, CUBLAS_OP_N, CUBLAS_OP_N, hd, T, T, &one, sv.QKV + 2 * E + h * hd, 3 * E,
+            int64_t(T) * 3 * E, sv.Pm + size_t(h) * T * T, T, int64_t(H) * T * T, &zero,
+            sv.O + h * hd, E, int64_t(T) * E, int(B)));
+      if (int rc = linear(m->blas, tokens, E, E, sv.O, ly.out_w, ly.out_b, m->X, 0, m->X, m->tmp, st))
+        return rc;
+      TGM_CUDA(cudaMemcpyAsync(sv.X1, m->X, tokE, cudaMemcpyDeviceToDevice, st));
+      layernorm_kernel<<<grid_for(tokens, 8, 8), 256, 0, st>>>(m->X, ly.ln1_w, ly.ln1_b, tokens, E,
+                                                               m->eps, m->Xn);
+      TGM_LAUNCH_CHECK();
+      if (int rc = linear(m->blas, tokens, 4 * E, E, m->Xn, ly.f1_w, ly.f1_b, nullptr, 0, sv.F1pre,
+                          nullptr, st))
+        return rc;
+      gelu_fwd_kernel<<<grid_for(tokens * 4 * E, 256, 8), 256, 0, st>>>(sv.F1pre, tokens * 4 * E,
+                                                                       m->F1);
+      TGM_LAUNCH_CHECK();
+      if (int rc = linear(m->blas, tokens, E, 4 * E, m->F1, ly.f2_w, ly.f2_b, m->X, 0, m->X, m->tmp,
+                          st))
+        return rc;
+    }
+    meanpool_kernel<<<grid_for(2 * B * E, 256, 8), 256, 0, st>>>(m->X, B, NP, E, m->pooled);
+    TGM_LAUNCH_CHECK();
+  }
+
+  // ---- output layer and mean pooling ------------------------------------------------------------
+  TGM_CUDA(cudaMemcpyAsync(m->Gst, d_src, size_t(B) * m->out * 4, cudaMemcpyDeviceToDevice, st));
+  TGM_CUDA(cudaMemcpyAsync(m->Gst + size_t(B) * m->out, d_dst, size_t(B) * m->out * 4,
+                           cudaMemcpyDeviceToDevice, st));
+  DYG_BLAS(gemm_tn(m->blas, 2 * B, m->out, E, m->Gst, m->out, m->pooled, E, gr->out_w, E));
+  if (int rc = colsum(m->Gst, 2 * B, m->out, gr->out_b, st)) return rc;
+  DYG_BLAS(gemm_nn(m->blas, 2 * B, E, m->out, m->Gst, m->out, m->out_w, E, m->dPool, E));
+  meanpool_bwd_kernel<<<grid_for(tokens * E, 256, 8), 256, 0, st>>>(m->dPool, B, NP, E, m->dX);
+  TGM_LAUNCH_CHECK();
+
+  // ---- transformer layers, last to first ------------------------------------------------------
+  const size_t ln_smem = size_t(2) * E * sizeof(float);
+  for (int l = m->layers - 1; l >= 0; --l) {
+    const DygLayerDev &ly = m->lay[l];
+    const tgm_dyg::Saved &sv = m->saved[l];
+    const tgm_dyg_layer_grads &gl = gr->layers[l];
+    // FFN2: X2 = X1 + G1 W2^T + b2
+    gelu_fwd_kernel<<<grid_for(tokens * 4 * E, 256, 8), 256, 0, st>>>(sv.F1pre, tokens * 4 * E,
+                                                                     m->G1);
+    TGM_LAUNCH_CHECK();
+    DYG_BLAS(gemm_tn(m->blas, tokens, E, 4 * E, m->dX, E, m->G1, 4 * E, gl.ffn2_w, 4 * E));
+    if (int rc = colsum(m->dX, tokens, E, gl.ffn2_b, st)) return rc;
+    DYG_BLAS(gemm_nn(m->blas, tokens, 4 * E, E, m->dX, E, ly.f2_w, 4 * E, m->dF1, 4 * E));
+    gelu_bwd_kernel<<<grid_for(tokens * 4 * E, 256, 8), 256, 0, st>>>(sv.F1pre, tokens * 4 * E,
+                                                                     m->dF1);
+    TGM_LAUNCH_CHECK();
+    // FFN1: F1pre = LN1(X1) W1^T + b1
+    layernorm_kernel<<<grid_for(tokens, 8, 8), 256, 0, st>>>(sv.X1, ly.ln1_w, ly.ln1_b, tokens, E,
+                                                             m->eps, m->Xn);
+    TGM_LAUNCH_CHECK();
+    DYG_BLAS(gemm_tn(m->blas, tokens, 4 * E, E, m->dF1, 4 * E, m->Xn, E, gl.ffn1_w, E));
+    if (int rc = colsum(m->dF1, tokens, 4 * E, gl.ffn1_b, st)) return rc;
+    DYG_BLAS(gemm_nn(m->blas, tokens, E, 4 * E, m->dF1, 4 * E, ly.f1_w, E, m->dXn, E));
+    TGM_CUDA(cudaMemsetAsync(gl.ln1_w, 0, size_t(E) * 4, st));
+    TGM_CUDA(cudaMemsetAsync(gl.ln1_b, 0, size_t(E) * 4, st));
+    layernorm_bwd_kernel<<<grid_for(tokens, 8, 4), 256, ln_smem, st>>>(
+        sv.X1, ly.ln1_w, m->dXn, tokens, E, m->eps, m->dX, gl.ln1_w, gl.ln1_b);  // dX is now dX1
+    TGM_LAUNCH_CHECK();
+    // attention output projection: X1 = Xin + O Wout^T + bout
+    DYG_BLAS(gemm_tn(m->blas, tokens, E, E, m->dX, E, sv.O, E, gl.out_proj_w, E));
+    if (int rc = colsum(m->dX, tokens, E, gl.out_proj_b, st)) return rc;
+    DYG_BLAS(gemm_nn(m->blas, tokens, E, E, m->dX, E, ly.out_w, E, m->dO, E));
+    // attention core, per head batched over the B sequences pairs
+    for (int h = 0; h < H; ++h) {
+      const float *V = sv.QKV + 2 * E + h * hd;
+      float *dV = m->dQKV + 2 * E + h * hd;
+      const float *Pm = sv.Pm + size_t(h) * T * T;
+      float *dPh = m->dP + size_t(h) * T * T;
+      const float *dOh = m->dO + h * hd;
+      const int64_t sQ = int64_t(T) * 3 * E, sP = int64_t(H) * T * T, sO = int64_t(T) * E;
+      // dP[q,k] = sum_d dO[q,d] V[k,d]
+      DYG_BLAS(cublasSgemmStridedBatched(m->blas, CUBLAS_OP_T, CUBLAS_OP_N, T, T, hd, &one, V, 3 * E,
+                                         sQ, dOh, E, sO, &zero, dPh, T, sP, int(B)));
+      // dV[k,d] = sum_q P[q,k] dO[q,d]
+      DYG_BLAS(cublasSgemmStridedBatched(m->blas, CUBLAS_OP_N, CUBLAS_OP_T, hd, T, T, &one, dOh, E,
+                                         sO, Pm, T, sP, &zero, dV, 3 * E, sQ, int(B)));
+    }
+    softmax_bwd_kernel<<<grid_for(B * H * T, 8, 8), 256, 0, st>>>(sv.Pm, m->dP, B * H * T, T, scale);
+    TGM_LAUNCH_CHECK();
+    for (int h = 0; h < H; ++h) {
+      const float *Q = sv.QKV + h * hd, *K = sv.QKV + E + h * hd;
+      float *dQ = m->dQKV + h * hd, *dK = m->dQKV + E + h * hd;
+      const float *dS = m->dP + size_t(h) * T * T;
+      const int64_t sQ = int64_t(T) * 3 * E, sP = int64_t(H) * T * T;
+      // dQ[q,d] = sum_k dS[q,k] K[k,d]
+      DYG_BLAS(cublasSgemmStridedBatched(m->blas, CUBLAS_OP_N, CUBLAS_OP_N, hd, T, T, &one, K, 3 * E,
+                                         sQ, dS, T, sP, &zero, dQ, 3 * E, sQ, int(B)));
+      // dK[k,d] = sum_q dS[q,k] Q[q,d]
+      DYG_BLAS(cublasSgemmStridedBatched(m->blas, CUBLAS_OP_N, CUBLAS_OP_T, hd, T, T, &one, Q, 3 * E,
+                                         sQ, dS, T, sP, &zero, dK, 3 * E, sQ, int(B)));
+    }
+    // in_proj: QKV = LN0(Xin) Win^T + bin
+    layernorm_kernel<<<grid_for(tokens, 8, 8), 256, 0, st>>>(sv.Xin, ly.ln0_w, ly.ln0_b, tokens, E,
+                                                             m->eps, m->Xn);
+    TGM_LAUNCH_CHECK();
+    DYG_BLAS(gemm_tn(m->blas, tokens, 3 * E, E, m->dQKV, 3 * E, m->Xn, E, gl.in_proj_w, E));
+    if (int rc = colsum(m->dQKV, tokens, 3 * E, gl.in_proj_b, st)) return rc;
+    DYG_BLAS(gemm_nn(m->blas, tokens, E, 3 * E, m->dQKV, 3 * E, ly.in_w, E, m->dXn, E));
+    TGM_CUDA(cudaMemsetAsync(gl.ln0_w, 0, size_t(E) * 4, st));
+    TGM_CUDA(cudaMemsetAsync(gl.ln0_b, 0, size_t(E) * 4, st));
+    layernorm_bwd_kernel<<<grid_for(tokens, 8, 4), 256, ln_smem, st>>>(
+        sv.Xin, ly.ln0_w, m->dXn, tokens, E, m->eps, m->dX, gl.ln0_w, gl.ln0_b);  // dX is now dXin
+    TGM_LAUNCH_CHECK();
+  }
+
+  // ---- channel projections and the two learnable feature channels -------------------------------
+  const int dmax = std::max(m->dT, C);
+  float *dTime = m->dFeat, *dCooc = m->dFeat + size_t(rowsF) * dmax;
+  for (int c = 0; c < 4; ++c) {
+    const int K = P * dims[c];
+    gather_channel_kernel<<<grid_for(rowsP * C, 256, 8), 256, 0, st>>>(m->dX, B, NP, E, C, c, m->dCh);
+    TGM_LAUNCH_CHECK();
+    // patches of channel c: the [2B*NP, P*d_c] view of feat[c]
+    DYG_BLAS(gemm_tn(m->blas, rowsP, C, K, m->dCh, C, m->feat[c], K, gr->proj_w[c], K));
+    if (int rc = colsum(m->dCh, rowsP, C, gr->proj_b[c], st)) return rc;
+    if (c >= 2)
+      DYG_BLAS(gemm_nn(m->blas, rowsP, K, C, m->dCh, C, m->proj_w[c], K, c == 2 ? dTime : dCooc, K));
+  }
+  for (float *q : {gr->t2v_w, gr->t2v_b})
+    TGM_CUDA(cudaMemsetAsync(q, 0, size_t(m->dT) * 4, st));
+  for (float *q : {gr->cooc_w1, gr->cooc_b1, gr->cooc_b2})
+    TGM_CUDA(cudaMemsetAsync(q, 0, size_t(C) * 4, st));
+  TGM_CUDA(cudaMemsetAsync(gr->cooc_w2, 0, size_t(C) * C * 4, st));
+  {
+    const int wpb = 8;
+    const size_t smem = (size_t(2) * m->dT + 3 * C + size_t(C) * C + size_t(wpb) * 2 * C) * sizeof(float);
+    TGM_REQUIRE(smem <= 96 * 1024, "tgm_dyg_backward: channel_dim too large for the frontend backward");
+    if (smem > 48 * 1024)
+      TGM_CUDA(cudaFuncSetAttribute(dyg_frontend_bwd_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    dyg_frontend_bwd_kernel<<<grid_for(rowsF, wpb, 2), 256, smem, st>>>(
+        src, dst, edge_time, nbrs, nbr_t, B, L, m->dT, C, m->tw, m->tb, m->c_w1, m->c_b1, m->c_w2,
+        dTime, dCooc, gr->t2v_w, gr->t2v_b, gr->cooc_w1, gr->cooc_b1, gr->cooc_w2, gr->cooc_b2);
+    TGM_LAUNCH_CHECK();
+  }
   return TGM_OK;
 }

@@ -1,6 +1,8 @@
 """DyGFormer on the B200 library: same constructor, parameter names and forward signature as
 tgm/nn/encoder/dygformer.py:146-444 (state_dicts interchange with the reference); the forward
-pass runs in `tgm_dyg_forward` (include/tgm_b200.h).  Forward / evaluation only."""
+pass runs in `tgm_dyg_forward` (include/tgm_b200.h).  Differentiable with respect to every
+parameter when autograd is recording (`tgm_dyg_backward` behind a torch.autograd.Function; dropout
+must be 0 in training mode -- a dropout mask cannot follow the reference's RNG stream)."""
 from __future__ import annotations
 
 import ctypes
@@ -12,6 +14,40 @@ from torch import Tensor
 
 from tgm_b200 import _cabi
 from tgm_b200.nn.attention import Time2Vec, _NativeHandle, _f32, _need_cuda, _version
+
+
+class _DyGFunction(torch.autograd.Function):
+    """tgm_dyg_forward / tgm_dyg_backward as one differentiable op.  The parameters are passed
+    explicitly so autograd routes their gradients; backward recomputes the forward activations
+    inside the library, so only the inputs are kept."""
+
+    @staticmethod
+    def forward(ctx, module, table, src, dst, t, nb, nt, nx, *params):
+        zs, zd = module._run_forward(table, src, dst, t, nb, nt, nx)
+        ctx.module, ctx.inputs = module, (table, src, dst, t, nb, nt, nx)
+        return zs, zd
+
+    @staticmethod
+    def backward(ctx, d_zs, d_zd):
+        module = ctx.module
+        table, src, dst, t, nb, nt, nx = ctx.inputs
+        dev, B = table.device, src.numel()
+        z = lambda d: (torch.zeros((B, module.output_dim), dtype=torch.float32, device=dev)
+                       if d is None else _f32(d))
+        d_zs, d_zd = z(d_zs), z(d_zd)
+        params = list(module.parameters())
+        flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+        grads = [v.view_as(p) for v, p in zip(flat.split([p.numel() for p in params]), params)]
+        by_param = {id(p): g for p, g in zip(params, grads)}
+        G = lambda p: by_param[id(p)].data_ptr()
+        layers = (_cabi.DygLayer * max(1, module.num_layers))()
+        gr = _cabi.DygGrads()
+        module._fill_tables(gr, layers, G)
+        _cabi.check(_cabi.lib.tgm_dyg_backward(
+            module._handle(dev), table.data_ptr(), table.shape[0], src.data_ptr(), dst.data_ptr(),
+            t.data_ptr(), nb.data_ptr(), nt.data_ptr(), nx.data_ptr(), B, d_zs.data_ptr(),
+            d_zd.data_ptr(), ctypes.byref(gr), _cabi.current_stream(dev)))
+        return (None,) * 8 + tuple(grads)
 
 
 class NeighborCooccurrenceEncoder(nn.Module):
@@ -64,22 +100,9 @@ class DyGFormer(nn.Module):
         self._native = _NativeHandle(_cabi.lib.tgm_dyg_destroy)
         self.to(device)
 
-    def _handle(self, dev: torch.device) -> ctypes.c_void_p:
-        params = list(self.parameters())
-        ver = _version(params)
-        if self._native.version == ver:
-            return self._native.h
-        self._native.free()
-        for p in params:
-            _need_cuda(p, 'DyGFormer parameters')
-        keep = []  # contiguous fp32 copies must outlive the create call
-
-        def P(t: Tensor) -> int:
-            c = _f32(t)
-            keep.append(c)
-            return c.data_ptr()
-
-        layers = (_cabi.DygLayer * max(1, self.num_layers))()
+    def _fill_tables(self, table, layers, P) -> None:
+        """Pointer tables of include/tgm_b200.h (tgm_dyg_params / tgm_dyg_grads share the field
+        order); `P(tensor)` yields the device pointer to put in the slot of that parameter."""
         for i, tr in enumerate(self.transformers):
             mha, ly = tr.multi_head_attention, layers[i]
             ly.in_proj_w, ly.in_proj_b = P(mha.in_proj_weight), P(mha.in_proj_bias)
@@ -88,33 +111,68 @@ class DyGFormer(nn.Module):
             ly.ffn2_w, ly.ffn2_b = P(tr.linear_layers[1].weight), P(tr.linear_layers[1].bias)
             ly.ln0_w, ly.ln0_b = P(tr.norm_layers[0].weight), P(tr.norm_layers[0].bias)
             ly.ln1_w, ly.ln1_b = P(tr.norm_layers[1].weight), P(tr.norm_layers[1].bias)
+        table.t2v_w, table.t2v_b = P(self.time_encoder.w.weight), P(self.time_encoder.w.bias)
+        mlp = self.co_occurrence_encoder.neighbor_co_occurrence_encoder
+        table.cooc_w1, table.cooc_b1 = P(mlp[0].weight), P(mlp[0].bias)
+        table.cooc_w2, table.cooc_b2 = P(mlp[2].weight), P(mlp[2].bias)
+        for c, name in enumerate(('node', 'edge', 'time', 'neighbor_co_occurrence')):
+            table.proj_w[c] = P(self.projection_layer[name].weight)
+            table.proj_b[c] = P(self.projection_layer[name].bias)
+        table.layers = ctypes.cast(layers, ctypes.POINTER(_cabi.DygLayer))
+        table.out_w, table.out_b = P(self.output_layer.weight), P(self.output_layer.bias)
+
+    def _handle(self, dev: torch.device) -> ctypes.c_void_p:
+        params = list(self.parameters())
+        ver = _version(params)
+        if self._native.version == ver:
+            return self._native.h
+        for p in params:
+            _need_cuda(p, 'DyGFormer parameters')
+        keep = []  # contiguous fp32 copies must outlive the call
+
+        def P(t: Tensor) -> int:
+            c = _f32(t)
+            keep.append(c)
+            return c.data_ptr()
+
+        layers = (_cabi.DygLayer * max(1, self.num_layers))()
         pr = _cabi.DygParams()
         pr.node_dim, pr.edge_dim, pr.time_dim = self.node_feat_dim, self.edge_x_dim, self.time_feat_dim
         pr.channel_dim, pr.out_dim, pr.patch_size = self.channel_embedding_dim, self.output_dim, self.patch_size
         pr.num_layers, pr.num_heads = self.num_layers, self.num_heads
         pr.seq_len = self.max_input_sequence_length
         pr.ln_eps = float(self.transformers[0].norm_layers[0].eps) if self.num_layers else 1e-5
-        pr.t2v_w, pr.t2v_b = P(self.time_encoder.w.weight.reshape(-1)), P(self.time_encoder.w.bias)
-        mlp = self.co_occurrence_encoder.neighbor_co_occurrence_encoder
-        pr.cooc_w1, pr.cooc_b1 = P(mlp[0].weight.reshape(-1)), P(mlp[0].bias)
-        pr.cooc_w2, pr.cooc_b2 = P(mlp[2].weight), P(mlp[2].bias)
-        for c, name in enumerate(('node', 'edge', 'time', 'neighbor_co_occurrence')):
-            pr.proj_w[c] = P(self.projection_layer[name].weight)
-            pr.proj_b[c] = P(self.projection_layer[name].bias)
-        pr.layers = ctypes.cast(layers, ctypes.POINTER(_cabi.DygLayer))
-        pr.out_w, pr.out_b = P(self.output_layer.weight), P(self.output_layer.bias)
-        _cabi.check(_cabi.lib.tgm_dyg_create(ctypes.byref(self._native.h), ctypes.byref(pr),
-                                             dev.index))
+        self._fill_tables(pr, layers, P)
+        if self._native.h.value and getattr(self, '_native_dev', None) == dev:
+            # same shapes, new values (optimizer step): refresh the copies in place
+            _cabi.check(_cabi.lib.tgm_dyg_set_params(self._native.h, ctypes.byref(pr),
+                                                     _cabi.current_stream(dev)))
+        else:
+            self._native.free()
+            _cabi.check(_cabi.lib.tgm_dyg_create(ctypes.byref(self._native.h), ctypes.byref(pr),
+                                                 dev.index))
+            self._native_dev = dev
         self._native.version = ver
         return self._native.h
 
-    @torch.no_grad()
+    def _run_forward(self, table, src, dst, t, nb, nt, nx) -> Tuple[Tensor, Tensor]:
+        dev, B = table.device, src.numel()
+        zs = torch.empty((B, self.output_dim), dtype=torch.float32, device=dev)
+        zd = torch.empty((B, self.output_dim), dtype=torch.float32, device=dev)
+        _cabi.check(_cabi.lib.tgm_dyg_forward(
+            self._handle(dev), table.data_ptr(), table.shape[0], src.data_ptr(), dst.data_ptr(),
+            t.data_ptr(), nb.data_ptr(), nt.data_ptr(), nx.data_ptr(), B, zs.data_ptr(),
+            zd.data_ptr(), _cabi.current_stream(dev)))
+        return zs, zd
+
     def forward(self, node_x: Tensor, edge_index: Tensor, edge_time: Tensor, neighbours: Tensor,
                 neighbours_time: Tensor, neighbours_edge_feat: Tensor) -> Tuple[Tensor, Tensor]:
         """Rows [0, E_b) of `neighbours*` belong to the sources, [E_b, 2 E_b) to the destinations
         (dygformer.py:262-270); extra rows (e.g. negatives) are ignored, as in the reference."""
-        if self.training:
-            raise RuntimeError('DyGFormer on the B200 path is forward/eval only')
+        if self.training and any(m.p > 0 for m in self.modules() if isinstance(m, nn.Dropout)) or \
+                self.training and any(tr.multi_head_attention.dropout > 0 for tr in self.transformers):
+            raise RuntimeError('DyGFormer on the B200 path trains with dropout=0 only '
+                               '(use eval() for inference)')
         dev = _need_cuda(node_x, 'DyGFormer')
         B = edge_index.shape[1]
         k = self.max_input_sequence_length - 1
@@ -128,10 +186,8 @@ class DyGFormer(nn.Module):
         nt = neighbours_time[:2 * B].to(device=dev, dtype=torch.int64).contiguous()
         nx = _f32(neighbours_edge_feat[:2 * B].to(dev))
         table = _f32(node_x)
-        zs = torch.empty((B, self.output_dim), dtype=torch.float32, device=dev)
-        zd = torch.empty((B, self.output_dim), dtype=torch.float32, device=dev)
-        _cabi.check(_cabi.lib.tgm_dyg_forward(
-            self._handle(dev), table.data_ptr(), table.shape[0], src.data_ptr(), dst.data_ptr(),
-            t.data_ptr(), nb.data_ptr(), nt.data_ptr(), nx.data_ptr(), B, zs.data_ptr(),
-            zd.data_ptr(), _cabi.current_stream(dev)))
-        return zs, zd
+        params = list(self.parameters())
+        if B > 0 and torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _DyGFunction.apply(self, table, src, dst, t, nb, nt, nx, *params)
+        with torch.no_grad():
+            return self._run_forward(table, src, dst, t, nb, nt, nx)
