@@ -13,8 +13,9 @@ config 5  per rank a time-range shard of a synthetic stream: one pre-sampled win
           DyGFormer sequence is 32), then per batch of 200 edges a DyGFormer forward (patch 1,
           4x50 channels, 2 layers, 2 heads) -> 2x200 embeddings.  No collective on the data path.
 
-Forward/evaluation pipelines; `--config 3 --train` adds the backward pass (tgm_attn_backward
-through autograd) and an Adam step.  One JSON line on rank 0; CUDA-event
+Forward/evaluation pipelines; `--train` adds the backward pass (tgm_attn_backward /
+tgm_dyg_backward through autograd) and an Adam step; config 5 under torchrun averages the
+gradients across the time shards with one NCCL all-reduce per step (data-parallel training).  One JSON line on rank 0; CUDA-event
 times, max over ranks; the CPU oracle is timed beside it on a few batches (config 3 only: the
 numpy DyGFormer oracle is timed in bench_rows.py).
 """
@@ -144,7 +145,12 @@ def config5(a, dev, rank, world):
     torch.manual_seed(0)
     model = DyGFormer(node_feat_dim=128, edge_x_dim=D, time_feat_dim=100, channel_embedding_dim=50,
                       output_dim=172, patch_size=1, num_layers=2, num_heads=2,
-                      max_input_sequence_length=k + 1).to(dev).eval()
+                      max_input_sequence_length=k + 1, dropout=0.0).to(dev)
+    model = model.train() if a.train else model.eval()
+    decoder = torch.nn.Sequential(torch.nn.Linear(2 * 172, 172), torch.nn.ReLU(),
+                                  torch.nn.Linear(172, 1)).to(dev)  # the example's link predictor
+    train_params = list(model.parameters()) + list(decoder.parameters())
+    opt = torch.optim.Adam(train_params, lr=1e-4)
     node_x = torch.randn(N, 128, generator=g, device=dev)
     shard = shard_batches(E, bs, rank, world)
     lo = shard.edge_lo + (shard.num_edges // 2 // bs) * bs  # mid-shard: populated histories
@@ -156,8 +162,22 @@ def config5(a, dev, rank, world):
             b_hi = min(b_lo + bs, hi)
             r0, r1 = 2 * (b_lo - lo), 2 * (b_hi - lo)
             ei = torch.stack([src[b_lo:b_hi], dst[b_lo:b_hi]])
+            if a.train:
+                opt.zero_grad(set_to_none=True)
             zs, zd = model(node_x, ei, t[b_lo:b_hi], hop.nbr_nids[r0:r1], hop.nbr_edge_time[r0:r1],
                            hop.nbr_edge_x[r0:r1])
+            if a.train:  # positives only: the backward pass and the optimizer step are what is timed
+                logit = decoder(torch.cat([zs, zd], 1))
+                loss = torch.nn.functional.binary_cross_entropy_with_logits(logit, torch.ones_like(logit))
+                loss.backward()
+                if world > 1:  # data-parallel over the time shards: average the gradients (NCCL)
+                    grads = [q.grad for q in train_params]
+                    flat = torch.cat([g_.reshape(-1) for g_ in grads])
+                    dist.all_reduce(flat)
+                    flat /= world
+                    for g_, v in zip(grads, flat.split([g_.numel() for g_ in grads])):
+                        g_.copy_(v.view_as(g_))
+                opt.step()
         return zs
 
     run()
@@ -177,13 +197,16 @@ def config5(a, dev, rank, world):
     return {'row': 'config 5: DyGFormer on a time-sharded synthetic stream, sequence 32 (k=31), patch 1',
             'n_gpus': world, 'edges': E, 'batches_per_rank': nb, 'ms_per_batch': ms / nb,
             'events_per_s': events / (ms * 1e-3), 'sequences_per_s': 2 * events / (ms * 1e-3),
-            'note': 'one pre-sampled window per rank + DyGFormer.forward per 200-edge batch; '
-                    'store/adjacency replicated, no collective on the data path; forward only'}
+            'mode': 'train (forward + tgm_dyg_backward + Adam step, dropout 0)' if a.train else 'forward',
+            'note': 'one pre-sampled window per rank + DyGFormer.forward per 200-edge batch' +
+                    (' + BCE loss on a torch MLP decoder + backward + gradient all-reduce (NCCL, when '
+                     'n_gpus > 1) + Adam' if a.train else '') +
+                    '; store/adjacency replicated, no collective on the sampling path'}
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--train', action='store_true', help='config 3: forward + backward + Adam')
+    ap.add_argument('--train', action='store_true', help='forward + backward + Adam step per batch')
     ap.add_argument('--config', type=int, required=True, choices=[3, 5])
     ap.add_argument('--batches', type=int, default=200)
     ap.add_argument('--window-batches', type=int, default=25)

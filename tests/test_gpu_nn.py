@@ -305,6 +305,35 @@ def test_dygformer_gradients_match_reference_autograd(path):
     assert float((zs2 - zs).detach().abs().max()) > 1e-3
 
 
+def test_dygformer_gradients_vs_oracle_at_config5_dims():
+    """BASELINE configs[4] shapes (sequence 32, 4 x 50 channels, 2 layers, 2 heads, edge dim 16),
+    40 edge pairs = 5120 tokens, so the recomputed forward inside tgm_dyg_backward runs its token
+    linears on the tensor cores; every parameter gradient against the float64 oracle."""
+    torch.manual_seed(9)
+    rng = np.random.default_rng(9)
+    N, B, L, dN, dE, dT, C, out = 400, 40, 32, 8, 16, 100, 50, 172
+    m = DyGFormer(dN, dE, dT, C, output_dim=out, patch_size=1, num_layers=2, num_heads=2, dropout=0.0,
+                  max_input_sequence_length=L).to(DEV).train()
+    k = L - 1
+    node_x = rng.standard_normal((N, dN)).astype(np.float32)
+    ei = np.stack([rng.integers(0, N, B), rng.integers(0, N, B)])
+    t = rng.integers(10_000, 50_000, B)
+    nbrs = rng.integers(0, 40, (2 * B, k)).astype(np.int32)
+    nt = np.sort(np.clip(np.tile(t, 2)[:, None] - rng.integers(1, 9000, (2 * B, k)), 0, None), 1)
+    ef = rng.standard_normal((2 * B, k, dE)).astype(np.float32)
+    pad = np.arange(k)[None, :] < rng.integers(0, k + 1, 2 * B)[:, None]
+    nbrs[pad], nt[pad], ef[pad] = -1, 0, 0.0
+    Gs = rng.standard_normal((B, out)).astype(np.float32)
+    Gd = rng.standard_normal((B, out)).astype(np.float32)
+    zs, zd = m(T(node_x), T(ei), T(t), T(nbrs), T(nt), T(ef))
+    ((zs * T(Gs)).sum() + (zd * T(Gd)).sum()).backward()
+    p = {k_: v.detach().cpu().numpy() for k_, v in m.state_dict().items()}
+    want = nn_oracle.dygformer_backward(p, 1, 2, 2, node_x, ei, t, nbrs, nt, ef, Gs, Gd)
+    for name, prm in m.named_parameters():
+        got = prm.grad.detach().cpu().numpy()
+        assert np.abs(got - want[name]).max() <= 5e-4 * max(1e-2, np.abs(want[name]).max()), name
+
+
 def test_dygformer_refuses_training_with_dropout():
     m = DyGFormer(3, 4, 6, 4, output_dim=5, num_layers=1, max_input_sequence_length=8).to(DEV).train()
     with pytest.raises(RuntimeError, match='dropout=0'):
