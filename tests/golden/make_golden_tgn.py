@@ -4,7 +4,7 @@ examples/linkproppred/tgn.py:60-124 drives it:  python tests/golden/make_golden_
 
 torch_geometric is not installed here; the import shim supplies `zeros` (in-place fill) and a
 `scatter(reduce=max|mean)` restatement over torch.scatter_reduce_ (tests/golden/_ref_shim.py).
-Writes tests/golden/tgn_*.npz."""
+Writes tests/golden/tgn_*.npz (states) and tests/golden/tgngrad_*.npz (gradients)."""
 from __future__ import annotations
 
 import os
@@ -76,12 +76,63 @@ def run(name, N, E, T, D, M, TD, bs, eval_from, seed, bias):
     print(name, 'ok', float(np.abs(out['final_memory']).max()))
 
 
+def run_grad(name, N, E, T, D, M, TD, bs, seed, bias, record_from):
+    """Training-mode gradients: the loop of examples/linkproppred/tgn.py:70-121 with the loss
+    replaced by sum(z * G) for a recorded random G (forward, update_state, backward, detach); the
+    .grad of every TGNMemory parameter is saved for the batches >= record_from (earlier batches
+    only warm the memory and the message stores).  Writes tests/golden/tgngrad_*.npz."""
+    rng = np.random.default_rng(seed)
+    src, dst = rng.integers(0, N, E), rng.integers(0, N, E)
+    t = np.sort(rng.choice(T, E, replace=False))
+    x = rng.standard_normal((E, D)).astype(np.float32)
+    neg = rng.integers(0, N, E)
+    torch.manual_seed(seed)
+    mem = TGNMemory(N, D, M, TD, message_module=IdentityMessage(D, M, TD),
+                    aggregator_module=LastAggregator())
+    with torch.no_grad():
+        for prm in mem.memory_updater.parameters():
+            prm.copy_(torch.randn(prm.shape) * 0.3)
+        if bias:
+            mem.time_enc.w.bias.copy_(torch.randn(TD) * 0.3)
+    mem.train()
+    mem.reset_state()
+    out = {}
+    for b, lo in enumerate(range(0, E, bs)):
+        hi = min(lo + bs, E)
+        s_, d_, t_ = (torch.from_numpy(a[lo:hi]).long() for a in (src, dst, t))
+        n_id = torch.cat([s_, d_, torch.from_numpy(neg[lo:hi]).long()]).unique()
+        mem.zero_grad()
+        z, lu = mem(n_id)
+        G = torch.from_numpy(rng.standard_normal(tuple(z.shape)).astype(np.float32))
+        loss = (z * G).sum()
+        mem.update_state(s_, d_, t_, torch.from_numpy(x[lo:hi]))
+        loss.backward()
+        mem.detach()
+        if b >= record_from:
+            out[f'b{b}_nid'] = n_id.numpy()
+            out[f'b{b}_z'] = z.detach().numpy().copy()
+            out[f'b{b}_G'] = G.numpy()
+            for k, prm in mem.named_parameters():
+                out[f'b{b}_g.{k}'] = prm.grad.numpy().copy()
+    sd = {'p.' + k: v.numpy() for k, v in mem.state_dict().items()
+          if k not in ('memory', 'last_update', '_assoc')}
+    np.savez_compressed(os.path.join(HERE, f'tgngrad_{name}.npz'), src=src.astype(np.int32),
+                        dst=dst.astype(np.int32), t=t.astype(np.int64), x=x,
+                        neg=neg.astype(np.int32), N=np.int64(N), bs=np.int64(bs),
+                        record_from=np.int64(record_from), **sd, **out)
+    print('grad', name, 'ok', max(float(np.abs(v).max()) for k, v in out.items() if '_g.' in k))
+
+
 def main():
     # name, N, E, T, D, M, time_dim, bs, first eval-mode batch (-1: never), seed, t2v bias != 0
     run('train_small', 30, 400, 3000, 4, 8, 6, 20, -1, 1, False)
     run('train_ties', 12, 300, 0, 3, 6, 4, 25, -1, 2, True)         # timestamp ties across nodes
     run('train_then_eval', 40, 600, 5000, 5, 10, 8, 30, 12, 3, False)
     run('wiki_dims', 200, 600, 100000, 172, 100, 100, 200, 2, 4, False)
+    # name, N, E, T, D, M, time_dim, bs, seed, t2v bias != 0, first recorded batch
+    run_grad('small', 30, 300, 3000, 4, 8, 6, 20, 5, False, 3)
+    run_grad('bias', 25, 300, 900, 3, 6, 4, 25, 6, True, 4)
+    run_grad('c4_dims', 300, 1200, 2_000_000, 16, 100, 100, 200, 7, False, 3)
 
 
 if __name__ == '__main__':
