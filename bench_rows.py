@@ -321,6 +321,7 @@ def row_tgn():
     x = torch.randn(E, D, generator=g, device=DEV)
     nids = [torch.cat([src[i * bs:(i + 1) * bs], dst[i * bs:(i + 1) * bs]]).long() for i in range(nb)]
 
+    @torch.no_grad()  # the inference row: no autograd rows are saved
     def epoch():
         for i in range(nb):
             lo, hi = i * bs, (i + 1) * bs

@@ -67,6 +67,7 @@ def main():
     mem.reset_state()
     touched = torch.zeros(N, dtype=torch.bool, device=dev)
 
+    @torch.no_grad()  # the inference step (mem is in train() mode for its update order only)
     def run_shard():
         """The per-batch model step of examples/linkproppred/tgn.py (without the decoder): sampled
         neighbourhoods -> unique nodes -> memory.forward -> GraphAttentionEmbedding over the

@@ -314,6 +314,28 @@ int tgm_tgn_update_state(tgm_tgn *, const int32_t *src, const int32_t *dst, cons
                          const float *raw_msg, int64_t Eb, int training, tgm_stream stream);
 /* train() -> eval() transition: consume every stored message into memory, clear the stores. */
 int tgm_tgn_flush(tgm_tgn *, tgm_stream stream);
+/* Training (autograd of memory(n_id) in examples/linkproppred/tgn.py:100-118, where
+ * loss.backward() runs AFTER memory.update_state()).  The state has moved on by then, so the
+ * training forward hands the caller what the backward needs of its rows:
+ *   saved_x f32[n,in] (in = raw_msg_dim + 2*memory_dim + time_dim: the LastAggregator's message per
+ *   node, zeros without one), saved_h f32[n,M] (memory[n_id]), saved_aux f32[n,2] = {float32(t -
+ *   last_update) of that message, 1 if the node has a message else 0}.
+ * tgm_tgn_forward_saved == tgm_tgn_forward(training = 1) + those rows.  tgm_tgn_backward is a
+ * function of the saved rows, the handle's CURRENT parameters and d_memory f32[n,M] only; it ADDS
+ * into the gradient buffers (torch layouts: g_w_ih [3M,in], g_w_hh [3M,M], g_b_ih/g_b_hh [3M],
+ * g_t2v_w/g_t2v_b [time_dim]; zero them first for plain gradients).  memory[...] and the raw
+ * messages are buffers/inputs without gradient in the reference (tgn.py:128-133, :154-155).
+ * tgm_tgn_set_params refreshes the parameter copies in place after an optimizer step (the node
+ * state and the message stores are kept); pointers may be host or device. */
+int tgm_tgn_set_params(tgm_tgn *, const float *gru_w_ih, const float *gru_w_hh,
+                       const float *gru_b_ih, const float *gru_b_hh, const float *t2v_w,
+                       const float *t2v_b, tgm_stream stream);
+int tgm_tgn_forward_saved(tgm_tgn *, const int64_t *n_id, int64_t n, float *out_memory,
+                          int64_t *out_last_update, float *saved_x, float *saved_h,
+                          float *saved_aux, tgm_stream stream);
+int tgm_tgn_backward(tgm_tgn *, const float *saved_x, const float *saved_h, const float *saved_aux,
+                     int64_t n, const float *d_memory, float *g_w_ih, float *g_w_hh, float *g_b_ih,
+                     float *g_b_hh, float *g_t2v_w, float *g_t2v_b, tgm_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * DyGFormer forward (eval mode).  Replaces DyGFormer.forward with its co-occurrence encoder,
@@ -397,6 +419,23 @@ void tgm_gae_destroy(tgm_gae *);
 int tgm_gae_forward(tgm_gae *, const float *x, const int64_t *last_update, int64_t n,
                     const int64_t *edge_src, const int64_t *edge_dst, const int64_t *t,
                     const float *msg, int64_t m, float *out, tgm_stream stream);
+/* Training (dropout 0: the convolution's attention dropout cannot follow the reference's RNG).
+ * tgm_gae_backward recomputes the forward from the same inputs and ADDS the gradients of
+ * sum(out * d_out), d_out f32[n,out_channels], into: d_x f32[n,in_channels] (nullable),
+ * g_W_qkvs f32[4*out_channels,in_channels] and g_b_qkvs f32[4*out_channels] = the query, key, value
+ * and skip linears stacked in that order, g_W_edge f32[out_channels,time_dim+msg_dim],
+ * g_t2v_w/g_t2v_b f32[time_dim] (Time2Vec, through the first time_dim columns of edge_attr).
+ * Source-node rows of d key / d value are accumulated with atomics (summation order varies).
+ * tgm_gae_set_params refreshes the parameter copies in place after an optimizer step. */
+int tgm_gae_set_params(tgm_gae *, const float *W_query, const float *b_query, const float *W_key,
+                       const float *b_key, const float *W_value, const float *b_value,
+                       const float *W_edge, const float *W_skip, const float *b_skip,
+                       const float *t2v_w, const float *t2v_b, tgm_stream stream);
+int tgm_gae_backward(tgm_gae *, const float *x, const int64_t *last_update, int64_t n,
+                     const int64_t *edge_src, const int64_t *edge_dst, const int64_t *t,
+                     const float *msg, int64_t m, const float *d_out, float *d_x, float *g_W_qkvs,
+                     float *g_b_qkvs, float *g_W_edge, float *g_t2v_w, float *g_t2v_b,
+                     tgm_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * Batch de-duplication.  Replaces DeduplicationHook.__call__ (tgm/hooks/dedup.py:35-67): masked

@@ -109,3 +109,19 @@ def test_new_entry_points_fail_loudly_without_gpu_or_arguments():
     assert rc == -3 and not h.value and 'no such CUDA device' in _cabi.last_error()
     w, p, b = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
     assert _cabi.lib.tgm_dedup_sizes(1000, ctypes.byref(w), ctypes.byref(p), ctypes.byref(b)) < 0
+
+
+def test_tgn_training_entry_points_validate_their_arguments():
+    """tgm_tgn_set_params / forward_saved / backward and tgm_gae_set_params / backward: a NULL
+    handle is an argument error reported through the status code, with or without a GPU."""
+    L = _cabi.lib
+    calls = {
+        'tgm_tgn_set_params': lambda: L.tgm_tgn_set_params(*[None] * 8),
+        'tgm_tgn_forward_saved': lambda: L.tgm_tgn_forward_saved(None, None, 4, *[None] * 6),
+        'tgm_tgn_backward': lambda: L.tgm_tgn_backward(None, None, None, None, 4, *[None] * 8),
+        'tgm_gae_set_params': lambda: L.tgm_gae_set_params(*[None] * 13),
+        'tgm_gae_backward': lambda: L.tgm_gae_backward(None, None, None, 4, None, None, None, None,
+                                                       4, *[None] * 8)}
+    for name, call in calls.items():
+        assert call() == -1, name
+        assert name in _cabi.last_error() and 'handle is NULL' in _cabi.last_error(), name

@@ -151,7 +151,8 @@ def test_tgn_memory_matches_reference_fixture(path):
             mem.eval()
             assert np.abs(mem.memory.detach().cpu().numpy() - z['flush_memory']).max() <= TOL
             assert np.array_equal(mem.last_update.detach().cpu().numpy(), z['flush_last_update'])
-        zz, lu = mem(T(z[f'b{b}_nid']))
+        with torch.no_grad():  # the state machine; the autograd path: test_zz_gpu_tgn_train.py
+            zz, lu = mem(T(z[f'b{b}_nid']))
         assert np.abs(zz.detach().cpu().numpy() - z[f'b{b}_z']).max() <= TOL, b
         assert np.array_equal(lu.detach().cpu().numpy(), z[f'b{b}_lu']), b
         mem.update_state(T(z['src'][lo:hi]), T(z['dst'][lo:hi]), T(z['t'][lo:hi]), T(z['x'][lo:hi]))
@@ -175,7 +176,8 @@ def test_tgn_memory_vs_oracle_longer_stream():
     for b, lo in enumerate(range(0, E, bs)):
         hi = lo + bs
         n_id = np.unique(np.concatenate([src[lo:hi], dst[lo:hi], rng.integers(0, N, 50)]))
-        zz, lu = mem(T(n_id))
+        with torch.no_grad():
+            zz, lu = mem(T(n_id))
         wz, wlu = oracle.forward(n_id)
         assert np.abs(zz.detach().cpu().numpy() - wz).max() <= TOL and np.array_equal(lu.detach().cpu().numpy(), wlu)
         mem.update_state(T(src[lo:hi]), T(dst[lo:hi]), T(t[lo:hi]), T(x[lo:hi]))

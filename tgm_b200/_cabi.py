@@ -108,6 +108,9 @@ SIGNATURES = {
     'tgm_tgn_update_state': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                      c_int, c_void_p]),
     'tgm_tgn_flush': (c_int, [c_void_p, c_void_p]),
+    'tgm_tgn_set_params': (c_int, [c_void_p] * 8),
+    'tgm_tgn_forward_saved': (c_int, [c_void_p, c_void_p, c_int64] + [c_void_p] * 6),
+    'tgm_tgn_backward': (c_int, [c_void_p] * 4 + [c_int64] + [c_void_p] * 8),
     'tgm_dyg_create': (c_int, [POINTER(c_void_p), c_void_p, c_int]),
     'tgm_dyg_destroy': (None, [c_void_p]),
     'tgm_dyg_set_params': (c_int, [c_void_p, c_void_p, c_void_p]),
@@ -120,6 +123,9 @@ SIGNATURES = {
     'tgm_gae_destroy': (None, [c_void_p]),
     'tgm_gae_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'tgm_gae_set_params': (c_int, [c_void_p] * 13),
+    'tgm_gae_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_int64] + [c_void_p] * 8),
     'tgm_dedup_sizes': (c_int, [c_int32, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     'tgm_dedup_unique': (c_int, [POINTER(c_void_p), POINTER(c_int64), POINTER(c_int32), c_int32,
                                  c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,

@@ -26,6 +26,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <new>
 
+#include "bwd_common.cuh"
 #include "common.cuh"
 
 using namespace tgm;
@@ -41,9 +42,14 @@ struct tgm_gae {
   int64_t *rowptr = nullptr;
   void *cub_tmp = nullptr;
   size_t cub_bytes = 0;
+  // backward workspaces (tgm_gae_backward)
+  int64_t bcap_n = 0, bcap_m = 0;
+  float *dP = nullptr, *out_fwd = nullptr;                                // [n,4HC], [n,HC]
+  float *dE = nullptr, *dA = nullptr, *dAttr = nullptr, *rel = nullptr;   // [m,HC], [m,H], [m,TD], [m]
   ~tgm_gae() {
     if (device >= 0) {
       DeviceGuard g(device);
+      for (float *p : {dP, out_fwd, dE, dA, dAttr, rel}) cudaFree(p);
       for (float *p : {Wall, ball, We, tw, tb, P, attr, Ep, logit}) cudaFree(p);
       for (int32_t *p : {key_in, key_out, perm_in, perm_out}) cudaFree(p);
       cudaFree(rowptr), cudaFree(cub_tmp);
@@ -299,5 +305,185 @@ extern "C" int tgm_gae_forward(tgm_gae *g, const float *x, const int64_t *last_u
   gae_node_kernel<<<grid_for(n, 8, 8), 256, 0, st>>>(g->P, g->ball, g->Ep, edge_src, g->perm_out,
                                                      g->rowptr, n, g->H, g->C, g->logit, out);
   TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+
+// ---- training: parameter refresh and backward ----------------------------------------------------
+// Chain rule of the forward above (oracle/tgn_oracle.py::transformer_conv_backward states it in
+// float64).  With s_ij = q_i.(k_j + e_ij)/sqrt(C) and a = softmax over the edges entering i:
+//     d a_ij = dOut_i . (v_j + e_ij)             d s_ij = a_ij (d a_ij - sum_j' a_ij' d a_ij') / sqrt(C)
+//     d v_j += a_ij dOut_i     d k_j += d s_ij q_i     d q_i += d s_ij (k_j + e_ij)
+//     d e_ij = a_ij dOut_i + d s_ij q_i          d skip_i = dOut_i
+// (PyG's +1e-16 in the softmax denominator leaves the Jacobian a (delta - a) unchanged.)
+// The forward is recomputed (nothing is saved but the inputs); one warp per target node walks its
+// incoming edges again: d q / d skip rows are owned by the warp, d k / d v rows of the SOURCE nodes
+// are accumulated with atomics; the linears' gradients are cuBLAS GEMMs over dP / dE.
+namespace {
+
+__global__ void __launch_bounds__(256)
+gae_node_bwd_kernel(const float *__restrict__ P, const float *__restrict__ ball,
+                    const float *__restrict__ Ep, const int64_t *__restrict__ esrc,
+                    const int32_t *__restrict__ perm, const int64_t *__restrict__ rowptr, int64_t n,
+                    int H, int C, const float *__restrict__ logit, const float *__restrict__ d_out,
+                    float *__restrict__ dA, float *__restrict__ dP, float *__restrict__ dE) {
+  const int HC = H * C, ld = 4 * HC;
+  const int lane = lane_id();
+  const float scale = sqrtf(float(C));
+  for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; i < n;
+       i += (int64_t(gridDim.x) * blockDim.x) >> 5) {
+    const int64_t lo = rowptr[i], hi = rowptr[i + 1];
+    const float *Pi = P + i * ld;
+    const float *go = d_out + i * HC;
+    for (int h = 0; h < H; ++h) {
+      const int c0 = h * C;
+      // softmax statistics, as the forward computes them (edge order)
+      float mx = -INFINITY;
+      for (int64_t p = lo; p < hi; ++p) mx = fmaxf(mx, logit[int64_t(perm[p]) * H + h]);
+      float sum = 0.f;
+      for (int64_t p = lo; p < hi; ++p) sum += expf(logit[int64_t(perm[p]) * H + h] - mx);
+      const float den = sum + 1e-16f;
+      // pass A: d a_ij for every incoming edge and dot = sum_j a_ij d a_ij
+      float dot = 0.f;
+      for (int64_t p = lo; p < hi; ++p) {
+        const int32_t e = perm[p];
+        const float *Pj = P + esrc[e] * ld + 2 * HC;  // v_j
+        const float *Ee = Ep + int64_t(e) * HC;
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32)
+          acc = __fmaf_rn(go[c0 + c], Pj[c0 + c] + ball[2 * HC + c0 + c] + Ee[c0 + c], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) dA[int64_t(e) * H + h] = acc;
+        dot = __fmaf_rn(expf(logit[int64_t(e) * H + h] - mx) / den, acc, dot);
+      }
+      __syncwarp();
+      // pass B: lanes own channels
+      for (int c = lane; c < C; c += 32) {
+        const float q = Pi[c0 + c] + ball[c0 + c];
+        const float g = go[c0 + c];
+        float dq = 0.f;
+        for (int64_t p = lo; p < hi; ++p) {
+          const int32_t e = perm[p];
+          const int64_t j = esrc[e];
+          const float a = expf(logit[int64_t(e) * H + h] - mx) / den;
+          const float ds = a * (dA[int64_t(e) * H + h] - dot) / scale;
+          const float kk = P[j * ld + HC + c0 + c] + ball[HC + c0 + c] + Ep[int64_t(e) * HC + c0 + c];
+          dq = __fmaf_rn(ds, kk, dq);
+          dE[int64_t(e) * HC + c0 + c] = a * g + ds * q;
+          atomicAdd(dP + j * ld + HC + c0 + c, ds * q);
+          atomicAdd(dP + j * ld + 2 * HC + c0 + c, a * g);
+        }
+        dP[i * ld + c0 + c] = dq;
+        dP[i * ld + 3 * HC + c0 + c] = g;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// rel[e] = float(last_update[src[e]] - t[e])  (the Time2Vec input of the forward)
+__global__ void gae_rel_kernel(const int64_t *__restrict__ esrc, const int64_t *__restrict__ t,
+                               const int64_t *__restrict__ last_update, int64_t m,
+                               float *__restrict__ rel) {
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < m;
+       e += int64_t(gridDim.x) * blockDim.x)
+    rel[e] = float(last_update[esrc[e]] - t[e]);
+}
+
+int gae_reserve_bwd(tgm_gae *g, int64_t n, int64_t m) {
+  if (n > g->bcap_n) {
+    cudaFree(g->dP), cudaFree(g->out_fwd);
+    g->dP = g->out_fwd = nullptr, g->bcap_n = 0;
+    const int64_t cap = n + n / 4 + 64;
+    TGM_CUDA(cudaMalloc(&g->dP, size_t(cap) * 4 * g->HC * sizeof(float)));
+    TGM_CUDA(cudaMalloc(&g->out_fwd, size_t(cap) * g->HC * sizeof(float)));
+    g->bcap_n = cap;
+  }
+  if (m > g->bcap_m) {
+    for (float **p : {&g->dE, &g->dA, &g->dAttr, &g->rel}) cudaFree(*p), *p = nullptr;
+    g->bcap_m = 0;
+    const int64_t cap = m + m / 4 + 64;
+    TGM_CUDA(cudaMalloc(&g->dE, size_t(cap) * g->HC * sizeof(float)));
+    TGM_CUDA(cudaMalloc(&g->dA, size_t(cap) * g->H * sizeof(float)));
+    TGM_CUDA(cudaMalloc(&g->dAttr, size_t(cap) * g->TD * sizeof(float)));
+    TGM_CUDA(cudaMalloc(&g->rel, size_t(cap) * sizeof(float)));
+    g->bcap_m = cap;
+  }
+  return TGM_OK;
+}
+
+}  // namespace
+
+extern "C" int tgm_gae_set_params(tgm_gae *g, const float *W_query, const float *b_query,
+                                  const float *W_key, const float *b_key, const float *W_value,
+                                  const float *b_value, const float *W_edge, const float *W_skip,
+                                  const float *b_skip, const float *t2v_w, const float *t2v_b,
+                                  tgm_stream stream) {
+  TGM_REQUIRE(g != nullptr, "tgm_gae_set_params: handle is NULL");
+  TGM_REQUIRE(W_query && b_query && W_key && b_key && W_value && b_value && W_edge && W_skip &&
+                  b_skip && t2v_w && t2v_b, "tgm_gae_set_params: NULL parameter");
+  DeviceGuard guard(g->device);
+  cudaStream_t st = as_stream(stream);
+  const size_t HC = size_t(g->HC), in = size_t(g->in);
+  const float *Ws[4] = {W_query, W_key, W_value, W_skip};
+  const float *bs[4] = {b_query, b_key, b_value, b_skip};
+  for (int q = 0; q < 4; ++q) {
+    TGM_CUDA(cudaMemcpyAsync(g->Wall + q * HC * in, Ws[q], HC * in * 4, cudaMemcpyDefault, st));
+    TGM_CUDA(cudaMemcpyAsync(g->ball + q * HC, bs[q], HC * 4, cudaMemcpyDefault, st));
+  }
+  TGM_CUDA(cudaMemcpyAsync(g->We, W_edge, HC * size_t(g->A) * 4, cudaMemcpyDefault, st));
+  TGM_CUDA(cudaMemcpyAsync(g->tw, t2v_w, size_t(g->TD) * 4, cudaMemcpyDefault, st));
+  TGM_CUDA(cudaMemcpyAsync(g->tb, t2v_b, size_t(g->TD) * 4, cudaMemcpyDefault, st));
+  return TGM_OK;
+}
+
+extern "C" int tgm_gae_backward(tgm_gae *g, const float *x, const int64_t *last_update, int64_t n,
+                                const int64_t *edge_src, const int64_t *edge_dst, const int64_t *t,
+                                const float *msg, int64_t m, const float *d_out, float *d_x,
+                                float *g_W_qkvs, float *g_b_qkvs, float *g_W_edge, float *g_t2v_w,
+                                float *g_t2v_b, tgm_stream stream) {
+  TGM_REQUIRE(g != nullptr, "tgm_gae_backward: handle is NULL");
+  TGM_REQUIRE(n >= 0 && m >= 0 && n < (int64_t(1) << 31) && m < (int64_t(1) << 31),
+              "tgm_gae_backward: bad sizes");
+  if (n == 0) return TGM_OK;
+  TGM_REQUIRE(x && last_update && d_out, "tgm_gae_backward: NULL node argument");
+  TGM_REQUIRE(m == 0 || (edge_src && edge_dst && t && (msg || g->D == 0)),
+              "tgm_gae_backward: NULL edge argument");
+  TGM_REQUIRE(g_W_qkvs && g_b_qkvs && g_W_edge && g_t2v_w && g_t2v_b,
+              "tgm_gae_backward: NULL gradient buffer");
+  DeviceGuard guard(g->device);
+  cudaStream_t st = as_stream(stream);
+  int rc = gae_reserve_bwd(g, n, m);
+  if (rc) return rc;
+  // recompute P, attr, Ep, the target-sorted edge order and the logits
+  rc = tgm_gae_forward(g, x, last_update, n, edge_src, edge_dst, t, msg, m, g->out_fwd, stream);
+  if (rc) return rc;
+  const int HC = g->HC, HC4 = 4 * g->HC, in = g->in, A = g->A, TD = g->TD;
+  const float one = 1.f, zero = 0.f;
+  TGM_CUDA(cudaMemsetAsync(g->dP, 0, size_t(n) * HC4 * sizeof(float), st));
+  gae_node_bwd_kernel<<<grid_for(n, 8, 8), 256, 0, st>>>(g->P, g->ball, g->Ep, edge_src,
+                                                         g->perm_out, g->rowptr, n, g->H, g->C,
+                                                         g->logit, d_out, g->dA, g->dP, g->dE);
+  TGM_LAUNCH_CHECK();
+  GAE_BLAS(cublasSetStream(g->blas, st));
+  // g_W_qkvs[4HC,in] += dP^T x ; g_b_qkvs[4HC] += colsum(dP) ; d_x[n,in] += dP Wall   (row-major)
+  GAE_BLAS(cublasSgemm(g->blas, CUBLAS_OP_N, CUBLAS_OP_T, in, HC4, int(n), &one, x, in, g->dP, HC4,
+                       &one, g_W_qkvs, in));
+  colsum_add_kernel<<<colsum_grid(n, HC4), 128, 0, st>>>(g->dP, n, HC4, HC4, g_b_qkvs);
+  TGM_LAUNCH_CHECK();
+  if (d_x != nullptr)
+    GAE_BLAS(cublasSgemm(g->blas, CUBLAS_OP_N, CUBLAS_OP_N, in, int(n), HC4, &one, g->Wall, in,
+                         g->dP, HC4, &one, d_x, in));
+  if (m > 0) {
+    // g_W_edge[HC,A] += dE^T attr ; d(attr)[:, :TD] = dE W_edge[:, :TD] ; then Time2Vec
+    GAE_BLAS(cublasSgemm(g->blas, CUBLAS_OP_N, CUBLAS_OP_T, A, HC, int(m), &one, g->attr, A, g->dE,
+                         HC, &one, g_W_edge, A));
+    GAE_BLAS(cublasSgemm(g->blas, CUBLAS_OP_N, CUBLAS_OP_N, TD, int(m), HC, &one, g->We, A, g->dE,
+                         HC, &zero, g->dAttr, TD));
+    gae_rel_kernel<<<grid_for(m, 256, 8), 256, 0, st>>>(edge_src, t, last_update, m, g->rel);
+    TGM_LAUNCH_CHECK();
+    t2v_grad_kernel<<<colsum_grid(m, TD), 128, 0, st>>>(g->rel, nullptr, 1, g->dAttr, TD, m, TD,
+                                                        g->tw, g->tb, g_t2v_w, g_t2v_b);
+    TGM_LAUNCH_CHECK();
+  }
   return TGM_OK;
 }

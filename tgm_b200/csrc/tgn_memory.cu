@@ -22,6 +22,7 @@
 
 #include <new>
 
+#include "bwd_common.cuh"
 #include "common.cuh"
 
 using namespace tgm;
@@ -480,4 +481,158 @@ extern "C" int tgm_tgn_flush(tgm_tgn *h, tgm_stream stream) {
   if (!rc) rc = write_rows(h, h->N, st);
   if (!rc) rc = clear_stores(h, st);
   return rc;
+}
+
+// ---- training: parameter refresh, forward with saved rows, backward ------------------------------
+// The reference runs loss.backward() AFTER memory.update_state() (examples/linkproppred/tgn.py:
+// 111-118): autograd holds the tensors of memory(n_id)'s graph while the state moves on.  The
+// device equivalent: tgm_tgn_forward_saved hands the caller the GRU inputs of its rows (X, H and
+// {t - last_update, has-a-message}); tgm_tgn_backward is a pure function of those rows, the
+// current parameters and d_memory.  memory[...] and the raw messages carry no gradient in the
+// reference (buffers, tgn.py:128-133, detached every step :154-155), so the parameters that
+// receive one are the GRU cell's and, through the message's time-encoding columns, Time2Vec's.
+namespace {
+
+__global__ void tgn_aux_kernel(const int64_t *__restrict__ last_update,
+                               const int32_t *__restrict__ o_s, const int64_t *__restrict__ t_s,
+                               const int32_t *__restrict__ o_d, const int64_t *__restrict__ t_d,
+                               int32_t N, const int32_t *__restrict__ rows, int64_t n,
+                               float *__restrict__ aux) {
+  for (int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n;
+       r += int64_t(gridDim.x) * blockDim.x) {
+    const int32_t v = rows[r];
+    float dt = 0.f, has = 0.f;
+    if (v >= 0 && v < N) {
+      // the same pick as tgn_message_kernel
+      const bool has_s = o_s[v] >= 0, has_d = o_d[v] >= 0;
+      const bool use_d = has_d && (!has_s || float(t_d[v]) > float(t_s[v]));
+      if (has_s || has_d) {
+        const int64_t te = use_d ? t_d[v] : t_s[v];
+        dt = float(te - last_update[v]);
+        has = 1.f;
+      }
+    }
+    aux[2 * r] = dt;
+    aux[2 * r + 1] = has;
+  }
+}
+
+// In place: GI/GH hold the gate pre-activations without bias on entry, d(gi)/d(gh) on exit.
+//   h' = (1 - z) n + z h;  d n = d h' (1 - z);  d z = d h' (h - n);  d pre_n = d n (1 - n^2)
+//   d pre_r = d pre_n gh_n r (1 - r);  d pre_z = d z z (1 - z);  d gh_n = d pre_n r
+__global__ void tgn_gru_bwd_kernel(float *__restrict__ GI, float *__restrict__ GH,
+                                   const float *__restrict__ bih, const float *__restrict__ bhh,
+                                   const float *__restrict__ H, const float *__restrict__ d_out,
+                                   int64_t n, int M) {
+  const int64_t total = n * M;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / M;
+    const int c = int(i - r * M);
+    float *gi = GI + r * 3 * M, *gh = GH + r * 3 * M;
+    const float ir = gi[c] + __ldg(bih + c), hr = gh[c] + __ldg(bhh + c);
+    const float iz = gi[M + c] + __ldg(bih + M + c), hz = gh[M + c] + __ldg(bhh + M + c);
+    const float in_ = gi[2 * M + c] + __ldg(bih + 2 * M + c);
+    const float hn = gh[2 * M + c] + __ldg(bhh + 2 * M + c);
+    const float rg = 1.f / (1.f + expf(-(ir + hr)));
+    const float zg = 1.f / (1.f + expf(-(iz + hz)));
+    const float ng = tanhf(in_ + rg * hn);
+    const float go = d_out[i];
+    const float d_pn = go * (1.f - zg) * (1.f - ng * ng);
+    const float d_pz = go * (H[i] - ng) * zg * (1.f - zg);
+    const float d_pr = d_pn * hn * rg * (1.f - rg);
+    gi[c] = d_pr, gi[M + c] = d_pz, gi[2 * M + c] = d_pn;
+    gh[c] = d_pr, gh[M + c] = d_pz, gh[2 * M + c] = d_pn * rg;
+  }
+}
+
+}  // namespace
+
+extern "C" int tgm_tgn_set_params(tgm_tgn *h, const float *gru_w_ih, const float *gru_w_hh,
+                                  const float *gru_b_ih, const float *gru_b_hh, const float *t2v_w,
+                                  const float *t2v_b, tgm_stream stream) {
+  TGM_REQUIRE(h != nullptr, "tgm_tgn_set_params: handle is NULL");
+  TGM_REQUIRE(gru_w_ih && gru_w_hh && gru_b_ih && gru_b_hh && t2v_w && t2v_b,
+              "tgm_tgn_set_params: NULL parameter");
+  DeviceGuard g(h->device);
+  cudaStream_t st = as_stream(stream);
+  const size_t M = size_t(h->M);
+  TGM_CUDA(cudaMemcpyAsync(h->Wih, gru_w_ih, 3 * M * size_t(h->in) * 4, cudaMemcpyDefault, st));
+  TGM_CUDA(cudaMemcpyAsync(h->Whh, gru_w_hh, 3 * M * M * 4, cudaMemcpyDefault, st));
+  TGM_CUDA(cudaMemcpyAsync(h->bih, gru_b_ih, 3 * M * 4, cudaMemcpyDefault, st));
+  TGM_CUDA(cudaMemcpyAsync(h->bhh, gru_b_hh, 3 * M * 4, cudaMemcpyDefault, st));
+  TGM_CUDA(cudaMemcpyAsync(h->tw, t2v_w, size_t(h->TD) * 4, cudaMemcpyDefault, st));
+  TGM_CUDA(cudaMemcpyAsync(h->tb, t2v_b, size_t(h->TD) * 4, cudaMemcpyDefault, st));
+  return TGM_OK;
+}
+
+extern "C" int tgm_tgn_forward_saved(tgm_tgn *h, const int64_t *n_id, int64_t n,
+                                     float *out_memory, int64_t *out_last_update, float *saved_x,
+                                     float *saved_h, float *saved_aux, tgm_stream stream) {
+  TGM_REQUIRE(h != nullptr, "tgm_tgn_forward_saved: handle is NULL");
+  TGM_REQUIRE(n >= 0, "tgm_tgn_forward_saved: n must be >= 0");
+  if (n == 0) return TGM_OK;
+  TGM_REQUIRE(n_id && out_memory && out_last_update && saved_x && saved_h && saved_aux,
+              "tgm_tgn_forward_saved: NULL array argument");
+  DeviceGuard g(h->device);
+  cudaStream_t st = as_stream(stream);
+  int rc = ensure_rows(h, n, st);
+  if (rc) return rc;
+  cast_ids_kernel<int64_t><<<grid_for(n, 256, 8), 256, 0, st>>>(n_id, n, h->rows);
+  TGM_LAUNCH_CHECK();
+  rc = compute_rows(h, n, st);
+  if (rc) return rc;
+  const size_t rows = size_t(n);
+  TGM_CUDA(cudaMemcpyAsync(out_memory, h->newmem, rows * h->M * 4, cudaMemcpyDeviceToDevice, st));
+  TGM_CUDA(cudaMemcpyAsync(out_last_update, h->newlu, rows * 8, cudaMemcpyDeviceToDevice, st));
+  TGM_CUDA(cudaMemcpyAsync(saved_x, h->X, rows * h->in * 4, cudaMemcpyDeviceToDevice, st));
+  TGM_CUDA(cudaMemcpyAsync(saved_h, h->H, rows * h->M * 4, cudaMemcpyDeviceToDevice, st));
+  tgn_aux_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(h->last_update, h->st[0].other, h->st[0].t,
+                                                      h->st[1].other, h->st[1].t, h->N, h->rows, n,
+                                                      saved_aux);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+
+extern "C" int tgm_tgn_backward(tgm_tgn *h, const float *saved_x, const float *saved_h,
+                                const float *saved_aux, int64_t n, const float *d_memory,
+                                float *g_w_ih, float *g_w_hh, float *g_b_ih, float *g_b_hh,
+                                float *g_t2v_w, float *g_t2v_b, tgm_stream stream) {
+  TGM_REQUIRE(h != nullptr, "tgm_tgn_backward: handle is NULL");
+  TGM_REQUIRE(n >= 0 && n < (int64_t(1) << 31), "tgm_tgn_backward: bad n");
+  if (n == 0) return TGM_OK;
+  TGM_REQUIRE(saved_x && saved_h && saved_aux && d_memory, "tgm_tgn_backward: NULL input");
+  TGM_REQUIRE(g_w_ih && g_w_hh && g_b_ih && g_b_hh && g_t2v_w && g_t2v_b,
+              "tgm_tgn_backward: NULL gradient buffer");
+  DeviceGuard g(h->device);
+  cudaStream_t st = as_stream(stream);
+  int rc = ensure_rows(h, n, st);
+  if (rc) return rc;
+  const int M = h->M, in = h->in, TD = h->TD, M3 = 3 * h->M;
+  const float one = 1.f, zero = 0.f;
+  TGN_BLAS(cublasSetStream(h->blas, st));
+  // recompute the gate pre-activations from the saved rows (as compute_rows)
+  TGN_BLAS(cublasSgemm(h->blas, CUBLAS_OP_T, CUBLAS_OP_N, M3, int(n), in, &one, h->Wih, in, saved_x,
+                       in, &zero, h->GI, M3));
+  TGN_BLAS(cublasSgemm(h->blas, CUBLAS_OP_T, CUBLAS_OP_N, M3, int(n), M, &one, h->Whh, M, saved_h, M,
+                       &zero, h->GH, M3));
+  tgn_gru_bwd_kernel<<<grid_for(n * M, 256, 8), 256, 0, st>>>(h->GI, h->GH, h->bih, h->bhh, saved_h,
+                                                              d_memory, n, M);
+  TGM_LAUNCH_CHECK();
+  // g_w_ih[3M,in] += dGI^T X ; g_w_hh[3M,M] += dGH^T H   (row-major)
+  TGN_BLAS(cublasSgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, in, M3, int(n), &one, saved_x, in, h->GI,
+                       M3, &one, g_w_ih, in));
+  TGN_BLAS(cublasSgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, M, M3, int(n), &one, saved_h, M, h->GH, M3,
+                       &one, g_w_hh, M));
+  colsum_add_kernel<<<colsum_grid(n, M3), 128, 0, st>>>(h->GI, n, M3, M3, g_b_ih);
+  TGM_LAUNCH_CHECK();
+  colsum_add_kernel<<<colsum_grid(n, M3), 128, 0, st>>>(h->GH, n, M3, M3, g_b_hh);
+  TGM_LAUNCH_CHECK();
+  // d(time encoding)[n,TD] = dGI[n,3M] W_ih[:, 2M+D:]   (into the X workspace), then Time2Vec
+  TGN_BLAS(cublasSgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, TD, int(n), M3, &one,
+                       h->Wih + (2 * M + h->D), in, h->GI, M3, &zero, h->X, TD));
+  t2v_grad_kernel<<<colsum_grid(n, TD), 128, 0, st>>>(saved_aux, saved_aux + 1, 2, h->X, TD, n, TD,
+                                                      h->tw, h->tb, g_t2v_w, g_t2v_b);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
 }
