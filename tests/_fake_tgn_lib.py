@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE: a stand-in for the `tgm_tgn_*` / `tgm_gae_*` entry points of the C ABI,
 implemented with the numpy oracle over HOST pointers, so that the host-side logic of
 tgm_b200/nn/tgn.py (handle life cycle, parameter refresh, autograd routing, argument order, buffer
-shapes) and the bodies of the GPU tests in tests/test_zz_gpu_tgn_train.py can run on a CPU-only box.
+shapes) and the bodies of the GPU tests in tests/test_gpu_tgn_train.py can run on a CPU-only box.
 
 It checks the Python face only; the CUDA kernels are checked by the `-m gpu` tests.  Nothing under
 tgm_b200/ imports this.

@@ -151,7 +151,7 @@ def test_tgn_memory_matches_reference_fixture(path):
             mem.eval()
             assert np.abs(mem.memory.detach().cpu().numpy() - z['flush_memory']).max() <= TOL
             assert np.array_equal(mem.last_update.detach().cpu().numpy(), z['flush_last_update'])
-        with torch.no_grad():  # the state machine; the autograd path: test_zz_gpu_tgn_train.py
+        with torch.no_grad():  # the state machine; the autograd path: test_gpu_tgn_train.py
             zz, lu = mem(T(z[f'b{b}_nid']))
         assert np.abs(zz.detach().cpu().numpy() - z[f'b{b}_z']).max() <= TOL, b
         assert np.array_equal(lu.detach().cpu().numpy(), z[f'b{b}_lu']), b

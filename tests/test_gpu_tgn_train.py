@@ -2,11 +2,9 @@
 tgm_tgn_set_params and tgm_gae_backward / tgm_gae_set_params behind the autograd integration of
 tgm_b200.nn.TGNMemory and GraphAttentionEmbedding.
 
-STATUS: these entry points were written after round 1's GPU budget was spent.  They are compiled
-for sm_100a, their float64 oracles are pinned on the reference's autograd on CPU
-(tests/test_oracle_golden.py), and the Python plumbing was exercised on CPU against the oracle, but
-the kernels have NOT yet run on hardware.  Until they have, the tests are non-strict xfail (a pass
-shows as XPASS) and live in the last test module so that the verified suites run first.
+The float64 oracles are pinned on the reference's autograd on CPU (tests/test_oracle_golden.py); the
+same test bodies also run on CPU against an oracle-backed stand-in library
+(tests/test_tgn_train_host_logic.py).  First hardware run: profiles/r1_tgn_train_gpu_tests.log.
 """
 import glob
 import os
@@ -19,10 +17,7 @@ from oracle.tgn_oracle import (TGNMemoryOracle, graph_attention_embedding,
                                graph_attention_embedding_backward, tgn_memory_backward)
 from tests._golden import GOLDEN_DIR
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason='TGN backward: compiled and oracle-pinned on '
-                                                     'CPU, not yet executed on a GPU (round-1 GPU '
-                                                     'budget spent)')]
+pytestmark = pytest.mark.gpu
 
 from tgm_b200.nn import GraphAttentionEmbedding, TGNMemory, Time2Vec  # noqa: E402
 

@@ -2,7 +2,7 @@
 tgm_b200/nn/tgn.py (handle life cycle, in-place parameter refresh, autograd routing, argument order
 and buffer shapes of tgm_tgn_forward_saved / tgm_tgn_backward / tgm_gae_backward) driven through a
 stand-in library built on the numpy oracle (tests/_fake_tgn_lib.py).  The bodies are the GPU tests
-of tests/test_zz_gpu_tgn_train.py with DEV = 'cpu'; the CUDA kernels themselves are NOT exercised
+of tests/test_gpu_tgn_train.py with DEV = 'cpu'; the CUDA kernels themselves are NOT exercised
 here."""
 import glob
 import os
@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from tests import _fake_tgn_lib
-from tests import test_zz_gpu_tgn_train as gpu_tests
+from tests import test_gpu_tgn_train as gpu_tests
 from tests._golden import GOLDEN_DIR
 
 
