@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""End-to-end pipelines for BASELINE.json configs[2] and configs[4] (configs[3], TGN memory with
-the shard join, is bench_tgn_shard.py; configs[1]/headline is bench.py).
+"""End-to-end pipelines for BASELINE.json configs[2], [3] and [4] (the 4-GPU time-sharded form of
+configs[3], TGN memory with the shard join, is bench_tgn_shard.py; configs[1]/headline is bench.py).
 
     python bench_configs.py --config 3                      # TGAT, tgbl-wiki-shaped, 1 GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
@@ -9,12 +9,15 @@ the shard join, is bench_tgn_shard.py; configs[1]/headline is bench.py).
 config 3  per loader batch of 200 edges: random negatives -> 2-hop recent-neighbour sampling
           k=[20,20] over [src|dst|neg] (windowed hook through DGDataLoader/HookManager, the
           drop-in API) -> TGAT forward (2 layers, 2 heads, time 100, embed 172) -> 600 embeddings.
+config 4  the loop of examples/linkproppred/tgn.py on one GPU, through the drop-in API: random
+          negatives -> recent neighbours k=10 over [src|dst|neg] -> device de-duplication ->
+          TGNMemory.forward -> GraphAttentionEmbedding -> link decoder -> update_state.
 config 5  per rank a time-range shard of a synthetic stream: one pre-sampled window (k=31 so the
           DyGFormer sequence is 32), then per batch of 200 edges a DyGFormer forward (patch 1,
           4x50 channels, 2 layers, 2 heads) -> 2x200 embeddings.  No collective on the data path.
 
 Forward/evaluation pipelines; `--train` adds the backward pass (tgm_attn_backward /
-tgm_dyg_backward through autograd) and an Adam step; config 5 under torchrun averages the
+tgm_gae_backward + tgm_tgn_backward / tgm_dyg_backward through autograd) and an Adam step; config 5 under torchrun averages the
 gradients across the time shards with one NCCL all-reduce per step (data-parallel training).  One JSON line on rank 0; CUDA-event
 times, max over ranks; the CPU oracle is timed beside it on a few batches (config 3 only: the
 numpy DyGFormer oracle is timed in bench_rows.py).
@@ -133,6 +136,93 @@ def config3(a, dev):
                     '; the CPU figure is forward only'}
 
 
+def config4(a, dev):
+    """examples/linkproppred/tgn.py:60-124 (train) / :127-190 (eval, without the ranking metric)."""
+    from bench_rows import wiki_stream
+    from tgm_b200 import DeduplicationHook
+    from tgm_b200.nn import GraphAttentionEmbedding, TGNMemory
+    src, dst, t, x, N = wiki_stream()
+    t = np.arange(len(t), dtype=np.int64) * 17  # unique times: the TGN-memory parity domain
+    ei = torch.from_numpy(np.stack([src, dst], 1))
+    dg = DGraph(DGData.from_raw(torch.from_numpy(t), ei, torch.from_numpy(x)), device=dev)
+    bs, k, D, M, TD, Z = 200, 10, x.shape[1], 100, 100, 100
+    torch.manual_seed(1337)
+    mem = TGNMemory(N, D, M, TD).to(dev)
+    enc = GraphAttentionEmbedding(M, Z, D, mem.time_enc)
+    enc.conv.dropout = 0.0  # the B200 path trains with dropout 0 (cannot follow the reference RNG)
+    enc = enc.to(dev)
+    decoder = torch.nn.Sequential(torch.nn.Linear(2 * Z, Z), torch.nn.ReLU(),
+                                  torch.nn.Linear(Z, 1)).to(dev)  # the example's LinkPredictor
+    params = {id(q): q for m_ in (mem, enc, decoder) for q in m_.parameters()}  # time_enc is shared
+    opt = torch.optim.Adam(params.values(), lr=1e-4)
+    for m_ in (mem, enc, decoder):
+        m_.train(a.train)
+    hm = HookManager(keys=['train'])
+    hm.register('train', RandomNegativeEdgeSamplerHook(low=8227, high=N))
+    hm.register('train', RecencyNeighborHook(
+        num_nodes=N, num_nbrs=[k], seed_nodes_keys=['edge_src', 'edge_dst', 'neg'],
+        seed_times_keys=['edge_time', 'edge_time', 'neg_time']))
+    hm.register('train', DeduplicationHook(seed_nodes_keys=['neg', 'nbr_nids']))
+    nb = a.batches
+    losses = []
+    bce = torch.nn.functional.binary_cross_entropy_with_logits
+
+    def epoch():
+        hm.reset_state()
+        mem.reset_state()
+        losses.clear()
+        done = 0
+        with hm.activate('train'):
+            for batch in DGDataLoader(dg, batch_size=bs, hook_manager=hm):
+                if a.train:
+                    opt.zero_grad(set_to_none=True)
+                nbr = batch.nbr_nids[0].flatten()
+                keep = nbr != -1
+                seeds = torch.cat([batch.edge_src, batch.edge_dst, batch.neg]).repeat_interleave(k)
+                eidx = torch.stack([batch.global_to_local(seeds[keep]),
+                                    batch.global_to_local(nbr[keep])]).long()
+                z, lu = mem(batch.unique_nids)
+                z = enc(z, lu, eidx, batch.nbr_edge_time[0].flatten()[keep],
+                        batch.nbr_edge_x[0].flatten(0, -2)[keep])
+                i_s, i_d, i_n = (batch.global_to_local(v).long()
+                                 for v in (batch.edge_src, batch.edge_dst, batch.neg))
+                pos = decoder(torch.cat([z[i_s], z[i_d]], 1))
+                neg = decoder(torch.cat([z[i_s], z[i_n]], 1))
+                # update memory with the ground-truth state BEFORE backward, as the example does
+                mem.update_state(batch.edge_src, batch.edge_dst, batch.edge_time, batch.edge_x)
+                if a.train:
+                    loss = bce(pos, torch.ones_like(pos)) + bce(neg, torch.zeros_like(neg))
+                    loss.backward()
+                    opt.step()
+                    mem.detach()
+                    losses.append(loss.detach())
+                done += 1
+                if done == nb:
+                    break
+        return z
+
+    epoch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    z = epoch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {'row': 'config 4 on one GPU: TGN (memory 100 + attention embedding 100) on a tgbl-wiki-'
+                   'shaped stream, k=10, bs=200 (+200 negatives), through the drop-in loader/hook API',
+            'batches': nb, 'ms_per_batch': ms / nb, 'events_per_s': nb * bs / (ms * 1e-3),
+            'unique_nodes_last_batch': int(z.shape[0]),
+            'mode': 'train (forward + tgm_gae_backward + tgm_tgn_backward + Adam step, dropout 0)'
+                    if a.train else 'forward',
+            'loss_first_last': [float(losses[0]), float(losses[-1])] if losses else None,
+            'note': 'negatives -> ring sampler -> device dedup -> TGNMemory.forward -> '
+                    'GraphAttentionEmbedding -> torch MLP decoder -> update_state' +
+                    (' -> BCE -> backward -> Adam' if a.train else '') +
+                    '; launch/Python-bound at bs=200; the 4-GPU time-sharded form with the memory '
+                    'join is bench_tgn_shard.py'}
+
+
 def config5(a, dev, rank, world):
     E, N, D, bs, k = a.edges, a.nodes, 16, 200, 31
     g = torch.Generator(device=dev).manual_seed(0)
@@ -207,7 +297,7 @@ def config5(a, dev, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--train', action='store_true', help='forward + backward + Adam step per batch')
-    ap.add_argument('--config', type=int, required=True, choices=[3, 5])
+    ap.add_argument('--config', type=int, required=True, choices=[3, 4, 5])
     ap.add_argument('--batches', type=int, default=200)
     ap.add_argument('--window-batches', type=int, default=25)
     ap.add_argument('--edges', type=int, default=100_000_000)
@@ -221,7 +311,8 @@ def main():
     if world > 1:
         os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
-    out = config3(a, dev) if a.config == 3 else config5(a, dev, rank, world)
+    out = (config3(a, dev) if a.config == 3 else config4(a, dev) if a.config == 4
+           else config5(a, dev, rank, world))
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -1,0 +1,15 @@
+#!/bin/bash
+# First GPU call of the next round (one box, ~6 min):  gpurun --timeout 900 -- 'bash scratch/next_gpu_call.sh'
+# Everything lands in gpurun_out/; copy what should be judged into profiles/.
+set -x
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests.log 2>&1; tail -3 gpurun_out/gpu_tests.log
+python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 600 gpurun_out/bench_n1.json
+# config 4 (TGN) on one GPU, forward and training step: not measured in round 1
+python bench_configs.py --config 4 > gpurun_out/config4_tgn_n1.json 2>> gpurun_out/configs.err
+python bench_configs.py --config 4 --train > gpurun_out/config4_tgn_train_n1.json 2>> gpurun_out/configs.err
+cat gpurun_out/config4_tgn_n1.json gpurun_out/config4_tgn_train_n1.json
+# launch list of the training step (shares, not absolutes)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
+    --log-file gpurun_out/launches_config4_train.csv \
+    python bench_configs.py --config 4 --train --batches 5 > /dev/null 2>&1
