@@ -13,3 +13,7 @@ cat gpurun_out/config4_tgn_n1.json gpurun_out/config4_tgn_train_n1.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
     --log-file gpurun_out/launches_config4_train.csv \
     python bench_configs.py --config 4 --train --batches 5 > /dev/null 2>&1
+# config 5 training step: eager launches vs the whole step replayed as one CUDA graph
+python bench_configs.py --config 5 --train --batches 100 --edges 20000000 > gpurun_out/config5_train_eager.json 2>> gpurun_out/configs.err
+timeout 300 python bench_configs.py --config 5 --train --cuda-graph --batches 100 --edges 20000000 > gpurun_out/config5_train_graph.json 2>> gpurun_out/configs.err
+cat gpurun_out/config5_train_eager.json gpurun_out/config5_train_graph.json; tail -5 gpurun_out/configs.err
