@@ -1,0 +1,44 @@
+"""Differential check of the drop-in surface: the reference's OWN unit tests for the host-side
+protocol (hook bases, HookManager, DGraph views, hook constructors) are run unmodified with
+`tgm` aliased to `tgm_b200`.  On this CPU-only box every test that needs edge data must fail with
+the loud "no CPU fallback" error and nothing else; all others must pass.  Skipped where the
+reference tree is absent (it does not travel to the GPU box)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from tests.golden._ref_shim import REFERENCE_ROOT, reference_available
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# reference test file -> tests that pass without touching device data
+CASES = {
+    'test/unit/test_hooks/test_hook_manager.py': 34,
+    'test/unit/test_core/test_dgraph.py': 7,
+    'test/unit/test_hooks/test_deduplication_hook.py': 3,
+    'test/unit/test_hooks/test_neighbor_sampler_hook.py': 4,
+}
+
+
+@pytest.mark.skipif(not reference_available(), reason='reference tree not present')
+@pytest.mark.parametrize('path', sorted(CASES))
+def test_reference_unit_tests_run_against_the_drop_in(path, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CPU-only differential check (with a GPU the reference tests build CPU graphs '
+                    'that this package refuses by design)')
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', PYTHONPATH=ROOT, COLUMNS='400')
+    proc = subprocess.run(
+        [sys.executable, '-m', 'pytest', '-p', 'tests._reference_alias_plugin', '-p',
+         'no:cacheprovider', '-q', '-rf', '--color=no', os.path.join(REFERENCE_ROOT, path)],
+        cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    out = proc.stdout
+    failed = re.findall(r'^FAILED (\S+) - (.*)$', out, flags=re.M)
+    other = [(name, why) for name, why in failed if 'no CPU fallback' not in why]
+    assert not other, f'failures that are not the no-CPU-fallback refusal:\n{other}\n{out[-3000:]}'
+    m = re.search(r'(\d+) passed', out)
+    assert m and int(m.group(1)) >= CASES[path], out[-3000:]
+    assert 'error' not in out.splitlines()[-1], out[-3000:]

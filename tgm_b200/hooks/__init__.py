@@ -4,3 +4,4 @@ from .recency import RecencyNeighborHook
 from .negatives import RandomNegativeEdgeSamplerHook
 from .dedup import DeduplicationHook
 from .uniform import NeighborSamplerHook
+from .registry import hook, list_hooks

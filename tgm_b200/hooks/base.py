@@ -5,6 +5,7 @@ object with `has_state`, `requires`, `produces`, `__call__(dg, batch) -> batch` 
 (:101-103)."""
 from __future__ import annotations
 
+from abc import ABC, abstractmethod
 from typing import Any, List, Optional, Protocol, Set, runtime_checkable
 
 
@@ -23,17 +24,34 @@ class DGHook(Protocol):
     def reset_state(self) -> None: ...
 
 
-class BaseDGHook:
-    """Common bookkeeping; subclasses call `_init_hook` at the end of their __init__."""
+class BaseDGHook(ABC):
+    """Bookkeeping shared by every hook, with the construction protocol of the reference's
+    dataclass bases (tgm/hooks/base.py:27-76) so that user hooks written against them run
+    unchanged: `super().__init__(_requires=..., _produces=..., _id=..., has_state=...)` and an
+    idempotent `__post_init__()` that folds the LEAF class's `_cls_requires/_cls_produces` into the
+    instance sets (:41-43).  As upstream, `__init__` stores `has_state` on the instance (default
+    False, whatever the class attribute says), so a stateful user hook sets it itself.
+    The hooks of this package call `_init_hook` instead and keep the class attribute."""
     has_state: bool = False
     _cls_requires: Set[str] = set()
     _cls_produces: Set[str] = set()
 
-    def _init_hook(self, id: Optional[str] = None, seed_keys: Optional[List[str]] = None) -> None:
+    def __init__(self, _requires: Optional[Set[str]] = None, _produces: Optional[Set[str]] = None,
+                 _id: Optional[str] = None, has_state: bool = False) -> None:
+        self._requires: Set[str] = set() if _requires is None else _requires
+        self._produces: Set[str] = set() if _produces is None else _produces
+        self._id = _id
+        self.has_state = has_state
+        self.__post_init__()
+
+    def __post_init__(self) -> None:
         leaf = type(self).__dict__
-        self._requires: Set[str] = set(leaf.get('_cls_requires', set()))
-        self._produces: Set[str] = set(leaf.get('_cls_produces', set()))
-        self._id = id
+        self._requires.update(leaf.get('_cls_requires', ()))
+        self._produces.update(leaf.get('_cls_produces', ()))
+
+    def _init_hook(self, id: Optional[str] = None, seed_keys: Optional[List[str]] = None) -> None:
+        self._requires, self._produces, self._id = set(), set(), id
+        BaseDGHook.__post_init__(self)
         self.seed_keys = seed_keys
         if seed_keys:
             self._requires.update(seed_keys)
@@ -52,6 +70,7 @@ class BaseDGHook:
         name = type(self).__name__
         return f'{name}_{self._id}' if self._id else name
 
+    @abstractmethod
     def __call__(self, dg, batch):
         raise NotImplementedError
 
@@ -71,4 +90,14 @@ class StatefulHook(BaseDGHook):
 
 
 class SeedableHook(BaseDGHook):
-    """Marker for hooks that take extra seed attribute names (`seed_keys`)."""
+    """Hooks that take extra seed attribute names: `seed_keys` join `requires` (:92-103)."""
+
+    def __init__(self, _requires: Optional[Set[str]] = None, _produces: Optional[Set[str]] = None,
+                 _id: Optional[str] = None, has_state: bool = False,
+                 seed_keys: Optional[List[str]] = None) -> None:
+        self.seed_keys = [] if seed_keys is None else seed_keys
+        super().__init__(_requires, _produces, _id, has_state)
+
+    def __post_init__(self) -> None:
+        super().__post_init__()
+        self._requires.update(getattr(self, 'seed_keys', None) or [])

@@ -15,19 +15,12 @@ from typing import Any, Dict, Iterator, List, Optional, Set
 from tgm_b200.exceptions import (BadEncoderProtocolError, BadHookProtocolError,
                                  UnresolvableHookDependenciesError)
 from tgm_b200.hooks.base import DGHook
+from tgm_b200.hooks.registry import hook as register_hook_class  # noqa: F401  (older name)
+from tgm_b200.hooks.registry import list_hooks  # module-level name so tests can patch it
 
 # attributes every materialised batch carries without any hook (:23-35)
 CORE_ATTRIBUTE: Set[str] = {'edge_src', 'edge_dst', 'edge_time', 'edge_type', 'node_x_time',
                             'node_x_nids', 'node_y_time', 'node_y_nids', 'node_type'}
-
-_KNOWN_HOOK_CLASSES: List[type] = []
-
-
-def register_hook_class(cls: type) -> type:
-    """Class decorator: makes a hook discoverable for validate_requirement's suggestions
-    (tgm/hooks/registry.py:8-22)."""
-    _KNOWN_HOOK_CLASSES.append(cls)
-    return cls
 
 
 class HookManager:
@@ -130,11 +123,12 @@ class HookManager:
 
     @staticmethod
     def _suggest(missing: Set[str], key: str) -> str:
+        # `list_hooks` is resolved through the module namespace at call time (patchable)
         msg = (f'Cannot resolve the following requirements {missing} from any hook registered '
                f"under key '{key}'.\nSuggestions:")
         for attr in missing:
             hit = False
-            for cls in _KNOWN_HOOK_CLASSES:
+            for cls in list_hooks():
                 produced = getattr(cls, '_cls_produces', set())
                 close = difflib.get_close_matches(attr, produced, n=2, cutoff=0.6)
                 if attr in produced:
