@@ -298,3 +298,28 @@ def test_view_metadata_and_loader_plan_match_reference_fixture(name):
                 nid, tt = nid[np.lexsort((nid, tt))], np.sort(tt)
                 w_id, w_t = w_id[np.lexsort((w_id, w_t))], np.sort(w_t)
             assert np.array_equal(nid, w_id) and np.array_equal(tt, w_t), (i, ids_k)
+
+
+# --- public signatures vs a snapshot of the reference's -----------------------------------------
+def test_public_signatures_accept_every_reference_argument():
+    """tests/golden/api_signatures.json (make_golden_api.py) holds parameter names, order, kinds and
+    defaults of the reference's constructors/methods on the hot path.  The drop-in must accept each
+    of them at the same position with the same default; extra optional parameters may follow
+    (e.g. RecencyNeighborHook(window_batches=...))."""
+    import tgm_b200
+    from tests.golden._api_sig import describe, resolve
+    snap = json.load(open(os.path.join(GOLDEN_DIR, 'api_signatures.json')))
+    assert len(snap) >= 35
+    for dotted, want in snap.items():
+        got = describe(resolve(tgm_b200, dotted))
+        assert len(got) >= len(want), dotted
+        for g, w in zip(got, want):
+            assert g[:2] == w[:2], (dotted, g, w)  # same name, same kind, same position
+            if w[2] == ['required']:  # may have become optional here (default None): still accepted
+                assert g[2] == ['required'] or g[2] == ['value', None], (dotted, g, w)
+            elif w[2][0] == 'object':  # a class / factory default upstream: any default will do
+                assert g[2] != ['required'], (dotted, g, w)
+            else:
+                assert g[2] == w[2], (dotted, g, w)
+        for extra in got[len(want):]:
+            assert extra[2] != ['required'] or extra[1].startswith('VAR_'), (dotted, extra)
