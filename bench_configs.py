@@ -58,7 +58,10 @@ def config3(a, dev):
     # not part of the hot path; only used by --train to give the backward pass a loss
     decoder = torch.nn.Sequential(torch.nn.Linear(2 * 172, 172), torch.nn.ReLU(),
                                   torch.nn.Linear(172, 1)).to(dev)
-    opt = torch.optim.Adam(list(model.parameters()) + list(decoder.parameters()), lr=1e-4)
+    if a.cuda_graph and not a.train:
+        raise SystemExit('--cuda-graph captures the training step: add --train')
+    opt = torch.optim.Adam(list(model.parameters()) + list(decoder.parameters()), lr=1e-4,
+                           capturable=bool(a.cuda_graph))
     node_x = torch.randn(N, 1, device=dev)
     hm = HookManager(keys=['train'])
     hm.register('train', RandomNegativeEdgeSamplerHook(low=8227, high=N))
@@ -68,6 +71,42 @@ def config3(a, dev):
     nb = a.batches
 
     losses = []
+    graph = {}  # --cuda-graph: static input buffers + the captured training step
+
+    def model_inputs(batch):
+        return [*batch.seed_nids, *batch.seed_times, *batch.nbr_nids, *batch.nbr_edge_x,
+                *batch.nbr_edge_time]
+
+    def static_step():
+        st, L = graph['static'], len(nn)
+        z = model(node_x, st[0:L], st[L:2 * L], st[2 * L:3 * L], st[3 * L:4 * L], st[4 * L:5 * L])
+        n = bs
+        zs, zd, zn = z[:n], z[n:2 * n], z[2 * n:]
+        pos = decoder(torch.cat([zs, zd], 1))
+        neg = decoder(torch.cat([zs, zn], 1))
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(pos, torch.ones_like(pos)) + \
+            torch.nn.functional.binary_cross_entropy_with_logits(neg, torch.zeros_like(neg))
+        loss.backward()
+        opt.step()
+        return z, loss
+
+    def capture(batch):
+        """Whole model step (TGAT forward + tgm_attn_backward + Adam) as one CUDA graph over static
+        copies of the hook outputs; the loader and the hooks stay eager Python."""
+        graph['static'] = [torch.empty_like(v) for v in model_inputs(batch)]
+        for dst_, src_ in zip(graph['static'], model_inputs(batch)):
+            dst_.copy_(src_)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                opt.zero_grad(set_to_none=True)
+                static_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        opt.zero_grad(set_to_none=True)
+        graph['g'] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph['g']):
+            graph['out'] = static_step()
 
     def epoch():
         hm.reset_state()
@@ -75,6 +114,18 @@ def config3(a, dev):
         losses.clear()
         with hm.activate('train'):
             for batch in DGDataLoader(dg, batch_size=bs, hook_manager=hm):
+                if a.cuda_graph and batch.edge_src.numel() == bs and batch.neg.numel() == bs:
+                    if 'g' not in graph:
+                        capture(batch)
+                    for dst_, src_ in zip(graph['static'], model_inputs(batch)):
+                        dst_.copy_(src_)
+                    graph['g'].replay()
+                    z = graph['out'][0]
+                    losses.append(graph['out'][1].detach().clone())
+                    done += 1
+                    if done == nb:
+                        break
+                    continue
                 if a.train:
                     opt.zero_grad(set_to_none=True)
                 z = model(node_x, batch.seed_nids, batch.seed_times, batch.nbr_nids,
@@ -129,7 +180,8 @@ def config3(a, dev):
             'cpu_baseline': {'value': cpu_ms, 'unit': 'ms/batch', 'kind': 'port',
                              'cores': os.cpu_count(),
                              'sample': f'{nbc} batches: C ring sampler + numpy TGAT oracle'},
-            'mode': 'train (forward + tgm_attn_backward + Adam step, dropout 0)' if a.train else 'forward',
+            'mode': ('train (forward + tgm_attn_backward + Adam step, dropout 0)' +
+                     (', model step replayed as one CUDA graph' if graph else '')) if a.train else 'forward',
             'loss_first_last': [float(losses[0]), float(losses[-1])] if losses else None,
             'note': 'DGDataLoader + HookManager + windowed RecencyNeighborHook + TGAT.forward' +
                     (' + BCE loss on a torch MLP decoder + backward + Adam' if a.train else '') +
@@ -353,7 +405,8 @@ def main():
     ap.add_argument('--train', action='store_true', help='forward + backward + Adam step per batch')
     ap.add_argument('--config', type=int, required=True, choices=[3, 4, 5])
     ap.add_argument('--cuda-graph', action='store_true',
-                    help='config 5 --train on one GPU: capture the whole training step in a CUDA graph')
+                    help='configs 3 and 5 with --train on one GPU: capture the training step (forward + '
+                         'backward + Adam) in a CUDA graph and replay it per batch')
     ap.add_argument('--batches', type=int, default=200)
     ap.add_argument('--window-batches', type=int, default=25)
     ap.add_argument('--edges', type=int, default=100_000_000)

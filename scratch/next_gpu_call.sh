@@ -17,3 +17,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
 python bench_configs.py --config 5 --train --batches 100 --edges 20000000 > gpurun_out/config5_train_eager.json 2>> gpurun_out/configs.err
 timeout 300 python bench_configs.py --config 5 --train --cuda-graph --batches 100 --edges 20000000 > gpurun_out/config5_train_graph.json 2>> gpurun_out/configs.err
 cat gpurun_out/config5_train_eager.json gpurun_out/config5_train_graph.json; tail -5 gpurun_out/configs.err
+# config 3 training step: eager vs CUDA graph of the model step
+python bench_configs.py --config 3 --train --batches 100 > gpurun_out/config3_train_eager.json 2>> gpurun_out/configs.err
+timeout 300 python bench_configs.py --config 3 --train --cuda-graph --batches 100 > gpurun_out/config3_train_graph.json 2>> gpurun_out/configs.err
+cat gpurun_out/config3_train_eager.json gpurun_out/config3_train_graph.json; tail -5 gpurun_out/configs.err
