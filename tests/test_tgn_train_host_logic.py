@@ -74,3 +74,30 @@ def test_inference_paths_do_not_record_autograd(fake):
         enc.train()(torch.randn(6, 4), torch.zeros(6, dtype=torch.int64),
                     torch.zeros(2, 0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64),
                     torch.zeros(0, 3))
+
+
+def test_state_dict_interchanges_with_the_reference_checkpoint_layout(fake):
+    """The reference registers memory / last_update / _assoc as buffers (tgn.py:128-133), so its
+    checkpoints carry them; here they live behind the native handle and are mapped in and out."""
+    from tgm_b200.nn import TGNMemory
+    N, D, M, TD = 10, 3, 4, 5
+    m = TGNMemory(N, D, M, TD)
+    sd = m.state_dict()
+    assert {'memory', 'last_update', '_assoc', 'memory_updater.weight_ih', 'time_enc.w.weight'} <= set(sd)
+    assert sd['memory'].shape == (N, M) and not sd['memory'].any() and sd['last_update'].dtype == torch.int64
+    ckpt = {k: v.clone() for k, v in sd.items()}
+    ckpt['memory'], ckpt['last_update'] = torch.arange(40.).view(N, M), torch.arange(N)
+    m2 = TGNMemory(N, D, M, TD)
+    m2.load_state_dict(ckpt)                               # before any handle exists: kept pending
+    assert torch.equal(m2.state_dict()['memory'], ckpt['memory']) and 'tgm_tgn_create' not in fake.calls
+    assert torch.equal(m2.memory, ckpt['memory']) and torch.equal(m2.last_update, ckpt['last_update'])
+    assert '_pending_state' not in m2.__dict__ and fake.calls['tgm_tgn_create'] == 1
+    live = m2.state_dict()
+    live['memory'] = live['memory'] * 2
+    m2.load_state_dict(live)                               # live handle: written through
+    assert torch.equal(m2.memory, ckpt['memory'] * 2) and fake.calls['tgm_tgn_create'] == 1
+    params_only = {k: v for k, v in sd.items() if k not in ('memory', 'last_update', '_assoc')}
+    TGNMemory(N, D, M, TD).load_state_dict(params_only)    # parameter-only checkpoints still load
+    bad = dict(sd, memory=torch.zeros(3, M))
+    with pytest.raises(RuntimeError, match='memory'):
+        TGNMemory(N, D, M, TD).load_state_dict(bad)

@@ -131,7 +131,10 @@ class TGNMemory(nn.Module):
                 _device_index(dev)))
             self._native.version = ver
             self._native_dev = dev
-            if old is not None:  # parameters moved to another device: memory carries over
+            pending = self.__dict__.pop('_pending_state', None)  # from load_state_dict
+            if pending is not None:
+                old = pending
+            if old is not None:  # parameters moved to another device / a loaded checkpoint
                 self.memory.copy_(old[0])
                 self.last_update.copy_(old[1])
         return self._native.h
@@ -150,6 +153,45 @@ class TGNMemory(nn.Module):
         return (_cabi.device_view(pm.value, (self.num_nodes, self.memory_dim), torch.float32,
                                   dev).clone(),
                 _cabi.device_view(pl.value, (self.num_nodes,), torch.int64, dev).clone())
+
+    # -- checkpoints: the reference registers `memory`, `last_update` and `_assoc` as buffers
+    #    (tgn.py:128-133), so its state_dict carries them; here they live behind the handle
+    def _save_to_state_dict(self, destination, prefix, keep_vars) -> None:
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        pending = self.__dict__.get('_pending_state')
+        if self._native.h.value:
+            mem, lu = self._snapshot()
+        elif pending is not None:
+            mem, lu = pending[0].clone(), pending[1].clone()
+        else:  # no state yet: what reset_state() would give
+            dev = self.device
+            mem = torch.zeros((self.num_nodes, self.memory_dim), dtype=torch.float32, device=dev)
+            lu = torch.zeros((self.num_nodes,), dtype=torch.int64, device=dev)
+        destination[prefix + 'memory'] = mem
+        destination[prefix + 'last_update'] = lu
+        destination[prefix + '_assoc'] = torch.zeros((self.num_nodes,), dtype=torch.int64,
+                                                     device=lu.device)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys,
+                              unexpected_keys, error_msgs) -> None:
+        mem = state_dict.pop(prefix + 'memory', None)
+        lu = state_dict.pop(prefix + 'last_update', None)
+        state_dict.pop(prefix + '_assoc', None)  # scratch of _get_updated_memory upstream
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys,
+                                      unexpected_keys, error_msgs)
+        if mem is None and lu is None:
+            return
+        if mem is None or lu is None or tuple(mem.shape) != (self.num_nodes, self.memory_dim) or \
+                tuple(lu.shape) != (self.num_nodes,):
+            error_msgs.append(f'{prefix}memory / {prefix}last_update: expected shapes '
+                              f'({self.num_nodes}, {self.memory_dim}) and ({self.num_nodes},)')
+            return
+        state = (mem.detach().to(torch.float32), lu.detach().to(torch.int64))
+        if self._native.h.value:  # live handle: write through the views
+            self.memory.copy_(state[0])
+            self.last_update.copy_(state[1])
+        else:  # applied when the handle is created (parameters may still be on the CPU)
+            self.__dict__['_pending_state'] = state
 
     @property
     def memory(self) -> Tensor:
