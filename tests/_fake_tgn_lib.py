@@ -126,13 +126,14 @@ class FakeLib:
         nid = _arr(nid_p, (n,), _I64)
         obj.orc.training = True
         z, lu = obj.orc.forward(nid)
-        aggr, dt, has = obj.orc.aggregated_messages(nid)
+        aggr, rows, dt, _ = obj.orc.aggregated_messages(nid)  # LastAggregator: one message per row
         _arr(mem_p, (n, M))[:] = z
         _arr(lu_p, (n,), _I64)[:] = lu
         _arr(sx_p, (n, D + 2 * M + TD))[:] = aggr
         _arr(sh_p, (n, M))[:] = obj.orc.memory[nid]
         aux = _arr(aux_p, (n, 2))
-        aux[:, 0], aux[:, 1] = dt, has
+        aux[:] = 0
+        aux[rows, 0], aux[rows, 1] = dt, 1.0
         return 0
 
     def tgm_tgn_update_state(self, h, src_p, dst_p, t_p, raw_p, Eb, training, stream):

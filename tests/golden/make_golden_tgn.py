@@ -4,7 +4,8 @@ examples/linkproppred/tgn.py:60-124 drives it:  python tests/golden/make_golden_
 
 torch_geometric is not installed here; the import shim supplies `zeros` (in-place fill) and a
 `scatter(reduce=max|mean)` restatement over torch.scatter_reduce_ (tests/golden/_ref_shim.py).
-Writes tests/golden/tgn_*.npz (states) and tests/golden/tgngrad_*.npz (gradients)."""
+Writes tests/golden/tgn_*.npz (states) and tgngrad_*.npz (gradients) for the LastAggregator,
+tgnmean_*.npz / tgnmeangrad_*.npz for the MeanAggregator."""
 from __future__ import annotations
 
 import os
@@ -18,10 +19,10 @@ sys.path.insert(0, HERE)
 from _ref_shim import import_reference  # noqa: E402
 
 import_reference()
-from tgm.nn.encoder.tgn import IdentityMessage, LastAggregator, TGNMemory  # noqa: E402
+from tgm.nn.encoder.tgn import IdentityMessage, LastAggregator, MeanAggregator, TGNMemory  # noqa: E402
 
 
-def run(name, N, E, T, D, M, TD, bs, eval_from, seed, bias):
+def run(name, N, E, T, D, M, TD, bs, eval_from, seed, bias, mean=False):
     # Parity domain: within one batch no node may have two events with the same timestamp in the
     # same role.  TGNMemory._update_msg_store orders a node's events with `src.sort()`
     # (tgn.py:226), which is NOT stable on CPU, so LastAggregator's first-of-the-ties choice
@@ -42,7 +43,7 @@ def run(name, N, E, T, D, M, TD, bs, eval_from, seed, bias):
     neg = rng.integers(0, N, E)
     torch.manual_seed(seed)
     mem = TGNMemory(N, D, M, TD, message_module=IdentityMessage(D, M, TD),
-                    aggregator_module=LastAggregator())
+                    aggregator_module=MeanAggregator() if mean else LastAggregator())
     with torch.no_grad():
         for prm in mem.memory_updater.parameters():
             prm.copy_(torch.randn(prm.shape) * 0.3)
@@ -69,14 +70,14 @@ def run(name, N, E, T, D, M, TD, bs, eval_from, seed, bias):
     out['final_last_update'] = mem.last_update.numpy().copy()
     sd = {'p.' + k: v.numpy() for k, v in mem.state_dict().items()
           if k not in ('memory', 'last_update', '_assoc')}
-    np.savez_compressed(os.path.join(HERE, f'tgn_{name}.npz'), src=src.astype(np.int32),
+    np.savez_compressed(os.path.join(HERE, f"tgn{'mean' if mean else ''}_{name}.npz"), src=src.astype(np.int32),
                         dst=dst.astype(np.int32), t=t.astype(np.int64), x=x,
                         neg=neg.astype(np.int32), N=np.int64(N), bs=np.int64(bs),
-                        eval_from=np.int64(eval_from), **sd, **out)
+                        eval_from=np.int64(eval_from), mean=np.int64(mean), **sd, **out)
     print(name, 'ok', float(np.abs(out['final_memory']).max()))
 
 
-def run_grad(name, N, E, T, D, M, TD, bs, seed, bias, record_from):
+def run_grad(name, N, E, T, D, M, TD, bs, seed, bias, record_from, mean=False):
     """Training-mode gradients: the loop of examples/linkproppred/tgn.py:70-121 with the loss
     replaced by sum(z * G) for a recorded random G (forward, update_state, backward, detach); the
     .grad of every TGNMemory parameter is saved for the batches >= record_from (earlier batches
@@ -88,7 +89,7 @@ def run_grad(name, N, E, T, D, M, TD, bs, seed, bias, record_from):
     neg = rng.integers(0, N, E)
     torch.manual_seed(seed)
     mem = TGNMemory(N, D, M, TD, message_module=IdentityMessage(D, M, TD),
-                    aggregator_module=LastAggregator())
+                    aggregator_module=MeanAggregator() if mean else LastAggregator())
     with torch.no_grad():
         for prm in mem.memory_updater.parameters():
             prm.copy_(torch.randn(prm.shape) * 0.3)
@@ -116,10 +117,10 @@ def run_grad(name, N, E, T, D, M, TD, bs, seed, bias, record_from):
                 out[f'b{b}_g.{k}'] = prm.grad.numpy().copy()
     sd = {'p.' + k: v.numpy() for k, v in mem.state_dict().items()
           if k not in ('memory', 'last_update', '_assoc')}
-    np.savez_compressed(os.path.join(HERE, f'tgngrad_{name}.npz'), src=src.astype(np.int32),
+    np.savez_compressed(os.path.join(HERE, f"tgn{'mean' if mean else ''}grad_{name}.npz"), src=src.astype(np.int32),
                         dst=dst.astype(np.int32), t=t.astype(np.int64), x=x,
                         neg=neg.astype(np.int32), N=np.int64(N), bs=np.int64(bs),
-                        record_from=np.int64(record_from), **sd, **out)
+                        record_from=np.int64(record_from), mean=np.int64(mean), **sd, **out)
     print('grad', name, 'ok', max(float(np.abs(v).max()) for k, v in out.items() if '_g.' in k))
 
 
@@ -133,6 +134,11 @@ def main():
     run_grad('small', 30, 300, 3000, 4, 8, 6, 20, 5, False, 3)
     run_grad('bias', 25, 300, 900, 3, 6, 4, 25, 6, True, 4)
     run_grad('c4_dims', 300, 1200, 2_000_000, 16, 100, 100, 200, 7, False, 3)
+    # MeanAggregator (tgn.py:59-63): small node sets so that nodes collect several messages per batch
+    run('small', 12, 400, 3000, 4, 8, 6, 20, -1, 8, True, mean=True)
+    run('then_eval', 25, 600, 5000, 5, 10, 8, 30, 12, 9, False, mean=True)
+    run_grad('small', 12, 300, 3000, 4, 8, 6, 20, 10, True, 3, mean=True)
+    run_grad('c4_dims', 60, 1200, 2_000_000, 16, 100, 100, 200, 11, False, 3, mean=True)
 
 
 if __name__ == '__main__':

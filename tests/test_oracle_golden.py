@@ -460,3 +460,55 @@ def test_graph_attention_embedding_backward_oracle_agrees_with_torch_autograd():
         # 1e-5: the oracle takes -sin of the float32-rounded Time2Vec argument (as the forward
         # rounds it), torch here of the float64 one
         assert np.abs(g[name] - want).max() <= 1e-5 * max(1.0, np.abs(want).max()), name
+
+
+# ---- TGN memory with the MeanAggregator (tgn.py:59-63) -------------------------------------------------
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'tgnmean_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[8:-4])
+def test_tgn_mean_aggregator_oracle_matches_reference(path):
+    z = np.load(path)
+    p = _params(z)
+    N, bs, eval_from = int(z['N']), int(z['bs']), int(z['eval_from'])
+    D, M, TD = z['x'].shape[1], p['memory_updater.weight_hh'].shape[1], p['time_enc.w.bias'].shape[0]
+    assert int(z['mean']) == 1
+    mem = TGNMemoryOracle(N, D, M, TD, p, aggregator='mean')
+    E = len(z['src'])
+    for b, lo in enumerate(range(0, E, bs)):
+        hi = min(lo + bs, E)
+        if b == eval_from:
+            mem.train(False)
+            assert np.abs(mem.memory - z['flush_memory']).max() <= 1e-5
+            assert np.array_equal(mem.last_update, z['flush_last_update'])
+        zz, lu = mem.forward(z[f'b{b}_nid'])
+        assert np.abs(zz - z[f'b{b}_z']).max() <= 1e-5, b
+        assert np.array_equal(lu, z[f'b{b}_lu']), b
+        mem.update_state(z['src'][lo:hi], z['dst'][lo:hi], z['t'][lo:hi], z['x'][lo:hi])
+    assert np.abs(mem.memory - z['final_memory']).max() <= 1e-5
+    assert np.array_equal(mem.last_update, z['final_last_update'])
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'tgnmeangrad_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[12:-4])
+def test_tgn_mean_aggregator_backward_oracle_matches_reference_autograd(path):
+    from oracle.tgn_oracle import tgn_memory_backward
+    z = np.load(path)
+    p = _params(z)
+    N, bs, rec = int(z['N']), int(z['bs']), int(z['record_from'])
+    D, M, TD = z['x'].shape[1], p['memory_updater.weight_hh'].shape[1], p['time_enc.w.bias'].shape[0]
+    mem = TGNMemoryOracle(N, D, M, TD, p, aggregator='mean')
+    E, checked, multi = len(z['src']), 0, 0
+    for b, lo in enumerate(range(0, E, bs)):
+        hi = min(lo + bs, E)
+        if b >= rec:
+            n_id = z[f'b{b}_nid']
+            zz, _ = mem.forward(n_id)
+            assert np.abs(zz - z[f'b{b}_z']).max() <= 1e-5, b
+            _, rows, _, weight = mem.aggregated_messages(n_id)
+            multi += int((weight < 1).sum())
+            g = tgn_memory_backward(mem, n_id, z[f'b{b}_G'])
+            for name in [k.split('_g.', 1)[1] for k in z.files if k.startswith(f'b{b}_g.')]:
+                want = z[f'b{b}_g.{name}']
+                assert np.abs(g[name] - want).max() <= 2e-4 * max(1.0, np.abs(want).max()), (b, name)
+            checked += 1
+        mem.update_state(z['src'][lo:hi], z['dst'][lo:hi], z['t'][lo:hi], z['x'][lo:hi])
+    assert checked >= 3 and multi > 0  # nodes with several messages were exercised
