@@ -318,8 +318,9 @@ int tgm_tgn_flush(tgm_tgn *, tgm_stream stream);
  * loss.backward() runs AFTER memory.update_state()).  The state has moved on by then, so the
  * training forward hands the caller what the backward needs of its rows:
  *   saved_x f32[n,in] (in = raw_msg_dim + 2*memory_dim + time_dim: the LastAggregator's message per
- *   node, zeros without one), saved_h f32[n,M] (memory[n_id]), saved_aux f32[n,2] = {float32(t -
- *   last_update) of that message, 1 if the node has a message else 0}.
+ *   node, zeros without one), saved_h f32[n,M] (memory[n_id]), saved_aux f32[n,
+ *   tgm_tgn_saved_aux_width()] = {float32(t - last_update) of that message, 1 if the node has a
+ *   message else 0} for the LastAggregator.
  * tgm_tgn_forward_saved == tgm_tgn_forward(training = 1) + those rows.  tgm_tgn_backward is a
  * function of the saved rows, the handle's CURRENT parameters and d_memory f32[n,M] only; it ADDS
  * into the gradient buffers (torch layouts: g_w_ih [3M,in], g_w_hh [3M,M], g_b_ih/g_b_hh [3M],
@@ -327,6 +328,17 @@ int tgm_tgn_flush(tgm_tgn *, tgm_stream stream);
  * messages are buffers/inputs without gradient in the reference (tgn.py:128-133, :154-155).
  * tgm_tgn_set_params refreshes the parameter copies in place after an optimizer step (the node
  * state and the message stores are kept); pointers may be host or device. */
+/* Message aggregator (tgn.py:43-63).  TGM_TGN_AGGR_LAST (the default, LastAggregator): the message
+ * with the largest t per node.  TGM_TGN_AGGR_MEAN (MeanAggregator = scatter(mean)): the mean over
+ * all messages of the node's last batch as source and as destination; the batches pushed since the
+ * last reset/flush are then kept in an append-only device log (log_capacity events reserved up
+ * front, grown by doubling -- the one synchronising path).  Switching resets the state; call it
+ * right after tgm_tgn_create.  tgm_tgn_saved_aux_width: floats per row of saved_aux below
+ * (2 for LAST, 2 * time_dim for MEAN: the means of sin(arg) and sin(arg) * dt over the messages). */
+#define TGM_TGN_AGGR_LAST 0
+#define TGM_TGN_AGGR_MEAN 1
+int tgm_tgn_set_aggregator(tgm_tgn *, int kind, int64_t log_capacity, tgm_stream stream);
+int tgm_tgn_saved_aux_width(const tgm_tgn *);
 int tgm_tgn_set_params(tgm_tgn *, const float *gru_w_ih, const float *gru_w_hh,
                        const float *gru_b_ih, const float *gru_b_hh, const float *t2v_w,
                        const float *t2v_b, tgm_stream stream);

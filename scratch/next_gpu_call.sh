@@ -4,6 +4,8 @@
 set -x
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests.log 2>&1; tail -3 gpurun_out/gpu_tests.log
+# first hardware run of the MeanAggregator kernels (own process; remove the env gate once green)
+TGM_B200_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_zz_gpu_tgn_mean.py -q > gpurun_out/gpu_tgn_mean.log 2>&1; tail -15 gpurun_out/gpu_tgn_mean.log
 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 600 gpurun_out/bench_n1.json
 # config 4 (TGN) on one GPU, forward and training step: not measured in round 1
 python bench_configs.py --config 4 > gpurun_out/config4_tgn_n1.json 2>> gpurun_out/configs.err

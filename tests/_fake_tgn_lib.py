@@ -97,6 +97,33 @@ class FakeLib:
         self._get(h).set_params(rest[:6])
         return 0
 
+    def tgm_tgn_set_aggregator(self, h, kind, log_capacity, stream):
+        self._count('tgm_tgn_set_aggregator')
+        obj = self._get(h)
+        obj.orc.aggregator = 'mean' if kind == 1 else 'last'
+        obj.orc.reset_state()
+        return 0
+
+    def tgm_tgn_saved_aux_width(self, h):
+        obj = self._get(h)
+        return 2 * obj.dims[3] if obj.orc.aggregator == 'mean' else 2
+
+    def _aux(self, obj, nid, n):
+        """saved_aux as the library lays it out for the handle's aggregator."""
+        N, D, M, TD = obj.dims
+        aggr, rows, dt, weight = obj.orc.aggregated_messages(nid)
+        if obj.orc.aggregator == 'mean':  # per row: mean of sin(arg) | mean of sin(arg) * dt
+            p = obj.orc.p
+            sn = np.sin(O._t2v_arg(dt, p['time_enc.w.weight'].reshape(-1), p['time_enc.w.bias']))
+            x = np.asarray(dt).astype(np.float32).astype(np.float64)
+            aux = np.zeros((n, 2 * TD))
+            np.add.at(aux[:, :TD], rows, sn * weight[:, None])
+            np.add.at(aux[:, TD:], rows, sn * (x * weight)[:, None])
+            return aggr, aux
+        aux = np.zeros((n, 2))
+        aux[rows, 0], aux[rows, 1] = dt, 1.0
+        return aggr, aux
+
     def tgm_tgn_reset(self, h, stream):
         self._get(h).orc.reset_state()
         return 0
@@ -126,14 +153,12 @@ class FakeLib:
         nid = _arr(nid_p, (n,), _I64)
         obj.orc.training = True
         z, lu = obj.orc.forward(nid)
-        aggr, rows, dt, _ = obj.orc.aggregated_messages(nid)  # LastAggregator: one message per row
+        aggr, aux_rows = self._aux(obj, nid, n)
         _arr(mem_p, (n, M))[:] = z
         _arr(lu_p, (n,), _I64)[:] = lu
         _arr(sx_p, (n, D + 2 * M + TD))[:] = aggr
         _arr(sh_p, (n, M))[:] = obj.orc.memory[nid]
-        aux = _arr(aux_p, (n, 2))
-        aux[:] = 0
-        aux[rows, 0], aux[rows, 1] = dt, 1.0
+        _arr(aux_p, aux_rows.shape)[:] = aux_rows
         return 0
 
     def tgm_tgn_update_state(self, h, src_p, dst_p, t_p, raw_p, Eb, training, stream):
@@ -158,11 +183,15 @@ class FakeLib:
         N, D, M, TD = obj.dims
         IN = D + 2 * M + TD
         p = obj.orc.p
-        aux = _arr(aux_p, (n, 2))
         g = O.gru_cell_backward(p, _arr(sx_p, (n, IN)), _arr(sh_p, (n, M)), _arr(dm_p, (n, M)))
-        d_enc = g.pop('x')[:, 2 * M + D:] * aux[:, 1:2]
-        gw, gb = O.time2vec_backward(aux[:, 0], p['time_enc.w.weight'].reshape(-1),
-                                     p['time_enc.w.bias'], d_enc)
+        d_enc = g.pop('x')[:, 2 * M + D:]
+        if obj.orc.aggregator == 'mean':
+            aux = _arr(aux_p, (n, 2 * TD)).astype(np.float64)
+            gw, gb = -(aux[:, TD:] * d_enc).sum(0), -(aux[:, :TD] * d_enc).sum(0)
+        else:
+            aux = _arr(aux_p, (n, 2))
+            gw, gb = O.time2vec_backward(aux[:, 0], p['time_enc.w.weight'].reshape(-1),
+                                         p['time_enc.w.bias'], d_enc * aux[:, 1:2])
         _arr(gwih, (3 * M, IN))[:] += g['memory_updater.weight_ih']
         _arr(gwhh, (3 * M, M))[:] += g['memory_updater.weight_hh']
         _arr(gbih, (3 * M,))[:] += g['memory_updater.bias_ih']

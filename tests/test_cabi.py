@@ -119,6 +119,8 @@ def test_tgn_training_entry_points_validate_their_arguments():
         'tgm_tgn_set_params': lambda: L.tgm_tgn_set_params(*[None] * 8),
         'tgm_tgn_forward_saved': lambda: L.tgm_tgn_forward_saved(None, None, 4, *[None] * 6),
         'tgm_tgn_backward': lambda: L.tgm_tgn_backward(None, None, None, None, 4, *[None] * 8),
+        'tgm_tgn_set_aggregator': lambda: L.tgm_tgn_set_aggregator(None, 1, 0, None),
+        'tgm_tgn_saved_aux_width': lambda: L.tgm_tgn_saved_aux_width(None),
         'tgm_gae_set_params': lambda: L.tgm_gae_set_params(*[None] * 13),
         'tgm_gae_backward': lambda: L.tgm_gae_backward(None, None, None, 4, None, None, None, None,
                                                        4, *[None] * 8)}

@@ -101,3 +101,38 @@ def test_state_dict_interchanges_with_the_reference_checkpoint_layout(fake):
     bad = dict(sd, memory=torch.zeros(3, M))
     with pytest.raises(RuntimeError, match='memory'):
         TGNMemory(N, D, M, TD).load_state_dict(bad)
+
+
+# --- MeanAggregator: the same host-side checks for tests/test_zz_gpu_tgn_mean.py ---------------------
+from tests import test_zz_gpu_tgn_mean as gpu_mean_tests  # noqa: E402
+
+
+@pytest.fixture
+def fake_mean(monkeypatch):
+    monkeypatch.setattr(gpu_mean_tests, 'DEV', 'cpu')
+    with _fake_tgn_lib.installed() as lib:
+        yield lib
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'tgnmean_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[8:-4])
+def test_mean_aggregator_state_machine_through_the_python_face(fake_mean, path):
+    gpu_mean_tests.test_tgn_mean_memory_matches_reference_fixture(path)
+    assert fake_mean.calls['tgm_tgn_set_aggregator'] == 1
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'tgnmeangrad_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[12:-4])
+def test_mean_aggregator_gradients_through_the_python_face(fake_mean, path):
+    gpu_mean_tests.test_tgn_mean_memory_gradients_match_reference_autograd(path)
+    assert fake_mean.calls['tgm_tgn_backward'] >= 3
+
+
+def test_mean_aggregator_many_messages_per_node(fake_mean):
+    gpu_mean_tests.test_tgn_mean_gradients_vs_oracle_at_c4_dims_with_many_messages_per_node()
+
+
+def test_unknown_aggregator_is_refused():
+    from tgm_b200.nn import TGNMemory
+    with pytest.raises(NotImplementedError):
+        TGNMemory(10, 3, 4, 5, aggregator_module=torch.nn.Identity())

@@ -109,6 +109,8 @@ SIGNATURES = {
                                      c_int, c_void_p]),
     'tgm_tgn_flush': (c_int, [c_void_p, c_void_p]),
     'tgm_tgn_set_params': (c_int, [c_void_p] * 8),
+    'tgm_tgn_set_aggregator': (c_int, [c_void_p, c_int, c_int64, c_void_p]),
+    'tgm_tgn_saved_aux_width': (c_int, [c_void_p]),
     'tgm_tgn_forward_saved': (c_int, [c_void_p, c_void_p, c_int64] + [c_void_p] * 6),
     'tgm_tgn_backward': (c_int, [c_void_p] * 4 + [c_int64] + [c_void_p] * 8),
     'tgm_dyg_create': (c_int, [POINTER(c_void_p), c_void_p, c_int]),

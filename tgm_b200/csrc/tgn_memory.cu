@@ -43,9 +43,22 @@ struct tgm_tgn {
   int32_t *rows = nullptr;  // [cap] node id of each workspace row
   float *X = nullptr, *H = nullptr, *GI = nullptr, *GH = nullptr, *newmem = nullptr;
   int64_t *newlu = nullptr;
+  // MeanAggregator mode (tgm_tgn_set_aggregator): a node's store is "the events of the last batch
+  // it appeared in", so the batches pushed since the last reset/flush are kept in an append-only
+  // log and every node remembers where its last batch sits: bstart (-1 = none) / blen, per role
+  int aggr = 0;  // 0 = LastAggregator, 1 = MeanAggregator
+  int32_t *log_src = nullptr, *log_dst = nullptr;
+  int64_t *log_t = nullptr;
+  float *log_raw = nullptr;
+  int64_t log_cap = 0, log_used = 0;
+  int64_t *bstart[2] = {nullptr, nullptr};
+  int32_t *blen[2] = {nullptr, nullptr};
+  float *S = nullptr;  // [cap, 2*TD] per row: mean of sin(arg) | mean of sin(arg) * dt (backward)
   ~tgm_tgn() {
     if (device >= 0) {
       DeviceGuard g(device);
+      cudaFree(log_src), cudaFree(log_dst), cudaFree(log_t), cudaFree(log_raw), cudaFree(S);
+      for (int r = 0; r < 2; ++r) cudaFree(bstart[r]), cudaFree(blen[r]);
       cudaFree(memory), cudaFree(last_update);
       for (auto &s : st) cudaFree(s.other), cudaFree(s.t), cudaFree(s.tmax), cudaFree(s.raw);
       for (float *p : {Wih, Whh, bih, bhh, tw, tb, X, H, GI, GH, newmem}) cudaFree(p);
@@ -255,6 +268,116 @@ tgn_store_raw_kernel(const int32_t *__restrict__ winner_of, const float *__restr
   }
 }
 
+// ---- MeanAggregator (tgn.py:59-63) ------------------------------------------------------------------
+// One warp per workspace row.  The node's messages are the events of its last batch as source
+// (role 0) and as destination (role 1) in which it is the key endpoint; the GRU input is the mean
+// of [mem[v] | mem[other] | raw | Time2Vec(t - last_update[v])] over them (zeros without any),
+// accumulated in list order (source store first) and divided by the count, as scatter(mean) does.
+// Lanes own columns, so the read-modify-write of the X row needs no synchronisation.
+// S (nullable): per row the means of sin(arg) and sin(arg) * dt, all the backward needs of the
+// individual messages (d/dw cos(w dt + b) = -sin(.) dt, d/db = -sin(.)).
+__global__ void __launch_bounds__(256)
+tgn_message_mean_kernel(const float *__restrict__ memory, const int64_t *__restrict__ last_update,
+                        const int32_t *__restrict__ log_src, const int32_t *__restrict__ log_dst,
+                        const int64_t *__restrict__ log_t, const float *__restrict__ log_raw,
+                        const int64_t *__restrict__ bstart_s, const int32_t *__restrict__ blen_s,
+                        const int64_t *__restrict__ bstart_d, const int32_t *__restrict__ blen_d,
+                        const float *__restrict__ tw, const float *__restrict__ tb, int32_t N, int M,
+                        int D, int TD, const int32_t *__restrict__ rows, int64_t n,
+                        float *__restrict__ X, float *__restrict__ H, int64_t *__restrict__ newlu,
+                        float *__restrict__ S) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int in = 2 * M + D + TD;
+  for (int64_t r = int64_t(blockIdx.x) * wpb + (threadIdx.x >> 5); r < n;
+       r += int64_t(gridDim.x) * wpb) {
+    const int32_t v = rows[r];
+    float *x = X + r * in, *h = H + r * M;
+    float *s = S ? S + r * 2 * TD : nullptr;
+    for (int c = lane; c < in; c += 32) x[c] = 0.f;
+    if (s) for (int c = lane; c < 2 * TD; c += 32) s[c] = 0.f;
+    if (v < 0 || v >= N) {  // not a node: inert row
+      for (int c = lane; c < M; c += 32) h[c] = 0.f;
+      if (lane == 0) newlu[r] = 0;
+      continue;
+    }
+    const float *mv = memory + int64_t(v) * M;
+    for (int c = lane; c < M; c += 32) h[c] = mv[c];
+    const int64_t lu_v = last_update[v];
+    int count = 0;
+    int64_t tmax = 0;
+    for (int role = 0; role < 2; ++role) {
+      const int64_t st = role ? bstart_d[v] : bstart_s[v];
+      if (st < 0) continue;
+      const int len = role ? blen_d[v] : blen_s[v];
+      const int32_t *key = role ? log_dst : log_src, *oth = role ? log_src : log_dst;
+      for (int base = 0; base < len; base += 32) {
+        const int p = base + lane;
+        unsigned m = __ballot_sync(0xffffffffu, p < len && key[st + p] == v);
+        while (m) {
+          const int64_t idx = st + base + (__ffs(m) - 1);
+          m &= m - 1;
+          const int32_t other = oth[idx];
+          const int64_t te = log_t[idx];
+          const float dt = float(te - lu_v);  // t_rel.to(float32) (:239-240)
+          tmax = count == 0 ? te : (te > tmax ? te : tmax);
+          ++count;
+          const float *mo = memory + int64_t(other) * M;
+          for (int c = lane; c < M; c += 32) {
+            x[c] += mv[c];
+            x[M + c] += mo[c];
+          }
+          for (int c = lane; c < D; c += 32) x[2 * M + c] += log_raw[idx * D + c];
+          for (int c = lane; c < TD; c += 32) {
+            const float arg = __fmaf_rn(dt, __ldg(tw + c), __ldg(tb + c));
+            x[2 * M + D + c] += cosf(arg);
+            if (s) {
+              const float sn = sinf(arg);
+              s[c] += sn;
+              s[TD + c] += sn * dt;
+            }
+          }
+        }
+      }
+    }
+    if (count > 0) {
+      const float cnt = float(count);
+      for (int c = lane; c < in; c += 32) x[c] = x[c] / cnt;
+      if (s) for (int c = lane; c < 2 * TD; c += 32) s[c] = s[c] / cnt;
+    }
+    if (lane == 0) newlu[r] = count > 0 ? tmax : 0;  // scatter(max) leaves nodes without messages at 0
+  }
+}
+
+// every endpoint of the batch now points at it: duplicates write identical values
+__global__ void tgn_log_mark_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                                    int64_t Eb, int32_t N, int64_t off,
+                                    int64_t *__restrict__ bstart_s, int32_t *__restrict__ blen_s,
+                                    int64_t *__restrict__ bstart_d, int32_t *__restrict__ blen_d) {
+  for (int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; p < Eb;
+       p += int64_t(gridDim.x) * blockDim.x) {
+    const int32_t u = src[p], w = dst[p];
+    if (u >= 0 && u < N) bstart_s[u] = off, blen_s[u] = int32_t(Eb);
+    if (w >= 0 && w < N) bstart_d[w] = off, blen_d[w] = int32_t(Eb);
+  }
+}
+
+// Time2Vec gradients from the per-row sums of the mean kernel:
+//   gw[c] -= sum_r S[r, TD + c] * d_enc[r, c];   gb[c] -= sum_r S[r, c] * d_enc[r, c]
+__global__ void __launch_bounds__(128)
+t2v_grad_sums_kernel(const float *__restrict__ S, const float *__restrict__ d_enc, int64_t n, int TD,
+                     float *__restrict__ gw, float *__restrict__ gb) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= TD) return;
+  float aw = 0.f, ab = 0.f;
+  for (int64_t r = blockIdx.y; r < n; r += gridDim.y) {
+    const float g = d_enc[r * TD + c];
+    aw = __fmaf_rn(-S[r * 2 * TD + TD + c], g, aw);
+    ab = __fmaf_rn(-S[r * 2 * TD + c], g, ab);
+  }
+  atomicAdd(gw + c, aw);
+  atomicAdd(gb + c, ab);
+}
+
 int dev_copy2(float **dst, const float *src, size_t n) {
   TGM_CUDA(cudaMalloc(dst, (n ? n : 1) * sizeof(float)));
   if (n) TGM_CUDA(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyDefault));
@@ -264,13 +387,14 @@ int dev_copy2(float **dst, const float *src, size_t n) {
 int ensure_rows(tgm_tgn *h, int64_t n, cudaStream_t st) {
   if (n <= h->cap) return TGM_OK;
   TGM_CUDA(cudaStreamSynchronize(st));
-  for (float **p : {&h->X, &h->H, &h->GI, &h->GH, &h->newmem}) {
+  for (float **p : {&h->X, &h->H, &h->GI, &h->GH, &h->newmem, &h->S}) {
     cudaFree(*p);
     *p = nullptr;
   }
   cudaFree(h->rows), cudaFree(h->newlu);
   h->rows = nullptr, h->newlu = nullptr, h->cap = 0;
   const size_t cap = size_t(n + n / 4 + 64);
+  if (h->aggr == 1) TGM_CUDA(cudaMalloc(&h->S, cap * 2 * h->TD * 4));
   TGM_CUDA(cudaMalloc(&h->rows, cap * 4));
   TGM_CUDA(cudaMalloc(&h->newlu, cap * 8));
   TGM_CUDA(cudaMalloc(&h->X, cap * h->in * 4));
@@ -285,10 +409,17 @@ int ensure_rows(tgm_tgn *h, int64_t n, cudaStream_t st) {
 // _get_updated_memory for the node ids in h->rows[0..n): results in h->newmem / h->newlu
 int compute_rows(tgm_tgn *h, int64_t n, cudaStream_t st) {
   const int M = h->M, in = h->in;
-  tgn_message_kernel<<<grid_for(n, 8, 8), 256, 0, st>>>(
-      h->memory, h->last_update, h->st[0].other, h->st[0].t, h->st[0].tmax, h->st[0].raw,
-      h->st[1].other, h->st[1].t, h->st[1].tmax, h->st[1].raw, h->tw, h->tb, h->N, M, h->D, h->TD,
-      h->rows, n, h->X, h->H, h->newlu);
+  if (h->aggr == 1) {
+    tgn_message_mean_kernel<<<grid_for(n, 8, 8), 256, 0, st>>>(
+        h->memory, h->last_update, h->log_src, h->log_dst, h->log_t, h->log_raw, h->bstart[0],
+        h->blen[0], h->bstart[1], h->blen[1], h->tw, h->tb, h->N, M, h->D, h->TD, h->rows, n, h->X,
+        h->H, h->newlu, h->S);
+  } else {
+    tgn_message_kernel<<<grid_for(n, 8, 8), 256, 0, st>>>(
+        h->memory, h->last_update, h->st[0].other, h->st[0].t, h->st[0].tmax, h->st[0].raw,
+        h->st[1].other, h->st[1].t, h->st[1].tmax, h->st[1].raw, h->tw, h->tb, h->N, M, h->D, h->TD,
+        h->rows, n, h->X, h->H, h->newlu);
+  }
   TGM_LAUNCH_CHECK();
   TGN_BLAS(cublasSetStream(h->blas, st));
   const float one = 1.f, zero = 0.f;
@@ -312,6 +443,10 @@ int write_rows(tgm_tgn *h, int64_t n, cudaStream_t st) {
 }
 
 int clear_stores(tgm_tgn *h, cudaStream_t st) {
+  if (h->aggr == 1) {  // forget every node's last batch; the log starts over
+    for (int r = 0; r < 2; ++r) TGM_CUDA(cudaMemsetAsync(h->bstart[r], 0xFF, size_t(h->N) * 8, st));
+    h->log_used = 0;
+  }
   for (auto &s : h->st) {
     TGM_CUDA(cudaMemsetAsync(s.other, 0xFF, size_t(h->N) * 4, st));  // -1 = empty
     TGM_CUDA(cudaMemsetAsync(s.t, 0, size_t(h->N) * 8, st));
@@ -320,8 +455,12 @@ int clear_stores(tgm_tgn *h, cudaStream_t st) {
   return TGM_OK;
 }
 
+int push_log(tgm_tgn *h, const int32_t *src, const int32_t *dst, const int64_t *t,
+             const float *raw, int64_t Eb, cudaStream_t st);
+
 int push_stores(tgm_tgn *h, const int32_t *src, const int32_t *dst, const int64_t *t,
                 const float *raw, int64_t Eb, cudaStream_t st) {
+  if (h->aggr == 1) return push_log(h, src, dst, t, raw, Eb, st);
   // winner_of scratch: reuse the row-id buffer tail (rows has >= 2*Eb entries here)
   int32_t *winner = h->rows;
   const int grid = int((Eb + kStoreThreads - 1) / kStoreThreads);
@@ -336,6 +475,46 @@ int push_stores(tgm_tgn *h, const int32_t *src, const int32_t *dst, const int64_
       TGM_LAUNCH_CHECK();
     }
   }
+  return TGM_OK;
+}
+
+// MeanAggregator: append the batch to the log (grown by doubling: the one synchronising path) and
+// point its endpoints at it.
+int push_log(tgm_tgn *h, const int32_t *src, const int32_t *dst, const int64_t *t,
+             const float *raw, int64_t Eb, cudaStream_t st) {
+  const size_t D = size_t(h->D);
+  if (h->log_used + Eb > h->log_cap) {
+    TGM_CUDA(cudaStreamSynchronize(st));
+    int64_t cap = h->log_cap > 0 ? h->log_cap : (int64_t(1) << 16);
+    while (cap < h->log_used + Eb) cap *= 2;
+    int32_t *ns = nullptr, *nd = nullptr;
+    int64_t *nt = nullptr;
+    float *nr = nullptr;
+    TGM_CUDA(cudaMalloc(&ns, size_t(cap) * 4));
+    TGM_CUDA(cudaMalloc(&nd, size_t(cap) * 4));
+    TGM_CUDA(cudaMalloc(&nt, size_t(cap) * 8));
+    TGM_CUDA(cudaMalloc(&nr, (size_t(cap) * D ? size_t(cap) * D : 1) * 4));
+    const size_t used = size_t(h->log_used);
+    if (used) {
+      TGM_CUDA(cudaMemcpy(ns, h->log_src, used * 4, cudaMemcpyDeviceToDevice));
+      TGM_CUDA(cudaMemcpy(nd, h->log_dst, used * 4, cudaMemcpyDeviceToDevice));
+      TGM_CUDA(cudaMemcpy(nt, h->log_t, used * 8, cudaMemcpyDeviceToDevice));
+      if (D) TGM_CUDA(cudaMemcpy(nr, h->log_raw, used * D * 4, cudaMemcpyDeviceToDevice));
+    }
+    cudaFree(h->log_src), cudaFree(h->log_dst), cudaFree(h->log_t), cudaFree(h->log_raw);
+    h->log_src = ns, h->log_dst = nd, h->log_t = nt, h->log_raw = nr, h->log_cap = cap;
+  }
+  const int64_t off = h->log_used;
+  const size_t n = size_t(Eb);
+  TGM_CUDA(cudaMemcpyAsync(h->log_src + off, src, n * 4, cudaMemcpyDeviceToDevice, st));
+  TGM_CUDA(cudaMemcpyAsync(h->log_dst + off, dst, n * 4, cudaMemcpyDeviceToDevice, st));
+  TGM_CUDA(cudaMemcpyAsync(h->log_t + off, t, n * 8, cudaMemcpyDeviceToDevice, st));
+  if (D) TGM_CUDA(cudaMemcpyAsync(h->log_raw + size_t(off) * D, raw, n * D * 4,
+                                  cudaMemcpyDeviceToDevice, st));
+  tgn_log_mark_kernel<<<grid_for(Eb, 256, 8), 256, 0, st>>>(src, dst, Eb, h->N, off, h->bstart[0],
+                                                            h->blen[0], h->bstart[1], h->blen[1]);
+  TGM_LAUNCH_CHECK();
+  h->log_used += Eb;
   return TGM_OK;
 }
 
@@ -587,6 +766,10 @@ extern "C" int tgm_tgn_forward_saved(tgm_tgn *h, const int64_t *n_id, int64_t n,
   TGM_CUDA(cudaMemcpyAsync(out_last_update, h->newlu, rows * 8, cudaMemcpyDeviceToDevice, st));
   TGM_CUDA(cudaMemcpyAsync(saved_x, h->X, rows * h->in * 4, cudaMemcpyDeviceToDevice, st));
   TGM_CUDA(cudaMemcpyAsync(saved_h, h->H, rows * h->M * 4, cudaMemcpyDeviceToDevice, st));
+  if (h->aggr == 1) {  // MeanAggregator: the per-row sin sums written by the message kernel
+    TGM_CUDA(cudaMemcpyAsync(saved_aux, h->S, rows * 2 * h->TD * 4, cudaMemcpyDeviceToDevice, st));
+    return TGM_OK;
+  }
   tgn_aux_kernel<<<grid_for(n, 256, 8), 256, 0, st>>>(h->last_update, h->st[0].other, h->st[0].t,
                                                       h->st[1].other, h->st[1].t, h->N, h->rows, n,
                                                       saved_aux);
@@ -631,8 +814,49 @@ extern "C" int tgm_tgn_backward(tgm_tgn *h, const float *saved_x, const float *s
   // d(time encoding)[n,TD] = dGI[n,3M] W_ih[:, 2M+D:]   (into the X workspace), then Time2Vec
   TGN_BLAS(cublasSgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, TD, int(n), M3, &one,
                        h->Wih + (2 * M + h->D), in, h->GI, M3, &zero, h->X, TD));
-  t2v_grad_kernel<<<colsum_grid(n, TD), 128, 0, st>>>(saved_aux, saved_aux + 1, 2, h->X, TD, n, TD,
-                                                      h->tw, h->tb, g_t2v_w, g_t2v_b);
+  if (h->aggr == 1)
+    t2v_grad_sums_kernel<<<colsum_grid(n, TD), 128, 0, st>>>(saved_aux, h->X, n, TD, g_t2v_w, g_t2v_b);
+  else
+    t2v_grad_kernel<<<colsum_grid(n, TD), 128, 0, st>>>(saved_aux, saved_aux + 1, 2, h->X, TD, n, TD,
+                                                        h->tw, h->tb, g_t2v_w, g_t2v_b);
   TGM_LAUNCH_CHECK();
   return TGM_OK;
+}
+
+extern "C" int tgm_tgn_set_aggregator(tgm_tgn *h, int kind, int64_t log_capacity, tgm_stream stream) {
+  TGM_REQUIRE(h != nullptr, "tgm_tgn_set_aggregator: handle is NULL");
+  TGM_REQUIRE(kind == TGM_TGN_AGGR_LAST || kind == TGM_TGN_AGGR_MEAN,
+              "tgm_tgn_set_aggregator: kind must be TGM_TGN_AGGR_LAST or TGM_TGN_AGGR_MEAN");
+  TGM_REQUIRE(log_capacity >= 0, "tgm_tgn_set_aggregator: log_capacity must be >= 0");
+  DeviceGuard g(h->device);
+  cudaStream_t st = as_stream(stream);
+  TGM_CUDA(cudaStreamSynchronize(st));
+  if (kind == TGM_TGN_AGGR_MEAN && h->bstart[0] == nullptr) {
+    for (int r = 0; r < 2; ++r) {
+      TGM_CUDA(cudaMalloc(&h->bstart[r], size_t(h->N) * 8));
+      TGM_CUDA(cudaMalloc(&h->blen[r], size_t(h->N) * 4));
+      TGM_CUDA(cudaMemset(h->blen[r], 0, size_t(h->N) * 4));
+    }
+  }
+  if (kind == TGM_TGN_AGGR_MEAN && log_capacity > h->log_cap) {
+    cudaFree(h->log_src), cudaFree(h->log_dst), cudaFree(h->log_t), cudaFree(h->log_raw);
+    h->log_src = h->log_dst = nullptr, h->log_t = nullptr, h->log_raw = nullptr, h->log_cap = 0;
+    const size_t cap = size_t(log_capacity), D = size_t(h->D);
+    TGM_CUDA(cudaMalloc(&h->log_src, cap * 4));
+    TGM_CUDA(cudaMalloc(&h->log_dst, cap * 4));
+    TGM_CUDA(cudaMalloc(&h->log_t, cap * 8));
+    TGM_CUDA(cudaMalloc(&h->log_raw, (cap * D ? cap * D : 1) * 4));
+    h->log_cap = log_capacity;
+  }
+  // the row workspaces are re-created on the next call (the mean mode adds one)
+  for (float **p : {&h->X, &h->H, &h->GI, &h->GH, &h->newmem, &h->S}) cudaFree(*p), *p = nullptr;
+  cudaFree(h->rows), cudaFree(h->newlu);
+  h->rows = nullptr, h->newlu = nullptr, h->cap = 0;
+  h->aggr = kind;
+  return tgm_tgn_reset(h, stream);  // memory, last_update and the message stores start empty
+}
+
+extern "C" int tgm_tgn_saved_aux_width(const tgm_tgn *h) {
+  if (h == nullptr) return fail(TGM_ERR_INVALID, "tgm_tgn_saved_aux_width: handle is NULL");
+  return h->aggr == 1 ? 2 * h->TD : 2;
 }

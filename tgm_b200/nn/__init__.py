@@ -5,9 +5,9 @@ dropout 0 (`tgm_attn_backward`, `tgm_dyg_backward`, `tgm_tgn_backward`, `tgm_gae
 from .attention import MergeLayer, TemporalAttention, Time2Vec, masked_mean
 from .dygformer import DyGFormer
 from .tgat import TGAT
-from .tgn import (GraphAttentionEmbedding, IdentityMessage, LastAggregator, TGNMemory,
-                  TransformerConv)
+from .tgn import (GraphAttentionEmbedding, IdentityMessage, LastAggregator, MeanAggregator,
+                  TGNMemory, TransformerConv)
 
 __all__ = ['TemporalAttention', 'Time2Vec', 'MergeLayer', 'TGAT', 'DyGFormer', 'masked_mean',
-           'TGNMemory', 'IdentityMessage', 'LastAggregator', 'GraphAttentionEmbedding',
+           'TGNMemory', 'IdentityMessage', 'LastAggregator', 'MeanAggregator', 'GraphAttentionEmbedding',
            'TransformerConv']

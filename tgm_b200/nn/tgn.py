@@ -42,6 +42,11 @@ class LastAggregator(nn.Module):
     """Marker module: the device state machine implements exactly this aggregator (tgn.py:43-56)."""
 
 
+class MeanAggregator(nn.Module):
+    """Marker module for scatter(mean) over a node's messages (tgn.py:59-63): selects
+    TGM_TGN_AGGR_MEAN (an append-only device log of the batches since the last reset/flush)."""
+
+
 class _TGNMemoryFn(torch.autograd.Function):
     """memory(n_id) in training mode as one differentiable op.  The reference calls
     loss.backward() after memory.update_state() (examples/linkproppred/tgn.py:111-118), so the
@@ -55,9 +60,13 @@ class _TGNMemoryFn(torch.autograd.Function):
         in_dim = module.raw_msg_dim + 2 * module.memory_dim + module.time_dim
         f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
         mem, lu = f(n, module.memory_dim), torch.empty((n,), dtype=torch.int64, device=dev)
-        saved = (f(n, in_dim), f(n, module.memory_dim), f(n, 2))
+        handle = module._handle()
+        aux_width = _cabi.lib.tgm_tgn_saved_aux_width(handle)  # 2 (last) | 2 * time_dim (mean)
+        if aux_width <= 0:
+            _cabi.check(aux_width)
+        saved = (f(n, in_dim), f(n, module.memory_dim), f(n, aux_width))
         _cabi.check(_cabi.lib.tgm_tgn_forward_saved(
-            module._handle(), n_id.data_ptr(), n, mem.data_ptr(), lu.data_ptr(),
+            handle, n_id.data_ptr(), n, mem.data_ptr(), lu.data_ptr(),
             *[t.data_ptr() for t in saved], _cabi.current_stream(dev)))
         ctx.module, ctx.saved_rows = module, saved
         ctx.mark_non_differentiable(lu)
@@ -86,9 +95,9 @@ class TGNMemory(nn.Module):
         message_module = message_module or IdentityMessage(raw_msg_dim, memory_dim, time_dim)
         aggregator_module = aggregator_module or LastAggregator()
         if not isinstance(message_module, IdentityMessage) or \
-                not isinstance(aggregator_module, LastAggregator):
-            raise NotImplementedError('the B200 TGN memory implements IdentityMessage + '
-                                      'LastAggregator (examples/linkproppred/tgn.py)')
+                not isinstance(aggregator_module, (LastAggregator, MeanAggregator)):
+            raise NotImplementedError('the B200 TGN memory implements IdentityMessage with the '
+                                      'LastAggregator or the MeanAggregator (tgn.py:43-74)')
         self.num_nodes, self.raw_msg_dim = num_nodes, raw_msg_dim
         self.memory_dim, self.time_dim = memory_dim, time_dim
         self.msg_s_module, self.msg_d_module = message_module, message_module
@@ -129,6 +138,9 @@ class TGNMemory(nn.Module):
                 self.time_dim, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(),
                 t[4].reshape(-1).data_ptr(), t[5].data_ptr(),
                 _device_index(dev)))
+            if isinstance(self.aggr_module, MeanAggregator):
+                _cabi.check(_cabi.lib.tgm_tgn_set_aggregator(self._native.h, 1, 0,
+                                                             _cabi.current_stream(dev)))
             self._native.version = ver
             self._native_dev = dev
             pending = self.__dict__.pop('_pending_state', None)  # from load_state_dict
