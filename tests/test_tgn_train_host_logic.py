@@ -136,3 +136,7 @@ def test_unknown_aggregator_is_refused():
     from tgm_b200.nn import TGNMemory
     with pytest.raises(NotImplementedError):
         TGNMemory(10, 3, 4, 5, aggregator_module=torch.nn.Identity())
+
+
+def test_mean_aggregator_long_run_and_flush(fake_mean):
+    gpu_mean_tests.test_tgn_mean_event_log_grows_and_restarts_after_a_flush()
