@@ -41,7 +41,8 @@ from tgm_b200 import (DGData, DGDataLoader, DGraph, HookManager,  # noqa: E402
                       RandomNegativeEdgeSamplerHook, RecencyCSR, RecencyNeighborHook)
 from tgm_b200.core.storage import DeviceCOOStorage  # noqa: E402
 from tgm_b200.nn import TGAT, DyGFormer  # noqa: E402
-from tgm_b200.parallel import max_over_ranks, shard_batches, sum_over_ranks  # noqa: E402
+from tgm_b200.parallel import (average_gradients, max_over_ranks, shard_batches,  # noqa: E402
+                               sum_over_ranks)
 
 
 def config3(a, dev):
@@ -365,12 +366,7 @@ def config5(a, dev, rank, world):
                 loss = torch.nn.functional.binary_cross_entropy_with_logits(logit, torch.ones_like(logit))
                 loss.backward()
                 if world > 1:  # data-parallel over the time shards: average the gradients (NCCL)
-                    grads = [q.grad for q in train_params]
-                    flat = torch.cat([g_.reshape(-1) for g_ in grads])
-                    dist.all_reduce(flat)
-                    flat /= world
-                    for g_, v in zip(grads, flat.split([g_.numel() for g_ in grads])):
-                        g_.copy_(v.view_as(g_))
+                    average_gradients(train_params)
                 opt.step()
         return zs
 

@@ -110,3 +110,35 @@ def test_merge_node_memory_world_size_2_gloo(tmp_path):
             assert z['mem'][i, 0] == 1000.0 * (r + 1) + i and z['lu'][i] == 1000 * (r + 1) + i
         else:
             assert torch.equal(z['mem'][i], z['base_mem'][i]) and z['lu'][i] == z['base_lu'][i]
+
+
+def _grad_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    from tgm_b200.parallel import average_gradients
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        lin = torch.nn.Linear(5, 3)
+        frozen = torch.nn.Parameter(torch.ones(2), requires_grad=False)
+        unused = torch.nn.Parameter(torch.ones(4))  # no gradient on rank 1
+        x = torch.full((2, 5), float(rank + 1))
+        loss = lin(x).sum() + (unused.sum() * 3 if rank == 0 else 0)
+        loss.backward()
+        average_gradients([lin.weight, lin.bias, frozen, unused])
+        torch.save({'w': lin.weight.grad, 'b': lin.bias.grad, 'u': unused.grad, 'f': frozen.grad},
+                   os.path.join(out_dir, f'grads{rank}.pt'))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_average_gradients_world_size_2_gloo(tmp_path):
+    """Sharded training: every rank ends with the mean of the per-rank gradients, including a
+    parameter that received no gradient on one rank; frozen parameters are left alone."""
+    world = 2
+    mp.spawn(_grad_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g0, g1 = (torch.load(tmp_path / f'grads{r}.pt') for r in range(world))
+    for k in ('w', 'b', 'u'):
+        assert torch.equal(g0[k], g1[k]), k
+    # d/dW sum(W x + b) = sum over the 2 rows of x: 2*(rank+1) per entry -> mean over ranks = 3
+    assert torch.allclose(g0['w'], torch.full((3, 5), 3.0)) and torch.allclose(g0['b'], torch.full((3,), 2.0))
+    assert torch.allclose(g0['u'], torch.full((4,), 1.5)) and g0['f'] is None

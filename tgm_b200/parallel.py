@@ -122,3 +122,25 @@ def merge_node_memory(memory: torch.Tensor, last_update: torch.Tensor,
     dist.all_reduce(lu, op=dist.ReduceOp.MAX)
     memory.copy_(contrib)
     last_update.copy_(lu)
+
+
+def average_gradients(params) -> None:
+    """Data-parallel training over time shards: average `.grad` of the given parameters across
+    ranks with ONE all-reduce over a flat buffer (a training step's gradients are a few MB: one
+    launch-latency-sized message, NVLS-reducible on NVSwitch).  Parameters without a gradient on
+    this rank contribute zeros; afterwards every rank holds the same gradients.  No-op outside
+    torch.distributed.  Works on NCCL and on gloo (CPU tests)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    params = [p for p in params if p.requires_grad]
+    if not params:
+        return
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1)
+                      for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat /= dist.get_world_size()
+    for p, v in zip(params, flat.split([p.numel() for p in params])):
+        if p.grad is None:
+            p.grad = v.view_as(p).clone()
+        else:
+            p.grad.copy_(v.view_as(p))
