@@ -28,7 +28,8 @@ from tgm_b200 import RecencyCSR  # noqa: E402
 from tgm_b200.core.storage import DeviceCOOStorage  # noqa: E402
 from tgm_b200.hooks.dedup import _BatchIdSet  # noqa: E402
 from tgm_b200.nn import GraphAttentionEmbedding, TGNMemory  # noqa: E402
-from tgm_b200.parallel import max_over_ranks, merge_node_memory, shard_batches, sum_over_ranks  # noqa: E402
+from tgm_b200.parallel import (average_gradients, max_over_ranks, merge_node_memory,  # noqa: E402
+                               shard_batches, sum_over_ranks)
 
 
 def main():
@@ -41,6 +42,10 @@ def main():
     ap.add_argument('--batches', type=int, default=500, help='loader batches per rank')
     ap.add_argument('--no-embedding', dest='embedding', action='store_false',
                     help='memory state machine only (the first measurement of the round)')
+    ap.add_argument('--train', action='store_true',
+                    help='training step per batch: link decoder + BCE loss (positives vs the batch\'s '
+                         'rolled destinations), tgm_gae_backward + tgm_tgn_backward, gradient '
+                         'all-reduce across the time shards, Adam')
     a = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -62,10 +67,49 @@ def main():
     hi = min(shard.edge_hi, lo + a.batches * bs)
     torch.manual_seed(0)
     mem = TGNMemory(N, D, 100, 100).to(dev)
-    enc = GraphAttentionEmbedding(100, 100, D, mem.time_enc).to(dev).eval()
+    enc = GraphAttentionEmbedding(100, 100, D, mem.time_enc)
+    enc.conv.dropout = 0.0  # the B200 path trains with dropout 0
+    enc = enc.to(dev).train(a.train)
     mem.train()
     mem.reset_state()
     touched = torch.zeros(N, dtype=torch.bool, device=dev)
+    decoder = torch.nn.Sequential(torch.nn.Linear(200, 100), torch.nn.ReLU(),
+                                  torch.nn.Linear(100, 1)).to(dev)  # the example's LinkPredictor
+    params = list({id(q): q for m_ in (mem, enc, decoder) for q in m_.parameters()}.values())
+    opt = torch.optim.Adam(params, lr=1e-4)
+    bce = torch.nn.functional.binary_cross_entropy_with_logits
+    if a.train and not a.embedding:
+        raise SystemExit('--train needs the embedding (drop --no-embedding)')
+
+    def train_shard():
+        """examples/linkproppred/tgn.py:70-121 per batch on this rank's shard; the gradients are
+        averaged over the shards (data-parallel in time) before every Adam step."""
+        hop = csr.sample_window(lo, hi, [k])[0]
+        loss = None
+        for b_lo in range(lo, hi, bs):
+            b_hi = min(b_lo + bs, hi)
+            s, d = src[b_lo:b_hi], dst[b_lo:b_hi]
+            r0, r1 = 2 * (b_lo - lo), 2 * (b_hi - lo)
+            nbr = hop.nbr_nids[r0:r1].reshape(-1)
+            ids = _BatchIdSet(N, dev)
+            uniq = ids.unique([(s, False), (d, False), (nbr, True)])
+            keep = nbr != -1
+            seeds = torch.cat([s, d]).repeat_interleave(k)
+            ei = torch.stack([ids.local(seeds[keep]), ids.local(nbr[keep])]).long()
+            opt.zero_grad(set_to_none=True)
+            zz, lu = mem(uniq)
+            z = enc(zz, lu, ei, hop.nbr_edge_time[r0:r1].reshape(-1)[keep],
+                    hop.nbr_edge_x[r0:r1].reshape(-1, D)[keep])
+            i_s, i_d = ids.local(s).long(), ids.local(d).long()
+            pos = decoder(torch.cat([z[i_s], z[i_d]], 1))
+            neg = decoder(torch.cat([z[i_s], z[i_d.roll(1)]], 1))
+            mem.update_state(s, d, t[b_lo:b_hi], x[b_lo:b_hi])  # before backward, as the example
+            loss = bce(pos, torch.ones_like(pos)) + bce(neg, torch.zeros_like(neg))
+            loss.backward()
+            average_gradients(params)
+            opt.step()
+            touched[torch.cat([s, d]).long()] = True
+        return loss
 
     @torch.no_grad()  # the inference step (mem is in train() mode for its update order only)
     def run_shard():
@@ -99,6 +143,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    if a.train:
+        run_shard = train_shard  # noqa: F811  same timing harness, training step per batch
     run_shard()  # warm-up (allocations, cuBLAS heuristics)
     for _ in range(2):  # warm-up of the collective (communicator setup, NVLS buffers)
         merge_node_memory(mem.memory.clone(), mem.last_update.clone(), touched)
@@ -120,7 +166,9 @@ def main():
     if rank == 0:
         row_bytes = N * (100 * 4 + 8 + 4)
         print(json.dumps({
-            'row': 'config 4: TGN ' + ('memory + attention embedding (model step without the decoder)'
+            'row': 'config 4: TGN ' + ('TRAINING step (memory + embedding + decoder, backward, '
+                                       'gradient all-reduce, Adam)' if a.train else
+                                       'memory + attention embedding (model step without the decoder)'
                                        if a.embedding else 'memory') +
                    ', time-sharded, memory join at the shard boundary',
             'n_gpus': world, 'batches_per_rank': (hi - lo) // bs, 'nodes': N,

@@ -23,3 +23,6 @@ cat gpurun_out/config5_train_eager.json gpurun_out/config5_train_graph.json; tai
 python bench_configs.py --config 3 --train --batches 100 > gpurun_out/config3_train_eager.json 2>> gpurun_out/configs.err
 timeout 300 python bench_configs.py --config 3 --train --cuda-graph --batches 100 > gpurun_out/config3_train_graph.json 2>> gpurun_out/configs.err
 cat gpurun_out/config3_train_eager.json gpurun_out/config3_train_graph.json; tail -5 gpurun_out/configs.err
+# (separate call, gpurun --gpus 4) config 4 time-sharded TGN, inference and training:
+#   python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29533 bench_tgn_shard.py --batches 500
+#   python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29534 bench_tgn_shard.py --batches 300 --train
