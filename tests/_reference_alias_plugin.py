@@ -22,3 +22,29 @@ def _alias(pkg, as_name: str) -> None:
 
 
 _alias(tgm_b200, 'tgm')
+
+
+# Names the reference's test modules import that are OUT OF SCOPE here (splits,
+# TGB loaders/recipes, historical / pre-generated negatives): placeholders that refuse to be used,
+# so that the in-scope tests of those modules can still be collected and run.
+import types  # noqa: E402
+
+import tgm_b200.data as _data  # noqa: E402
+import tgm_b200.hooks as _hooks  # noqa: E402
+
+
+class _OutOfScope:
+    def __init__(self, *a, **k):
+        raise NotImplementedError('out of scope for tgm_b200')
+
+
+for _mod, _names in ((_data, ['TemporalRatioSplit', 'TemporalSplit', 'TGBSplit', 'SplitStrategy']),
+                     (_hooks, ['TGBNegativeEdgeSamplerHook', 'HistoricalNegativeEdgeSamplerHook',
+                               'RecipeRegistry'])):
+    for _n in _names:
+        if not hasattr(_mod, _n):
+            setattr(_mod, _n, type(_n, (_OutOfScope,), {}))
+_split = types.ModuleType('tgm.data.split')
+for _n in ['TemporalRatioSplit', 'TemporalSplit', 'TGBSplit', 'SplitStrategy']:
+    setattr(_split, _n, getattr(_data, _n))
+sys.modules['tgm.data.split'] = _split

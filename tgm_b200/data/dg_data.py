@@ -31,27 +31,48 @@ def _as_tensor(x, name: str) -> Tensor:
     return x
 
 
-def _ids(x, name: str) -> Tensor:
+def _integral(x, name: str) -> Tensor:
     x = _as_tensor(x, name)
     if x.dtype not in _INT_TYPES:
         raise TypeError(f'{name} must have integer dtype but got: {x.dtype}')
-    if x.numel() and (x == PADDED_NODE_ID).any():
-        raise InvalidNodeIDError(
-            f'{name} contains the reserved padded node id {PADDED_NODE_ID}')
-    if x.numel() and (x < 0).any():
-        raise InvalidNodeIDError(f'{name} contains negative node ids')
+    return x
+
+
+def _to_int32(x: Tensor, name: str) -> Tensor:
     if x.dtype == torch.int64:
         warnings.warn(f'Downcasting {name} from torch.int64 to torch.int32', UserWarning)
     return x.to(torch.int32)
 
 
-def _feats(x, name: str, rows: int) -> Tensor:
+def _ids(x, name: str) -> Tensor:
+    """Node ids: integral, not the padded id, inside the int32 range (dg_data.py:148-161,
+    :199-213); negative ids are rejected here as well (they can only corrupt the samplers)."""
+    x = _integral(x, name)
+    if x.numel() and (x == PADDED_NODE_ID).any():
+        raise InvalidNodeIDError(
+            f'{name} contains node ids matching PADDED_NODE_ID: {PADDED_NODE_ID}, which is used '
+            'to mark invalid neighbors. Try remapping all node ids to positive integers.')
+    if x.numel() and (x < 0).any():
+        raise InvalidNodeIDError(f'{name} contains negative node ids')
+    if x.numel() and (x >= _INT32_MAX).any():
+        raise InvalidNodeIDError(f'{name} contains node ids that exceed the int32 limit '
+                                 f'({_INT32_MAX})')
+    return _to_int32(x, name)
+
+
+def _feats(x, name: str, rows: Optional[int], what: str = '') -> Tensor:
     x = _as_tensor(x, name)
-    if x.ndim != 2 or x.shape[0] != rows:
-        raise ValueError(f'{name} must have shape [{rows}, D], got {tuple(x.shape)}')
+    if x.ndim != 2 or (rows is not None and x.shape[0] != rows):
+        raise ValueError(f'{name} must have shape [{rows if rows is not None else "N"}, D]'
+                         f'{what}, got {tuple(x.shape)}')
     if x.dtype == torch.float64:
         warnings.warn(f'Downcasting {name} from torch.float64 to torch.float32', UserWarning)
     return x.to(torch.float32)
+
+
+def _mask(x, name: str) -> Tensor:
+    """Event positions inside the timeline; int32 like upstream (the event count fits)."""
+    return _integral(x, name).to(torch.int32)
 
 
 @dataclass
@@ -74,9 +95,7 @@ class DGData:
     def __post_init__(self) -> None:
         if isinstance(self.time_delta, str):
             self.time_delta = TimeDeltaDG(self.time_delta)
-        t = _as_tensor(self.time, 'timestamps')
-        if t.dtype not in _INT_TYPES:
-            raise TypeError(f'timestamps must have integer dtype but got: {t.dtype}')
+        t = _integral(self.time, 'timestamps')
         if t.numel() == 0:
             raise EmptyGraphError('Cannot construct a graph without events')
         if (t < 0).any():
@@ -85,59 +104,73 @@ class DGData:
             raise ValueError(f'timestamps exceed the int32 limit ({_INT32_MAX})')
         self.time = t.to(torch.int64)
 
-        ei = _as_tensor(self.edge_index, 'edge_index')
+        ei = _integral(self.edge_index, 'edge_index')
         if ei.ndim != 2 or ei.shape[1] != 2:
             raise ValueError(f'edge_index must have shape [num_edges, 2], got {tuple(ei.shape)}')
+        self.edge_index = _ids(ei, 'edge_index')
         E = ei.shape[0]
         if E == 0:
-            raise EmptyGraphError('Cannot construct a graph without edge events')
-        self.edge_index = _ids(ei, 'edge_index')
-        self.edge_mask = _as_tensor(self.edge_mask, 'edge_mask').to(torch.int64)
+            raise EmptyGraphError('TGM does not support graphs without edge events')
+        self.edge_mask = _mask(self.edge_mask, 'edge_mask')
         if self.edge_mask.shape != (E,):
             raise ValueError('edge_mask must have one entry per edge')
         if self.edge_x is not None:
             self.edge_x = _feats(self.edge_x, 'edge_x', E)
-        if self.edge_type is not None:
-            et = _as_tensor(self.edge_type, 'edge_type')
-            if et.shape != (E,):
-                raise ValueError('edge_type must have shape [num_edges]')
-            self.edge_type = et.to(torch.int32)
+
+        def node_events(mask, nids, feats, kind):
+            """(mask, ids, features, count) of the node events / node labels (:186-263)."""
+            mask = _mask(mask, f'{kind}_mask')
+            n = mask.shape[0]
+            if n == 0:
+                raise ValueError(f'{kind}_mask is an empty tensor, please double-check your inputs')
+            nids = _integral(nids, f'{kind}_nids')
+            if nids.ndim != 1 or nids.shape[0] != n:
+                raise ValueError(f'{kind}_nids must have shape [{n}], got {tuple(nids.shape)}')
+            nids = _ids(nids, f'{kind}_nids')
+            if feats is not None:
+                feats = _feats(feats, kind, n)
+            return mask, nids, feats, n
 
         n_nx = n_ny = 0
         if self.node_x_mask is not None:
-            if self.node_x_nids is None:
-                raise ValueError('node_x_nids is required when node events are given')
-            self.node_x_nids = _ids(self.node_x_nids, 'node_x_nids')
-            n_nx = self.node_x_nids.shape[0]
-            self.node_x_mask = self.node_x_mask.to(torch.int64)
-            if self.node_x is not None:
-                self.node_x = _feats(self.node_x, 'node_x', n_nx)
+            self.node_x_mask, self.node_x_nids, self.node_x, n_nx = node_events(
+                self.node_x_mask, self.node_x_nids, self.node_x, 'node_x')
         if self.node_y_mask is not None:
-            if self.node_y_nids is None:
-                raise ValueError('node_y_nids is required when node labels are given')
-            self.node_y_nids = _ids(self.node_y_nids, 'node_y_nids')
-            n_ny = self.node_y_nids.shape[0]
-            self.node_y_mask = self.node_y_mask.to(torch.int64)
-            if self.node_y is not None:
-                self.node_y = _feats(self.node_y, 'node_y', n_ny)
-
-        if self.time.ndim != 1 or self.time.shape[0] != E + n_nx + n_ny:
-            raise ValueError(
-                'time must have shape [num_edges + num_node_events + num_node_labels], got '
-                f'{E} edges, {n_nx} node events, {n_ny} node labels, shape {tuple(self.time.shape)}')
+            self.node_y_mask, self.node_y_nids, self.node_y, n_ny = node_events(
+                self.node_y_mask, self.node_y_nids, self.node_y, 'node_y')
 
         num_nodes = int(self.edge_index.max()) + 1
         if n_nx:
             num_nodes = max(num_nodes, int(self.node_x_nids.max()) + 1)
         if n_ny and int(self.node_y_nids.max()) >= num_nodes:
-            raise InvalidNodeIDError('node label ids must lie inside the graph id range')
+            raise InvalidNodeIDError(
+                "Dynamic node labels (node_y) reference node IDs outside the graph's node ID "
+                f'range ({num_nodes} nodes)')
         if self.static_node_x is not None:
-            sx = _as_tensor(self.static_node_x, 'static_node_x')
-            if sx.ndim != 2 or sx.shape[0] < num_nodes:
-                raise ValueError(
-                    f'static_node_x must have shape [>= {num_nodes}, D], got {tuple(sx.shape)}')
-            self.static_node_x = sx.to(torch.float32)
+            sx = _feats(self.static_node_x, 'static_node_x', None)
+            if sx.shape[0] < num_nodes:
+                raise ValueError(f'static_node_x has shape {tuple(sx.shape)} but the data requires '
+                                 f'features for at least {num_nodes} nodes')
+            self.static_node_x = sx
+        if self.edge_type is not None:
+            # upstream validates and warns but keeps the dtype (:321-329)
+            et = _integral(self.edge_type, 'edge_type')
+            if et.ndim != 1 or et.shape[0] != E:
+                raise ValueError(f'edge_type must have shape [num_edges], got {E} edges and '
+                                 f'shape {tuple(et.shape)}')
+            _to_int32(et, 'edge_type')
+        if self.node_type is not None:
+            nt = _integral(self.node_type, 'node_type')
+            if nt.ndim != 1 or nt.shape[0] < num_nodes:
+                raise ValueError(f'node_type must have shape [num_nodes], got {num_nodes} nodes '
+                                 f'and shape {tuple(nt.shape)}')
+            _to_int32(nt, 'node_type')
         self._num_nodes = num_nodes
+
+        if self.time.ndim != 1 or self.time.shape[0] != E + n_nx + n_ny:
+            raise ValueError(
+                'time must have shape [num_edges + num_node_events + num_node_labels], got '
+                f'{E} edges, {n_nx} node events, {n_ny} node labels, shape {tuple(self.time.shape)}')
 
         if (self.time[1:] < self.time[:-1]).any():
             self._sort_events()
@@ -149,10 +182,11 @@ class DGData:
         order = torch.argsort(self.time, stable=True)
         rank = torch.empty_like(order)
         rank[order] = torch.arange(order.numel())
+        rank = rank.to(torch.int32)
         self.time = self.time[order]
 
         def reorder(mask, *arrays):
-            new_pos = rank[mask]
+            new_pos = rank[mask.long()]
             perm = torch.argsort(new_pos, stable=True)
             return (new_pos[perm], *[None if a is None else a[perm] for a in arrays])
 
@@ -187,11 +221,11 @@ class DGData:
         nx_mask = ny_mask = None
         if node_x_time is not None:
             nx_mask = torch.arange(E, E + node_x_time.shape[0])
-            parts.append(node_x_time.to(edge_time.dtype))
+            parts.append(_as_tensor(node_x_time, 'node_x_time'))  # cat promotes: floats are refused below
         if node_y_time is not None:
             off = E + (0 if node_x_time is None else node_x_time.shape[0])
             ny_mask = torch.arange(off, off + node_y_time.shape[0])
-            parts.append(node_y_time.to(edge_time.dtype))
+            parts.append(_as_tensor(node_y_time, 'node_y_time'))
         return cls(time_delta=time_delta, time=torch.cat(parts), edge_mask=torch.arange(E),
                    edge_index=edge_index, edge_x=edge_x, node_x_mask=nx_mask,
                    node_x_nids=node_x_nids, node_x=node_x, node_y_mask=ny_mask,
