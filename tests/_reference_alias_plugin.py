@@ -48,3 +48,9 @@ _split = types.ModuleType('tgm.data.split')
 for _n in ['TemporalRatioSplit', 'TemporalSplit', 'TGBSplit', 'SplitStrategy']:
     setattr(_split, _n, getattr(_data, _n))
 sys.modules['tgm.data.split'] = _split
+
+import tgm_b200.core.timedelta as _td  # noqa: E402
+
+for _n in ('TGB_TIME_DELTAS', 'TGB_SEQ_TIME_DELTAS'):  # per-dataset tables of the TGB loaders
+    if not hasattr(_td, _n):
+        setattr(_td, _n, {})
