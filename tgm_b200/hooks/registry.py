@@ -9,8 +9,7 @@ _HOOK_REGISTRY: List[type] = []
 
 def hook(cls: type) -> type:
     """Class decorator registering a hook class."""
-    if cls not in _HOOK_REGISTRY:
-        _HOOK_REGISTRY.append(cls)
+    _HOOK_REGISTRY.append(cls)  # as upstream: registering a class twice lists it twice
     return cls
 
 
