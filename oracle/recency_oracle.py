@@ -257,3 +257,48 @@ def uniform_sample_deterministic(src, dst, t, x, e_lo: int, e_hi: int, seeds, k:
             if D:
                 nx[i, j] = x[e]
     return nid, nt, nx, exact
+
+
+def uniform_sample_reference_rng(src, dst, t, x, e_lo: int, e_hi: int, seeds, k: int,
+                                 directed: bool = False):
+    """get_nbrs (array_backend.py:108-171) INCLUDING the sub-sampling: the unique seed nodes are
+    visited in ascending order (:118, :147) and a node with more than k candidates keeps
+    `random.sample(candidates, k)` -- CPython's GLOBAL generator, so the caller controls the stream
+    with `random.seed` exactly as a user of the reference does; all occurrences of a node share
+    the draw (:166).  Left-aligned, right-padded (-1, 0, 0.0)."""
+    import random
+    seeds = np.asarray(seeds).reshape(-1)
+    D = 0 if x is None else x.shape[1]
+    cand = uniform_candidates(src, dst, e_lo, e_hi, seeds, directed)
+    S = len(seeds)
+    nid = np.full((S, k), PADDED_NODE_ID, np.int32)
+    nt = np.zeros((S, k), np.int64)
+    nx = np.zeros((S, k, D), np.float32)
+    for v in sorted(set(int(u) for u in seeds.tolist())):
+        c = cand[v]
+        if not c:
+            continue
+        if len(c) > k:
+            c = random.sample(c, k)
+        rows = np.flatnonzero(seeds == v)
+        for j, (e, nb) in enumerate(c):
+            nid[rows, j], nt[rows, j] = nb, t[e]
+            if D:
+                nx[rows, j] = x[e]
+    return nid, nt, nx
+
+
+def reference_rng_picks(counts, k: int) -> np.ndarray:
+    """The same draws as candidate ORDINALS: counts[i] = number of candidates of the i-th unique
+    seed node (ascending node order); returns int32 [len(counts), k], -1 = padding.
+    `random.sample` selects by position only, so sampling range(c) consumes the generator exactly
+    like sampling the candidate list."""
+    import random
+    picks = np.full((len(counts), k), -1, np.int32)
+    for i, c in enumerate(counts):
+        c = int(c)
+        if c > k:
+            picks[i] = random.sample(range(c), k)
+        elif c:
+            picks[i, :c] = np.arange(c)
+    return picks

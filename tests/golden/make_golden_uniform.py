@@ -3,7 +3,8 @@
 
 Graphs are the reference's own unit-test graphs (test/unit/test_hooks/test_neighbor_sampler_hook.py)
 plus seeded random streams whose k is >= every node's degree, so no `random.sample` is involved and
-the reference output is deterministic.  Writes tests/golden/uniform_*.npz."""
+the reference output is deterministic (tests/golden/uniform_*.npz), plus streams with k below the
+degrees under a fixed `random.seed` (tests/golden/uniformrng_*.npz)."""
 from __future__ import annotations
 
 import os
@@ -22,7 +23,7 @@ from tgm.data import DGData, DGDataLoader  # noqa: E402
 from tgm.hooks import HookManager, NeighborSamplerHook  # noqa: E402
 
 
-def save(name, src, dst, t, x, bs, num_nbrs, directed):
+def save(name, src, dst, t, x, bs, num_nbrs, directed, rng_seed=None):
     ei = torch.from_numpy(np.stack([src, dst], 1).astype(np.int32))
     data = DGData.from_raw(torch.from_numpy(t.astype(np.int64)), ei,
                            None if x is None else torch.from_numpy(x))
@@ -33,6 +34,9 @@ def save(name, src, dst, t, x, bs, num_nbrs, directed):
                                          seed_times_keys=['edge_time', 'edge_time'],
                                          directed=directed))
     out = {}
+    if rng_seed is not None:  # get_nbrs sub-samples with CPython's global generator (:152-153)
+        import random
+        random.seed(rng_seed)
     with hm.activate('g'):
         for b, batch in enumerate(DGDataLoader(dg, batch_size=bs, hook_manager=hm)):
             for h in range(len(num_nbrs)):
@@ -44,10 +48,12 @@ def save(name, src, dst, t, x, bs, num_nbrs, directed):
                 out[tag + '_nx'] = batch.nbr_edge_x[h].numpy()
     meta = dict(src=src.astype(np.int32), dst=dst.astype(np.int32), t=t.astype(np.int64),
                 bs=np.int64(bs), num_nbrs=np.array(num_nbrs, np.int64),
-                directed=np.int64(directed), has_x=np.int64(x is not None))
+                directed=np.int64(directed), has_x=np.int64(x is not None),
+                rng_seed=np.int64(-1 if rng_seed is None else rng_seed))
     if x is not None:
         meta['x'] = x.astype(np.float32)
-    np.savez_compressed(os.path.join(HERE, f'uniform_{name}.npz'), **meta, **out)
+    prefix = 'uniform_' if rng_seed is None else 'uniformrng_'
+    np.savez_compressed(os.path.join(HERE, f'{prefix}{name}.npz'), **meta, **out)
     print(name, 'ok')
 
 
@@ -71,6 +77,16 @@ def main():
         deg = np.bincount(np.concatenate([src, dst]), minlength=N).max()
         assert deg <= min(nn), (name, deg)  # k >= every degree: no random.sample on any query
         save(name, src, dst, t, x, bs, nn, directed)
+    # sub-sampled queries: k below the degrees, random.seed() fixed before the loader loop, so the
+    # reference's random.sample stream -- one draw per unique seed node with more than k
+    # candidates, in ascending node order, hop after hop, batch after batch -- is reproducible
+    for name, N, E, T, D, bs, nn, directed, seed in [('sub_a', 12, 150, 60, 3, 10, [4], False, 7),
+                                                     ('sub_b', 10, 120, 40, 2, 8, [3, 2], False, 8),
+                                                     ('sub_c', 8, 100, 30, 0, 9, [5], True, 9)]:
+        src, dst = rng.integers(0, N, E), rng.integers(0, N, E)
+        t = np.sort(rng.integers(0, T, E))
+        x = rng.standard_normal((E, D)).astype(f32) if D else None
+        save(name, src, dst, t, x, bs, nn, directed, rng_seed=seed)
 
 
 if __name__ == '__main__':

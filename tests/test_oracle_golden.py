@@ -512,3 +512,53 @@ def test_tgn_mean_aggregator_backward_oracle_matches_reference_autograd(path):
             checked += 1
         mem.update_state(z['src'][lo:hi], z['dst'][lo:hi], z['t'][lo:hi], z['x'][lo:hi])
     assert checked >= 3 and multi > 0  # nodes with several messages were exercised
+
+
+# ---- uniform sampler INCLUDING the reference's random.sample sub-sampling ------------------------------
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'uniformrng_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[11:-4])
+def test_uniform_oracle_reproduces_the_reference_random_sample_stream(path):
+    """k below the degrees: get_nbrs keeps random.sample(candidates, k) per unique seed node
+    (array_backend.py:147-153).  With random.seed fixed as the fixture generator fixed it, the oracle
+    -- and the candidate-ordinal form the device path consumes -- reproduce every draw bit for bit."""
+    import random
+
+    from oracle.recency_oracle import (reference_rng_picks, uniform_candidates,
+                                       uniform_sample_reference_rng)
+    z = np.load(path)
+    src, dst, t = z['src'], z['dst'], z['t']
+    x = z['x'] if int(z['has_x']) else None
+    bs, nn, directed = int(z['bs']), [int(v) for v in z['num_nbrs']], bool(int(z['directed']))
+    subsampled = 0
+    for ordinal_form in (False, True):
+        random.seed(int(z['rng_seed']))
+        for b, lo in enumerate(range(0, len(src), bs)):
+            hi = min(lo + bs, len(src))
+            e_hi = int(np.searchsorted(t, t[lo:hi].min() - 1, 'right'))
+            seeds = np.concatenate([src[lo:hi], dst[lo:hi]])
+            for h, k in enumerate(nn):
+                if h:
+                    seeds = nid.reshape(-1)
+                if not ordinal_form:
+                    nid, nt, nx = uniform_sample_reference_rng(src, dst, t, x, 0, e_hi, seeds, k, directed)
+                else:  # what the device path does: counts -> host draws -> gather by ordinal
+                    cand = uniform_candidates(src, dst, 0, e_hi, seeds, directed)
+                    uniq = sorted(cand)
+                    picks = reference_rng_picks([len(cand[v]) for v in uniq], k)
+                    subsampled += sum(len(cand[v]) > k for v in uniq)
+                    D = 0 if x is None else x.shape[1]
+                    nid = np.full((len(seeds), k), -1, np.int32)
+                    nt = np.zeros((len(seeds), k), np.int64)
+                    nx = np.zeros((len(seeds), k, D), np.float32)
+                    for i, v in enumerate(uniq):
+                        rows = np.flatnonzero(seeds == v)
+                        for j, p in enumerate(picks[i]):
+                            if p >= 0:
+                                e, nb = cand[v][p]
+                                nid[rows, j], nt[rows, j] = nb, t[e]
+                                if D:
+                                    nx[rows, j] = x[e]
+                assert np.array_equal(nid, z[f'b{b}_h{h}_nid']), (ordinal_form, b, h)
+                assert np.array_equal(nt, z[f'b{b}_h{h}_nt'])
+                assert np.array_equal(nx, z[f'b{b}_h{h}_nx'])
+    assert subsampled > 20
