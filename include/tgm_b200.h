@@ -179,6 +179,20 @@ int tgm_csr_export_ring(const tgm_csr *, int64_t e_cut, tgm_recency *ring, tgm_s
 int tgm_csr_sample_uniform(const tgm_csr *, const int32_t *seeds, int64_t S, int64_t e_lo,
                            int64_t e_hi, int32_t k, uint64_t rng_seed, int32_t *out_nid,
                            int64_t *out_t, float *out_x, tgm_stream stream);
+/* Reference-exact sub-sampling.  The reference keeps random.sample(candidates, k) -- CPython's
+ * global generator -- per unique seed node with more than k candidates, visiting the unique nodes
+ * in ascending order (array_backend.py:118, :147-153).  That draw depends only on the candidate
+ * COUNT, so the host can make it with the very same call:
+ *   tgm_csr_candidate_counts: out_counts int64[S] = number of candidates of every seed;
+ *   (host) picks = random.sample(range(count), k) per unique node, in ascending node order;
+ *   tgm_csr_gather_picks: column c of seed s takes candidate ordinal picks[s*k + c]
+ *     (int32, -1 = padding), left to right as the reference writes its sampled list (:155-169).
+ * Same adjacency requirements and output layout as tgm_csr_sample_uniform. */
+int tgm_csr_candidate_counts(const tgm_csr *, const int32_t *seeds, int64_t S, int64_t e_lo,
+                             int64_t e_hi, int64_t *out_counts, tgm_stream stream);
+int tgm_csr_gather_picks(const tgm_csr *, const int32_t *seeds, int64_t S, int64_t e_lo,
+                         int64_t e_hi, int32_t k, const int32_t *picks, int32_t *out_nid,
+                         int64_t *out_t, float *out_x, tgm_stream stream);
 
 /* Host-buffer form of tgm_csr_sample_edges: what a CPU-resident caller binds (the reference
  * keeps its arrays on the CPU and moves every batch property with .to(device),

@@ -26,3 +26,5 @@ cat gpurun_out/config3_train_eager.json gpurun_out/config3_train_graph.json; tai
 # (separate call, gpurun --gpus 4) config 4 time-sharded TGN, inference and training:
 #   python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29533 bench_tgn_shard.py --batches 500
 #   python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29534 bench_tgn_shard.py --batches 300 --train
+# first hardware run of the reference-exact uniform sampling kernels (own process)
+TGM_B200_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_zz_gpu_uniform_exact.py -q > gpurun_out/gpu_uniform_exact.log 2>&1; tail -8 gpurun_out/gpu_uniform_exact.log

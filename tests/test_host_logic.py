@@ -323,3 +323,23 @@ def test_public_signatures_accept_every_reference_argument():
                 assert g[2] == w[2], (dotted, g, w)
         for extra in got[len(want):]:
             assert extra[2] != ['required'] or extra[1].startswith('VAR_'), (dotted, extra)
+
+
+def test_reference_rng_picks_replay_the_reference_draws():
+    """tgm_b200.sampler.reference_rng_picks (host half of NeighborSamplerHook(reference_rng=True))
+    consumes CPython's global generator exactly like get_nbrs' random.sample(candidates, k)
+    (array_backend.py:147-153): same picks as sampling the candidate lists themselves."""
+    import random
+
+    from tgm_b200.sampler import reference_rng_picks
+    rng = np.random.default_rng(3)
+    counts = rng.integers(0, 40, 200).tolist()
+    for k in (1, 5, 21):  # 21 < count crosses CPython's set/pool switch (setsize 21 for k <= 5...)
+        random.seed(99)
+        got = reference_rng_picks(counts, k)
+        random.seed(99)
+        for c, row in zip(counts, got):
+            cand = [('cand', i) for i in range(c)]
+            want = random.sample(cand, k) if c > k else cand
+            assert [p for p in row if p >= 0] == [i for _, i in want]
+            assert len(row) == k and all(p == -1 for p in row[len(want):])

@@ -74,6 +74,10 @@ SIGNATURES = {
     'tgm_csr_export_ring': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     'tgm_csr_sample_uniform': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32,
                                        c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'tgm_csr_candidate_counts': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
+                                         c_void_p]),
+    'tgm_csr_gather_picks': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'tgm_csr_sample_edges_host': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_int, c_void_p]),

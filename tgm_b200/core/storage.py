@@ -76,7 +76,7 @@ class DGStorageBase(ABC):
     def get_static_node_x_dim(self) -> Optional[int]: ...
     @abstractmethod
     def get_nbrs(self, seed_nodes: Tensor, num_nbrs: int, slice: DGSliceTracker,
-                 directed: bool) -> Tuple[Tensor, ...]: ...
+                 directed: bool, reference_rng: bool = False) -> Tuple[Tensor, ...]: ...
 
 
 class DeviceCOOStorage(DGStorageBase):
@@ -381,15 +381,18 @@ class DeviceCOOStorage(DGStorageBase):
         return None if sx is None else int(sx.shape[1])
 
     def get_nbrs(self, seed_nodes: Tensor, num_nbrs: int, slice: DGSliceTracker,
-                 directed: bool) -> Tuple[Tensor, ...]:
+                 directed: bool, reference_rng: bool = False) -> Tuple[Tensor, ...]:
         """Neighbours among all edges of the slice (array_backend.py:108-171), right-padded.
         Served from the (edge, side)-ordered adjacency by `tgm_csr_sample_uniform`: seeds with
         <= `num_nbrs` candidates get exactly the reference's rows; with more, a uniform subset is
-        drawn on the device (the reference uses CPython's `random.sample`, :152-153, which no
-        device path can reproduce bit for bit)."""
+        drawn on the device.  `reference_rng=True` (not part of the reference signature) instead
+        replays the reference's own `random.sample` calls (:152-153) on the host from the
+        candidate counts and gathers those picks on the device: bit-exact under `random.seed`,
+        at the price of one host sync per call."""
         self._require_device()
         from tgm_b200.sampler import full_history_neighbors
-        return full_history_neighbors(self, seed_nodes, num_nbrs, slice, directed)
+        return full_history_neighbors(self, seed_nodes, num_nbrs, slice, directed,
+                                      reference_rng=reference_rng)
 
 
 # registry mirroring tgm/core/_storage/__init__.py:14-28 and backends/__init__.py:3-7

@@ -1192,3 +1192,10 @@ extern "C" int tgm_csr_export_ring(const tgm_csr *c, int64_t e_cut, tgm_recency 
   TGM_LAUNCH_CHECK();
   return TGM_OK;
 }
+
+
+// accessor for other translation units (uniform_exact.cu)
+tgm::CsrView tgm::csr_view(const tgm_csr *c) {
+  return tgm::CsrView{c->device, c->entries, c->rowptr, c->store ? c->store->x : nullptr,
+                      c->N,      c->D,       c->bs,     c->e_start, c->Ew};
+}

@@ -20,3 +20,17 @@ struct tgm_store {
   std::vector<int64_t> t_host;
   ~tgm_store();
 };
+
+// Read-only view of the per-node adjacency handle (defined in csr.cu) for other translation units.
+struct tgm_csr;
+namespace tgm {
+struct CsrView {
+  int device;
+  const Entry *entries;      // grouped by node, per node ordered (batch, time, side, edge)
+  const int64_t *rowptr;     // [N + 1]
+  const float *x;            // the store's feature rows [E, D] (NULL when D == 0)
+  int32_t N, D;
+  int64_t bs, e_start, Ew;
+};
+CsrView csr_view(const tgm_csr *c);
+}  // namespace tgm

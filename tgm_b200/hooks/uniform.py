@@ -29,7 +29,10 @@ class NeighborSamplerHook(StatelessHook, SeedableHook):
 
     def __init__(self, num_nbrs: List[int], seed_nodes_keys: List[str],
                  seed_times_keys: List[str], directed: bool = False,
-                 id: Optional[str] = None) -> None:
+                 id: Optional[str] = None, reference_rng: bool = False) -> None:
+        """`reference_rng=True` (an addition to the reference signature): sub-sample with the
+        reference's own `random.sample` stream -- bit-exact outputs under `random.seed`, one host
+        sync per hop -- instead of the device generator."""
         if not len(num_nbrs):
             raise ValueError('num_nbrs must be non-empty')
         if not all(isinstance(x, int) and x > 0 for x in num_nbrs):
@@ -41,6 +44,7 @@ class NeighborSamplerHook(StatelessHook, SeedableHook):
                 f'seed_times_keys={seed_times_keys}')
         self._num_nbrs = num_nbrs
         self._directed = directed
+        self._reference_rng = bool(reference_rng)
         self._seed_nodes_keys = seed_nodes_keys
         self._seed_times_keys = seed_times_keys
         self._warned_seed_None = False
@@ -70,8 +74,9 @@ class NeighborSamplerHook(StatelessHook, SeedableHook):
                 if hop > 0:
                     seed_nodes = nids[hop - 1].flatten()
                     seed_times = nts[hop - 1].flatten()
+                extra = {'reference_rng': True} if self._reference_rng else {}
                 nid, nt, nx = dg._storage.get_nbrs(seed_nodes, num_nbrs=k, slice=cut,
-                                                   directed=self._directed)
+                                                   directed=self._directed, **extra)
                 seeds_out.append(seed_nodes)
                 times_out.append(seed_times)
                 nids.append(nid)

@@ -168,8 +168,24 @@ class RecencyCSR:
             row += n
 
 
+def reference_rng_picks(counts, k: int):
+    """Candidate ordinals the reference would keep: `counts[i]` candidates for the i-th unique
+    seed node (ascending node order, array_backend.py:118,:147); a node with more than k keeps
+    `random.sample(range(count), k)` -- the same call on CPython's GLOBAL generator as upstream
+    (:152-153: sampling a list selects by position, so the stream of draws is identical) -- the
+    others keep all their candidates in order.  Returns a list of k-long lists, -1 = padding."""
+    import random
+    picks = []
+    for c in counts:
+        if c > k:
+            picks.append(random.sample(range(c), k))
+        else:
+            picks.append(list(range(c)) + [-1] * (k - c))
+    return picks
+
+
 def full_history_neighbors(storage, seed_nodes: Tensor, num_nbrs: int, slice, directed: bool,
-                           rng_seed: Optional[int] = None):
+                           rng_seed: Optional[int] = None, reference_rng: bool = False):
     """DGStorageArrayBackend.get_nbrs (array_backend.py:108-171) on the device: neighbours among
     all edges of `slice`, left-aligned / right-padded.  The (edge, side)-ordered adjacency is
     built once per `directed` flag and cached on the storage."""
@@ -178,7 +194,7 @@ def full_history_neighbors(storage, seed_nodes: Tensor, num_nbrs: int, slice, di
     if key not in cache:
         cache[key] = RecencyCSR(storage, 1, directed=directed, colocate_x=False)
     csr = cache[key]
-    if rng_seed is None:  # a fresh draw per call, reproducible under torch.manual_seed
+    if rng_seed is None and not reference_rng:  # a fresh draw per call, reproducible under torch.manual_seed
         rng_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     lo, hi = storage.edge_range(slice)
     dev = storage.device
@@ -187,6 +203,21 @@ def full_history_neighbors(storage, seed_nodes: Tensor, num_nbrs: int, slice, di
     nid = torch.empty((S, num_nbrs), dtype=torch.int32, device=dev)
     nt = torch.empty((S, num_nbrs), dtype=torch.int64, device=dev)
     nx = torch.empty((S, num_nbrs, D), dtype=torch.float32, device=dev)
+    if reference_rng and S:
+        # bit-exact with the reference under `random.seed`: counts to the host (one sync), the
+        # reference's own random.sample calls there, the gather on the device
+        uniq, inverse = torch.unique(seeds, return_inverse=True)  # ascending, like upstream (:118)
+        counts = torch.empty((uniq.numel(),), dtype=torch.int64, device=dev)
+        _cabi.check(_cabi.lib.tgm_csr_candidate_counts(
+            csr.handle, uniq.data_ptr(), uniq.numel(), lo, hi, counts.data_ptr(),
+            _cabi.current_stream(dev)))
+        picks = torch.tensor(reference_rng_picks(counts.cpu().tolist(), int(num_nbrs)),
+                             dtype=torch.int32).reshape(-1, num_nbrs).to(dev)[inverse].contiguous()
+        _cabi.check(_cabi.lib.tgm_csr_gather_picks(
+            csr.handle, seeds.data_ptr(), S, lo, hi, int(num_nbrs), picks.data_ptr(),
+            nid.data_ptr(), nt.data_ptr(), nx.data_ptr() if D else None,
+            _cabi.current_stream(dev)))
+        return nid, nt, nx
     _cabi.check(_cabi.lib.tgm_csr_sample_uniform(
         csr.handle, seeds.data_ptr(), S, lo, hi, int(num_nbrs), int(rng_seed), nid.data_ptr(),
         nt.data_ptr(), nx.data_ptr() if D else None, _cabi.current_stream(dev)))
