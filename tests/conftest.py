@@ -22,7 +22,7 @@ def pytest_addoption(parser):
 
 @pytest.fixture(autouse=True, scope='session')
 def _default_window_batches(request):
-    n = request.config.getoption('--default-window-batches')
+    n = request.config.getoption('--default-window-batches', default=0)
     if not n:
         yield
         return
