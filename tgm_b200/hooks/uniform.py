@@ -5,6 +5,25 @@ Stateless uniform sampling over the full history before the batch: per hop one
 (uniform.py:122-127), served by `tgm_csr_sample_uniform` instead of a Python loop over every
 edge of the history (array_backend.py:125-137).  Outputs are right-padded, per-seed query times
 are ignored (only the batch-min cut applies) -- both as in the reference.
+
+How the device serves a call.  The store keeps one extra adjacency for this hook, built lazily
+and cached on the storage object: `RecencyCSR(storage, batch_size=1, colocate_x=False)`, i.e. every
+node's incident entries {neighbour, edge, time} in (edge, side) order -- the order in which
+get_nbrs appends candidates while it walks the history (array_backend.py:132-137).  A slice of
+the history [e_lo, e_hi) is then, per seed node, a contiguous run of that node's entries found
+by two binary searches over the edge index; nothing is scanned.  With at most k candidates the
+run is copied out left-aligned (the reference's rows, bit for bit).  With more than k:
+
+* default: `tgm_csr_sample_uniform` draws a uniform k-subset per node with Floyd's algorithm from
+  a counter-based generator keyed by (call seed, node id), so all occurrences of a node in one
+  call share the draw exactly as the reference's `inverse_indices == i` write does (:166);
+* `reference_rng=True`: `tgm_csr_candidate_counts` returns the run lengths of the unique seed
+  nodes, the host makes the reference's own `random.sample` calls in ascending node order
+  (`tgm_b200.sampler.reference_rng_picks`), and `tgm_csr_gather_picks` gathers those candidate
+  ordinals: bit-exact under `random.seed`, one host synchronisation per hop.
+
+Seed validation (missing / None / non-tensor / wrong-rank attributes, negative ids or times)
+raises the reference's exceptions; the bounds checks of all seed keys share one host read.
 """
 from __future__ import annotations
 
