@@ -1,12 +1,6 @@
 """GPU parity of the TGN memory with the MeanAggregator (tgm_tgn_set_aggregator(TGM_TGN_AGGR_MEAN):
 tgn_message_mean_kernel, the append-only event log, the sin-sum form of the Time2Vec gradient).
 
-STATUS: written after round 1's GPU budget was spent.  The float32/float64 oracles are pinned on
-fixtures from the reference (tests/test_oracle_golden.py::test_tgn_mean_aggregator_*), the Python
-face runs on CPU against the oracle-backed stand-in library (tests/test_tgn_train_host_logic.py),
-and the kernels compile for sm_100a, but they have NOT run on hardware yet.  Until they have, these
-tests only run when TGM_B200_RUN_UNVERIFIED=1 (scratch/next_gpu_call.sh sets it): a first run of
-new kernels belongs in a process of its own, not in the suite that certifies the verified paths.
 """
 import glob
 import os
@@ -18,11 +12,7 @@ import torch
 from oracle.tgn_oracle import TGNMemoryOracle, tgn_memory_backward
 from tests._golden import GOLDEN_DIR
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('TGM_B200_RUN_UNVERIFIED') != '1',
-                                 reason='MeanAggregator kernels: compiled and oracle-pinned on CPU, '
-                                        'not yet executed on a GPU (round-1 GPU budget spent); set '
-                                        'TGM_B200_RUN_UNVERIFIED=1 to run them')]
+pytestmark = pytest.mark.gpu
 
 from tgm_b200.nn import IdentityMessage, MeanAggregator, TGNMemory  # noqa: E402
 

@@ -3,10 +3,6 @@ tgm_csr_candidate_counts + the reference's own random.sample calls on the host +
 tgm_csr_gather_picks): with `random.seed` fixed as the fixture generator fixed it, every output of
 every hop of every batch equals the unmodified reference's, sub-sampled rows included.
 
-STATUS: written after round 1's GPU budget was spent.  The oracle (direct and candidate-ordinal
-form) reproduces the fixtures bit for bit on CPU (tests/test_oracle_golden.py), the two kernels
-compile for sm_100a, but they have NOT run on hardware yet: the tests only run with
-TGM_B200_RUN_UNVERIFIED=1 (scratch/next_gpu_call.sh), in a process of their own.
 """
 import glob
 import os
@@ -18,11 +14,7 @@ import torch
 
 from tests._golden import GOLDEN_DIR
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('TGM_B200_RUN_UNVERIFIED') != '1',
-                                 reason='reference-exact uniform sampling: oracle-pinned on CPU, '
-                                        'kernels not yet executed on a GPU; set '
-                                        'TGM_B200_RUN_UNVERIFIED=1 to run them')]
+pytestmark = pytest.mark.gpu
 
 from tgm_b200 import (DGData, DGDataLoader, DGraph, HookManager,  # noqa: E402
                       NeighborSamplerHook)

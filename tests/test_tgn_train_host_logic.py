@@ -103,8 +103,8 @@ def test_state_dict_interchanges_with_the_reference_checkpoint_layout(fake):
         TGNMemory(N, D, M, TD).load_state_dict(bad)
 
 
-# --- MeanAggregator: the same host-side checks for tests/test_zz_gpu_tgn_mean.py ---------------------
-from tests import test_zz_gpu_tgn_mean as gpu_mean_tests  # noqa: E402
+# --- MeanAggregator: the same host-side checks for tests/test_gpu_tgn_mean.py ---------------------
+from tests import test_gpu_tgn_mean as gpu_mean_tests  # noqa: E402
 
 
 @pytest.fixture
