@@ -9,12 +9,20 @@ A *step* is one pass of the hot path over one window of `--window-batches` loade
 each, D-float edge features gathered): one `tgm_csr_sample_edges` launch.  A *sampled edge* is
 one (seed, neighbour-slot) pair returned.
 
-  value  device-resident inputs and outputs, CUDA-event time of exactly K steps, max over ranks
-  e2e    the same work through the host-buffer C-ABI call (`tgm_csr_sample_edges_host`): every
-         step uploads its slab of stream edges from pinned host memory and downloads the full
-         sampled output to pinned host memory
+  value  device-resident inputs and outputs, CUDA-event time of exactly K steps, max over ranks;
+         the timed windows come from the steady state of the stream (every ring full)
+  e2e    the same sampling through the host-buffer C-ABI call `tgm_csr_sample_edges_host_ids`:
+         every step uploads its slab of stream edges (src, dst, t) from pinned host memory, the
+         kernel reads its seeds from that slab, and (nid, t, eid) -- 16 bytes per sampled edge,
+         what a host that owns the feature table lacks -- come back to pinned host memory;
+         `e2e.variants` holds the full-row form (12 + 4D bytes per sampled edge back) and the
+         fused sample + masked-mean form (4D bytes per seed back)
+  full_pass  one pass over the whole stream including the build of the adjacency
+         (`value_incl_build`)
   N>1    the batch stream is time-range sharded, store + adjacency replicated, no data-path
-         collective; weak scaling: every rank runs K steps of its shard
+         collective for sampling; weak scaling: every rank runs K steps of
+         its shard.  `collective` times the one exchange the path has: the TGN node-memory join
+         at shard boundaries (rows each shard touched, all-gathered over NCCL)
 
 Only the cpu_baseline / --impl reference legs touch oracle/ (as the thing being timed there).
 """
@@ -58,10 +66,16 @@ def parse_args():
     p.add_argument('--window-batches', type=int, default=5000)
     p.add_argument('--e2e-window-batches', type=int, default=1000)
     p.add_argument('--e2e-steps', type=int, default=0, help='0 = same as --steps')
-    p.add_argument('--cpu-sample-edges', type=int, default=9_000_000)
+    p.add_argument('--cpu-sample-edges', type=int, default=4_000_000,
+                   help='stream edges the CPU baseline is timed on (after a steady-state warm-up)')
+    p.add_argument('--e2e-full-steps', type=int, default=20)
     p.add_argument('--no-cpu-baseline', action='store_true')
     p.add_argument('--no-e2e', action='store_true')
     p.add_argument('--no-numa-bind', action='store_true')
+    p.add_argument('--no-collective', action='store_true')
+    p.add_argument('--join-edges', type=int, default=100_000,
+                   help='stream edges per shard whose endpoints count as touched in the memory '
+                        'join (500 loader batches of 200, as bench_tgn_shard.py runs between joins)')
     p.add_argument('--loader-batches', type=int, default=20000,
                    help='loader batches iterated for the public-API (DGDataLoader + hook) number; 0 = skip')
     p.add_argument('--no-colocate', action='store_true')
@@ -72,6 +86,14 @@ def parse_args():
     return p.parse_args()
 
 
+def steady_start_edge(a):
+    """First stream edge of the steady state: from here on a node has seen on average >= 2.5 k
+    entries, so practically every ring holds k neighbours and no sampled slot is padding."""
+    e = int(1.25 * a.k * a.nodes)
+    e -= e % a.batch_size
+    return min(e, a.edges // 2 // a.batch_size * a.batch_size)
+
+
 def workload_config(a, world):
     return {
         'workload': f'synthetic CTDG {a.edges // 1_000_000}M edges / {a.nodes // 1000}k nodes, '
@@ -79,6 +101,8 @@ def workload_config(a, world):
                     f'batch_size={a.batch_size}, seeds=[edge_src|edge_dst], undirected',
         'edges': a.edges, 'nodes': a.nodes, 't_max': a.t_max, 'edge_x_dim': a.dim, 'k': a.k,
         'batch_size': a.batch_size, 'window_batches': a.window_batches,
+        'timed_region': f'steady state: windows drawn from stream edges >= {steady_start_edge(a)} '
+                        f'(mean adjacency length >= 2.5 k, every ring full)',
         'sharding': f'time-range x{world}, store+adjacency replicated, no collective',
         'l2': 'every step reads a different window; bytes touched per step >> 126 MB L2',
     }
@@ -171,65 +195,70 @@ def bind_to_gpu_numa_node(index: int):
 
 
 # ---- CPU baseline (the only place oracle/ is executed, as the thing timed) -----------------------
-def numpy_prefix_stream(a, n_edges):
-    import numpy as np
+def numpy_stream(a, e_lo, e_hi):
+    """Edges [e_lo, e_hi) of a stream with the bench workload's statistics, generated on the host
+    (the reference arm runs without touching the GPU)."""
     rng = np.random.default_rng(a.seed)
-    src = rng.integers(0, a.nodes, n_edges).astype(np.int32)
-    dst = rng.integers(0, a.nodes, n_edges).astype(np.int32)
-    t_hi = max(1, int(a.t_max * n_edges / a.edges))  # a prefix of the stream covers early times
-    t = np.sort(rng.integers(0, t_hi, n_edges)).astype(np.int64)
-    x = rng.standard_normal((n_edges, a.dim)).astype(np.float32) if a.dim else None
+    n = e_hi - e_lo
+    src = rng.integers(0, a.nodes, n).astype(np.int32)
+    dst = rng.integers(0, a.nodes, n).astype(np.int32)
+    t_lo, t_hi = int(a.t_max * e_lo / a.edges), max(1, int(a.t_max * e_hi / a.edges))
+    t = np.sort(rng.integers(t_lo, max(t_hi, t_lo + 1), n)).astype(np.int64)
+    x = rng.standard_normal((n, a.dim), dtype=np.float32) if a.dim else None
     return src, dst, t, x
 
 
-def time_cpu_port(a, stream, n_edges, warm_edges=0):
-    """C port of the reference ring sampler (oracle/recency_ring.c) over a prefix of the stream,
-    loader batch by loader batch: query both endpoints, then push the batch."""
+def cpu_port_steady(a, stream, warm_edges, step_edges, steps, warmup):
+    """C port of the reference ring sampler (oracle/recency_ring.c), loader batch by loader batch:
+    query both endpoints, then push the batch.  The first `warm_edges` edges of `stream` are pushed
+    without querying so that the timed batches see full rings (steady state, like the GPU arm)."""
     from oracle.c_oracle import CRing
     src, dst, t, x = stream
     ring = CRing(a.nodes, [a.k], a.dim)
-    if warm_edges:
-        ring.run_stream(src, dst, t, x, 0, warm_edges, a.batch_size)
     t0 = time.perf_counter()
-    slots, _, _ = ring.run_stream(src, dst, t, x, warm_edges, n_edges, a.batch_size)
+    ring.push_stream(src, dst, t, x, 0, warm_edges, a.batch_size)
+    warm_s = time.perf_counter() - t0
+    at = warm_edges
+    for _ in range(warmup):
+        ring.run_stream(src, dst, t, x, at, at + step_edges, a.batch_size, checksum=False)
+        at += step_edges
+    t0 = time.perf_counter()
+    slots = 0
+    for _ in range(steps):
+        sl, _, _ = ring.run_stream(src, dst, t, x, at, at + step_edges, a.batch_size,
+                                   checksum=False)
+        slots += sl
+        at += step_edges
     dt = time.perf_counter() - t0
-    return slots / dt, slots, dt
+    return slots / dt, slots, dt, warm_s
 
 
 def run_reference(a):
     """`--impl reference`: the reference's algorithm on the host cores.  The reference is pure
     Python and cannot travel to the GPU box, so this times the C port of its state machine
     (a far faster stand-in than the reference's eager-PyTorch implementation: SURVEY.md section 6
-    measured the real one at ~4e5 sampled-edges/s at this geometry)."""
+    measured the real one at ~4e5 sampled-edges/s at this geometry).  One thread: the state
+    machine is sequential across loader batches and one batch is 400 seeds."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from oracle.c_oracle import CRing
     step_edges = 250 * a.batch_size  # bounded sample per step
-    need = (a.steps + a.warmup) * step_edges
-    src, dst, t, x = numpy_prefix_stream(a, need)
-    ring = CRing(a.nodes, [a.k], a.dim)
-    at = 0
-    for _ in range(a.warmup):
-        ring.run_stream(src, dst, t, x, at, at + step_edges, a.batch_size)
-        at += step_edges
-    t0 = time.perf_counter()
-    slots = 0
-    for _ in range(a.steps):
-        s, _, _ = ring.run_stream(src, dst, t, x, at, at + step_edges, a.batch_size)
-        slots += s
-        at += step_edges
-    dt = time.perf_counter() - t0
-    value = slots / dt
-    sample = (f'{a.steps} steps x 250 loader batches (bs={a.batch_size}) from the head of the '
-              f'stream after {a.warmup} warm-up steps; C port of the ring sampler, 1 thread '
-              f'(the state machine is sequential across batches)')
+    # the ring of a node holds its last k entries: pushing the `warm` edges that precede the timed
+    # region reproduces the steady state (a node sees on average 2 * warm / nodes >= 2.5 k entries)
+    warm = steady_start_edge(a)
+    need = warm + (a.steps + a.warmup) * step_edges
+    stream = numpy_stream(a, 0, need)
+    value, slots, dt, warm_s = cpu_port_steady(a, stream, warm, step_edges, a.steps, a.warmup)
+    sample = (f'{a.steps} steps x 250 loader batches (bs={a.batch_size}) starting at stream edge '
+              f'{warm + a.warmup * step_edges} (steady state: the preceding {warm} edges were pushed '
+              f'first, {warm_s:.0f} s untimed); C port of the ring sampler, 1 thread (the state '
+              f'machine is sequential across batches)')
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': a.gpus,
         'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': dt / a.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32/int64 '
         'ids+times, f32 feature copy', 'data': 'synthetic',
-        'config': workload_config(a, 1),
+        'config': workload_config(a, a.gpus),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': 1, 'kind': 'port',
                          'sample': sample, 'host_cores': os.cpu_count()},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -245,6 +274,8 @@ def run_b200(a):
     from tgm_b200.core.storage import DeviceCOOStorage
     _cabi.check(_cabi.lib.tgm_set_option(b'csr_feature_copy', int(a.feature_copy == 'tma')))
     _cabi.check(_cabi.lib.tgm_set_option(b'csr_tma_ctas_per_sm', a.tma_ctas_per_sm))
+    if os.environ.get('TGM_B200_TRACE'):
+        _cabi.check(_cabi.lib.tgm_set_option(b'trace', 1))
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -255,9 +286,13 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO; keep stdout to the
-        # one JSON line the driver parses
-        os.environ['NCCL_DEBUG'] = 'WARN'
+        # stdout carries the one JSON line the driver parses: NCCL's own log (whatever level the
+        # environment asks for; INIT lines by default so the communicator size is on record) goes
+        # to stderr
+        os.environ.setdefault('NCCL_DEBUG', 'INFO')
+        if os.environ['NCCL_DEBUG'].upper() == 'INFO':
+            os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
 
     E, N, D, k, bs = a.edges, a.nodes, a.dim, a.k, a.batch_size
@@ -267,23 +302,28 @@ def run_b200(a):
     dst = torch.randint(0, N, (E,), generator=gen, device=dev, dtype=torch.int32)
     t = torch.sort(torch.randint(0, a.t_max, (E,), generator=gen, device=dev))[0]
     x = torch.randn((E, D), generator=gen, device=dev) if D else None
+    torch.cuda.synchronize(dev)
     t_build = time.perf_counter()
     store = DeviceCOOStorage.from_device_tensors(src, dst, t, x, N)
     csr = RecencyCSR(store, bs, colocate_x=not a.no_colocate)
     torch.cuda.synchronize(dev)
     t_build = time.perf_counter() - t_build
 
-    # this rank's time-range shard of the batch stream (tgm_b200/parallel.py)
+    # this rank's time-range shard (tgm_b200/parallel.py) of the steady-state part of the batch
+    # stream; `full` = its shard of the whole stream (the full pass below)
     from tgm_b200.parallel import shard_batches
-    shard = shard_batches(E, bs, rank, world)
-    b_lo, b_hi = shard.batch_lo, shard.batch_hi
+    nb_total = (E + bs - 1) // bs
+    sb0 = steady_start_edge(a) // bs
+    steady = shard_batches((nb_total - sb0) * bs, bs, rank, world)
+    b_lo, b_hi = sb0 + steady.batch_lo, sb0 + steady.batch_hi
+    full = shard_batches(E, bs, rank, world)
     W = min(a.window_batches, b_hi - b_lo)
     nwin = max(1, (b_hi - b_lo) // W)
 
-    def window(i, wb=W, count=nwin):
+    def window(i, wb=W, count=nwin, base=b_lo, end=b_hi):
         j = i % count
-        lo = (b_lo + j * wb) * bs
-        return lo, min(lo + wb * bs, E, b_hi * bs)
+        lo = (base + j * wb) * bs
+        return lo, min(lo + wb * bs, E, end * bs)
 
     max_edges = W * bs
     out = (torch.empty((2 * max_edges, k), dtype=torch.int32, device=dev),
@@ -295,28 +335,13 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def step(i):
-        lo, hi = window(i)
+    def sample_into(lo, hi):
         n = 2 * (hi - lo)
         csr.sample_edges(lo, hi, k, k, out=(out[0][:n], out[1][:n], out[2][:n]))
         return n * k
 
-    clocks = ClockSampler(local)
-    for i in range(max(a.warmup, 3)):  # never fewer than 3 untimed steps
-        step(i)
-    barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(a.steps)]
-    clocks.start()
-    slots = 0
-    for i in range(a.steps):
-        ev[i][0].record()
-        slots += step(max(a.warmup, 3) + i)
-        ev[i][1].record()
-    barrier()
-    clocks.pause()
-    kernel_ms = [s.elapsed_time(e) for s, e in ev]
-    total_ms = ev[0][0].elapsed_time(ev[-1][1])
+    def step(i):
+        return sample_into(*window(i))
 
     def reduce_max(v):
         if world == 1:
@@ -332,9 +357,30 @@ def run_b200(a):
         dist.all_reduce(tt, op=dist.ReduceOp.SUM)
         return float(tt.item())
 
+    clocks = ClockSampler(local)
+    nwarm = max(a.warmup, 3)  # never fewer than 3 untimed steps
+    for i in range(nwarm):
+        step(i)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(a.steps)]
+    clocks.start()
+    slots = 0
+    for i in range(a.steps):
+        ev[i][0].record()
+        slots += step(nwarm + i)
+        ev[i][1].record()
+    barrier()
+    clocks.pause()
+    kernel_ms = [s.elapsed_time(e) for s, e in ev]
+    total_ms = ev[0][0].elapsed_time(ev[-1][1])
     total_ms_max = reduce_max(total_ms)
     slots_all = reduce_sum(float(slots))
     value = slots_all / (total_ms_max * 1e-3)
+    # how much of the timed output was padding (steady state: ~0)
+    lo_s, hi_s = window(nwarm)
+    sample_into(lo_s, hi_s)
+    pad_frac = float((out[0][:2 * (hi_s - lo_s)] < 0).float().mean().item())
 
     # roofline of the dominant (only) kernel: algorithmic bytes per launch / mean launch duration
     slots_per_launch = slots / a.steps
@@ -362,7 +408,27 @@ def run_b200(a):
                 'traffic_source': 'profiles/traffic.json (ncu dram__bytes_read+write per sampled edge '
                                   'x sampled edges per launch)' if traffic else None,
                 'algorithmic_bytes_per_launch': algo_bytes,
-                'bytes_per_sampled_edge': bytes_per_slot, 'launch_ms': launch_s * 1e3}
+                'bytes_per_sampled_edge': bytes_per_slot, 'launch_ms': launch_s * 1e3,
+                'padded_slot_fraction': pad_frac}
+
+    # ---- one pass over the WHOLE stream, build included -------------------------------------
+    fW = min(a.window_batches, full.batch_hi - full.batch_lo)
+    fwins = [((full.batch_lo + j) * bs, min((full.batch_lo + j + fW) * bs, E, full.batch_hi * bs))
+             for j in range(0, full.batch_hi - full.batch_lo, fW)]
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    fslots = sum(sample_into(lo, hi) for lo, hi in fwins)
+    f1.record()
+    barrier()
+    pass_s = f0.elapsed_time(f1) * 1e-3
+    build_max, pass_max = reduce_max(t_build), reduce_max(pass_s)
+    full_pass = {
+        'value_incl_build': reduce_sum(float(fslots)) / reduce_max(t_build + pass_s), 'unit': UNIT,
+        'build_s': build_max, 'sample_s': pass_max, 'windows': len(fwins),
+        'what': 'every loader batch of the stream sampled once (this rank\'s shard; under-filled '
+                'head included), plus the one-off build of store handle + adjacency + anchors + '
+                'colocated feature rows from the device-resident edge arrays'}
 
     # ---- e2e: host buffers in, host buffers out, through the C ABI --------------------------
     e2e = None
@@ -377,110 +443,171 @@ def run_b200(a):
             host_in.append((lo, hi, tuple(
                 None if v is None else v[lo:hi].cpu().pin_memory() for v in (src, dst, t, x))))
         nslot = 2
-        host_out = [(torch.empty((2 * me, k), dtype=torch.int32).pin_memory(),
-                     torch.empty((2 * me, k), dtype=torch.int64).pin_memory(),
-                     torch.empty((2 * me, k, D), dtype=torch.float32).pin_memory())
-                    for _ in range(nslot)]
         streams = [torch.cuda.Stream(dev) for _ in range(nslot)]
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()  # noqa: E731
+        cells = (2 * me, k)
 
-        def e2e_step(i):
-            lo, hi, hin = host_in[i % n_host_win]
-            sl = i % nslot
-            streams[sl].synchronize()  # the previous result in this slot has been consumed
-            csr.sample_edges_host(lo, hi, k, k, hin, host_out[sl], slot=sl,
-                                  stream=streams[sl].cuda_stream)
-            return 2 * (hi - lo) * k, hin
+        def run_variant(name, nsteps):
+            """K steps of one host-buffer form, double-buffered over two streams; returns
+            (sampled edges, seconds, h2d bytes, d2h bytes, spot-check)."""
+            if name == 'ids':
+                outs = [(pin(cells, torch.int32), pin(cells, torch.int64), pin(cells, torch.int32))
+                        for _ in range(nslot)]
+                call = csr.sample_edges_host_ids
+                nin = 3
+            elif name == 'mean':
+                outs = [(None, None, pin((2 * me, D), torch.float32)) for _ in range(nslot)]
+                call = csr.sample_edges_host_mean
+                nin = 3
+            else:
+                outs = [(pin(cells, torch.int32), pin(cells, torch.int64),
+                         pin(cells + (D,), torch.float32)) for _ in range(nslot)]
+                call = csr.sample_edges_host
+                nin = 4
 
-        for i in range(max(3, a.warmup)):
-            e2e_step(i)
-        barrier()
-        clocks.start()
-        t0 = time.perf_counter()
-        eslots = 0
-        for i in range(ke):
-            s, hin = e2e_step(i)
-            eslots += s
-        for s_ in streams:
-            s_.synchronize()
-        barrier()
-        dt = time.perf_counter() - t0
-        clocks.pause()
-        h2d = sum(v.numel() * v.element_size() for v in hin if v is not None)
-        d2h = 2 * (host_in[0][1] - host_in[0][0]) * k * (4 + 8 + 4 * D)
-        # spot-check: the host result equals the device-resident path on the same window
-        lo, hi, hin = host_in[(ke - 1) % n_host_win]
-        sl = (ke - 1) % nslot
-        ref = csr.sample_edges(lo, hi, k, k)
-        n = 2 * (hi - lo)
-        assert torch.equal(host_out[sl][0][:n], ref[0].cpu()), 'e2e ids differ from device path'
-        assert torch.equal(host_out[sl][1][:n], ref[1].cpu())
-        assert torch.equal(host_out[sl][2][:n], ref[2].cpu())
-        dt_max = reduce_max(dt)
-        e2e = {'value': reduce_sum(float(eslots)) / dt_max, 'unit': UNIT,
-               'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': ke,
-               'ms_per_step': dt_max / ke * 1e3, 'window_batches': We,
-               'api': 'tgm_csr_sample_edges_host (pinned host slab in, pinned host result out, '
-                      '2 streams)'}
-        del host_out, host_in
+            def one(i):
+                lo, hi, hin = host_in[i % n_host_win]
+                sl = i % nslot
+                streams[sl].synchronize()  # the previous result in this slot has been consumed
+                call(lo, hi, k, k, hin[:nin], outs[sl], slot=sl, stream=streams[sl].cuda_stream)
+                return 2 * (hi - lo) * k
+
+            for i in range(3):
+                one(i)
+            for s_ in streams:
+                s_.synchronize()
+            barrier()
+            clocks.start()
+            t0 = time.perf_counter()
+            got = 0
+            for i in range(nsteps):
+                got += one(i)
+            for s_ in streams:
+                s_.synchronize()
+            barrier()
+            dt = time.perf_counter() - t0
+            clocks.pause()
+            lo, hi, hin = host_in[(nsteps - 1) % n_host_win]
+            res = outs[(nsteps - 1) % nslot]
+            n = 2 * (hi - lo)
+            h2d = sum(v.numel() * v.element_size() for v in hin[:nin] if v is not None)
+            d2h = sum(v[:n].numel() * v.element_size() for v in res if v is not None)
+            # spot-check: the host result equals the device-resident path on the same window
+            ref = csr.sample_edges(lo, hi, k, k)
+            if name == 'mean':
+                want = torch.empty((n, D), dtype=torch.float32, device=dev)
+                _cabi.check(_cabi.lib.tgm_masked_mean(ref[2].data_ptr(), ref[0].data_ptr(), n, k, D,
+                                                      want.data_ptr(), _cabi.current_stream(dev)))
+                assert torch.equal(res[2][:n], want.cpu()), 'e2e fused mean differs'
+            else:
+                assert torch.equal(res[0][:n], ref[0].cpu()), 'e2e ids differ from device path'
+                assert torch.equal(res[1][:n], ref[1].cpu())
+                if name == 'ids':  # the host gathers the rows it owns: edge_x[eid]
+                    rows = res[2][:4096].to(dev).long()
+                    assert torch.equal(x[rows.clamp(min=0)] * (rows >= 0)[..., None],
+                                       ref[2][:4096]), 'edge_x[eid] differs from nbr_edge_x'
+                else:
+                    assert torch.equal(res[2][:n], ref[2].cpu())
+            dt_max = reduce_max(dt)
+            return {'value': reduce_sum(float(got)) / dt_max, 'unit': UNIT, 'steps': nsteps,
+                    'ms_per_step': dt_max / nsteps * 1e3, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h}
+
+        # what the host link itself delivers with every rank copying at once (pinned, one stream)
+        lk = pin((64 << 20,), torch.uint8)
+        lkd = torch.empty_like(lk, device=dev)
+        link = {}
+        for name, (dst_, src_) in (('d2h', (lk, lkd)), ('h2d', (lkd, lk))):
+            dst_.copy_(src_, non_blocking=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(8):
+                dst_.copy_(src_, non_blocking=True)
+            barrier()
+            link[name + '_gbs_per_rank'] = 8 * lk.numel() / reduce_max(time.perf_counter() - t0) / 1e9
+        del lk, lkd
+
+        e2e = run_variant('ids', ke)
+        e2e.update({
+            'window_batches': We,
+            'api': 'tgm_csr_sample_edges_host_ids (pinned host slab [src|dst|t] in, kernel reads '
+                   'its seeds from that slab, pinned (nid, t, eid) out, 2 streams); the host owns '
+                   'edge_x and gathers nbr_edge_x = edge_x[eid] itself when it needs rows',
+            'link': link,
+            'variants': {
+                'full_rows': dict(run_variant('rows', min(ke, a.e2e_full_steps)),
+                                  api='tgm_csr_sample_edges_host: slab incl. edge_x in, '
+                                      '(nid, t, nbr_edge_x) out'),
+                'fused_mean': dict(run_variant('mean', ke),
+                                   api='tgm_csr_sample_edges_host_mean: slab in, masked mean of '
+                                       'the sampled rows (S, D) out') if D and D % 4 == 0 else None,
+            }})
+        del host_in
 
     # ---- the call a TGM user makes: for batch in DGDataLoader(dg, 200, hook_manager=hm) ---------
     loader_api = None
     if a.loader_batches and not a.no_e2e:
-        from tgm_b200 import DGDataLoader, DGraph, HookManager, RecencyNeighborHook
+        from tgm_b200 import (DGDataLoader, DGraph, HookManager, RandomNegativeEdgeSamplerHook,
+                              RecencyNeighborHook)
         from tgm_b200.core.storage import DGSliceTracker
         from tgm_b200.core.timedelta import TimeDeltaDG
-        nbl = min(a.loader_batches, b_hi - b_lo)
+        nbl = min(a.loader_batches, nb_total)
         # every rank walks the head of the stream (loader.py:137-139 iterates absolute event indices
         # from 0, so an index-sliced view cannot start mid-stream); this key measures the Python API
         sl = DGSliceTracker(end_idx=min(nbl * bs, E))
         dg = DGraph._from_storage(store, TimeDeltaDG('r'), dev, sl)
-        hm = HookManager(keys=['bench'])
-        hm.register('bench', RecencyNeighborHook(
-            num_nodes=N, num_nbrs=[k], seed_nodes_keys=['edge_src', 'edge_dst'],
-            seed_times_keys=['edge_time', 'edge_time'], window_batches=min(5000, nbl)))
-        with hm.activate('bench'):
-            for pass_ in range(2):  # first pass warms the adjacency cache and the allocator
-                hm.reset_state()
-                barrier()
-                t0 = time.perf_counter()
-                got = 0
-                for batch in DGDataLoader(dg, batch_size=bs, hook_manager=hm):
-                    got += batch.nbr_nids[0].numel()
-                barrier()
-                dt = time.perf_counter() - t0
-        dt_max = reduce_max(dt)
-        loader_api = {'value': reduce_sum(float(got)) / dt_max, 'unit': UNIT, 'batches': nbl,
-                      'us_per_batch': dt_max / nbl * 1e6,
-                      'api': 'DGDataLoader(batch_size=200) + HookManager + RecencyNeighborHook('
-                             'window_batches=5000): outputs stay on the device, one DGBatch per '
-                             'iteration (Python-bound)'}
+
+        def loader_run(with_neg):
+            hm = HookManager(keys=['bench'])
+            keys_n, keys_t = ['edge_src', 'edge_dst'], ['edge_time', 'edge_time']
+            if with_neg:  # the link-prediction recipe (tgm/hooks/recipe.py:51-79)
+                hm.register('bench', RandomNegativeEdgeSamplerHook(low=0, high=N))
+                keys_n, keys_t = keys_n + ['neg'], keys_t + ['neg_time']
+            hm.register('bench', RecencyNeighborHook(
+                num_nodes=N, num_nbrs=[k], seed_nodes_keys=keys_n, seed_times_keys=keys_t))
+            with hm.activate('bench'):
+                for pass_ in range(2):  # first pass warms the adjacency cache and the allocator
+                    hm.reset_state()
+                    barrier()
+                    t0 = time.perf_counter()
+                    got = 0
+                    for batch in DGDataLoader(dg, batch_size=bs, hook_manager=hm):
+                        got += batch.nbr_nids[0].numel()
+                    barrier()
+                    dt = time.perf_counter() - t0
+            dt_max = reduce_max(dt)
+            return {'value': reduce_sum(float(got)) / dt_max, 'unit': UNIT, 'batches': nbl,
+                    'us_per_batch': dt_max / nbl * 1e6}
+
+        loader_api = loader_run(False)
+        loader_api['api'] = ('DGDataLoader(batch_size=200) + HookManager + default-constructed '
+                             'RecencyNeighborHook: outputs stay on the device, one DGBatch per '
+                             'iteration (Python-bound)')
+        loader_api['with_negatives'] = dict(
+            loader_run(True), api='the same with RandomNegativeEdgeSamplerHook in front and seeds '
+                                  '[edge_src | edge_dst | neg] (negatives drawn one window ahead)')
+
+    # ---- the one exchange of the path: TGN node-memory join at shard boundaries (N > 1) ---------
+    collective = None
+    if world > 1 and not a.no_collective:
+        from tgm_b200.parallel import bench_memory_join
+        collective = bench_memory_join(N, 100, src[full.batch_lo * bs:min(full.batch_hi * bs, E)],
+                                       dst[full.batch_lo * bs:min(full.batch_hi * bs, E)],
+                                       a.join_edges, dev, reps=5)
 
     # ---- CPU baseline on this host (rank 0, N=1 only) ---------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        n_cpu = min(a.cpu_sample_edges, E)
-        warm = n_cpu // 3
-        stream = tuple(None if v is None else v[:n_cpu].cpu().numpy() for v in (src, dst, t, x))
-        v, s, dt = time_cpu_port(a, stream, n_cpu, warm)
-        # the numpy restatement follows the reference's eager tensor-op structure (gathers, masks,
-        # argsort) more closely than the C port does: reported beside it, on fewer batches
-        from oracle.recency_oracle import RingOracle
-        nb_np = 300
-        ring_np = RingOracle(N, [k], D)
-        lo_np = warm
-        t0 = time.perf_counter()
-        for b in range(nb_np):
-            lo_b, hi_b = lo_np + b * bs, lo_np + (b + 1) * bs
-            sd = np.concatenate([stream[0][lo_b:hi_b], stream[1][lo_b:hi_b]])
-            tq_ = np.concatenate([stream[2][lo_b:hi_b]] * 2)
-            ring_np.hook_call(sd, tq_, stream[0][lo_b:hi_b], stream[1][lo_b:hi_b],
-                              stream[2][lo_b:hi_b], None if D == 0 else stream[3][lo_b:hi_b])
-        np_rate = nb_np * 2 * bs * k / (time.perf_counter() - t0)
+        # steady state like the GPU arm: the `warm` edges preceding the sample are pushed first
+        warm = steady_start_edge(a)
+        n_cpu = min(a.cpu_sample_edges, E - warm)
+        stream = tuple(None if v is None else v[:warm + n_cpu].cpu().numpy() for v in (src, dst, t, x))
+        v, s, dt, warm_s = cpu_port_steady(a, stream, warm, n_cpu, 1, 0)
         cpu = {'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'host_cores': os.cpu_count(),
-               'numpy_port_value': np_rate,
-               'sample': f'edges [{warm}, {n_cpu}) of the same stream ({s} sampled edges, '
-                         f'{dt:.1f} s) after pushing the first {warm}; C port of the '
-                         f'reference ring sampler (oracle/recency_ring.c), batch by batch'}
+               'sample': f'edges [{warm}, {warm + n_cpu}) of the same stream ({s} sampled edges, '
+                         f'{dt:.1f} s) after pushing the first {warm} ({warm_s:.0f} s untimed: '
+                         f'steady state, full rings); C port of the reference ring sampler '
+                         f'(oracle/recency_ring.c), batch by batch, 1 thread'}
 
     if rank == 0:
         line = {
@@ -490,9 +617,10 @@ def run_b200(a):
             'dtype': 'int32/int64 ids+times, f32 feature copy', 'data': 'synthetic',
             'config': workload_config(a, world), 'gpu_launches': a.steps,
             'stream_edges_per_s': value / (2 * k),
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'loader_api': loader_api,
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'full_pass': full_pass,
+            'loader_api': loader_api, 'collective': collective,
             'clocks': clocks.result(), 'numa': numa,
-            'build_s': t_build,
+            'build_s': build_max,
         }
         print(json.dumps(line))
     if world > 1:

@@ -61,13 +61,15 @@ int tgm_set_option(const char *name, int value);
  *   tgm/core/_storage/backends/array_backend.py:15-21   (__init__ holding DGData)
  *   tgm/core/_storage/backends/array_backend.py:301-321 (_binary_search)
  *   tgm/core/_storage/backends/array_backend.py:57-68, 259-268 (get_edges / get_edge_x)
- * The reference rebuilds O(E) boolean masks per batch; here a slice is two binary searches on a
- * host mirror of the timestamps and a pointer offset into the device slabs.
+ * The reference rebuilds O(E) boolean masks per batch; here a slice is two binary searches over the
+ * timestamps and a pointer offset into the device slabs.
  *
  * src,dst: int32[E]; t: int64[E] non-decreasing; edge_x: float32[E*D] row-major or NULL (D=0).
  * mem = TGM_MEM_HOST: pointers are host memory, uploaded on `device`.
  * mem = TGM_MEM_DEVICE: pointers are device memory on `device`, adopted without a copy; t_host
- *       may pass a host copy of t (else it is read back once).
+ *       may pass a host copy of t, BORROWED for the life of the store (bounds are then searched on
+ *       the host).  With t_host = NULL the store keeps no host mirror: the order of t is verified
+ *       by one device pass and time bounds are searched on the device (16 bytes read back).
  * device = -1 (TGM_MEM_HOST only): metadata-only store; bounds work, slabs/kernels do not.
  */
 int tgm_store_create(tgm_store **out, const int32_t *src, const int32_t *dst, const int64_t *t,
@@ -209,6 +211,71 @@ int tgm_csr_sample_edges_host(tgm_csr *, int64_t e_lo, int64_t e_hi, int32_t B, 
                               const int32_t *h_src, const int32_t *h_dst, const int64_t *h_t,
                               const float *h_x, int32_t *h_out_nid, int64_t *h_out_t,
                               float *h_out_x, int slot, tgm_stream stream);
+
+/* Hop-0 forms that never materialise the (S, k, D) feature block (with D = 172 a
+ * sampled slot is 700 B of feature row against 12 B of id + time).  Same seeds, row layout, window
+ * and time rule as tgm_csr_sample_edges; B <= 32.
+ *   search = 0: history cuts from the prebuilt anchor table;
+ *   search = 1: every seed is read from the store's src/dst slab and its cut found by a binary
+ *               search over the node's adjacency (what the host forms below use, so the slab
+ *               they upload is what the kernel consumes).
+ * tgm_csr_sample_edges_ids: out_nid int32[2n*k], out_t int64[2n*k] as tgm_csr_sample_edges, plus
+ *   out_eid int32[2n*k] = store edge index of every slot (-1 for padding), so that
+ *   nbr_edge_x[s, c, :] == edge_x[out_eid[s, c]] (zeros where -1): a caller that owns the feature
+ *   table gathers the rows itself.  Any output may be NULL.
+ * tgm_csr_sample_edges_mean: fused sample + masked mean over the sampled rows
+ *   (examples/linkproppred/graphmixer.py:131-135 applied to recency.py:239-321's output):
+ *   out_mean float32[2n*D] = sum of the seed's valid feature rows (oldest to newest, fp32) /
+ *   max(1, #valid) -- bit-identical to tgm_masked_mean over tgm_csr_sample_edges' output.  Needs
+ *   colocated feature rows and D % 4 == 0.  out_nid/out_t/out_eid are optional (NULL = skip). */
+int tgm_csr_sample_edges_ids(const tgm_csr *, int64_t e_lo, int64_t e_hi, int32_t B, int32_t k,
+                             int search, int32_t *out_nid, int64_t *out_t, int32_t *out_eid,
+                             tgm_stream stream);
+int tgm_csr_sample_edges_mean(const tgm_csr *, int64_t e_lo, int64_t e_hi, int32_t B, int32_t k,
+                              int search, int32_t *out_nid, int64_t *out_t, int32_t *out_eid,
+                              float *out_mean, tgm_stream stream);
+/* Host-buffer forms of the two calls above (search = 1): H2D of the slab (h_src/h_dst int32[n],
+ * h_t int64[n]; NULL = already resident), the kernel, D2H of the outputs -- 16 bytes per sampled
+ * slot (ids form) or 4*D bytes per seed (+ optional ids/times) instead of 12 + 4*D bytes per slot.
+ * The host gathers nbr_edge_x = edge_x[eid] from the table it already owns when it needs rows. */
+int tgm_csr_sample_edges_host_ids(tgm_csr *, int64_t e_lo, int64_t e_hi, int32_t B, int32_t k,
+                                  const int32_t *h_src, const int32_t *h_dst, const int64_t *h_t,
+                                  int32_t *h_out_nid, int64_t *h_out_t, int32_t *h_out_eid,
+                                  int slot, tgm_stream stream);
+int tgm_csr_sample_edges_host_mean(tgm_csr *, int64_t e_lo, int64_t e_hi, int32_t B, int32_t k,
+                                   const int32_t *h_src, const int32_t *h_dst, const int64_t *h_t,
+                                   int32_t *h_out_nid, int64_t *h_out_t, float *h_out_mean,
+                                   int slot, tgm_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * TGN node-memory join at time-shard boundaries (multi-GPU, BASELINE config 4).  The reference
+ * keeps memory f32[N, M] / last_update int64[N] in one process (tgm/nn/encoder/tgn.py:95-110,
+ * written by :192-216); time-sharded over GPUs, the rows a shard touched travel through ONE
+ * all-gather as packed records { int32 id | int32 0 | int64 last_update | float memory[M] }
+ * (tgm_join_row_bytes(M) = 16 + 4 M bytes; M % 4 == 0).
+ *   tgm_join_pack: rows[i] = record of node ids[i] for i < n; rows n .. cap-1 are padding records
+ *     (id -1) so every rank sends a block of the common size `cap`.
+ *   tgm_join_scatter: applies n records to memory / last_update (ids < 0 or >= num_nodes are
+ *     skipped).  Applying the ranks' blocks in ascending rank order makes the later time shard win
+ *     a row two shards touched. */
+int64_t tgm_join_row_bytes(int32_t M);
+int tgm_join_pack(const float *memory, const int64_t *last_update, int32_t M, const int32_t *ids,
+                  int64_t n, int64_t cap, void *rows, tgm_stream stream);
+int tgm_join_scatter(const void *rows, int64_t n, int32_t M, int32_t num_nodes, float *memory,
+                     int64_t *last_update, tgm_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Negative destinations for a window of loader batches in one launch.  Replaces the per-batch
+ * torch.randint(low, high, (n,), dtype=int32, device=dg.device) of RandomNegativeEdgeSamplerHook
+ * (tgm/hooks/negatives/sampler.py:45-65).  out int32[total]: element g belongs to batch
+ * j = g / per_batch of the window (the last batch may be short) and is element i = g % per_batch
+ * of the j-th randint call:  low + philox4x32_10(key=seed, counter={(offset + 4j)/4, i}).x %
+ * (high - low) -- the numbers `ceil(total / per_batch)` consecutive torch.randint calls draw from
+ * a CUDA generator at (seed, offset), i.e. the reference's own device='cuda' stream.  The caller
+ * advances its generator by 4 per batch.  offset % 4 == 0, per_batch <= 65536, range < 2^28 (from
+ * there on ATen switches to 64-bit draws). */
+int tgm_negatives_window(uint64_t seed, uint64_t offset, int64_t low, int64_t high,
+                         int64_t per_batch, int64_t total, int32_t *out, tgm_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * Frontier compaction (hop h+1 seeds = flatten(hop h), recency.py:141-143; the non-padded

@@ -136,9 +136,18 @@ class CRing:
                 self.update(src, dst, t, x)
         return out
 
-    def run_stream(self, src, dst, t, x, e_lo: int, e_hi: int, bs: int, keep_hop0: bool = False):
+    def push_stream(self, src, dst, t, x, e_lo: int, e_hi: int, bs: int) -> None:
+        """Push edges [e_lo, e_hi) batch by batch without querying (recency.py:323-399 only):
+        the state a hook reaches after those batches, for timing runs that start mid-stream."""
+        for lo in range(e_lo, e_hi, bs):
+            hi = min(lo + bs, e_hi)
+            self.update(src[lo:hi], dst[lo:hi], t[lo:hi], None if x is None else x[lo:hi])
+
+    def run_stream(self, src, dst, t, x, e_lo: int, e_hi: int, bs: int, keep_hop0: bool = False,
+                   checksum: bool = True):
         """Loader + hook over edges [e_lo, e_hi) with seeds [src | dst].  Returns
-        (sampled slots, csum uint64[nhops, 3], hop-0 outputs or None)."""
+        (sampled slots, csum uint64[nhops, 3], hop-0 outputs or None); `checksum=False` skips the
+        checksum pass over the outputs (timing runs)."""
         src, dst, t = _c(src, np.int32), _c(dst, np.int32), _c(t, np.int64)
         x = None if (x is None or self.D == 0) else _c(x, np.float32)
         nn = np.asarray(self.num_nbrs, np.int32)
@@ -150,7 +159,8 @@ class CRing:
                     np.empty((S, k, self.D), np.float32))
         slots = lib().ring_run_stream(
             self._h, _p(src), _p(dst), _p(t), _p(x), e_lo, e_hi, bs, _p(nn), len(nn),
-            int(self.directed), _p(csum), *(map(_p, outs) if outs else (None, None, None)))
+            int(self.directed), _p(csum) if checksum else None,
+            *(map(_p, outs) if outs else (None, None, None)))
         if slots < 0:
             raise MemoryError('ring_run_stream failed')
         return int(slots), csum, outs

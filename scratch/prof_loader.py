@@ -13,10 +13,17 @@ t = torch.sort(torch.randint(0, 2000, (E,), generator=g, device=dev))[0]
 x = torch.randn((E, D), generator=g, device=dev)
 store = DeviceCOOStorage.from_device_tensors(src, dst, t, x, N)
 dg = DGraph._from_storage(store, TimeDeltaDG('r'), dev, DGSliceTracker(end_idx=E))
-for wb in (5000, 0):
+from tgm_b200 import RandomNegativeEdgeSamplerHook
+for wb in ('default', 'default+neg', 0):
     hm = HookManager(keys=['bench'])
-    hm.register('bench', RecencyNeighborHook(num_nodes=N, num_nbrs=[k], seed_nodes_keys=['edge_src', 'edge_dst'],
-                seed_times_keys=['edge_time', 'edge_time'], window_batches=wb))
+    kw = {} if wb != 0 else {'window_batches': 0}
+    if wb == 'default+neg':
+        hm.register('bench', RandomNegativeEdgeSamplerHook(low=0, high=N))
+        hm.register('bench', RecencyNeighborHook(num_nodes=N, num_nbrs=[k], seed_nodes_keys=['edge_src', 'edge_dst', 'neg'],
+                    seed_times_keys=['edge_time', 'edge_time', 'neg_time']))
+    else:
+        hm.register('bench', RecencyNeighborHook(num_nodes=N, num_nbrs=[k], seed_nodes_keys=['edge_src', 'edge_dst'],
+                    seed_times_keys=['edge_time', 'edge_time'], **kw))
     def run():
         got = 0
         with hm.activate('bench'):

@@ -146,8 +146,11 @@ def test_loader_hook_api_matches_reference_fixture(path):
     if g.neg is not None:
         hm.register('g', _InjectNegatives(dev(g.neg, torch.int32)))
         keys_n, keys_t = keys_n + ['neg'], keys_t + ['neg_time']
+    # window_batches=0: the stateful ring kernels batch by batch (the default-constructed hook
+    # pre-samples windows and only materialises ring state on demand; tests/test_gpu_negatives.py
+    # and test_windowed_hook_* cover it)
     hook = RecencyNeighborHook(num_nodes=g.N, num_nbrs=g.num_nbrs, seed_nodes_keys=keys_n,
-                               seed_times_keys=keys_t, directed=g.directed)
+                               seed_times_keys=keys_t, directed=g.directed, window_batches=0)
     hm.register('g', hook)
     with hm.activate('g'):
         for ep in range(g.epochs):
@@ -883,44 +886,87 @@ def test_dgraph_to_cuda_uploads_a_host_side_graph():
     assert dg.edge_x.shape == (2, 2)
 
 
-def test_config1_wiki_shaped_epoch_is_index_exact():
-    """BASELINE configs[0]: tgbl-wiki-shaped stream (9,227 nodes, 157,474 edges, D=172,
-    t in [0, 2.68e6]), DGDataLoader batch_size=200, recent-neighbour hook k=10.  Every id, time
-    and feature of the whole epoch, from both the stateful and the windowed hook, is compared with
-    the C oracle through position-sensitive checksums (plus exact tensors on sampled batches)."""
-    rng = np.random.default_rng(0)
-    E, N, D, bs, k = 157_474, 9227, 172, 200, 10
+class _PublishNegatives:
+    """Fixture negatives handed out as a window drawn ahead (hooks/negatives.py protocol), so the
+    default-constructed hook samples [src | dst | neg] of many batches in one launch per hop."""
+    has_state = False
+    requires = {'edge_src', 'edge_dst', 'edge_time'}
+    produces = {'neg', 'neg_time'}
+
+    def __init__(self, neg):
+        self.neg, self.pub = neg, None
+
+    def reset_state(self):
+        pass
+
+    def __call__(self, dg, batch):
+        from tgm_b200.hooks.negatives import SeedWindow
+        store, lo, hi = batch._slab[:3]
+        if self.pub is None:
+            self.pub = SeedWindow(store, 0, store.num_edges, self.neg, store._t.clone(), 0, 1 << 30)
+        batch.neg, batch.neg_time = self.pub.nodes[lo:hi], self.pub.times[lo:hi]
+        batch._seed_windows = {'neg': self.pub}
+        return batch
+
+
+@pytest.mark.parametrize('mode', ['ring', 'windowed'])
+def test_config1_wiki_shaped_epoch_equals_the_unmodified_reference(mode):
+    """BASELINE configs[0] pinned on the REAL reference (tests/golden/make_golden_config1.py ran
+    tgm-team/tgm unmodified in the build container): tgbl-wiki-shaped stream (9,227 nodes, 157,474
+    edges, D=172, t < 2.68e6), DGDataLoader batch_size=200, recent-neighbour hook k=10, seeds
+    src + dst + the negatives the reference's own RandomNegativeEdgeSamplerHook drew.  Every id,
+    time and feature row of every batch of the epoch is compared through the position-sensitive
+    checksums the reference run recorded (exact tensors on every 97th batch), for the stateful
+    ring path and for the default windowed path.
+
+    The stream lies outside the reference's int32 sort-key domain (recency.py:347-348); on this
+    epoch the unmodified reference deviates from the ideal semantics on the batches listed in
+    `differs_from_ideal` (1 of 788), where the expectation is the reference with its one-token
+    `.long()` fix (`patched_csum`; the generator checks that fix equals the ideal semantics on
+    all 788 batches)."""
+    import os
+    from tests._golden import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, 'config1_wiki_epoch.npz'))
+    E, N, D, bs, k = (int(z[n]) for n in ('E', 'N', 'D', 'bs', 'k'))
+    rng = np.random.default_rng(int(z['seed']))
     src = rng.integers(0, 8227, E).astype(np.int32)
     dst = rng.integers(8227, N, E).astype(np.int32)
     t = np.sort(rng.integers(0, 2_678_374, E)).astype(np.int64)
     x = rng.standard_normal((E, D)).astype(np.float32)
-    assert N * (int(t.max()) + 1) >= 2 ** 31  # outside the reference's int32-key domain (H1):
-    # the oracle computes the ideal semantics, i.e. the reference with node_ids.long()
-    oracle = CRing(N, [k], D)
-    slots, want, hop0 = oracle.run_stream(src, dst, t, x, 0, E, bs, keep_hop0=True)
+    assert [c_oracle.checksum_np(v) for v in (src, dst, t, x)] == [int(v) for v in z['input_csum']], \
+        'the regenerated stream is not the one the reference ran on'
+    assert N * (int(t.max()) + 1) >= 2 ** 31
+    differs = {int(b): i for i, b in enumerate(z['differs_from_ideal'])}
+    assert len(differs) <= 2
+    neg = dev(z['neg'], torch.int32)
     dg = DGraph(DGData.from_raw(torch.from_numpy(t), torch.from_numpy(np.stack([src, dst], 1)),
                                 torch.from_numpy(x)), device=DEV)
-    for window in (0, 100):
-        hook = RecencyNeighborHook(num_nodes=N, num_nbrs=[k], seed_nodes_keys=['edge_src', 'edge_dst'],
-                                   seed_times_keys=['edge_time', 'edge_time'], window_batches=window)
-        hm = HookManager(keys=['g'])
-        hm.register('g', hook)
-        got, rows = [0, 0, 0], 0
-        with hm.activate('g'):
-            for b, batch in enumerate(DGDataLoader(dg, batch_size=bs, hook_manager=hm)):
-                nid, nt, nx = batch.nbr_nids[0], batch.nbr_edge_time[0], batch.nbr_edge_x[0]
-                base = rows * k
-                got[0] += torch_checksum(nid, base)
-                got[1] += torch_checksum(nt, base)
-                got[2] += torch_checksum(nx, base * D)
-                if b % 97 == 0:
-                    a, e = rows, rows + nid.shape[0]
-                    assert np.array_equal(nid.cpu().numpy(), hop0[0][a:e])
-                    assert np.array_equal(nt.cpu().numpy(), hop0[1][a:e])
-                    assert np.array_equal(nx.cpu().numpy(), hop0[2][a:e])
-                rows += nid.shape[0]
-        assert rows * k == slots == 2 * E * k
-        assert [v % (1 << 64) for v in got] == [int(v) for v in want[0]], f'window={window}'
+    hm = HookManager(keys=['g'])
+    if mode == 'ring':
+        hm.register('g', _InjectNegatives(neg))
+        kw = {'window_batches': 0}
+    else:
+        hm.register('g', _PublishNegatives(neg))
+        kw = {}
+    hook = RecencyNeighborHook(num_nodes=N, num_nbrs=[k],
+                               seed_nodes_keys=['edge_src', 'edge_dst', 'neg'],
+                               seed_times_keys=['edge_time', 'edge_time', 'neg_time'], **kw)
+    hm.register('g', hook)
+    nb = 0
+    with hm.activate('g'):
+        for b, batch in enumerate(DGDataLoader(dg, batch_size=bs, hook_manager=hm)):
+            nid, nt, nx = batch.nbr_nids[0], batch.nbr_edge_time[0], batch.nbr_edge_x[0]
+            assert nid.shape == (3 * batch.edge_src.numel(), k)
+            got = [torch_checksum(nid), torch_checksum(nt), torch_checksum(nx)]
+            want = z['patched_csum'][differs[b]] if b in differs else z['csum'][b]
+            assert got == [int(v) for v in want], f'batch {b} ({mode})'
+            if f'b{b}_nid' in z.files and b not in differs:
+                assert np.array_equal(nid.cpu().numpy(), z[f'b{b}_nid'])
+                assert np.array_equal(nt.cpu().numpy(), z[f'b{b}_nt'])
+            nb += 1
+            if mode == 'windowed':
+                assert isinstance(hook._win, dict) and hook._win['pub'] is not None
+    assert nb == len(z['csum']) == 788
 
 
 def test_realistic_timestamps_r_domain():

@@ -562,3 +562,35 @@ def test_uniform_oracle_reproduces_the_reference_random_sample_stream(path):
                 assert np.array_equal(nt, z[f'b{b}_h{h}_nt'])
                 assert np.array_equal(nx, z[f'b{b}_h{h}_nx'])
     assert subsampled > 20
+
+
+def test_c_oracle_equals_the_unmodified_reference_on_the_config1_epoch():
+    """BASELINE configs[0] at full size: the C ring oracle against what the unmodified reference
+    put on every batch of the wiki-shaped epoch (tests/golden/make_golden_config1.py; seeds
+    src + dst + the reference sampler's negatives, k=10, bs=200).  The stream lies outside the
+    reference's int32 sort-key domain; on the batches the generator lists in `differs_from_ideal`
+    (1 of 788) the expectation is the reference with its `.long()` fix."""
+    import os
+
+    from oracle.c_oracle import CRing, checksum_np
+    from tests._golden import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, 'config1_wiki_epoch.npz'))
+    E, N, D, bs, k = (int(z[n]) for n in ('E', 'N', 'D', 'bs', 'k'))
+    rng = np.random.default_rng(int(z['seed']))
+    src = rng.integers(0, 8227, E).astype(np.int32)
+    dst = rng.integers(8227, N, E).astype(np.int32)
+    t = np.sort(rng.integers(0, 2_678_374, E)).astype(np.int64)
+    x = rng.standard_normal((E, D)).astype(np.float32)
+    assert [checksum_np(v) for v in (src, dst, t, x)] == [int(v) for v in z['input_csum']]
+    differs = {int(b): i for i, b in enumerate(z['differs_from_ideal'])}
+    neg = z['neg']
+    oracle = CRing(N, [k], D)
+    for b, lo in enumerate(range(0, E, bs)):
+        hi = min(lo + bs, E)
+        seeds = np.concatenate([src[lo:hi], dst[lo:hi], neg[lo:hi]]).astype(np.int32)
+        w = oracle.hook_call(seeds, np.concatenate([t[lo:hi]] * 3), src[lo:hi], dst[lo:hi],
+                             t[lo:hi], x[lo:hi])[0]
+        want = z['patched_csum'][differs[b]] if b in differs else z['csum'][b]
+        assert [checksum_np(v) for v in w[2:]] == [int(v) for v in want], f'batch {b}'
+        if f'b{b}_nid' in z.files and b not in differs:
+            assert np.array_equal(w[2], z[f'b{b}_nid']) and np.array_equal(w[3], z[f'b{b}_nt'])

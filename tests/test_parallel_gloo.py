@@ -112,6 +112,63 @@ def test_merge_node_memory_world_size_2_gloo(tmp_path):
             assert torch.equal(z['mem'][i], z['base_mem'][i]) and z['lu'][i] == z['base_lu'][i]
 
 
+def _join_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    """join_node_memory (touched rows packed, ONE all-gather, scatter in rank order) must leave
+    what the dense merge leaves; rank `world - 1` touches nothing when world == 3."""
+    from tgm_b200.parallel import join_node_memory, merge_node_memory
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        N, M = 61, 8
+        g = torch.Generator().manual_seed(0)
+        base_mem = torch.randn(N, M, generator=g)
+        base_lu = torch.randint(0, 100, (N,), generator=g)
+        idx = torch.arange(N)
+        touched = (idx % 3 == rank) | (idx % 7 == 0) | ((idx % 11 == 0) & (rank == 1))
+        if world == 3 and rank == 2:
+            touched = torch.zeros(N, dtype=torch.bool)
+        mem, lu = base_mem.clone(), base_lu.clone()
+        mem[touched] = 1000.0 * (rank + 1) + idx[touched, None].float() + torch.arange(M).float()
+        lu[touched] = 1000 * (rank + 1) + idx[touched]
+        dense_mem, dense_lu = mem.clone(), lu.clone()
+        merge_node_memory(dense_mem, dense_lu, touched)
+        info = join_node_memory(mem, lu, idx[touched].to(torch.int32))
+        assert torch.equal(mem, dense_mem) and torch.equal(lu, dense_lu)
+        assert info['counts'][rank] == int(touched.sum()) and info['row_bytes'] == 16 + 4 * M
+        assert info['recv_bytes'] == sum(info['counts']) * info['row_bytes']
+        ref = [torch.empty_like(mem) for _ in range(world)]
+        dist.all_gather(ref, mem)
+        assert all(torch.equal(r, mem) for r in ref)
+        if rank == 0:
+            torch.save({'mem': mem, 'lu': lu, 'base_mem': base_mem, 'base_lu': base_lu,
+                        'counts': info['counts']}, os.path.join(out_dir, 'joined.pt'))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_join_node_memory_gloo(tmp_path, world):
+    mp.spawn(_join_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    z = torch.load(tmp_path / 'joined.pt')
+    for i in range(61):
+        owners = [r for r in range(world) if not (world == 3 and r == 2) and
+                  ((i % 3 == r) or (i % 7 == 0) or (i % 11 == 0 and r == 1))]
+        if owners:
+            r = max(owners)  # the later time shard wins
+            assert z['mem'][i, 0] == 1000.0 * (r + 1) + i and z['lu'][i] == 1000 * (r + 1) + i
+        else:
+            assert torch.equal(z['mem'][i], z['base_mem'][i]) and z['lu'][i] == z['base_lu'][i]
+    assert len(z['counts']) == world and (world == 2 or z['counts'][2] == 0)
+
+
+def test_join_node_memory_is_a_no_op_outside_torch_distributed():
+    from tgm_b200.parallel import join_node_memory
+    mem, lu = torch.randn(5, 4), torch.arange(5)
+    want = mem.clone()
+    info = join_node_memory(mem, lu, torch.tensor([1, 3], dtype=torch.int32))
+    assert torch.equal(mem, want) and info['counts'] == [2] and info['recv_bytes'] == 0
+
+
 def _grad_worker(rank: int, world: int, port: int, out_dir: str) -> None:
     from tgm_b200.parallel import average_gradients
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))

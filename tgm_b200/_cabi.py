@@ -81,6 +81,23 @@ SIGNATURES = {
     'tgm_csr_sample_edges_host': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_int, c_void_p]),
+    'tgm_csr_sample_edges_ids': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_int,
+                                         c_void_p, c_void_p, c_void_p, c_void_p]),
+    'tgm_csr_sample_edges_mean': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_int,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'tgm_csr_sample_edges_host_ids': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32,
+                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                              c_void_p, c_int, c_void_p]),
+    'tgm_csr_sample_edges_host_mean': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32,
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_void_p, c_int, c_void_p]),
+    'tgm_join_row_bytes': (c_int64, [c_int32]),
+    'tgm_join_pack': (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_int64, c_void_p,
+                              c_void_p]),
+    'tgm_join_scatter': (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+                                 c_void_p]),
+    'tgm_negatives_window': (c_int, [c_uint64, c_uint64, c_int64, c_int64, c_int64, c_int64,
+                                     c_void_p, c_void_p]),
     'tgm_frontier_compact': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'tgm_masked_mean': (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p,
                                 c_void_p]),

@@ -31,4 +31,5 @@ class DGBatch:
             if isinstance(v, (list, tuple)):
                 return f'{type(v).__name__}({"|".join(sorted({show(u) for u in v}))} x{len(v)})'
             return type(v).__name__
-        return 'DGBatch(' + ', '.join(f'{k} = {show(v)}' for k, v in vars(self).items()) + ')'
+        return 'DGBatch(' + ', '.join(f'{k} = {show(v)}' for k, v in vars(self).items()
+                                       if not k.startswith('_')) + ')'

@@ -3,8 +3,8 @@
 API = tgm/core/_storage/base.py:10-118 (DGSliceTracker, DGStorageBase and its getters, same
 names / argument meaning / return dtypes).  `DeviceCOOStorage` replaces DGStorageArrayBackend
 (tgm/core/_storage/backends/array_backend.py:15-321): the time-sorted edge arrays live in HBM
-behind a `tgm_store` handle (include/tgm_b200.h), a slice is two O(log E) binary searches on a
-host mirror of the timestamps plus a pointer offset, and batch materialisation is a zero-copy
+behind a `tgm_store` handle (include/tgm_b200.h), a slice is two O(log E) binary searches over
+the timestamps plus a pointer offset, and batch materialisation is a zero-copy
 view -- the reference's per-batch O(E) boolean masks (:59,:264) and per-property H2D copies
 (tgm/core/graph.py:232-263) are gone.
 """
@@ -95,12 +95,12 @@ class DeviceCOOStorage(DGStorageBase):
         self._D = 0 if data.edge_x is None else int(data.edge_x.shape[1])
         self._num_nodes = int(data.num_nodes)
         self._edge_only = data.time.shape[0] == self._E  # event index == edge index
-        self._time_np = data.time.numpy()
+        self._time_np_cache = data.time.numpy()
         self._edge_pos_np = None if self._edge_only else data.edge_mask.numpy()
         edge_time = data.time if self._edge_only else data.time[data.edge_mask]
         self._edge_time_host = edge_time.contiguous()
         self._handle = ctypes.c_void_p()
-        self._src = self._dst = self._t = self._x = None
+        self._src = self._dst = self._t = self._x = self._edge_type = None
         self._node_cache: dict = {}
 
         src = data.edge_index[:, 0].contiguous()
@@ -147,8 +147,10 @@ class DeviceCOOStorage(DGStorageBase):
         self._E, self._D = int(src.numel()), 0 if x is None else int(x.shape[1])
         self._num_nodes = int(num_nodes)
         self._edge_only = True
-        self._edge_time_host = t.cpu()
-        self._time_np = self._edge_time_host.numpy()
+        # no host mirror of the timestamps (800 MB at 1e8 edges): slice bounds are searched on the
+        # device; `_time_np` reads one back on first use (get_num_timestamps on a view)
+        self._edge_time_host = None
+        self._time_np_cache = None
         self._edge_pos_np = None
         self._node_cache = {}
         self._src, self._dst, self._t = src.contiguous(), dst.contiguous(), t.contiguous()
@@ -158,8 +160,14 @@ class DeviceCOOStorage(DGStorageBase):
         _cabi.check(_cabi.lib.tgm_store_create(
             ctypes.byref(self._handle), self._src.data_ptr(), self._dst.data_ptr(),
             self._t.data_ptr(), _cabi.ptr(self._x), self._E, self._D, self._num_nodes,
-            self._device.index, _cabi.TGM_MEM_DEVICE, self._edge_time_host.data_ptr()))
+            self._device.index, _cabi.TGM_MEM_DEVICE, None))
         return self
+
+    @property
+    def _time_np(self):
+        if self._time_np_cache is None:
+            self._time_np_cache = self._t.cpu().numpy()
+        return self._time_np_cache
 
     def __del__(self, _destroy=_cabi.lib.tgm_store_destroy) -> None:
         h = getattr(self, '_handle', None)
@@ -262,13 +270,18 @@ class DeviceCOOStorage(DGStorageBase):
                 None if self._x is None else self._x[lo:hi])
 
     # -- getters --------------------------------------------------------------------------
+    def _time_at(self, i: int) -> int:
+        if self._time_np_cache is None:  # adopted device stream: read the one word
+            return int(self._t[i])
+        return int(self._time_np_cache[i])
+
     def get_start_time(self, slice: DGSliceTracker) -> Optional[int]:
         lb, ub = self._event_bounds(slice)
-        return None if lb >= ub else int(self._time_np[lb])
+        return None if lb >= ub else self._time_at(lb)
 
     def get_end_time(self, slice: DGSliceTracker) -> Optional[int]:
         lb, ub = self._event_bounds(slice)
-        return None if lb >= ub else int(self._time_np[ub - 1])
+        return None if lb >= ub else self._time_at(ub - 1)
 
     def get_num_events(self, slice: DGSliceTracker) -> int:
         lb, ub = self._event_bounds(slice)

@@ -19,6 +19,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <new>
 
@@ -41,12 +42,11 @@ struct tgm_csr {
   static constexpr int kTickets = 64;
   unsigned long long *ticket = nullptr;
   mutable unsigned launches = 0;
-  // device staging of the host-buffer entry point: one output block per slot, grown on demand
+  // device staging of the host-buffer entry points: per slot one block per output kind
+  // (nid, t, x, eid, mean), grown on demand
   struct Stage {
-    int32_t *nid = nullptr;
-    int64_t *t = nullptr;
-    float *x = nullptr;
-    int64_t cells = 0;  // capacity in (seed, slot) cells
+    void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[5] = {0, 0, 0, 0, 0};
   } stage[TGM_HOST_SLOTS];
   ~tgm_csr() {
     if (device >= 0) {
@@ -56,18 +56,16 @@ struct tgm_csr {
       cudaFree(anchors);
       cudaFree(xrows);
       cudaFree(ticket);
-      for (auto &st : stage) {
-        cudaFree(st.nid);
-        cudaFree(st.t);
-        cudaFree(st.x);
-      }
+      for (auto &st : stage)
+        for (void *q : st.p) cudaFree(q);
     }
   }
 };
 
 // 0: feature rows copied by the warp (LSU), 1: by the TMA unit (cp.async.bulk staging)
 static int g_csr_feature_copy = 1;
-static int g_csr_tma_ctas_per_sm = 0;  // 0 = as many as shared memory allows (<= TGM_FAST_MIN_BLOCKS)
+static int g_csr_tma_ctas_per_sm = 0;
+static int g_trace = 0;  // tgm_set_option("trace", 1): phase timings of tgm_csr_build on stderr  // 0 = as many as shared memory allows (<= TGM_FAST_MIN_BLOCKS)
 
 namespace {
 
@@ -123,10 +121,32 @@ __global__ void csr_rowptr_kernel(const uint32_t *__restrict__ keys, int64_t n, 
   }
 }
 
-__global__ void csr_entries_kernel(const uint32_t *__restrict__ vals, int64_t n,
+// Run heads of the sorted list: position j starts a new (node, batch) run.  hp[j] = j for heads,
+// 0 otherwise; an inclusive max-scan then gives every position the start of its run -- which is
+// the anchor of every edge endpoint in that run (first entry of the node that belongs to the
+// edge's own batch), with no search.
+__global__ void csr_heads_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                 int64_t n, uint32_t bs, uint32_t *__restrict__ hp) {
+  for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n;
+       j += int64_t(gridDim.x) * blockDim.x) {
+    bool head = j == 0;
+    if (!head)
+      head = keys[j] != keys[j - 1] || (vals[j] >> 1) / bs != (vals[j - 1] >> 1) / bs;
+    hp[j] = head ? uint32_t(j) : 0u;
+  }
+}
+
+struct MaxU32 {
+  __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+
+// entries in adjacency order + (optionally) the anchor table, scattered back to stream order
+__global__ void csr_entries_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                   const uint32_t *__restrict__ run_start, int64_t n,
                                    const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
-                                   const int64_t *__restrict__ t, int64_t e_start,
-                                   Entry *__restrict__ entries) {
+                                   const int64_t *__restrict__ t, const int64_t *__restrict__ rowptr,
+                                   int64_t e_start, int64_t Ew, Entry *__restrict__ entries,
+                                   uint2 *__restrict__ anchors) {
   for (int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n;
        j += int64_t(gridDim.x) * blockDim.x) {
     const uint32_t val = vals[j];
@@ -136,6 +156,10 @@ __global__ void csr_entries_kernel(const uint32_t *__restrict__ vals, int64_t n,
     en.eid = int32_t(e_start + l);
     en.t = t[l];
     entries[j] = en;
+    if (anchors) {
+      const uint32_t rs = run_start[j];
+      anchors[(val & 1u) ? Ew + l : l] = make_uint2(rs, rs - uint32_t(__ldg(rowptr + keys[j])));
+    }
   }
 }
 
@@ -149,6 +173,7 @@ __device__ __forceinline__ int64_t lower_bound_eid(const Entry *__restrict__ ent
   return lo;
 }
 
+// search-based anchors (directed adjacencies: a dst endpoint owns no entry in its batch's run)
 __global__ void csr_anchor_kernel(const Entry *__restrict__ entries,
                                   const int64_t *__restrict__ rowptr,
                                   const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
@@ -341,7 +366,7 @@ __device__ __forceinline__ void emit_fast(const float4 *__restrict__ x4, int D4,
                                           int nwin, int64_t q, int k, int64_t s, const Entry &cur,
                                           int32_t *__restrict__ out_nid,
                                           int64_t *__restrict__ out_t, float4 *__restrict__ out_x4,
-                                          int lane) {
+                                          int lane, int32_t *__restrict__ out_eid = nullptr) {
   const unsigned m = __ballot_sync(0xffffffffu, lane < nwin && cur.t < q);
   const int last = m ? 31 - __clz(m) : -1;  // recency.py:267-281
   const int nvalid = last + 1 < k ? last + 1 : k;
@@ -349,10 +374,12 @@ __device__ __forceinline__ void emit_fast(const float4 *__restrict__ x4, int D4,
   const int srcl = (first + lane - pad) & 31;
   const int32_t nbr = __shfl_sync(0xffffffffu, cur.nbr, srcl);
   const int64_t tt = shfl_i64(cur.t, srcl);
+  const int32_t eid = __shfl_sync(0xffffffffu, cur.eid, srcl);
   if (lane < k) {  // right-aligned, left-padded with (-1, 0) (:287-319)
     const bool v = lane >= pad;
-    out_nid[s * k + lane] = v ? nbr : TGM_PADDED_NODE_ID;
-    out_t[s * k + lane] = v ? tt : 0;
+    if (out_nid) out_nid[s * k + lane] = v ? nbr : TGM_PADDED_NODE_ID;
+    if (out_t) out_t[s * k + lane] = v ? tt : 0;
+    if (out_eid) out_eid[s * k + lane] = v ? eid : -1;
   }
   if (D4 > 0) {
     float4 *o4 = out_x4 + s * int64_t(k) * D4;
@@ -472,6 +499,161 @@ csr_sample_fast_kernel(const Entry *__restrict__ entries, const int64_t *__restr
     }
     const int nseeds = S - s_base < 32 ? int(S - s_base) : 32;
     walk_chunk(entries, x4, D4, mine, s_base, nseeds, k, out_nid, out_t, out_x4, lane);
+  }
+}
+
+// ---- hop-0 forms that never materialise the (S, k, D) feature block ---------------------------
+// Where a seed's window comes from: the prebuilt anchor table, or (SEARCH) the seed is read from
+// the store's src/dst slab and its history cut is found by a private binary search -- the form the
+// host-buffer entry points use, so that the slab they upload is what the kernel consumes.
+struct EdgeSeedArgs {
+  const uint2 *anchors;
+  const int64_t *rowptr;
+  const int32_t *src, *dst;  // store slabs, offset to the adjacency's e_start
+  const int64_t *t;
+  int64_t Ew, l_lo, l_hi, e_start;
+  uint32_t bs;
+  int32_t N;
+};
+
+template <bool SEARCH>
+__device__ __forceinline__ SeedWin resolve_edge_seed(const Entry *__restrict__ entries,
+                                                     const EdgeSeedArgs &a, int64_t s, int B) {
+  // row s -> (edge, endpoint): batch jb owns rows [2*bs*jb, ...), src seeds then dst seeds
+  const int64_t bs = a.bs;
+  const int64_t jb = s / (2 * bs);
+  const int64_t bstart = a.l_lo + jb * bs;
+  const int64_t nb = a.l_hi - bstart < bs ? a.l_hi - bstart : bs;
+  const int64_t rr = s - jb * 2 * bs;
+  const bool side = rr >= nb;
+  const int64_t l = bstart + (side ? rr - nb : rr);
+  SeedWin w{0, 0, __ldg(a.t + l)};
+  if (SEARCH) {
+    const int32_t v = side ? __ldg(a.dst + l) : __ldg(a.src + l);
+    if (v >= 0 && v < a.N) {
+      const int64_t lo = __ldg(a.rowptr + v), hi = __ldg(a.rowptr + v + 1);
+      const int64_t pos = lower_bound_eid(entries, lo, hi, a.e_start + bstart);
+      w.wstart = pos - B > lo ? pos - B : lo;
+      w.nwin = int(pos - w.wstart);
+    }
+  } else {
+    const uint2 an = __ldg(a.anchors + (side ? a.Ew + l : l));
+    w.nwin = an.y < uint32_t(B) ? int(an.y) : B;
+    w.wstart = int64_t(an.x) - w.nwin;
+  }
+  return w;
+}
+
+// ids only: (nid, t, eid) per slot, 16 bytes -- what a caller that owns the feature table lacks
+constexpr int kIdsMinBlocks = 4;  // 64 registers: no spills in the walk / mean loops
+
+template <bool SEARCH>
+__global__ void __launch_bounds__(kFastThreads, kIdsMinBlocks)
+csr_sample_edges_ids_kernel(const Entry *__restrict__ entries, const EdgeSeedArgs a, int B, int k,
+                            int32_t *__restrict__ out_nid, int64_t *__restrict__ out_t,
+                            int32_t *__restrict__ out_eid, unsigned long long *__restrict__ ticket) {
+  const int lane = threadIdx.x & 31;
+  const int64_t S = 2 * (a.l_hi - a.l_lo);
+  const int64_t nchunks = (S + 31) >> 5;
+  const int64_t wstride = int64_t(gridDim.x) * (kFastThreads >> 5);
+  for (int64_t ch = int64_t(blockIdx.x) * (kFastThreads >> 5) + (threadIdx.x >> 5); ch < nchunks;
+       ch = next_chunk(ticket, wstride, lane)) {
+    const int64_t s_base = ch << 5, s = s_base + lane;
+    SeedWin mine{0, 0, 0};
+    if (s < S) mine = resolve_edge_seed<SEARCH>(entries, a, s, B);
+    const int nseeds = S - s_base < 32 ? int(S - s_base) : 32;
+    int64_t wstart = shfl_i64(mine.wstart, 0);
+    int nwin = __shfl_sync(0xffffffffu, mine.nwin, 0);
+    Entry cur = load_window_entry(entries, wstart, nwin, lane);
+    for (int i = 0; i < nseeds; ++i) {
+      const int64_t q = shfl_i64(mine.q, i);
+      const int nxt = i + 1 < nseeds ? i + 1 : i;
+      const int64_t wstart_n = shfl_i64(mine.wstart, nxt);
+      const int nwin_n = __shfl_sync(0xffffffffu, mine.nwin, nxt);
+      const Entry ahead = load_window_entry(entries, wstart_n, nwin_n, lane);  // one seed ahead
+      emit_fast(nullptr, 0, wstart, nwin, q, k, s_base + i, cur, out_nid, out_t, nullptr, lane,
+                out_eid);
+      cur = ahead;
+      wstart = wstart_n;
+      nwin = nwin_n;
+    }
+  }
+}
+
+// Fused sample + masked mean (examples/linkproppred/graphmixer.py:131-135 over the rows
+// _get_recency_neighbors returns, recency.py:239-321): out_mean[s, :] = sum of the seed's valid
+// feature rows / max(1, #valid), accumulated oldest to newest in fp32 -- bit-identical to
+// tgm_masked_mean over tgm_csr_sample_edges' output, without the (S, k, D) block ever existing.
+// Phase 1 walks the 32 seeds of a chunk like the kernels above (ids/times/eids are optional
+// outputs); lane i keeps seed i's first valid row and count.  Phase 2: groups of G lanes (G = the
+// power of two >= D/4, <= 32) take one seed each, lane c of a group owns float4 column c and adds
+// the rows in order; the row loads are independent, so several are in flight per lane.
+template <bool SEARCH>
+__global__ void __launch_bounds__(kFastThreads, kIdsMinBlocks)
+csr_sample_edges_mean_kernel(const Entry *__restrict__ entries, const EdgeSeedArgs a,
+                             const float4 *__restrict__ x4, int D4, int G, int B, int k,
+                             int32_t *__restrict__ out_nid, int64_t *__restrict__ out_t,
+                             int32_t *__restrict__ out_eid, float4 *__restrict__ out_mean4,
+                             unsigned long long *__restrict__ ticket) {
+  const int lane = threadIdx.x & 31;
+  const int64_t S = 2 * (a.l_hi - a.l_lo);
+  const int64_t nchunks = (S + 31) >> 5;
+  const int64_t wstride = int64_t(gridDim.x) * (kFastThreads >> 5);
+  const int per = 32 / G, sub = lane / G, col = lane - sub * G;
+  const bool want_ids = out_nid || out_t || out_eid;
+  for (int64_t ch = int64_t(blockIdx.x) * (kFastThreads >> 5) + (threadIdx.x >> 5); ch < nchunks;
+       ch = next_chunk(ticket, wstride, lane)) {
+    const int64_t s_base = ch << 5, s = s_base + lane;
+    SeedWin mine{0, 0, 0};
+    if (s < S) mine = resolve_edge_seed<SEARCH>(entries, a, s, B);
+    const int nseeds = S - s_base < 32 ? int(S - s_base) : 32;
+    int64_t wstart = shfl_i64(mine.wstart, 0);
+    int nwin = __shfl_sync(0xffffffffu, mine.nwin, 0);
+    Entry cur = load_window_entry(entries, wstart, nwin, lane);
+    int64_t row0 = 0;  // lane i: first valid feature row of seed i
+    int nv = 0;        //         and how many follow
+    for (int i = 0; i < nseeds; ++i) {
+      const int64_t q = shfl_i64(mine.q, i);
+      const int nxt = i + 1 < nseeds ? i + 1 : i;
+      const int64_t wstart_n = shfl_i64(mine.wstart, nxt);
+      const int nwin_n = __shfl_sync(0xffffffffu, mine.nwin, nxt);
+      const Entry ahead = load_window_entry(entries, wstart_n, nwin_n, lane);
+      const unsigned m = __ballot_sync(0xffffffffu, lane < nwin && cur.t < q);
+      const int last = m ? 31 - __clz(m) : -1;
+      const int nvalid = last + 1 < k ? last + 1 : k;
+      const int first = last + 1 - nvalid;
+      if (lane == i) {
+        row0 = wstart + first;
+        nv = nvalid;
+      }
+      if (want_ids)
+        emit_fast(nullptr, 0, wstart, nwin, q, k, s_base + i, cur, out_nid, out_t, nullptr, lane,
+                  out_eid);
+      cur = ahead;
+      wstart = wstart_n;
+      nwin = nwin_n;
+    }
+    for (int g0 = 0; g0 < nseeds; g0 += per) {
+      const int si = g0 + sub;
+      const int64_t r0 = shfl_i64(row0, si & 31);
+      const int n = __shfl_sync(0xffffffffu, nv, si & 31);
+      if (si >= nseeds) continue;
+      const float den = float(n > 1 ? n : 1);
+      for (int c = col; c < D4; c += G) {
+        const float4 *p = x4 + r0 * D4 + c;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int r = 0; r < n; ++r) {
+          const float4 v = ldg_stream_f4(p + int64_t(r) * D4);
+          acc.x = __fadd_rn(acc.x, v.x);
+          acc.y = __fadd_rn(acc.y, v.y);
+          acc.z = __fadd_rn(acc.z, v.z);
+          acc.w = __fadd_rn(acc.w, v.w);
+        }
+        out_mean4[(s_base + si) * D4 + c] =
+            make_float4(acc.x / den, acc.y / den, acc.z / den, acc.w / den);
+      }
+    }
   }
 }
 
@@ -798,6 +980,21 @@ csr_sample_tma_kernel(const Entry *__restrict__ entries, const float *__restrict
   }
 }
 
+// wall-clock phase marks of a build (each mark synchronises the stream; only when tracing)
+struct Trace {
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point last;
+  explicit Trace(cudaStream_t s) : st(s), last(std::chrono::steady_clock::now()) {}
+  void mark(const char *what) {
+    if (!g_trace) return;
+    cudaStreamSynchronize(st);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[tgm_csr_build] %-16s %8.2f ms\n", what,
+            std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+  }
+};
+
 int bits_for(uint32_t max_value) {
   int b = 1;
   while (b < 32 && (max_value >> b) != 0) ++b;
@@ -834,14 +1031,8 @@ extern "C" int tgm_csr_build(tgm_csr **out, const tgm_store *store, int64_t e_st
   const int64_t n = c->n, Ew = c->Ew;
 
   uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr;
-  void *cub_tmp = nullptr;
-  auto cleanup_tmp = [&]() {
-    cudaFree(keys_a);
-    cudaFree(keys_b);
-    cudaFree(vals_a);
-    cudaFree(vals_b);
-    cudaFree(cub_tmp);
-  };
+  unsigned char *work = nullptr;
+  auto cleanup_tmp = [&]() { cudaFree(work); };
   auto bail = [&](int code) {
     cleanup_tmp();
     delete c;
@@ -853,6 +1044,7 @@ extern "C" int tgm_csr_build(tgm_csr **out, const tgm_store *store, int64_t e_st
     if (_e != cudaSuccess) return bail(cuda_fail(_e, #expr, __FILE__, __LINE__));   \
   } while (0)
 
+  Trace tr(st);
   CSR_CUDA(cudaMalloc(&c->rowptr, size_t(c->N + 1) * 8));
   CSR_CUDA(cudaMalloc(&c->ticket, tgm_csr::kTickets * sizeof(unsigned long long)));
   if (n == 0) {
@@ -865,10 +1057,21 @@ extern "C" int tgm_csr_build(tgm_csr **out, const tgm_store *store, int64_t e_st
   CSR_CUDA(cudaMalloc(&c->entries, nn * sizeof(Entry)));
   CSR_CUDA(cudaMalloc(&c->anchors, size_t(2 * Ew) * sizeof(uint2)));
   if (c->colocate) CSR_CUDA(cudaMalloc(&c->xrows, nn * size_t(c->D) * 4));
-  CSR_CUDA(cudaMalloc(&keys_a, nn * 4));
-  CSR_CUDA(cudaMalloc(&keys_b, nn * 4));
-  CSR_CUDA(cudaMalloc(&vals_a, nn * 4));
-  CSR_CUDA(cudaMalloc(&vals_b, nn * 4));
+  // one workspace for every temporary: 4 key/value arrays + the CUB scratch
+  const int end_bit = bits_for(uint32_t(c->N - 1));
+  size_t sort_bytes = 0, scan_bytes = 0;
+  CSR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys_a, keys_b, vals_a, vals_b, n, 0,
+                                           end_bit, st));
+  CSR_CUDA(cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, keys_a, vals_a, MaxU32(), n, st));
+  const size_t arr = (nn * 4 + 255) & ~size_t(255);
+  const size_t tmp_bytes = std::max(sort_bytes, scan_bytes);
+  CSR_CUDA(cudaMalloc(&work, 4 * arr + tmp_bytes + 256));
+  keys_a = reinterpret_cast<uint32_t *>(work);
+  keys_b = reinterpret_cast<uint32_t *>(work + arr);
+  vals_a = reinterpret_cast<uint32_t *>(work + 2 * arr);
+  vals_b = reinterpret_cast<uint32_t *>(work + 3 * arr);
+  void *cub_tmp = work + 4 * arr;
+  tr.mark("alloc");
 
   const int32_t *src = store->src + e_start, *dst = store->dst + e_start;
   const int64_t *t = store->t + e_start;
@@ -876,25 +1079,36 @@ extern "C" int tgm_csr_build(tgm_csr **out, const tgm_store *store, int64_t e_st
   csr_keys_kernel<<<grid_for(Ew, threads, 8), threads, 0, st>>>(src, dst, t, Ew, batch_size,
                                                                 c->directed, keys_a, vals_a);
   CSR_CUDA(cudaGetLastError());
+  tr.mark("keys");
 
   // stable LSD radix sort by node id; the input order already is the chronological order
-  const int end_bit = bits_for(uint32_t(c->N - 1));
-  size_t tmp_bytes = 0;
-  CSR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, vals_a, vals_b, n, 0,
+  size_t tb = tmp_bytes;
+  CSR_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, tb, keys_a, keys_b, vals_a, vals_b, n, 0,
                                            end_bit, st));
-  CSR_CUDA(cudaMalloc(&cub_tmp, tmp_bytes ? tmp_bytes : 1));
-  CSR_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp_bytes, keys_a, keys_b, vals_a, vals_b, n, 0,
-                                           end_bit, st));
+  tr.mark("sort");
 
   csr_rowptr_kernel<<<grid_for(int64_t(c->N) + 1, threads, 8), threads, 0, st>>>(keys_b, n, c->N,
                                                                                  c->rowptr);
   CSR_CUDA(cudaGetLastError());
-  csr_entries_kernel<<<grid_for(n, threads, 8), threads, 0, st>>>(vals_b, n, src, dst, t, e_start,
-                                                                  c->entries);
+  const bool scan_anchors = !c->directed && batch_size < (int64_t(1) << 32);
+  if (scan_anchors) {
+    csr_heads_kernel<<<grid_for(n, threads, 8), threads, 0, st>>>(keys_b, vals_b, n,
+                                                                  uint32_t(batch_size), keys_a);
+    CSR_CUDA(cudaGetLastError());
+    tb = tmp_bytes;
+    CSR_CUDA(cub::DeviceScan::InclusiveScan(cub_tmp, tb, keys_a, vals_a, MaxU32(), n, st));
+  }
+  tr.mark("rowptr+runs");
+  csr_entries_kernel<<<grid_for(n, threads, 8), threads, 0, st>>>(
+      keys_b, vals_b, vals_a, n, src, dst, t, c->rowptr, e_start, Ew, c->entries,
+      scan_anchors ? c->anchors : nullptr);
   CSR_CUDA(cudaGetLastError());
-  csr_anchor_kernel<<<grid_for(2 * Ew, threads, 8), threads, 0, st>>>(
-      c->entries, c->rowptr, src, dst, Ew, batch_size, e_start, c->N, c->anchors);
-  CSR_CUDA(cudaGetLastError());
+  if (!scan_anchors) {
+    csr_anchor_kernel<<<grid_for(2 * Ew, threads, 8), threads, 0, st>>>(
+        c->entries, c->rowptr, src, dst, Ew, batch_size, e_start, c->N, c->anchors);
+    CSR_CUDA(cudaGetLastError());
+  }
+  tr.mark("entries+anchors");
   if (c->colocate) {
     const bool vec4 = (c->D % 4 == 0) && aligned16(store->x) && aligned16(c->xrows);
     if (vec4)
@@ -906,8 +1120,10 @@ extern "C" int tgm_csr_build(tgm_csr **out, const tgm_store *store, int64_t e_st
     CSR_CUDA(cudaGetLastError());
   }
   CSR_CUDA(cudaStreamSynchronize(st));
+  tr.mark("gather_x");
 #undef CSR_CUDA
   cleanup_tmp();
+  tr.mark("free");
   *out = c;
   return TGM_OK;
 }
@@ -1073,6 +1289,118 @@ extern "C" int tgm_csr_sample_edges(const tgm_csr *c, int64_t e_lo, int64_t e_hi
 }
 
 
+namespace {
+// common checks + argument block of the hop-0 forms without a feature block
+int edge_seed_args(const tgm_csr *c, const char *who, int64_t e_lo, int64_t e_hi, int32_t B,
+                   int32_t k, EdgeSeedArgs *a) {
+  if (c == nullptr) return fail(TGM_ERR_INVALID, std::string(who) + ": csr is NULL");
+  const int64_t l_lo = e_lo - c->e_start, l_hi = e_hi - c->e_start;
+  if (!(l_lo >= 0 && l_lo <= l_hi && l_hi <= c->Ew))
+    return fail(TGM_ERR_INVALID, std::string(who) + ": [e_lo, e_hi) outside the indexed stream");
+  if (l_lo % c->bs != 0)
+    return fail(TGM_ERR_INVALID, std::string(who) + ": e_lo must sit on a batch boundary");
+  if (!(B >= 1 && B <= 32))
+    return fail(TGM_ERR_INVALID, std::string(who) + ": B must be in [1, 32]");
+  if (!(k >= 1 && k <= B)) return fail(TGM_ERR_INVALID, std::string(who) + ": k must be in [1, B]");
+  if (c->bs >= (int64_t(1) << 31))
+    return fail(TGM_ERR_INVALID, std::string(who) + ": batch_size must be < 2^31");
+  a->anchors = c->anchors;
+  a->rowptr = c->rowptr;
+  a->src = c->store->src + c->e_start;
+  a->dst = c->store->dst + c->e_start;
+  a->t = c->store->t + c->e_start;
+  a->Ew = c->Ew, a->l_lo = l_lo, a->l_hi = l_hi, a->e_start = c->e_start;
+  a->bs = uint32_t(c->bs);
+  a->N = c->N;
+  return TGM_OK;
+}
+
+int stage_reserve(tgm_csr::Stage &sg, int which, size_t bytes, cudaStream_t st) {
+  if (bytes <= sg.cap[which]) return TGM_OK;
+  TGM_CUDA(cudaStreamSynchronize(st));  // growing is the only synchronising path
+  cudaFree(sg.p[which]);
+  sg.p[which] = nullptr, sg.cap[which] = 0;
+  TGM_CUDA(cudaMalloc(&sg.p[which], bytes));
+  sg.cap[which] = bytes;
+  return TGM_OK;
+}
+
+// H2D of the caller's slab of stream edges into the store (any pointer may be NULL = resident)
+int upload_slab(const tgm_csr *c, int64_t e_lo, int64_t nE, const int32_t *h_src,
+                const int32_t *h_dst, const int64_t *h_t, const float *h_x, cudaStream_t st) {
+  const tgm_store *s = c->store;
+  const size_t D = size_t(c->D);
+  if (h_src) TGM_CUDA(cudaMemcpyAsync(const_cast<int32_t *>(s->src) + e_lo, h_src, size_t(nE) * 4,
+                                      cudaMemcpyHostToDevice, st));
+  if (h_dst) TGM_CUDA(cudaMemcpyAsync(const_cast<int32_t *>(s->dst) + e_lo, h_dst, size_t(nE) * 4,
+                                      cudaMemcpyHostToDevice, st));
+  if (h_t) TGM_CUDA(cudaMemcpyAsync(const_cast<int64_t *>(s->t) + e_lo, h_t, size_t(nE) * 8,
+                                    cudaMemcpyHostToDevice, st));
+  if (h_x && D) TGM_CUDA(cudaMemcpyAsync(const_cast<float *>(s->x) + size_t(e_lo) * D, h_x,
+                                         size_t(nE) * D * 4, cudaMemcpyHostToDevice, st));
+  return TGM_OK;
+}
+}  // namespace
+
+extern "C" int tgm_csr_sample_edges_ids(const tgm_csr *c, int64_t e_lo, int64_t e_hi, int32_t B,
+                                        int32_t k, int search, int32_t *out_nid, int64_t *out_t,
+                                        int32_t *out_eid, tgm_stream stream) {
+  EdgeSeedArgs a{};
+  int rc = edge_seed_args(c, "tgm_csr_sample_edges_ids", e_lo, e_hi, B, k, &a);
+  if (rc != TGM_OK) return rc;
+  const int64_t S = 2 * (a.l_hi - a.l_lo);
+  if (S == 0) return TGM_OK;
+  TGM_REQUIRE(out_nid || out_t || out_eid, "tgm_csr_sample_edges_ids: every output is NULL");
+  DeviceGuard g(c->device);
+  cudaStream_t st = as_stream(stream);
+  unsigned long long *ticket = nullptr;
+  rc = new_ticket(c, st, &ticket);
+  if (rc != TGM_OK) return rc;
+  const int grid = grid_for((S + 31) / 32, kFastThreads / 32, kIdsMinBlocks);
+  if (search)
+    csr_sample_edges_ids_kernel<true><<<grid, kFastThreads, 0, st>>>(c->entries, a, B, k, out_nid,
+                                                                     out_t, out_eid, ticket);
+  else
+    csr_sample_edges_ids_kernel<false><<<grid, kFastThreads, 0, st>>>(c->entries, a, B, k, out_nid,
+                                                                      out_t, out_eid, ticket);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+
+extern "C" int tgm_csr_sample_edges_mean(const tgm_csr *c, int64_t e_lo, int64_t e_hi, int32_t B,
+                                         int32_t k, int search, int32_t *out_nid, int64_t *out_t,
+                                         int32_t *out_eid, float *out_mean, tgm_stream stream) {
+  EdgeSeedArgs a{};
+  int rc = edge_seed_args(c, "tgm_csr_sample_edges_mean", e_lo, e_hi, B, k, &a);
+  if (rc != TGM_OK) return rc;
+  TGM_REQUIRE(c->D > 0 && c->D % 4 == 0 && c->colocate && aligned16(c->xrows),
+              "tgm_csr_sample_edges_mean: needs colocated feature rows with D % 4 == 0 (otherwise "
+              "tgm_csr_sample_edges + tgm_masked_mean)");
+  const int64_t S = 2 * (a.l_hi - a.l_lo);
+  if (S == 0) return TGM_OK;
+  TGM_REQUIRE(out_mean != nullptr && aligned16(out_mean),
+              "tgm_csr_sample_edges_mean: out_mean must be a 16-byte aligned array");
+  DeviceGuard g(c->device);
+  cudaStream_t st = as_stream(stream);
+  unsigned long long *ticket = nullptr;
+  rc = new_ticket(c, st, &ticket);
+  if (rc != TGM_OK) return rc;
+  const int D4 = c->D / 4;
+  int G = 1;
+  while (G < D4 && G < 32) G <<= 1;
+  const int grid = grid_for((S + 31) / 32, kFastThreads / 32, kIdsMinBlocks);
+  const float4 *x4 = reinterpret_cast<const float4 *>(c->xrows);
+  float4 *o4 = reinterpret_cast<float4 *>(out_mean);
+  if (search)
+    csr_sample_edges_mean_kernel<true><<<grid, kFastThreads, 0, st>>>(
+        c->entries, a, x4, D4, G, B, k, out_nid, out_t, out_eid, o4, ticket);
+  else
+    csr_sample_edges_mean_kernel<false><<<grid, kFastThreads, 0, st>>>(
+        c->entries, a, x4, D4, G, B, k, out_nid, out_t, out_eid, o4, ticket);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+
 // Host-buffer form: H2D of the slab, the same kernel, D2H of the outputs, all on `stream`.
 extern "C" int tgm_csr_sample_edges_host(tgm_csr *c, int64_t e_lo, int64_t e_hi, int32_t B,
                                          int32_t k, const int32_t *h_src, const int32_t *h_dst,
@@ -1090,33 +1418,88 @@ extern "C" int tgm_csr_sample_edges_host(tgm_csr *c, int64_t e_lo, int64_t e_hi,
   TGM_REQUIRE(c->D == 0 || h_out_x, "tgm_csr_sample_edges_host: h_out_x is NULL but D > 0");
   DeviceGuard g(c->device);
   cudaStream_t st = as_stream(stream);
-  const tgm_store *s = c->store;
   const size_t D = size_t(c->D);
   // the slab of the window as the caller holds it on the host (the reference keeps its arrays on
   // the CPU and copies each batch's properties to the device, tgm/core/graph.py:232-263)
-  if (h_src) TGM_CUDA(cudaMemcpyAsync(const_cast<int32_t *>(s->src) + e_lo, h_src, size_t(nE) * 4,
-                                      cudaMemcpyHostToDevice, st));
-  if (h_dst) TGM_CUDA(cudaMemcpyAsync(const_cast<int32_t *>(s->dst) + e_lo, h_dst, size_t(nE) * 4,
-                                      cudaMemcpyHostToDevice, st));
-  if (h_t) TGM_CUDA(cudaMemcpyAsync(const_cast<int64_t *>(s->t) + e_lo, h_t, size_t(nE) * 8,
-                                    cudaMemcpyHostToDevice, st));
-  if (h_x && D) TGM_CUDA(cudaMemcpyAsync(const_cast<float *>(s->x) + size_t(e_lo) * D, h_x,
-                                         size_t(nE) * D * 4, cudaMemcpyHostToDevice, st));
-  tgm_csr::Stage &sg = c->stage[slot];
-  if (cells > sg.cells) {  // growing is the only synchronising path
-    TGM_CUDA(cudaStreamSynchronize(st));
-    cudaFree(sg.nid), cudaFree(sg.t), cudaFree(sg.x);
-    sg = tgm_csr::Stage();
-    TGM_CUDA(cudaMalloc(&sg.nid, size_t(cells) * 4));
-    TGM_CUDA(cudaMalloc(&sg.t, size_t(cells) * 8));
-    if (D) TGM_CUDA(cudaMalloc(&sg.x, size_t(cells) * D * 4));
-    sg.cells = cells;
-  }
-  int rc = tgm_csr_sample_edges(c, e_lo, e_hi, B, k, sg.nid, sg.t, sg.x, stream);
+  int rc = upload_slab(c, e_lo, nE, h_src, h_dst, h_t, h_x, st);
   if (rc != TGM_OK) return rc;
-  TGM_CUDA(cudaMemcpyAsync(h_out_nid, sg.nid, size_t(cells) * 4, cudaMemcpyDeviceToHost, st));
-  TGM_CUDA(cudaMemcpyAsync(h_out_t, sg.t, size_t(cells) * 8, cudaMemcpyDeviceToHost, st));
-  if (D) TGM_CUDA(cudaMemcpyAsync(h_out_x, sg.x, size_t(cells) * D * 4, cudaMemcpyDeviceToHost, st));
+  tgm_csr::Stage &sg = c->stage[slot];
+  if ((rc = stage_reserve(sg, 0, size_t(cells) * 4, st)) != TGM_OK) return rc;
+  if ((rc = stage_reserve(sg, 1, size_t(cells) * 8, st)) != TGM_OK) return rc;
+  if (D && (rc = stage_reserve(sg, 2, size_t(cells) * D * 4, st)) != TGM_OK) return rc;
+  int32_t *d_nid = static_cast<int32_t *>(sg.p[0]);
+  int64_t *d_t = static_cast<int64_t *>(sg.p[1]);
+  float *d_x = static_cast<float *>(sg.p[2]);
+  rc = tgm_csr_sample_edges(c, e_lo, e_hi, B, k, d_nid, d_t, d_x, stream);
+  if (rc != TGM_OK) return rc;
+  TGM_CUDA(cudaMemcpyAsync(h_out_nid, d_nid, size_t(cells) * 4, cudaMemcpyDeviceToHost, st));
+  TGM_CUDA(cudaMemcpyAsync(h_out_t, d_t, size_t(cells) * 8, cudaMemcpyDeviceToHost, st));
+  if (D) TGM_CUDA(cudaMemcpyAsync(h_out_x, d_x, size_t(cells) * D * 4, cudaMemcpyDeviceToHost, st));
+  return TGM_OK;
+}
+
+// Host-buffer forms that move only what the host lacks.  Both consume the uploaded slab: the
+// kernel reads its seeds (src/dst), query times and history cuts from it (search form).
+extern "C" int tgm_csr_sample_edges_host_ids(tgm_csr *c, int64_t e_lo, int64_t e_hi, int32_t B,
+                                             int32_t k, const int32_t *h_src, const int32_t *h_dst,
+                                             const int64_t *h_t, int32_t *h_out_nid,
+                                             int64_t *h_out_t, int32_t *h_out_eid, int slot,
+                                             tgm_stream stream) {
+  TGM_REQUIRE(c != nullptr, "tgm_csr_sample_edges_host_ids: csr is NULL");
+  TGM_REQUIRE(slot >= 0 && slot < TGM_HOST_SLOTS, "tgm_csr_sample_edges_host_ids: bad slot");
+  const int64_t nE = e_hi - e_lo, cells = 2 * nE * k;
+  TGM_REQUIRE(nE >= 0 && e_lo >= 0 && e_hi <= c->store->E,
+              "tgm_csr_sample_edges_host_ids: [e_lo, e_hi) outside the store");
+  if (nE == 0) return TGM_OK;
+  TGM_REQUIRE(h_out_nid && h_out_t && h_out_eid,
+              "tgm_csr_sample_edges_host_ids: NULL output argument");
+  DeviceGuard g(c->device);
+  cudaStream_t st = as_stream(stream);
+  int rc = upload_slab(c, e_lo, nE, h_src, h_dst, h_t, nullptr, st);
+  if (rc != TGM_OK) return rc;
+  tgm_csr::Stage &sg = c->stage[slot];
+  if ((rc = stage_reserve(sg, 0, size_t(cells) * 4, st)) != TGM_OK) return rc;
+  if ((rc = stage_reserve(sg, 1, size_t(cells) * 8, st)) != TGM_OK) return rc;
+  if ((rc = stage_reserve(sg, 3, size_t(cells) * 4, st)) != TGM_OK) return rc;
+  int32_t *d_nid = static_cast<int32_t *>(sg.p[0]), *d_eid = static_cast<int32_t *>(sg.p[3]);
+  int64_t *d_t = static_cast<int64_t *>(sg.p[1]);
+  rc = tgm_csr_sample_edges_ids(c, e_lo, e_hi, B, k, 1, d_nid, d_t, d_eid, stream);
+  if (rc != TGM_OK) return rc;
+  TGM_CUDA(cudaMemcpyAsync(h_out_nid, d_nid, size_t(cells) * 4, cudaMemcpyDeviceToHost, st));
+  TGM_CUDA(cudaMemcpyAsync(h_out_t, d_t, size_t(cells) * 8, cudaMemcpyDeviceToHost, st));
+  TGM_CUDA(cudaMemcpyAsync(h_out_eid, d_eid, size_t(cells) * 4, cudaMemcpyDeviceToHost, st));
+  return TGM_OK;
+}
+
+extern "C" int tgm_csr_sample_edges_host_mean(tgm_csr *c, int64_t e_lo, int64_t e_hi, int32_t B,
+                                              int32_t k, const int32_t *h_src,
+                                              const int32_t *h_dst, const int64_t *h_t,
+                                              int32_t *h_out_nid, int64_t *h_out_t,
+                                              float *h_out_mean, int slot, tgm_stream stream) {
+  TGM_REQUIRE(c != nullptr, "tgm_csr_sample_edges_host_mean: csr is NULL");
+  TGM_REQUIRE(slot >= 0 && slot < TGM_HOST_SLOTS, "tgm_csr_sample_edges_host_mean: bad slot");
+  const int64_t nE = e_hi - e_lo, S = 2 * nE, cells = S * k;
+  TGM_REQUIRE(nE >= 0 && e_lo >= 0 && e_hi <= c->store->E,
+              "tgm_csr_sample_edges_host_mean: [e_lo, e_hi) outside the store");
+  if (nE == 0) return TGM_OK;
+  TGM_REQUIRE(h_out_mean != nullptr, "tgm_csr_sample_edges_host_mean: h_out_mean is NULL");
+  DeviceGuard g(c->device);
+  cudaStream_t st = as_stream(stream);
+  const size_t D = size_t(c->D);
+  int rc = upload_slab(c, e_lo, nE, h_src, h_dst, h_t, nullptr, st);
+  if (rc != TGM_OK) return rc;
+  tgm_csr::Stage &sg = c->stage[slot];
+  if (h_out_nid && (rc = stage_reserve(sg, 0, size_t(cells) * 4, st)) != TGM_OK) return rc;
+  if (h_out_t && (rc = stage_reserve(sg, 1, size_t(cells) * 8, st)) != TGM_OK) return rc;
+  if ((rc = stage_reserve(sg, 4, size_t(S) * D * 4 + 16, st)) != TGM_OK) return rc;
+  int32_t *d_nid = h_out_nid ? static_cast<int32_t *>(sg.p[0]) : nullptr;
+  int64_t *d_t = h_out_t ? static_cast<int64_t *>(sg.p[1]) : nullptr;
+  float *d_mean = static_cast<float *>(sg.p[4]);
+  rc = tgm_csr_sample_edges_mean(c, e_lo, e_hi, B, k, 1, d_nid, d_t, nullptr, d_mean, stream);
+  if (rc != TGM_OK) return rc;
+  if (d_nid) TGM_CUDA(cudaMemcpyAsync(h_out_nid, d_nid, size_t(cells) * 4, cudaMemcpyDeviceToHost, st));
+  if (d_t) TGM_CUDA(cudaMemcpyAsync(h_out_t, d_t, size_t(cells) * 8, cudaMemcpyDeviceToHost, st));
+  TGM_CUDA(cudaMemcpyAsync(h_out_mean, d_mean, size_t(S) * D * 4, cudaMemcpyDeviceToHost, st));
   return TGM_OK;
 }
 
@@ -1156,6 +1539,10 @@ extern "C" int tgm_set_option(const char *name, int value) {
   if (std::strcmp(name, "csr_tma_ctas_per_sm") == 0) {
     TGM_REQUIRE(value >= 0 && value <= 32, "tgm_set_option: csr_tma_ctas_per_sm must be in [0, 32]");
     g_csr_tma_ctas_per_sm = value;
+    return TGM_OK;
+  }
+  if (std::strcmp(name, "trace") == 0) {
+    g_trace = value != 0;
     return TGM_OK;
   }
   if (std::strcmp(name, "gemm_fastf32") == 0) {

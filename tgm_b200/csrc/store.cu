@@ -1,8 +1,9 @@
 // Device-resident time-sorted COO edge store + error plumbing.
 // Replaces the edge arrays / slice lookup of tgm/core/_storage/backends/array_backend.py
 // (reference tgm-team/tgm @ 5183dc9): _binary_search :301-321, get_edges :57-68,
-// get_edge_x :259-268.  A slice is two binary searches on a host mirror of the timestamps and a
-// pointer offset into the device slabs (no O(E) masks, no per-batch H2D).
+// get_edge_x :259-268.  A slice is two binary searches over the timestamps (a host mirror when the
+// caller has one, else a two-thread device search whose 16-byte answer is read back) and a pointer
+// offset into the device slabs (no O(E) masks, no per-batch H2D).
 #include "store.cuh"
 
 #include <algorithm>
@@ -43,6 +44,10 @@ extern "C" int tgm_device_count(void) {
 }
 
 tgm_store::~tgm_store() {
+  if (scratch && device >= 0) {
+    DeviceGuard g(device);
+    cudaFree(scratch);
+  }
   if (owns_device && device >= 0) {
     DeviceGuard g(device);
     cudaFree(const_cast<int32_t *>(src));
@@ -51,6 +56,32 @@ tgm_store::~tgm_store() {
     cudaFree(const_cast<float *>(x));
   }
 }
+
+namespace {
+// number of adjacent pairs out of order (0 = the stream is time-sorted)
+__global__ void store_unsorted_kernel(const int64_t *__restrict__ t, int64_t E,
+                                      unsigned long long *__restrict__ bad) {
+  unsigned long long mine = 0;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i + 1 < E;
+       i += int64_t(gridDim.x) * blockDim.x)
+    mine += t[i] > t[i + 1];
+  mine = __reduce_add_sync(0xffffffffu, unsigned(mine));
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(bad, mine);
+}
+// thread 0: first index with t >= t_lo; thread 1: first index with t > t_hi
+__global__ void store_bounds_kernel(const int64_t *__restrict__ t, int64_t E, int64_t t_lo,
+                                    int64_t t_hi, int64_t *__restrict__ out) {
+  const bool upper = threadIdx.x == 1;
+  const int64_t key = upper ? t_hi : t_lo;
+  int64_t lo = 0, hi = E;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const int64_t v = t[mid];
+    if (upper ? v <= key : v < key) lo = mid + 1; else hi = mid;
+  }
+  out[threadIdx.x] = lo;
+}
+}  // namespace
 
 extern "C" int tgm_store_create(tgm_store **out, const int32_t *src, const int32_t *dst,
                                 const int64_t *t, const float *edge_x, int64_t E, int32_t D,
@@ -74,21 +105,19 @@ extern "C" int tgm_store_create(tgm_store **out, const int32_t *src, const int32
   s->num_nodes = num_nodes;
   s->device = device;
 
-  // host mirror of the timestamps: bounds never touch the device
-  try {
-    s->t_host.resize(size_t(E));
-  } catch (...) {
-    delete s;
-    return fail(TGM_ERR_OOM, "tgm_store_create: host mirror allocation failed");
-  }
-
   auto bail = [&](int code) {
     delete s;
     return code;
   };
 
   if (mem == TGM_MEM_HOST) {
-    if (E) std::memcpy(s->t_host.data(), t, size_t(E) * sizeof(int64_t));
+    // the caller's arrays may be temporaries: the timestamps are copied into an owned mirror
+    try {
+      s->t_owned.assign(t, t + size_t(E));
+    } catch (...) {
+      return bail(fail(TGM_ERR_OOM, "tgm_store_create: host mirror allocation failed"));
+    }
+    s->t_host = s->t_owned.data();
     if (device >= 0) {
       DeviceGuard g(device);
       if (!g.ok) return bail(fail(TGM_ERR_CUDA, "tgm_store_create: cannot select device"));
@@ -113,6 +142,8 @@ extern "C" int tgm_store_create(tgm_store **out, const int32_t *src, const int32
           return bail(cuda_fail(e, "store upload", __FILE__, __LINE__));
       }
     }
+    if (!std::is_sorted(s->t_owned.begin(), s->t_owned.end()))
+      return bail(fail(TGM_ERR_INVALID, "tgm_store_create: timestamps must be non-decreasing"));
   } else {
     DeviceGuard g(device);
     if (!g.ok) return bail(fail(TGM_ERR_CUDA, "tgm_store_create: cannot select device"));
@@ -120,17 +151,22 @@ extern "C" int tgm_store_create(tgm_store **out, const int32_t *src, const int32
     s->dst = dst;
     s->t = t;
     s->x = edge_x;
-    if (E) {
-      if (t_host) {
-        std::memcpy(s->t_host.data(), t_host, size_t(E) * sizeof(int64_t));
-      } else {
-        cudaError_t e = cudaMemcpy(s->t_host.data(), t, size_t(E) * 8, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) return bail(cuda_fail(e, "timestamp read-back", __FILE__, __LINE__));
-      }
+    // t_host, when given, is BORROWED (it must outlive the store); without it the store keeps no
+    // host mirror at all: order is verified and bounds are searched on the device
+    s->t_host = t_host;
+    cudaError_t e = cudaMalloc(&s->scratch, 2 * sizeof(int64_t));
+    if (e != cudaSuccess) return bail(cuda_fail(e, "store scratch", __FILE__, __LINE__));
+    if (E > 1) {
+      e = cudaMemset(s->scratch, 0, 2 * sizeof(int64_t));
+      if (e != cudaSuccess) return bail(cuda_fail(e, "store scratch", __FILE__, __LINE__));
+      store_unsorted_kernel<<<grid_for(E - 1, 256 * 8, 8), 256>>>(
+          t, E, reinterpret_cast<unsigned long long *>(s->scratch));
+      int64_t bad = 0;
+      e = cudaMemcpy(&bad, s->scratch, sizeof bad, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) return bail(cuda_fail(e, "timestamp order check", __FILE__, __LINE__));
+      if (bad) return bail(fail(TGM_ERR_INVALID, "tgm_store_create: timestamps must be non-decreasing"));
     }
   }
-  if (!std::is_sorted(s->t_host.begin(), s->t_host.end()))
-    return bail(fail(TGM_ERR_INVALID, "tgm_store_create: timestamps must be non-decreasing"));
   *out = s;
   return TGM_OK;
 }
@@ -151,10 +187,20 @@ extern "C" int tgm_store_bounds(const tgm_store *s, int64_t t_lo, int has_lo, in
                                 int has_hi, int64_t idx_lo, int64_t idx_hi, int64_t *lb,
                                 int64_t *ub) {
   TGM_REQUIRE(s != nullptr && lb != nullptr && ub != nullptr, "tgm_store_bounds: NULL argument");
-  const auto &ts = s->t_host;
   int64_t lo = 0, hi = s->E;
-  if (has_lo) lo = std::lower_bound(ts.begin(), ts.end(), t_lo) - ts.begin();
-  if (has_hi) hi = std::upper_bound(ts.begin(), ts.end(), t_hi) - ts.begin();
+  if (s->t_host) {
+    const int64_t *ts = s->t_host, *te = s->t_host + s->E;
+    if (has_lo) lo = std::lower_bound(ts, te, t_lo) - ts;
+    if (has_hi) hi = std::upper_bound(ts, te, t_hi) - ts;
+  } else if ((has_lo || has_hi) && s->E > 0) {  // no host mirror: search on the device
+    DeviceGuard g(s->device);
+    int64_t got[2];
+    store_bounds_kernel<<<1, 2>>>(s->t, s->E, t_lo, t_hi, s->scratch);
+    TGM_LAUNCH_CHECK();
+    TGM_CUDA(cudaMemcpy(got, s->scratch, sizeof got, cudaMemcpyDeviceToHost));
+    if (has_lo) lo = got[0];
+    if (has_hi) hi = got[1];
+  }
   int64_t cl = idx_lo < 0 ? 0 : idx_lo;
   int64_t ch = idx_hi < 0 ? s->E : idx_hi;
   // clamp(x, cl, ch) = max(cl, min(ch, x))  (array_backend.py:318-320)

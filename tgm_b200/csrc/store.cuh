@@ -16,8 +16,11 @@ struct tgm_store {
   const int32_t *dst = nullptr;
   const int64_t *t = nullptr;
   const float *x = nullptr;  // [E, D] row-major, NULL when D == 0
-  // host mirror of t for O(log E) slice bounds without touching the device
-  std::vector<int64_t> t_host;
+  // host mirror of t for O(log E) slice bounds without touching the device: owned (uploaded
+  // stores), borrowed from the caller, or absent (adopted device stream: bounds search on device)
+  const int64_t *t_host = nullptr;
+  std::vector<int64_t> t_owned;
+  int64_t *scratch = nullptr;  // 2 device words: order check / device bounds
   ~tgm_store();
 };
 

@@ -90,6 +90,9 @@ class DGDataLoader:
             store._src[lo:hi], store._dst[lo:hi], store._t[lo:hi],
             None if store._x is None else store._x[lo:hi])
         batch = DGBatch(src, dst, t, x if hi > lo else None)
+        # which rows of the store these views are (hooks verify by identity that nobody replaced
+        # the tensors since, instead of re-deriving the offsets from pointers every batch)
+        batch._slab = (store, lo, hi, src, dst, t)
         if self._hook_manager is not None:
             src_dg = self._dg
             s = src_dg._slice

@@ -29,6 +29,7 @@ from tgm_b200.hooks.hook_manager import register_hook_class
 # DGData construction): checking them again would cost a host sync per batch
 _TRUSTED_NODE_KEYS = ('edge_src', 'edge_dst')
 _TRUSTED_TIME_KEYS = ('edge_time',)
+_DEFAULT_WINDOW_BATCHES = 1024
 
 
 def _is_store_view(store, tensor: Tensor) -> bool:
@@ -43,6 +44,21 @@ def _is_store_view(store, tensor: Tensor) -> bool:
     return False
 
 
+def _slab_offset(slab: Optional[Tensor], tensor, n: int) -> Optional[int]:
+    """Row offset of `tensor` inside `slab` when it is a contiguous n-row view of that very slab
+    (same storage, dtype and row shape); None otherwise."""
+    if slab is None or not isinstance(tensor, Tensor) or not tensor.is_cuda or \
+            tensor.dtype != slab.dtype or tensor.shape[0] != n or \
+            tensor.shape[1:] != slab.shape[1:] or not tensor.is_contiguous() or \
+            tensor.untyped_storage().data_ptr() != slab.untyped_storage().data_ptr():
+        return None
+    row_bytes = slab.element_size() * max(1, slab[0].numel()) if slab.numel() else slab.element_size()
+    off = tensor.data_ptr() - slab.data_ptr()
+    if off < 0 or off % row_bytes:
+        return None
+    return off // row_bytes
+
+
 @register_hook_class
 class RecencyNeighborHook(StatefulHook, SeedableHook):
     """Load the most recent neighbors of each seed node; every node keeps a fixed number of
@@ -54,12 +70,14 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
 
     def __init__(self, num_nodes: int, num_nbrs: List[int], seed_nodes_keys: List[str],
                  seed_times_keys: List[str], directed: bool = False,
-                 id: Optional[str] = None, window_batches: int = 0) -> None:
-        """`window_batches` > 0 turns on pre-sampling (an addition to the reference signature):
-        while the loader walks one store front to back in equal event batches, the neighbourhoods
+                 id: Optional[str] = None, window_batches: Optional[int] = None) -> None:
+        """`window_batches` (an addition to the reference signature) controls pre-sampling: while
+        the loader walks one device store front to back in equal event batches, the neighbourhoods
         of `window_batches` upcoming batches are sampled by ONE launch per hop over the stateless
         adjacency (tgm_csr_*) and each call only slices views.  Outputs are identical; any other
-        call pattern (another store, a skipped batch) hands the state over to the ring kernels."""
+        call pattern (another store, a skipped batch, time-unit batches) hands the state over to
+        the ring kernels.  None (default) = 1024 batches when the adjacency fits comfortably in
+        free HBM; 0 = always drive the ring kernels batch by batch."""
         if not len(num_nbrs):
             raise ValueError('num_nbrs must be non-empty')
         if not all(isinstance(x, int) and x > 0 for x in num_nbrs):
@@ -76,9 +94,11 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         self._seed_nodes_keys = seed_nodes_keys
         self._seed_times_keys = seed_times_keys
         self._warned_seed_None = False
-        if not isinstance(window_batches, int) or window_batches < 0:
-            raise ValueError('window_batches must be a non-negative integer')
-        self._window_batches = window_batches
+        if window_batches is not None and (not isinstance(window_batches, int) or
+                                           window_batches < 0):
+            raise ValueError('window_batches must be a non-negative integer or None')
+        self._window_auto = window_batches is None
+        self._window_batches = _DEFAULT_WINDOW_BATCHES if window_batches is None else window_batches
         self._win = None  # windowed-mode cursor, see _windowed_call
         self._standard_seeds = (list(seed_nodes_keys) == ['edge_src', 'edge_dst'] and
                                 list(seed_times_keys) == ['edge_time', 'edge_time'])
@@ -104,9 +124,17 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
             _cabi.check(_cabi.lib.tgm_recency_reset(self._handle, _cabi.current_stream(self._device)))
 
     # -- state ------------------------------------------------------------------------------
-    def _ensure_state(self, dg) -> None:
-        """First call fixes D = dg.edge_x_dim or 0 and the device (recency.py:401-416)."""
+    def _ensure_state(self, dg, ring: bool = True) -> None:
+        """First call fixes D = dg.edge_x_dim or 0 and the device (recency.py:401-416); the ring
+        buffers are allocated when the ring kernels are first needed (a windowed run never touches
+        them until it hands over)."""
         if self._handle.value:
+            return
+        if self._device is not None:
+            if ring:
+                _cabi.check(_cabi.lib.tgm_recency_create(
+                    ctypes.byref(self._handle), self._num_nodes, self._max_nbrs,
+                    self._edge_x_dim, self._device.index))
             return
         device = dg.device
         if device.type != 'cuda':
@@ -117,13 +145,20 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
             device = torch.device('cuda', torch.cuda.current_device())
         self._device = device
         self._edge_x_dim = dg.edge_x_dim or 0
-        _cabi.check(_cabi.lib.tgm_recency_create(ctypes.byref(self._handle), self._num_nodes,
-                                                 self._max_nbrs, self._edge_x_dim, device.index))
+        if ring:
+            _cabi.check(_cabi.lib.tgm_recency_create(ctypes.byref(self._handle), self._num_nodes,
+                                                     self._max_nbrs, self._edge_x_dim, device.index))
 
     def state_tensors(self) -> Dict[str, Tensor]:
-        """Copies of the ring state (ids, times, feats, write_pos) for inspection/checkpoints."""
-        if not self._handle.value:
+        """Copies of the ring state (ids, times, feats, write_pos) for inspection/checkpoints.
+        During a windowed run the state every edge served so far would have left is exported."""
+        if self._device is None:
             raise RuntimeError('hook state is created on the first call')
+        self._ensure_state(None)
+        if isinstance(self._win, dict):
+            _cabi.check(_cabi.lib.tgm_csr_export_ring(
+                self._win['csr'].handle, self._win['next'], self._handle,
+                _cabi.current_stream(self._device)))
         N, B, D = self._num_nodes, self._max_nbrs, self._edge_x_dim
         p = [ctypes.c_void_p() for _ in range(4)]
         _cabi.check(_cabi.lib.tgm_recency_state(self._handle, *[ctypes.byref(q) for q in p]))
@@ -146,10 +181,43 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         if store is None or not hasattr(store, 'edge_range') or getattr(store, 'device', None) is None:
             return None
         src = batch.edge_src
-        if not (isinstance(src, Tensor) and _is_store_view(store, src)):
+        slab = getattr(batch, '_slab', None)
+        if slab is not None and slab[0] is store and src is slab[3] and \
+                batch.edge_dst is slab[4] and batch.edge_time is slab[5]:
+            return store, slab[1], slab[2]  # the loader's own views, untouched since
+        if not isinstance(src, Tensor) or src.ndim != 1:
             return None
-        lo = (src.data_ptr() - store._src.data_ptr()) // 4
-        return store, lo, lo + src.numel()
+        n = src.numel()
+        lo = _slab_offset(store._src, src, n)
+        # every edge tensor must be the same rows of its own slab (a hook earlier in the chain
+        # may have replaced or cast one of them)
+        if lo is None or _slab_offset(store._dst, batch.edge_dst, n) != lo or \
+                _slab_offset(store._t, batch.edge_time, n) != lo:
+            return None
+        return store, lo, lo + n
+
+    def _published_window(self, store, batch, lo: int, n: int, node_attr: str, time_attr: str):
+        """The seed window a producer hook published for `node_attr` (negatives drawn ahead for a
+        stretch of the stream, hooks/negatives.py), provided the batch's attributes still are its
+        views for this batch; else None."""
+        pubs = getattr(batch, '_seed_windows', None)
+        sw = pubs.get(node_attr) if pubs else None
+        if sw is None or sw.store is not store or not (sw.e_lo <= lo and lo + n <= sw.e_hi):
+            return None
+        sn, stt = getattr(batch, node_attr, None), getattr(batch, time_attr, None)
+        if not (isinstance(sn, Tensor) and isinstance(stt, Tensor)) or sn.numel() != n or \
+                stt.numel() != n or sn.data_ptr() != sw.nodes.data_ptr() + 4 * (lo - sw.e_lo) or \
+                stt.data_ptr() != sw.times.data_ptr() + 8 * (lo - sw.e_lo):
+            return None
+        return sw
+
+    def _window_feasible(self, store) -> bool:
+        """Default (auto) mode only: the adjacency of the whole store (entries, anchors, colocated
+        feature rows, sort workspace) must fit in a quarter of the free HBM."""
+        E, D = store.num_edges, self._edge_x_dim
+        need = 2 * E * (16 + 8 + 16 + 4 * D)
+        free, _ = torch.cuda.mem_get_info(self._device)
+        return need <= free // 4
 
     def _windowed_call(self, dg, batch):
         """Returns the decorated batch, or None when this call cannot be served from a window (the
@@ -161,9 +229,14 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         if rng is None or rng[2] == rng[1]:
             return None
         store, lo, hi = rng
+        n = hi - lo
+        extra = keys[2:]
+        pub = self._published_window(store, batch, lo, n, *extra[0]) if len(extra) == 1 else None
         w = self._win
         if w is None:
             if self._win is False:  # already handed over to the ring since the last reset
+                return None
+            if self._window_auto and not self._window_feasible(store):
                 return None
             from tgm_b200.sampler import RecencyCSR
             bs = hi - lo
@@ -173,35 +246,54 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
                 cache[key] = RecencyCSR(store, bs, directed=self._directed, colocate_x=True,
                                         e_start=lo)
             w = self._win = {'store': store, 'csr': cache[key], 'bs': bs, 'next': lo,
-                             'w_lo': lo, 'w_hi': lo, 'hops': None, 'start': lo}
+                             'w_lo': lo, 'w_hi': lo, 'hops': None, 'start': lo, 'pub': None}
         elif w['store'] is not store or lo != w['next'] or \
                 (hi - lo != w['bs'] and hi != store.num_edges):
             return None
         csr, bs = w['csr'], w['bs']
         if hi > w['w_hi']:  # pre-sample the next window, one launch per hop
-            nwin = min(self._window_batches, self._window_budget_batches(bs))
+            P = 3 if pub is not None else 2
+            # cudaMemGetInfo costs milliseconds: the budget is fixed when a run starts
+            if w.get('budget', (0, 0))[0] != P:
+                w['budget'] = (P, self._window_budget_batches(bs, P))
+            nwin = min(self._window_batches, w['budget'][1])
             w['w_lo'], w['w_hi'] = lo, min(lo + nwin * bs, store.num_edges)
-            w['hops'] = csr.sample_window(w['w_lo'], w['w_hi'], self._num_nbrs)
+            neg = None
+            if pub is not None:
+                w['w_hi'] = min(w['w_hi'], pub.e_hi)
+                neg = pub.nodes[lo - pub.e_lo:w['w_hi'] - pub.e_lo]
+                if not (0 <= pub.low and pub.high <= self._num_nodes):
+                    self._validate([(extra[0][0], neg, True)])  # one sync per window
+            w['pub'] = pub
+            w['hops'] = csr.sample_window(w['w_lo'], w['w_hi'], self._num_nbrs, neg=neg)
             # per-batch views of the whole window in five C++ calls per hop (Tensor.split) rather
             # than five slicing calls per hop per batch; only the stream's last batch can be short
-            rows, split = 2 * bs, []
+            rows, split = P * bs, []
             for hop in w['hops']:
                 split.append(tuple(v.split(rows) for v in (
                     hop.seed_nids, hop.seed_times, hop.nbr_nids, hop.nbr_edge_time,
                     hop.nbr_edge_x)))
                 rows *= hop.nbr_nids.shape[1]
             w['split'] = split
+            w['mask'] = None
+        elif w['pub'] is not pub:
+            # the window was sampled with (without) a published seed window this batch does not
+            # (does) carry any more: its rows do not describe this batch
+            return None
         # rows of this batch inside the window block, hop by hop
         j = (lo - w['w_lo']) // bs
         parts = [tuple(v[j] for v in hop) for hop in w['split']]
-        n = hi - lo
         dev = self._device
         mask = w.get('mask')
         if mask is None or mask[0] != n:
-            mask = w['mask'] = (n, self._arange(0, n), self._arange(n, 2 * n))
-        mask = {'edge_src': mask[1], 'edge_dst': mask[2]}
-        extra = keys[2:]
-        if extra:  # seeds the window cannot know in advance (negatives): one launch per hop
+            mask = w['mask'] = (n, self._arange(0, n), self._arange(n, 2 * n),
+                                self._arange(2 * n, 3 * n))
+        if pub is not None:
+            mask = {'edge_src': mask[1], 'edge_dst': mask[2], extra[0][0]: mask[3]}
+            extra = []
+        else:
+            mask = {'edge_src': mask[1], 'edge_dst': mask[2]}
+        if extra:  # seeds the window cannot know in advance: one launch per hop
             xs, xt, offset = [], [], 2 * n
             to_check = []
             for node_attr, time_attr in extra:
@@ -249,10 +341,10 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         self.add_batch_attribute(batch, 'seed_node_nbr_mask', mask)
         return batch
 
-    def _window_budget_batches(self, bs: int) -> int:
+    def _window_budget_batches(self, bs: int, seeds_per_edge: int = 2) -> int:
         """How many batches fit the pre-sampling budget (a quarter of the free HBM, at most 16 GB):
         multi-hop outputs grow as prod(k) -- 165 MB per batch for k=[20,20] at D=172."""
-        per_batch, seeds = 0, 2 * bs
+        per_batch, seeds = 0, seeds_per_edge * bs
         for k in self._num_nbrs:
             per_batch += seeds * k * (12 + 4 * self._edge_x_dim)
             seeds *= k
@@ -273,18 +365,20 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         """Hand the state of a windowed run over to the ring: after this the ring holds what the
         batch-by-batch hook would hold once every edge before `next` was pushed."""
         w = self._win
+        self._ensure_state(None)  # the ring buffers, if this run never needed them so far
         if isinstance(w, dict):
             _cabi.check(_cabi.lib.tgm_csr_export_ring(w['csr'].handle, w['next'], self._handle,
                                                       _cabi.current_stream(self._device)))
         self._win = False
 
     def __call__(self, dg, batch):
-        self._ensure_state(dg)
+        self._ensure_state(dg, ring=False)
         if self._window_batches and self._win is not False:
             out = self._windowed_call(dg, batch)
             if out is not None:
                 return out
             self._leave_window()
+        self._ensure_state(dg)
         if self._standard_seeds and self._step_call(dg, batch):
             return batch
         seed_nodes, seed_times, seed_mask = self._get_seed_tensors(dg, batch)
@@ -331,11 +425,12 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         n = src.numel()
         store = getattr(dg, '_storage', None)
         if n == 0 or getattr(store, 'num_nodes_global', 1 << 62) > self._num_nodes or \
-                not _is_store_view(store, src) or batch.edge_dst.numel() != n:
+                self._batch_range(dg, batch) is None:
             return False
         x = batch.edge_x
         D, dev = self._edge_x_dim, self._device
-        if D and (x is None or x.dtype != torch.float32 or not x.is_contiguous()):
+        if D and not (isinstance(x, Tensor) and x.is_cuda and x.dtype == torch.float32 and
+                      x.is_contiguous() and x.shape == (n, D)):
             return False
         hops = len(self._num_nbrs)
         seeds0 = torch.empty(2 * n, dtype=torch.int32, device=dev)

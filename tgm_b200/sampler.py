@@ -105,6 +105,55 @@ class RecencyCSR:
             nx.data_ptr() if self.D else None, int(slot),
             _cabi.current_stream(self.device) if stream is None else stream))
 
+    def sample_edges_ids(self, e_lo: int, e_hi: int, k: int, B: int, search: bool = False,
+                         out=None):
+        """Hop 0 without the feature block (tgm_csr_sample_edges_ids): (nbr_nids, nbr_edge_time,
+        eid) with nbr_edge_x[s, c] == edge_x[eid[s, c]] (zeros where eid == -1)."""
+        S = 2 * (e_hi - e_lo)
+        if out is None:
+            out = (torch.empty((S, k), dtype=torch.int32, device=self.device),
+                   torch.empty((S, k), dtype=torch.int64, device=self.device),
+                   torch.empty((S, k), dtype=torch.int32, device=self.device))
+        _cabi.check(_cabi.lib.tgm_csr_sample_edges_ids(
+            self._handle, int(e_lo), int(e_hi), int(B), int(k), int(search), _cabi.ptr(out[0]),
+            _cabi.ptr(out[1]), _cabi.ptr(out[2]), _cabi.current_stream(self.device)))
+        return out
+
+    def sample_edges_mean(self, e_lo: int, e_hi: int, k: int, B: int, search: bool = False,
+                          with_ids: bool = True, out=None):
+        """Fused hop-0 sample + masked mean (tgm_csr_sample_edges_mean): (nbr_nids, nbr_edge_time,
+        mean[S, D]); the first two are None when `with_ids` is False."""
+        S = 2 * (e_hi - e_lo)
+        if out is None:
+            out = (torch.empty((S, k), dtype=torch.int32, device=self.device) if with_ids else None,
+                   torch.empty((S, k), dtype=torch.int64, device=self.device) if with_ids else None,
+                   torch.empty((S, self.D), dtype=torch.float32, device=self.device))
+        _cabi.check(_cabi.lib.tgm_csr_sample_edges_mean(
+            self._handle, int(e_lo), int(e_hi), int(B), int(k), int(search), _cabi.ptr(out[0]),
+            _cabi.ptr(out[1]), None, out[2].data_ptr(), _cabi.current_stream(self.device)))
+        return out
+
+    def sample_edges_host_ids(self, e_lo: int, e_hi: int, k: int, B: int, host_in, host_out,
+                              slot: int = 0, stream: Optional[int] = None) -> None:
+        """tgm_csr_sample_edges_host_ids: `host_in` = (src, dst, t) CPU tensors of the slab,
+        `host_out` = (nid, t, eid) CPU tensors; 16 bytes per sampled slot come back."""
+        src, dst, t = host_in[:3]
+        nid, nt, eid = host_out
+        _cabi.check(_cabi.lib.tgm_csr_sample_edges_host_ids(
+            self._handle, int(e_lo), int(e_hi), int(B), int(k), _cabi.ptr(src), _cabi.ptr(dst),
+            _cabi.ptr(t), nid.data_ptr(), nt.data_ptr(), eid.data_ptr(), int(slot),
+            _cabi.current_stream(self.device) if stream is None else stream))
+
+    def sample_edges_host_mean(self, e_lo: int, e_hi: int, k: int, B: int, host_in, host_out,
+                               slot: int = 0, stream: Optional[int] = None) -> None:
+        """tgm_csr_sample_edges_host_mean: `host_out` = (nid | None, t | None, mean[S, D])."""
+        src, dst, t = host_in[:3]
+        nid, nt, mean = host_out
+        _cabi.check(_cabi.lib.tgm_csr_sample_edges_host_mean(
+            self._handle, int(e_lo), int(e_hi), int(B), int(k), _cabi.ptr(src), _cabi.ptr(dst),
+            _cabi.ptr(t), _cabi.ptr(nid), _cabi.ptr(nt), mean.data_ptr(), int(slot),
+            _cabi.current_stream(self.device) if stream is None else stream))
+
     # -- whole windows ----------------------------------------------------------------------
     def window_seed_tensors(self, e_lo: int, e_hi: int, neg: Optional[Tensor] = None):
         """hop-0 seeds/times/cuts of the window laid out batch by batch in the reference's
