@@ -265,6 +265,61 @@ def run_reference(a):
     }))
 
 
+def time_eager_cuda(a, csr, src, dst, t, x, dev, batches=300):
+    """The reference hook's tensor-op sequence (oracle/torch_eager.py::TorchRing: the O(N*B) `.min()`
+    scan + host sync per call, ~25 eager ops per query, argsort + ~15 ops per push;
+    recency.py:239-399) run on the B200 itself, batch by batch, in the steady state: its ring
+    buffers are loaded with the exact state after the first `steady_start_edge` stream edges
+    (tgm_csr_export_ring), the first batch's answer is checked against the CUDA sampler."""
+    import ctypes
+
+    import torch
+
+    from oracle.torch_eager import TorchRing
+    from tgm_b200 import _cabi
+    N, D, k, bs = a.nodes, a.dim, a.k, a.batch_size
+    e0 = steady_start_edge(a)
+    h = ctypes.c_void_p()
+    _cabi.check(_cabi.lib.tgm_recency_create(ctypes.byref(h), N, k, D, dev.index))
+    try:
+        _cabi.check(_cabi.lib.tgm_csr_export_ring(csr.handle, e0, h, _cabi.current_stream(dev)))
+        p = [ctypes.c_void_p() for _ in range(4)]
+        _cabi.check(_cabi.lib.tgm_recency_state(h, *[ctypes.byref(q) for q in p]))
+        ring = TorchRing(N, [k], D, device=dev)
+        ring.ids.copy_(_cabi.device_view(p[0].value, (N, k), torch.int32, dev))
+        ring.times.copy_(_cabi.device_view(p[1].value, (N, k), torch.int64, dev))
+        if D:
+            ring.feats.copy_(_cabi.device_view(p[2].value, (N, k, D), torch.float32, dev))
+        ring.write_pos.copy_(_cabi.device_view(p[3].value, (N,), torch.int32, dev))
+        torch.cuda.synchronize(dev)
+    finally:
+        _cabi.lib.tgm_recency_destroy(h)
+
+    def batch(i):
+        lo, hi = e0 + i * bs, e0 + (i + 1) * bs
+        seeds = torch.cat([src[lo:hi], dst[lo:hi]])
+        tq = torch.cat([t[lo:hi], t[lo:hi]])
+        return ring.hook_call(seeds, tq, src[lo:hi], dst[lo:hi], t[lo:hi],
+                              None if x is None else x[lo:hi])
+    got = batch(0)[0]
+    want = csr.sample_edges(e0, e0 + bs, k, k)
+    same = all(torch.equal(u, v) for u, v in zip(got[2:], want))
+    for i in range(1, 20):
+        batch(i)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for i in range(20, 20 + batches):
+        batch(i)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    return {'value': batches * 2 * bs * k / dt, 'unit': UNIT, 'us_per_batch': dt / batches * 1e6,
+            'kind': 'eager-torch restatement of the reference hook (oracle/torch_eager.py) on the '
+                    'same B200: what the reference\'s device=\'cuda\' mode launches',
+            'first_batch_equals_cuda_sampler': bool(same),
+            'sample': f'{batches} loader batches from stream edge {e0 + 20 * bs} on, hook only (no '
+                      f'O(E) materialize), steady-state rings'}
+
+
 # ---- B200 arm -----------------------------------------------------------------------------------
 def run_b200(a):
     import torch
@@ -595,6 +650,11 @@ def run_b200(a):
                                        dst[full.batch_lo * bs:min(full.batch_hi * bs, E)],
                                        a.join_edges, dev, reps=5)
 
+    # ---- the reference's own eager device='cuda' mode, restated (rank 0, N=1 only) ---------------
+    eager = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        eager = time_eager_cuda(a, csr, src, dst, t, x, dev)
+
     # ---- CPU baseline on this host (rank 0, N=1 only) ---------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -617,7 +677,8 @@ def run_b200(a):
             'dtype': 'int32/int64 ids+times, f32 feature copy', 'data': 'synthetic',
             'config': workload_config(a, world), 'gpu_launches': a.steps,
             'stream_edges_per_s': value / (2 * k),
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'full_pass': full_pass,
+            'roofline': roofline, 'cpu_baseline': cpu, 'eager_cuda_baseline': eager, 'e2e': e2e,
+            'full_pass': full_pass,
             'loader_api': loader_api, 'collective': collective,
             'clocks': clocks.result(), 'numa': numa,
             'build_s': build_max,

@@ -6,7 +6,11 @@ timed beside it on the host on a bounded sample.  One JSON line per row.
 
     python bench_rows.py [--rows store,ring,...] > profiles/rNN_rows.jsonl
 
-oracle/ is executed here only as the timed CPU baseline, never on the product path.
+Rows with a model in them also carry `eager_cuda_baseline`: the reference's own tensor-op sequence
+(oracle/torch_eager.py, pinned on the reference fixtures) run on the SAME B200 -- what the
+reference's device='cuda' mode launches -- so the ratio is GPU over GPU, not GPU over numpy.
+
+oracle/ is executed here only as a timed baseline, never on the product path.
 """
 from __future__ import annotations
 
@@ -138,16 +142,54 @@ def row_ring():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
     slots = 2 * len(src) * k
+    # the same epoch on the stateful ring kernels, batch by batch (window_batches=0)
+    hm0 = HookManager(keys=['g'])
+    hm0.register('g', RecencyNeighborHook(num_nodes=N, num_nbrs=[k],
+                                          seed_nodes_keys=['edge_src', 'edge_dst'],
+                                          seed_times_keys=['edge_time', 'edge_time'],
+                                          window_batches=0))
+    with hm0.activate('g'):
+        for batch in DGDataLoader(dg, batch_size=bs, hook_manager=hm0):
+            pass
+        hm0.reset_state()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for batch in DGDataLoader(dg, batch_size=bs, hook_manager=hm0):
+            pass
+        torch.cuda.synchronize()
+        dt_ring = time.perf_counter() - t0
     ring = CRing(N, [k], x.shape[1])
     c0 = time.perf_counter()
-    ring.run_stream(src, dst, t, x, 0, len(src), bs)
+    ring.run_stream(src, dst, t, x, 0, len(src), bs, checksum=False)
     cdt = time.perf_counter() - c0
+    # the reference's tensor-op sequence on this GPU (hook only, batches pre-sliced)
+    from oracle.torch_eager import TorchRing
+    tr = TorchRing(N, [k], x.shape[1], device=DEV)
+    dsrc, ddst, dt_, dx = (torch.from_numpy(v).to(DEV) for v in (src, dst, t, x))
+
+    def eager_epoch(nb_):
+        for b in range(nb_):
+            lo, hi = b * bs, min((b + 1) * bs, len(src))
+            tr.hook_call(torch.cat([dsrc[lo:hi], ddst[lo:hi]]), torch.cat([dt_[lo:hi], dt_[lo:hi]]),
+                         dsrc[lo:hi], ddst[lo:hi], dt_[lo:hi], dx[lo:hi])
+        torch.cuda.synchronize()
+    eager_epoch(50)
+    tr.reset_state()
+    e0 = time.perf_counter()
+    eager_epoch(nb)
+    edt = time.perf_counter() - e0
     emit('R1-R4 DGDataLoader + RecencyNeighborHook epoch (wiki-shaped, bs=200, k=10, D=172)',
          value=slots / dt, unit='sampled-edges/s', batches_per_s=nb / dt, us_per_batch=dt / nb * 1e6,
-         note='3 launches per batch (query, update rank, update commit); host-bound: Python + launch '
-              'latency per 200-edge batch, the reason the stateless window form exists',
+         ring_kernels_us_per_batch=dt_ring / nb * 1e6,
+         note='default-constructed hook: windows of 1024 batches pre-sampled by one launch per hop, '
+              'each call hands out views (Python-bound); ring_kernels_us_per_batch = the same epoch '
+              'with window_batches=0 (one tgm_recency_step call = 3 launches per batch)',
          cpu_baseline={'value': slots / cdt, 'unit': 'sampled-edges/s', 'kind': 'port', 'cores': 1,
-                       'sample': 'C port of the ring sampler over the same epoch'})
+                       'sample': 'C port of the ring sampler over the same epoch'},
+         eager_cuda_baseline={'value': slots / edt, 'unit': 'sampled-edges/s',
+                              'us_per_batch': edt / nb * 1e6,
+                              'sample': 'oracle/torch_eager.py::TorchRing over the same epoch on '
+                                        'cuda:0, hook only (batches pre-sliced on the device)'})
     # the ring kernels alone at a size where bandwidth shows: 1M random seeds against full rings
     N2, B, D = 1_000_000, 20, 16
     h = RecencyNeighborHook(N2, [B], ['edge_src'], ['edge_time'])
@@ -290,6 +332,12 @@ def row_tgat():
     t_cpu = cpu_s(lambda: nn_oracle.tgat_forward(p, 2, 2, npx, [hop[h][0] for h in range(2)],
                                                  [hop[h][1] for h in range(2)], [hop[h][2] for h in range(2)],
                                                  [hop[h][4] for h in range(2)], [hop[h][3] for h in range(2)]))
+    from oracle import torch_eager as te
+    pt = {k_: v.detach() for k_, v in model.state_dict().items()}
+    largs = [[a_.long() if a_.dtype == torch.int32 else a_ for a_ in lst] for lst in args[1:]]
+    eager_fwd = lambda: te.tgat_forward(pt, 2, 2, node_x, *largs)  # noqa: E731
+    err = float((eager_fwd() - model(*args)).abs().max())
+    ms_eager = cuda_ms(eager_fwd, iters=10)
     key1, out1 = 1 + D + TD, 102
     flops_ref = 2 * sizes[1] * k * key1 * 2 * out1
     emit('A2/A3 TGAT forward, one batch (600 seeds, k=[20,20], edge 172, time 100, embed 172)',
@@ -301,7 +349,11 @@ def row_tgat():
               'SIMT fp32 (Time2Vec cosines + dot products over cp.async-staged rows), '
               'issue/latency-bound rather than HBM-bound',
          cpu_baseline={'value': t_cpu * 1e3, 'unit': 'ms/batch', 'kind': 'port', 'cores': os.cpu_count(),
-                       'sample': 'numpy oracle of the same batch (BLAS threads = all cores)'})
+                       'sample': 'numpy oracle of the same batch (BLAS threads = all cores)'},
+         eager_cuda_baseline={'value': ms_eager, 'unit': 'ms/batch', 'max_abs_diff_vs_b200_path': err,
+                              'sample': 'oracle/torch_eager.py::tgat_forward (the reference module\'s '
+                                        'op sequence: cat -> W_KV GEMM over S*k rows -> softmax -> '
+                                        'W_O -> LayerNorm) on cuda:0, same batch, same weights'})
 
 
 # ---- A6 TGN memory (config 4) ---------------------------------------------------------------------
@@ -340,12 +392,30 @@ def row_tgn():
             orc.forward(np.unique(np.concatenate([s_np[lo:hi], d_np[lo:hi]])))
             orc.update_state(s_np[lo:hi], d_np[lo:hi], t_np[lo:hi], x_np[lo:hi])
     t_cpu = cpu_s(cpu_epoch) / 20
+    from oracle.torch_eager import TorchTGNMemory
+    pt = {k_: v.detach() for k_, v in mem.state_dict().items()}
+    tmem = TorchTGNMemory(N, D, M, TD, pt, device=DEV)  # builds the 2 x N-entry dict store (tgn.py:183)
+    sl_, dl_ = src.long(), dst.long()
+
+    def eager_epoch(nb_=50):
+        for i in range(nb_):
+            lo, hi = i * bs, (i + 1) * bs
+            tmem.forward(nids[i].unique())
+            tmem.update_state(sl_[lo:hi], dl_[lo:hi], t[lo:hi], x[lo:hi])
+        torch.cuda.synchronize()
+    eager_epoch(10)
+    e0 = time.perf_counter()
+    eager_epoch(50)
+    ms_eager = (time.perf_counter() - e0) / 50 * 1e3
     emit('A6 TGNMemory forward + update_state per batch (N=1e6, bs=200, D=16, M=100)', value=ms,
          unit='ms/batch', higher_is_better=False,
          note='11 launches per batch (gather/message, 2 SGEMM, GRU gates, scatter, store) x2; '
               'launch-latency bound at bs=200',
          cpu_baseline={'value': t_cpu * 1e3, 'unit': 'ms/batch', 'kind': 'port', 'cores': os.cpu_count(),
-                       'sample': 'numpy oracle, 20 batches, N=2e4 nodes'})
+                       'sample': 'numpy oracle, 20 batches, N=2e4 nodes'},
+         eager_cuda_baseline={'value': ms_eager, 'unit': 'ms/batch',
+                              'sample': 'oracle/torch_eager.py::TorchTGNMemory on cuda:0, N=1e6, 50 '
+                                        'batches (per-node Python dict message store as upstream)'})
 
 
 # ---- N4 full TGN inference step through the drop-in API (examples/linkproppred/tgn.py loop) --------
@@ -433,6 +503,15 @@ def row_dygformer():
     p = {k_: v.detach().cpu().numpy() for k_, v in m.state_dict().items()}
     npx = node_x.cpu().numpy()
     t_cpu = cpu_s(lambda: nn_oracle.dygformer_forward(p, 1, 2, 2, npx, np.stack([src, dst]), t, nbrs, nt, ef))
+    from oracle import torch_eager as te
+    pt = {k_: v.detach() for k_, v in m.state_dict().items()}
+    eargs = (node_x, args[1].long(), args[2], args[3].long(), args[4], args[5])
+    eager_fwd = lambda: te.dygformer_forward(pt, 1, 2, 2, *eargs)  # noqa: E731
+    with torch.no_grad():
+        zs, zd = m(*args)
+        es, ed = eager_fwd()
+        err = float(max((zs - es).abs().max(), (zd - ed).abs().max()))
+        ms_eager = cuda_ms(eager_fwd, iters=10)
     E_ = 4 * C
     tok = B * 2 * L
     flops = 2 * (2 * tok * E_ * (3 * E_ + E_ + 8 * E_) + 2 * 2 * B * 2 * (2 * L) ** 2 * (E_ // 2))
@@ -442,7 +521,10 @@ def row_dygformer():
               'the tensor cores (tcgen05, fp32-accurate 9xBF16 emulation, fused bias/residual/GELU), '
               'per-head attention products on cuBLAS fp32',
          cpu_baseline={'value': t_cpu * 1e3, 'unit': 'ms/call', 'kind': 'port', 'cores': os.cpu_count(),
-                       'sample': 'numpy oracle of the same call'})
+                       'sample': 'numpy oracle of the same call'},
+         eager_cuda_baseline={'value': ms_eager, 'unit': 'ms/call', 'max_abs_diff_vs_b200_path': err,
+                              'sample': 'oracle/torch_eager.py::dygformer_forward on cuda:0 (cuBLAS '
+                                        'TF32 off: torch default fp32 matmul), same call, same weights'})
 
 
 ROWS = {'tgn_step': row_tgn_step, 'store': row_store, 'ring': row_ring, 'twohop': row_twohop, 'uniform': row_uniform,

@@ -247,22 +247,28 @@ class DeviceCOOStorage(DGStorageBase):
                     (self._data is None or (self._data.node_x_mask is None and
                                             self._data.node_y_mask is None)))
 
-    def batch_views(self, origin: int, batch_size: int, lo: int, hi: int):
-        """(src, dst, t, x) views of the slab [lo, hi), where lo = origin + j * batch_size: served
-        from per-chunk `Tensor.split` tuples (one C++ call yields the views of 4096 batches)
-        instead of four slicing calls per batch.  Identical tensors to get_edges/get_edge_x."""
-        j = (lo - origin) // batch_size
-        c, r = divmod(j, self._CHUNK_BATCHES)
+    def batch_chunk(self, origin: int, batch_size: int, c: int):
+        """Per-batch views of chunk `c` (4096 batches starting at origin + c * 4096 * batch_size):
+        a tuple (src, dst, t, x) of `Tensor.split` tuples -- one C++ call yields the views of 4096
+        batches instead of four slicing calls per batch.  One live chunk: the loader walks forward."""
         key = ('batch_views', origin, batch_size, c)
         chunk = self._node_cache.get(key)
         if chunk is None:
             for k in [k for k in self._node_cache if isinstance(k, tuple) and k[0] == 'batch_views']:
-                del self._node_cache[k]  # one live chunk: the loader walks forward
+                del self._node_cache[k]
             a = origin + c * self._CHUNK_BATCHES * batch_size
             b = min(a + self._CHUNK_BATCHES * batch_size, self._E)
             chunk = tuple(None if v is None else v[a:b].split(batch_size)
                           for v in (self._src, self._dst, self._t, self._x))
             self._node_cache[key] = chunk
+        return chunk
+
+    def batch_views(self, origin: int, batch_size: int, lo: int, hi: int):
+        """(src, dst, t, x) views of the slab [lo, hi), where lo = origin + j * batch_size.
+        Identical tensors to get_edges/get_edge_x."""
+        j = (lo - origin) // batch_size
+        c, r = divmod(j, self._CHUNK_BATCHES)
+        chunk = self.batch_chunk(origin, batch_size, c)
         if hi - lo == batch_size or lo + batch_size > self._E:
             if hi - lo == len(chunk[0][r]):
                 return tuple(None if v is None else v[r] for v in chunk)

@@ -63,6 +63,8 @@ class DGDataLoader:
         store = getattr(dg, '_storage', None)
         if self._by_events and getattr(store, 'edges_only', False) and dg.device == store.device:
             self._fast = (store,) + tuple(store.edge_range(dg._slice))
+            self._origin = self._fast[1] - self._fast[1] % batch_size
+            self._chunk = None
 
     @property
     def dgraph(self) -> DGraph:
@@ -86,19 +88,36 @@ class DGDataLoader:
         lo, hi = max(start, lo0), min(start + bs, hi0)
         if hi < lo:
             hi = lo
-        src, dst, t, x = store.batch_views(lo0 - lo0 % bs, bs, lo, hi) if lo % bs == 0 else (
-            store._src[lo:hi], store._dst[lo:hi], store._t[lo:hi],
-            None if store._x is None else store._x[lo:hi])
-        batch = DGBatch(src, dst, t, x if hi > lo else None)
+        n = hi - lo
+        src = None
+        if lo % bs == 0 and n:
+            # the views of 4096 batches come from one Tensor.split per array (storage.batch_chunk)
+            c, r = divmod((lo - self._origin) // bs, store._CHUNK_BATCHES)
+            cur = self._chunk
+            if cur is None or cur[0] != c:
+                cur = self._chunk = (c, store.batch_chunk(self._origin, bs, c))
+            ch = cur[1]
+            src = ch[0][r]
+            if src.shape[0] == n:
+                dst, t = ch[1][r], ch[2][r]
+                x = None if ch[3] is None else ch[3][r]
+            else:
+                src = None
+        if src is None:
+            src, dst, t = store._src[lo:hi], store._dst[lo:hi], store._t[lo:hi]
+            x = None if store._x is None or not n else store._x[lo:hi]
+        batch = DGBatch(src, dst, t, x)
         # which rows of the store these views are (hooks verify by identity that nobody replaced
         # the tensors since, instead of re-deriving the offsets from pointers every batch)
-        batch._slab = (store, lo, hi, src, dst, t)
-        if self._hook_manager is not None:
+        if n:
+            batch._slab = (store, lo, hi, src, dst, t)
+        hm = self._hook_manager
+        if hm is not None:
             src_dg = self._dg
             s = src_dg._slice
             view = DGraph._from_storage(store, src_dg._time_delta, src_dg._device, DGSliceTracker(
                 s.start_time, s.end_time, lo, hi))
-            batch = self._hook_manager.execute_active_hooks(view, batch)
+            batch = hm.execute_active_hooks(view, batch)
         return batch
 
     # kept for API parity with the reference, whose loader is its own collate_fn (:158)

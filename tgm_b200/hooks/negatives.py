@@ -31,7 +31,10 @@ from tgm_b200.hooks.hook_manager import register_hook_class
 
 class SeedWindow(NamedTuple):
     """Seeds a producer hook drew ahead for the stream edges [e_lo, e_hi) of `store`:
-    nodes[j] / times[j] belong to stream edge e_lo + j; every id lies in [low, high)."""
+    nodes[j] / times[j] belong to stream edge e_lo + j; every id lies in [low, high).
+    `node_views[i]` / `time_views[i]` are the tensors handed to batch i of the window
+    (batches of `batch_size` edges, the last one may be short): a consumer recognises an untouched
+    batch attribute by identity."""
     store: object
     e_lo: int
     e_hi: int
@@ -39,6 +42,9 @@ class SeedWindow(NamedTuple):
     times: Tensor
     low: int
     high: int
+    batch_size: int = 0
+    node_views: tuple = ()
+    time_views: tuple = ()
 
 
 @register_hook_class
@@ -74,22 +80,25 @@ class RandomNegativeEdgeSamplerHook(StatelessHook):
                 gen.set_offset(w['offset'] + 4 * w['served'])
 
     def _windowed(self, dg, batch):
-        # ranges of 2^28 and more take ATen's 64-bit draw: left to torch.randint itself
-        if not self._window_batches or self.neg_ratio != 1.0 or self.high - self.low >= 1 << 28:
-            return None
-        store = getattr(dg, '_storage', None)
         slab = getattr(batch, '_slab', None)  # set by the loader: these rows of this store
-        if slab is None or slab[0] is not store or batch.edge_src is not slab[3] or \
-                batch.edge_time is not slab[5] or getattr(store, 'device', None) is None:
+        if slab is None:
             return None
-        lo, hi = slab[1], slab[2]
-        n = hi - lo
+        store, lo, hi = slab[0], slab[1], slab[2]
         w = self._win
-        if w is not None and (w['store'] is not store or lo != w['next'] or hi > w['e_hi'] or
-                              (n != w['bs'] and hi != w['e_hi'])):
-            self._leave_window()
-            w = None
-        if w is None:
+        if w is not None and store is w['store'] and lo == w['next'] and \
+                (hi - lo == w['bs'] or hi == w['e_hi']) and hi <= w['e_hi'] and \
+                batch.edge_src is slab[3] and batch.edge_time is slab[5]:
+            j = w['served']  # the common case: the next batch of the window
+        else:
+            # ranges of 2^28 and more take ATen's 64-bit draw: left to torch.randint itself
+            if not self._window_batches or self.neg_ratio != 1.0 or \
+                    self.high - self.low >= 1 << 28 or store is not getattr(dg, '_storage', None) or \
+                    batch.edge_src is not slab[3] or batch.edge_time is not slab[5] or \
+                    getattr(store, 'device', None) is None:
+                return None
+            if w is not None:
+                self._leave_window()
+            n = hi - lo
             if n > 65536:
                 return None
             dev = store.device
@@ -106,34 +115,40 @@ class RandomNegativeEdgeSamplerHook(StatelessHook):
             batches = -(-total // n)
             gen.set_offset(offset + 4 * batches)
             times = store._t[lo:e_hi].clone()  # `neg_time` is a copy upstream (sampler.py:63)
+            nv, tv = nodes.split(n), times.split(n)
             w = self._win = {
                 'store': store, 'device': dev, 'bs': n, 'next': lo, 'e_lo': lo, 'e_hi': e_hi,
                 'offset': offset, 'offset_after': offset + 4 * batches, 'batches': batches,
-                'served': 0, 'nodes': nodes.split(n), 'times': times.split(n),
-                'pub': SeedWindow(store, lo, e_hi, nodes, times, self.low, self.high)}
-        j = (lo - w['e_lo']) // w['bs']
+                'served': 0, 'nodes': nv, 'times': tv,
+                'pub': SeedWindow(store, lo, e_hi, nodes, times, self.low, self.high, n, nv, tv),
+                'key': f'neg_{self._id}' if self._id else 'neg'}
+            j = 0
         w['next'] = hi
         w['served'] = j + 1
         pubs = getattr(batch, '_seed_windows', None)
         if pubs is None:
-            pubs = batch._seed_windows = {}
-        pubs[f'neg_{self._id}' if self._id else 'neg'] = w['pub']
-        if w['served'] == w['batches']:
+            batch._seed_windows = {w['key']: w['pub']}
+        else:
+            pubs[w['key']] = w['pub']
+        if j + 1 == w['batches']:
             self._win = None
         return w['nodes'][j], w['times'][j]
 
     def __call__(self, dg, batch):
-        n = round(self.neg_ratio * batch.edge_dst.size(0))
-        if n == 0:
-            neg = torch.empty((0,), dtype=torch.int32, device=dg.device)
-            neg_time = torch.empty((0,), dtype=torch.int64, device=dg.device)
+        got = self._windowed(dg, batch)  # None for empty batches too (the loader marks no slab rows)
+        if got is not None:
+            neg, neg_time = got
         else:
-            got = self._windowed(dg, batch)
-            if got is not None:
-                neg, neg_time = got
+            n = round(self.neg_ratio * batch.edge_dst.size(0))
+            if n == 0:
+                neg = torch.empty((0,), dtype=torch.int32, device=dg.device)
+                neg_time = torch.empty((0,), dtype=torch.int64, device=dg.device)
             else:
                 neg = torch.randint(self.low, self.high, (n,), dtype=torch.int32, device=dg.device)
                 neg_time = batch.edge_time.clone()
-        self.add_batch_attribute(batch, 'neg', neg)
-        self.add_batch_attribute(batch, 'neg_time', neg_time)
+        if self._id is None:
+            batch.neg, batch.neg_time = neg, neg_time
+        else:
+            self.add_batch_attribute(batch, 'neg', neg)
+            self.add_batch_attribute(batch, 'neg_time', neg_time)
         return batch

@@ -102,6 +102,9 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         self._win = None  # windowed-mode cursor, see _windowed_call
         self._standard_seeds = (list(seed_nodes_keys) == ['edge_src', 'edge_dst'] and
                                 list(seed_times_keys) == ['edge_time', 'edge_time'])
+        keys = list(zip(seed_nodes_keys, seed_times_keys))
+        self._extra_keys = (keys[2:] if keys[:2] == [('edge_src', 'edge_time'),
+                                                     ('edge_dst', 'edge_time')] else None)
         self._num_nbrs_c = (ctypes.c_int32 * len(num_nbrs))(*num_nbrs)
         self._handle = ctypes.c_void_p()   # tgm_recency*, created on first call
         self._device: Optional[torch.device] = None
@@ -205,6 +208,10 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         if sw is None or sw.store is not store or not (sw.e_lo <= lo and lo + n <= sw.e_hi):
             return None
         sn, stt = getattr(batch, node_attr, None), getattr(batch, time_attr, None)
+        if sw.batch_size:  # the producer kept the views it handed out: identity says untouched
+            j, r = divmod(lo - sw.e_lo, sw.batch_size)
+            if r == 0 and sn is sw.node_views[j] and stt is sw.time_views[j]:
+                return sw
         if not (isinstance(sn, Tensor) and isinstance(stt, Tensor)) or sn.numel() != n or \
                 stt.numel() != n or sn.data_ptr() != sw.nodes.data_ptr() + 4 * (lo - sw.e_lo) or \
                 stt.data_ptr() != sw.times.data_ptr() + 8 * (lo - sw.e_lo):
@@ -222,16 +229,33 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
     def _windowed_call(self, dg, batch):
         """Returns the decorated batch, or None when this call cannot be served from a window (the
         caller then continues on the ring kernels, after `_leave_window` moved the state over)."""
-        keys = list(zip(self._seed_nodes_keys, self._seed_times_keys))
-        if keys[:2] != [('edge_src', 'edge_time'), ('edge_dst', 'edge_time')]:
+        extra = self._extra_keys  # seed keys beyond [edge_src | edge_dst] (None: not windowable)
+        if extra is None:
             return None
-        rng = self._batch_range(dg, batch)
-        if rng is None or rng[2] == rng[1]:
-            return None
-        store, lo, hi = rng
+        slab = getattr(batch, '_slab', None)
+        if slab is not None and slab[0] is getattr(dg, '_storage', None) and \
+                batch.edge_src is slab[3] and batch.edge_dst is slab[4] and \
+                batch.edge_time is slab[5]:
+            store, lo, hi = slab[0], slab[1], slab[2]  # the loader's own views, untouched since
+        else:
+            rng = self._batch_range(dg, batch)
+            if rng is None or rng[2] == rng[1]:
+                return None
+            store, lo, hi = rng
         n = hi - lo
-        extra = keys[2:]
-        pub = self._published_window(store, batch, lo, n, *extra[0]) if len(extra) == 1 else None
+        pub = None
+        if len(extra) == 1:
+            # inlined fast case of _published_window: the producer's own views, by identity
+            pubs = getattr(batch, '_seed_windows', None)
+            sw = pubs.get(extra[0][0]) if pubs else None
+            if sw is not None and sw.store is store and sw.batch_size and sw.e_lo <= lo and \
+                    hi <= sw.e_hi:
+                jj, r = divmod(lo - sw.e_lo, sw.batch_size)
+                if r == 0 and getattr(batch, extra[0][0], None) is sw.node_views[jj] and \
+                        getattr(batch, extra[0][1], None) is sw.time_views[jj]:
+                    pub = sw
+            if pub is None and sw is not None:
+                pub = self._published_window(store, batch, lo, n, *extra[0])
         w = self._win
         if w is None:
             if self._win is False:  # already handed over to the ring since the last reset
@@ -246,7 +270,8 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
                 cache[key] = RecencyCSR(store, bs, directed=self._directed, colocate_x=True,
                                         e_start=lo)
             w = self._win = {'store': store, 'csr': cache[key], 'bs': bs, 'next': lo,
-                             'w_lo': lo, 'w_hi': lo, 'hops': None, 'start': lo, 'pub': None}
+                             'w_lo': lo, 'w_hi': lo, 'hops': None, 'start': lo, 'pub': None,
+                             'mask': None}
         elif w['store'] is not store or lo != w['next'] or \
                 (hi - lo != w['bs'] and hi != store.num_edges):
             return None
@@ -268,11 +293,11 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
             w['hops'] = csr.sample_window(w['w_lo'], w['w_hi'], self._num_nbrs, neg=neg)
             # per-batch views of the whole window in five C++ calls per hop (Tensor.split) rather
             # than five slicing calls per hop per batch; only the stream's last batch can be short
-            rows, split = P * bs, []
+            rows, split = P * bs, [[], [], [], [], []]  # split[attribute][hop] = per-batch views
             for hop in w['hops']:
-                split.append(tuple(v.split(rows) for v in (
-                    hop.seed_nids, hop.seed_times, hop.nbr_nids, hop.nbr_edge_time,
-                    hop.nbr_edge_x)))
+                for i, v in enumerate((hop.seed_nids, hop.seed_times, hop.nbr_nids,
+                                       hop.nbr_edge_time, hop.nbr_edge_x)):
+                    split[i].append(v.split(rows))
                 rows *= hop.nbr_nids.shape[1]
             w['split'] = split
             w['mask'] = None
@@ -282,9 +307,9 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
             return None
         # rows of this batch inside the window block, hop by hop
         j = (lo - w['w_lo']) // bs
-        parts = [tuple(v[j] for v in hop) for hop in w['split']]
+        split = w['split']
         dev = self._device
-        mask = w.get('mask')
+        mask = w['mask']
         if mask is None or mask[0] != n:
             mask = w['mask'] = (n, self._arange(0, n), self._arange(n, 2 * n),
                                 self._arange(2 * n, 3 * n))
@@ -293,6 +318,17 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
             extra = []
         else:
             mask = {'edge_src': mask[1], 'edge_dst': mask[2]}
+        if not extra:
+            w['next'] = hi
+            if self._id is None:  # the common case, without the per-attribute call overhead
+                batch.seed_nids = [v[j] for v in split[0]]
+                batch.seed_times = [v[j] for v in split[1]]
+                batch.nbr_nids = [v[j] for v in split[2]]
+                batch.nbr_edge_time = [v[j] for v in split[3]]
+                batch.nbr_edge_x = [v[j] for v in split[4]]
+                batch.seed_node_nbr_mask = mask
+                return batch
+        parts = [tuple(split[i][h][j] for i in range(5)) for h in range(len(self._num_nbrs))]
         if extra:  # seeds the window cannot know in advance: one launch per hop
             xs, xt, offset = [], [], 2 * n
             to_check = []
@@ -372,7 +408,8 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         self._win = False
 
     def __call__(self, dg, batch):
-        self._ensure_state(dg, ring=False)
+        if self._device is None:
+            self._ensure_state(dg, ring=False)
         if self._window_batches and self._win is not False:
             out = self._windowed_call(dg, batch)
             if out is not None:
