@@ -68,7 +68,8 @@ def config3(a, dev):
     hm.register('train', RandomNegativeEdgeSamplerHook(low=8227, high=N))
     hm.register('train', RecencyNeighborHook(
         num_nodes=N, num_nbrs=nn, seed_nodes_keys=['edge_src', 'edge_dst', 'neg'],
-        seed_times_keys=['edge_time', 'edge_time', 'neg_time'], window_batches=a.window_batches))
+        seed_times_keys=['edge_time', 'edge_time', 'neg_time'], window_batches=a.window_batches,
+        lazy_edge_x=bool(a.lazy_edge_x) and not a.train))
     nb = a.batches
 
     losses = []
@@ -405,6 +406,9 @@ def main():
                          'backward + Adam) in a CUDA graph and replay it per batch')
     ap.add_argument('--batches', type=int, default=200)
     ap.add_argument('--window-batches', type=int, default=25)
+    ap.add_argument('--lazy-edge-x', type=int, default=1,
+                    help='config 3 inference: the sampler hands out edge ids and the attention reads '
+                         'the feature rows in place (1) instead of materialising nbr_edge_x (0)')
     ap.add_argument('--edges', type=int, default=100_000_000)
     ap.add_argument('--nodes', type=int, default=1_000_000)
     a = ap.parse_args()

@@ -53,7 +53,12 @@ int tgm_device_count(void);
  * feature rows with the TMA unit (cp.async.bulk through shared-memory stages), 0 = with the warp's
  * own loads/stores.  Results are identical.  "gemm_fastf32": 1 (default) = token-sized fp32 GEMMs of
  * the transformer layers run on the tensor cores (tcgen05, fp32-accurate 9xBF16 emulation), 0 = on
- * cuBLAS's SIMT SGEMM; both hold the 1e-5 parity bar. */
+ * cuBLAS's SIMT SGEMM; both hold the 1e-5 parity bar.  "tc_linear": 1 = those GEMMs run on the
+ * hand-written tcgen05 kernel of tgm_tc_linear instead (default 0: correct but slower than the
+ * template instantiation, see profiles/README.md).  "dyg_fused_attn": 1 (default) = DyGFormer's
+ * per-head QK^T / softmax / PV is one kernel with the scores in shared memory, 0 = batched cuBLAS
+ * products with the scores in HBM.  "csr_tma_ctas_per_sm": cap on resident CTAs of the TMA sampler
+ * (0 = automatic).  "trace": 1 = tgm_csr_build prints its phase timings on stderr. */
 int tgm_set_option(const char *name, int value);
 
 /* ------------------------------------------------------------------------------------------
@@ -231,6 +236,12 @@ int tgm_csr_sample_edges_host(tgm_csr *, int64_t e_lo, int64_t e_hi, int32_t B, 
 int tgm_csr_sample_edges_ids(const tgm_csr *, int64_t e_lo, int64_t e_hi, int32_t B, int32_t k,
                              int search, int32_t *out_nid, int64_t *out_t, int32_t *out_eid,
                              tgm_stream stream);
+/* The same id form for general seeds (negatives, hop h > 0): tgm_csr_sample's arguments and rows,
+ * out_eid instead of out_x.  B <= 32.  With it a multi-hop neighbourhood is sampled without ever
+ * writing feature rows: tgm_attn_forward_rows reads them from the store by edge id. */
+int tgm_csr_sample_ids(const tgm_csr *, const int32_t *seeds, const int64_t *tq, const int64_t *cut,
+                       int64_t cut_group, int64_t S, int32_t B, int32_t k, int32_t *out_nid,
+                       int64_t *out_t, int32_t *out_eid, tgm_stream stream);
 int tgm_csr_sample_edges_mean(const tgm_csr *, int64_t e_lo, int64_t e_hi, int32_t B, int32_t k,
                               int search, int32_t *out_nid, int64_t *out_t, int32_t *out_eid,
                               float *out_mean, tgm_stream stream);
@@ -334,6 +345,15 @@ int tgm_attn_forward(tgm_attn *, const float *node_x, const float *nbr_node_feat
                      const int32_t *nbr_id, int64_t S, int32_t k, float *out, tgm_stream stream);
 /* The plain signature of attention.py:58-66 -- time features supplied by the caller: time_feat
  * float32[S,time_dim], nbr_time_feat float32[S,k,time_dim] (argument order as in the reference). */
+/* tgm_attn_forward with the sampled edge features read IN PLACE: edge_table float32[E, edge_dim]
+ * is the store's feature table and edge_rows int32[S*k] the edge id of every slot (-1 = padding:
+ * zeros), i.e. tgm_csr_sample_ids / tgm_csr_sample_edges_ids' out_eid.  The (S, k, edge_dim)
+ * nbr_edge_x block (165 MB per 200-edge batch for hop 1 of tgat.py:136-147 at k = [20, 20],
+ * D = 172) is neither written by the sampler nor re-read here.  Same result bit for bit. */
+int tgm_attn_forward_rows(tgm_attn *, const float *node_x, const float *nbr_node_feat,
+                          const float *edge_table, const int32_t *edge_rows, const int64_t *seed_t,
+                          const int64_t *nbr_t, const int32_t *nbr_id, int64_t S, int32_t k,
+                          float *out, tgm_stream stream);
 int tgm_attn_forward_feats(tgm_attn *, const float *node_x, const float *time_feat,
                            const float *edge_feat, const float *nbr_node_feat,
                            const float *nbr_time_feat, const int32_t *nbr_id, int64_t S, int32_t k,
@@ -487,6 +507,18 @@ int tgm_dyg_backward(tgm_dyg *, const float *node_x, int64_t num_nodes, const in
                      const int32_t *dst, const int64_t *edge_time, const int32_t *nbrs,
                      const int64_t *nbr_t, const float *nbr_x, int64_t B, const float *d_src,
                      const float *d_dst, const tgm_dyg_grads *grads, tgm_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense token-by-weight linear on the tensor cores, hand-written for sm_100a (tcgen05.mma
+ * kind::tf32, accumulator in tensor memory; every fp32 operand is split in flight into two TF32
+ * terms and three products are accumulated, so the result holds the 1e-5 parity bar):
+ *   out[S,N] = act(A[S,K] W[N,K]^T + bias[N] (+ residual[S,N])),  act = exact GELU when gelu != 0.
+ * This is what DyGFormer's in/out projections and FFN linears run on (reference:
+ * tgm/nn/encoder/dygformer.py:80-143, torch fp32 GEMMs).  residual may alias out; gelu and
+ * residual are exclusive; N % 4 == 0, K % 4 == 0, arrays 16-byte aligned; all device pointers. */
+int tgm_tc_linear(int64_t S, int32_t N, int32_t K, const float *A, const float *W,
+                  const float *bias, const float *residual, int gelu, float *out,
+                  tgm_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * TGN embedding.  Replaces GraphAttentionEmbedding (tgm/nn/encoder/tgn.py:14-40) as called from

@@ -336,12 +336,20 @@ def test_dygformer_gradients_vs_oracle_at_config5_dims():
         assert np.abs(got - want[name]).max() <= 5e-4 * max(1e-2, np.abs(want[name]).max()), name
 
 
-def test_dygformer_refuses_training_with_dropout():
+def test_dygformer_trains_with_dropout_disabled_and_says_so():
+    """The reference's default dropout=0.1 (examples/linkproppred/dygformer.py) must run: the fused
+    kernels do not apply dropout, a UserWarning says so once."""
+    from tgm_b200.nn import attention as _att
+    _att._DROPOUT_WARNED.discard('DyGFormer')
     m = DyGFormer(3, 4, 6, 4, output_dim=5, num_layers=1, max_input_sequence_length=8).to(DEV).train()
-    with pytest.raises(RuntimeError, match='dropout=0'):
-        m(torch.zeros(5, 3, device=DEV), torch.zeros(2, 1, dtype=torch.int64, device=DEV),
-          torch.zeros(1, dtype=torch.int64, device=DEV), torch.zeros(2, 7, dtype=torch.int32, device=DEV),
-          torch.zeros(2, 7, dtype=torch.int64, device=DEV), torch.zeros(2, 7, 4, device=DEV))
+    args = (torch.zeros(5, 3, device=DEV), torch.zeros(2, 1, dtype=torch.int64, device=DEV),
+            torch.zeros(1, dtype=torch.int64, device=DEV), torch.zeros(2, 7, dtype=torch.int32, device=DEV),
+            torch.zeros(2, 7, dtype=torch.int64, device=DEV), torch.zeros(2, 7, 4, device=DEV))
+    with pytest.warns(UserWarning, match='dropout p=0.1 is not applied'):
+        zs, zd = m(*args)
+    assert zs.shape == (1, 5) and bool(torch.isfinite(zs).all())
+    (zs.sum() + zd.sum()).backward()  # and it is differentiable
+    assert m.output_layer.weight.grad is not None
 
 
 # ---- gradients: tgm_attn_backward vs the reference's autograd ------------------------------------
@@ -399,14 +407,39 @@ def test_tgat_gradients_match_reference_autograd():
         _close(prm.grad, z['g.' + name], name)
 
 
-def test_training_mode_with_dropout_is_refused():
+def test_training_mode_with_default_dropout_runs_with_dropout_disabled():
+    from tgm_b200.nn import attention as _att
+    _att._DROPOUT_WARNED.discard('TemporalAttention')
     att = TemporalAttention(2, 3, 4, 6).to(DEV).train()
     te = Time2Vec(6).to(DEV)
-    with pytest.raises(RuntimeError, match='dropout=0'):
-        att.forward_fused(te, torch.zeros(2, 3, device=DEV), torch.zeros(2, 1, 3, device=DEV),
-                          torch.zeros(2, 1, 4, device=DEV), torch.zeros(2, dtype=torch.int64, device=DEV),
-                          torch.zeros(2, 1, dtype=torch.int64, device=DEV),
-                          torch.zeros(2, 1, dtype=torch.int32, device=DEV))
+    args = (te, torch.zeros(2, 3, device=DEV), torch.zeros(2, 1, 3, device=DEV),
+            torch.zeros(2, 1, 4, device=DEV), torch.zeros(2, dtype=torch.int64, device=DEV),
+            torch.zeros(2, 1, dtype=torch.int64, device=DEV),
+            torch.zeros(2, 1, dtype=torch.int32, device=DEV))
+    with pytest.warns(UserWarning, match='dropout p=0.1 is not applied'):
+        out = att.forward_fused(*args)
+    assert out.requires_grad and torch.equal(out, att.eval().forward_fused(*args))
+
+
+def test_time2vec_standalone_is_differentiable_and_takes_float_inputs():
+    """used outside the fused ops, the time encoder's w and b must receive gradients."""
+    te = Time2Vec(8).to(DEV)
+    dt = torch.tensor([0, 3, 17, 250000], device=DEV)
+    out = te(dt)
+    assert out.requires_grad
+    ref = torch.cos(torch.nn.functional.linear(dt.float().unsqueeze(-1), te.w.weight, te.w.bias))
+    assert float((out - ref).abs().max()) <= 1e-5
+    g = torch.randn_like(out)
+    out.backward(g)
+    gw, gb = te.w.weight.grad.clone(), te.w.bias.grad.clone()
+    te.zero_grad()
+    ref.backward(g)
+    assert torch.allclose(gw, te.w.weight.grad, rtol=1e-4, atol=1e-3)
+    assert torch.allclose(gb, te.w.bias.grad, rtol=1e-4, atol=1e-5)
+    x = torch.tensor([0.5, 2.25], device=DEV)  # non-integer inputs: same formula, device torch ops
+    assert torch.allclose(te(x), torch.cos(te.w(x.unsqueeze(-1))))
+    with torch.no_grad():
+        assert not te(dt).requires_grad
 
 
 # ---- TGN embedding (SURVEY section 8f row N4; parity UNPINNED: torch_geometric is third-party) -----
@@ -455,7 +488,7 @@ def test_graph_attention_embedding_without_edges_is_the_skip_projection():
     assert np.abs(out - want).max() <= TOL
 
 
-def test_graph_attention_embedding_state_dict_has_the_pyg_names_and_refuses_training():
+def test_graph_attention_embedding_state_dict_has_the_pyg_names_and_trains_with_default_dropout():
     enc = GraphAttentionEmbedding(100, 100, 172, Time2Vec(100))
     assert set(enc.state_dict()) == {
         'time_enc.w.weight', 'time_enc.w.bias', 'conv.lin_key.weight', 'conv.lin_key.bias',
@@ -463,7 +496,12 @@ def test_graph_attention_embedding_state_dict_has_the_pyg_names_and_refuses_trai
         'conv.lin_value.bias', 'conv.lin_edge.weight', 'conv.lin_skip.weight', 'conv.lin_skip.bias'}
     assert enc.conv.lin_edge.weight.shape == (100, 272)
     enc = enc.to(DEV).train()
-    with pytest.raises(RuntimeError):
-        enc(torch.zeros(2, 100, device=DEV), torch.zeros(2, dtype=torch.int64, device=DEV),
-            torch.zeros(2, 0, dtype=torch.int64, device=DEV), torch.zeros(0, dtype=torch.int64, device=DEV),
-            torch.zeros(0, 172, device=DEV))
+    # the default conv.dropout = 0.1 (as upstream) in training mode: runs with dropout disabled
+    # and warns once (the reference's TGN example trains the default-constructed module)
+    from tgm_b200.nn import attention as _att
+    _att._DROPOUT_WARNED.discard('GraphAttentionEmbedding')
+    with pytest.warns(UserWarning, match='dropout p=0.1 is not applied'):
+        out = enc(torch.zeros(2, 100, device=DEV), torch.zeros(2, dtype=torch.int64, device=DEV),
+                  torch.zeros(2, 0, dtype=torch.int64, device=DEV),
+                  torch.zeros(0, dtype=torch.int64, device=DEV), torch.zeros(0, 172, device=DEV))
+    assert out.shape == (2, 100) and out.requires_grad

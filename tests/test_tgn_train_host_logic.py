@@ -70,10 +70,15 @@ def test_inference_paths_do_not_record_autograd(fake):
     out = enc(torch.randn(6, 4), torch.zeros(6, dtype=torch.int64), torch.zeros(2, 0, dtype=torch.int64),
               torch.zeros(0, dtype=torch.int64), torch.zeros(0, 3))
     assert not out.requires_grad and 'tgm_gae_backward' not in fake.calls
-    with pytest.raises(RuntimeError):  # dropout 0.1 (the constructor's default) in training mode
-        enc.train()(torch.randn(6, 4), torch.zeros(6, dtype=torch.int64),
-                    torch.zeros(2, 0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64),
-                    torch.zeros(0, 3))
+    # dropout 0.1 (the constructor's default) in training mode: runs with dropout disabled and
+    # says so once (the reference's example trains the default-constructed module)
+    from tgm_b200.nn import attention as _att
+    _att._DROPOUT_WARNED.discard('GraphAttentionEmbedding')
+    with pytest.warns(UserWarning, match='dropout p=0.1 is not applied'):
+        out = enc.train()(torch.randn(6, 4), torch.zeros(6, dtype=torch.int64),
+                          torch.zeros(2, 0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64),
+                          torch.zeros(0, 3))
+    assert out.shape == (6, 6)
 
 
 def test_state_dict_interchanges_with_the_reference_checkpoint_layout(fake):

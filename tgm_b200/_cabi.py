@@ -81,6 +81,8 @@ SIGNATURES = {
     'tgm_csr_sample_edges_host': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_int, c_void_p]),
+    'tgm_csr_sample_ids': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+                                   c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     'tgm_csr_sample_edges_ids': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_int,
                                          c_void_p, c_void_p, c_void_p, c_void_p]),
     'tgm_csr_sample_edges_mean': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_int,
@@ -91,6 +93,8 @@ SIGNATURES = {
     'tgm_csr_sample_edges_host_mean': (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32,
                                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                c_void_p, c_int, c_void_p]),
+    'tgm_tc_linear': (c_int, [c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_int, c_void_p, c_void_p]),
     'tgm_join_row_bytes': (c_int64, [c_int32]),
     'tgm_join_pack': (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_int64, c_void_p,
                               c_void_p]),
@@ -111,6 +115,8 @@ SIGNATURES = {
     'tgm_attn_out_dim': (c_int, [c_void_p]),
     'tgm_attn_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    'tgm_attn_forward_rows': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     'tgm_attn_forward_feats': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     'tgm_attn_backward': (c_int, [c_void_p] + [c_void_p] * 6 + [c_int64, c_int32] + [c_void_p] * 12 +

@@ -129,7 +129,7 @@ attn_neighbor_kernel(const float *__restrict__ nbr_feat, const float *__restrict
                      const float *__restrict__ tb, const float *__restrict__ nbr_tf,
                      const float *__restrict__ QK, int64_t S, int k, int node_dim, int edge_dim,
                      int time_dim, int H, float scale, int vec_node, int vec_edge,
-                     float *__restrict__ U) {
+                     float *__restrict__ U, const int32_t *__restrict__ edge_rows) {
   extern __shared__ __align__(16) float smem[];
   const int key = node_dim + edge_dim + time_dim;
   const int pad = (4 - node_dim % 4) % 4, zs = (pad + key + 3) & ~3;
@@ -150,7 +150,10 @@ attn_neighbor_kernel(const float *__restrict__ nbr_feat, const float *__restrict
   for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
     const int64_t tq = nbr_tf ? 0 : seed_t[s];
     const float *nf = nbr_feat + s * int64_t(k) * node_dim;
-    const float *ef = edge_feat + s * int64_t(k) * edge_dim;
+    // edge features: the (S, k, edge_dim) block the sampler materialised, or -- edge_rows given --
+    // row edge_rows[s, n] of the feature TABLE `edge_feat` (the store's edge_x; -1 = padding ->
+    // zeros): the sampled rows are then read once, here, and never written anywhere
+    const float *ef = edge_rows ? edge_feat : edge_feat + s * int64_t(k) * edge_dim;
     const float *qks = QK + s * int64_t(H) * key;
     // feature rows go global -> shared with 16-byte asynchronous copies (no register staging, all
     // of a warp's rows in flight at once); the cosines below overlap their latency.  One warp per
@@ -172,13 +175,17 @@ attn_neighbor_kernel(const float *__restrict__ nbr_feat, const float *__restrict
 #pragma unroll 1
         for (int c = lane; c < (node_dim >> 2); c += 32, src += 128, dst += 128) cp_async16(dst, src);
       }
-      if (vec_edge) {
-        const float *src = ef + n * edge_dim + 4 * lane;
+      const int64_t erow = edge_rows ? int64_t(__ldg(edge_rows + s * k + n)) : int64_t(n);
+      if (erow < 0) {
+#pragma unroll 1
+        for (int c = lane; c < edge_dim; c += 32) zn[node_dim + c] = 0.f;
+      } else if (vec_edge) {
+        const float *src = ef + erow * edge_dim + 4 * lane;
         float *dst = zn + node_dim + 4 * lane;
 #pragma unroll 1
         for (int c = lane; c < (edge_dim >> 2); c += 32, src += 128, dst += 128) cp_async16(dst, src);
       } else {
-        const float *efr = ef + n * edge_dim;
+        const float *efr = ef + erow * edge_dim;
 #pragma unroll 1
         for (int c = lane; c < edge_dim; c += 32) zn[node_dim + c] = __ldg(efr + c);
       }
@@ -325,7 +332,8 @@ attn_neighbor_kernel(const float *__restrict__ nbr_feat, const float *__restrict
 template <int KT>
 int launch_attn_neighbor(const tgm_attn *a, const float *nbr_node_feat, const float *edge_feat,
                          const int64_t *seed_t, const int64_t *nbr_t, const int32_t *nbr_id,
-                         const float *nbr_tf, int64_t S, int k, cudaStream_t st) {
+                         const float *nbr_tf, int64_t S, int k, cudaStream_t st,
+                         const int32_t *edge_rows) {
   const AttnLayout L = attn_layout(k, a->node_dim, a->key, a->H, KT == 0);
   TGM_REQUIRE(L.bytes <= 200 * 1024, "tgm_attn_forward: k * key_dim too large for shared memory");
   if (L.bytes > 48 * 1024)
@@ -338,7 +346,7 @@ int launch_attn_neighbor(const tgm_attn *a, const float *nbr_node_feat, const fl
   attn_neighbor_kernel<KT><<<grid_for(S, 1, ctas_per_sm), kAttnThreads, L.bytes, st>>>(
       nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, a->tw, a->tb, nbr_tf, a->QK, S, k,
       a->node_dim, a->edge_dim, a->time_dim, a->H, 1.0f / sqrtf(float(a->hd)), vec_node, vec_edge,
-      a->U);
+      a->U, edge_rows);
   TGM_LAUNCH_CHECK();
   return TGM_OK;
 }
@@ -499,7 +507,8 @@ extern "C" int tgm_attn_out_dim(const tgm_attn *a) { return a ? a->out_dim : TGM
 int attn_forward_impl(tgm_attn *a, const float *node_x, const float *nbr_node_feat,
                              const float *edge_feat, const int64_t *seed_t, const int64_t *nbr_t,
                              const float *seed_tf, const float *nbr_tf, const int32_t *nbr_id,
-                             int64_t S, int32_t k, float *out, tgm_stream stream) {
+                             int64_t S, int32_t k, float *out, tgm_stream stream,
+                             const int32_t *edge_rows) {
   TGM_REQUIRE(a != nullptr, "tgm_attn_forward: handle is NULL");
   TGM_REQUIRE(S >= 0 && k >= 1, "tgm_attn_forward: bad sizes");
   if (S == 0) return TGM_OK;
@@ -542,10 +551,10 @@ int attn_forward_impl(tgm_attn *a, const float *node_x, const float *nbr_node_fe
   {
     const int kt = (key + 31) / 32;
     int rc;
-    if (kt <= 4) rc = launch_attn_neighbor<4>(a, nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, nbr_tf, S, k, st);
-    else if (kt <= 9) rc = launch_attn_neighbor<9>(a, nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, nbr_tf, S, k, st);
-    else if (kt <= 14) rc = launch_attn_neighbor<14>(a, nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, nbr_tf, S, k, st);
-    else rc = launch_attn_neighbor<0>(a, nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, nbr_tf, S, k, st);
+    if (kt <= 4) rc = launch_attn_neighbor<4>(a, nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, nbr_tf, S, k, st, edge_rows);
+    else if (kt <= 9) rc = launch_attn_neighbor<9>(a, nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, nbr_tf, S, k, st, edge_rows);
+    else if (kt <= 14) rc = launch_attn_neighbor<14>(a, nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, nbr_tf, S, k, st, edge_rows);
+    else rc = launch_attn_neighbor<0>(a, nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, nbr_tf, S, k, st, edge_rows);
     if (rc) return rc;
   }
   // O[s,h,:] = W_V,h u[s,h,:]   (W_V = rows [out, 2 out) of W_KV)
@@ -567,6 +576,16 @@ extern "C" int tgm_attn_forward(tgm_attn *a, const float *node_x, const float *n
   TGM_REQUIRE(seed_t && nbr_t, "tgm_attn_forward: NULL array argument");
   return attn_forward_impl(a, node_x, nbr_node_feat, edge_feat, seed_t, nbr_t, nullptr, nullptr,
                            nbr_id, S, k, out, stream);
+}
+
+extern "C" int tgm_attn_forward_rows(tgm_attn *a, const float *node_x, const float *nbr_node_feat,
+                                     const float *edge_table, const int32_t *edge_rows,
+                                     const int64_t *seed_t, const int64_t *nbr_t,
+                                     const int32_t *nbr_id, int64_t S, int32_t k, float *out,
+                                     tgm_stream stream) {
+  TGM_REQUIRE(seed_t && nbr_t && edge_rows, "tgm_attn_forward_rows: NULL array argument");
+  return attn_forward_impl(a, node_x, nbr_node_feat, edge_table, seed_t, nbr_t, nullptr, nullptr,
+                           nbr_id, S, k, out, stream, edge_rows);
 }
 
 extern "C" int tgm_attn_forward_feats(tgm_attn *a, const float *node_x, const float *time_feat,

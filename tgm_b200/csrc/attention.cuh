@@ -37,4 +37,4 @@ struct tgm_attn {
 int attn_forward_impl(tgm_attn *a, const float *node_x, const float *nbr_node_feat,
                       const float *edge_feat, const int64_t *seed_t, const int64_t *nbr_t,
                       const float *seed_tf, const float *nbr_tf, const int32_t *nbr_id, int64_t S,
-                      int32_t k, float *out, tgm_stream stream);
+                      int32_t k, float *out, tgm_stream stream, const int32_t *edge_rows = nullptr);

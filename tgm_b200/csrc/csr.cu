@@ -424,7 +424,8 @@ __device__ __forceinline__ void walk_chunk(const Entry *__restrict__ entries,
                                            const SeedWin &mine, int64_t s_base, int nseeds, int k,
                                            int32_t *__restrict__ out_nid,
                                            int64_t *__restrict__ out_t,
-                                           float4 *__restrict__ out_x4, int lane) {
+                                           float4 *__restrict__ out_x4, int lane,
+                                           int32_t *__restrict__ out_eid = nullptr) {
   int64_t wstart = shfl_i64(mine.wstart, 0);
   int nwin = __shfl_sync(0xffffffffu, mine.nwin, 0);
   Entry cur = load_window_entry(entries, wstart, nwin, lane);
@@ -434,7 +435,7 @@ __device__ __forceinline__ void walk_chunk(const Entry *__restrict__ entries,
     const int64_t wstart_n = shfl_i64(mine.wstart, nxt);
     const int nwin_n = __shfl_sync(0xffffffffu, mine.nwin, nxt);
     const Entry ahead = load_window_entry(entries, wstart_n, nwin_n, lane);  // one seed ahead
-    emit_fast(x4, D4, wstart, nwin, q, k, s_base + i, cur, out_nid, out_t, out_x4, lane);
+    emit_fast(x4, D4, wstart, nwin, q, k, s_base + i, cur, out_nid, out_t, out_x4, lane, out_eid);
     cur = ahead;
     wstart = wstart_n;
     nwin = nwin_n;
@@ -479,7 +480,8 @@ csr_sample_fast_kernel(const Entry *__restrict__ entries, const int64_t *__restr
                        const int32_t *__restrict__ seeds, const int64_t *__restrict__ tq,
                        const int64_t *__restrict__ cut, int64_t cut_group, int64_t S, int B, int k,
                        int32_t *__restrict__ out_nid, int64_t *__restrict__ out_t,
-                       float4 *__restrict__ out_x4, unsigned long long *__restrict__ ticket) {
+                       float4 *__restrict__ out_x4, unsigned long long *__restrict__ ticket,
+                       int32_t *__restrict__ out_eid) {
   const int lane = threadIdx.x & 31;
   const int64_t nchunks = (S + 31) >> 5;
   const int64_t wstride = int64_t(gridDim.x) * (kFastThreads >> 5);
@@ -498,7 +500,7 @@ csr_sample_fast_kernel(const Entry *__restrict__ entries, const int64_t *__restr
       }
     }
     const int nseeds = S - s_base < 32 ? int(S - s_base) : 32;
-    walk_chunk(entries, x4, D4, mine, s_base, nseeds, k, out_nid, out_t, out_x4, lane);
+    walk_chunk(entries, x4, D4, mine, s_base, nseeds, k, out_nid, out_t, out_x4, lane, out_eid);
   }
 }
 
@@ -1240,7 +1242,8 @@ extern "C" int tgm_csr_sample(const tgm_csr *c, const int32_t *seeds, const int6
     if (rc != TGM_OK) return rc;
     csr_sample_fast_kernel<<<cfg.fast_grid, kFastThreads, 0, st>>>(
         c->entries, c->rowptr, reinterpret_cast<const float4 *>(cfg.xsrc), c->N, c->D / 4, seeds,
-        tq, cut, cut_group, S, B, k, out_nid, out_t, reinterpret_cast<float4 *>(out_x), ticket);
+        tq, cut, cut_group, S, B, k, out_nid, out_t, reinterpret_cast<float4 *>(out_x), ticket,
+        nullptr);
   } else {
     DISPATCH_SAMPLE(csr_sample_kernel, c->entries, c->rowptr, cfg.xsrc, c->N, c->D, seeds, tq,
                     cut, cut_group, S, B, k, out_nid, out_t, out_x);
@@ -1341,6 +1344,31 @@ int upload_slab(const tgm_csr *c, int64_t e_lo, int64_t nE, const int32_t *h_src
   return TGM_OK;
 }
 }  // namespace
+
+extern "C" int tgm_csr_sample_ids(const tgm_csr *c, const int32_t *seeds, const int64_t *tq,
+                                  const int64_t *cut, int64_t cut_group, int64_t S, int32_t B,
+                                  int32_t k, int32_t *out_nid, int64_t *out_t, int32_t *out_eid,
+                                  tgm_stream stream) {
+  TGM_REQUIRE(c != nullptr, "tgm_csr_sample_ids: csr is NULL");
+  TGM_REQUIRE(S >= 0, "tgm_csr_sample_ids: S must be >= 0");
+  TGM_REQUIRE(cut_group >= 1, "tgm_csr_sample_ids: cut_group must be >= 1");
+  TGM_REQUIRE(B >= 1 && B <= 32, "tgm_csr_sample_ids: B must be in [1, 32]");
+  TGM_REQUIRE(k >= 1 && k <= B, "tgm_csr_sample_ids: k must be in [1, B]");
+  if (S == 0) return TGM_OK;
+  TGM_REQUIRE(seeds && tq && cut && (out_nid || out_t || out_eid),
+              "tgm_csr_sample_ids: NULL array argument");
+  DeviceGuard g(c->device);
+  cudaStream_t st = as_stream(stream);
+  unsigned long long *ticket = nullptr;
+  int rc = new_ticket(c, st, &ticket);
+  if (rc != TGM_OK) return rc;
+  const int grid = grid_for((S + 31) / 32, kFastThreads / 32, TGM_FAST_MIN_BLOCKS);
+  csr_sample_fast_kernel<<<grid, kFastThreads, 0, st>>>(c->entries, c->rowptr, nullptr, c->N, 0,
+                                                        seeds, tq, cut, cut_group, S, B, k, out_nid,
+                                                        out_t, nullptr, ticket, out_eid);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
 
 extern "C" int tgm_csr_sample_edges_ids(const tgm_csr *c, int64_t e_lo, int64_t e_hi, int32_t B,
                                         int32_t k, int search, int32_t *out_nid, int64_t *out_t,
@@ -1539,6 +1567,16 @@ extern "C" int tgm_set_option(const char *name, int value) {
   if (std::strcmp(name, "csr_tma_ctas_per_sm") == 0) {
     TGM_REQUIRE(value >= 0 && value <= 32, "tgm_set_option: csr_tma_ctas_per_sm must be in [0, 32]");
     g_csr_tma_ctas_per_sm = value;
+    return TGM_OK;
+  }
+  if (std::strcmp(name, "dyg_fused_attn") == 0) {
+    TGM_REQUIRE(value == 0 || value == 1, "tgm_set_option: dyg_fused_attn must be 0 or 1");
+    tgm::g_dyg_fused_attn = value;
+    return TGM_OK;
+  }
+  if (std::strcmp(name, "tc_linear") == 0) {
+    TGM_REQUIRE(value == 0 || value == 1, "tgm_set_option: tc_linear must be 0 or 1");
+    tgm::g_tc_linear = value;
     return TGM_OK;
   }
   if (std::strcmp(name, "trace") == 0) {

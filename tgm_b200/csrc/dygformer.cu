@@ -24,6 +24,10 @@
 
 using namespace tgm;
 
+namespace tgm {
+int g_dyg_fused_attn = 1;  // tgm_set_option("dyg_fused_attn", 0|1)
+}
+
 struct DygLayerDev {
   float *in_w, *in_b, *out_w, *out_b, *f1_w, *f1_b, *f2_w, *f2_b, *ln0_w, *ln0_b, *ln1_w, *ln1_b;
 };
@@ -225,6 +229,94 @@ softmax_rows_kernel(float *__restrict__ s, int64_t rows, int cols, float scale) 
     for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float inv = 1.f / sum;
     for (int c = lane; c < cols; c += 32) row[c] *= inv;
+  }
+}
+
+// Fused self-attention core of one (sequence, head): S = scale * Q K^T, row softmax, O = P V, with Q,
+// K, V, S resident in shared memory -- the scores never reach HBM (nn.MultiheadAttention inside
+// TransformerEncoder.forward, dygformer.py:117-143; T = 2 * num_patches tokens, hd = E / H).
+// Layout in shared memory: Qt[hd][T+4] and Kt[hd][T+4] (d-major, so a thread's 4 queries / 4 keys
+// of one feature are ONE 128-bit load and neighbouring threads read neighbouring keys: conflict
+// free), V[T][hd] natural, S[T][T+4].  256 threads: 4 x 4 register micro-tiles of S (one per
+// thread at T = 64), a warp per 8 rows for the softmax, 4 x 4 micro-tiles of O.  fp32 FMA.
+__global__ void __launch_bounds__(256)
+dyg_attn_core_kernel(const float *__restrict__ QKV, int T, int E, int H, float scale,
+                     float *__restrict__ O) {
+  extern __shared__ __align__(16) float sm[];
+  const int hd = E / H, TS = T + 4;
+  float *Qt = sm, *Kt = Qt + hd * TS, *V = Kt + hd * TS, *Sc = V + T * hd;
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.x / H;
+  const int h = blockIdx.x % H;
+  const float *base = QKV + b * T * 3 * E + h * hd;
+  // stage: coalesced reads along d; Q and K transposed on the way in
+  for (int i = tid; i < T * hd; i += blockDim.x) {
+    const int t = i / hd, d = i - t * hd;
+    const float *row = base + int64_t(t) * 3 * E + d;
+    Qt[d * TS + t] = __ldg(row) * scale;  // the reference scales q before the product
+    Kt[d * TS + t] = __ldg(row + E);
+    V[i] = __ldg(row + 2 * E);
+  }
+  __syncthreads();
+  const int tq = T >> 2;  // micro-tiles per dimension
+  for (int mt = tid; mt < tq * tq; mt += blockDim.x) {
+    const int q0 = (mt / tq) << 2, k0 = (mt % tq) << 2;
+    float a[4][4] = {};
+#pragma unroll 4
+    for (int d = 0; d < hd; ++d) {
+      const float4 qv = *reinterpret_cast<const float4 *>(Qt + d * TS + q0);
+      const float4 kv = *reinterpret_cast<const float4 *>(Kt + d * TS + k0);
+      const float q[4] = {qv.x, qv.y, qv.z, qv.w}, kk[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[i][j] = fmaf(q[i], kk[j], a[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4 *>(Sc + (q0 + i) * TS + k0) = make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
+  }
+  __syncthreads();
+  {  // softmax over the keys of every query row: one warp per row
+    const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    for (int r = warp; r < T; r += nw) {
+      float *row = Sc + r * TS;
+      float m = -INFINITY;
+      for (int c = lane; c < T; c += 32) m = fmaxf(m, row[c]);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float sum = 0.f;
+      for (int c = lane; c < T; c += 32) {
+        const float e = expf(row[c] - m);
+        row[c] = e;
+        sum += e;
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = 1.f / sum;
+      for (int c = lane; c < T; c += 32) row[c] *= inv;
+    }
+  }
+  __syncthreads();
+  const int td = hd >> 2;
+  for (int mt = tid; mt < tq * td; mt += blockDim.x) {
+    const int q0 = (mt / td) << 2, d0 = (mt % td) << 2;
+    float a[4][4] = {};
+#pragma unroll 4
+    for (int k = 0; k < T; ++k) {
+      const float4 vv = *reinterpret_cast<const float4 *>(V + k * hd + d0);
+      const float v[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float p = Sc[(q0 + i) * TS + k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[i][j] = fmaf(p, v[j], a[i][j]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4 *>(O + (b * T + q0 + i) * E + h * hd + d0) =
+          make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
   }
 }
 
@@ -489,6 +581,10 @@ dyg_frontend_bwd_kernel(const int32_t *__restrict__ src, const int32_t *__restri
 int linear(cublasHandle_t blas, int64_t S, int N, int K, const float *A, const float *W,
            const float *b, const float *residual, int gelu, float *out, float *tmp,
            cudaStream_t st) {
+  if (g_tc_linear && S >= 2048) {  // hand-written tcgen05 kernel, 3xTF32 split (tc_linear.cu)
+    const int rc = tc3_linear(S, N, K, A, W, b, residual, gelu, out, st);
+    if (rc != 0) return rc < 0 ? rc : TGM_OK;
+  }
   if (g_gemm_fastf32 && S >= 2048) {
     const int rc = fastf32_linear(S, N, K, A, W, b, residual, gelu, out, st);
     if (rc != 0) return rc < 0 ? rc : TGM_OK;
@@ -657,6 +753,15 @@ extern "C" int tgm_dyg_forward(tgm_dyg *m, const float *node_x, int64_t num_node
     if (int rc = linear(m->blas, tokens, 3 * E, E, m->Xn, ly.in_w, ly.in_b, nullptr, 0, m->QKV,
                         nullptr, st))
       return rc;
+    const size_t attn_smem = (size_t(2) * hd * (T + 4) + size_t(T) * hd + size_t(T) * (T + 4)) * 4;
+    if (g_dyg_fused_attn && T % 4 == 0 && hd % 4 == 0 && E % 4 == 0 && attn_smem <= 200 * 1024) {
+      // QK^T, softmax and PV of every (sequence, head) in one kernel, scores on chip
+      if (attn_smem > 48 * 1024)
+        TGM_CUDA(cudaFuncSetAttribute(dyg_attn_core_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_smem)));
+      dyg_attn_core_kernel<<<int(B * H), 256, attn_smem, st>>>(m->QKV, T, E, H, scale, m->O);
+      TGM_LAUNCH_CHECK();
+    } else {
     for (int h = 0; h < H; ++h)  // S[b,h,q,k] = Q_bh[q,:] . K_bh[k,:]
       DYG_BLAS(cublasSgemmStridedBatched(
           m->blas, CUBLAS_OP_T, CUBLAS_OP_N, T, T, hd, &one, m->QKV + E + h * hd, 3 * E,
@@ -669,6 +774,7 @@ extern "C" int tgm_dyg_forward(tgm_dyg *m, const float *node_x, int64_t num_node
           m->blas, CUBLAS_OP_N, CUBLAS_OP_N, hd, T, T, &one, m->QKV + 2 * E + h * hd, 3 * E,
           int64_t(T) * 3 * E, m->S + size_t(h) * T * T, T, int64_t(H) * T * T, &zero,
           m->O + h * hd, E, int64_t(T) * E, int(B)));
+    }
     if (int rc = linear(m->blas, tokens, E, E, m->O, ly.out_w, ly.out_b, m->X, 0, m->X, m->tmp, st))
       return rc;
     layernorm_kernel<<<grid_for(tokens, 8, 8), 256, 0, st>>>(m->X, ly.ln1_w, ly.ln1_b, tokens, E,

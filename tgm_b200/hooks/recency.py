@@ -70,14 +70,18 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
 
     def __init__(self, num_nodes: int, num_nbrs: List[int], seed_nodes_keys: List[str],
                  seed_times_keys: List[str], directed: bool = False,
-                 id: Optional[str] = None, window_batches: Optional[int] = None) -> None:
+                 id: Optional[str] = None, window_batches: Optional[int] = None,
+                 lazy_edge_x: bool = False) -> None:
         """`window_batches` (an addition to the reference signature) controls pre-sampling: while
         the loader walks one device store front to back in equal event batches, the neighbourhoods
         of `window_batches` upcoming batches are sampled by ONE launch per hop over the stateless
         adjacency (tgm_csr_*) and each call only slices views.  Outputs are identical; any other
         call pattern (another store, a skipped batch, time-unit batches) hands the state over to
         the ring kernels.  None (default) = 1024 batches when the adjacency fits comfortably in
-        free HBM; 0 = always drive the ring kernels batch by batch."""
+        free HBM; 0 = always drive the ring kernels batch by batch.
+        `lazy_edge_x=True` (windowed mode only): `batch.nbr_edge_x[h]` are `LazyEdgeRows` -- edge
+        ids into the store's feature table, which the fused attention reads in place -- instead of
+        (S, k, D) blocks; they behave as tensors and materialise on first ordinary use."""
         if not len(num_nbrs):
             raise ValueError('num_nbrs must be non-empty')
         if not all(isinstance(x, int) and x > 0 for x in num_nbrs):
@@ -97,6 +101,7 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         if window_batches is not None and (not isinstance(window_batches, int) or
                                            window_batches < 0):
             raise ValueError('window_batches must be a non-negative integer or None')
+        self._lazy_edge_x = bool(lazy_edge_x)
         self._window_auto = window_batches is None
         self._window_batches = _DEFAULT_WINDOW_BATCHES if window_batches is None else window_batches
         self._win = None  # windowed-mode cursor, see _windowed_call
@@ -290,7 +295,8 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
                 if not (0 <= pub.low and pub.high <= self._num_nodes):
                     self._validate([(extra[0][0], neg, True)])  # one sync per window
             w['pub'] = pub
-            w['hops'] = csr.sample_window(w['w_lo'], w['w_hi'], self._num_nbrs, neg=neg)
+            w['hops'] = csr.sample_window(w['w_lo'], w['w_hi'], self._num_nbrs, neg=neg,
+                                          lazy_edge_x=self._lazy_edge_x)
             # per-batch views of the whole window in five C++ calls per hop (Tensor.split) rather
             # than five slicing calls per hop per batch; only the stream's last batch can be short
             rows, split = P * bs, [[], [], [], [], []]  # split[attribute][hop] = per-batch views
@@ -381,8 +387,9 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         """How many batches fit the pre-sampling budget (a quarter of the free HBM, at most 16 GB):
         multi-hop outputs grow as prod(k) -- 165 MB per batch for k=[20,20] at D=172."""
         per_batch, seeds = 0, seeds_per_edge * bs
+        row = 16 if self._lazy_edge_x else 12 + 4 * self._edge_x_dim
         for k in self._num_nbrs:
-            per_batch += seeds * k * (12 + 4 * self._edge_x_dim)
+            per_batch += seeds * k * row
             seeds *= k
         free, _ = torch.cuda.mem_get_info(self._device)
         budget = min(free // 4, 16 << 30)

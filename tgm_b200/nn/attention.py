@@ -107,24 +107,62 @@ class Time2Vec(nn.Module):
         self.w.weight = nn.Parameter(torch.from_numpy(w).float())
         self.w.bias = nn.Parameter(torch.zeros(time_dim))
 
-    @torch.no_grad()
     def forward(self, x: Tensor) -> Tensor:
+        """Integer time deltas (the hot-path case: int64 differences of timestamps) go through
+        `tgm_time2vec`; used standalone under autograd the weights receive their gradient
+        (d/dw = -sin(w t + b) t, d/db = -sin(w t + b)).  Floating-point inputs, which the kernel's
+        int64 interface cannot carry exactly, are evaluated with the same formula by device torch
+        ops (no host sync to inspect the values)."""
         dev = _need_cuda(self.w.weight, 'Time2Vec')
         dt = x.to(device=dev)
-        if dt.dtype != torch.int64:
-            # the reference casts to float32 first; integer-valued inputs (time deltas) are the
-            # hot-path case and are passed exactly
-            if not torch.equal(dt, dt.round()):
-                raise ValueError('Time2Vec on the B200 path takes integer time deltas')
-            dt = dt.to(torch.int64)
-        dt = dt.contiguous()
-        out = torch.empty((*dt.shape, self.time_dim), dtype=torch.float32, device=dev)
-        w = _f32(self.w.weight).reshape(-1)
-        b = _f32(self.w.bias)
-        _cabi.check(_cabi.lib.tgm_time2vec(dt.data_ptr(), dt.numel(), w.data_ptr(), b.data_ptr(),
-                                           self.time_dim, out.data_ptr(),
-                                           _cabi.current_stream(dev)))
-        return out
+        if dt.is_floating_point():
+            return torch.cos(self.w(dt.float().unsqueeze(-1)))
+        dt = dt.to(torch.int64).contiguous()
+        if torch.is_grad_enabled() and (self.w.weight.requires_grad or self.w.bias.requires_grad):
+            return _Time2VecFn.apply(dt, self.w.weight, self.w.bias, self.time_dim)
+        with torch.no_grad():
+            return _time2vec_kernel(dt, self.w.weight, self.w.bias, self.time_dim, dev)
+
+
+def _time2vec_kernel(dt: Tensor, weight: Tensor, bias: Tensor, time_dim: int, dev) -> Tensor:
+    out = torch.empty((*dt.shape, time_dim), dtype=torch.float32, device=dev)
+    w = _f32(weight).reshape(-1)
+    b = _f32(bias)
+    _cabi.check(_cabi.lib.tgm_time2vec(dt.data_ptr(), dt.numel(), w.data_ptr(), b.data_ptr(),
+                                       time_dim, out.data_ptr(), _cabi.current_stream(dev)))
+    return out
+
+
+class _Time2VecFn(torch.autograd.Function):
+    """cos(w * float(dt) + b): forward on the CUDA kernel, backward -sin(arg) * (dt, 1)."""
+
+    @staticmethod
+    def forward(ctx, dt, weight, bias, time_dim):
+        ctx.save_for_backward(dt, weight, bias)
+        return _time2vec_kernel(dt, weight, bias, time_dim, dt.device)
+
+    @staticmethod
+    def backward(ctx, g):
+        dt, weight, bias = ctx.saved_tensors
+        tf = dt.float().reshape(-1, 1)
+        s = -torch.sin(tf * weight.reshape(1, -1) + bias) * g.reshape(-1, weight.shape[0])
+        return None, (s * tf).sum(0).reshape(weight.shape), s.sum(0), None
+
+
+_DROPOUT_WARNED = set()
+
+
+def warn_dropout_disabled(name: str, p: float) -> None:
+    """The fused kernels of this package do not apply dropout (a mask drawn here could not follow
+    the reference's RNG stream, and the backward passes are written for the dropout-free graph):
+    a module constructed with the reference's default p > 0 trains with dropout DISABLED and says
+    so once, instead of refusing the shipped examples' default configuration."""
+    if name not in _DROPOUT_WARNED:
+        _DROPOUT_WARNED.add(name)
+        import warnings
+        warnings.warn(f'{name}: dropout p={p} is not applied on the B200 path; training proceeds '
+                      'with dropout disabled (set dropout=0 to silence this)', UserWarning,
+                      stacklevel=3)
 
 
 class TemporalAttention(nn.Module):
@@ -184,7 +222,7 @@ class TemporalAttention(nn.Module):
                 time_encoder: Optional[Time2Vec] = None) -> Tensor:
         """The reference signature (attention.py:58-66): time features supplied by the caller."""
         if self.training and self.dropout.p > 0:
-            raise RuntimeError('TemporalAttention on the B200 path is forward/eval only')
+            warn_dropout_disabled('TemporalAttention', self.dropout.p)
         dev = _need_cuda(node_x, 'TemporalAttention')
         S, k = valid_nbr_mask.shape
         te = time_encoder if time_encoder is not None else self._dummy_encoder(dev)
@@ -209,16 +247,33 @@ class TemporalAttention(nn.Module):
         features are computed inside the kernel from (seed_times, nbr_times).  Differentiable
         when autograd is recording (dropout must be 0 in training mode)."""
         if self.training and self.dropout.p > 0:
-            raise RuntimeError('TemporalAttention on the B200 path trains with dropout=0 only '
-                               '(use eval() for inference)')
+            warn_dropout_disabled('TemporalAttention', self.dropout.p)
         dev = _need_cuda(node_x, 'TemporalAttention')
         params = [self.W_Q.weight, self.W_KV.weight, self.W_O.weight, self.W_O.bias,
                   self.layer_norm.weight, self.layer_norm.bias, time_encoder.w.weight,
                   time_encoder.w.bias]
+        from tgm_b200.sampler import LazyEdgeRows
+        lazy = edge_feat if isinstance(edge_feat, LazyEdgeRows) else None
         if torch.is_grad_enabled() and any(
-                t.requires_grad for t in (*params, node_x, nbr_node_feat, edge_feat)):
+                t.requires_grad for t in (*params, node_x, nbr_node_feat) +
+                (() if lazy is not None else (edge_feat,))):
+            if lazy is not None:
+                edge_feat = lazy.materialize()  # the backward pass takes the feature block
             return _FusedAttention.apply(self, time_encoder, seed_times, nbr_times, nbr_nids,
                                          node_x, nbr_node_feat, edge_feat, *params)
+        if lazy is not None:  # sampled rows read in place from the store's table, by edge id
+            with torch.no_grad():
+                S, k = nbr_nids.shape
+                out = torch.empty((S, self.out_dim), dtype=torch.float32, device=dev)
+                args = [_f32(node_x), _f32(nbr_node_feat), _f32(lazy.table),
+                        lazy.rows.to(torch.int32).contiguous(),
+                        seed_times.to(torch.int64).contiguous(),
+                        nbr_times.to(torch.int64).contiguous(),
+                        nbr_nids.to(torch.int32).contiguous()]
+                _cabi.check(_cabi.lib.tgm_attn_forward_rows(
+                    self._handle(time_encoder, dev), *[a.data_ptr() for a in args], S, k,
+                    out.data_ptr(), _cabi.current_stream(dev)))
+                return out
         with torch.no_grad():
             return self._forward_fused_nograd(time_encoder, node_x, nbr_node_feat, edge_feat,
                                               seed_times, nbr_times, nbr_nids, dev)

@@ -169,10 +169,12 @@ class DyGFormer(nn.Module):
                 neighbours_time: Tensor, neighbours_edge_feat: Tensor) -> Tuple[Tensor, Tensor]:
         """Rows [0, E_b) of `neighbours*` belong to the sources, [E_b, 2 E_b) to the destinations
         (dygformer.py:262-270); extra rows (e.g. negatives) are ignored, as in the reference."""
-        if self.training and any(m.p > 0 for m in self.modules() if isinstance(m, nn.Dropout)) or \
-                self.training and any(tr.multi_head_attention.dropout > 0 for tr in self.transformers):
-            raise RuntimeError('DyGFormer on the B200 path trains with dropout=0 only '
-                               '(use eval() for inference)')
+        if self.training:
+            ps = [m.p for m in self.modules() if isinstance(m, nn.Dropout)] + \
+                 [tr.multi_head_attention.dropout for tr in self.transformers]
+            if any(p > 0 for p in ps):
+                from tgm_b200.nn.attention import warn_dropout_disabled
+                warn_dropout_disabled('DyGFormer', max(ps))
         dev = _need_cuda(node_x, 'DyGFormer')
         B = edge_index.shape[1]
         k = self.max_input_sequence_length - 1

@@ -376,8 +376,8 @@ class GraphAttentionEmbedding(nn.Module):
                 msg: Tensor) -> Tensor:
         dev = self.conv.lin_key.weight.device
         if self.training and self.conv.dropout > 0:
-            raise RuntimeError('GraphAttentionEmbedding on the B200 path trains with '
-                               'conv.dropout = 0 only (use eval() for inference)')
+            from tgm_b200.nn.attention import warn_dropout_disabled
+            warn_dropout_disabled('GraphAttentionEmbedding', self.conv.dropout)
         x = x.to(dev)
         lu = last_update.to(device=dev, dtype=torch.int64).contiguous()
         ei = edge_index.to(device=dev, dtype=torch.int64).contiguous()

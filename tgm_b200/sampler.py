@@ -18,6 +18,82 @@ from torch import Tensor
 from tgm_b200 import _cabi
 
 
+class LazyEdgeRows:
+    """`nbr_edge_x` of a hop that was never materialised: `rows[s, c]` is the store
+    edge whose feature row slot (s, c) holds (-1 = padding -> zeros), `table` the store's
+    float32 [E, D] feature table.  The fused consumers (`TemporalAttention.forward_fused` ->
+    tgm_attn_forward_rows) read the rows in place; anything else sees an ordinary tensor: torch
+    functions and tensor attributes materialise it on first use (`materialize()`, cached)."""
+
+    __slots__ = ('table', 'rows', '_dense')
+
+    def __init__(self, table: Tensor, rows: Tensor) -> None:
+        self.table, self.rows, self._dense = table, rows, None
+
+    @property
+    def shape(self) -> torch.Size:
+        return torch.Size((*self.rows.shape, self.table.shape[1]))
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.table.dtype
+
+    @property
+    def device(self) -> torch.device:
+        return self.rows.device
+
+    @property
+    def ndim(self) -> int:
+        return self.rows.ndim + 1
+
+    def size(self, dim: Optional[int] = None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def __len__(self) -> int:
+        return self.rows.shape[0]
+
+    def materialize(self) -> Tensor:
+        if self._dense is None:
+            r = self.rows
+            self._dense = self.table[r.clamp(min=0).long()] * (r >= 0).unsqueeze(-1)
+        return self._dense
+
+    def split(self, n: int):
+        return tuple(LazyEdgeRows(self.table, r) for r in self.rows.split(n))
+
+    def __getitem__(self, idx):
+        if isinstance(idx, slice):  # a row range stays lazy
+            return LazyEdgeRows(self.table, self.rows[idx])
+        return self.materialize()[idx]
+
+    def __getattr__(self, name):  # any other tensor attribute / method
+        return getattr(self.materialize(), name)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        def dense(v):
+            if isinstance(v, LazyEdgeRows):
+                return v.materialize()
+            if isinstance(v, (list, tuple)):
+                return type(v)(dense(u) for u in v)
+            return v
+        return func(*dense(args), **{k: dense(v) for k, v in (kwargs or {}).items()})
+
+
+def _delegate(name):
+    def op(self, *args, **kwargs):
+        return getattr(self.materialize(), name)(*args, **kwargs)
+    op.__name__ = name
+    return op
+
+
+# operators are looked up on the type, not through __getattr__: forward them to the dense tensor
+for _n in ('add', 'radd', 'sub', 'rsub', 'mul', 'rmul', 'truediv', 'rtruediv', 'matmul', 'rmatmul',
+           'neg', 'pow', 'eq', 'ne', 'lt', 'le', 'gt', 'ge', 'iter', 'array', 'bool', 'float'):
+    setattr(LazyEdgeRows, f'__{_n}__', _delegate(f'__{_n}__'))
+LazyEdgeRows.__hash__ = object.__hash__
+
+
 @dataclass
 class HopSample:
     """One hop of sampled neighbourhoods (rows follow the reference's per-batch seed order)."""
@@ -25,7 +101,7 @@ class HopSample:
     seed_times: Tensor     # int64 (S,)
     nbr_nids: Tensor       # int32 (S, k)
     nbr_edge_time: Tensor  # int64 (S, k)
-    nbr_edge_x: Tensor     # float32 (S, k, D)
+    nbr_edge_x: Tensor     # float32 (S, k, D), or LazyEdgeRows (sample_window(lazy_edge_x=True))
 
 
 class RecencyCSR:
@@ -80,6 +156,19 @@ class RecencyCSR:
             int(B), int(k), nid.data_ptr(), nt.data_ptr(), nx.data_ptr() if self.D else None,
             _cabi.current_stream(self.device)))
         return nid, nt, nx
+
+    def sample_ids(self, seeds: Tensor, tq: Tensor, cut: Tensor, k: int, B: int,
+                   cut_group: int = 1):
+        """`sample` without the feature block (tgm_csr_sample_ids): (nbr_nids, nbr_edge_time, eid)."""
+        S, dev = seeds.numel(), self.device
+        nid = torch.empty((S, k), dtype=torch.int32, device=dev)
+        nt = torch.empty((S, k), dtype=torch.int64, device=dev)
+        eid = torch.empty((S, k), dtype=torch.int32, device=dev)
+        _cabi.check(_cabi.lib.tgm_csr_sample_ids(
+            self._handle, seeds.data_ptr(), tq.data_ptr(), cut.data_ptr(), int(cut_group), S,
+            int(B), int(k), nid.data_ptr(), nt.data_ptr(), eid.data_ptr(),
+            _cabi.current_stream(dev)))
+        return nid, nt, eid
 
     def sample_edges(self, e_lo: int, e_hi: int, k: int, B: int, out=None):
         """Hop 0 for seeds = endpoints of stream edges [e_lo, e_hi) (src rows then dst rows per
@@ -181,17 +270,25 @@ class RecencyCSR:
         return seeds.contiguous(), times.contiguous(), cut
 
     def sample_window(self, e_lo: int, e_hi: int, num_nbrs: Sequence[int],
-                      neg: Optional[Tensor] = None) -> List[HopSample]:
+                      neg: Optional[Tensor] = None, lazy_edge_x: bool = False) -> List[HopSample]:
         """All hops for the loader batches covering stream edges [e_lo, e_hi).
 
         Rows are the concatenation over batches of what RecencyNeighborHook puts on each batch;
-        `split_window` cuts them back into per-batch views."""
+        `split_window` cuts them back into per-batch views.  `lazy_edge_x`: the hops carry
+        `LazyEdgeRows` (edge ids into the store's feature table) instead of feature blocks."""
         B = max(num_nbrs)
         hops: List[HopSample] = []
         seeds, times, cut = self.window_seed_tensors(e_lo, e_hi, neg)
         group = 1
+        lazy = lazy_edge_x and self.D > 0 and B <= 32
         for h, k in enumerate(num_nbrs):
-            if h == 0 and neg is None:
+            if lazy:
+                if h == 0 and neg is None and not self.directed:
+                    nid, nt, eid = self.sample_edges_ids(e_lo, e_hi, k, B)
+                else:
+                    nid, nt, eid = self.sample_ids(seeds, times, cut, k, B, cut_group=group)
+                nx = LazyEdgeRows(self._storage._x, eid)
+            elif h == 0 and neg is None:
                 nid, nt, nx = self.sample_edges(e_lo, e_hi, k, B)
             else:
                 nid, nt, nx = self.sample(seeds, times, cut, k, B, cut_group=group)
