@@ -337,6 +337,11 @@ def run_b200(a):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the B200 path has no CPU fallback')
+    # stdout carries exactly ONE line, the JSON the driver parses: anything native code prints
+    # there (NCCL's version banner does, whatever NCCL_DEBUG_FILE says) is sent to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     numa = bind_to_gpu_numa_node(local) if not a.no_numa_bind else {'node': None, 'why': 'disabled'}
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -683,7 +688,8 @@ def run_b200(a):
             'clocks': clocks.result(), 'numa': numa,
             'build_s': build_max,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

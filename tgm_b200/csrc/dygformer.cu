@@ -249,13 +249,41 @@ dyg_attn_core_kernel(const float *__restrict__ QKV, int T, int E, int H, float s
   const int64_t b = blockIdx.x / H;
   const int h = blockIdx.x % H;
   const float *base = QKV + b * T * 3 * E + h * hd;
-  // stage: coalesced reads along d; Q and K transposed on the way in
-  for (int i = tid; i < T * hd; i += blockDim.x) {
-    const int t = i / hd, d = i - t * hd;
-    const float *row = base + int64_t(t) * 3 * E + d;
-    Qt[d * TS + t] = __ldg(row) * scale;  // the reference scales q before the product
-    Kt[d * TS + t] = __ldg(row + E);
-    V[i] = __ldg(row + 2 * E);
+  // stage: 128-bit coalesced reads along d, batches of independent loads in flight (one L2
+  // latency per batch, not per element); Q and K transposed on the way in
+  {
+    const int hd4 = hd >> 2, total = T * hd4;
+    constexpr int kBatch = 4;
+    for (int i0 = tid; i0 < total; i0 += kBatch * blockDim.x) {
+      float4 q[kBatch], kk[kBatch], vv[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < total) {
+          const int t = i / hd4, d4 = i - t * hd4;
+          const float4 *row = reinterpret_cast<const float4 *>(base + int64_t(t) * 3 * E) + d4;
+          q[u] = __ldg(row);
+          kk[u] = __ldg(row + (E >> 2));
+          vv[u] = __ldg(row + (E >> 1));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < total) {
+          const int t = i / hd4, d = (i - t * hd4) << 2;
+          Qt[(d + 0) * TS + t] = q[u].x * scale;  // the reference scales q before the product
+          Qt[(d + 1) * TS + t] = q[u].y * scale;
+          Qt[(d + 2) * TS + t] = q[u].z * scale;
+          Qt[(d + 3) * TS + t] = q[u].w * scale;
+          Kt[(d + 0) * TS + t] = kk[u].x;
+          Kt[(d + 1) * TS + t] = kk[u].y;
+          Kt[(d + 2) * TS + t] = kk[u].z;
+          Kt[(d + 3) * TS + t] = kk[u].w;
+          *reinterpret_cast<float4 *>(V + t * hd + d) = vv[u];
+        }
+      }
+    }
   }
   __syncthreads();
   const int tq = T >> 2;  // micro-tiles per dimension
