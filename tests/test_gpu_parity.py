@@ -841,10 +841,47 @@ def test_host_buffer_entry_point_matches_device_path():
         csr.sample_edges_host(lo, hi, k, k, host_in, outs[0], slot=99)
 
 
+@pytest.mark.parametrize('window', [None, 3, 0], ids=['default', 'w3', 'ring'])
+@pytest.mark.parametrize('name', ['a', 'b', 'c'])
+def test_time_unit_batches_match_reference_fixture(name, window):
+    """batch_unit='s' (tgm/data/loader.py:101-156) against the unmodified reference
+    (tests/golden/make_golden_timeunit.py): uneven, partly empty time windows, 1 and 2 hops,
+    directed, no features -- on the ring kernels and on pre-sampled windows (the loader publishes
+    its batch plan; per node the push order (batch, time, side, edge) is (time, side, edge))."""
+    import os
+    from tests._golden import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, f'timeunit_{name}.npz'))
+    N, nn, directed = int(z['N']), [int(v) for v in z['num_nbrs']], bool(int(z['directed']))
+    x = torch.from_numpy(z['x']) if int(z['has_x']) else None
+    ei = torch.from_numpy(np.stack([z['src'], z['dst']], 1))
+    dg = DGraph(DGData.from_raw(torch.from_numpy(z['t']), ei, x, time_delta='s'), device=DEV)
+    kw = {} if window is None else {'window_batches': window}
+    hook = RecencyNeighborHook(num_nodes=N, num_nbrs=nn, seed_nodes_keys=['edge_src', 'edge_dst'],
+                               seed_times_keys=['edge_time', 'edge_time'], directed=directed, **kw)
+    hm = HookManager(keys=['g'])
+    hm.register('g', hook)
+    nb = 0
+    with hm.activate('g'):
+        for epoch in range(2):  # the second epoch after a reset replays the first
+            nb = 0
+            for batch in DGDataLoader(dg, batch_size=int(z['bs']), batch_unit='s', hook_manager=hm):
+                lo, hi = int(z[f'b{nb}_lo']), int(z[f'b{nb}_hi'])
+                assert batch.edge_src.numel() == hi - lo
+                for h in range(len(nn)):
+                    got = (batch.seed_nids[h], batch.seed_times[h], batch.nbr_nids[h],
+                           batch.nbr_edge_time[h], batch.nbr_edge_x[h])
+                    want = tuple(z[f'b{nb}_h{h}_{n_}'] for n_ in ('seed', 'tq', 'nid', 'nt', 'nx'))
+                    assert_hop_equal(to_np(got), want, f'{name} batch{nb} hop{h}')
+                assert (isinstance(hook._win, dict) and hook._win.get('mode') == 'time') == (window != 0)
+                nb += 1
+            assert nb == int(z['nb'])
+            hm.reset_state()
+
+
 def test_time_unit_batches_run_through_the_hook():
-    """batch_unit='s' (tgm/data/loader.py:101-156): batches are time windows of unequal size, so a
-    windowed hook leaves its window on the first irregular batch and continues on the ring
-    kernels; outputs equal the oracle driven with the same batches."""
+    """batch_unit='s' on a larger random stream: windowed (default) and ring modes both equal the
+    C oracle driven with the same batches; a time-window run hands over to the ring like an
+    event-ordered one (state_tensors exports it)."""
     N, D, nn = 200, 3, [5]
     src, dst, t, x = _random_stream(9, N, 3000, 600, D)
     ei = torch.from_numpy(np.stack([src, dst], 1))
@@ -870,6 +907,14 @@ def test_time_unit_batches_run_through_the_hook():
                 assert_hop_equal(to_np(got), want[0], f'window{window} edge{lo}')
                 seen = hi
         assert seen == len(src)
+        st = hook.state_tensors()  # windowed: exported from the adjacency; ring: the live state
+        B = max(nn)
+        rot = (st['write_pos'].cpu().numpy()[:, None] + np.arange(B)[None, :]) % B
+        o_rot = (oracle.write_pos[:, None].astype(np.int64) + np.arange(B)[None, :]) % B
+        assert np.array_equal(np.take_along_axis(st['ids'].cpu().numpy(), rot, 1),
+                              np.take_along_axis(oracle.ids, o_rot, 1))
+        assert np.array_equal(np.take_along_axis(st['times'].cpu().numpy(), rot, 1),
+                              np.take_along_axis(oracle.times, o_rot, 1))
 
 
 def test_dgraph_to_cuda_uploads_a_host_side_graph():

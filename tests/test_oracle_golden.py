@@ -594,3 +594,26 @@ def test_c_oracle_equals_the_unmodified_reference_on_the_config1_epoch():
         assert [checksum_np(v) for v in w[2:]] == [int(v) for v in want], f'batch {b}'
         if f'b{b}_nid' in z.files and b not in differs:
             assert np.array_equal(w[2], z[f'b{b}_nid']) and np.array_equal(w[3], z[f'b{b}_nt'])
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN_DIR, 'timeunit_*.npz'))),
+                         ids=lambda p: os.path.basename(p)[:-4])
+def test_ring_oracles_match_the_reference_under_time_window_batching(path):
+    """Time-unit batches (tgm/data/loader.py:101-156) through the reference hook: uneven and empty
+    windows.  The C and numpy ring oracles driven with the fixture's batch ranges."""
+    from oracle.c_oracle import CRing
+    from oracle.recency_oracle import RingOracle
+    z = np.load(path)
+    N, nn, directed = int(z['N']), [int(v) for v in z['num_nbrs']], bool(int(z['directed']))
+    x = z['x'] if int(z['has_x']) else None
+    D = 0 if x is None else x.shape[1]
+    for oracle in (CRing(N, nn, D, directed), RingOracle(N, nn, D, directed)):
+        for b in range(int(z['nb'])):
+            lo, hi = int(z[f'b{b}_lo']), int(z[f'b{b}_hi'])
+            s = np.concatenate([z['src'][lo:hi], z['dst'][lo:hi]]).astype(np.int32)
+            q = np.concatenate([z['t'][lo:hi]] * 2)
+            got = oracle.hook_call(s, q, z['src'][lo:hi], z['dst'][lo:hi], z['t'][lo:hi],
+                                   None if x is None else x[lo:hi])
+            for h in range(len(nn)):
+                for u, name in zip(got[h][2:], ('nid', 'nt', 'nx')):
+                    assert np.array_equal(u, z[f'b{b}_h{h}_{name}']), f'batch {b} hop {h} {name}'

@@ -20,6 +20,37 @@ from tgm_b200.exceptions import (EmptyBatchError, EventOrderedConversionError,
 _ON_EMPTY = ('skip', 'raise', None)
 
 
+class _TimePlan:
+    """Edge-index bounds of every time-window batch of a loader over an edge-only device store."""
+
+    _CHUNK = 4096
+
+    def __init__(self, store, dg: DGraph, starts: range, batch_size: int) -> None:
+        import torch
+        lo0, hi0 = store.edge_range(dg._slice)
+        th = torch.arange(starts.start, starts.start + (len(starts) + 1) * batch_size, batch_size,
+                          device=store.device, dtype=torch.int64)
+        b = torch.searchsorted(store._t[lo0:hi0], th) + lo0
+        self.store, self.starts, self.batch_size = store, starts, batch_size
+        self.bounds_dev = b                       # int64[nb + 1], non-decreasing
+        self.bounds = b.tolist()                  # one host sync for the whole plan
+        self.e_start = lo0
+        self._chunk = None
+
+    def views(self, j: int):
+        """(src, dst, t, x) views of batch j, served from per-chunk `Tensor.split` tuples."""
+        c, r = divmod(j, self._CHUNK)
+        if self._chunk is None or self._chunk[0] != c:
+            a = c * self._CHUNK
+            bnd = self.bounds[a:a + self._CHUNK + 1]
+            sizes = [y - x for x, y in zip(bnd, bnd[1:])]
+            st = self.store
+            self._chunk = (c, tuple(None if v is None else v[bnd[0]:bnd[-1]].split(sizes)
+                                    for v in (st._src, st._dst, st._t, st._x)))
+        ch = self._chunk[1]
+        return ch[0][r], ch[1][r], ch[2][r], None if ch[3] is None else ch[3][r]
+
+
 class DGDataLoader:
     def __init__(self, dg: DGraph, batch_size: int = 1, batch_unit: str = 'r',
                  on_empty: Optional[str] = 'skip', hook_manager=None, **kwargs: Any) -> None:
@@ -65,6 +96,14 @@ class DGDataLoader:
             self._fast = (store,) + tuple(store.edge_range(dg._slice))
             self._origin = self._fast[1] - self._fast[1] % batch_size
             self._chunk = None
+        # The same for time-window batches (batch j = edges with start + j*bs <= t < start + (j+1)*bs,
+        # graph.py:130-152): the window bounds of the whole plan come from ONE device searchsorted,
+        # and the plan travels on every batch (`batch._plan`) so that the neighbour hook can
+        # pre-sample many upcoming windows per launch.
+        self._time_plan = None
+        if not self._by_events and getattr(store, 'edges_only', False) and \
+                dg.device == store.device and len(self._starts):
+            self._time_plan = _TimePlan(store, dg, self._starts, batch_size)
 
     @property
     def dgraph(self) -> DGraph:
@@ -73,9 +112,32 @@ class DGDataLoader:
     def __len__(self) -> int:
         return len(self._starts)
 
+    def _load_time(self, start: int) -> DGBatch:
+        plan = self._time_plan
+        j = (start - plan.starts.start) // plan.batch_size
+        lo, hi = plan.bounds[j], plan.bounds[j + 1]
+        src, dst, t, x = plan.views(j)
+        n = hi - lo
+        batch = DGBatch(src, dst, t, x if n else None)
+        if n:
+            batch._slab = (plan.store, lo, hi, src, dst, t)
+        batch._plan = (plan, j)
+        hm = self._hook_manager
+        if hm is not None:
+            src_dg = self._dg
+            s = src_dg._slice
+            t_lo, t_hi = start, start + plan.batch_size - 1  # slice_time's inclusive bounds
+            view = DGraph._from_storage(plan.store, src_dg._time_delta, src_dg._device, DGSliceTracker(
+                t_lo if s.start_time is None else max(t_lo, s.start_time),
+                t_hi if s.end_time is None else min(t_hi, s.end_time), s.start_idx, s.end_idx))
+            batch = hm.execute_active_hooks(view, batch)
+        return batch
+
     def _load(self, start: int) -> DGBatch:
         if self._fast is not None:
             return self._load_fast(start)
+        if self._time_plan is not None:
+            return self._load_time(start)
         dg = self._slice_op(start, start + self._batch_size)
         batch = dg.materialize()
         if self._hook_manager is not None:

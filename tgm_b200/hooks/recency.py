@@ -262,6 +262,8 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
             if pub is None and sw is not None:
                 pub = self._published_window(store, batch, lo, n, *extra[0])
         w = self._win
+        if w is not None and w.get('mode') == 'time':
+            return None  # a time-window run: this batch does not continue it
         if w is None:
             if self._win is False:  # already handed over to the ring since the last reset
                 return None
@@ -383,6 +385,116 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         self.add_batch_attribute(batch, 'seed_node_nbr_mask', mask)
         return batch
 
+    # -- windowed mode for time-window batches ------------------------------------------------
+    def _emit_empty(self, dg, batch):
+        """No seeds on this batch: empty CPU tensors with exact dtypes per hop (recency.py:127-137)."""
+        hops = len(self._num_nbrs)
+        add = self.add_batch_attribute
+        add(batch, 'seed_nids', [torch.empty(0, dtype=torch.int32) for _ in range(hops)])
+        add(batch, 'seed_times', [torch.empty(0, dtype=torch.int64) for _ in range(hops)])
+        add(batch, 'nbr_nids', [torch.empty(0, dtype=torch.int32) for _ in range(hops)])
+        add(batch, 'nbr_edge_time', [torch.empty(0, dtype=torch.int64) for _ in range(hops)])
+        add(batch, 'nbr_edge_x', [torch.empty(0, dg.edge_x_dim).float() for _ in range(hops)])
+        mask = {}
+        for name in self._seed_nodes_keys:
+            v = getattr(batch, name, None)
+            if isinstance(v, Tensor):
+                mask[name] = torch.arange(0, 0, device=v.device)
+        add(batch, 'seed_node_nbr_mask', mask)
+        return batch
+
+    def _windowed_time_call(self, dg, batch, plan, j: int):
+        """Time-window batches (tgm/data/loader.py:101-156) served from pre-sampled windows.  The
+        loader published its plan (edge bounds of every batch); since batches are disjoint time
+        ranges, a node's push order (batch, time, side, edge) is simply (time, side, edge): the
+        adjacency built with ONE batch spanning the stream, with a history cut per seed = the
+        first edge of its batch.  Seeds [src | dst] only; anything else returns None (ring path)."""
+        if self._extra_keys != [] or plan.store is not getattr(dg, '_storage', None):
+            return None
+        store, bounds = plan.store, plan.bounds
+        lo, hi = bounds[j], bounds[j + 1]
+        n = hi - lo
+        slab = getattr(batch, '_slab', None)
+        if n and not (slab is not None and slab[0] is store and batch.edge_src is slab[3] and
+                      batch.edge_dst is slab[4] and batch.edge_time is slab[5]):
+            return None
+        w = self._win
+        if w is None:
+            if self._window_auto and not self._window_feasible(store):
+                return None
+            from tgm_b200.sampler import RecencyCSR
+            cache = store._node_cache
+            key = ('recency_csr_time', plan.e_start, self._directed)
+            if key not in cache:
+                cache[key] = RecencyCSR(store, max(1, store.num_edges), directed=self._directed,
+                                        colocate_x=True, e_start=plan.e_start)
+            w = self._win = {'mode': 'time', 'store': store, 'plan': plan, 'csr': cache[key],
+                             'next_j': j, 'j_lo': j, 'j_hi': j, 'split': None, 'next': lo}
+        elif w.get('mode') != 'time' or w['plan'] is not plan or j != w['next_j']:
+            return None
+        if j >= w['j_hi']:  # pre-sample the next window of batches
+            dev = self._device
+            nb = len(bounds) - 1
+            j_hi = min(j + self._window_batches, nb)
+            per_edge = 0
+            rows = 2
+            for k in self._num_nbrs:
+                per_edge += rows * k * (16 if self._lazy_edge_x else 12 + 4 * self._edge_x_dim)
+                rows *= k
+            if 'budget' not in w:
+                free, _ = torch.cuda.mem_get_info(dev)
+                w['budget'] = min(free // 4, 16 << 30)
+            while j_hi > j + 1 and (bounds[j_hi] - lo) * per_edge > w['budget']:
+                j_hi = j + max(1, (j_hi - j) // 2)
+            e_lo, e_hi = lo, bounds[j_hi]
+            sizes = [bounds[i + 1] - bounds[i] for i in range(j, j_hi)]
+            split = None
+            if e_hi > e_lo:
+                bd = plan.bounds_dev[j:j_hi + 1]
+                sz = bd[1:] - bd[:-1]
+                batch_of = torch.repeat_interleave(torch.arange(j_hi - j, device=dev), sz)
+                start_of = bd[batch_of]                                  # first edge of the batch
+                e_idx = torch.arange(e_lo, e_hi, device=dev)
+                row_src = (e_idx - e_lo) + (start_of - e_lo)             # 2*(start-e_lo) + offset
+                row_dst = row_src + sz[batch_of]
+                S0 = 2 * (e_hi - e_lo)
+                seeds = torch.empty(S0, dtype=torch.int32, device=dev)
+                times = torch.empty(S0, dtype=torch.int64, device=dev)
+                cut = torch.empty(S0, dtype=torch.int64, device=dev)
+                es, ed, et = store._src[e_lo:e_hi], store._dst[e_lo:e_hi], store._t[e_lo:e_hi]
+                seeds[row_src], seeds[row_dst] = es, ed
+                times[row_src], times[row_dst] = et, et
+                cut[row_src], cut[row_dst] = start_of, start_of
+                csr, B = w['csr'], self._max_nbrs
+                lazy = self._lazy_edge_x and self._edge_x_dim > 0 and B <= 32
+                split, group, rows = [[], [], [], [], []], 1, [2 * v for v in sizes]
+                for k in self._num_nbrs:
+                    if lazy:
+                        from tgm_b200.sampler import LazyEdgeRows
+                        nid, nt, eid = csr.sample_ids(seeds, times, cut, k, B, cut_group=group)
+                        nx = LazyEdgeRows(store._x, eid)
+                    else:
+                        nid, nt, nx = csr.sample(seeds, times, cut, k, B, cut_group=group)
+                    for i, v in enumerate((seeds, times, nid, nt, nx)):
+                        split[i].append(v.split(rows))
+                    seeds, times = nid.reshape(-1), nt.reshape(-1)
+                    group *= k
+                    rows = [r * k for r in rows]
+            w['j_lo'], w['j_hi'], w['split'] = j, j_hi, split
+        w['next_j'] = j + 1
+        w['next'] = hi
+        if n == 0:
+            return self._emit_empty(dg, batch)
+        i = j - w['j_lo']
+        split = w['split']
+        add = self.add_batch_attribute
+        for a, name in enumerate(('seed_nids', 'seed_times', 'nbr_nids', 'nbr_edge_time',
+                                  'nbr_edge_x')):
+            add(batch, name, [v[i] for v in split[a]])
+        add(batch, 'seed_node_nbr_mask', {'edge_src': self._arange(0, n),
+                                          'edge_dst': self._arange(n, 2 * n)})
+        return batch
+
     def _window_budget_batches(self, bs: int, seeds_per_edge: int = 2) -> int:
         """How many batches fit the pre-sampling budget (a quarter of the free HBM, at most 16 GB):
         multi-hop outputs grow as prod(k) -- 165 MB per batch for k=[20,20] at D=172."""
@@ -418,7 +530,9 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         if self._device is None:
             self._ensure_state(dg, ring=False)
         if self._window_batches and self._win is not False:
-            out = self._windowed_call(dg, batch)
+            plan = getattr(batch, '_plan', None)
+            out = self._windowed_call(dg, batch) if plan is None else \
+                self._windowed_time_call(dg, batch, plan[0], plan[1])
             if out is not None:
                 return out
             self._leave_window()
