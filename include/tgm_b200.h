@@ -53,9 +53,9 @@ int tgm_device_count(void);
  * feature rows with the TMA unit (cp.async.bulk through shared-memory stages), 0 = with the warp's
  * own loads/stores.  Results are identical.  "gemm_fastf32": 1 (default) = token-sized fp32 GEMMs of
  * the transformer layers run on the tensor cores (tcgen05, fp32-accurate 9xBF16 emulation), 0 = on
- * cuBLAS's SIMT SGEMM; both hold the 1e-5 parity bar.  "tc_linear": 1 = those GEMMs run on the
- * hand-written tcgen05 kernel of tgm_tc_linear instead (default 0: correct but slower than the
- * template instantiation, see profiles/README.md).  "dyg_fused_attn": 1 (default) = DyGFormer's
+ * cuBLAS's SIMT SGEMM; both hold the 1e-5 parity bar.  "tc_linear": which of those GEMMs run on the
+ * hand-written tcgen05 kernel of tgm_tc_linear instead: 0 = none, 1 = all, 2 (default) = the ones
+ * where it measured faster than the template instantiation (the GELU-fused FFN linear).  "dyg_fused_attn": 1 (default) = DyGFormer's
  * per-head QK^T / softmax / PV is one kernel with the scores in shared memory, 0 = batched cuBLAS
  * products with the scores in HBM.  "csr_tma_ctas_per_sm": cap on resident CTAs of the TMA sampler
  * (0 = automatic).  "trace": 1 = tgm_csr_build prints its phase timings on stderr. */
@@ -519,6 +519,13 @@ int tgm_dyg_backward(tgm_dyg *, const float *node_x, int64_t num_nodes, const in
 int tgm_tc_linear(int64_t S, int32_t N, int32_t K, const float *A, const float *W,
                   const float *bias, const float *residual, int gelu, float *out,
                   tgm_stream stream);
+/* The same contract on the CUTLASS sm_100 FastF32 collective (9xBF16 emulation, TMA, 2-SM tcgen05
+ * tiles of 256x128x16 -- K steps of 32 / 64 and 1-SM 128x128 tiles measured 6-20 % slower on the
+ * DyGFormer shapes) that DyGFormer's linears use by default.  TGM_ERR_INVALID when the shape is
+ * unsupported or the library was built without the CUTLASS header tree. */
+int tgm_fastf32_linear(int64_t S, int32_t N, int32_t K, const float *A, const float *W,
+                       const float *bias, const float *residual, int gelu, float *out,
+                       tgm_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * TGN embedding.  Replaces GraphAttentionEmbedding (tgm/nn/encoder/tgn.py:14-40) as called from

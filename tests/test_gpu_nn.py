@@ -262,12 +262,23 @@ def test_dygformer_tensor_core_gemm_matches_cublas_path_and_oracle():
     try:
         for flag in (1, 0):
             _cabi.check(_cabi.lib.tgm_set_option(b'gemm_fastf32', flag))
+            _cabi.check(_cabi.lib.tgm_set_option(b'tc_linear', 0))
             outs[flag] = [v.detach().cpu().numpy() for v in m(*args)]
+        _cabi.check(_cabi.lib.tgm_set_option(b'gemm_fastf32', 1))
+        # every token linear on the hand-written tcgen05 kernel (3xTF32), and the default mix
+        for mode, key in ((1, 'tc_all'), (2, 'tc_default')):
+            _cabi.check(_cabi.lib.tgm_set_option(b'tc_linear', mode))
+            outs[key] = [v.detach().cpu().numpy() for v in m(*args)]
+        # the per-head attention as batched cuBLAS products instead of the fused on-chip kernel
+        _cabi.check(_cabi.lib.tgm_set_option(b'dyg_fused_attn', 0))
+        outs['unfused_attn'] = [v.detach().cpu().numpy() for v in m(*args)]
     finally:
         _cabi.check(_cabi.lib.tgm_set_option(b'gemm_fastf32', 1))
+        _cabi.check(_cabi.lib.tgm_set_option(b'tc_linear', 2))
+        _cabi.check(_cabi.lib.tgm_set_option(b'dyg_fused_attn', 1))
     p = {k_: v.detach().cpu().numpy() for k_, v in m.state_dict().items()}
     want = nn_oracle.dygformer_forward(p, 1, 2, 2, node_x, ei, t, nbrs, nt, ef)
-    for flag in (1, 0):
+    for flag in outs:
         for got, w in zip(outs[flag], want):
             assert np.abs(got - w).max() <= TOL, flag
     assert max(np.abs(a - b).max() for a, b in zip(outs[0], outs[1])) <= TOL

@@ -95,6 +95,8 @@ SIGNATURES = {
                                                c_void_p, c_int, c_void_p]),
     'tgm_tc_linear': (c_int, [c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int, c_void_p, c_void_p]),
+    'tgm_fastf32_linear': (c_int, [c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int, c_void_p, c_void_p]),
     'tgm_join_row_bytes': (c_int64, [c_int32]),
     'tgm_join_pack': (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_int64, c_void_p,
                               c_void_p]),

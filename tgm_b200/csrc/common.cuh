@@ -44,7 +44,7 @@ extern int g_gemm_fastf32;  // tgm_set_option("gemm_fastf32", 0|1); default 1
 // into two TF32 terms, three products accumulated in TMEM).  N % 4 == 0, K % 4 == 0.
 int tc3_linear(int64_t S, int N, int K, const float *A, const float *W, const float *bias,
                const float *residual, int gelu, float *out, cudaStream_t stream);
-extern int g_tc_linear;  // tgm_set_option("tc_linear", 0|1); default 0 (see tc_linear.cu)
+extern int g_tc_linear;  // tgm_set_option("tc_linear", 0|1|2); default 2 (see tc_linear.cu)
 extern int g_dyg_fused_attn;  // tgm_set_option("dyg_fused_attn", 0|1); default 1
 
 inline cudaStream_t as_stream(tgm_stream s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -1575,7 +1575,7 @@ extern "C" int tgm_set_option(const char *name, int value) {
     return TGM_OK;
   }
   if (std::strcmp(name, "tc_linear") == 0) {
-    TGM_REQUIRE(value == 0 || value == 1, "tgm_set_option: tc_linear must be 0 or 1");
+    TGM_REQUIRE(value >= 0 && value <= 2, "tgm_set_option: tc_linear must be 0, 1 or 2");
     tgm::g_tc_linear = value;
     return TGM_OK;
   }

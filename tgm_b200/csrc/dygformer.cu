@@ -609,7 +609,9 @@ dyg_frontend_bwd_kernel(const int32_t *__restrict__ src, const int32_t *__restri
 int linear(cublasHandle_t blas, int64_t S, int N, int K, const float *A, const float *W,
            const float *b, const float *residual, int gelu, float *out, float *tmp,
            cudaStream_t st) {
-  if (g_tc_linear && S >= 2048) {  // hand-written tcgen05 kernel, 3xTF32 split (tc_linear.cu)
+  // hand-written tcgen05 kernel, 3xTF32 split (tc_linear.cu): always (1) or where it measured
+  // faster than the CUTLASS collective (2: the GELU-fused FFN linear)
+  if ((g_tc_linear == 1 || (g_tc_linear == 2 && gelu)) && S >= 2048) {
     const int rc = tc3_linear(S, N, K, A, W, b, residual, gelu, out, st);
     if (rc != 0) return rc < 0 ? rc : TGM_OK;
   }

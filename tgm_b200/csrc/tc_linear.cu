@@ -4,29 +4,32 @@
 //  tgm/nn/encoder/dygformer.py:80-143 -- nn.MultiheadAttention in/out projections and the two
 //  FFN linears, 97 % of the model's flops -- evaluated there by torch's fp32 GEMMs.)
 //
-// The 1e-5 parity bar rules out plain TF32/BF16 inputs, so every fp32 operand is split in flight
-// into two TF32 terms, x = hi + lo with hi = x truncated to 10 mantissa bits (what the tensor core
-// reads of an fp32 word) and lo = x - hi (exact in fp32), and three tcgen05 products are
+// The 1e-5 parity bar rules out plain TF32/BF16 inputs, so every fp32 operand is used as two TF32
+// terms, x = hi + lo: hi = x truncated to 10 mantissa bits -- exactly what the tensor core reads of
+// an fp32 word (checked bit for bit on the B200: feeding raw words == feeding masked words), so the
+// RAW tile is the hi operand -- and lo = x - hi (exact in fp32).  Three tcgen05 products are
 // accumulated in fp32 in tensor memory:  A W^T ~= A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T
 // (the dropped lo x lo term is 2^-20 relative; measured max abs error vs float64 in
 // tests/test_gpu_tc_linear.py).
 //
-// Structure (no library code: plain PTX for tcgen05 / mbarrier / fences):
+// Structure (no library code: plain PTX for tcgen05 / mbarrier / cp.async / fences):
 //   * one CTA (512 threads, one per SM) = one 128 x BN output tile at a time, persistent over tiles
 //     (n fastest, so the CTAs of one wave share A rows in L2)
-//   * per K chunk of 40: every thread loads A and W rows from global with 128-bit loads, splits
-//     them and stores hi / lo into shared memory in the canonical no-swizzle K-major UMMA layout
-//     (8-row x 16-byte core matrices; LBO = 128 B between the core matrices of one k-step, SBO =
-//     1280 B between 8-row groups); two operand buffers, so chunk c + 1 is staged while the
-//     tensor core works on chunk c
+//   * K runs in chunks of 40.  The raw fp32 rows of A and W go global -> shared by 16-byte
+//     `cp.async`, each granule straight to its place in the canonical no-swizzle K-major UMMA
+//     layout (8-row x 16-byte core matrices; LBO = 128 B between the core matrices of one k-step,
+//     SBO = 1280 B between 8-row groups) -- no registers, two chunks ahead of the tensor core
+//   * a shared -> shared pass computes lo = x - trunc(x) for the NEXT chunk while the tensor core
+//     works on the current one (two raw + two lo stages, 210 KB)
 //   * ONE thread issues the chunk's 15 `tcgen05.mma.cta_group::1.kind::tf32` instructions
 //     (5 k-steps of 8 x 3 products) and commits them to an mbarrier.  The hi x hi products go to
-//     one TMEM accumulator, the two correction products to a second one, and BOTH are drained
+//     one TMEM accumulator, the two correction products to a second one; the first is drained
 //     into fp32 registers after every chunk (tcgen05.ld, then round-to-nearest adds): the tensor
 //     core's own accumulate step truncates, and a 75-step chain in a single TMEM accumulator
-//     drifts by ~1e-5 (measured); 5-step chains promoted in registers stay at fp32-GEMM accuracy
-//   * epilogue straight from the register accumulators: bias / residual / exact GELU, 208-byte
-//     row segments to global
+//     drifts by ~1e-5 (measured); 5-step chains promoted in registers stay at fp32-GEMM accuracy.
+//     The correction accumulator (2^-11 of the other) runs over the whole tile
+//   * epilogue: bias / residual / exact GELU on the register accumulators, transposed through
+//     shared memory so that every warp writes whole 800-byte output rows
 #include "common.cuh"
 
 using namespace tgm;
@@ -42,7 +45,9 @@ constexpr int kCorrCol = 256;
 constexpr int kColsPerThread = kMaxBN / 4;     // 4 warps share a TMEM lane quarter: 52 columns each
 constexpr uint32_t kLBO = 128;                 // bytes between the two core matrices of a k-step
 constexpr uint32_t kSBO = (KC / 4) * 128;      // bytes between 8-row groups
-constexpr size_t kBufBytes = size_t(2) * BM * KC * 4 + size_t(2) * kMaxBN * KC * 4;  // one stage
+constexpr uint32_t kABytes = BM * KC * 4, kWBytes = kMaxBN * KC * 4;
+constexpr uint32_t kStageBytes = kABytes + kWBytes;  // one stage: A rows | W rows
+constexpr int kEpiStride = kMaxBN + 1;         // odd row stride of the epilogue transpose: no conflicts
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) {
   return uint32_t(__cvta_generic_to_shared(p));
@@ -99,29 +104,28 @@ __device__ __forceinline__ uint32_t umma_off(int r, int c4) {
   return uint32_t(r >> 3) * kSBO + uint32_t(c4) * kLBO + uint32_t(r & 7) * 16u;
 }
 
-// Staging of one K chunk of both operands as hi / lo: BM rows of A and UN rows of W, KC floats
-// each (rows / columns outside the matrices read as zeros).  Item idx of a chunk = one 16-byte K
-// column group of one row; 8 consecutive items are 8 consecutive rows of one group (a
-// conflict-free 128-byte core matrix in shared memory), the next 8 the neighbouring group (so a
-// warp reads whole 32-byte sectors of 8 rows).  A thread owns the same (at most 7) items in every
-// chunk, so their global / shared offsets are computed ONCE per kernel (`StageMap`); per chunk
-// only the K offset moves.  All of a thread's loads are issued before the first split / store:
-// one L2 latency per chunk, not one per item.
+// Staging.  Item idx of a chunk = one 16-byte K column group of one row; 8 consecutive items are 8
+// consecutive rows of one group (a 128-byte core matrix in shared memory), the next 8 the
+// neighbouring group (so a warp reads whole 32-byte sectors of 8 rows).  A thread owns the same
+// (at most 7) items in every chunk, so their global / shared offsets are computed ONCE per kernel
+// (`StageMap`); per chunk only the K offset moves.  Rows / columns outside the matrices are
+// zero-filled by cp.async itself (src-size 0).
 constexpr int kC4 = KC / 4;
 constexpr int kAItems = BM * kC4;                                   // 1280
 constexpr int kMaxItems = (kAItems + kMaxBN * kC4 + kThreads - 1) / kThreads;  // 7
 
 struct StageMap {
   uint32_t g_off[kMaxItems];  // element offset from the tile's first row: r * K + 4 * c4
-  uint32_t s_off[kMaxItems];  // byte offset of the hi copy inside a stage (A_hi | A_lo | W_hi | W_lo)
+  uint32_t s_off[kMaxItems];  // byte offset inside a stage (A rows | W rows)
   uint32_t r_pack[2];         // row inside the tile, 8 bits per item (255 = no item)
   uint32_t c_pack[2];         // 4 * c4, 8 bits per item
   uint32_t w_mask;            // bit i: item i belongs to W
+  uint32_t have;              // bit i: item i exists
 };
 
 __device__ __forceinline__ void stage_map_init(StageMap &m, int UN, int K, int tid) {
   const int total = kAItems + UN * kC4;
-  m.r_pack[0] = m.r_pack[1] = m.c_pack[0] = m.c_pack[1] = m.w_mask = 0u;
+  m.r_pack[0] = m.r_pack[1] = m.c_pack[0] = m.c_pack[1] = m.w_mask = m.have = 0u;
 #pragma unroll
   for (int i = 0; i < kMaxItems; ++i) {
     const int idx = tid + i * kThreads;
@@ -130,39 +134,66 @@ __device__ __forceinline__ void stage_map_init(StageMap &m, int UN, int K, int t
     const int r = idx < total ? (it & 7) + 8 * (it / (8 * kC4)) : 255;
     const int c4 = (it >> 3) % kC4;
     m.g_off[i] = uint32_t(r) * uint32_t(K) + 4u * c4;
-    m.s_off[i] = (is_w ? 2u * BM * KC * 4u : 0u) + umma_off(r == 255 ? 0 : r, c4);
+    m.s_off[i] = (is_w ? kABytes : 0u) + umma_off(r == 255 ? 0 : r, c4);
     m.r_pack[i >> 2] |= uint32_t(r) << (8 * (i & 3));
     m.c_pack[i >> 2] |= uint32_t(4 * c4) << (8 * (i & 3));
     m.w_mask |= uint32_t(is_w) << i;
+    m.have |= uint32_t(idx < total) << i;
   }
 }
 
-__device__ __forceinline__ void stage_chunk(const StageMap &m, const float *__restrict__ At,
-                                            const float *__restrict__ Wt, int a_rows, int w_rows,
-                                            int K, int k0, unsigned char *base) {
-  float4 v[kMaxItems];
+// which of this thread's items lie inside the matrices for a tile with a_rows x w_rows valid rows
+__device__ __forceinline__ uint32_t stage_row_mask(const StageMap &m, int a_rows, int w_rows) {
+  uint32_t ok = 0u;
 #pragma unroll
   for (int i = 0; i < kMaxItems; ++i) {
     const int r = int((m.r_pack[i >> 2] >> (8 * (i & 3))) & 255u);
-    const int c = int((m.c_pack[i >> 2] >> (8 * (i & 3))) & 255u);
-    const bool is_w = (m.w_mask >> i) & 1u;
-    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < (is_w ? w_rows : a_rows) && k0 + c < K)
-      v[i] = __ldg(reinterpret_cast<const float4 *>((is_w ? Wt : At) + m.g_off[i] + k0));
+    ok |= uint32_t(r < (((m.w_mask >> i) & 1u) ? w_rows : a_rows)) << i;
   }
+  return ok & m.have;
+}
+
+// raw fp32 rows of one chunk -> shared memory, asynchronously (one commit group per chunk).
+// `rows_ok` = stage_row_mask of the tile; `full_k`: the chunk lies entirely inside K.
+__device__ __forceinline__ void stage_raw_async(const StageMap &m, const float *__restrict__ At,
+                                                const float *__restrict__ Wt, uint32_t rows_ok,
+                                                int K, int k0, uint32_t raw_s) {
+  const bool full_k = k0 + KC <= K;
 #pragma unroll
   for (int i = 0; i < kMaxItems; ++i) {
-    if (((m.r_pack[i >> 2] >> (8 * (i & 3))) & 255u) != 255u) {
-      const bool is_w = (m.w_mask >> i) & 1u;
-      float4 h, l;
-      h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u);
-      h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u);
-      h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u);
-      h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u);
-      l.x = v[i].x - h.x, l.y = v[i].y - h.y, l.z = v[i].z - h.z, l.w = v[i].w - h.w;
-      unsigned char *hi = base + m.s_off[i];
-      *reinterpret_cast<float4 *>(hi) = h;
-      *reinterpret_cast<float4 *>(hi + (is_w ? kMaxBN : BM) * KC * 4) = l;
+    if ((m.have >> i) & 1u) {
+      bool ok = (rows_ok >> i) & 1u;
+      if (!full_k) ok = ok && k0 + int((m.c_pack[i >> 2] >> (8 * (i & 3))) & 255u) < K;
+      const float *src = ok ? (((m.w_mask >> i) & 1u) ? Wt : At) + m.g_off[i] + k0 : At;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(raw_s + m.s_off[i]),
+                   "l"(src), "r"(ok ? 16u : 0u)
+                   : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// lo = x - trunc_tf32(x) of this thread's own granules (it copied them itself: its own
+// cp.async.wait_group makes them visible to it, no barrier needed in between)
+__device__ __forceinline__ void stage_lo(const StageMap &m, const unsigned char *raw,
+                                         unsigned char *lo) {
+#pragma unroll
+  for (int i0 = 0; i0 < kMaxItems; i0 += 2) {  // two granules in flight: short dependent chains
+    float4 v[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (i0 + u < kMaxItems && ((m.have >> (i0 + u)) & 1u))
+        v[u] = *reinterpret_cast<const float4 *>(raw + m.s_off[i0 + u]);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (i0 + u < kMaxItems && ((m.have >> (i0 + u)) & 1u)) {
+        float4 l;
+        l.x = v[u].x - __uint_as_float(__float_as_uint(v[u].x) & 0xffffe000u);
+        l.y = v[u].y - __uint_as_float(__float_as_uint(v[u].y) & 0xffffe000u);
+        l.z = v[u].z - __uint_as_float(__float_as_uint(v[u].z) & 0xffffe000u);
+        l.w = v[u].w - __uint_as_float(__float_as_uint(v[u].w) & 0xffffe000u);
+        *reinterpret_cast<float4 *>(lo + m.s_off[i0 + u]) = l;
+      }
     }
   }
 }
@@ -181,12 +212,13 @@ __global__ void __launch_bounds__(kThreads, 1)
 tc3_linear_kernel(const float *__restrict__ A, const float *__restrict__ W,
                   const float *__restrict__ bias, const float *residual, float *out, int64_t S,
                   int N, int K, int BN, int gelu) {
-  extern __shared__ __align__(1024) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem[];  // raw0 | raw1 | lo0 | lo1
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int UN = (BN + 15) & ~15;  // UMMA N
   const uint32_t bar = smem_addr(&s_bar);
+  unsigned char *lo_base = smem + 2 * kStageBytes;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -207,54 +239,63 @@ tc3_linear_kernel(const float *__restrict__ A, const float *__restrict__ W,
 
   StageMap map;
   stage_map_init(map, UN, K, tid);
-  auto stage = [&](int64_t m0, int n0, int kc) {
-    const int a_rows = int(S - m0 < BM ? S - m0 : BM);
-    const int w_rows = (n0 + BN < N ? n0 + BN : N) - n0;
-    stage_chunk(map, A + m0 * K, W + int64_t(n0) * K, a_rows, w_rows, K, kc * KC,
-                smem + size_t(kc & 1) * kBufBytes);
-  };
-
   const int64_t m_tiles = (S + BM - 1) / BM;
   const int n_tiles = (N + BN - 1) / BN;
+  const int64_t tiles = m_tiles * n_tiles;
   const int k_chunks = (K + KC - 1) / KC;
+  // raw chunk kc of tile `t` -> raw stage (kc & 1), asynchronously
+  auto prefetch = [&](int64_t t, int kc) {
+    const int64_t m0 = (t / n_tiles) * BM;
+    const int n0 = int(t % n_tiles) * BN;
+    const int a_rows = int(S - m0 < BM ? S - m0 : BM);
+    const int w_rows = (n0 + BN < N ? n0 + BN : N) - n0;
+    stage_raw_async(map, A + m0 * K, W + int64_t(n0) * K, stage_row_mask(map, a_rows, w_rows), K,
+                    kc * KC, smem_addr(smem) + uint32_t(kc & 1) * kStageBytes);
+  };
   // this thread's share of the accumulator: TMEM lane (= tile row) 32 * (warp & 3) + lane,
   // columns [cbase, cbase + UN / 4)
   const int q = warp & 3, cols = UN >> 2, cbase = (warp >> 2) * cols;
   const uint32_t lane_addr = tmem + (uint32_t(32 * q) << 16);
   uint32_t phase = 0;  // parity of the next completion of the MMA barrier
-  for (int64_t tile = blockIdx.x; tile < m_tiles * n_tiles; tile += gridDim.x) {
+
+  int64_t tile = blockIdx.x;
+  if (tile < tiles) {  // the first tile's first two chunks
+    prefetch(tile, 0);
+    if (k_chunks > 1) prefetch(tile, 1);
+  }
+  for (; tile < tiles; tile += gridDim.x) {
     const int64_t m0 = (tile / n_tiles) * BM;
     const int n0 = int(tile % n_tiles) * BN;
     float acc[kColsPerThread];
 #pragma unroll
     for (int j = 0; j < kColsPerThread; ++j) acc[j] = 0.f;
-    // acc += this thread's columns of the accumulator at TMEM column `col0`: 16-column loads, one
-    // wait per 32 columns
-    // (columns past this thread's share may be read -- they stay inside the 256-column region of
-    // the accumulator -- but are never used)
+    // acc += this thread's columns of the accumulator at TMEM column `col0`, 16 columns per load
+    // (columns past this thread's share may be read -- they stay inside the
+    // 256-column region of the accumulator -- but are never used)
     auto drain = [&](uint32_t col0) {
-      uint32_t t[32];
 #pragma unroll
-      for (int j = 0; j < kColsPerThread; j += 32) {
+      for (int j = 0; j < kColsPerThread; j += 16) {
         if (j < cols) {
-          const uint32_t ta = lane_addr + col0 + uint32_t(cbase + j);
-          tmem_ld16(ta, t);
-          if (j + 16 < cols) tmem_ld16(ta + 16, t + 16);
+          uint32_t t[16];
+          tmem_ld16(lane_addr + col0 + uint32_t(cbase + j), t);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int u = 0; u < 32; ++u)
+          for (int u = 0; u < 16; ++u)
             if (j + u < kColsPerThread && j + u < cols) acc[j + u] += __uint_as_float(t[u]);
         }
       }
     };
-    stage(m0, n0, 0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy
-    __syncthreads();
+    // chunk 0: its raw tile has landed (requested during the previous tile) -> its lo terms
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    stage_lo(map, smem, lo_base);
     for (int kc = 0; kc < k_chunks; ++kc) {
+      // raw(kc) and lo(kc) written by all threads -> visible to the tensor core
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t ah = smem_addr(smem + size_t(kc & 1) * kBufBytes);
-        const uint32_t al = ah + BM * KC * 4, wh = al + BM * KC * 4, wl = wh + kMaxBN * KC * 4;
+        const uint32_t ah = smem_addr(smem) + uint32_t(kc & 1) * kStageBytes, wh = ah + kABytes;
+        const uint32_t al = smem_addr(lo_base) + uint32_t(kc & 1) * kStageBytes, wl = al + kABytes;
 #pragma unroll
         for (int ks = 0; ks < KC / 8; ++ks) {
           const uint32_t o = uint32_t(ks) * 2u * kLBO;  // two core matrices per k-step
@@ -268,9 +309,13 @@ tc3_linear_kernel(const float *__restrict__ A, const float *__restrict__ W,
             "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
             : "memory");
       }
-      // the other buffer was last read by the MMAs of chunk kc - 1, which completed before the
-      // drain of the previous iteration: stage the next chunk while the tensor core runs
-      if (kc + 1 < k_chunks) stage(m0, n0, kc + 1);
+      // while the tensor core runs: the lo terms of the next chunk (its raw tile was requested
+      // two iterations ago; lo stage (kc+1)&1 was last read by the MMAs of chunk kc-1, complete)
+      if (kc + 1 < k_chunks) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        stage_lo(map, smem + size_t((kc + 1) & 1) * kStageBytes,
+                 lo_base + size_t((kc + 1) & 1) * kStageBytes);
+      }
       mbar_wait(bar, phase);
       phase ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -278,37 +323,70 @@ tc3_linear_kernel(const float *__restrict__ A, const float *__restrict__ W,
       // correction accumulator is 2^-11 of it: its own truncation is far below fp32 resolution, so
       // it runs over the whole tile and is added once, below)
       drain(0u);
-      // TMEM drained and the next chunk's operands written: both visible before the next MMAs
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
+      // raw stage kc&1 is free again (its MMAs completed): request chunk kc+2 of this tile, or
+      // the first chunks of the next tile
+      if (kc + 2 < k_chunks) {
+        prefetch(tile, kc + 2);
+      } else if (tile + gridDim.x < tiles && (kc & 1) < k_chunks) {
+        // tail of the tile: the released stage takes the next tile's chunk of the same parity
+        // (chunk 0 lives in stage 0, chunk 1 in stage 1)
+        prefetch(tile + gridDim.x, kc & 1);
+      }
     }
     drain(uint32_t(kCorrCol));
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // next tile's MMAs overwrite it
-    // ---- epilogue: bias / residual / GELU on the register accumulators -> global ---------------
-    const int64_t row = m0 + 32 * q + lane;
-    if (row < S) {
+    // ---- epilogue: bias / residual / GELU in registers, transposed through the lo stages (free:
+    // every MMA of the tile is complete) so that warps write whole output rows --------------------
+    float *ep = reinterpret_cast<float *>(lo_base);
+    {
+      const int row = 32 * q + lane;
 #pragma unroll
-      for (int j = 0; j < kColsPerThread; j += 4) {
-        const int c = cbase + j, n = n0 + c;
-        if (j < cols && c < BN && n < N) {  // N and BN are multiples of 4
-          const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + n));
-          float4 y = make_float4(acc[j] + b.x, acc[j + 1] + b.y, acc[j + 2] + b.z, acc[j + 3] + b.w);
-          if (residual) {
-            const float4 r = *reinterpret_cast<const float4 *>(residual + row * N + n);
-            y.x += r.x, y.y += r.y, y.z += r.z, y.w += r.w;
+      for (int j = 0; j < kColsPerThread; ++j)
+        if (j < cols) ep[row * kEpiStride + cbase + j] = acc[j];
+    }
+    __syncthreads();
+    {
+      // lane owns columns lane, lane + 32, ... of every row its warp writes: their bias values
+      // stay in registers, and the loads of a row are all issued before its first store
+      const int n_valid = (n0 + BN < N ? n0 + BN : N) - n0;
+      constexpr int kCols = (kMaxBN + 31) / 32;  // 7
+      float bv[kCols];
+#pragma unroll
+      for (int i = 0; i < kCols; ++i) {
+        const int c = lane + 32 * i;
+        bv[i] = c < n_valid ? __ldg(bias + n0 + c) : 0.f;
+      }
+      const int r_end = int(S - m0 < BM ? S - m0 : BM);
+      for (int r = warp; r < r_end; r += kThreads / 32) {
+        const int64_t o = (m0 + r) * N + n0;
+        float y[kCols];
+#pragma unroll
+        for (int i = 0; i < kCols; ++i) {
+          const int c = lane + 32 * i;
+          y[i] = c < n_valid ? ep[r * kEpiStride + c] + bv[i] : 0.f;
+        }
+        if (residual) {
+#pragma unroll
+          for (int i = 0; i < kCols; ++i) {
+            const int c = lane + 32 * i;
+            if (c < n_valid) y[i] += residual[o + c];
           }
-          if (gelu) {  // exact GELU (F.gelu)
-            y.x = 0.5f * y.x * (1.f + erff(y.x * 0.70710678118654752440f));
-            y.y = 0.5f * y.y * (1.f + erff(y.y * 0.70710678118654752440f));
-            y.z = 0.5f * y.z * (1.f + erff(y.z * 0.70710678118654752440f));
-            y.w = 0.5f * y.w * (1.f + erff(y.w * 0.70710678118654752440f));
+        }
+#pragma unroll
+        for (int i = 0; i < kCols; ++i) {
+          const int c = lane + 32 * i;
+          if (c < n_valid) {
+            float v = y[i];
+            if (gelu) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));  // exact GELU
+            out[o + c] = v;
           }
-          *reinterpret_cast<float4 *>(out + row * N + n) = y;
         }
       }
     }
+    __syncthreads();  // the lo stages are reused by the next tile
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0)
@@ -317,16 +395,17 @@ tc3_linear_kernel(const float *__restrict__ A, const float *__restrict__ W,
                  : "memory");
 }
 
-constexpr size_t kSmemBytes = 2 * kBufBytes;
+constexpr size_t kSmemBytes = 4 * size_t(kStageBytes);
 
 }  // namespace
 
 namespace tgm {
 
-// tgm_set_option("tc_linear", 0|1).  Default 0: measured on the B200 (profiles/README.md) this
-// kernel reaches 45 TFLOP/s fp32-equivalent on the DyGFormer shapes (1.5x cuBLAS fp32) against 64
-// for the CUTLASS FastF32 collective, which therefore stays the default for the token linears.
-int g_tc_linear = 0;
+// tgm_set_option("tc_linear", 0|1|2): 0 = never, 1 = every token linear, 2 (default) = where it
+// measured faster than the CUTLASS FastF32 collective on the B200 (profiles/r2_tc_linear_timings.txt):
+// the GELU-fused FFN linear (158 vs 177 us on 25600x800x200); the other three DyGFormer shapes
+// stay on the collective (113 / 54 / 167 us here vs 86 / 42 / 115).
+int g_tc_linear = 2;
 
 // 1 = computed, 0 = shape / alignment not supported (caller falls back), < 0 = error
 int tc3_linear(int64_t S, int N, int K, const float *A, const float *W, const float *bias,
@@ -363,5 +442,18 @@ extern "C" int tgm_tc_linear(int64_t S, int32_t N, int32_t K, const float *A, co
   if (rc == 0)
     return fail(TGM_ERR_INVALID, "tgm_tc_linear: needs S >= 1, N % 4 == 0, K % 4 == 0, 16-byte "
                                  "aligned arrays and not both gelu and residual");
+  return rc < 0 ? rc : TGM_OK;
+}
+
+// The CUTLASS FastF32 (9xBF16) instantiation behind DyGFormer's token linears, same contract
+// (gemm_fastf32.cu).
+extern "C" int tgm_fastf32_linear(int64_t S, int32_t N, int32_t K, const float *A, const float *W,
+                                  const float *bias, const float *residual, int gelu, float *out,
+                                  tgm_stream stream) {
+  TGM_REQUIRE(A && W && bias && out, "tgm_fastf32_linear: NULL array argument");
+  const int rc = tgm::fastf32_linear(S, N, K, A, W, bias, residual, gelu, out, as_stream(stream));
+  if (rc == 0)
+    return fail(TGM_ERR_INVALID, "tgm_fastf32_linear: shape / alignment not supported, or the "
+                                 "library was built without the CUTLASS headers");
   return rc < 0 ? rc : TGM_OK;
 }
