@@ -55,7 +55,11 @@ int tgm_device_count(void);
  * the transformer layers run on the tensor cores (tcgen05, fp32-accurate 9xBF16 emulation), 0 = on
  * cuBLAS's SIMT SGEMM; both hold the 1e-5 parity bar.  "tc_linear": which of those GEMMs run on the
  * hand-written tcgen05 kernel of tgm_tc_linear instead: 0 = none, 1 = all, 2 (default) = the ones
- * where it measured faster than the template instantiation (the GELU-fused FFN linear).  "dyg_fused_attn": 1 (default) = DyGFormer's
+ * where it measured faster than the template instantiation (the GELU-fused FFN linear); a non-zero
+ * value also puts TGAT's merge-layer and folded output products on it.  "attn_folded": 1
+ * (default) = tgm_attn_forward* without caller time features run the folded inference chain
+ * (projection weights pre-multiplied, one warp per seed), 0 = the unfolded chain the backward
+ * pass uses.  "dyg_fused_attn": 1 (default) = DyGFormer's
  * per-head QK^T / softmax / PV is one kernel with the scores in shared memory, 0 = batched cuBLAS
  * products with the scores in HBM.  "csr_tma_ctas_per_sm": cap on resident CTAs of the TMA sampler
  * (0 = automatic).  "trace": 1 = tgm_csr_build prints its phase timings on stderr. */
@@ -354,6 +358,19 @@ int tgm_attn_forward_rows(tgm_attn *, const float *node_x, const float *nbr_node
                           const float *edge_table, const int32_t *edge_rows, const int64_t *seed_t,
                           const int64_t *nbr_t, const int32_t *nbr_id, int64_t S, int32_t k,
                           float *out, tgm_stream stream);
+/* One call for several hops of a TGAT layer (tgat.py:136-147 runs the same attention module once
+ * per hop): the seeds of all hops are one row range [0, S); node_x, nbr_node_feat, seed_t, nbr_t,
+ * nbr_id cover it contiguously (hop i+1's rows ARE hop i's neighbour slots, so the hop recursion
+ * already stores them back to back), and the dense edge-feature blocks stay where the sampler
+ * wrote them: segment i is float32[seg_rows[i], k, edge_dim], sum(seg_rows) == S, n_segs <= 4.
+ * Needs tgm_attn_folded_covers(handle, k) == 1 (k <= 32, heads <= 2, node/edge_dim <= 192,
+ * time_dim <= 128, out_dim <= 384, option "attn_folded" on).  Same result as the per-hop calls. */
+int tgm_attn_folded_covers(const tgm_attn *, int32_t k);
+int tgm_attn_forward_segments(tgm_attn *, const float *node_x, const float *nbr_node_feat,
+                              const float *const *edge_feat_segs, const int64_t *seg_rows,
+                              int32_t n_segs, const int64_t *seed_t, const int64_t *nbr_t,
+                              const int32_t *nbr_id, int64_t S, int32_t k, float *out,
+                              tgm_stream stream);
 int tgm_attn_forward_feats(tgm_attn *, const float *node_x, const float *time_feat,
                            const float *edge_feat, const float *nbr_node_feat,
                            const float *nbr_time_feat, const int32_t *nbr_id, int64_t S, int32_t k,

@@ -27,12 +27,16 @@ def _run(S, N, K, residual, gelu, seed=0, scale=1.0):
     want = A.double() @ W.double().T + b.double()
     if residual:
         want = want + R.double()
-    if gelu:
+    if gelu == 2:
+        want = want.relu()
+    elif gelu:
         want = 0.5 * want * (1 + torch.erf(want / 2 ** 0.5))
     fp32 = torch.nn.functional.linear(A, W, b)  # cuBLAS fp32 for scale
     if residual:
         fp32 = fp32 + R
-    if gelu:
+    if gelu == 2:
+        fp32 = fp32.relu()
+    elif gelu:
         fp32 = torch.nn.functional.gelu(fp32)
     return out, want, fp32
 
@@ -46,7 +50,13 @@ def _run(S, N, K, residual, gelu, seed=0, scale=1.0):
     (257, 404, 44, True, False),       # three column tiles of 136, K tail in a second chunk
     (4096, 172, 400, False, True),
     (1, 4, 4, False, False),
-], ids=['in_proj', 'out_proj', 'ffn1_gelu', 'ffn2', 'tails_a', 'tails_b', 'wiki_out', 'tiny'])
+    (12600, 104, 548, False, False),   # TGAT layer 1: folded output product (attn_fold.cu)
+    (12600, 172, 104, False, 2),       # merge layer fc1 + ReLU
+    (600, 172, 172, False, False),     # short matrix: narrow column tiles over more SMs
+    (600, 272, 888, False, False),     # two-wide, many chunks
+    (3000, 64, 33 * 4, False, 2),      # chunk count not a multiple of the stage counts
+], ids=['in_proj', 'out_proj', 'ffn1_gelu', 'ffn2', 'tails_a', 'tails_b', 'wiki_out', 'tiny',
+        'tgat_out', 'merge_relu', 'short', 'short_wide', 'chunks_5'])
 def test_tc_linear_matches_float64(S, N, K, residual, gelu):
     out, want, fp32 = _run(S, N, K, residual, gelu)
     assert bool(torch.isfinite(out).all()), 'unwritten or non-finite outputs'

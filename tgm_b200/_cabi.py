@@ -119,6 +119,10 @@ SIGNATURES = {
                                  c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     'tgm_attn_forward_rows': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    'tgm_attn_folded_covers': (c_int, [c_void_p, c_int32]),
+    'tgm_attn_forward_segments': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                          c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
+                                          c_void_p]),
     'tgm_attn_forward_feats': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     'tgm_attn_backward': (c_int, [c_void_p] + [c_void_p] * 6 + [c_int64, c_int32] + [c_void_p] * 12 +

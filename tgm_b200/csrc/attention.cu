@@ -30,6 +30,7 @@ using namespace tgm;
 struct tgm_mlp2 {
   int device = -1;
   int in1 = 0, in2 = 0, hidden = 0, out = 0;
+  int inp = 0;  // in1 + in2 rounded up to a multiple of 4: row pitch of `cat` and of W1 (zero padded)
   float *W1 = nullptr, *b1 = nullptr, *W2 = nullptr, *b2 = nullptr;
   cublasHandle_t blas = nullptr;
   int64_t cap = 0;
@@ -382,15 +383,15 @@ attn_epilogue_kernel(const float *__restrict__ Y, const float *__restrict__ bo,
 }
 
 // ---- MergeLayer pieces (tgat.py:34-38) ----------------------------------------------------------
+// out[s] = [a[s] | b[s] | 0 ...] with row pitch d >= da + db
 __global__ void concat2_kernel(const float *__restrict__ a, const float *__restrict__ b, int64_t S,
-                               int da, int db, float *__restrict__ out) {
-  const int d = da + db;
+                               int da, int db, int d, float *__restrict__ out) {
   const int64_t total = S * d;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += int64_t(gridDim.x) * blockDim.x) {
     const int64_t s = i / d;
     const int c = int(i - s * d);
-    out[i] = c < da ? a[s * da + c] : b[s * db + (c - da)];
+    out[i] = c < da ? a[s * da + c] : c < da + db ? b[s * db + (c - da)] : 0.f;
   }
 }
 __global__ void bias_act_kernel(float *__restrict__ x, const float *__restrict__ b, int64_t S,
@@ -469,6 +470,12 @@ extern "C" int tgm_attn_create(tgm_attn **out, int32_t n_heads, int32_t node_dim
     if (s != CUBLAS_STATUS_SUCCESS) rc = blas_fail(s, "cublasCreate");
     else cublasSetMathMode(a->blas, CUBLAS_PEDANTIC_MATH);  // true fp32, no TF32 down-conversion
   }
+  if (!rc) rc = attn_fold_alloc(a);
+  if (!rc) rc = attn_fold_refresh(a, nullptr);
+  if (!rc) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = cuda_fail(e, "weight folding", __FILE__, __LINE__);
+  }
   if (rc) {
     delete a;
     return rc;
@@ -497,18 +504,38 @@ extern "C" int tgm_attn_set_params(tgm_attn *a, const float *W_Q, const float *W
   TGM_CUDA(cudaMemcpyAsync(a->tb, t2v_b, td * 4, cudaMemcpyDefault, st));
   cos_kernel<<<(a->time_dim + 127) / 128, 128, 0, st>>>(a->tb, a->time_dim, a->t0);
   TGM_LAUNCH_CHECK();
-  return TGM_OK;
+  return attn_fold_refresh(a, st);
 }
 
 extern "C" void tgm_attn_destroy(tgm_attn *a) { delete a; }
 
 extern "C" int tgm_attn_out_dim(const tgm_attn *a) { return a ? a->out_dim : TGM_ERR_INVALID; }
 
+int attn_workspace(tgm_attn *a, int64_t S, cudaStream_t st) {
+  if (S <= a->cap) return TGM_OK;
+  const int od = a->out_dim, key = a->key, H = a->H;
+  TGM_CUDA(cudaStreamSynchronize(st));
+  for (float **p : {&a->R, &a->Q, &a->QK, &a->U, &a->O, &a->Y}) {
+    cudaFree(*p);
+    *p = nullptr;
+  }
+  a->cap = 0;
+  const size_t rows = size_t(S + S / 4);
+  TGM_CUDA(cudaMalloc(&a->R, rows * od * 4));
+  TGM_CUDA(cudaMalloc(&a->Q, rows * od * 4));
+  TGM_CUDA(cudaMalloc(&a->QK, rows * H * key * 4));
+  TGM_CUDA(cudaMalloc(&a->U, rows * a->Kp * 4));  // Kp >= H key, Np >= od: both chains fit
+  TGM_CUDA(cudaMalloc(&a->O, rows * od * 4));
+  TGM_CUDA(cudaMalloc(&a->Y, rows * a->Np * 4));
+  a->cap = int64_t(rows);
+  return TGM_OK;
+}
+
 int attn_forward_impl(tgm_attn *a, const float *node_x, const float *nbr_node_feat,
                              const float *edge_feat, const int64_t *seed_t, const int64_t *nbr_t,
                              const float *seed_tf, const float *nbr_tf, const int32_t *nbr_id,
                              int64_t S, int32_t k, float *out, tgm_stream stream,
-                             const int32_t *edge_rows) {
+                             const int32_t *edge_rows, bool keep_intermediates) {
   TGM_REQUIRE(a != nullptr, "tgm_attn_forward: handle is NULL");
   TGM_REQUIRE(S >= 0 && k >= 1, "tgm_attn_forward: bad sizes");
   if (S == 0) return TGM_OK;
@@ -520,22 +547,10 @@ int attn_forward_impl(tgm_attn *a, const float *node_x, const float *nbr_node_fe
   DeviceGuard g(a->device);
   cudaStream_t st = as_stream(stream);
   const int od = a->out_dim, key = a->key, H = a->H, hd = a->hd;
-  if (S > a->cap) {
-    TGM_CUDA(cudaStreamSynchronize(st));
-    for (float **p : {&a->R, &a->Q, &a->QK, &a->U, &a->O, &a->Y}) {
-      cudaFree(*p);
-      *p = nullptr;
-    }
-    a->cap = 0;
-    const size_t rows = size_t(S + S / 4);
-    TGM_CUDA(cudaMalloc(&a->R, rows * od * 4));
-    TGM_CUDA(cudaMalloc(&a->Q, rows * od * 4));
-    TGM_CUDA(cudaMalloc(&a->QK, rows * H * key * 4));
-    TGM_CUDA(cudaMalloc(&a->U, rows * H * key * 4));
-    TGM_CUDA(cudaMalloc(&a->O, rows * od * 4));
-    TGM_CUDA(cudaMalloc(&a->Y, rows * od * 4));
-    a->cap = int64_t(rows);
-  }
+  if (int rc = attn_workspace(a, S, st)) return rc;
+  if (!keep_intermediates && !seed_tf && attn_folded_covers(a, k))
+    return attn_forward_folded(a, node_x, nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, S, k,
+                               out, st, edge_rows);
   TGM_BLAS(cublasSetStream(a->blas, st));
   const float one = 1.f, zero = 0.f;
   // R = [X | pad | Time2Vec(0)],  Q = R W_Q^T
@@ -588,6 +603,39 @@ extern "C" int tgm_attn_forward_rows(tgm_attn *a, const float *node_x, const flo
                            nbr_id, S, k, out, stream, edge_rows);
 }
 
+extern "C" int tgm_attn_folded_covers(const tgm_attn *a, int32_t k) {
+  return a ? int(attn_folded_covers(a, k)) : TGM_ERR_INVALID;
+}
+
+extern "C" int tgm_attn_forward_segments(tgm_attn *a, const float *node_x, const float *nbr_node_feat,
+                                         const float *const *edge_feat_segs, const int64_t *seg_rows,
+                                         int32_t n_segs, const int64_t *seed_t, const int64_t *nbr_t,
+                                         const int32_t *nbr_id, int64_t S, int32_t k, float *out,
+                                         tgm_stream stream) {
+  TGM_REQUIRE(a != nullptr, "tgm_attn_forward_segments: handle is NULL");
+  TGM_REQUIRE(S >= 0 && k >= 1, "tgm_attn_forward_segments: bad sizes");
+  TGM_REQUIRE(n_segs >= 1 && n_segs <= 4 && edge_feat_segs && seg_rows,
+              "tgm_attn_forward_segments: 1..4 edge-feature segments");
+  int64_t total = 0;
+  for (int i = 0; i < n_segs; ++i) {
+    TGM_REQUIRE(seg_rows[i] >= 0 && (edge_feat_segs[i] || seg_rows[i] == 0),
+                "tgm_attn_forward_segments: bad segment");
+    total += seg_rows[i];
+  }
+  TGM_REQUIRE(total == S, "tgm_attn_forward_segments: segment rows must add up to S");
+  if (S == 0) return TGM_OK;
+  TGM_REQUIRE(node_x && nbr_node_feat && seed_t && nbr_t && nbr_id && out,
+              "tgm_attn_forward_segments: NULL array argument");
+  TGM_REQUIRE(S < (int64_t(1) << 31), "tgm_attn_forward_segments: S must be < 2^31");
+  TGM_REQUIRE(attn_folded_covers(a, k),
+              "tgm_attn_forward_segments: shape outside the folded chain (see tgm_attn_folded_covers)");
+  DeviceGuard g(a->device);
+  cudaStream_t st = as_stream(stream);
+  if (int rc = attn_workspace(a, S, st)) return rc;
+  return attn_forward_folded(a, node_x, nbr_node_feat, edge_feat_segs[0], seed_t, nbr_t, nbr_id, S, k,
+                             out, st, nullptr, edge_feat_segs, seg_rows, n_segs);
+}
+
 extern "C" int tgm_attn_forward_feats(tgm_attn *a, const float *node_x, const float *time_feat,
                                       const float *edge_feat, const float *nbr_node_feat,
                                       const float *nbr_time_feat, const int32_t *nbr_id, int64_t S,
@@ -610,7 +658,16 @@ extern "C" int tgm_mlp2_create(tgm_mlp2 **out, int32_t in1, int32_t in2, int32_t
   tgm_mlp2 *m = new (std::nothrow) tgm_mlp2();
   if (!m) return fail(TGM_ERR_OOM, "tgm_mlp2_create: host allocation failed");
   m->device = device, m->in1 = in1, m->in2 = in2, m->hidden = hidden, m->out = out_dim;
-  int rc = dev_copy(&m->W1, W1, size_t(hidden) * (in1 + in2));
+  m->inp = (in1 + in2 + 3) & ~3;
+  int rc = TGM_OK;
+  {
+    cudaError_t e = cudaMalloc(&m->W1, size_t(hidden) * m->inp * 4);
+    if (e == cudaSuccess) e = cudaMemset(m->W1, 0, size_t(hidden) * m->inp * 4);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2D(m->W1, size_t(m->inp) * 4, W1, size_t(in1 + in2) * 4, size_t(in1 + in2) * 4,
+                       hidden, cudaMemcpyDefault);
+    if (e != cudaSuccess) rc = cuda_fail(e, "tgm_mlp2_create: W1", __FILE__, __LINE__);
+  }
   if (!rc) rc = dev_copy(&m->b1, b1, hidden);
   if (!rc) rc = dev_copy(&m->W2, W2, size_t(out_dim) * hidden);
   if (!rc) rc = dev_copy(&m->b2, b2, out_dim);
@@ -637,7 +694,7 @@ extern "C" int tgm_mlp2_forward(tgm_mlp2 *m, const float *x1, const float *x2, i
   TGM_REQUIRE(x1 && (x2 || m->in2 == 0) && out, "tgm_mlp2_forward: NULL array argument");
   DeviceGuard g(m->device);
   cudaStream_t st = as_stream(stream);
-  const int in = m->in1 + m->in2;
+  const int in = m->inp;
   if (S > m->cap) {
     TGM_CUDA(cudaStreamSynchronize(st));
     cudaFree(m->cat), cudaFree(m->h);
@@ -648,16 +705,11 @@ extern "C" int tgm_mlp2_forward(tgm_mlp2 *m, const float *x1, const float *x2, i
     TGM_CUDA(cudaMalloc(&m->h, rows * m->hidden * 4));
     m->cap = int64_t(rows);
   }
-  TGM_BLAS(cublasSetStream(m->blas, st));
-  concat2_kernel<<<grid_for(S * in, 256, 8), 256, 0, st>>>(x1, x2, S, m->in1, m->in2, m->cat);
+  concat2_kernel<<<grid_for(S * in, 256, 8), 256, 0, st>>>(x1, x2, S, m->in1, m->in2, in, m->cat);
   TGM_LAUNCH_CHECK();
-  TGM_BLAS(gemm_nt(m->blas, S, m->hidden, in, m->cat, in, m->W1, m->h, m->hidden));
-  bias_act_kernel<<<grid_for(S * m->hidden, 256, 8), 256, 0, st>>>(m->h, m->b1, S, m->hidden, 1);
-  TGM_LAUNCH_CHECK();
-  TGM_BLAS(gemm_nt(m->blas, S, m->out, m->hidden, m->h, m->hidden, m->W2, out, m->out));
-  bias_act_kernel<<<grid_for(S * m->out, 256, 8), 256, 0, st>>>(out, m->b2, S, m->out, 0);
-  TGM_LAUNCH_CHECK();
-  return TGM_OK;
+  // bias and ReLU ride in the product's epilogue (tensor-core kernel) or one pass after it (cuBLAS)
+  if (int rc = dense_linear(m->blas, S, m->hidden, in, m->cat, m->W1, m->b1, 2, m->h, st)) return rc;
+  return dense_linear(m->blas, S, m->out, m->hidden, m->h, m->W2, m->b2, 0, out, st);
 }
 
 extern "C" int tgm_gather_rows(const float *table, int64_t num_rows, int32_t dim,

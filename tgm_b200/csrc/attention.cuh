@@ -13,8 +13,14 @@ struct tgm_attn {
   float *Wq = nullptr, *Wkv = nullptr, *Wo = nullptr, *bo = nullptr, *lnw = nullptr, *lnb = nullptr;
   float *tw = nullptr, *tb = nullptr;  // Time2Vec weight [time_dim], bias [time_dim]
   float *t0 = nullptr;                 // Time2Vec(0) = cos(b)   [time_dim]
+  // folded weights of the inference path (attn_fold.cu), rebuilt whenever the parameters change:
+  //   Wqx [H*key, node_dim]  = (W_K,h^T W_Q,h)[:, :node_dim]      qk = Wqx x + cqk
+  //   cqk [H*key]            = (W_K,h^T W_Q,h)[:, time part] Time2Vec(0)
+  //   Wov [Np, Kp]           = W_O[:, h] W_V,h   (zero padded to multiples of 4)
+  float *Wqx = nullptr, *cqk = nullptr, *Wov = nullptr, *zeros = nullptr, *qt0 = nullptr;
+  int Np = 0, Kp = 0;
   cublasHandle_t blas = nullptr;
-  // workspace, grown on demand (rows = seeds)
+  // workspace, grown on demand (rows = seeds); U rows hold Kp floats, Y rows Np
   int64_t cap = 0;
   float *R = nullptr, *Q = nullptr, *QK = nullptr, *U = nullptr, *O = nullptr, *Y = nullptr;
   // backward workspace (rows = seeds)
@@ -24,8 +30,8 @@ struct tgm_attn {
   ~tgm_attn() {
     if (device >= 0) {
       tgm::DeviceGuard g(device);
-      for (float *p : {Wq, Wkv, Wo, bo, lnw, lnb, tw, tb, t0, R, Q, QK, U, O, Y, dV, dO, dU, dQK, dQ,
-                       dR, fwd_out})
+      for (float *p : {Wq, Wkv, Wo, bo, lnw, lnb, tw, tb, t0, Wqx, cqk, Wov, zeros, qt0, R, Q, QK, U,
+                       O, Y, dV, dO, dU, dQK, dQ, dR, fwd_out})
         cudaFree(p);
       if (blas) cublasDestroy(blas);
     }
@@ -33,8 +39,26 @@ struct tgm_attn {
 };
 
 
-// forward pass into the handle's workspace (attention.cu); leaves R, Q, QK, U, O, Y valid
+// forward pass into the handle's workspace (attention.cu).  keep_intermediates: run the unfolded
+// chain and leave R, Q, QK, U, O, Y valid (what the backward pass reads); otherwise the folded
+// inference chain (attn_fold.cu) serves the call whenever its kernel covers the shape.
 int attn_forward_impl(tgm_attn *a, const float *node_x, const float *nbr_node_feat,
                       const float *edge_feat, const int64_t *seed_t, const int64_t *nbr_t,
                       const float *seed_tf, const float *nbr_tf, const int32_t *nbr_id, int64_t S,
-                      int32_t k, float *out, tgm_stream stream, const int32_t *edge_rows = nullptr);
+                      int32_t k, float *out, tgm_stream stream, const int32_t *edge_rows = nullptr,
+                      bool keep_intermediates = false);
+
+// attn_fold.cu
+int attn_fold_alloc(tgm_attn *a);                       // once, at create
+int attn_fold_refresh(tgm_attn *a, cudaStream_t st);    // after every parameter change
+bool attn_folded_covers(const tgm_attn *a, int k);
+int attn_workspace(tgm_attn *a, int64_t S, cudaStream_t st);
+int attn_forward_folded(tgm_attn *a, const float *node_x, const float *nbr_node_feat,
+                        const float *edge_feat, const int64_t *seed_t, const int64_t *nbr_t,
+                        const int32_t *nbr_id, int64_t S, int32_t k, float *out, cudaStream_t st,
+                        const int32_t *edge_rows, const float *const *seg_ptrs = nullptr,
+                        const int64_t *seg_rows = nullptr, int n_segs = 0);
+// C[S, N] = act(A[S, K] W[N, K]^T + bias): the hand-written tensor-core kernel when the shape
+// allows, cuBLAS SGEMM + one elementwise pass otherwise.  act: 0 none, 2 ReLU.
+int dense_linear(cublasHandle_t blas, int64_t S, int N, int K, const float *A, const float *W,
+                 const float *bias, int act, float *out, cudaStream_t st);

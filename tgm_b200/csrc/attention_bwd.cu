@@ -276,7 +276,7 @@ extern "C" int tgm_attn_backward(tgm_attn *a, const float *node_x, const float *
   }
   // recompute the forward intermediates (R, Q, QK, U, O, Y) into the workspace
   int rc = attn_forward_impl(a, node_x, nbr_node_feat, edge_feat, seed_t, nbr_t, nullptr, nullptr,
-                             nbr_id, S, k, a->fwd_out, stream);
+                             nbr_id, S, k, a->fwd_out, stream, nullptr, /*keep_intermediates=*/true);
   if (rc != TGM_OK) return rc;
   BWD_BLAS(cublasSetStream(a->blas, st));
   // LayerNorm backward: dV = d(Y + b_O + R)

@@ -41,10 +41,12 @@ int fastf32_linear(int64_t S, int N, int K, const float *A, const float *W, cons
                    const float *residual, int gelu, float *out, cudaStream_t stream);
 extern int g_gemm_fastf32;  // tgm_set_option("gemm_fastf32", 0|1); default 1
 // tc_linear.cu: the same contract on a hand-written tcgen05 kernel (fp32 operands split in flight
-// into two TF32 terms, three products accumulated in TMEM).  N % 4 == 0, K % 4 == 0.
+// into two TF32 terms, three products accumulated in TMEM).  N % 4 == 0, K % 4 == 0.  `gelu`: 0 no
+// activation, 1 exact GELU, 2 ReLU.
 int tc3_linear(int64_t S, int N, int K, const float *A, const float *W, const float *bias,
                const float *residual, int gelu, float *out, cudaStream_t stream);
 extern int g_tc_linear;  // tgm_set_option("tc_linear", 0|1|2); default 2 (see tc_linear.cu)
+extern int g_attn_folded;  // tgm_set_option("attn_folded", 0|1); default 1 (attn_fold.cu)
 extern int g_dyg_fused_attn;  // tgm_set_option("dyg_fused_attn", 0|1); default 1
 
 inline cudaStream_t as_stream(tgm_stream s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -121,8 +123,8 @@ __device__ __forceinline__ int64_t shfl_i64(int64_t v, int src_lane) {
 // add, a three-term Cody-Waite reduction with FMAs (pi = C1 - D1 - D2), a degree-14 Taylor
 // polynomial on |r| <~ 1.75 and the sign from the parity of q.  15 instructions against ~47 for
 // libdevice cosf's fast path; larger arguments take cosf.
-__device__ __forceinline__ float t2v_cos(float a) {
-  if (!(fabsf(a) < 4194304.f)) return cosf(a);
+// the reduced-range path alone: the caller guarantees |a| < 4194304
+__device__ __forceinline__ float t2v_cos_fast(float a) {
   const float kMagic = 12582912.f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
   const float t = __fmaf_rn(a, 0.318309886183790672f, kMagic);
   const float q = t - kMagic;
@@ -139,6 +141,10 @@ __device__ __forceinline__ float t2v_cos(float a) {
   p = __fmaf_rn(p, x2, -0.5f);
   p = __fmaf_rn(p, x2, 1.0f);
   return __uint_as_float(__float_as_uint(p) ^ ((__float_as_uint(t) & 1u) << 31));
+}
+__device__ __forceinline__ float t2v_cos(float a) {
+  if (!(fabsf(a) < 4194304.f)) return cosf(a);
+  return t2v_cos_fast(a);
 }
 
 __device__ __forceinline__ void stg_stream_f4(float4 *p, const float4 &v) {

@@ -30,6 +30,8 @@
 //     The correction accumulator (2^-11 of the other) runs over the whole tile
 //   * epilogue: bias / residual / exact GELU on the register accumulators, transposed through
 //     shared memory so that every warp writes whole 800-byte output rows
+#include <algorithm>
+
 #include "common.cuh"
 
 using namespace tgm;
@@ -378,7 +380,8 @@ tc3_linear_kernel(const float *__restrict__ A, const float *__restrict__ W,
           const int c = lane + 32 * i;
           if (c < n_valid) {
             float v = y[i];
-            if (gelu) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));  // exact GELU
+            if (gelu == 1) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));  // exact GELU
+            else if (gelu == 2) v = fmaxf(v, 0.f);                                       // ReLU
             out[o + c] = v;
           }
         }
@@ -414,8 +417,17 @@ int tc3_linear(int64_t S, int N, int K, const float *A, const float *W, const fl
       !aligned16(out) || !aligned16(bias) || (residual && !aligned16(residual)) ||
       (gelu && residual))
     return 0;
-  // column tile: as wide as fits the 208-column accumulator while dividing N evenly
-  const int n_tiles = (N + 199) / 200;
+  // column tile: as wide as fits the 208-column accumulator while dividing N evenly; a short
+  // matrix (fewer row tiles than half the SMs) is cut into narrower column tiles -- down to 48
+  // columns -- so that more SMs share it and each tile's chunk loop gets shorter
+  int n_tiles = (N + 199) / 200;
+  {
+    const int64_t m_tiles = (S + BM - 1) / BM;
+    if (m_tiles * n_tiles * 2 <= kSmCount) {
+      const int fit = int(kSmCount / m_tiles), narrow = (N + 47) / 48;
+      n_tiles = std::max(n_tiles, std::min(fit, narrow));
+    }
+  }
   int BN = ((N + n_tiles - 1) / n_tiles + 3) & ~3;
   if (BN > 200) BN = 200;
   static bool configured = false;

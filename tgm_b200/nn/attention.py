@@ -278,6 +278,41 @@ class TemporalAttention(nn.Module):
             return self._forward_fused_nograd(time_encoder, node_x, nbr_node_feat, edge_feat,
                                               seed_times, nbr_times, nbr_nids, dev)
 
+    def covers_hops(self, time_encoder: Time2Vec, k: int, dev: torch.device) -> bool:
+        """True when `forward_hops` can serve this module (tgm_attn_folded_covers)."""
+        return _cabi.lib.tgm_attn_folded_covers(self._handle(time_encoder, dev), int(k)) == 1
+
+    def forward_hops(self, time_encoder: Time2Vec, node_x: Tensor, nbr_node_feat: Tensor,
+                     edge_feats, seed_times: Tensor, nbr_times: Tensor,
+                     nbr_nids: Tensor) -> Tensor:
+        """Several hops of one TGAT layer in ONE call (no gradient): all arguments cover the hops'
+        seeds back to back except the edge features, given per hop -- a list of dense
+        (rows_i, k, edge_dim) blocks left where the sampler wrote them, or of LazyEdgeRows (their
+        row ids are concatenated, the table is shared).  tgm_attn_forward_segments / _rows."""
+        from tgm_b200.sampler import LazyEdgeRows
+        dev = _need_cuda(node_x, 'TemporalAttention')
+        S, k = nbr_nids.shape
+        out = torch.empty((S, self.out_dim), dtype=torch.float32, device=dev)
+        h = self._handle(time_encoder, dev)
+        common = [seed_times.to(torch.int64).contiguous(), nbr_times.to(torch.int64).contiguous(),
+                  nbr_nids.to(torch.int32).contiguous()]
+        x, nf = _f32(node_x), _f32(nbr_node_feat)
+        if all(isinstance(e, LazyEdgeRows) for e in edge_feats):
+            table = _f32(edge_feats[0].table)
+            rows = torch.cat([e.rows.to(torch.int32).reshape(-1, k) for e in edge_feats])
+            _cabi.check(_cabi.lib.tgm_attn_forward_rows(
+                h, x.data_ptr(), nf.data_ptr(), table.data_ptr(), rows.data_ptr(),
+                *[a.data_ptr() for a in common], S, k, out.data_ptr(), _cabi.current_stream(dev)))
+            return out
+        segs = [_f32(e.materialize() if isinstance(e, LazyEdgeRows) else e) for e in edge_feats]
+        n = len(segs)
+        ptrs = (ctypes.c_void_p * n)(*[e.data_ptr() for e in segs])
+        rows = (ctypes.c_int64 * n)(*[e.shape[0] for e in segs])
+        _cabi.check(_cabi.lib.tgm_attn_forward_segments(
+            h, x.data_ptr(), nf.data_ptr(), ptrs, rows, n, *[a.data_ptr() for a in common], S, k,
+            out.data_ptr(), _cabi.current_stream(dev)))
+        return out
+
     def _forward_fused_nograd(self, time_encoder, node_x, nbr_node_feat, edge_feat, seed_times,
                               nbr_times, nbr_nids, dev) -> Tensor:
         S, k = nbr_nids.shape

@@ -34,6 +34,10 @@ class TGAT(nn.Module):
                 nbr_edge_time: List[Tensor]) -> Tensor:
         """Hop recursion of tgat.py:122-149; z[j][i] = embedding of hop-i nodes after j layers."""
         L = self.num_layers
+        if self._can_batch_hops(node_x, nbr_nids):
+            with torch.no_grad():
+                return self._forward_hops_batched(node_x, seed_nids, seed_times, nbr_nids,
+                                                  nbr_edge_x, nbr_edge_time)
         z: Dict[int, Dict[int, Tensor]] = {j: {} for j in range(L + 1)}
         z[0][0] = gather_rows(node_x, seed_nids[0])
         for i in range(1, L + 1):
@@ -48,3 +52,42 @@ class TGAT(nn.Module):
                     seed_times=seed_times[i], nbr_times=nbr_edge_time[i], nbr_nids=nbr_nids[i])
                 z[j][i] = self.merge_layers[j - 1](out, z[0][i])
         return z[L][0]
+
+    def _can_batch_hops(self, node_x: Tensor, nbr_nids: List[Tensor]) -> bool:
+        """Inference on the device with one k for all hops (tgat.py:139) and shapes the folded
+        attention chain covers: every layer runs once over the rows of all its hops."""
+        if self.num_layers < 2 or self.num_layers > 4 or not node_x.is_cuda:
+            return False
+        if torch.is_grad_enabled() and (node_x.requires_grad or
+                                        any(p.requires_grad for p in self.parameters())):
+            return False
+        k = nbr_nids[0].shape[-1]
+        if any(n.shape[-1] != k for n in nbr_nids[:self.num_layers]):
+            return False
+        return all(a.covers_hops(self.time_encoder, k, node_x.device) for a in self.attn)
+
+    def _forward_hops_batched(self, node_x, seed_nids, seed_times, nbr_nids, nbr_edge_x,
+                              nbr_edge_time) -> Tensor:
+        """The same recursion with each layer's hops as one row range.  Hop i+1's nodes are hop i's
+        neighbour slots, so with the hops stored back to back -- rows [off[i], off[i+1]) -- the
+        neighbour features of hops 0..m are simply rows [off[1], off[m+2]): no copies, and layer j
+        is one attention call + one merge call over off[L-j+1] rows instead of L-j+1 of each."""
+        L = self.num_layers
+        k = nbr_nids[0].shape[-1]
+        dev = node_x.device
+        ids = [seed_nids[0].reshape(-1)] + [nbr_nids[i].reshape(-1) for i in range(L)]
+        off = [0]
+        for t in ids:
+            off.append(off[-1] + t.numel())
+        z0 = gather_rows(node_x, torch.cat([t.to(device=dev, dtype=torch.int32) for t in ids]))
+        st = torch.cat([seed_times[i].reshape(-1).to(torch.int64) for i in range(L)])
+        nt = torch.cat([nbr_edge_time[i].reshape(-1, k).to(torch.int64) for i in range(L)])
+        ni = torch.cat([nbr_nids[i].reshape(-1, k).to(torch.int32) for i in range(L)])
+        prev = z0
+        for j in range(1, L + 1):
+            rows = off[L - j + 1]  # seeds of hops 0 .. L-j
+            out = self.attn[j - 1].forward_hops(
+                self.time_encoder, prev[:rows], prev[off[1]:off[L - j + 2]].reshape(rows, k, -1),
+                [nbr_edge_x[i] for i in range(L - j + 1)], st[:rows], nt[:rows], ni[:rows])
+            prev = self.merge_layers[j - 1](out, z0[:rows])
+        return prev[:off[1]]
