@@ -371,6 +371,24 @@ int tgm_attn_forward_segments(tgm_attn *, const float *node_x, const float *nbr_
                               int32_t n_segs, const int64_t *seed_t, const int64_t *nbr_t,
                               const int32_t *nbr_id, int64_t S, int32_t k, float *out,
                               tgm_stream stream);
+/* TGAT.forward (tgat.py:122-149) for inference as one call: the handle ties the L attention and
+ * merge-layer handles together (borrowed: they must outlive it) and owns the scratch rows.
+ * seed_ids int32[S0]; per hop i < L: nbr_ids[i] int32[S_i, k], seed_t[i] int64[S_i],
+ * nbr_t[i] int64[S_i, k] with S_0 = S0, S_{i+1} = S_i k (the hop recursion of the sampler hooks:
+ * hop i+1's seeds are hop i's slots), and the edge features either as dense blocks
+ * edge_feat[i] float32[S_i, k, edge_dim] (edge_table NULL) or as row ids edge_rows[i] int32[S_i, k]
+ * (-1 = zeros) into edge_table (edge_feat NULL).  node_x float32[num_nodes, node_dim] is indexed
+ * with torch's negative-index rule (id -1 reads the last row).  out float32[S0, embed].  Every layer
+ * needs tgm_attn_folded_covers(attn[j], k) == 1.  Same result as the per-hop calls (<= 1e-5). */
+typedef struct tgm_tgat tgm_tgat;
+int tgm_tgat_create(tgm_tgat **out, int32_t num_layers, tgm_attn *const *attn,
+                    tgm_mlp2 *const *merge, int device);
+void tgm_tgat_destroy(tgm_tgat *);
+int tgm_tgat_forward(tgm_tgat *, const float *node_x, int64_t num_nodes, const int32_t *seed_ids,
+                     int64_t S0, const int32_t *const *nbr_ids, const int64_t *const *seed_t,
+                     const int64_t *const *nbr_t, const float *const *edge_feat,
+                     const float *edge_table, const int32_t *const *edge_rows, int32_t k,
+                     float *out, tgm_stream stream);
 int tgm_attn_forward_feats(tgm_attn *, const float *node_x, const float *time_feat,
                            const float *edge_feat, const float *nbr_node_feat,
                            const float *nbr_time_feat, const int32_t *nbr_id, int64_t S, int32_t k,

@@ -145,7 +145,7 @@ def test_merge_layer_on_both_gemm_engines(dims):
         _set(b'tc_linear', 2)
 
 
-@pytest.mark.parametrize('L,lazy', [(2, False), (2, True), (3, False)])
+@pytest.mark.parametrize('L,lazy', [(1, False), (2, False), (2, True), (3, False), (3, True)])
 def test_tgat_runs_each_layer_once_over_all_hops(L, lazy):
     """TGAT.forward without gradients batches the hops of a layer into one attention + one merge
     call; with the folded chain switched off it walks the hops one by one (tgat.py:136-147).

@@ -27,23 +27,6 @@ using namespace tgm;
 
 #include "attention.cuh"
 
-struct tgm_mlp2 {
-  int device = -1;
-  int in1 = 0, in2 = 0, hidden = 0, out = 0;
-  int inp = 0;  // in1 + in2 rounded up to a multiple of 4: row pitch of `cat` and of W1 (zero padded)
-  float *W1 = nullptr, *b1 = nullptr, *W2 = nullptr, *b2 = nullptr;
-  cublasHandle_t blas = nullptr;
-  int64_t cap = 0;
-  float *cat = nullptr, *h = nullptr;
-  ~tgm_mlp2() {
-    if (device >= 0) {
-      DeviceGuard g(device);
-      for (float *p : {W1, b1, W2, b2, cat, h}) cudaFree(p);
-      if (blas) cublasDestroy(blas);
-    }
-  }
-};
-
 namespace {
 
 int blas_fail(cublasStatus_t s, const char *what) {
@@ -549,8 +532,9 @@ int attn_forward_impl(tgm_attn *a, const float *node_x, const float *nbr_node_fe
   const int od = a->out_dim, key = a->key, H = a->H, hd = a->hd;
   if (int rc = attn_workspace(a, S, st)) return rc;
   if (!keep_intermediates && !seed_tf && attn_folded_covers(a, k))
-    return attn_forward_folded(a, node_x, nbr_node_feat, edge_feat, seed_t, nbr_t, nbr_id, S, k,
-                               out, st, edge_rows);
+    return attn_forward_folded(a, node_x, nbr_node_feat,
+                               single_hop(edge_feat, edge_rows, seed_t, nbr_t, nbr_id, S), S, k,
+                               LnTarget{out, a->out_dim, nullptr, 0}, st);
   TGM_BLAS(cublasSetStream(a->blas, st));
   const float one = 1.f, zero = 0.f;
   // R = [X | pad | Time2Vec(0)],  Q = R W_Q^T
@@ -632,8 +616,19 @@ extern "C" int tgm_attn_forward_segments(tgm_attn *a, const float *node_x, const
   DeviceGuard g(a->device);
   cudaStream_t st = as_stream(stream);
   if (int rc = attn_workspace(a, S, st)) return rc;
-  return attn_forward_folded(a, node_x, nbr_node_feat, edge_feat_segs[0], seed_t, nbr_t, nbr_id, S, k,
-                             out, st, nullptr, edge_feat_segs, seg_rows, n_segs);
+  HopSegs hops{};
+  hops.n = n_segs;
+  int64_t first = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (i < n_segs) {
+      hops.nid[i] = nbr_id + first * k, hops.nt[i] = nbr_t + first * k, hops.st[i] = seed_t + first;
+      hops.ef[i] = edge_feat_segs[i];
+      first += seg_rows[i];
+    }
+    hops.end[i] = first;
+  }
+  return attn_forward_folded(a, node_x, nbr_node_feat, hops, S, k,
+                             LnTarget{out, a->out_dim, nullptr, 0}, st);
 }
 
 extern "C" int tgm_attn_forward_feats(tgm_attn *a, const float *node_x, const float *time_feat,
@@ -686,6 +681,25 @@ extern "C" int tgm_mlp2_create(tgm_mlp2 **out, int32_t in1, int32_t in2, int32_t
 
 extern "C" void tgm_mlp2_destroy(tgm_mlp2 *m) { delete m; }
 
+int mlp2_workspace(tgm_mlp2 *m, int64_t S, cudaStream_t st) {
+  if (S <= m->cap) return TGM_OK;
+  TGM_CUDA(cudaStreamSynchronize(st));
+  cudaFree(m->cat), cudaFree(m->h);
+  m->cat = m->h = nullptr;
+  m->cap = 0;
+  const size_t rows = size_t(S + S / 4);
+  TGM_CUDA(cudaMalloc(&m->cat, rows * m->inp * 4));
+  TGM_CUDA(cudaMalloc(&m->h, rows * m->hidden * 4));
+  m->cap = int64_t(rows);
+  return TGM_OK;
+}
+
+int mlp2_forward_cat(tgm_mlp2 *m, int64_t S, float *out, cudaStream_t st) {
+  // bias and ReLU ride in the product's epilogue (tensor-core kernel) or one pass after it (cuBLAS)
+  if (int rc = dense_linear(m->blas, S, m->hidden, m->inp, m->cat, m->W1, m->b1, 2, m->h, st)) return rc;
+  return dense_linear(m->blas, S, m->out, m->hidden, m->h, m->W2, m->b2, 0, out, st);
+}
+
 extern "C" int tgm_mlp2_forward(tgm_mlp2 *m, const float *x1, const float *x2, int64_t S,
                                 float *out, tgm_stream stream) {
   TGM_REQUIRE(m != nullptr, "tgm_mlp2_forward: handle is NULL");
@@ -694,22 +708,11 @@ extern "C" int tgm_mlp2_forward(tgm_mlp2 *m, const float *x1, const float *x2, i
   TGM_REQUIRE(x1 && (x2 || m->in2 == 0) && out, "tgm_mlp2_forward: NULL array argument");
   DeviceGuard g(m->device);
   cudaStream_t st = as_stream(stream);
-  const int in = m->inp;
-  if (S > m->cap) {
-    TGM_CUDA(cudaStreamSynchronize(st));
-    cudaFree(m->cat), cudaFree(m->h);
-    m->cat = m->h = nullptr;
-    m->cap = 0;
-    const size_t rows = size_t(S + S / 4);
-    TGM_CUDA(cudaMalloc(&m->cat, rows * in * 4));
-    TGM_CUDA(cudaMalloc(&m->h, rows * m->hidden * 4));
-    m->cap = int64_t(rows);
-  }
-  concat2_kernel<<<grid_for(S * in, 256, 8), 256, 0, st>>>(x1, x2, S, m->in1, m->in2, in, m->cat);
+  if (int rc = mlp2_workspace(m, S, st)) return rc;
+  concat2_kernel<<<grid_for(S * m->inp, 256, 8), 256, 0, st>>>(x1, x2, S, m->in1, m->in2, m->inp,
+                                                             m->cat);
   TGM_LAUNCH_CHECK();
-  // bias and ReLU ride in the product's epilogue (tensor-core kernel) or one pass after it (cuBLAS)
-  if (int rc = dense_linear(m->blas, S, m->hidden, in, m->cat, m->W1, m->b1, 2, m->h, st)) return rc;
-  return dense_linear(m->blas, S, m->out, m->hidden, m->h, m->W2, m->b2, 0, out, st);
+  return mlp2_forward_cat(m, S, out, st);
 }
 
 extern "C" int tgm_gather_rows(const float *table, int64_t num_rows, int32_t dim,

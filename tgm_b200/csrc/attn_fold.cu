@@ -115,22 +115,12 @@ __device__ __forceinline__ void warp_sum4(float &a, float &b, float &c, float &d
   d = __shfl_sync(0xffffffffu, w, 24);
 }
 
-// Dense edge features may arrive as up to four consecutive row ranges (the hops of one TGAT layer,
-// each its own (rows, k, edge_dim) block): segment i covers seeds [end[i-1], end[i]).
-struct EdgeSegs {
-  const float *p[4];
-  int64_t end[4];
-  int n;
-};
-
 // INLINE_Q: node_dim == 1 (TGAT layer 1 on a featureless graph): qk = x Wqx + cqk built here;
 // otherwise the x part arrives as QK = X Wqx from a plain product.
 template <int TN, int TE, int MINB, bool INLINE_Q>
 __global__ void __launch_bounds__(kWarpThreads, MINB)
 attn_warp_kernel(const float *__restrict__ X, const float *__restrict__ nbr_feat,
-                 const EdgeSegs segs, const int32_t *__restrict__ edge_rows,
-                 const int64_t *__restrict__ seed_t, const int64_t *__restrict__ nbr_t,
-                 const int32_t *__restrict__ nbr_id, const float *__restrict__ tw,
+                 const HopSegs segs, const float *__restrict__ tw,
                  const float *__restrict__ tb, const float *__restrict__ QK,
                  const float *__restrict__ Wqx, const float *__restrict__ cqk, int64_t S, int k,
                  int nd, int ed, int td, int H, float scale, int Kp, float *__restrict__ U) {
@@ -141,23 +131,23 @@ attn_warp_kernel(const float *__restrict__ X, const float *__restrict__ nbr_feat
   const bool two = H > 1;
   const int64_t base = s * k;
 
-  // per-slot scalars: lane n holds slot n (k <= 32)
-  const int64_t tq = seed_t[s];
+  // this seed's hop segment (warp-uniform), then the per-slot scalars: lane n holds slot n (k <= 32)
+  int seg = 0;
+  int64_t first = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (i + 1 < segs.n && s >= segs.end[i]) seg = i + 1, first = segs.end[i];
+  const int64_t lbase = (s - first) * k;  // slot 0 of this seed inside its segment
+  const int64_t tq = segs.st[seg][s - first];
+  const bool lazy = segs.table != nullptr;
   int my_id = TGM_PADDED_NODE_ID, my_er = -1;
   float my_dt = 0.f;
   if (lane < k) {
-    my_id = __ldg(nbr_id + base + lane);
-    my_dt = float(tq - __ldg(nbr_t + base + lane));  // int64 difference, then .float() (:23)
-    my_er = edge_rows ? __ldg(edge_rows + base + lane) : lane;
+    my_id = __ldg(segs.nid[seg] + lbase + lane);
+    my_dt = float(tq - __ldg(segs.nt[seg] + lbase + lane));  // int64 difference, then .float() (:23)
+    my_er = lazy ? __ldg(segs.er[seg] + lbase + lane) : lane;
   }
-  const float *ef = segs.p[0];  // edge_rows given: the feature table
-  if (!edge_rows) {
-    int64_t first = 0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-      if (i + 1 < segs.n && s >= segs.end[i]) ef = segs.p[i + 1], first = segs.end[i];
-    ef += (s - first) * k * ed;
-  }
+  const float *ef = lazy ? segs.table : segs.ef[seg] + lbase * ed;
   const float *nf = nbr_feat + base * nd;
 
   // qk of both heads, this lane's columns (column c of a segment at offset `off`: index off + c of
@@ -358,7 +348,8 @@ __global__ void __launch_bounds__(256)
 attn_ln_kernel(const float *__restrict__ Y, int ldy, const float *__restrict__ bo,
                const float *__restrict__ X, const float *__restrict__ t0,
                const float *__restrict__ lnw, const float *__restrict__ lnb, int64_t S, int od,
-               int nd, int toff, float eps, float *__restrict__ dst) {
+               int nd, int toff, float eps, float *__restrict__ dst, int pitch,
+               const float *__restrict__ x2, int nd2) {
   const int lane = threadIdx.x & 31;
   const int64_t s = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= S) return;
@@ -392,8 +383,11 @@ attn_ln_kernel(const float *__restrict__ Y, int ldy, const float *__restrict__ b
 #pragma unroll
   for (int t = 0; t < kLnTiles; ++t) {
     const int c = lane + 32 * t;
-    if (c < od) dst[s * od + c] = (v[t] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
+    if (c < od) dst[s * pitch + c] = (v[t] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
   }
+  // the rest of a wider destination row: the merge layer's second input, then zeros
+  for (int c = od + lane; c < pitch; c += 32)
+    dst[s * pitch + c] = (x2 && c - od < nd2) ? __ldg(x2 + s * nd2 + (c - od)) : 0.f;
 }
 
 __global__ void bias_act2_kernel(float *__restrict__ x, const float *__restrict__ b, int64_t S,
@@ -407,19 +401,18 @@ __global__ void bias_act2_kernel(float *__restrict__ x, const float *__restrict_
 }
 
 template <int TN, int TE, int MINB>
-int launch_warp(const tgm_attn *a, const float *X, const float *nbr_feat, const EdgeSegs &edge_feat,
-                const int32_t *edge_rows, const int64_t *seed_t, const int64_t *nbr_t,
-                const int32_t *nbr_id, const float *QK, int64_t S, int k, cudaStream_t st) {
+int launch_warp(const tgm_attn *a, const float *X, const float *nbr_feat, const HopSegs &hops,
+                const float *QK, int64_t S, int k, cudaStream_t st) {
   const int wpb = kWarpThreads / 32;
   const unsigned grid = unsigned((S + wpb - 1) / wpb);
   const float scale = 1.0f / sqrtf(float(a->hd));
   if (QK)
     attn_warp_kernel<TN, TE, MINB, false><<<grid, kWarpThreads, 0, st>>>(
-        X, nbr_feat, edge_feat, edge_rows, seed_t, nbr_t, nbr_id, a->tw, a->tb, QK, a->Wqx, a->cqk,
+        X, nbr_feat, hops, a->tw, a->tb, QK, a->Wqx, a->cqk,
         S, k, a->node_dim, a->edge_dim, a->time_dim, a->H, scale, a->Kp, a->U);
   else
     attn_warp_kernel<TN, TE, MINB, true><<<grid, kWarpThreads, 0, st>>>(
-        X, nbr_feat, edge_feat, edge_rows, seed_t, nbr_t, nbr_id, a->tw, a->tb, QK, a->Wqx, a->cqk,
+        X, nbr_feat, hops, a->tw, a->tb, QK, a->Wqx, a->cqk,
         S, k, a->node_dim, a->edge_dim, a->time_dim, a->H, scale, a->Kp, a->U);
   TGM_LAUNCH_CHECK();
   return TGM_OK;
@@ -489,19 +482,20 @@ bool attn_folded_covers(const tgm_attn *a, int k) {
          a->time_dim <= 32 * kTT && a->out_dim <= 32 * kLnTiles;
 }
 
+HopSegs single_hop(const float *edge_feat, const int32_t *edge_rows, const int64_t *seed_t,
+                   const int64_t *nbr_t, const int32_t *nbr_id, int64_t S) {
+  HopSegs h{};
+  h.n = 1;
+  h.nid[0] = nbr_id, h.nt[0] = nbr_t, h.st[0] = seed_t, h.end[0] = S;
+  if (edge_rows) h.table = edge_feat, h.er[0] = edge_rows;
+  else h.ef[0] = edge_feat;
+  for (int i = 1; i < 4; ++i) h.end[i] = S;
+  return h;
+}
+
 int attn_forward_folded(tgm_attn *a, const float *node_x, const float *nbr_node_feat,
-                        const float *edge_feat0, const int64_t *seed_t, const int64_t *nbr_t,
-                        const int32_t *nbr_id, int64_t S, int32_t k, float *out, cudaStream_t st,
-                        const int32_t *edge_rows, const float *const *seg_ptrs,
-                        const int64_t *seg_rows, int n_segs) {
-  EdgeSegs edge_feat;
-  edge_feat.n = 1, edge_feat.p[0] = edge_feat0, edge_feat.end[0] = S;
-  for (int i = 1; i < 4; ++i) edge_feat.p[i] = nullptr, edge_feat.end[i] = S;
-  if (seg_ptrs) {
-    edge_feat.n = n_segs;
-    int64_t end = 0;
-    for (int i = 0; i < n_segs; ++i) edge_feat.p[i] = seg_ptrs[i], edge_feat.end[i] = (end += seg_rows[i]);
-  }
+                        const HopSegs &hops, int64_t S, int32_t k, const LnTarget &target,
+                        cudaStream_t st) {
   const int od = a->out_dim, key = a->key, H = a->H, nd = a->node_dim;
   const float *QK = nullptr;
   if (nd > 1) {  // qk's x part is a plain product; a single node column folds into the kernel
@@ -514,15 +508,15 @@ int attn_forward_folded(tgm_attn *a, const float *node_x, const float *nbr_node_
   int rc;
   const bool wide_n = nd > 32, wide_e = a->edge_dim > 64;
   if (!wide_n && !wide_e)
-    rc = launch_warp<1, 2, 5>(a, node_x, nbr_node_feat, edge_feat, edge_rows, seed_t, nbr_t, nbr_id, QK, S, k, st);
+    rc = launch_warp<1, 2, 5>(a, node_x, nbr_node_feat, hops, QK, S, k, st);
   else if (!wide_n && g_attn_folded == 1)
-    rc = launch_warp<1, 6, 4>(a, node_x, nbr_node_feat, edge_feat, edge_rows, seed_t, nbr_t, nbr_id, QK, S, k, st);
+    rc = launch_warp<1, 6, 4>(a, node_x, nbr_node_feat, hops, QK, S, k, st);
   else if (!wide_n)  // experiment: attn_folded = 2
-    rc = launch_warp<1, 6, 5>(a, node_x, nbr_node_feat, edge_feat, edge_rows, seed_t, nbr_t, nbr_id, QK, S, k, st);
+    rc = launch_warp<1, 6, 5>(a, node_x, nbr_node_feat, hops, QK, S, k, st);
   else if (!wide_e)
-    rc = launch_warp<6, 2, 4>(a, node_x, nbr_node_feat, edge_feat, edge_rows, seed_t, nbr_t, nbr_id, QK, S, k, st);
+    rc = launch_warp<6, 2, 4>(a, node_x, nbr_node_feat, hops, QK, S, k, st);
   else
-    rc = launch_warp<6, 6, 3>(a, node_x, nbr_node_feat, edge_feat, edge_rows, seed_t, nbr_t, nbr_id, QK, S, k, st);
+    rc = launch_warp<6, 6, 3>(a, node_x, nbr_node_feat, hops, QK, S, k, st);
   if (rc) return rc;
   // Y = U Wov^T (bias and residual join in the LayerNorm pass)
   rc = 0;
@@ -539,7 +533,8 @@ int attn_forward_folded(tgm_attn *a, const float *node_x, const float *nbr_node_
   }
   const int wpb = 8;
   attn_ln_kernel<<<unsigned((S + wpb - 1) / wpb), 32 * wpb, 0, st>>>(
-      a->Y, a->Np, a->bo, node_x, a->t0, a->lnw, a->lnb, S, od, nd, nd + a->pad_dim, a->eps, out);
+      a->Y, a->Np, a->bo, node_x, a->t0, a->lnw, a->lnb, S, od, nd, nd + a->pad_dim, a->eps,
+      target.dst, target.pitch, target.x2, target.nd2);
   TGM_LAUNCH_CHECK();
   return TGM_OK;
 }

@@ -346,7 +346,9 @@ class MergeLayer(nn.Module):
         with torch.no_grad():
             return self._forward_nograd(x1, x2, dev, params)
 
-    def _forward_nograd(self, x1: Tensor, x2: Tensor, dev, params) -> Tensor:
+    def _handle(self, dev: torch.device) -> ctypes.c_void_p:
+        """The C handle for the current parameters (rebuilt when they change)."""
+        params = [self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias]
         ver = _version(params)
         if self._native.version != ver:
             self._native.free()
@@ -357,10 +359,14 @@ class MergeLayer(nn.Module):
                 ctypes.byref(self._native.h), self.in_dim1, self.in_dim2, self.fc1.out_features,
                 self.fc2.out_features, *[p.data_ptr() for p in t], dev.index))
             self._native.version = ver
+        return self._native.h
+
+    def _forward_nograd(self, x1: Tensor, x2: Tensor, dev, params) -> Tensor:
+        h = self._handle(dev)
         S = x1.shape[0]
         out = torch.empty((S, self.fc2.out_features), dtype=torch.float32, device=dev)
         a, b = _f32(x1), _f32(x2)
-        _cabi.check(_cabi.lib.tgm_mlp2_forward(self._native.h, a.data_ptr(), b.data_ptr(), S,
+        _cabi.check(_cabi.lib.tgm_mlp2_forward(h, a.data_ptr(), b.data_ptr(), S,
                                                out.data_ptr(), _cabi.current_stream(dev)))
         return out
 

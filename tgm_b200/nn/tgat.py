@@ -8,7 +8,11 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
-from tgm_b200.nn.attention import MergeLayer, TemporalAttention, Time2Vec, gather_rows
+import ctypes
+
+from tgm_b200 import _cabi
+from tgm_b200.nn.attention import (MergeLayer, TemporalAttention, Time2Vec, _NativeHandle, _f32,
+                                   gather_rows)
 
 
 class TGAT(nn.Module):
@@ -28,6 +32,7 @@ class TGAT(nn.Module):
             self.merge_layers.append(MergeLayer(
                 in_dim1=self.attn[-1].out_dim, in_dim2=node_dim, hidden_dim=embed_dim,
                 output_dim=embed_dim))
+        self._native = _NativeHandle(_cabi.lib.tgm_tgat_destroy)
 
     def forward(self, node_x: Tensor, seed_nids: List[Tensor], seed_times: List[Tensor],
                 nbr_nids: List[Tensor], nbr_edge_x: List[Tensor],
@@ -56,7 +61,7 @@ class TGAT(nn.Module):
     def _can_batch_hops(self, node_x: Tensor, nbr_nids: List[Tensor]) -> bool:
         """Inference on the device with one k for all hops (tgat.py:139) and shapes the folded
         attention chain covers: every layer runs once over the rows of all its hops."""
-        if self.num_layers < 2 or self.num_layers > 4 or not node_x.is_cuda:
+        if self.num_layers > 4 or not node_x.is_cuda:
             return False
         if torch.is_grad_enabled() and (node_x.requires_grad or
                                         any(p.requires_grad for p in self.parameters())):
@@ -64,30 +69,63 @@ class TGAT(nn.Module):
         k = nbr_nids[0].shape[-1]
         if any(n.shape[-1] != k for n in nbr_nids[:self.num_layers]):
             return False
+        rows = nbr_nids[0].numel() // k  # the hop recursion: every slot of hop i seeds hop i+1
+        for n in nbr_nids[:self.num_layers]:
+            if n.numel() != rows * k:
+                return False
+            rows *= k
         return all(a.covers_hops(self.time_encoder, k, node_x.device) for a in self.attn)
 
     def _forward_hops_batched(self, node_x, seed_nids, seed_times, nbr_nids, nbr_edge_x,
                               nbr_edge_time) -> Tensor:
-        """The same recursion with each layer's hops as one row range.  Hop i+1's nodes are hop i's
-        neighbour slots, so with the hops stored back to back -- rows [off[i], off[i+1]) -- the
-        neighbour features of hops 0..m are simply rows [off[1], off[m+2]): no copies, and layer j
-        is one attention call + one merge call over off[L-j+1] rows instead of L-j+1 of each."""
+        """The whole recursion as ONE native call (tgm_tgat_forward, csrc/tgat.cu).  Hop i+1's
+        nodes are hop i's neighbour slots, so with the hops stored back to back the neighbour
+        features of hops 0..m are simply a later row range of the same buffer: layer j is one
+        folded attention chain + one merge layer over the rows of hops 0..L-j, and the per-hop id /
+        time / edge-feature arrays are read where the sampler wrote them (no concatenation)."""
+        from tgm_b200.sampler import LazyEdgeRows
         L = self.num_layers
         k = nbr_nids[0].shape[-1]
         dev = node_x.device
-        ids = [seed_nids[0].reshape(-1)] + [nbr_nids[i].reshape(-1) for i in range(L)]
-        off = [0]
-        for t in ids:
-            off.append(off[-1] + t.numel())
-        z0 = gather_rows(node_x, torch.cat([t.to(device=dev, dtype=torch.int32) for t in ids]))
-        st = torch.cat([seed_times[i].reshape(-1).to(torch.int64) for i in range(L)])
-        nt = torch.cat([nbr_edge_time[i].reshape(-1, k).to(torch.int64) for i in range(L)])
-        ni = torch.cat([nbr_nids[i].reshape(-1, k).to(torch.int32) for i in range(L)])
-        prev = z0
-        for j in range(1, L + 1):
-            rows = off[L - j + 1]  # seeds of hops 0 .. L-j
-            out = self.attn[j - 1].forward_hops(
-                self.time_encoder, prev[:rows], prev[off[1]:off[L - j + 2]].reshape(rows, k, -1),
-                [nbr_edge_x[i] for i in range(L - j + 1)], st[:rows], nt[:rows], ni[:rows])
-            prev = self.merge_layers[j - 1](out, z0[:rows])
-        return prev[:off[1]]
+        attn_h = [a._handle(self.time_encoder, dev) for a in self.attn]
+        merge_h = [m._handle(dev) for m in self.merge_layers]
+        ver = tuple(h.value for h in attn_h + merge_h)
+        if self._native.version != ver:
+            self._native.free()
+            _cabi.check(_cabi.lib.tgm_tgat_create(
+                ctypes.byref(self._native.h), L, (ctypes.c_void_p * L)(*attn_h),
+                (ctypes.c_void_p * L)(*merge_h), dev.index))
+            self._native.version = ver
+        i32 = lambda t: t.to(device=dev, dtype=torch.int32).contiguous()  # noqa: E731
+        i64 = lambda t: t.to(device=dev, dtype=torch.int64).contiguous()  # noqa: E731
+        seeds = i32(seed_nids[0].reshape(-1))
+        nids = [i32(nbr_nids[i].reshape(-1, k)) for i in range(L)]
+        st = [i64(seed_times[i].reshape(-1)) for i in range(L)]
+        nt = [i64(nbr_edge_time[i].reshape(-1, k)) for i in range(L)]
+        rows = seeds.numel()
+        for i in range(L):
+            if nids[i].shape[0] != rows or st[i].numel() != rows or nt[i].shape[0] != rows:
+                raise ValueError(f'TGAT: hop {i} arrays do not hold {rows} seeds')
+            rows *= k
+        ptrs = lambda ts: (ctypes.c_void_p * L)(*[t.data_ptr() for t in ts])  # noqa: E731
+        x = _f32(node_x)
+        keep = [x, seeds, nids, st, nt]
+        lazy = all(isinstance(e, LazyEdgeRows) for e in nbr_edge_x[:L])
+        t0 = nbr_edge_x[0].table if lazy else None
+        if lazy and all(e.table.data_ptr() == t0.data_ptr() and e.table.shape == t0.shape and
+                        e.table.dtype == t0.dtype for e in nbr_edge_x[:L]):
+            table = _f32(nbr_edge_x[0].table)
+            er = [i32(e.rows.reshape(-1, k)) for e in nbr_edge_x[:L]]
+            keep += [table, er]
+            edge_args = (None, table.data_ptr(), ptrs(er))
+        else:
+            ef = [_f32(e.materialize() if isinstance(e, LazyEdgeRows) else e)
+                  for e in nbr_edge_x[:L]]
+            keep.append(ef)
+            edge_args = (ptrs(ef), None, None)
+        out = torch.empty((seeds.numel(), self.embed_dim), dtype=torch.float32, device=dev)
+        _cabi.check(_cabi.lib.tgm_tgat_forward(
+            self._native.h, x.data_ptr(), x.shape[0], seeds.data_ptr(), seeds.numel(), ptrs(nids),
+            ptrs(st), ptrs(nt), *edge_args, k, out.data_ptr(), _cabi.current_stream(dev)))
+        del keep
+        return out
