@@ -181,3 +181,41 @@ def test_tgat_runs_each_layer_once_over_all_hops(L, lazy):
             _set(b'attn_folded', 1)
     assert batched.shape == (S0, emb)
     assert float((batched - per_hop).abs().max()) <= TOL
+
+
+def test_native_tgat_and_segment_calls_reject_bad_arguments():
+    import ctypes
+    from tgm_b200.nn import TGAT
+    torch.manual_seed(0)
+    model = TGAT(3, 16, 20, 24, 2, 2).to(DEV).eval()
+    a = [m._handle(model.time_encoder, DEV) for m in model.attn]
+    g = [m._handle(DEV) for m in model.merge_layers]
+    h = ctypes.c_void_p()
+    arr = lambda hs: (ctypes.c_void_p * len(hs))(*hs)  # noqa: E731
+    lib = _cabi.lib
+    assert lib.tgm_tgat_create(ctypes.byref(h), 5, arr(a), arr(g), 0) != 0       # too many layers
+    assert lib.tgm_tgat_create(ctypes.byref(h), 2, arr(a), arr(g), -1) != 0      # no CPU form
+    assert lib.tgm_tgat_create(ctypes.byref(h), 2, arr(a[::-1]), arr(g), 0) != 0  # dims do not chain
+    assert lib.tgm_tgat_create(ctypes.byref(h), 2, arr(a), arr(g), 0) == 0 and h.value
+    try:
+        x = torch.zeros(10, 3, device=DEV)
+        st = _cabi.current_stream(DEV)
+        # NULL arrays; both / neither edge-feature form
+        assert lib.tgm_tgat_forward(h, x.data_ptr(), 10, None, 4, None, None, None, None, None,
+                                    None, 4, None, st) != 0
+        assert 'tgm_tgat_forward' in _cabi.last_error()
+        # segments that do not add up to S
+        S, k = 6, 4
+        nid = torch.zeros(S, k, dtype=torch.int32, device=DEV)
+        t64 = torch.zeros(S, k, dtype=torch.int64, device=DEV)
+        ef = torch.zeros(S, k, 16, device=DEV)
+        out = torch.zeros(S, 24, device=DEV)
+        nf = torch.zeros(S, k, 3, device=DEV)
+        segs = (ctypes.c_void_p * 2)(ef.data_ptr(), ef.data_ptr())
+        rows = (ctypes.c_int64 * 2)(2, 3)
+        assert lib.tgm_attn_forward_segments(a[0], x.data_ptr(), nf.data_ptr(), segs, rows, 2,
+                                             t64.data_ptr(), t64.data_ptr(), nid.data_ptr(), S, k,
+                                             out.data_ptr(), st) != 0
+        assert lib.tgm_attn_folded_covers(a[0], 33) == 0 and lib.tgm_attn_folded_covers(a[0], 32) == 1
+    finally:
+        lib.tgm_tgat_destroy(h)

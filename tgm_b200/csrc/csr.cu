@@ -1570,7 +1570,7 @@ extern "C" int tgm_set_option(const char *name, int value) {
     return TGM_OK;
   }
   if (std::strcmp(name, "attn_folded") == 0) {
-    TGM_REQUIRE(value >= 0 && value <= 2, "tgm_set_option: attn_folded must be 0 or 1");
+    TGM_REQUIRE(value == 0 || value == 1, "tgm_set_option: attn_folded must be 0 or 1");
     tgm::g_attn_folded = value;
     return TGM_OK;
   }
