@@ -11,10 +11,12 @@ from .constants import PADDED_NODE_ID
 from .core import DGBatch, DGraph, TimeDeltaDG
 from .data import DGData, DGDataLoader
 from .hooks import (DeduplicationHook, HookManager, NeighborSamplerHook,
-                    RandomNegativeEdgeSamplerHook, RecencyNeighborHook)
+                    RandomNegativeEdgeSamplerHook, RecencyNeighborHook, TGBNegativeEdgeSamplerHook,
+                    TGBTHGNegativeEdgeSamplerHook, TGBTKGNegativeEdgeSamplerHook)
 from .sampler import RecencyCSR
 
 __version__ = '0.1.0'
 __all__ = ['DGraph', 'DGBatch', 'DGData', 'DGDataLoader', 'TimeDeltaDG', 'HookManager',
            'RecencyNeighborHook', 'NeighborSamplerHook', 'RandomNegativeEdgeSamplerHook', 'DeduplicationHook',
+           'TGBNegativeEdgeSamplerHook', 'TGBTHGNegativeEdgeSamplerHook', 'TGBTKGNegativeEdgeSamplerHook',
            'RecencyCSR', 'PADDED_NODE_ID']
