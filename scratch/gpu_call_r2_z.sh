@@ -1,4 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 100 python scratch/minb_ab.py 2>&1 | tail -4
-timeout 400 python -m pytest tests/test_gpu_attn_folded.py -q > gpurun_out/z_tests.log 2>&1; tail -3 gpurun_out/z_tests.log
+timeout 600 python bench.py > gpurun_out/full_bench.json 2> gpurun_out/full_bench.err
+python - <<'PY'
+import json
+d = json.load(open('gpurun_out/full_bench.json'))
+print('build_s', d['build_s'], 'incl_build', d['full_pass']['value_incl_build'], 'value', d['value'], 'e2e', d['e2e']['value'])
+PY
