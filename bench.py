@@ -499,7 +499,8 @@ def run_b200(a):
         'build_s': build_max, 'sample_s': pass_max, 'windows': len(fwins),
         'what': 'every loader batch of the stream sampled once (this rank\'s shard; under-filled '
                 'head included), plus the one-off build of store handle + adjacency + anchors + '
-                'colocated feature rows from the device-resident edge arrays'}
+                'colocated feature rows from the device-resident edge arrays (timed after a '
+                'throw-away 100k-edge build that loads the build kernels)'}
 
     # ---- e2e: host buffers in, host buffers out, through the C ABI --------------------------
     e2e = None
