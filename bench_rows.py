@@ -291,10 +291,21 @@ def row_stream_kernels():
          note='single pass (tile tickets + decoupled look-back); includes one .item() sync for the count')
     te = Time2Vec(100).to(DEV)
     dt = torch.randint(0, 2_600_000, (400_000,), generator=g, device=DEV)
-    ms = cuda_ms(lambda: te(dt))
+    from tgm_b200 import _cabi
+    w, b = te.w.weight.detach().reshape(-1).contiguous(), te.w.bias.detach().contiguous()
+    out = torch.empty((dt.numel(), 100), device=DEV)
+    st = torch.cuda.current_stream(DEV).cuda_stream
+    ms = cuda_ms(lambda: _cabi.check(_cabi.lib.tgm_time2vec(dt.data_ptr(), dt.numel(), w.data_ptr(),
+                                                            b.data_ptr(), 100, out.data_ptr(), st)))
+    with torch.no_grad():
+        ms_module = cuda_ms(lambda: te(dt))
     emit('A1 time2vec_kernel (4e5 deltas x 100 dims)', value=dt.numel() * 100 / (ms * 1e-3),
-         unit='encodings/s', ms=ms, roofline=hbm(dt.numel() * (8 + 400), ms),
-         note='warp per row, 15-instruction cosine (1.6e-7 abs); includes the torch output allocation')
+         unit='encodings/s', ms=ms, ms_through_the_module=ms_module,
+         roofline=hbm(dt.numel() * (8 + 400), ms),
+         note='tgm_time2vec into a preallocated output: warp per row, 15-instruction cosine (1.6e-7 '
+              'abs); issue-bound (IPC 2.2 per SM, fixed-latency stalls of the polynomial chain). A '
+              'variant with no idle lanes (8 rows = 25 whole tiles per warp) measured the same '
+              '84 us and was dropped')
 
 
 # ---- A2/A3 TGAT (config 3) --------------------------------------------------------------------------

@@ -1,8 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python bench.py > gpurun_out/full_bench.json 2> gpurun_out/full_bench.err
-python - <<'PY'
-import json
-d = json.load(open('gpurun_out/full_bench.json'))
-print('build_s', d['build_s'], 'incl_build', d['full_pass']['value_incl_build'], 'value', d['value'], 'e2e', d['e2e']['value'])
-PY
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:time2vec -s 2 -c 1 -o gpurun_out/t2v -f python scratch/t2v_probe.py > gpurun_out/t2v_ncu.log 2>&1; tail -2 gpurun_out/t2v_ncu.log

@@ -439,6 +439,26 @@ def test_time2vec_within_1e5():
         assert float(np.abs(out.cpu().numpy().astype(np.float64) - want).max()) <= 1e-5
 
 
+@pytest.mark.parametrize('d', [36, 50, 96, 100, 128, 33, 7])
+def test_time2vec_widths_and_row_counts(d):
+    """Widths with full, partial and single column tiles over row counts that leave partial
+    grids, with arguments on both sides of the cosine's reduced-range limit."""
+    from oracle.recency_oracle import time2vec
+    rng = np.random.default_rng(d)
+    w = (1.0 / 10 ** np.linspace(0, 9, d)).astype(np.float32)
+    b = rng.standard_normal(d).astype(np.float32)
+    for n, hi in ((1, 1000), (37, 2_700_000), (1025, 2_000_000_000)):
+        dt = rng.integers(0, hi, n).astype(np.int64)
+        out = torch.full((n + 1, d), float('nan'), dtype=torch.float32, device=DEV)
+        ddt, dw, db = dev(dt, torch.int64), dev(w, torch.float32), dev(b, torch.float32)
+        _cabi.check(_cabi.lib.tgm_time2vec(ddt.data_ptr(), n, dw.data_ptr(), db.data_ptr(), d,
+                                           out.data_ptr(), stream()))
+        got = out.cpu().numpy()
+        assert np.isnan(got[n]).all()  # nothing written past the last row
+        want = time2vec(dt, w, b, fused=True)
+        assert float(np.abs(got[:n].astype(np.float64) - want).max()) <= 1e-5, (d, n)
+
+
 # ---- error behaviour of the C ABI on a live device --------------------------------------------
 def test_query_argument_errors():
     ring = Ring(8, 4, 0)
