@@ -371,6 +371,11 @@ int tgm_attn_forward_segments(tgm_attn *, const float *node_x, const float *nbr_
                               int32_t n_segs, const int64_t *seed_t, const int64_t *nbr_t,
                               const int32_t *nbr_id, int64_t S, int32_t k, float *out,
                               tgm_stream stream);
+/* C[M,N] = act(A[M,K] W[N,K]^T + bias[N]) (bias nullable; act 0 = none, 2 = ReLU), fp32 FMA in
+ * ascending k, for short matrices (M <= 2^20; built for the few-hundred-row products of TGAT's last
+ * layer, tgat.py:136-149): 32x32 output tiles, one launch, epilogue fused. */
+int tgm_small_gemm(int64_t M, int32_t N, int32_t K, const float *A, const float *W, const float *bias,
+                   int32_t act, float *C, tgm_stream stream);
 /* TGAT.forward (tgat.py:122-149) for inference as one call: the handle ties the L attention and
  * merge-layer handles together (borrowed: they must outlive it) and owns the scratch rows.
  * seed_ids int32[S0]; per hop i < L: nbr_ids[i] int32[S_i, k], seed_t[i] int64[S_i],

@@ -86,3 +86,33 @@ def test_tc_linear_argument_errors():
     with pytest.raises(_cabi.TGMNativeError, match='N % 4 == 0'):
         _cabi.check(_cabi.lib.tgm_tc_linear(8, 8, 6, A.data_ptr(), A.data_ptr(), A.data_ptr(), None,
                                             0, A.data_ptr(), None))
+
+
+@pytest.mark.parametrize('M,N,K,act,with_bias', [
+    (600, 888, 172, 0, False),   # TGAT layer 2: x-side qk product
+    (600, 272, 888, 0, False),   # folded output product
+    (600, 172, 444, 2, True),    # merge layer fc1 + ReLU
+    (600, 172, 172, 0, True),
+    (33, 31, 50, 2, True),       # tails in every dimension, K % 4 != 0 (scalar loads)
+    (1, 1, 1, 0, True),
+    (4096, 104, 548, 0, False),
+], ids=['qk', 'out', 'fc1_relu', 'fc2', 'tails', 'one', 'limit'])
+def test_small_gemm_matches_float64(M, N, K, act, with_bias):
+    """tgm_small_gemm (csrc/small_gemm.cu): 32x32 SIMT tiles, fused bias / ReLU."""
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g, device=DEV)
+    W = torch.randn(N, K, generator=g, device=DEV) / K ** 0.5
+    b = torch.randn(N, generator=g, device=DEV) if with_bias else None
+    out = torch.full((M + 1, N), float('nan'), device=DEV)
+    _cabi.check(_cabi.lib.tgm_small_gemm(M, N, K, A.data_ptr(), W.data_ptr(), _cabi.ptr(b), act,
+                                         out.data_ptr(), torch.cuda.current_stream(DEV).cuda_stream))
+    want = A.double() @ W.double().T
+    if with_bias:
+        want = want + b.double()
+    if act == 2:
+        want = want.relu()
+    assert bool(torch.isnan(out[M]).all()), 'wrote past the last row'
+    err = float((out[:M].double() - want).abs().max())
+    # one fp32 FMA chain over K (what an SGEMM does): the bar is the path's 1e-5, not the 4e-6 of
+    # the chunk-promoted tensor-core kernel
+    assert err <= 1e-5 * max(1.0, float(want.abs().max()) / 8), err

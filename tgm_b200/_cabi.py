@@ -123,6 +123,8 @@ SIGNATURES = {
     'tgm_attn_forward_segments': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                           c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
                                           c_void_p]),
+    'tgm_small_gemm': (c_int, [c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
+                               c_void_p, c_void_p]),
     'tgm_tgat_create': (c_int, [POINTER(c_void_p), c_int32, c_void_p, c_void_p, c_int]),
     'tgm_tgat_destroy': (None, [c_void_p]),
     'tgm_tgat_forward': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,

@@ -16,7 +16,7 @@ CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc')
 LIB_PATH = os.path.join(CSRC, 'libtgm_b200.so')
 OBJ_DIR = os.path.join(CSRC, '_obj')
 SOURCES = ['store.cu', 'recency_ring.cu', 'csr.cu', 'frontier.cu', 'dedup.cu', 'aggregate.cu', 'attention.cu', 'attn_fold.cu', 'tgat.cu', 'attention_bwd.cu',
-           'tgn_memory.cu', 'graph_attn.cu', 'dygformer.cu', 'gemm_fastf32.cu', 'uniform_exact.cu', 'negatives.cu', 'memory_join.cu', 'tc_linear.cu']
+           'tgn_memory.cu', 'graph_attn.cu', 'dygformer.cu', 'gemm_fastf32.cu', 'uniform_exact.cu', 'negatives.cu', 'memory_join.cu', 'tc_linear.cu', 'small_gemm.cu']
 LINK_FLAGS = ['-lcublas', '-Xlinker', '-rpath=/usr/local/cuda/lib64']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC']

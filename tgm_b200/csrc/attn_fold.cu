@@ -11,7 +11,7 @@
 //
 // The folded matrices are a few hundred kB, computed in float64 and rounded once, every time the
 // parameters change (create / set_params).  A call is then
-//   [node_dim > 4: QK = X Wqx^T]  ->  attn_warp_kernel  ->  Y = U Wov^T  ->  LayerNorm epilogue
+//   [node_dim > 1: QK = X Wqx^T]  ->  attn_warp_kernel  ->  Y = U Wov^T  ->  LayerNorm epilogue
 // 3-4 launches against 7, and the neighbour kernel is one WARP per seed: every lane owns columns
 // lane, lane+32, ... of the key vector in registers, rows stream through once (next row
 // prefetched), the softmax is the running-maximum form, and nothing goes through shared memory or
@@ -56,8 +56,9 @@ __global__ void fold_qt0_kernel(const float *__restrict__ Wq, const float *__res
   qt0_lo[r] = float(acc - double(hi));
 }
 
-// column i < nd: Wqx[i, n] = sum_d W_K[(h, d), j] W_Q[(h, d), i]  (stored [nd, H key]: lanes read
-// consecutive n);  i == nd: cqk[n] with qt0
+// column i < nd: Wqx[n, i] = sum_d W_K[(h, d), j] W_Q[(h, d), i]  ([H key, nd]: the W of an
+// "A W^T" product; with node_dim == 1, the in-kernel case, lanes read consecutive n);
+// i == nd: cqk[n] with qt0
 __global__ void fold_qk_kernel(const float *__restrict__ Wq, const float *__restrict__ Wk,
                                const float *__restrict__ qt0_hi, const float *__restrict__ qt0_lo,
                                int H, int hd, int od, int key, int nd, float *__restrict__ Wqx,
@@ -74,7 +75,7 @@ __global__ void fold_qk_kernel(const float *__restrict__ Wq, const float *__rest
     const double q = i < nd ? double(Wq[size_t(r) * od + i]) : double(qt0_hi[r]) + double(qt0_lo[r]);
     acc += wk * q;
   }
-  if (i < nd) Wqx[size_t(i) * H * key + n] = float(acc);
+  if (i < nd) Wqx[size_t(n) * nd + i] = float(acc);
   else cqk[n] = float(acc);
 }
 
@@ -422,17 +423,26 @@ int launch_warp(const tgm_attn *a, const float *X, const float *nbr_feat, const 
 
 // which engine for C[S, N] = A[S, K] W[N, K]^T: measured on the B200 (profiles/r2_tc_linear_timings.txt)
 //   * no activation, >= 2048 rows: the CUTLASS FastF32 collective (31 vs 42 us at 12600x104x548)
-//   * short matrices (row tiles <= half the SMs) with K > 256: cuBLAS (its split-K beats one CTA
-//     walking 23 chunks: 25 vs 56 us at 600x272x888)
+//   * short matrices (<= 4096 rows) WITH a bias / activation: the 32x32-tile SIMT kernel of
+//     small_gemm.cu, one launch with the epilogue fused (600x172x444 + ReLU: 12 us against
+//     cuBLAS split-K + reduce + bias pass 23 us; 600x172x172: 9 vs 18 on the tensor-core kernel,
+//     whose 128-row tiles leave most SMs idle there).  Without an epilogue cuBLAS split-K keeps the
+//     short products (600x888x172: 11 vs 18 us; 600x272x888: 32 vs 36)
 //   * otherwise the hand-written tcgen05 kernel with bias / ReLU in its epilogue
+constexpr int64_t kSmallRows = 4096;
 static bool tc3_suits(int64_t S, int K) {
-  return g_tc_linear != 0 && !(((S + 127) / 128) * 2 <= kSmCount && K > 256);
+  (void)K;
+  return g_tc_linear != 0 && S > kSmallRows;
 }
 
 int dense_linear(cublasHandle_t blas, int64_t S, int N, int K, const float *A, const float *W,
                  const float *bias, int act, float *out, cudaStream_t st) {
   if (act == 0 && S >= 2048 && g_gemm_fastf32) {
     const int rc = fastf32_linear(S, N, K, A, W, bias, nullptr, 0, out, st);
+    if (rc != 0) return rc < 0 ? rc : TGM_OK;
+  }
+  if (S <= kSmallRows) {
+    const int rc = small_gemm_nt(S, N, K, A, K, 0, W, K, 0, bias, act, out, N, 0, 1, st);
     if (rc != 0) return rc < 0 ? rc : TGM_OK;
   }
   if (tc3_suits(S, K)) {
@@ -501,8 +511,8 @@ int attn_forward_folded(tgm_attn *a, const float *node_x, const float *nbr_node_
   if (nd > 1) {  // qk's x part is a plain product; a single node column folds into the kernel
     const float one = 1.f, zero = 0.f;
     TGM_BLAS2(cublasSetStream(a->blas, st));
-    TGM_BLAS2(cublasSgemm(a->blas, CUBLAS_OP_N, CUBLAS_OP_N, H * key, int(S), nd, &one, a->Wqx,
-                          H * key, node_x, nd, &zero, a->QK, H * key));
+    TGM_BLAS2(cublasSgemm(a->blas, CUBLAS_OP_T, CUBLAS_OP_N, H * key, int(S), nd, &one, a->Wqx, nd,
+                          node_x, nd, &zero, a->QK, H * key));
     QK = a->QK;
   }
   int rc;

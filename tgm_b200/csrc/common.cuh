@@ -45,6 +45,11 @@ extern int g_gemm_fastf32;  // tgm_set_option("gemm_fastf32", 0|1); default 1
 // activation, 1 exact GELU, 2 ReLU.
 int tc3_linear(int64_t S, int N, int K, const float *A, const float *W, const float *bias,
                const float *residual, int gelu, float *out, cudaStream_t stream);
+// small_gemm.cu: C[M,N] = act(A[M,K] W[N,K]^T + bias) for short matrices (32x32 SIMT tiles, fused
+// epilogue, optional batch via strides); act 0 none / 2 ReLU; bias may be NULL.  1 = computed.
+int small_gemm_nt(int64_t M, int N, int K, const float *A, int lda, int64_t strideA, const float *W,
+                  int ldw, int64_t strideW, const float *bias, int act, float *C, int ldc,
+                  int64_t strideC, int batch, cudaStream_t st);
 extern int g_tc_linear;  // tgm_set_option("tc_linear", 0|1|2); default 2 (see tc_linear.cu)
 extern int g_attn_folded;  // tgm_set_option("attn_folded", 0|1); default 1 (attn_fold.cu)
 extern int g_dyg_fused_attn;  // tgm_set_option("dyg_fused_attn", 0|1); default 1
