@@ -47,6 +47,17 @@ int tc3_linear(int64_t S, int N, int K, const float *A, const float *W, const fl
                const float *residual, int gelu, float *out, cudaStream_t stream);
 // small_gemm.cu: C[M,N] = act(A[M,K] W[N,K]^T + bias) for short matrices (32x32 SIMT tiles, fused
 // epilogue, optional batch via strides); act 0 none / 2 ReLU; bias may be NULL.  1 = computed.
+constexpr int kSmallGemmMaxGroups = 8;
+struct SmallGemmGroups {  // group i: batch[i] products A_i[z] (M x K_i) W_i^T -> C_i[z] (M x N)
+  const float *A[kSmallGemmMaxGroups], *W[kSmallGemmMaxGroups], *bias[kSmallGemmMaxGroups];
+  float *C[kSmallGemmMaxGroups];
+  int K[kSmallGemmMaxGroups], lda[kSmallGemmMaxGroups], ldw[kSmallGemmMaxGroups],
+      batch[kSmallGemmMaxGroups];
+  int64_t strideA[kSmallGemmMaxGroups], strideC[kSmallGemmMaxGroups];
+  bool vec[kSmallGemmMaxGroups];  // filled by small_gemm_groups
+  int n;
+};
+int small_gemm_groups(const SmallGemmGroups &g, int64_t M, int N, int ldc, int act, cudaStream_t st);
 int small_gemm_nt(int64_t M, int N, int K, const float *A, int lda, int64_t strideA, const float *W,
                   int ldw, int64_t strideW, const float *bias, int act, float *C, int ldc,
                   int64_t strideC, int batch, cudaStream_t st);

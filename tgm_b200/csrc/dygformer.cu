@@ -761,19 +761,42 @@ extern "C" int tgm_dyg_forward(tgm_dyg *m, const float *node_x, int64_t num_node
   TGM_LAUNCH_CHECK();
 
   // channel projections into the token layout X[b, side*NP + p, c*C ...] (dygformer.py:330-413);
-  // a patch is P consecutive positions, i.e. a row of the [rows*NP, P*d] view of the channel
-  for (int c = 0; c < 4; ++c) {
-    const int K = P * dims[c];
-    for (int side = 0; side < 2; ++side) {
-      const float *A = m->feat[c] + size_t(side) * B * L * dims[c];
-      float *Cp = m->X + size_t(side) * NP * E + size_t(c) * C;
-      DYG_BLAS(cublasSgemmStridedBatched(m->blas, CUBLAS_OP_T, CUBLAS_OP_N, C, NP, K, &one,
-                                         m->proj_w[c], K, 0, A, K, int64_t(NP) * K, &zero, Cp, E,
-                                         int64_t(T) * E, int(B)));
+  // a patch is P consecutive positions, i.e. a row of the [rows*NP, P*d] view of the channel.
+  // The 8 B small products (4 channels x 2 sides x B pairs, NP x C x P d_c each) and their bias go
+  // out as ONE launch of the grouped short-matrix kernel (small_gemm.cu); the library form is
+  // eight strided-batched SGEMMs + a bias pass.
+  int proj_rc = 0;
+  if (2 * B <= 8000) {
+    SmallGemmGroups pg{};
+    pg.n = 8;
+    for (int c = 0; c < 4; ++c) {
+      const int K = P * dims[c];
+      for (int side = 0; side < 2; ++side) {
+        const int gi = 2 * c + side;
+        pg.A[gi] = m->feat[c] + size_t(side) * B * L * dims[c];
+        pg.W[gi] = m->proj_w[c], pg.bias[gi] = m->proj_b + c * C;
+        pg.C[gi] = m->X + size_t(side) * NP * E + size_t(c) * C;
+        pg.K[gi] = K, pg.lda[gi] = K, pg.ldw[gi] = K, pg.batch[gi] = int(B);
+        pg.strideA[gi] = int64_t(NP) * K, pg.strideC[gi] = int64_t(T) * E;
+      }
     }
+    proj_rc = small_gemm_groups(pg, NP, C, E, 0, st);
+    if (proj_rc < 0) return proj_rc;
   }
-  add_bias_kernel<<<grid_for(tokens * E, 256, 8), 256, 0, st>>>(m->X, m->proj_b, tokens, E, 0);
-  TGM_LAUNCH_CHECK();
+  if (proj_rc == 0) {
+    for (int c = 0; c < 4; ++c) {
+      const int K = P * dims[c];
+      for (int side = 0; side < 2; ++side) {
+        const float *A = m->feat[c] + size_t(side) * B * L * dims[c];
+        float *Cp = m->X + size_t(side) * NP * E + size_t(c) * C;
+        DYG_BLAS(cublasSgemmStridedBatched(m->blas, CUBLAS_OP_T, CUBLAS_OP_N, C, NP, K, &one,
+                                           m->proj_w[c], K, 0, A, K, int64_t(NP) * K, &zero, Cp, E,
+                                           int64_t(T) * E, int(B)));
+      }
+    }
+    add_bias_kernel<<<grid_for(tokens * E, 256, 8), 256, 0, st>>>(m->X, m->proj_b, tokens, E, 0);
+    TGM_LAUNCH_CHECK();
+  }
 
   const float scale = 1.0f / sqrtf(float(hd));
   for (const DygLayerDev &ly : m->lay) {  // TransformerEncoder.forward (:117-143)

@@ -45,24 +45,36 @@ __device__ __forceinline__ void store_tile(float (*dst)[kBM + kPad], int tid, co
   }
 }
 
-// act: 0 none, 2 ReLU.  grid (N tiles, M tiles, batch); strides in elements between batch items.
-template <bool VEC>
+// act: 0 none, 2 ReLU.  grid (N tiles, M tiles, sum of the groups' batch counts); a group is a
+// batch of equally shaped products (same W, A / C advancing by a stride); all groups share M, N, ldc.
 __global__ void __launch_bounds__(kThreadsSG)
-sgemm_nt_small_kernel(const float *__restrict__ A, int lda, int64_t strideA,
-                      const float *__restrict__ W, int ldw, int64_t strideW,
-                      const float *__restrict__ bias, float *__restrict__ C, int ldc,
-                      int64_t strideC, int M, int N, int K, int act) {
+sgemm_nt_small_kernel(const SmallGemmGroups g, int ldc, int M, int N, int act) {
   __shared__ __align__(16) float As[2][kBK][kBM + kPad];
   __shared__ __align__(16) float Ws[2][kBK][kBN + kPad];
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;  // 4 columns x 2 rows per thread
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
-  A += blockIdx.z * strideA + int64_t(m0) * lda;
-  W += blockIdx.z * strideW + int64_t(n0) * ldw;
-  C += blockIdx.z * strideC;
+  int gi = 0, z = int(blockIdx.z);
+#pragma unroll
+  for (int i = 0; i < kSmallGemmMaxGroups - 1; ++i)
+    if (i + 1 < g.n && z >= g.batch[gi]) z -= g.batch[gi], gi = i + 1;
+  const int lda = g.lda[gi], ldw = g.ldw[gi], K = g.K[gi];
+  const float *__restrict__ A = g.A[gi] + z * g.strideA[gi] + int64_t(m0) * lda;
+  const float *__restrict__ W = g.W[gi] + int64_t(n0) * ldw;
+  const float *__restrict__ bias = g.bias[gi];
+  float *__restrict__ C = g.C[gi] + z * g.strideC[gi];
   const int a_rows = min(kBM, M - m0), w_rows = min(kBN, N - n0);
+  const bool vec = g.vec[gi];  // 128-bit loads: K, the leading dimensions and the bases allow it
   float ra[8], rw[8];
-  load_tile<VEC>(A, lda, a_rows, 0, K, tid, ra);
-  load_tile<VEC>(W, ldw, w_rows, 0, K, tid, rw);
+  auto load = [&](int k0) {
+    if (vec) {
+      load_tile<true>(A, lda, a_rows, k0, K, tid, ra);
+      load_tile<true>(W, ldw, w_rows, k0, K, tid, rw);
+    } else {
+      load_tile<false>(A, lda, a_rows, k0, K, tid, ra);
+      load_tile<false>(W, ldw, w_rows, k0, K, tid, rw);
+    }
+  };
+  load(0);
   store_tile(As[0], tid, ra);
   store_tile(Ws[0], tid, rw);
   __syncthreads();
@@ -70,10 +82,7 @@ sgemm_nt_small_kernel(const float *__restrict__ A, int lda, int64_t strideA,
   const int chunks = (K + kBK - 1) / kBK;
   for (int c = 0; c < chunks; ++c) {
     const int cur = c & 1;
-    if (c + 1 < chunks) {  // next chunk's global loads fly during this chunk's FMAs
-      load_tile<VEC>(A, lda, a_rows, (c + 1) * kBK, K, tid, ra);
-      load_tile<VEC>(W, ldw, w_rows, (c + 1) * kBK, K, tid, rw);
-    }
+    if (c + 1 < chunks) load((c + 1) * kBK);  // the next chunk's loads fly during this chunk's FMAs
 #pragma unroll
     for (int k = 0; k < kBK; ++k) {
       const float2 a = *reinterpret_cast<const float2 *>(&As[cur][k][2 * ty]);
@@ -110,22 +119,34 @@ sgemm_nt_small_kernel(const float *__restrict__ A, int lda, int64_t strideA,
 namespace tgm {
 
 // 1 = computed, 0 = not applicable (batch or tile count out of range), < 0 = error
+int small_gemm_groups(const SmallGemmGroups &g_in, int64_t M, int N, int ldc, int act,
+                      cudaStream_t st) {
+  SmallGemmGroups g = g_in;
+  if (M < 1 || N < 1 || g.n < 1 || g.n > kSmallGemmMaxGroups || M > (int64_t(1) << 20)) return 0;
+  int64_t batches = 0;
+  for (int i = 0; i < g.n; ++i) {
+    if (g.K[i] < 1 || g.batch[i] < 1) return 0;
+    batches += g.batch[i];
+    g.vec[i] = g.K[i] % 4 == 0 && g.lda[i] % 4 == 0 && g.ldw[i] % 4 == 0 && g.strideA[i] % 4 == 0 &&
+               aligned16(g.A[i]) && aligned16(g.W[i]);
+  }
+  const dim3 grid(unsigned((N + kBN - 1) / kBN), unsigned((M + kBM - 1) / kBM), unsigned(batches));
+  if (grid.y > 65535 || batches > 65535) return 0;
+  sgemm_nt_small_kernel<<<grid, kThreadsSG, 0, st>>>(g, ldc, int(M), N, act);
+  TGM_LAUNCH_CHECK();
+  return 1;
+}
+
 int small_gemm_nt(int64_t M, int N, int K, const float *A, int lda, int64_t strideA, const float *W,
                   int ldw, int64_t strideW, const float *bias, int act, float *C, int ldc,
                   int64_t strideC, int batch, cudaStream_t st) {
-  if (M < 1 || N < 1 || K < 1 || batch < 1 || batch > 65535 || M > (int64_t(1) << 20)) return 0;
-  const dim3 grid(unsigned((N + kBN - 1) / kBN), unsigned((M + kBM - 1) / kBM), unsigned(batch));
-  if (grid.y > 65535) return 0;
-  const bool vec = K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0 && strideA % 4 == 0 &&
-                   strideW % 4 == 0 && aligned16(A) && aligned16(W);
-  if (vec)
-    sgemm_nt_small_kernel<true><<<grid, kThreadsSG, 0, st>>>(A, lda, strideA, W, ldw, strideW, bias,
-                                                             C, ldc, strideC, int(M), N, K, act);
-  else
-    sgemm_nt_small_kernel<false><<<grid, kThreadsSG, 0, st>>>(A, lda, strideA, W, ldw, strideW, bias,
-                                                              C, ldc, strideC, int(M), N, K, act);
-  TGM_LAUNCH_CHECK();
-  return 1;
+  if (strideW != 0 && batch != 1) return 0;  // one W per group
+  SmallGemmGroups g{};
+  g.n = 1;
+  g.A[0] = A, g.W[0] = W, g.bias[0] = bias, g.C[0] = C;
+  g.K[0] = K, g.lda[0] = lda, g.ldw[0] = ldw, g.strideA[0] = strideA, g.strideC[0] = strideC;
+  g.batch[0] = batch;
+  return small_gemm_groups(g, M, N, ldc, act, st);
 }
 
 }  // namespace tgm
