@@ -349,10 +349,13 @@ def run_b200(a):
         # stdout carries the one JSON line the driver parses: NCCL's own log (whatever level the
         # environment asks for; INIT lines by default so the communicator size is on record) goes
         # to stderr
-        os.environ.setdefault('NCCL_DEBUG', 'INFO')
-        if os.environ['NCCL_DEBUG'].upper() == 'INFO':
+        # never lowered, never silenced: a quieter preset (this pool's boxes export
+        # NCCL_DEBUG=VERSION) is raised to INFO / INIT so the communicator size is on record
+        if os.environ.get('NCCL_DEBUG', '').upper() not in ('INFO', 'TRACE'):
+            os.environ['NCCL_DEBUG'] = 'INFO'
             os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT')
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        # (no NCCL_DEBUG_FILE: NCCL logs to fd 1, which now IS stderr; reopening /dev/stderr by
+        # name would truncate it when stderr is a regular file)
         dist.init_process_group('nccl', device_id=dev)
 
     E, N, D, k, bs = a.edges, a.nodes, a.dim, a.k, a.batch_size
