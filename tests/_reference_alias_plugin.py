@@ -22,6 +22,10 @@ def _alias(pkg, as_name: str) -> None:
 
 
 _alias(tgm_b200, 'tgm')
+# import paths the package registers without a file behind them (tgm_b200/nn/__init__.py)
+for _name, _m in list(sys.modules.items()):
+    if _name.startswith('tgm_b200.') and _m is not None:
+        sys.modules.setdefault('tgm' + _name[len('tgm_b200'):], _m)
 
 
 # Names the reference's test modules import that are OUT OF SCOPE here (splits,
