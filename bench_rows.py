@@ -285,10 +285,18 @@ def row_stream_kernels():
     emit('A4 masked_mean_kernel (2e6 seeds, k=20, D=16)', value=S / (ms * 1e-3), unit='seeds/s', ms=ms,
          roofline=hbm(S * (k * D * 4 + k * 4 + D * 4), ms))
     flat = nid.reshape(-1)
-    ms = cuda_ms(lambda: compact_frontier(flat))
+    from tgm_b200 import _cabi
+    st = torch.cuda.current_stream(DEV).cuda_stream
+    idx = torch.empty(flat.numel(), dtype=torch.int64, device=DEV)
+    cnt = torch.zeros(1, dtype=torch.int64, device=DEV)
+    ms = cuda_ms(lambda: _cabi.check(_cabi.lib.tgm_frontier_compact(
+        flat.data_ptr(), flat.numel(), idx.data_ptr(), cnt.data_ptr(), st)))
+    kept = int(cnt.item())
+    ms_api = cuda_ms(lambda: compact_frontier(flat))
     emit('frontier compaction (4e7 slots)', value=flat.numel() / (ms * 1e-3), unit='slots/s', ms=ms,
-         roofline=hbm(flat.numel() * (4 + 4 + 8), ms),
-         note='single pass (tile tickets + decoupled look-back); includes one .item() sync for the count')
+         roofline=hbm(flat.numel() * 4 + kept * 8, ms), kept=kept, ms_python_api_incl_count_sync=ms_api,
+         note='one pass over the ids (segment masks in shared memory, one exchange of segment '
+              'totals); algorithmic bytes = 4 per slot read + 8 per kept slot written')
     te = Time2Vec(100).to(DEV)
     dt = torch.randint(0, 2_600_000, (400_000,), generator=g, device=DEV)
     from tgm_b200 import _cabi

@@ -381,6 +381,50 @@ def test_frontier_compact(n):
     assert np.array_equal(idx[:len(want)].cpu().numpy(), want)
 
 
+@pytest.mark.parametrize('n,pad,offset', [(1_000_003, 0.37, 1), (5_000_001, 0.0, 3), (5_000_000, 1.0, 0),
+                                          (40_000_000, 0.02, 0), (250_000_000, 0.6, 0)])
+def test_frontier_compact_large_unaligned_and_multi_launch(n, pad, offset):
+    """Sizes past one CTA wave, inputs that do not start on a 16-byte boundary (scalar load
+    path), all kept / none kept, and an input longer than one launch's mask capacity (2.4e8
+    slots: consecutive launches carry the count); checked against torch.nonzero."""
+    g = torch.Generator(device=DEV).manual_seed(n)
+    buf = torch.randint(0, 1000, (n + offset,), generator=g, device=DEV, dtype=torch.int32)
+    nid = buf[offset:]
+    if pad >= 1.0:
+        nid.fill_(-1)
+    elif pad > 0:
+        nid[torch.rand(n, generator=g, device=DEV) < pad] = -1
+    idx = torch.empty(n, dtype=torch.int64, device=DEV)
+    cnt = torch.full((1,), -7, dtype=torch.int64, device=DEV)
+    _cabi.check(_cabi.lib.tgm_frontier_compact(nid.data_ptr(), n, idx.data_ptr(), cnt.data_ptr(),
+                                               stream()))
+    want = torch.nonzero(nid != -1).reshape(-1)
+    assert int(cnt.item()) == want.numel()
+    assert torch.equal(idx[:want.numel()], want)
+
+
+def test_frontier_compact_calls_on_two_streams_do_not_interfere():
+    """The calls share per-device status words: a call on another stream waits for the previous
+    launch (event), so interleaved calls on two streams stay exact."""
+    g = torch.Generator(device=DEV).manual_seed(5)
+    n = 3_000_000
+    nids = [torch.where(torch.rand(n, generator=g, device=DEV) < p, -1, 7).to(torch.int32)
+            for p in (0.2, 0.7)]
+    streams = [torch.cuda.Stream(device=DEV) for _ in nids]
+    idx = [torch.empty(n, dtype=torch.int64, device=DEV) for _ in nids]
+    cnt = [torch.zeros(1, dtype=torch.int64, device=DEV) for _ in nids]
+    torch.cuda.synchronize()
+    for _ in range(6):
+        for i, st in enumerate(streams):
+            _cabi.check(_cabi.lib.tgm_frontier_compact(nids[i].data_ptr(), n, idx[i].data_ptr(),
+                                                       cnt[i].data_ptr(), st.cuda_stream))
+    torch.cuda.synchronize()
+    for i in range(2):
+        want = torch.nonzero(nids[i] != -1).reshape(-1)
+        assert int(cnt[i].item()) == want.numel()
+        assert torch.equal(idx[i][:want.numel()], want)
+
+
 @pytest.mark.parametrize('S,k,D', [(1, 1, 1), (257, 20, 16), (100, 7, 5), (64, 20, 172)])
 def test_masked_mean_bit_exact(S, k, D):
     rng = np.random.default_rng(S)
@@ -708,6 +752,33 @@ def test_bulk_ring_update_matches_oracle(directed):
     want = oracle.query(seeds, tq, B)
     for g_, w_ in zip(got, want):
         assert np.array_equal(g_.cpu().numpy(), w_)
+
+
+@pytest.mark.parametrize('N,B,D,k', [(3000, 20, 16, 20), (3000, 20, 16, 7), (500, 32, 4, 32), (4000, 5, 8, 3)])
+def test_large_ring_queries_take_the_bulk_copy_kernel_and_equal_the_oracle(N, B, D, k):
+    """Queries of >= 4096 seeds run `ring_query_tma_kernel` (feature rows by bulk copies, windows
+    that wrap around the ring as two runs): equal to the C oracle and, bit for bit, to the same
+    seeds asked 1000 at a time (the warp-per-seed kernel).  Rings under-filled, full and wrapped;
+    padded seeds (-1 reads row N-1, recency.py:256); query times inside the stored range."""
+    src, dst, t, x = _random_stream(N + k, N, 60_000, 3000, D, hot=0.05)
+    ring, oracle = Ring(N, B, D), CRing(N, [B], D, False)
+    ring.update(dev(src, torch.int32), dev(dst, torch.int32), dev(t, torch.int64),
+                dev(x, torch.float32), False)
+    oracle.update(src, dst, t, x)
+    rng = np.random.default_rng(B * 1000 + k)
+    S = 20_000
+    seeds = rng.integers(0, N, S).astype(np.int32)
+    seeds[rng.random(S) < 0.05] = -1
+    tq = rng.integers(0, 3300, S).astype(np.int64)
+    d_seeds, d_tq = dev(seeds, torch.int32), dev(tq, torch.int64)
+    got = ring.query(d_seeds, d_tq, k)
+    want = oracle.query(seeds, tq, k)
+    for g_, w_ in zip(got, want):
+        assert np.array_equal(g_.cpu().numpy(), w_)
+    for lo in range(0, S, 1000):
+        part = ring.query(d_seeds[lo:lo + 1000], d_tq[lo:lo + 1000], k)
+        for g_, p_ in zip(got, part):
+            assert torch.equal(g_[lo:lo + 1000], p_)
 
 
 # ---- section 8f rows N2 / N3: dedup and negative hooks around the sampler ----------------------

@@ -24,6 +24,7 @@
 #include <new>
 
 #include "store.cuh"
+#include "tma.cuh"
 
 using namespace tgm;
 
@@ -790,46 +791,6 @@ csr_uniform_kernel(const Entry *__restrict__ entries, const int64_t *__restrict_
 #endif
 constexpr int kTmaStages = TGM_TMA_STAGES, kTmaLag = TGM_TMA_LAG, kTmaMaxStageBytes = 4096;
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return uint32_t(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes,
-                                         uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
-               "r"(src_smem), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-
 struct TmaMeta {  // what the retiring step needs to know about an in-flight seed
   float *dst;        // first float of the seed's out_x row block
   uint32_t nbytes;   // valid feature bytes (bulk-loaded); 0 = nothing was loaded
@@ -1577,6 +1538,11 @@ extern "C" int tgm_set_option(const char *name, int value) {
   if (std::strcmp(name, "dyg_fused_attn") == 0) {
     TGM_REQUIRE(value == 0 || value == 1, "tgm_set_option: dyg_fused_attn must be 0 or 1");
     tgm::g_dyg_fused_attn = value;
+    return TGM_OK;
+  }
+  if (std::strcmp(name, "tc_bn") == 0) {
+    TGM_REQUIRE(value >= 0 && value <= 200, "tgm_set_option: tc_bn must be in [0, 200]");
+    tgm::g_tc_bn = value;
     return TGM_OK;
   }
   if (std::strcmp(name, "tc_linear") == 0) {

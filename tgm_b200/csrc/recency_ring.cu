@@ -6,9 +6,11 @@
 // needed feature rows are read) and an update is two launches.
 #include <cub/cub.cuh>
 
+#include <algorithm>
 #include <new>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 using namespace tgm;
 
@@ -114,6 +116,155 @@ ring_query_kernel(const int32_t *__restrict__ ids, const int64_t *__restrict__ t
       }
     }
     __syncwarp();
+  }
+}
+
+// The same query with the feature block moved by bulk copies (the structure of
+// csr_sample_tma_kernel): a warp takes 32 consecutive seeds -- seed ids, query times and write
+// positions are loaded lane-parallel -- then walks them; lane j holds ring position j (oldest ..
+// newest) of the current seed, loaded a seed ahead; one ballot finds the right-most admissible
+// entry, shuffles route ids / times to the output columns, and lane 0 moves the k-window's
+// feature rows global -> shared -> global through a 4-stage ring (`cp.async.bulk` + mbarrier; the
+// window is one or, where it wraps around the ring, two contiguous runs of rows; padding comes
+// from a zeroed block), loads running two seeds ahead of stores.  Needs B <= 32, D % 4 == 0 and
+// k * D * 4 <= 4096.
+constexpr int kRqStages = 4, kRqLag = 2, kRqMaxStageBytes = 4096;
+struct RqMeta {
+  float *dst;
+  uint32_t nbytes;    // bulk-loaded feature bytes; 0 = nothing was loaded
+  uint32_t padbytes;  // zero bytes in front of them; bit 31 = mbarrier phase parity
+};
+
+__global__ void __launch_bounds__(kQueryThreads)
+ring_query_tma_kernel(const int32_t *__restrict__ ids, const int64_t *__restrict__ times,
+                      const float *__restrict__ feats, const int32_t *__restrict__ wpos, int N,
+                      int B, int D, const int32_t *__restrict__ seeds,
+                      const int64_t *__restrict__ tq, int64_t S, int k,
+                      int32_t *__restrict__ out_nid, int64_t *__restrict__ out_t,
+                      float *__restrict__ out_x, int stage_bytes) {
+  extern __shared__ __align__(128) unsigned char rq_smem[];
+  constexpr int W = kQueryThreads >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // layout: zero block | W * stages | W * stages mbarriers | W * stages metas
+  unsigned char *zero = rq_smem;
+  unsigned char *stages = zero + stage_bytes + size_t(warp) * kRqStages * stage_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(rq_smem + stage_bytes +
+                                                size_t(W) * kRqStages * stage_bytes) +
+                   warp * kRqStages;
+  RqMeta *meta = reinterpret_cast<RqMeta *>(rq_smem + stage_bytes +
+                                            size_t(W) * kRqStages * (stage_bytes + 8)) +
+                 warp * kRqStages;
+  for (int i = threadIdx.x * 4; i < stage_bytes; i += kQueryThreads * 4)
+    *reinterpret_cast<uint32_t *>(zero + i) = 0u;
+  if (lane == 0)
+    for (int s = 0; s < kRqStages; ++s) mbar_init(smem_u32(bars + s), 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const uint32_t zero_s = smem_u32(zero), stage_s = smem_u32(stages), bar_s = smem_u32(bars);
+  const uint32_t row_bytes = uint32_t(D) * 4u;
+
+  auto retire = [&](uint32_t q) {  // lane 0: seed number q of this warp has landed -> store it
+    const int st = int(q % kRqStages);
+    const RqMeta m = meta[st];
+    const uint32_t padbytes = m.padbytes & 0x7fffffffu;
+    if (m.nbytes) {
+      mbar_wait(bar_s + st * 8, m.padbytes >> 31);
+      bulk_s2g(reinterpret_cast<unsigned char *>(m.dst) + padbytes, stage_s + st * stage_bytes,
+               m.nbytes);
+    }
+    if (padbytes) bulk_s2g(m.dst, zero_s, padbytes);
+    bulk_commit();
+  };
+  // ring position `lane` of node v: {id, time}; id = padded for lanes >= B and out-of-range seeds
+  auto load_pos = [&](int v, int wp, int32_t &id, int64_t &tt) {
+    id = TGM_PADDED_NODE_ID;
+    tt = 0;
+    if (v >= 0 && lane < B) {
+      int slot = wp + lane;
+      if (slot >= B) slot -= B;
+      id = __ldg(ids + int64_t(v) * B + slot);
+      tt = __ldg(times + int64_t(v) * B + slot);
+    }
+  };
+
+  const int64_t nchunks = (S + 31) >> 5;
+  uint32_t g = 0, phases = 0;
+  for (int64_t ch = int64_t(blockIdx.x) * W + warp; ch < nchunks; ch += int64_t(gridDim.x) * W) {
+    const int64_t s_base = ch << 5, s = s_base + lane;
+    int my_v = -1, my_wp = 0;  // my_v < 0: all-padding row
+    int64_t my_q = 0;
+    if (s < S) {
+      int v = __ldg(seeds + s);
+      if (v < 0) v += N;  // torch negative indexing: the padded id -1 reads row N-1 (recency.py:256)
+      my_q = __ldg(tq + s);
+      if (v >= 0 && v < N) {
+        my_v = v;
+        my_wp = int(uint32_t(__ldg(wpos + v)) % uint32_t(B));
+      }
+    }
+    const int nseeds = S - s_base < 32 ? int(S - s_base) : 32;
+    int v = __shfl_sync(0xffffffffu, my_v, 0), wp = __shfl_sync(0xffffffffu, my_wp, 0);
+    int32_t cur_id;
+    int64_t cur_t;
+    load_pos(v, wp, cur_id, cur_t);
+    for (int i = 0; i < nseeds; ++i, ++g) {
+      const int64_t q = shfl_i64(my_q, i);
+      const int nxt = i + 1 < nseeds ? i + 1 : i;
+      const int v_n = __shfl_sync(0xffffffffu, my_v, nxt), wp_n = __shfl_sync(0xffffffffu, my_wp, nxt);
+      int32_t ahead_id;
+      int64_t ahead_t;
+      load_pos(v_n, wp_n, ahead_id, ahead_t);
+      const unsigned m = __ballot_sync(0xffffffffu, cur_id != TGM_PADDED_NODE_ID && cur_t < q);
+      const int last = m ? 31 - __clz(m) : -1;  // (:267-281)
+      const int nvalid = last + 1 < k ? last + 1 : k;
+      const int first = last + 1 - nvalid, pad = k - nvalid;
+      const int srcl = (first + lane - pad) & 31;
+      const int32_t id = __shfl_sync(0xffffffffu, cur_id, srcl);
+      const int64_t tt = shfl_i64(cur_t, srcl);
+      const int64_t sg = s_base + i;
+      if (lane < k) {
+        const bool ok = lane >= pad;
+        out_nid[sg * k + lane] = ok ? id : TGM_PADDED_NODE_ID;
+        out_t[sg * k + lane] = ok ? tt : 0;
+      }
+      if (lane == 0) {
+        const int st = int(g % kRqStages);
+        bulk_wait_read<kRqStages - kRqLag - 1>();  // the store that last read this stage is done
+        RqMeta mt;
+        mt.dst = out_x + sg * int64_t(k) * D;
+        mt.nbytes = uint32_t(nvalid) * row_bytes;
+        mt.padbytes = uint32_t(pad) * row_bytes;
+        if (mt.nbytes) {
+          mt.padbytes |= ((phases >> st) & 1u) << 31;
+          phases ^= 1u << st;
+        }
+        meta[st] = mt;
+        if (mt.nbytes) {
+          // unrolled positions first .. last live in slots (wp + p) % B: one run, or two when
+          // the window wraps around the end of the ring
+          int s0 = wp + first;
+          if (s0 >= B) s0 -= B;
+          const int len1 = nvalid < B - s0 ? nvalid : B - s0;
+          const float *rowp = feats + int64_t(v) * B * D;
+          mbar_expect_tx(bar_s + st * 8, mt.nbytes);
+          bulk_g2s(stage_s + st * stage_bytes, rowp + int64_t(s0) * D, uint32_t(len1) * row_bytes,
+                   bar_s + st * 8);
+          if (len1 < nvalid)
+            bulk_g2s(stage_s + st * stage_bytes + uint32_t(len1) * row_bytes, rowp,
+                     uint32_t(nvalid - len1) * row_bytes, bar_s + st * 8);
+        }
+        if (g >= uint32_t(kRqLag)) retire(g - kRqLag);
+      }
+      cur_id = ahead_id;
+      cur_t = ahead_t;
+      v = v_n;
+      wp = wp_n;
+    }
+  }
+  if (lane == 0) {  // drain
+    for (uint32_t q = g >= uint32_t(kRqLag) ? g - kRqLag : 0; q < g; ++q) retire(q);
+    bulk_wait_read<0>();
   }
 }
 
@@ -373,6 +524,22 @@ extern "C" int tgm_recency_query(const tgm_recency *h, const int32_t *seeds, con
   TGM_REQUIRE(h->D == 0 || out_x != nullptr, "tgm_recency_query: out_x is NULL but D > 0");
   DeviceGuard g(h->device);
   const int wpb = kQueryThreads / 32;
+  // feature block moved by bulk copies where the shapes allow (see ring_query_tma_kernel)
+  if (h->D > 0 && h->D % 4 == 0 && h->B <= 32 && k * h->D * 4 <= kRqMaxStageBytes &&
+      aligned16(h->feats) && aligned16(out_x) && S >= 4096) {
+    const int stage_bytes = k * h->D * 4;
+    const size_t smem = size_t(stage_bytes) + size_t(wpb) * kRqStages * (size_t(stage_bytes) + 8 + 16);
+    if (smem > 48 * 1024)
+      TGM_CUDA(cudaFuncSetAttribute(ring_query_tma_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const int per_sm = int(std::max<size_t>(1, std::min<size_t>(6, (220 * 1024) / (smem + 1024))));
+    ring_query_tma_kernel<<<grid_for((S + 31) / 32, wpb, per_sm), kQueryThreads, smem,
+                            as_stream(stream)>>>(h->ids, h->times, h->feats, h->wpos, h->N, h->B,
+                                                 h->D, seeds, tq, S, k, out_nid, out_t, out_x,
+                                                 stage_bytes);
+    TGM_LAUNCH_CHECK();
+    return TGM_OK;
+  }
   const size_t smem = size_t(wpb) * size_t(k) * sizeof(int32_t);
   TGM_REQUIRE(smem <= 48 * 1024, "tgm_recency_query: k too large");
   const int grid = grid_for(S, wpb, 8);

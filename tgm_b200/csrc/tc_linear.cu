@@ -409,6 +409,7 @@ namespace tgm {
 // the GELU-fused FFN linear (158 vs 177 us on 25600x800x200); the other three DyGFormer shapes
 // stay on the collective (113 / 54 / 167 us here vs 86 / 42 / 115).
 int g_tc_linear = 2;
+int g_tc_bn = 0;  // tgm_set_option("tc_bn", v): probe switch, v > 0 forces the column tile width
 
 // 1 = computed, 0 = shape / alignment not supported (caller falls back), < 0 = error
 int tc3_linear(int64_t S, int N, int K, const float *A, const float *W, const float *bias,
@@ -430,6 +431,7 @@ int tc3_linear(int64_t S, int N, int K, const float *A, const float *W, const fl
   }
   int BN = ((N + n_tiles - 1) / n_tiles + 3) & ~3;
   if (BN > 200) BN = 200;
+  if (g_tc_bn > 0) BN = std::min(200, (g_tc_bn + 3) & ~3);
   static bool configured = false;
   if (!configured) {
     TGM_CUDA(cudaFuncSetAttribute(tc3_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
