@@ -87,6 +87,69 @@ time2vec_kernel(const int64_t *__restrict__ dt, int64_t n, const float *__restri
   }
 }
 
+
+// The same values with every lane busy and one 128-bit store per lane (d % 4 == 0): the output
+// is walked as a flat array of float4 -- element e = (row e / (d/4), columns 4 (e % (d/4)) ..+3)
+// -- so a warp writes 512 contiguous bytes whatever d is (d = 100: the row kernel above leaves
+// 28 of 32 lanes idle in its fourth column tile and issues four 128-byte stores per 400-byte
+// row).  (row, column group) advance by a constant stride without a division; w and b sit in
+// shared memory as float4.  The reduced-range cosine is used when |x| * max|w| + max|b| < 2^22,
+// checked per element with one compare; the rare rest goes through t2v_cos.
+constexpr int kT2vFlatMaxD = 2048;
+__device__ __noinline__ float4 t2v_cos4_general(float a0, float a1, float a2, float a3) {
+  return make_float4(t2v_cos(a0), t2v_cos(a1), t2v_cos(a2), t2v_cos(a3));
+}
+__global__ void __launch_bounds__(256)
+time2vec_flat4_kernel(const int64_t *__restrict__ dt, int64_t n, const float *__restrict__ w,
+                      const float *__restrict__ b, int d4, float4 *__restrict__ out) {
+  __shared__ float4 s_w[kT2vFlatMaxD / 4], s_b[kT2vFlatMaxD / 4];
+  __shared__ float s_red[2][8];
+  float wm = 0.f, bm = 0.f;
+  for (int c = threadIdx.x; c < d4; c += blockDim.x) {
+    const float4 wv = __ldg(reinterpret_cast<const float4 *>(w) + c);
+    const float4 bv = __ldg(reinterpret_cast<const float4 *>(b) + c);
+    s_w[c] = wv, s_b[c] = bv;
+    wm = fmaxf(wm, fmaxf(fmaxf(fabsf(wv.x), fabsf(wv.y)), fmaxf(fabsf(wv.z), fabsf(wv.w))));
+    bm = fmaxf(bm, fmaxf(fmaxf(fabsf(bv.x), fabsf(bv.y)), fmaxf(fabsf(bv.z), fabsf(bv.w))));
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+  }
+  if ((threadIdx.x & 31) == 0) s_red[0][threadIdx.x >> 5] = wm, s_red[1][threadIdx.x >> 5] = bm;
+  __syncthreads();
+  wm = bm = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) wm = fmaxf(wm, s_red[0][i]), bm = fmaxf(bm, s_red[1][i]);
+  // |x| <= xlim  =>  |fma(x, w, b)| < 2^22 for every column (a NaN / zero wm leaves xlim non-finite
+  // or negative: the comparison then sends everything to the general path or the fast one, both exact)
+  const float xlim = wm > 0.f ? (4194304.f - bm) / wm * 0.999f : 3.0e38f;
+
+  const int64_t total = n * d4;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const int64_t srow = stride / d4;
+  const int scol = int(stride - srow * d4);
+  int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  int64_t row = e / d4;
+  int c = int(e - row * d4);
+  for (; e < total; e += stride) {
+    const float x = float(__ldg(dt + row));
+    const float4 wv = s_w[c], bv = s_b[c];
+    const float a0 = __fmaf_rn(x, wv.x, bv.x), a1 = __fmaf_rn(x, wv.y, bv.y),
+                a2 = __fmaf_rn(x, wv.z, bv.z), a3 = __fmaf_rn(x, wv.w, bv.w);
+    float4 y;
+    if (fabsf(x) <= xlim)
+      y = make_float4(t2v_cos_fast(a0), t2v_cos_fast(a1), t2v_cos_fast(a2), t2v_cos_fast(a3));
+    else
+      y = t2v_cos4_general(a0, a1, a2, a3);
+    out[e] = y;
+    row += srow;
+    c += scol;
+    if (c >= d4) c -= d4, ++row;
+  }
+}
+
 }  // namespace
 
 extern "C" int tgm_masked_mean(const float *z, const int32_t *nid, int64_t S, int32_t k,
@@ -109,7 +172,11 @@ extern "C" int tgm_time2vec(const int64_t *dt, int64_t n, const float *w, const 
   TGM_REQUIRE(n >= 0 && d >= 1, "tgm_time2vec: bad sizes");
   if (n == 0) return TGM_OK;
   TGM_REQUIRE(dt && w && b && out, "tgm_time2vec: NULL array argument");
-  time2vec_kernel<<<grid_for(n, 8, 8), 256, 0, as_stream(stream)>>>(dt, n, w, b, d, out);
+  if (d % 4 == 0 && d <= kT2vFlatMaxD && aligned16(w) && aligned16(b) && aligned16(out))
+    time2vec_flat4_kernel<<<grid_for(n * (d / 4), 256, 8), 256, 0, as_stream(stream)>>>(
+        dt, n, w, b, d / 4, reinterpret_cast<float4 *>(out));
+  else
+    time2vec_kernel<<<grid_for(n, 8, 8), 256, 0, as_stream(stream)>>>(dt, n, w, b, d, out);
   TGM_LAUNCH_CHECK();
   return TGM_OK;
 }

@@ -179,28 +179,25 @@ frontier_compact_kernel(const int32_t *__restrict__ nid, int64_t first, int64_t 
   }
   __syncthreads();
 
-  // ---- pass 2: mask words -> indices ----
-  int64_t run = s_base + woff;
+  // ---- pass 2: mask words -> indices.  Four words per (broadcast) 128-bit shared-memory read;
+  // lane l owns slot l of every word; the running output offset is a warp-uniform popcount sum,
+  // so no shuffle sits between a word and its store ----
+  int64_t *o = out_idx + s_base + woff;
+  const uint4 *my4 = reinterpret_cast<const uint4 *>(my);  // words % 4 == 0: 16-byte aligned
   const unsigned below = (1u << lane) - 1u;
-  for (int w0 = 0; w0 < words; w0 += 32) {
-    const unsigned word = (w0 + lane < words) ? my[w0 + lane] : 0u;
-    const int pc = __popc(word);
-    int incl = pc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int up = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += up;
-    }
-    const int excl = incl - pc;
-    const int nw = min(32, words - w0);
-#pragma unroll 8
-    for (int j = 0; j < nw; ++j) {
-      const unsigned m = __shfl_sync(0xffffffffu, word, j);
-      if (m == 0u) continue;  // warp-uniform: 32 padded slots in a row
-      const int off = __shfl_sync(0xffffffffu, excl, j);
-      if (m & (1u << lane)) out_idx[run + off + __popc(m & below)] = a + int64_t(w0 + j) * 32 + lane;
-    }
-    run += __shfl_sync(0xffffffffu, incl, 31);
+  int64_t val = a + lane;
+  int r = 0;
+  auto emit = [&](unsigned m, int64_t v) {
+    if ((m >> lane) & 1u) o[r + __popc(m & below)] = v;
+    r += __popc(m);
+  };
+#pragma unroll 2
+  for (int g = 0; g < (words >> 2); ++g, val += 128) {
+    const uint4 m = my4[g];
+    emit(m.x, val);
+    emit(m.y, val + 32);
+    emit(m.z, val + 64);
+    emit(m.w, val + 96);
   }
 }
 
