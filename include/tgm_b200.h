@@ -296,7 +296,10 @@ int tgm_negatives_window(uint64_t seed, uint64_t offset, int64_t low, int64_t hi
  * Frontier compaction (hop h+1 seeds = flatten(hop h), recency.py:141-143; the non-padded
  * subset is also what DeduplicationHook keeps, tgm/hooks/dedup.py:44-48).
  * Writes the indices i with nid[i] != -1 in increasing order to out_idx (capacity n) and their
- * number to *out_count (device int64). */
+ * number to *out_count (device int64).  One pass over the ids (4 bytes read per slot, 8 written
+ * per kept slot).  Stream-ordered; the launches of a device share a small status area, so a call
+ * on another stream first waits (cudaStreamWaitEvent) for the previous call's launch.  Inputs of
+ * more than ~2.4e8 slots are handled by consecutive launches inside the call. */
 int tgm_frontier_compact(const int32_t *nid, int64_t n, int64_t *out_idx, int64_t *out_count,
                          tgm_stream stream);
 

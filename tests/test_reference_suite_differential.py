@@ -55,3 +55,34 @@ def test_reference_unit_tests_run_against_the_drop_in(path, tmp_path):
     m = re.search(r'(\d+) passed', out)
     assert m and int(m.group(1)) >= CASES[path], out[-3000:]
     assert 'error' not in out.splitlines()[-1], out[-3000:]
+
+
+@pytest.mark.skipif(not reference_available(), reason='reference tree not present')
+def test_reference_storage_contract_suite_runs_over_the_registered_backend(tmp_path):
+    """The plug-in itself (tgm_b200/reference_plugin.py): the UNMODIFIED
+    reference package with this repo's store registered in ITS `DGStorageBackends`, and the
+    reference's own storage contract suite (test/unit/test_core/test_storage_impl.py, parametrised
+    over every registered backend, :23-25) run over both.  On this CPU-only box the backend is
+    metadata-only: every test that touches edge data must refuse with the no-CPU-fallback error and
+    nothing else; the others -- bounds, counts, node sets, node events / labels, sparse dynamic
+    node features and labels, static features, dims, on the reference's own DGData objects -- pass."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CPU-only differential check')
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', PYTHONPATH=ROOT, COLUMNS='400')
+    proc = subprocess.run(
+        [sys.executable, '-m', 'pytest', '-p', 'tests._reference_backend_plugin', '-p',
+         'no:cacheprovider', '-q', '-rfp', '--color=no',
+         os.path.join(REFERENCE_ROOT, 'test/unit/test_core/test_storage_impl.py')],
+        cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    out = proc.stdout
+    failed = re.findall(r'^FAILED (\S+) - (.*)$', out, flags=re.M)
+    passed = re.findall(r'^PASSED (\S+)', out, flags=re.M)
+    assert failed and all('B200Storage' in name and 'no CPU fallback' in why for name, why in failed), \
+        out[-3000:]
+    ours = [n for n in passed if 'B200Storage' in n]
+    theirs = [n for n in passed if 'DGStorageArrayBackend' in n]
+    # every parametrised case ran over both backends: the reference's passes all of its own, ours
+    # passes the 27 that need no edge data and refuses the other 7
+    assert len(theirs) >= 34 and len(ours) + len(failed) == len(theirs), out[-3000:]
+    assert len(ours) >= 27, out[-3000:]
