@@ -86,3 +86,46 @@ def test_reference_storage_contract_suite_runs_over_the_registered_backend(tmp_p
     # passes the 27 that need no edge data and refuses the other 7
     assert len(theirs) >= 34 and len(ours) + len(failed) == len(theirs), out[-3000:]
     assert len(ours) >= 27, out[-3000:]
+
+
+_HOOK_PROBE = r"""
+import sys
+sys.path.insert(0, {root!r})
+from tests.golden._ref_shim import import_reference
+import_reference()
+from tgm.hooks import HookManager, RandomNegativeEdgeSamplerHook as RefNeg, DeduplicationHook as RefDedup
+from tgm.hooks.base import DGHook
+from tgm_b200 import RecencyNeighborHook, NeighborSamplerHook
+from tgm_b200.hooks import RandomNegativeEdgeSamplerHook, DeduplicationHook
+
+recency = RecencyNeighborHook(num_nodes=100, num_nbrs=[5, 5],
+                              seed_nodes_keys=['edge_src', 'edge_dst', 'neg'],
+                              seed_times_keys=['edge_time', 'edge_time', 'neg_time'])
+uniform = NeighborSamplerHook(num_nbrs=[3], seed_nodes_keys=['edge_src'], seed_times_keys=['edge_time'])
+ours = [recency, uniform, RandomNegativeEdgeSamplerHook(low=0, high=9), DeduplicationHook()]
+assert all(isinstance(h, DGHook) for h in ours)          # hooks/base.py:11-24, runtime-checkable
+hm = HookManager(keys=['train', 'val'])                   # the REFERENCE's manager
+hm.register('train', recency)                             # registered FIRST ...
+hm.register('train', RefNeg(low=0, high=99))              # ... the reference's own producer of `neg`
+hm.register('train', RefDedup())
+hm.register('val', uniform)
+hm.register_shared(ours[2])
+hm.resolve_hooks()
+order = [type(h).__module__.split('.')[0] + ':' + type(h).__name__ for h in hm._key_to_hooks['train']]
+print('ORDER', order)
+assert order.index('tgm:RandomNegativeEdgeSamplerHook') < order.index('tgm_b200:RecencyNeighborHook')
+hm.reset_state()
+print('OK')
+"""
+
+
+@pytest.mark.skipif(not reference_available(), reason='reference tree not present')
+def test_reference_hook_manager_accepts_and_orders_the_drop_in_hooks(tmp_path):
+    """The hook face of the boundary from the reference's side: the UNMODIFIED reference's
+    `HookManager` (hook_manager.py:373-377 protocol check, :390-430 dependency sort) takes this
+    package's hook objects next to its own, puts the reference's negative sampler before this
+    package's neighbour sampler (which requires `neg`), and resets them."""
+    proc = subprocess.run([sys.executable, '-c', _HOOK_PROBE.format(root=ROOT)], cwd=str(tmp_path),
+                          capture_output=True, text=True, timeout=300,
+                          env=dict(os.environ, PYTHONDONTWRITEBYTECODE='1'))
+    assert proc.returncode == 0 and proc.stdout.strip().endswith('OK'), proc.stdout[-2000:] + proc.stderr[-3000:]
