@@ -190,6 +190,15 @@ int tgm_csr_export_ring(const tgm_csr *, int64_t e_cut, tgm_recency *ring, tgm_s
 int tgm_csr_sample_uniform(const tgm_csr *, const int32_t *seeds, int64_t S, int64_t e_lo,
                            int64_t e_hi, int32_t k, uint64_t rng_seed, int32_t *out_nid,
                            int64_t *out_t, float *out_x, tgm_stream stream);
+/* The same with the candidate range given as the slice's own closed time interval
+ * [t_lo, t_hi] (has_lo / has_hi = 0: unbounded on that side) instead of edge indices: for a
+ * time-sorted stream these are the same candidates (e < upper_bound(t, T) <=> t[e] <= T), and the
+ * hook's per-batch cut `end_time = min(batch time) - 1` (uniform.py:125) needs no slice -> index
+ * resolution (tgm_store_bounds) and no host round trip first. */
+int tgm_csr_sample_uniform_time(const tgm_csr *, const int32_t *seeds, int64_t S, int64_t t_lo,
+                                int has_lo, int64_t t_hi, int has_hi, int32_t k,
+                                uint64_t rng_seed, int32_t *out_nid, int64_t *out_t, float *out_x,
+                                tgm_stream stream);
 /* Reference-exact sub-sampling.  The reference keeps random.sample(candidates, k) -- CPython's
  * global generator -- per unique seed node with more than k candidates, visiting the unique nodes
  * in ascending order (array_backend.py:118, :147-153).  That draw depends only on the candidate

@@ -125,3 +125,42 @@ def test_get_nbrs_deterministic_cases_vs_oracle():
             assert np.array_equal(nt.cpu().numpy()[exact], w_nt[exact])
             assert np.array_equal(nx.cpu().numpy()[exact], w_nx[exact])
             assert bool((nid[torch.from_numpy(~exact)] != -1).all())  # over-full seeds: k slots
+
+
+@pytest.mark.parametrize('directed', [False, True])
+def test_time_bounded_slices_equal_the_index_resolved_call(directed):
+    """get_nbrs with a slice bounded by times only goes to the kernel as it is
+    (tgm_csr_sample_uniform_time: candidates by entry time); the same slice resolved to edge
+    indices first (tgm_store_bounds -> tgm_csr_sample_uniform) must give identical rows -- also
+    beyond k candidates, the draw being keyed by (seed, node).  Ties on the bounds, empty
+    intervals, unbounded sides; ids outside the graph give padding rows."""
+    from tgm_b200 import _cabi
+    from tgm_b200.sampler import full_history_neighbors
+    rng = np.random.default_rng(17)
+    N, E, T, D, k = 300, 20_000, 400, 8, 6
+    src, dst = rng.integers(0, N, E), rng.integers(0, N, E)
+    t = np.sort(rng.integers(0, T, E))
+    x = rng.standard_normal((E, D)).astype(np.float32)
+    dg = _graph(src, dst, t, x)
+    st = dg._storage
+    seeds = torch.from_numpy(np.concatenate([rng.integers(0, N, 500), [-1, N + 5]]).astype(np.int32)).to(DEV)
+    for t_lo, t_hi in [(None, None), (None, 123), (57, None), (57, 57), (100, 99), (0, T), (-5, 3),
+                       (T - 1, None), (None, -1)]:
+        sl = DGSliceTracker(start_time=t_lo, end_time=t_hi)
+        got = full_history_neighbors(st, seeds, k, sl, directed, rng_seed=99)
+        lo, hi = st.edge_range(sl)
+        csr = st._node_cache[('uniform_csr', directed)]
+        S = seeds.numel()
+        nid = torch.empty((S, k), dtype=torch.int32, device=DEV)
+        nt = torch.empty((S, k), dtype=torch.int64, device=DEV)
+        nx = torch.empty((S, k, D), dtype=torch.float32, device=DEV)
+        _cabi.check(_cabi.lib.tgm_csr_sample_uniform(
+            csr.handle, seeds.data_ptr(), S, lo, max(lo, hi), k, 99, nid.data_ptr(), nt.data_ptr(),
+            nx.data_ptr(), _cabi.current_stream(torch.device(DEV))))
+        for g_, w_ in zip(got, (nid, nt, nx)):
+            assert torch.equal(g_, w_), (t_lo, t_hi)
+        valid = got[0] != -1
+        if t_lo is not None:
+            assert bool((got[1][valid] >= t_lo).all())
+        if t_hi is not None:
+            assert bool((got[1][valid] <= t_hi).all())

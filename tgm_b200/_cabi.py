@@ -74,6 +74,9 @@ SIGNATURES = {
     'tgm_csr_export_ring': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     'tgm_csr_sample_uniform': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32,
                                        c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'tgm_csr_sample_uniform_time': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64,
+                                            c_int, c_int32, c_uint64, c_void_p, c_void_p, c_void_p,
+                                            c_void_p]),
     'tgm_csr_candidate_counts': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
                                          c_void_p]),
     'tgm_csr_gather_picks': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32,

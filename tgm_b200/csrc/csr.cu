@@ -716,6 +716,20 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 
 constexpr int kUniformThreads = 256;
 
+// first index in [lo, hi) whose entry has time >= t (a node's list is in edge order = time order)
+__device__ __forceinline__ int64_t lower_bound_time(const Entry *__restrict__ entries, int64_t lo,
+                                                    int64_t hi, int64_t t) {
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (entries[mid].t < t) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// BY_TIME: the candidate range is given as a closed time interval [e_lo, e_hi] instead of the edge
+// index range [e_lo, e_hi) -- the same candidates for a time-sorted stream (e < upper_bound(t, T)
+// <=> t[e] <= T), without resolving the slice to edge indices first
+template <bool BY_TIME>
 __global__ void __launch_bounds__(kUniformThreads)
 csr_uniform_kernel(const Entry *__restrict__ entries, const int64_t *__restrict__ rowptr,
                    const float *__restrict__ x, int32_t N, int D, const int32_t *__restrict__ seeds,
@@ -730,8 +744,13 @@ csr_uniform_kernel(const Entry *__restrict__ entries, const int64_t *__restrict_
     int64_t lo = 0, cnt = 0;
     if (v >= 0 && v < N) {
       const int64_t r0 = rowptr[v], r1 = rowptr[v + 1];
-      lo = lower_bound_eid(entries, r0, r1, e_lo);
-      cnt = lower_bound_eid(entries, lo, r1, e_hi) - lo;
+      if (BY_TIME) {
+        lo = lower_bound_time(entries, r0, r1, e_lo);
+        cnt = (e_hi == INT64_MAX ? r1 : lower_bound_time(entries, lo, r1, e_hi + 1)) - lo;
+      } else {
+        lo = lower_bound_eid(entries, r0, r1, e_lo);
+        cnt = lower_bound_eid(entries, lo, r1, e_hi) - lo;
+      }
     }
     if (cnt <= k) {
       for (int c = lane; c < k; c += 32) pick[c] = c < cnt ? lo + c : -1;
@@ -1510,9 +1529,31 @@ extern "C" int tgm_csr_sample_uniform(const tgm_csr *c, const int32_t *seeds, in
   const size_t smem = size_t(wpb) * size_t(k) * sizeof(int64_t);
   TGM_REQUIRE(smem <= 48 * 1024, "tgm_csr_sample_uniform: k too large");
   DeviceGuard g(c->device);
-  csr_uniform_kernel<<<grid_for(S, wpb, 8), kUniformThreads, smem, as_stream(stream)>>>(
+  csr_uniform_kernel<false><<<grid_for(S, wpb, 8), kUniformThreads, smem, as_stream(stream)>>>(
       c->entries, c->rowptr, c->store->x, c->N, c->D, seeds, S, e_lo, e_hi, k, rng_seed, out_nid,
       out_t, out_x);
+  TGM_LAUNCH_CHECK();
+  return TGM_OK;
+}
+
+extern "C" int tgm_csr_sample_uniform_time(const tgm_csr *c, const int32_t *seeds, int64_t S,
+                                           int64_t t_lo, int has_lo, int64_t t_hi, int has_hi,
+                                           int32_t k, uint64_t rng_seed, int32_t *out_nid,
+                                           int64_t *out_t, float *out_x, tgm_stream stream) {
+  TGM_REQUIRE(c != nullptr, "tgm_csr_sample_uniform_time: csr is NULL");
+  TGM_REQUIRE(c->bs == 1 && c->e_start == 0,
+              "tgm_csr_sample_uniform_time: the adjacency must be built with batch_size 1, e_start 0");
+  TGM_REQUIRE(S >= 0 && k >= 1, "tgm_csr_sample_uniform_time: bad sizes");
+  if (S == 0) return TGM_OK;
+  TGM_REQUIRE(seeds && out_nid && out_t, "tgm_csr_sample_uniform_time: NULL array argument");
+  TGM_REQUIRE(c->D == 0 || out_x != nullptr, "tgm_csr_sample_uniform_time: out_x is NULL but D > 0");
+  const int wpb = kUniformThreads / 32;
+  const size_t smem = size_t(wpb) * size_t(k) * sizeof(int64_t);
+  TGM_REQUIRE(smem <= 48 * 1024, "tgm_csr_sample_uniform_time: k too large");
+  DeviceGuard g(c->device);
+  csr_uniform_kernel<true><<<grid_for(S, wpb, 8), kUniformThreads, smem, as_stream(stream)>>>(
+      c->entries, c->rowptr, c->store->x, c->N, c->D, seeds, S, has_lo ? t_lo : INT64_MIN,
+      has_hi ? t_hi : INT64_MAX, k, rng_seed, out_nid, out_t, out_x);
   TGM_LAUNCH_CHECK();
   return TGM_OK;
 }

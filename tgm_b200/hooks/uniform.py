@@ -88,7 +88,7 @@ class NeighborSamplerHook(StatelessHook, SeedableHook):
                 nts.append(torch.empty(0, dtype=torch.int64))
                 nxs.append(torch.empty(0, dg.edge_x_dim).float())
         else:
-            cut = DGSliceTracker(end_time=int(batch.edge_time.min()) - 1)  # uniform.py:125
+            cut = DGSliceTracker(end_time=self._min_edge_time(dg, batch) - 1)  # uniform.py:125
             for hop, k in enumerate(self._num_nbrs):
                 if hop > 0:
                     seed_nodes = nids[hop - 1].flatten()
@@ -108,6 +108,19 @@ class NeighborSamplerHook(StatelessHook, SeedableHook):
         self.add_batch_attribute(batch, 'nbr_edge_x', nxs)
         self.add_batch_attribute(batch, 'seed_node_nbr_mask', seed_mask)
         return batch
+
+    @staticmethod
+    def _min_edge_time(dg, batch) -> int:
+        """`batch.edge_time.min()` without the device round trip when the batch still carries the
+        loader's own views of a device store: the stream is time-sorted, so the minimum is the
+        first row's time, read from the store's host copy of the edge times."""
+        slab = getattr(batch, '_slab', None)
+        store = getattr(dg, '_storage', None)
+        if slab is not None and slab[0] is store and batch.edge_time is slab[5] and slab[2] > slab[1]:
+            host_t = getattr(store, '_edge_time_host', None)
+            if host_t is not None and host_t.numel() > slab[1]:
+                return int(host_t[slab[1]])
+        return int(batch.edge_time.min())
 
     def _get_seed_tensors(self, batch) -> Tuple[Tensor, Tensor, Dict[str, Tensor]]:
         """uniform.py:144-210 (no upper bound on ids: `_num_nodes = inf`, :184-185); the bounds

@@ -342,7 +342,11 @@ def full_history_neighbors(storage, seed_nodes: Tensor, num_nbrs: int, slice, di
     csr = cache[key]
     if rng_seed is None and not reference_rng:  # a fresh draw per call, reproducible under torch.manual_seed
         rng_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-    lo, hi = storage.edge_range(slice)
+    # a slice bounded by times only (what the hook passes: end_time = min(batch time) - 1) is handed
+    # to the kernel as it is; only index-bounded slices are resolved to an edge range first
+    by_time = (not reference_rng and getattr(slice, 'start_idx', None) is None
+               and getattr(slice, 'end_idx', None) is None)
+    lo, hi = (0, 0) if by_time else storage.edge_range(slice)
     dev = storage.device
     seeds = seed_nodes.to(device=dev, dtype=torch.int32).contiguous()
     S, D = seeds.numel(), csr.D
@@ -363,6 +367,13 @@ def full_history_neighbors(storage, seed_nodes: Tensor, num_nbrs: int, slice, di
             csr.handle, seeds.data_ptr(), S, lo, hi, int(num_nbrs), picks.data_ptr(),
             nid.data_ptr(), nt.data_ptr(), nx.data_ptr() if D else None,
             _cabi.current_stream(dev)))
+        return nid, nt, nx
+    if by_time:
+        t_lo, t_hi = slice.start_time, slice.end_time
+        _cabi.check(_cabi.lib.tgm_csr_sample_uniform_time(
+            csr.handle, seeds.data_ptr(), S, int(t_lo or 0), t_lo is not None, int(t_hi or 0),
+            t_hi is not None, int(num_nbrs), int(rng_seed), nid.data_ptr(), nt.data_ptr(),
+            nx.data_ptr() if D else None, _cabi.current_stream(dev)))
         return nid, nt, nx
     _cabi.check(_cabi.lib.tgm_csr_sample_uniform(
         csr.handle, seeds.data_ptr(), S, lo, hi, int(num_nbrs), int(rng_seed), nid.data_ptr(),
