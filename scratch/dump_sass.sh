@@ -9,3 +9,5 @@ dump() {  # $1 = substring of the mangled name, $2 = output file
 dump 'csr_sample_tma_kernelILb1E' profiles/r2_sass_csr_sample_tma_kernel.txt
 dump 'tc3_linear_kernel' profiles/r2_sass_tc3_linear_kernel.txt
 dump 'attn_warp_kernelILi1ELi6ELi4ELb1E' profiles/r2_sass_attn_warp_kernel.txt
+dump 'ring_query_tma_kernel' profiles/r2_sass_ring_query_tma_kernel.txt
+dump 'frontier_compact_kernelILb1E' profiles/r2_sass_frontier_compact_kernel.txt
