@@ -79,7 +79,7 @@ def test_folded_chain_matches_the_oracle_and_the_unfolded_chain(shape, pad_mode)
                 outs[(folded, tc)] = att.forward_fused(te, *args).cpu().numpy()
     finally:
         _set(b'attn_folded', 1)
-        _set(b'tc_linear', 2)
+        _set(b'tc_linear', 1)  # the default
     for key, got in outs.items():
         assert np.isfinite(got).all(), key
         assert np.abs(got - want).max() <= TOL, (key, float(np.abs(got - want).max()))
@@ -142,7 +142,7 @@ def test_merge_layer_on_both_gemm_engines(dims):
                 got = m(x1, x2)
             assert float((got.double() - want).abs().max()) <= TOL, tc
     finally:
-        _set(b'tc_linear', 2)
+        _set(b'tc_linear', 1)  # the default
 
 
 @pytest.mark.parametrize('L,lazy', [(1, False), (2, False), (2, True), (3, False), (3, True)])

@@ -340,8 +340,9 @@ def test_dygformer_tensor_core_gemm_matches_cublas_path_and_oracle():
             _cabi.check(_cabi.lib.tgm_set_option(b'tc_linear', 0))
             outs[flag] = [v.detach().cpu().numpy() for v in m(*args)]
         _cabi.check(_cabi.lib.tgm_set_option(b'gemm_fastf32', 1))
-        # every token linear on the hand-written tcgen05 kernel (3xTF32), and the default mix
-        for mode, key in ((1, 'tc_all'), (2, 'tc_default')):
+        # every token linear on the hand-written tcgen05 kernel (3xTF32: the default), and the mix
+        # with the CUTLASS collective
+        for mode, key in ((1, 'tc_all'), (2, 'tc_mixed')):
             _cabi.check(_cabi.lib.tgm_set_option(b'tc_linear', mode))
             outs[key] = [v.detach().cpu().numpy() for v in m(*args)]
         # the per-head attention as batched cuBLAS products instead of the fused on-chip kernel
@@ -349,7 +350,7 @@ def test_dygformer_tensor_core_gemm_matches_cublas_path_and_oracle():
         outs['unfused_attn'] = [v.detach().cpu().numpy() for v in m(*args)]
     finally:
         _cabi.check(_cabi.lib.tgm_set_option(b'gemm_fastf32', 1))
-        _cabi.check(_cabi.lib.tgm_set_option(b'tc_linear', 2))
+        _cabi.check(_cabi.lib.tgm_set_option(b'tc_linear', 1))  # the default
         _cabi.check(_cabi.lib.tgm_set_option(b'dyg_fused_attn', 1))
     p = {k_: v.detach().cpu().numpy() for k_, v in m.state_dict().items()}
     want = nn_oracle.dygformer_forward(p, 1, 2, 2, node_x, ei, t, nbrs, nt, ef)

@@ -62,7 +62,7 @@ int small_gemm_nt(int64_t M, int N, int K, const float *A, int lda, int64_t stri
                   int ldw, int64_t strideW, const float *bias, int act, float *C, int ldc,
                   int64_t strideC, int batch, cudaStream_t st);
 extern int g_tc_bn;      // probe switch: forced column tile width of tc3_linear (0 = automatic)
-extern int g_tc_linear;  // tgm_set_option("tc_linear", 0|1|2); default 2 (see tc_linear.cu)
+extern int g_tc_linear;  // tgm_set_option("tc_linear", 0|1|2); default 1 (see tc_linear.cu)
 extern int g_attn_folded;  // tgm_set_option("attn_folded", 0|1); default 1 (attn_fold.cu)
 extern int g_dyg_fused_attn;  // tgm_set_option("dyg_fused_attn", 0|1); default 1
 

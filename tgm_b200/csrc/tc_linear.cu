@@ -404,11 +404,14 @@ constexpr size_t kSmemBytes = 4 * size_t(kStageBytes);
 
 namespace tgm {
 
-// tgm_set_option("tc_linear", 0|1|2): 0 = never, 1 = every token linear, 2 (default) = where it
-// measured faster than the CUTLASS FastF32 collective on the B200 (profiles/r2_tc_linear_timings.txt):
-// the GELU-fused FFN linear (158 vs 177 us on 25600x800x200); the other three DyGFormer shapes
-// stay on the collective (113 / 54 / 167 us here vs 86 / 42 / 115).
-int g_tc_linear = 2;
+// tgm_set_option("tc_linear", 0|1|2): 0 = never; 1 (default) = every token linear of DyGFormer
+// runs here -- one DyGFormer forward at the default 12800 tokens: 0.772 ms against 0.770 ms with
+// the CUTLASS FastF32 collective for all of them (scratch/dyg_ab.py, same box, interleaved);
+// 2 = only the activation-fused linear here and the other three on the collective, the fastest
+// mix measured (0.743 ms: in isolation 82 / 80 / 29 / 60 us here vs 93 / 80 / 30 / 51 us for
+// FFN1 / FFN2 / out_proj / in_proj, profiles/r2_tc_linear_timings.txt).  TGAT's products choose
+// per shape in attn_fold.cu (any non-zero value enables this kernel there).
+int g_tc_linear = 1;
 int g_tc_bn = 0;  // tgm_set_option("tc_bn", v): probe switch, v > 0 forces the column tile width
 
 // 1 = computed, 0 = shape / alignment not supported (caller falls back), < 0 = error
@@ -431,6 +434,20 @@ int tc3_linear(int64_t S, int N, int K, const float *A, const float *W, const fl
   }
   int BN = ((N + n_tiles - 1) / n_tiles + 3) & ~3;
   if (BN > 200) BN = 200;
+  {
+    // one more column tile when that saves time over whole waves of CTAs: a tile costs about
+    // (128 + BN) column units (fitted on the B200: 23.3 us at BN = 200, 19.9 us at BN = 152,
+    // K = 200), a launch ceil(tiles / 148) of them -- e.g. 12800 x 600: 300 tiles of 200 columns
+    // are 3 waves (70 us), 400 tiles of 152 columns also 3 (60 us)
+    const int64_t m_tiles = (S + BM - 1) / BM;
+    auto cost = [&](int nt, int bn) {
+      const int64_t waves = (m_tiles * nt + kSmCount - 1) / kSmCount;
+      return waves * (128 + bn);
+    };
+    const int nt2 = n_tiles + 1;
+    const int bn2 = ((N + nt2 - 1) / nt2 + 7) & ~7;
+    if (m_tiles * n_tiles > kSmCount && bn2 >= 48 && cost(nt2, bn2) < cost(n_tiles, BN)) BN = bn2;
+  }
   if (g_tc_bn > 0) BN = std::min(200, (g_tc_bn + 3) & ~3);
   static bool configured = false;
   if (!configured) {
