@@ -226,10 +226,28 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
     def _window_feasible(self, store) -> bool:
         """Default (auto) mode only: the adjacency of the whole store (entries, anchors, colocated
         feature rows, sort workspace) must fit in a quarter of the free HBM."""
+        known = getattr(self, '_feasible_store', None)
+        if known is not None and known[0] is store:  # asked once per store, not once per epoch
+            return known[1]
         E, D = store.num_edges, self._edge_x_dim
         need = 2 * E * (16 + 8 + 16 + 4 * D)
+        ok = need <= self._free_bytes() // 4
+        self._feasible_store = (store, ok)
+        return ok
+
+    def _free_bytes(self) -> int:
+        """Free HBM as this process sees it: what the driver reports plus what torch's allocator
+        holds without using.  cudaMemGetInfo costs milliseconds (tens, now and then), so the figure
+        is kept for 30 s: an epoch of a small graph is shorter than one such call."""
+        import time
+        now = time.monotonic()
+        cached = getattr(self, '_free_bytes_cache', None)
+        if cached is not None and now - cached[0] < 30.0:
+            return cached[1]
         free, _ = torch.cuda.mem_get_info(self._device)
-        return need <= free // 4
+        free += torch.cuda.memory_reserved(self._device) - torch.cuda.memory_allocated(self._device)
+        self._free_bytes_cache = (now, int(free))
+        return int(free)
 
     def _windowed_call(self, dg, batch):
         """Returns the decorated batch, or None when this call cannot be served from a window (the
@@ -442,8 +460,7 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
                 per_edge += rows * k * (16 if self._lazy_edge_x else 12 + 4 * self._edge_x_dim)
                 rows *= k
             if 'budget' not in w:
-                free, _ = torch.cuda.mem_get_info(dev)
-                w['budget'] = min(free // 4, 16 << 30)
+                w['budget'] = min(self._free_bytes() // 4, 16 << 30)
             while j_hi > j + 1 and (bounds[j_hi] - lo) * per_edge > w['budget']:
                 j_hi = j + max(1, (j_hi - j) // 2)
             e_lo, e_hi = lo, bounds[j_hi]
@@ -503,8 +520,7 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
         for k in self._num_nbrs:
             per_batch += seeds * k * row
             seeds *= k
-        free, _ = torch.cuda.mem_get_info(self._device)
-        budget = min(free // 4, 16 << 30)
+        budget = min(self._free_bytes() // 4, 16 << 30)
         return max(1, int(budget // max(per_batch, 1)))
 
     def _arange(self, a: int, b: int) -> Tensor:
