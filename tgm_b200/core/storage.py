@@ -23,6 +23,17 @@ from tgm_b200 import _cabi
 from tgm_b200.constants import PADDED_NODE_ID
 
 
+def block_views(v: Tensor, n: int):
+    """Views of the consecutive n-row blocks of `v` (`Tensor.split(n)` semantics: the last one may
+    be shorter).  When the rows divide evenly the views come from one unflatten + unbind, which
+    costs ~12 % less per view than split -- and view creation is most of the per-batch cost of the
+    loader and the windowed hooks (ten views per batch at ~0.9 us each)."""
+    rows = v.shape[0]
+    if type(v) is Tensor and n > 0 and rows >= n and rows % n == 0:
+        return v.unflatten(0, (rows // n, n)).unbind(0)
+    return v.split(n)
+
+
 @dataclass(slots=True)
 class DGSliceTracker:
     """Time / event-index window of a view (base.py:10-17).  Times are inclusive on both ends;
@@ -258,7 +269,7 @@ class DeviceCOOStorage(DGStorageBase):
                 del self._node_cache[k]
             a = origin + c * self._CHUNK_BATCHES * batch_size
             b = min(a + self._CHUNK_BATCHES * batch_size, self._E)
-            chunk = tuple(None if v is None else v[a:b].split(batch_size)
+            chunk = tuple(None if v is None else block_views(v[a:b], batch_size)
                           for v in (self._src, self._dst, self._t, self._x))
             self._node_cache[key] = chunk
         return chunk

@@ -25,6 +25,7 @@ import torch
 from torch import Tensor
 
 from tgm_b200 import _cabi
+from tgm_b200.core.storage import block_views
 from tgm_b200.hooks.base import StatelessHook
 from tgm_b200.hooks.hook_manager import register_hook_class
 
@@ -115,7 +116,7 @@ class RandomNegativeEdgeSamplerHook(StatelessHook):
             batches = -(-total // n)
             gen.set_offset(offset + 4 * batches)
             times = store._t[lo:e_hi].clone()  # `neg_time` is a copy upstream (sampler.py:63)
-            nv, tv = nodes.split(n), times.split(n)
+            nv, tv = block_views(nodes, n), block_views(times, n)
             w = self._win = {
                 'store': store, 'device': dev, 'bs': n, 'next': lo, 'e_lo': lo, 'e_hi': e_hi,
                 'offset': offset, 'offset_after': offset + 4 * batches, 'batches': batches,

@@ -22,6 +22,7 @@ from torch import Tensor
 
 from tgm_b200 import _cabi
 from tgm_b200.constants import PADDED_NODE_ID
+from tgm_b200.core.storage import block_views
 from tgm_b200.hooks.base import SeedableHook, StatefulHook
 from tgm_b200.hooks.hook_manager import register_hook_class
 
@@ -323,7 +324,7 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
             for hop in w['hops']:
                 for i, v in enumerate((hop.seed_nids, hop.seed_times, hop.nbr_nids,
                                        hop.nbr_edge_time, hop.nbr_edge_x)):
-                    split[i].append(v.split(rows))
+                    split[i].append(block_views(v, rows) if type(v) is Tensor else v.split(rows))
                 rows *= hop.nbr_nids.shape[1]
             w['split'] = split
             w['mask'] = None
@@ -493,7 +494,7 @@ class RecencyNeighborHook(StatefulHook, SeedableHook):
                     else:
                         nid, nt, nx = csr.sample(seeds, times, cut, k, B, cut_group=group)
                     for i, v in enumerate((seeds, times, nid, nt, nx)):
-                        split[i].append(v.split(rows))
+                        split[i].append(v.split(rows))  # uneven time windows: a list of sizes
                     seeds, times = nid.reshape(-1), nt.reshape(-1)
                     group *= k
                     rows = [r * k for r in rows]
