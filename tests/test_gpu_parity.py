@@ -425,7 +425,8 @@ def test_frontier_compact_calls_on_two_streams_do_not_interfere():
         assert torch.equal(idx[i][:want.numel()], want)
 
 
-@pytest.mark.parametrize('S,k,D', [(1, 1, 1), (257, 20, 16), (100, 7, 5), (64, 20, 172)])
+@pytest.mark.parametrize('S,k,D', [(1, 1, 1), (257, 20, 16), (100, 7, 5), (64, 20, 172), (33, 20, 100),
+                                   (50, 3, 8), (10, 40, 16), (7, 11, 172), (300_000, 20, 16)])
 def test_masked_mean_bit_exact(S, k, D):
     rng = np.random.default_rng(S)
     z = rng.standard_normal((S, k, D)).astype(np.float32)
