@@ -249,6 +249,48 @@ def row_twohop():
          note='includes the torch-side seed layout of the window; hop-1 features 4 GB per window')
 
 
+# ---- R1 stateless hop 0: the forms without the feature block, device-resident ---------------------
+def row_forms():
+    """tgm_csr_sample_edges_ids / _mean on a stream with the headline workload's statistics at a
+    tenth of its size (E=1e7, N=1e5: the same 100 entries per node, D=16, k=B=20), windows of 5000
+    batches from the steady state, outputs preallocated; a different window every call (>> L2)."""
+    E, N, D, k, bs, W = 10_000_000, 100_000, 16, 20, 200, 5000
+    g = torch.Generator(device=DEV).manual_seed(0)
+    src = torch.randint(0, N, (E,), generator=g, device=DEV, dtype=torch.int32)
+    dst = torch.randint(0, N, (E,), generator=g, device=DEV, dtype=torch.int32)
+    t = torch.sort(torch.randint(0, 2000, (E,), generator=g, device=DEV))[0]
+    x = torch.randn(E, D, generator=g, device=DEV)
+    from tgm_b200.core.storage import DeviceCOOStorage
+    st = DeviceCOOStorage.from_device_tensors(src, dst, t, x, N)
+    csr = RecencyCSR(st, bs, colocate_x=True)
+    me = W * bs
+    wins = [(lo, lo + me) for lo in range(3_000_000, E - me + 1, me)]
+    S = 2 * me
+    state = {'i': 0}
+
+    def window():
+        state['i'] += 1
+        return wins[state['i'] % len(wins)]
+    out_ids = (torch.empty((S, k), dtype=torch.int32, device=DEV), torch.empty((S, k), dtype=torch.int64, device=DEV),
+               torch.empty((S, k), dtype=torch.int32, device=DEV))
+    out_mean = (None, None, torch.empty((S, D), dtype=torch.float32, device=DEV))
+    out_full = (out_ids[0], out_ids[1], torch.empty((S, k, D), dtype=torch.float32, device=DEV))
+    ms_full = cuda_ms(lambda: csr.sample_edges(*window(), k, k, out=out_full), iters=6)
+    ms_ids = cuda_ms(lambda: csr.sample_edges_ids(*window(), k, k, out=out_ids), iters=6)
+    ms_mean = cuda_ms(lambda: csr.sample_edges_mean(*window(), k, k, with_ids=False, out=out_mean), iters=6)
+    slots = S * k
+    emit('R1 hop-0 forms, device-resident (E=1e7, N=1e5, D=16, k=B=20, 5000-batch windows)',
+         value=slots / (ms_ids * 1e-3), unit='sampled-edges/s (id form)', ms=ms_ids,
+         roofline=hbm(slots * (16 + 16) + S * 20, ms_ids),
+         full_rows={'ms': ms_full, 'sampled_edges_per_s': slots / (ms_full * 1e-3),
+                    'roofline': hbm(slots * 2 * (12 + 4 * D) + S * 20, ms_full)},
+         fused_mean={'ms': ms_mean, 'sampled_edges_per_s': slots / (ms_mean * 1e-3),
+                     'roofline': hbm(slots * (12 + 4 * D) + S * (4 * D + 20), ms_mean)},
+         note='id form: 16 B entry read + (nid, t, eid) = 16 B written per slot; fused mean: entry '
+              'ids/times + feature rows read (12 + 4D per slot), 4D written per SEED; full rows: the '
+              'headline kernel on this smaller stream')
+
+
 # ---- S5 uniform full-history sampler ---------------------------------------------------------------
 def row_uniform():
     E, N, D, k = 10_000_000, 1_000_000, 16, 20
@@ -557,7 +599,7 @@ def row_dygformer():
                                         'TF32 off: torch default fp32 matmul), same call, same weights'})
 
 
-ROWS = {'tgn_step': row_tgn_step, 'store': row_store, 'ring': row_ring, 'twohop': row_twohop, 'uniform': row_uniform,
+ROWS = {'tgn_step': row_tgn_step, 'store': row_store, 'ring': row_ring, 'twohop': row_twohop, 'forms': row_forms, 'uniform': row_uniform,
         'stream': row_stream_kernels, 'tgat': row_tgat, 'tgn': row_tgn, 'dygformer': row_dygformer}
 
 
