@@ -239,12 +239,21 @@ softmax_rows_kernel(float *__restrict__ s, int64_t rows, int cols, float scale) 
 // of one feature are ONE 128-bit load and neighbouring threads read neighbouring keys: conflict
 // free), V[T][hd] natural, S[T][T+4].  256 threads: 4 x 4 register micro-tiles of S (one per
 // thread at T = 64), a warp per 8 rows for the softmax, 4 x 4 micro-tiles of O.  fp32 FMA.
-__global__ void __launch_bounds__(256)
+// ALIAS_V (T * hd <= 8192 floats): V does not get its own region -- every thread keeps its (up to
+// eight) V granules in registers from the staging loads and writes them over Qt once the scores
+// are done.  71.8 KB instead of 97.4 KB at T = 64, hd = 100: three CTAs per SM instead of two, so the
+// 400 (sequence, head) CTAs of the default batch are ONE wave of the 148 SMs instead of 1.35.
+constexpr int kVHold = 8;
+template <bool ALIAS_V>
+__global__ void __launch_bounds__(256, ALIAS_V ? 3 : 2)
 dyg_attn_core_kernel(const float *__restrict__ QKV, int T, int E, int H, float scale,
                      float *__restrict__ O) {
   extern __shared__ __align__(16) float sm[];
   const int hd = E / H, TS = T + 4;
-  float *Qt = sm, *Kt = Qt + hd * TS, *V = Kt + hd * TS, *Sc = V + T * hd;
+  float *Qt = sm, *Kt = Qt + hd * TS;
+  float *V = ALIAS_V ? Qt : Kt + hd * TS;
+  float *Sc = ALIAS_V ? Kt + hd * TS : V + T * hd;
+  float4 vhold[kVHold];
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.x / H;
   const int h = blockIdx.x % H;
@@ -254,33 +263,40 @@ dyg_attn_core_kernel(const float *__restrict__ QKV, int T, int E, int H, float s
   {
     const int hd4 = hd >> 2, total = T * hd4;
     constexpr int kBatch = 4;
-    for (int i0 = tid; i0 < total; i0 += kBatch * blockDim.x) {
-      float4 q[kBatch], kk[kBatch], vv[kBatch];
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const int i = i0 + u * blockDim.x;
-        if (i < total) {
-          const int t = i / hd4, d4 = i - t * hd4;
-          const float4 *row = reinterpret_cast<const float4 *>(base + int64_t(t) * 3 * E) + d4;
-          q[u] = __ldg(row);
-          kk[u] = __ldg(row + (E >> 2));
-          vv[u] = __ldg(row + (E >> 1));
+    for (int it = 0; it < (ALIAS_V ? kVHold / kBatch : 1); ++it) {
+      for (int i0 = tid + it * kBatch * 256; i0 < total;
+           i0 += ALIAS_V ? total : kBatch * 256) {  // ALIAS_V: one pass per `it` (total <= 2048)
+        float4 q[kBatch], kk[kBatch], vv[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int i = i0 + u * 256;
+          if (i < total) {
+            const int t = i / hd4, d4 = i - t * hd4;
+            const float4 *row = reinterpret_cast<const float4 *>(base + int64_t(t) * 3 * E) + d4;
+            q[u] = __ldg(row);
+            kk[u] = __ldg(row + (E >> 2));
+            vv[u] = __ldg(row + (E >> 1));
+          }
         }
-      }
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
-        const int i = i0 + u * blockDim.x;
-        if (i < total) {
-          const int t = i / hd4, d = (i - t * hd4) << 2;
-          Qt[(d + 0) * TS + t] = q[u].x * scale;  // the reference scales q before the product
-          Qt[(d + 1) * TS + t] = q[u].y * scale;
-          Qt[(d + 2) * TS + t] = q[u].z * scale;
-          Qt[(d + 3) * TS + t] = q[u].w * scale;
-          Kt[(d + 0) * TS + t] = kk[u].x;
-          Kt[(d + 1) * TS + t] = kk[u].y;
-          Kt[(d + 2) * TS + t] = kk[u].z;
-          Kt[(d + 3) * TS + t] = kk[u].w;
-          *reinterpret_cast<float4 *>(V + t * hd + d) = vv[u];
+        for (int u = 0; u < kBatch; ++u) {
+          const int i = i0 + u * 256;
+          if (i < total) {
+            const int t = i / hd4, d = (i - t * hd4) << 2;
+            Qt[(d + 0) * TS + t] = q[u].x * scale;  // the reference scales q before the product
+            Qt[(d + 1) * TS + t] = q[u].y * scale;
+            Qt[(d + 2) * TS + t] = q[u].z * scale;
+            Qt[(d + 3) * TS + t] = q[u].w * scale;
+            Kt[(d + 0) * TS + t] = kk[u].x;
+            Kt[(d + 1) * TS + t] = kk[u].y;
+            Kt[(d + 2) * TS + t] = kk[u].z;
+            Kt[(d + 3) * TS + t] = kk[u].w;
+            if (ALIAS_V)
+              vhold[it * kBatch + u] = vv[u];
+            else
+              *reinterpret_cast<float4 *>(V + t * hd + d) = vv[u];
+          }
         }
       }
     }
@@ -305,6 +321,17 @@ dyg_attn_core_kernel(const float *__restrict__ QKV, int T, int E, int H, float s
       *reinterpret_cast<float4 *>(Sc + (q0 + i) * TS + k0) = make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
   }
   __syncthreads();
+  if (ALIAS_V) {  // every thread is past its reads of Qt: V takes the region
+    const int hd4 = hd >> 2, total = T * hd4;
+#pragma unroll
+    for (int j = 0; j < kVHold; ++j) {
+      const int i = tid + j * 256;
+      if (i < total) {
+        const int t = i / hd4, d = (i - t * hd4) << 2;
+        *reinterpret_cast<float4 *>(V + t * hd + d) = vhold[j];
+      }
+    }
+  }
   {  // softmax over the keys of every query row: one warp per row
     const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     for (int r = warp; r < T; r += nw) {
@@ -808,13 +835,22 @@ extern "C" int tgm_dyg_forward(tgm_dyg *m, const float *node_x, int64_t num_node
     if (int rc = linear(m->blas, tokens, 3 * E, E, m->Xn, ly.in_w, ly.in_b, nullptr, 0, m->QKV,
                         nullptr, st))
       return rc;
-    const size_t attn_smem = (size_t(2) * hd * (T + 4) + size_t(T) * hd + size_t(T) * (T + 4)) * 4;
+    const bool alias_v = int64_t(T) * hd <= int64_t(kVHold) * 256 * 4;
+    const size_t attn_smem =
+        (size_t(2) * hd * (T + 4) + (alias_v ? 0 : size_t(T) * hd) + size_t(T) * (T + 4)) * 4;
     if (g_dyg_fused_attn && T % 4 == 0 && hd % 4 == 0 && E % 4 == 0 && attn_smem <= 200 * 1024) {
       // QK^T, softmax and PV of every (sequence, head) in one kernel, scores on chip
-      if (attn_smem > 48 * 1024)
-        TGM_CUDA(cudaFuncSetAttribute(dyg_attn_core_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_smem)));
-      dyg_attn_core_kernel<<<int(B * H), 256, attn_smem, st>>>(m->QKV, T, E, H, scale, m->O);
+      if (alias_v) {
+        if (attn_smem > 48 * 1024)
+          TGM_CUDA(cudaFuncSetAttribute(dyg_attn_core_kernel<true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_smem)));
+        dyg_attn_core_kernel<true><<<int(B * H), 256, attn_smem, st>>>(m->QKV, T, E, H, scale, m->O);
+      } else {
+        if (attn_smem > 48 * 1024)
+          TGM_CUDA(cudaFuncSetAttribute(dyg_attn_core_kernel<false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_smem)));
+        dyg_attn_core_kernel<false><<<int(B * H), 256, attn_smem, st>>>(m->QKV, T, E, H, scale, m->O);
+      }
       TGM_LAUNCH_CHECK();
     } else {
     for (int h = 0; h < H; ++h)  // S[b,h,q,k] = Q_bh[q,:] . K_bh[k,:]
