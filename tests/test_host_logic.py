@@ -343,3 +343,27 @@ def test_reference_rng_picks_replay_the_reference_draws():
             want = random.sample(cand, k) if c > k else cand
             assert [p for p in row if p >= 0] == [i for _, i in want]
             assert len(row) == k and all(p == -1 for p in row[len(want):])
+
+
+def test_block_views_equal_tensor_split():
+    """`block_views` (core/storage.py) is Tensor.split(n) with cheaper views where the rows divide
+    evenly: the same views (same memory, same shapes) in every case, one view per batch."""
+    from tgm_b200.core.storage import block_views
+    for rows, n, tail in [(12, 4, (2,)), (12, 5, (2,)), (4, 4, ()), (3, 4, (7, 2)), (4096, 200, (3,))]:
+        x = torch.arange(rows * max(1, int(np.prod(tail)))).reshape(rows, *tail)
+        got, want = block_views(x, n), x.split(n)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert g.shape == w.shape and g.data_ptr() == w.data_ptr() and torch.equal(g, w)
+
+
+def test_reference_plugin_needs_the_reference_package():
+    """tgm_b200.reference_plugin imports without the reference installed; `install()` is what
+    needs `tgm` (here absent from sys.path unless the differential tests put it there)."""
+    import importlib
+    import sys
+    mod = importlib.import_module('tgm_b200.reference_plugin')
+    assert mod.BACKEND_NAME == 'B200Storage'
+    if 'tgm' not in sys.modules:
+        with pytest.raises(ImportError):
+            mod.make_backend(None)
