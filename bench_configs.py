@@ -194,6 +194,7 @@ def config4(a, dev):
     """examples/linkproppred/tgn.py:60-124 (train) / :127-190 (eval, without the ranking metric)."""
     from bench_rows import wiki_stream
     from tgm_b200 import DeduplicationHook
+    from tgm_b200.hooks.dedup import compact_frontier
     from tgm_b200.nn import GraphAttentionEmbedding, TGNMemory
     src, dst, t, x, N = wiki_stream()
     t = np.arange(len(t), dtype=np.int64) * 17  # unique times: the TGN-memory parity domain
@@ -230,14 +231,17 @@ def config4(a, dev):
             for batch in DGDataLoader(dg, batch_size=bs, hook_manager=hm):
                 if a.train:
                     opt.zero_grad(set_to_none=True)
+                # the sampled frontier without its padded slots: ONE compaction (tgm_frontier_compact,
+                # one host read for the count) and four gathers, instead of the example's four
+                # boolean-mask selections (each a select + count read-back)
                 nbr = batch.nbr_nids[0].flatten()
-                keep = nbr != -1
-                seeds = torch.cat([batch.edge_src, batch.edge_dst, batch.neg]).repeat_interleave(k)
-                eidx = torch.stack([batch.global_to_local(seeds[keep]),
-                                    batch.global_to_local(nbr[keep])]).long()
+                idx = compact_frontier(nbr)
+                seeds = torch.cat([batch.edge_src, batch.edge_dst, batch.neg])
+                eidx = torch.stack([batch.global_to_local(seeds.index_select(0, idx // k)),
+                                    batch.global_to_local(nbr.index_select(0, idx))]).long()
                 z, lu = mem(batch.unique_nids)
-                z = enc(z, lu, eidx, batch.nbr_edge_time[0].flatten()[keep],
-                        batch.nbr_edge_x[0].flatten(0, -2)[keep])
+                z = enc(z, lu, eidx, batch.nbr_edge_time[0].flatten().index_select(0, idx),
+                        batch.nbr_edge_x[0].flatten(0, -2).index_select(0, idx))
                 i_s, i_d, i_n = (batch.global_to_local(v).long()
                                  for v in (batch.edge_src, batch.edge_dst, batch.neg))
                 pos = decoder(torch.cat([z[i_s], z[i_d]], 1))

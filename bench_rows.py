@@ -512,12 +512,15 @@ def row_tgn_step():
     keep = {}
 
     def step(batch):
+        # non-padded slots of the sampled frontier: one tgm_frontier_compact + gathers (the example's
+        # four boolean-mask selections are four select kernels + four count read-backs)
         nbr = batch.nbr_nids[0].flatten()
-        mask = nbr != -1
-        seeds = torch.cat([batch.edge_src, batch.edge_dst, batch.neg]).repeat_interleave(k)
-        ei = torch.stack([batch.global_to_local(seeds[mask]), batch.global_to_local(nbr[mask])]).long()
-        et = batch.nbr_edge_time[0].flatten()[mask]
-        ex = batch.nbr_edge_x[0].flatten(0, -2)[mask]
+        idx = compact_frontier(nbr)
+        seeds = torch.cat([batch.edge_src, batch.edge_dst, batch.neg])
+        ei = torch.stack([batch.global_to_local(seeds.index_select(0, idx // k)),
+                          batch.global_to_local(nbr.index_select(0, idx))]).long()
+        et = batch.nbr_edge_time[0].flatten().index_select(0, idx)
+        ex = batch.nbr_edge_x[0].flatten(0, -2).index_select(0, idx)
         z, lu = mem(batch.unique_nids)
         emb = enc(z, lu, ei, et, ex)
         mem.update_state(batch.edge_src, batch.edge_dst, batch.edge_time, batch.edge_x)

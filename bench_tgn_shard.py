@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 
 from tgm_b200 import RecencyCSR  # noqa: E402
 from tgm_b200.core.storage import DeviceCOOStorage  # noqa: E402
-from tgm_b200.hooks.dedup import _BatchIdSet  # noqa: E402
+from tgm_b200.hooks.dedup import _BatchIdSet, compact_frontier  # noqa: E402
 from tgm_b200.nn import GraphAttentionEmbedding, TGNMemory  # noqa: E402
 from tgm_b200.parallel import (average_gradients, max_over_ranks, merge_node_memory,  # noqa: E402
                                shard_batches, sum_over_ranks)
@@ -93,13 +93,14 @@ def main():
             nbr = hop.nbr_nids[r0:r1].reshape(-1)
             ids = _BatchIdSet(N, dev)
             uniq = ids.unique([(s, False), (d, False), (nbr, True)])
-            keep = nbr != -1
-            seeds = torch.cat([s, d]).repeat_interleave(k)
-            ei = torch.stack([ids.local(seeds[keep]), ids.local(nbr[keep])]).long()
+            idx = compact_frontier(nbr)  # non-padded slots: one compaction + gathers
+            seeds = torch.cat([s, d])
+            ei = torch.stack([ids.local(seeds.index_select(0, idx // k)),
+                              ids.local(nbr.index_select(0, idx))]).long()
             opt.zero_grad(set_to_none=True)
             zz, lu = mem(uniq)
-            z = enc(zz, lu, ei, hop.nbr_edge_time[r0:r1].reshape(-1)[keep],
-                    hop.nbr_edge_x[r0:r1].reshape(-1, D)[keep])
+            z = enc(zz, lu, ei, hop.nbr_edge_time[r0:r1].reshape(-1).index_select(0, idx),
+                    hop.nbr_edge_x[r0:r1].reshape(-1, D).index_select(0, idx))
             i_s, i_d = ids.local(s).long(), ids.local(d).long()
             pos = decoder(torch.cat([z[i_s], z[i_d]], 1))
             neg = decoder(torch.cat([z[i_s], z[i_d.roll(1)]], 1))
@@ -126,12 +127,13 @@ def main():
             ids = _BatchIdSet(N, dev)
             uniq = ids.unique([(s, False), (d, False), (nbr, True)])
             if a.embedding:
-                keep = nbr != -1
-                seeds = torch.cat([s, d]).repeat_interleave(k)
-                ei = torch.stack([ids.local(seeds[keep]), ids.local(nbr[keep])]).long()
+                idx = compact_frontier(nbr)  # non-padded slots: one compaction + gathers
+                seeds = torch.cat([s, d])
+                ei = torch.stack([ids.local(seeds.index_select(0, idx // k)),
+                                  ids.local(nbr.index_select(0, idx))]).long()
                 zz, lu = mem(uniq)
-                z = enc(zz, lu, ei, hop.nbr_edge_time[r0:r1].reshape(-1)[keep],
-                        hop.nbr_edge_x[r0:r1].reshape(-1, D)[keep])
+                z = enc(zz, lu, ei, hop.nbr_edge_time[r0:r1].reshape(-1).index_select(0, idx),
+                        hop.nbr_edge_x[r0:r1].reshape(-1, D).index_select(0, idx))
             else:
                 mem(torch.cat([s, d]).long())
             mem.update_state(s, d, t[b_lo:b_hi], x[b_lo:b_hi])
